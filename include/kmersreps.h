@@ -1,0 +1,190 @@
+/*
+ * kmersreps.h -- C ABI of libkmersreps_cuda.so: the B200 (sm_100a) implementation of the
+ * protein k-mer similarity hot path of SEEDtk/kmers.reps.
+ *
+ * The reference has no FFI of its own: the boundary it exposes for this path is the public Java
+ * API of org.theseed.sequence.{SequenceKmers,ProteinKmers} and
+ * org.theseed.proteins.kmers.reps.{RepGenome,RepGenomeDb} (un-vendored module
+ * org.theseed:shared:1.0.0, reference pom.xml:80-94).  Each entry point below names the Java
+ * member(s) it replaces and the reference call site (file:line under
+ * src/main/java/org/theseed/proteins/kmers/reps/ unless a longer path is given) that drives it.
+ * INTEGRATION.md shows the Panama-FFM binding a maintainer adds on the Java side.
+ *
+ * Conventions
+ *   - plain C types only; every function returns a kr_status (0 = OK, < 0 = error) unless noted;
+ *     the message of the last error is kr_last_error(ctx) (ctx may be NULL for creation errors).
+ *   - host buffers are caller-owned and only touched during the call; kr_* handles are opaque,
+ *     library-owned, and freed by their _free / _destroy; "_device" variants take device pointers
+ *     of the context's GPU instead of host pointers and do not synchronise the host.
+ *   - there is NO CPU fallback: kr_create fails when no CUDA device is usable (reference
+ *     convention for fatal errors: RuntimeException, App.java:129).
+ *   - a kr_ctx is bound to one GPU and is internally serialised: it may be called from any
+ *     thread (NeighborProcessor.java:143-145 and GtoRepBuildProcessor.java:127 use parallel
+ *     streams).  Multi-GPU jobs use one context per GPU (one process or one thread each) and the
+ *     stripe / shard arguments below; nothing in this ABI communicates between GPUs.
+ *   - sequences are passed as one flat residue buffer plus offsets: sequence i is
+ *     residues[offsets[i] .. offsets[i+1]).  Residues are the characters of the Java String;
+ *     'A'..'Z', '*' and '-' are accepted (5-bit packing must stay injective);
+ *     any other byte fails the call with KR_ERR_ALPHABET and names the byte.
+ */
+#ifndef KMERSREPS_H
+#define KMERSREPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kr_ctx kr_ctx;
+typedef struct kr_seqset kr_seqset; /* a batch of ProteinKmers objects, encoded and resident in HBM */
+typedef struct kr_db kr_db;         /* the representatives of a RepGenomeDb, resident in HBM */
+
+typedef int32_t kr_status;
+#define KR_OK 0
+#define KR_ERR_ARG (-1)      /* bad argument (null pointer, K out of range, index out of range ...) */
+#define KR_ERR_CUDA (-2)     /* a CUDA call failed; message has the CUDA error string */
+#define KR_ERR_NODEVICE (-3) /* no usable CUDA device: there is no CPU fallback */
+#define KR_ERR_ALPHABET (-4) /* a residue outside 'A'..'Z', '*', '-' */
+#define KR_ERR_STATE (-5)    /* handle belongs to another context / K changed / destroyed */
+
+/* SequenceKmers.INFINITY (RepGenomeDbProcessor.java:249, GtoRepGenomeProcessor.java:300) */
+#define KR_INFINITY 9999
+#define KR_NO_REP 0xFFFFFFFFu
+
+/* context flags (policy switches for the semantics SURVEY.md 8c could not verify against a JVM) */
+#define KR_IDENT_IS_INFINITY 1u /* similarity of two equal sequences is KR_INFINITY, not the raw count */
+#define KR_TIE_LAST 2u          /* findClosest keeps the last maximum in iteration order, not the first */
+
+#define KR_MIN_K 3
+#define KR_MAX_K 11 /* 5 bits per residue + 8 bits of block-local sequence id in one 64-bit key */
+
+/* ---- context -------------------------------------------------------------------------------
+ * Replaces: static state of ProteinKmers -- ProteinKmers.setKmerSize(int) / kmerSize()
+ * (RepGenomeDbProcessor.java:77-80,121; RepMatrixProcessor.java:51-54). */
+kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out);
+void kr_destroy(kr_ctx *ctx);
+const char *kr_last_error(const kr_ctx *ctx);
+int kr_kmer_size(const kr_ctx *ctx);
+/* block until every kernel and copy the context issued has finished */
+kr_status kr_synchronize(kr_ctx *ctx);
+
+/* ---- ProteinKmers(String) in batches -------------------------------------------------------
+ * Replaces: new ProteinKmers(String) / new RepGenome(Sequence) (SequenceInfo.java:47,
+ * RepGenomeDbProcessor.java:161, GtoClassProcessor.java:129, ProteinData.java:211): the set of
+ * distinct length-K substrings, stored as a sorted array of packed 64-bit keys per sequence. */
+kr_status kr_encode(kr_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint32_t nseq, kr_seqset **out);
+/* same, residues already on the context's device (offsets stay a host array) */
+kr_status kr_encode_device(kr_ctx *ctx, const uint8_t *d_residues, const uint64_t *offsets, uint32_t nseq, kr_seqset **out);
+void kr_seqset_free(kr_seqset *set);
+uint32_t kr_seqset_count(const kr_seqset *set);
+/* SequenceKmers.size() for every sequence (ScoreCouplingReporter.java:73) */
+kr_status kr_seqset_sizes(const kr_seqset *set, uint32_t *sizes);
+/* SequenceKmers.iterator(): the sorted packed keys of sequence i (TargetProcessor.java:193);
+ * kr_key_decode turns one key back into its K characters */
+kr_status kr_seqset_keys(const kr_seqset *set, uint32_t i, uint64_t *keys, uint32_t cap, uint32_t *n);
+kr_status kr_key_decode(const kr_ctx *ctx, uint64_t key, char *out /* K bytes, not NUL-terminated */);
+/* new set holding sequences idx[0..n) of `set` (used to batch sub-lists of ProteinKmers objects) */
+kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *idx, uint32_t n, kr_seqset **out);
+
+/* ---- SequenceKmers.similarity / distance ---------------------------------------------------
+ * Replaces: a.similarity(b) for a list of pairs (DistanceMatrixProcessor.java:76,
+ * ScoreCouplingReporter.java:66-70, NeighborProcessor.java:168, KmerCollectionGroup.getDistance
+ * via ClassifyProcessor.java:116).  sim[p] is the raw shared-k-mer count, or KR_INFINITY for equal
+ * sequences under KR_IDENT_IS_INFINITY; identical[p] (may be NULL) is 1 for equal sequences under
+ * either policy. */
+kr_status kr_sim_pairs(kr_ctx *ctx, const kr_seqset *A, const uint32_t *ia, const kr_seqset *B, const uint32_t *ib,
+                       uint64_t npairs, int32_t *sim, uint8_t *identical);
+/* SequenceKmers.distance(int sim, a, b): 1 - sim/(|a|+|b|-sim); 1.0 for sim 0; 0.0 for INFINITY
+ * (ScoreCouplingReporter.java:72-73, SsuRepresentation.java:46-47).  Pure host arithmetic. */
+double kr_distance(int32_t sim, uint32_t size_a, uint32_t size_b);
+
+/* ---- all-vs-all matrices -------------------------------------------------------------------
+ * Replaces: the double loops of DistanceMatrixProcessor.java:71-76 and RepMatrixProcessor.java:88-93
+ * (+ SequenceInfo.java:62-76).  Rows are sequences of A, columns sequences of B (B == NULL: A
+ * against itself). */
+#define KR_ELEM_I32 0u
+#define KR_ELEM_U16 1u /* every similarity fits: counts are < 65536 and KR_INFINITY is 9999 */
+#define KR_LAYOUT_FULL 0u     /* row-major, leading dimension = number of columns */
+#define KR_LAYOUT_TRIANGLE 1u /* self only: cells j > i, packed row after row (N(N-1)/2 cells) */
+#define KR_LAYOUT_BLOCKTRI 2u /* self only: row i holds columns j >= 256*(i/256), row-major per
+                                 256-row stripe with leading dimension N - 256*(i/256) */
+#define KR_TILE 256u          /* rows per stripe unit; row_begin must be a multiple of it */
+
+typedef struct kr_matrix_desc {
+    uint32_t elem;      /* KR_ELEM_* */
+    uint32_t layout;    /* KR_LAYOUT_* */
+    uint32_t row_begin; /* first row computed by this call (multiple of KR_TILE) */
+    uint32_t row_end;   /* one past the last row (multiple of KR_TILE, or the row count) */
+} kr_matrix_desc;
+
+/* number of elements rows [row_begin,row_end) occupy in the given layout (n_rows x n_cols matrix) */
+uint64_t kr_matrix_elems(uint32_t n_rows, uint32_t n_cols, uint32_t layout, uint32_t row_begin, uint32_t row_end);
+/* split rows into nshards stripes of (nearly) equal cell count, boundaries multiples of KR_TILE:
+ * row_bounds[0..nshards] */
+kr_status kr_matrix_stripes(uint32_t n_rows, uint32_t n_cols, uint32_t layout, uint32_t nshards, uint32_t *row_bounds);
+/* out receives the cells of rows [row_begin,row_end), starting at out[0] */
+kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, void *out_host);
+kr_status kr_sim_matrix_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, void *out_dev);
+
+/* ---- RepGenomeDb ---------------------------------------------------------------------------
+ * Replaces the representative store of RepGenomeDb: new RepGenomeDb(threshold, protName)
+ * (RepGenomeDbProcessor.java:122), addRep (BaseGenomeProcessor.java:172-176,204),
+ * load (RepGenomeDbProcessor.java:209).  Representatives are numbered 0,1,2... in the order
+ * they are appended.  `rank` gives each one's position in the database's iteration order
+ * (java.util.HashMap order by genome id, emulated by the host layer); ties in findClosest are
+ * broken by it.  Without kr_db_set_ranks the rank is the append order. */
+kr_status kr_db_create(kr_ctx *ctx, kr_db **out);
+void kr_db_free(kr_db *db);
+uint32_t kr_db_size(const kr_db *db);
+kr_status kr_db_append(kr_ctx *ctx, kr_db *db, const uint8_t *residues, const uint64_t *offsets, uint32_t nseq);
+kr_status kr_db_append_set(kr_ctx *ctx, kr_db *db, const kr_seqset *set, const uint32_t *idx, uint32_t n);
+kr_status kr_db_set_ranks(kr_ctx *ctx, kr_db *db, const uint32_t *rank, uint32_t n);
+
+/* RepGenomeDb.findClosest(ProteinKmers|Sequence|RepGenome) for a batch of queries
+ * (RepGenomeDbProcessor.java:237, GtoRepGenomeProcessor.java:271, GtoClassProcessor.java:132,
+ * ProteinData.java:214).  best_sim[q] = max over representatives of similarity(rep, q);
+ * best_first[q] / best_last[q] = the representative with that similarity that comes first / last
+ * in iteration order (KR_NO_REP when best_sim is 0: "nothing close", GtoRepGenomeProcessor.java:277).
+ * Either index array may be NULL. */
+kr_status kr_db_find_closest(kr_ctx *ctx, const kr_db *db, const kr_seqset *queries, int32_t *best_sim,
+                             uint32_t *best_first, uint32_t *best_last);
+kr_status kr_db_find_closest_device(kr_ctx *ctx, const kr_db *db, const kr_seqset *queries, int32_t *d_best_sim,
+                                    uint32_t *d_best_first, uint32_t *d_best_last);
+/* RepGenomeDb.checkSimilarity(ProteinKmers, int sim) for a batch (BaseGenomeProcessor.java:203):
+ * represented[c] = 1 iff some representative has similarity >= threshold */
+kr_status kr_db_any_ge(kr_ctx *ctx, const kr_db *db, const kr_seqset *cands, int32_t threshold, uint8_t *represented);
+/* The greedy build loop: for each candidate in order, RepGenomeDb.checkGenome(candidate)
+ * (RepGenomeDbProcessor.java:160-163; GtoRepBuildProcessor.java:130-137;
+ * BaseGenomeProcessor.java:203-204): it becomes a representative iff no current representative
+ * (including candidates accepted earlier in this call) has similarity >= threshold.
+ * added[c] = 1 for the candidates appended to db, in candidate order.  `batch` candidates are
+ * scored per launch (0 = library default); the result does not depend on it. */
+kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_t threshold, uint32_t batch,
+                          uint8_t *added);
+
+/* ---- instrumentation -----------------------------------------------------------------------
+ * Replaces the rate logging of the reference (RepGenomeDbProcessor.java:172-179,253-261,
+ * DistanceMatrixProcessor.java:84-93). */
+typedef struct kr_stats {
+    uint64_t kernel_launches; /* kernels of this library launched since the last reset */
+    uint64_t pairs;           /* sequence pairs whose similarity was produced */
+    double encode_ms;         /* encode + per-sequence sort/dedupe kernels (device time) */
+    double blocklist_ms;      /* block key-list build kernels */
+    double join_ms;           /* tile join kernels (matrix / argmax) */
+    double other_ms;          /* pair, merge and bookkeeping kernels */
+    uint64_t join_launches;
+    uint64_t h2d_bytes, d2h_bytes;
+} kr_stats;
+kr_status kr_stats_get(kr_ctx *ctx, kr_stats *out); /* synchronises the context's stream */
+kr_status kr_stats_reset(kr_ctx *ctx);
+
+/* pinned host memory for callers that want full-speed copies of large matrices */
+kr_status kr_host_alloc(kr_ctx *ctx, size_t bytes, void **out);
+void kr_host_free(kr_ctx *ctx, void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERSREPS_H */

@@ -1,0 +1,329 @@
+"""ctypes binding of include/kmersreps.h (one Python method per C entry point)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+INFINITY = 9999
+NO_REP = 0xFFFFFFFF
+IDENT_IS_INFINITY = 1
+TIE_LAST = 2
+ELEM_I32, ELEM_U16 = 0, 1
+LAYOUT_FULL, LAYOUT_TRIANGLE, LAYOUT_BLOCKTRI = 0, 1, 2
+TILE = 256
+
+# every symbol include/kmersreps.h declares (tests check that the library exports them all)
+SYMBOLS = [
+    "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_synchronize", "kr_encode", "kr_encode_device",
+    "kr_seqset_free", "kr_seqset_count", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
+    "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
+    "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
+    "kr_db_find_closest", "kr_db_find_closest_device", "kr_db_any_ge", "kr_greedy_build", "kr_stats_get",
+    "kr_stats_reset", "kr_host_alloc", "kr_host_free",
+]
+
+
+class KrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("kmersreps error %d: %s" % (code, msg))
+        self.code = code
+
+
+class MatrixDesc(C.Structure):
+    _fields_ = [("elem", C.c_uint32), ("layout", C.c_uint32), ("row_begin", C.c_uint32), ("row_end", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("pairs", C.c_uint64), ("encode_ms", C.c_double),
+                ("blocklist_ms", C.c_double), ("join_ms", C.c_double), ("other_ms", C.c_double),
+                ("join_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, "libkmersreps_cuda.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libkmersreps_cuda.so; raise (never fall back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise KrError(-3, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % p)
+    lib = C.CDLL(p)
+    vp, u32, i32, u64 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64
+    lib.kr_create.argtypes = [C.c_int, C.c_int, u32, C.POINTER(vp)]
+    lib.kr_destroy.argtypes = [vp]
+    lib.kr_destroy.restype = None
+    lib.kr_last_error.argtypes = [vp]
+    lib.kr_last_error.restype = C.c_char_p
+    lib.kr_kmer_size.argtypes = [vp]
+    lib.kr_synchronize.argtypes = [vp]
+    lib.kr_encode.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
+    lib.kr_encode_device.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
+    lib.kr_seqset_free.argtypes = [vp]
+    lib.kr_seqset_free.restype = None
+    lib.kr_seqset_count.argtypes = [vp]
+    lib.kr_seqset_count.restype = u32
+    lib.kr_seqset_sizes.argtypes = [vp, vp]
+    lib.kr_seqset_keys.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+    lib.kr_key_decode.argtypes = [vp, u64, C.c_char_p]
+    lib.kr_seqset_gather.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
+    lib.kr_sim_pairs.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
+    lib.kr_distance.argtypes = [i32, u32, u32]
+    lib.kr_distance.restype = C.c_double
+    lib.kr_matrix_elems.argtypes = [u32, u32, u32, u32, u32]
+    lib.kr_matrix_elems.restype = u64
+    lib.kr_matrix_stripes.argtypes = [u32, u32, u32, u32, vp]
+    lib.kr_sim_matrix.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), vp]
+    lib.kr_sim_matrix_device.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), vp]
+    lib.kr_db_create.argtypes = [vp, C.POINTER(vp)]
+    lib.kr_db_free.argtypes = [vp]
+    lib.kr_db_free.restype = None
+    lib.kr_db_size.argtypes = [vp]
+    lib.kr_db_size.restype = u32
+    lib.kr_db_append.argtypes = [vp, vp, vp, vp, u32]
+    lib.kr_db_append_set.argtypes = [vp, vp, vp, vp, u32]
+    lib.kr_db_set_ranks.argtypes = [vp, vp, vp, u32]
+    lib.kr_db_find_closest.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.kr_db_find_closest_device.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.kr_db_any_ge.argtypes = [vp, vp, vp, i32, vp]
+    lib.kr_greedy_build.argtypes = [vp, vp, vp, i32, u32, vp]
+    lib.kr_stats_get.argtypes = [vp, C.POINTER(Stats)]
+    lib.kr_stats_reset.argtypes = [vp]
+    lib.kr_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.kr_host_free.argtypes = [vp, vp]
+    lib.kr_host_free.restype = None
+    _LIB = lib
+    return lib
+
+
+def flat(seqs):
+    """list[str|bytes] -> (uint8 residues, uint64 offsets[S+1])"""
+    bs = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    res = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    return res, off
+
+
+def distance(sim, size_a, size_b) -> float:
+    return load_library().kr_distance(int(sim), int(size_a), int(size_b))
+
+
+def matrix_elems(n_rows, n_cols, layout, row_begin=0, row_end=None) -> int:
+    return int(load_library().kr_matrix_elems(n_rows, n_cols, layout, row_begin, n_rows if row_end is None else row_end))
+
+
+def matrix_stripes(n_rows, n_cols, layout, nshards):
+    out = np.zeros(nshards + 1, dtype=np.uint32)
+    rc = load_library().kr_matrix_stripes(n_rows, n_cols, layout, nshards, out.ctypes.data)
+    if rc:
+        raise KrError(rc, "kr_matrix_stripes")
+    return out
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One GPU, one K (the static ProteinKmers.setKmerSize of the reference)."""
+
+    def __init__(self, device=0, K=8, flags=IDENT_IS_INFINITY):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.kr_create(device, K, flags, C.byref(h))
+        if rc:
+            raise KrError(rc, self.lib.kr_last_error(None).decode())
+        self.h = h
+        self.K = K
+        self.flags = flags
+
+    def _ck(self, rc):
+        if rc:
+            raise KrError(rc, self.lib.kr_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._ck(self.lib.kr_synchronize(self.h))
+
+    def encode(self, seqs=None, res=None, off=None) -> "SeqSet":
+        if res is None:
+            res, off = flat(seqs)
+        res = np.ascontiguousarray(res, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        h = C.c_void_p()
+        pad = res if res.size else np.zeros(1, np.uint8)
+        self._ck(self.lib.kr_encode(self.h, pad.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return SeqSet(self, h)
+
+    def encode_device(self, d_res_ptr: int, off) -> "SeqSet":
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        h = C.c_void_p()
+        self._ck(self.lib.kr_encode_device(self.h, d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return SeqSet(self, h)
+
+    def key_decode(self, key: int) -> str:
+        buf = C.create_string_buffer(self.K)
+        self._ck(self.lib.kr_key_decode(self.h, int(key), buf))
+        return buf.raw.decode()
+
+    def sim_pairs(self, A: "SeqSet", ia, B: "SeqSet", ib):
+        ia = np.ascontiguousarray(ia, dtype=np.uint32)
+        ib = np.ascontiguousarray(ib, dtype=np.uint32)
+        n = len(ia)
+        sim = np.zeros(n, dtype=np.int32)
+        ident = np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.kr_sim_pairs(self.h, A.h, ia.ctypes.data, B.h, ib.ctypes.data, n, sim.ctypes.data, ident.ctypes.data))
+        return sim, ident
+
+    def sim_matrix(self, A: "SeqSet", B: "SeqSet" = None, elem=ELEM_I32, layout=LAYOUT_FULL, row_begin=0, row_end=None, out=None):
+        n_rows = A.count
+        n_cols = A.count if B is None else B.count
+        row_end = n_rows if row_end is None else row_end
+        d = MatrixDesc(elem, layout, row_begin, row_end)
+        ne = matrix_elems(n_rows, n_cols, layout, row_begin, row_end)
+        if out is None:
+            out = np.zeros(ne, dtype=np.uint16 if elem == ELEM_U16 else np.int32)
+        self._ck(self.lib.kr_sim_matrix(self.h, A.h, None if B is None else B.h, C.byref(d), out.ctypes.data))
+        if layout == LAYOUT_FULL:
+            return out.reshape(row_end - row_begin, n_cols)
+        return out
+
+    def sim_matrix_device(self, A, B, d_out_ptr: int, elem=ELEM_U16, layout=LAYOUT_FULL, row_begin=0, row_end=None):
+        row_end = A.count if row_end is None else row_end
+        d = MatrixDesc(elem, layout, row_begin, row_end)
+        self._ck(self.lib.kr_sim_matrix_device(self.h, A.h, None if B is None else B.h, C.byref(d), d_out_ptr))
+
+    def db(self) -> "RepDb":
+        h = C.c_void_p()
+        self._ck(self.lib.kr_db_create(self.h, C.byref(h)))
+        return RepDb(self, h)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self.lib.kr_stats_get(self.h, C.byref(s)))
+        return s.asdict()
+
+    def stats_reset(self):
+        self._ck(self.lib.kr_stats_reset(self.h))
+
+
+class SeqSet:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+        self.count = int(ctx.lib.kr_seqset_count(h))
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.kr_seqset_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+    def sizes(self):
+        out = np.zeros(self.count, dtype=np.uint32)
+        self.ctx._ck(self.ctx.lib.kr_seqset_sizes(self.h, out.ctypes.data))
+        return out
+
+    def keys(self, i: int):
+        n = C.c_uint32(0)
+        self.ctx.lib.kr_seqset_keys(self.h, i, None, 0, C.byref(n))
+        out = np.zeros(max(n.value, 1), dtype=np.uint64)
+        self.ctx._ck(self.ctx.lib.kr_seqset_keys(self.h, i, out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value]
+
+    def kmers(self, i: int):
+        """SequenceKmers.iterator(): the distinct k-mers as strings"""
+        return [self.ctx.key_decode(k) for k in self.keys(i)]
+
+    def gather(self, idx) -> "SeqSet":
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        h = C.c_void_p()
+        self.ctx._ck(self.ctx.lib.kr_seqset_gather(self.ctx.h, self.h, idx.ctypes.data, len(idx), C.byref(h)))
+        return SeqSet(self.ctx, h)
+
+
+class RepDb:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.kr_db_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        return int(self.ctx.lib.kr_db_size(self.h))
+
+    def append(self, seqs=None, res=None, off=None):
+        if res is None:
+            res, off = flat(seqs)
+        res = np.ascontiguousarray(res, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        pad = res if res.size else np.zeros(1, np.uint8)
+        self.ctx._ck(self.ctx.lib.kr_db_append(self.ctx.h, self.h, pad.ctypes.data, off.ctypes.data, len(off) - 1))
+
+    def append_set(self, s: SeqSet, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        self.ctx._ck(self.ctx.lib.kr_db_append_set(self.ctx.h, self.h, s.h, idx.ctypes.data, len(idx)))
+
+    def set_ranks(self, rank):
+        rank = np.ascontiguousarray(rank, dtype=np.uint32)
+        self.ctx._ck(self.ctx.lib.kr_db_set_ranks(self.ctx.h, self.h, rank.ctypes.data, len(rank)))
+
+    def find_closest(self, q: SeqSet):
+        sim = np.zeros(q.count, dtype=np.int32)
+        first = np.zeros(q.count, dtype=np.uint32)
+        last = np.zeros(q.count, dtype=np.uint32)
+        self.ctx._ck(self.ctx.lib.kr_db_find_closest(self.ctx.h, self.h, q.h, sim.ctypes.data, first.ctypes.data, last.ctypes.data))
+        return sim, first, last
+
+    def find_closest_device(self, q: SeqSet, d_sim: int, d_first: int = None, d_last: int = None):
+        self.ctx._ck(self.ctx.lib.kr_db_find_closest_device(self.ctx.h, self.h, q.h, d_sim, d_first, d_last))
+
+    def any_ge(self, cands: SeqSet, threshold: int):
+        out = np.zeros(cands.count, dtype=np.uint8)
+        self.ctx._ck(self.ctx.lib.kr_db_any_ge(self.ctx.h, self.h, cands.h, threshold, out.ctypes.data))
+        return out
+
+    def greedy_build(self, cands: SeqSet, threshold: int, batch: int = 0):
+        added = np.zeros(cands.count, dtype=np.uint8)
+        self.ctx._ck(self.ctx.lib.kr_greedy_build(self.ctx.h, self.h, cands.h, threshold, batch, added.ctypes.data))
+        return added

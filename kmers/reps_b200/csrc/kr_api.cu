@@ -1,0 +1,906 @@
+// kr_api.cu -- C ABI of libkmersreps_cuda.so (see include/kmersreps.h) and the host-side
+// orchestration of the kernels in kr_kernels.cuh.  No CPU fallback anywhere: every entry point
+// that produces a similarity launches a kernel on the context's GPU.
+#include "../../../include/kmersreps.h"
+#include "kr_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace kr;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct EvPair { cudaEvent_t a, b; int stage; };
+enum { ST_ENCODE = 0, ST_BLOCKLIST = 1, ST_JOIN = 2, ST_OTHER = 3 };
+
+struct DevMem {   // refcounted device allocation (residue buffers are shared by gathered sets)
+    void *p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+};
+
+struct kr_ctx {
+    int dev = 0, K = 8;
+    u32 flags = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    u8 *d_lut = nullptr;
+    ErrInfo *d_err = nullptr;
+    kr_stats st{};
+    std::vector<EvPair> pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+struct kr_seqset {
+    kr_ctx *ctx = nullptr;
+    u32 n = 0;
+    std::shared_ptr<DevMem> res;   // residues (kept alive for the equal-sequence check)
+    u64 *d_off = nullptr;          // residue offsets (null for gathered sets)
+    u64 *d_koff = nullptr;         // key-list offsets [n+1]
+    u64 *d_keys = nullptr;
+    SeqMeta *d_meta = nullptr;
+    u64 key_cap = 0;
+    std::vector<u32> h_sizes;      // lazily fetched
+    // block lists (built on first use)
+    bool bl_ready = false;
+    u32 nblk = 0;
+    u64 *d_ent = nullptr; u32 *d_choff = nullptr, *d_chcnt = nullptr; u64 *d_blkbase = nullptr;
+    BlockRef *d_refs = nullptr;
+    std::vector<std::shared_ptr<DevMem>> keep;   // parents' residue buffers
+};
+
+struct DbSegment { kr_seqset *set; u32 base; };
+struct kr_db {
+    kr_ctx *ctx = nullptr;
+    std::vector<DbSegment> segs;
+    u32 n = 0;
+    // database-wide arrays, rebuilt when the database changes
+    bool dirty = true;
+    SeqMeta *d_meta = nullptr; BlockRef *d_refs = nullptr; u32 *d_rank = nullptr, *d_order = nullptr;
+    u32 nblk = 0, cap = 0, cap_blk = 0;
+    std::vector<u32> h_rank;   // empty = append order
+};
+
+// ------------------------------------------------------------------------------------------------
+static kr_status fail(kr_ctx *ctx, kr_status code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(ctx, KR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T> static cudaError_t dalloc(kr_ctx *ctx, T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMallocAsync((void **)p, count * sizeof(T), ctx->stream);
+}
+template <typename T> static void dfree(kr_ctx *ctx, T *p) { if (p) cudaFreeAsync((void *)p, ctx->stream); }
+
+static cudaEvent_t get_event(kr_ctx *ctx) {
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct StageTimer {   // device time of a group of launches, resolved lazily in kr_stats_get
+    kr_ctx *ctx; EvPair ev;
+    StageTimer(kr_ctx *c, int stage) : ctx(c) { ev.a = get_event(c); ev.b = get_event(c); ev.stage = stage; cudaEventRecord(ev.a, c->stream); }
+    ~StageTimer() { cudaEventRecord(ev.b, ctx->stream); ctx->pending.push_back(ev); if (ctx->pending.size() > 4096) drain(ctx); }
+    static void drain(kr_ctx *c) {
+        for (auto &e : c->pending) {
+            cudaEventSynchronize(e.b);
+            float ms = 0; cudaEventElapsedTime(&ms, e.a, e.b);
+            double *dst = e.stage == ST_ENCODE ? &c->st.encode_ms : e.stage == ST_BLOCKLIST ? &c->st.blocklist_ms
+                        : e.stage == ST_JOIN ? &c->st.join_ms : &c->st.other_ms;
+            *dst += ms;
+            c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b);
+        }
+        c->pending.clear();
+    }
+};
+#define LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
+
+// residue byte -> code: 'A'..'Z' -> 0..25, '*' -> 26, '-' -> 27
+static void make_code_table(u8 *t) {
+    memset(t, 0xFF, 256);
+    for (int c = 'A'; c <= 'Z'; ++c) t[c] = (u8)(c - 'A');
+    t['*'] = 26; t['-'] = 27;
+}
+
+// Chunk table: the 32^3 three-residue key prefixes, in key order, are cut into NCHUNK contiguous
+// groups of about equal expected mass under the background residue frequencies of seed proteins
+// (counts measured on data/rep50.db).  It only balances work; any monotone table is
+// correct.
+static void make_chunk_lut(u8 *lut) {
+    double w[32];
+    for (int i = 0; i < 32; ++i) w[i] = 40.0;
+    const char *aa = "LEGARIVDKFTPSNQMHYCW";
+    const double cnt[20] = {48827, 42607, 37306, 35185, 33689, 32513, 31252, 30691, 30145, 29359,
+                            25571, 25444, 25220, 19059, 18890, 15768, 13392, 13332, 6459, 4267};
+    for (int i = 0; i < 20; ++i) w[aa[i] - 'A'] = cnt[i];
+    double tot = 0;
+    for (int i = 0; i < 32; ++i) tot += w[i];
+    double total3 = tot * tot * tot, cum = 0;
+    for (int p = 0; p < (1 << LUT_BITS); ++p) {
+        double m = w[p >> 10] * w[(p >> 5) & 31] * w[p & 31];
+        int c = (int)((cum + 0.5 * m) * NCHUNK / total3);
+        lut[p] = (u8)std::min(c, NCHUNK - 1);
+        cum += m;
+    }
+    for (int p = 1; p < (1 << LUT_BITS); ++p) if (lut[p] < lut[p - 1]) lut[p] = lut[p - 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *kr_last_error(const kr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int kr_kmer_size(const kr_ctx *ctx) { return ctx ? ctx->K : 0; }
+
+kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
+    kr_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, KR_ERR_ARG, "kr_create: out is null");
+    *out = nullptr;
+    if (K < KR_MIN_K || K > KR_MAX_K)
+        return fail(nullptr, KR_ERR_ARG, "kr_create: K=%d outside [%d,%d] (5-bit packing + 8-bit sequence id in 64 bits)", K, KR_MIN_K, KR_MAX_K);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, KR_ERR_NODEVICE, "kr_create: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, KR_ERR_ARG, "kr_create: device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, KR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, KR_ERR_NODEVICE, "kr_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if ((size_t)prop.sharedMemPerBlockOptin < JOIN_SMEM_BYTES)
+        return fail(nullptr, KR_ERR_NODEVICE, "kr_create: device offers %zu B shared memory per block, need %zu", (size_t)prop.sharedMemPerBlockOptin, JOIN_SMEM_BYTES);
+    ctx = new kr_ctx();
+    ctx->dev = device; ctx->K = K; ctx->flags = flags; ctx->num_sms = prop.multiProcessorCount;
+#define CUC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(nullptr, KR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); delete ctx; return KR_ERR_CUDA; } } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CUC(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CUC(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    u8 code[256]; make_code_table(code);
+    CUC(cudaMemcpyToSymbol(c_code, code, 256));
+    std::vector<u8> lut(1 << LUT_BITS); make_chunk_lut(lut.data());
+    CUC(cudaMalloc(&ctx->d_lut, lut.size()));
+    CUC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
+    CUC(cudaMalloc(&ctx->d_err, sizeof(ErrInfo)));
+    CUC(cudaMemset(ctx->d_err, 0, sizeof(ErrInfo)));
+    CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JOIN_SMEM_BYTES));
+    CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JOIN_SMEM_BYTES));
+#undef CUC
+    *out = ctx;
+    return KR_OK;
+}
+
+void kr_destroy(kr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    cudaStreamSynchronize(ctx->stream);
+    StageTimer::drain(ctx);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaFree(ctx->d_lut); cudaFree(ctx->d_err);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+kr_status kr_synchronize(kr_ctx *ctx) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KR_OK;
+}
+
+kr_status kr_stats_get(kr_ctx *ctx, kr_stats *out) {
+    if (!ctx || !out) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaStreamSynchronize(ctx->stream));
+    StageTimer::drain(ctx);
+    *out = ctx->st;
+    return KR_OK;
+}
+kr_status kr_stats_reset(kr_ctx *ctx) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->dev);
+    cudaStreamSynchronize(ctx->stream);
+    StageTimer::drain(ctx);
+    ctx->st = kr_stats{};
+    return KR_OK;
+}
+
+kr_status kr_host_alloc(kr_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return KR_ERR_ARG;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return KR_OK;
+}
+void kr_host_free(kr_ctx *ctx, void *p) { if (ctx) cudaSetDevice(ctx->dev); if (p) cudaFreeHost(p); }
+
+double kr_distance(int32_t sim, uint32_t size_a, uint32_t size_b) {
+    if (sim == KR_INFINITY) return 0.0;
+    if (sim == 0) return 1.0;
+    return 1.0 - (sim / (double)((int64_t)size_a + (int64_t)size_b - sim));
+}
+
+kr_status kr_key_decode(const kr_ctx *ctx, uint64_t key, char *out) {
+    if (!ctx || !out) return KR_ERR_ARG;
+    for (int i = ctx->K - 1; i >= 0; --i) {
+        int c = (int)(key & 31); key >>= 5;
+        out[i] = c < 26 ? (char)('A' + c) : c == 26 ? '*' : c == 27 ? '-' : '?';
+    }
+    return KR_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+static void seqset_destroy(kr_seqset *s) {
+    if (!s) return;
+    kr_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->dev);
+    dfree(ctx, s->d_off); dfree(ctx, s->d_koff); dfree(ctx, s->d_keys); dfree(ctx, s->d_meta);
+    dfree(ctx, s->d_ent); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
+    if (s->res || !s->keep.empty()) cudaStreamSynchronize(ctx->stream);   // residue buffers use cudaFree
+    delete s;
+}
+
+static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, const u64 *offsets, u32 nseq, kr_seqset **out) {
+    if (!ctx || !out || (!offsets && nseq)) return fail(ctx, KR_ERR_ARG, "kr_encode: null argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    const int K = ctx->K;
+    u64 total = nseq ? offsets[nseq] - offsets[0] : 0;
+    if (total && !residues) return fail(ctx, KR_ERR_ARG, "kr_encode: null residues");
+    std::vector<u64> off(nseq + 1), koff(nseq + 1);
+    u64 kc = 0; u32 maxn = 0;
+    for (u32 i = 0; i < nseq; ++i) {
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, KR_ERR_ARG, "kr_encode: offsets not monotone at %u", i);
+        u64 L = offsets[i + 1] - offsets[i];
+        if (L > 65535u + (u64)K - 1) return fail(ctx, KR_ERR_ARG, "kr_encode: sequence %u has %llu residues; at most %u are supported", i, (unsigned long long)L, 65535u + K - 1);
+        off[i] = offsets[i] - offsets[0]; koff[i] = kc;
+        u32 n = L >= (u64)K ? (u32)(L - K + 1) : 0;
+        kc += n; maxn = std::max(maxn, n);
+    }
+    off[nseq] = total; koff[nseq] = kc;
+    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
+    s->ctx = ctx; s->n = nseq; s->key_cap = kc;
+    s->res = std::make_shared<DevMem>();
+    CU(cudaMalloc(&s->res->p, total + 16));
+    if (on_device) CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyDeviceToDevice, ctx->stream));
+    else { CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream)); ctx->st.h2d_bytes += total; }
+    CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_koff, nseq + 1));
+    CU(dalloc(ctx, &s->d_keys, kc + 16)); CU(dalloc(ctx, &s->d_meta, nseq));
+    CU(cudaMemcpyAsync(s->d_off, off.data(), (nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s->d_koff, koff.data(), (nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.h2d_bytes += 2ull * (nseq + 1) * 8;
+    if (nseq) {
+        StageTimer t(ctx, ST_ENCODE);
+        EncodeParams p;
+        p.res = (const u8 *)s->res->p; p.off = s->d_off; p.koff = s->d_koff; p.keys = s->d_keys; p.meta = s->d_meta;
+        p.err = ctx->d_err; p.nseq = nseq; p.K = K; p.smem_cap = 2048;
+        // proteins are a few hundred residues: one 128-thread CTA sorts up to 2048 keys in 16 KB of shared
+        // memory; longer sequences (rare) sort in place in global memory inside the same kernel
+        k_encode_sort<128><<<nseq, 128, p.smem_cap * 8, ctx->stream>>>(p);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+    }
+    ErrInfo ei;
+    CU(cudaMemcpyAsync(&ei, ctx->d_err, sizeof ei, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ei.flag) {
+        cudaMemsetAsync(ctx->d_err, 0, sizeof(ErrInfo), ctx->stream);
+        return fail(ctx, KR_ERR_ALPHABET, "kr_encode: sequence %u position %u: residue 0x%02x ('%c') is outside 'A'..'Z', '*', '-'",
+                    ei.seq, ei.pos, ei.byte, (ei.byte >= 32 && ei.byte < 127) ? (char)ei.byte : '?');
+    }
+    *out = s.release();
+    return KR_OK;
+}
+
+// block lists of a set (K2), built on first use
+static kr_status ensure_blocklists(kr_ctx *ctx, kr_seqset *s) {
+    if (s->bl_ready) return KR_OK;
+    u32 nblk = (s->n + TB - 1) / TB;
+    s->nblk = nblk;
+    u64 cap = s->key_cap + (u64)nblk * NCHUNK * CHUNK_ALIGN + 64;
+    CU(dalloc(ctx, &s->d_ent, cap)); CU(dalloc(ctx, &s->d_choff, (size_t)nblk * (NCHUNK + 1)));
+    CU(dalloc(ctx, &s->d_chcnt, (size_t)nblk * NCHUNK)); CU(dalloc(ctx, &s->d_blkbase, nblk + 1)); CU(dalloc(ctx, &s->d_refs, nblk));
+    if (nblk) {
+        StageTimer t(ctx, ST_BLOCKLIST);
+        int shift = 5 * ctx->K - LUT_BITS;
+        k_bl_count<<<nblk, 256, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt);
+        k_bl_offsets<<<1, 1024, 0, ctx->stream>>>(s->d_chcnt, nblk, s->d_choff, s->d_blkbase);
+        k_bl_scatter<<<nblk, 256, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt, s->d_choff,
+                                                    s->d_blkbase, s->d_ent, s->d_refs);
+        k_bl_sort<<<nblk * NCHUNK, 256, 0, ctx->stream>>>(s->d_refs);
+        ctx->st.kernel_launches += 4;
+        CU(cudaGetLastError());
+    }
+    s->bl_ready = true;
+    return KR_OK;
+}
+
+static kr_status fetch_sizes(kr_ctx *ctx, kr_seqset *s) {
+    if (s->h_sizes.size() == s->n) return KR_OK;
+    std::vector<SeqMeta> m(s->n);
+    CU(cudaMemcpyAsync(m.data(), s->d_meta, (size_t)s->n * sizeof(SeqMeta), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->st.d2h_bytes += (u64)s->n * sizeof(SeqMeta);
+    s->h_sizes.resize(s->n);
+    for (u32 i = 0; i < s->n; ++i) s->h_sizes[i] = m[i].size;
+    return KR_OK;
+}
+
+static kr_status gather_impl(kr_ctx *ctx, const kr_seqset *src_c, const u32 *idx, u32 n, kr_seqset **out) {
+    kr_seqset *src = const_cast<kr_seqset *>(src_c);
+    kr_status st = fetch_sizes(ctx, src);
+    if (st) return st;
+    std::vector<u64> koff(n + 1);
+    u64 kc = 0;
+    for (u32 i = 0; i < n; ++i) {
+        if (idx[i] >= src->n) return fail(ctx, KR_ERR_ARG, "gather: index %u out of range (%u)", idx[i], src->n);
+        koff[i] = kc; kc += src->h_sizes[idx[i]];
+    }
+    koff[n] = kc;
+    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
+    s->ctx = ctx; s->n = n; s->key_cap = kc;
+    if (src->res) s->keep.push_back(src->res);
+    for (auto &k : src->keep) s->keep.push_back(k);
+    u32 *d_idx = nullptr;
+    CU(dalloc(ctx, &d_idx, n)); CU(dalloc(ctx, &s->d_koff, n + 1)); CU(dalloc(ctx, &s->d_keys, kc + 16)); CU(dalloc(ctx, &s->d_meta, n));
+    CU(cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s->d_koff, koff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        StageTimer t(ctx, ST_OTHER);
+        k_gather_keys<<<n, 128, 0, ctx->stream>>>(src->d_keys, src->d_koff, src->d_meta, d_idx, n, s->d_koff, s->d_keys, s->d_meta);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+    }
+    dfree(ctx, d_idx);   // stream-ordered; idx / koff were staged before their copy calls returned
+    s->h_sizes.resize(n);
+    for (u32 i = 0; i < n; ++i) s->h_sizes[i] = src->h_sizes[idx[i]];
+    *out = s.release();
+    return KR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static u64 host_cell_index(u32 layout, u64 i, u64 j, u64 nrows, u64 ncols) {
+    if (layout == KR_LAYOUT_FULL) return i * ncols + j;
+    if (layout == KR_LAYOUT_TRIANGLE) return i * nrows - i * (i + 1) / 2 + (j - i - 1);
+    u64 I = i >> 8, c0 = I << 8;
+    return 256ull * (I * nrows - 128ull * I * (I - 1)) + (i - c0) * (nrows - c0) + (j - c0);
+}
+// element index of the first cell of row r (== number of cells in rows < r)
+static u64 row_start(u32 layout, u64 r, u64 nrows, u64 ncols) {
+    if (layout == KR_LAYOUT_FULL) return r * ncols;
+    if (layout == KR_LAYOUT_TRIANGLE) return r * nrows - r * (r + 1) / 2;
+    u64 I = r >> 8, c0 = I << 8;
+    return 256ull * (I * nrows - 128ull * I * (I - 1)) + (r - c0) * (nrows - c0);
+}
+
+static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool self, const kr_matrix_desc *d, void *out_dev) {
+    kr_status st;
+    if ((st = ensure_blocklists(ctx, A))) return st;
+    if (!self && (st = ensure_blocklists(ctx, B))) return st;
+    kr_seqset *Bs = self ? A : B;
+    u32 rb0 = d->row_begin / TB, rb1 = (d->row_end + TB - 1) / TB;
+    std::vector<uint2> tasks;
+    for (u32 I = rb0; I < rb1; ++I)
+        for (u32 J = (d->layout == KR_LAYOUT_FULL ? 0 : I); J < Bs->nblk; ++J) tasks.push_back(make_uint2(I, J));
+    if (tasks.empty()) return KR_OK;
+    uint2 *d_tasks = nullptr;
+    CU(dalloc(ctx, &d_tasks, tasks.size()));
+    CU(cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    JoinParams p{};
+    p.A = A->d_refs; p.B = Bs->d_refs; p.metaA = A->d_meta; p.metaB = Bs->d_meta;
+    p.nA = A->n; p.nB = Bs->n; p.nBblk = Bs->nblk;
+    p.tasks = d_tasks; p.ntasks = (u32)tasks.size(); p.flags = ctx->flags;
+    p.out = out_dev; p.elem = d->elem; p.layout = d->layout;
+    p.origin = row_start(d->layout, d->row_begin, A->n, Bs->n);
+    {
+        StageTimer t(ctx, ST_JOIN);
+        u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
+        k_join<MODE_MATRIX><<<grid, JOIN_THREADS, JOIN_SMEM_BYTES, ctx->stream>>>(p);
+        LAUNCHED(ctx); ctx->st.join_launches++;
+        CU(cudaGetLastError());
+    }
+    dfree(ctx, d_tasks);   // stream-ordered; the pageable task list was staged before the copy call returned
+    u64 rows = d->row_end - d->row_begin;
+    if (d->layout == KR_LAYOUT_FULL) ctx->st.pairs += rows * (u64)Bs->n;
+    else ctx->st.pairs += kr_matrix_elems(A->n, A->n, KR_LAYOUT_TRIANGLE, d->row_begin, d->row_end);
+    return KR_OK;
+}
+
+static kr_status check_desc(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *d) {
+    if (!A || !d) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix: null argument");
+    if (A->ctx != ctx || (B && B->ctx != ctx)) return fail(ctx, KR_ERR_STATE, "kr_sim_matrix: set belongs to another context");
+    if (d->elem > KR_ELEM_U16 || d->layout > KR_LAYOUT_BLOCKTRI) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix: bad elem/layout");
+    if (d->layout != KR_LAYOUT_FULL && B && B != A) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix: triangle layouts need B == NULL");
+    if (d->row_begin % TB || d->row_begin > d->row_end || d->row_end > A->n || (d->row_end % TB && d->row_end != A->n))
+        return fail(ctx, KR_ERR_ARG, "kr_sim_matrix: rows [%u,%u) must be multiples of %d inside [0,%u]", d->row_begin, d->row_end, TB, A->n);
+    return KR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static void db_free_arrays(kr_db *db) {
+    kr_ctx *ctx = db->ctx;
+    dfree(ctx, db->d_meta); dfree(ctx, db->d_refs); dfree(ctx, db->d_rank); dfree(ctx, db->d_order);
+    db->d_meta = nullptr; db->d_refs = nullptr; db->d_rank = nullptr; db->d_order = nullptr;
+}
+
+// (re)build the database-wide meta / block-ref / rank arrays after a change
+static kr_status db_refresh(kr_ctx *ctx, kr_db *db) {
+    if (!db->dirty) return KR_OK;
+    kr_status st;
+    u32 nblk = 0;
+    for (auto &sg : db->segs) { if ((st = ensure_blocklists(ctx, sg.set))) return st; nblk += sg.set->nblk; }
+    db_free_arrays(db);
+    CU(dalloc(ctx, &db->d_meta, db->n)); CU(dalloc(ctx, &db->d_refs, nblk));
+    CU(dalloc(ctx, &db->d_rank, db->n)); CU(dalloc(ctx, &db->d_order, db->n));
+    u32 bo = 0;
+    for (auto &sg : db->segs) {
+        kr_seqset *s = sg.set;
+        if (!s->n) continue;
+        CU(cudaMemcpyAsync(db->d_meta + sg.base, s->d_meta, (size_t)s->n * sizeof(SeqMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+        k_copy_refs<<<(s->nblk + 127) / 128, 128, 0, ctx->stream>>>(s->d_refs, s->nblk, sg.base, db->d_refs + bo);
+        LAUNCHED(ctx);
+        bo += s->nblk;
+    }
+    db->nblk = nblk;
+    if (db->n) {
+        if (db->h_rank.size() == db->n) {
+            std::vector<u32> order(db->n);
+            for (u32 i = 0; i < db->n; ++i) order[db->h_rank[i]] = i;
+            CU(cudaMemcpyAsync(db->d_rank, db->h_rank.data(), (size_t)db->n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(db->d_order, order.data(), (size_t)db->n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        } else {
+            k_fill_u32_iota<<<(db->n + 255) / 256, 256, 0, ctx->stream>>>(db->d_rank, db->n, 0);
+            k_fill_u32_iota<<<(db->n + 255) / 256, 256, 0, ctx->stream>>>(db->d_order, db->n, 0);
+            ctx->st.kernel_launches += 2;
+        }
+    }
+    CU(cudaGetLastError());
+    db->dirty = false;
+    return KR_OK;
+}
+
+// Segments other than the first are merged once there are too many of them (greedy build appends one
+// small segment per batch); the first is folded in when the tail has grown to half its size.
+static kr_status db_compact(kr_ctx *ctx, kr_db *db) {
+    if (db->segs.size() <= 6) return KR_OK;
+    size_t first = 1;
+    u32 tail = 0;
+    for (size_t i = 1; i < db->segs.size(); ++i) tail += db->segs[i].set->n;
+    if (tail * 2 >= db->segs[0].set->n) first = 0;
+    // concatenate key lists of segments [first, end) into one new set
+    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
+    u32 n = 0; u64 kc = 0;
+    for (size_t i = first; i < db->segs.size(); ++i) { n += db->segs[i].set->n; }
+    s->ctx = ctx; s->n = n;
+    std::vector<u64> koff(n + 1);
+    std::vector<u32> sizes; sizes.reserve(n);
+    kr_status st;
+    for (size_t i = first; i < db->segs.size(); ++i) {
+        kr_seqset *g = db->segs[i].set;
+        if ((st = fetch_sizes(ctx, g))) return st;
+        for (u32 k = 0; k < g->n; ++k) { koff[sizes.size()] = kc; kc += g->h_sizes[k]; sizes.push_back(g->h_sizes[k]); }
+        if (g->res) s->keep.push_back(g->res);
+        for (auto &kp : g->keep) s->keep.push_back(kp);
+    }
+    koff[n] = kc; s->key_cap = kc; s->h_sizes = sizes;
+    CU(dalloc(ctx, &s->d_koff, n + 1)); CU(dalloc(ctx, &s->d_keys, kc + 16)); CU(dalloc(ctx, &s->d_meta, n));
+    CU(cudaMemcpyAsync(s->d_koff, koff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    u32 at = 0;
+    for (size_t i = first; i < db->segs.size(); ++i) {
+        kr_seqset *g = db->segs[i].set;
+        if (!g->n) continue;
+        // gathered / compacted sets have dense key arenas only if built by gather; use the gather kernel for generality
+        u32 *d_idx = nullptr;
+        CU(dalloc(ctx, &d_idx, g->n));
+        k_fill_u32_iota<<<(g->n + 255) / 256, 256, 0, ctx->stream>>>(d_idx, g->n, 0);
+        k_gather_keys<<<g->n, 128, 0, ctx->stream>>>(g->d_keys, g->d_koff, g->d_meta, d_idx, g->n, s->d_koff + at, s->d_keys, s->d_meta + at);
+        ctx->st.kernel_launches += 2;
+        dfree(ctx, d_idx);
+        at += g->n;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    u32 base = db->segs[first].base;
+    for (size_t i = first; i < db->segs.size(); ++i) seqset_destroy(db->segs[i].set);
+    db->segs.resize(first);
+    db->segs.push_back(DbSegment{s.release(), base});
+    db->dirty = true;
+    return KR_OK;
+}
+
+static kr_status db_append_owned(kr_ctx *ctx, kr_db *db, kr_seqset *s) {
+    if (s->n == 0) { seqset_destroy(s); return KR_OK; }
+    db->segs.push_back(DbSegment{s, db->n});
+    db->n += s->n;
+    if (!db->h_rank.empty()) db->h_rank.clear();   // ranks must be supplied again after growth
+    db->dirty = true;
+    return db_compact(ctx, db);
+}
+
+// queries x database: per-query best similarity with first/last rank (device outputs)
+static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *d_sim, u32 *d_first, u32 *d_last) {
+    kr_status st;
+    if ((st = db_refresh(ctx, db))) return st;
+    if ((st = ensure_blocklists(ctx, Q))) return st;
+    if (Q->n == 0) return KR_OK;
+    if (db->n == 0) {
+        CU(cudaMemsetAsync(d_sim, 0, (size_t)Q->n * 4, ctx->stream));
+        if (d_first) CU(cudaMemsetAsync(d_first, 0xFF, (size_t)Q->n * 4, ctx->stream));
+        if (d_last) CU(cudaMemsetAsync(d_last, 0xFF, (size_t)Q->n * 4, ctx->stream));
+        return KR_OK;
+    }
+    u32 nI = Q->nblk;
+    u32 nsplit = std::max<u32>(1, std::min<u32>(db->nblk, (2 * (u32)ctx->num_sms + nI - 1) / nI));
+    std::vector<uint2> tasks;
+    for (u32 I = 0; I < nI; ++I) for (u32 sp = 0; sp < nsplit; ++sp) tasks.push_back(make_uint2(I, sp));
+    uint2 *d_tasks = nullptr; int4 *d_partial = nullptr;
+    CU(dalloc(ctx, &d_tasks, tasks.size())); CU(dalloc(ctx, &d_partial, tasks.size() * TB));
+    CU(cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    JoinParams p{};
+    p.A = Q->d_refs; p.B = db->d_refs; p.metaA = Q->d_meta; p.metaB = db->d_meta;
+    p.nA = Q->n; p.nB = db->n; p.nBblk = db->nblk;
+    p.tasks = d_tasks; p.ntasks = (u32)tasks.size(); p.flags = ctx->flags;
+    p.nsplit = nsplit; p.rankB = db->d_rank; p.partial = d_partial;
+    {
+        StageTimer t(ctx, ST_JOIN);
+        u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
+        k_join<MODE_ARGMAX><<<grid, JOIN_THREADS, JOIN_SMEM_BYTES, ctx->stream>>>(p);
+        LAUNCHED(ctx); ctx->st.join_launches++;
+    }
+    {
+        StageTimer t(ctx, ST_OTHER);
+        k_argmax_merge<<<(Q->n + 255) / 256, 256, 0, ctx->stream>>>(d_partial, Q->n, nsplit, db->d_order, d_sim, d_first, d_last);
+        LAUNCHED(ctx);
+    }
+    CU(cudaGetLastError());
+    dfree(ctx, d_tasks); dfree(ctx, d_partial);
+    ctx->st.pairs += (u64)Q->n * db->n;
+    return KR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+kr_status kr_encode(kr_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint32_t nseq, kr_seqset **out) {
+    return encode_impl(ctx, residues, false, offsets, nseq, out);
+}
+kr_status kr_encode_device(kr_ctx *ctx, const uint8_t *d_residues, const uint64_t *offsets, uint32_t nseq, kr_seqset **out) {
+    return encode_impl(ctx, d_residues, true, offsets, nseq, out);
+}
+void kr_seqset_free(kr_seqset *set) {
+    if (!set) return;
+    std::lock_guard<std::mutex> lk(set->ctx->mu);
+    seqset_destroy(set);
+}
+uint32_t kr_seqset_count(const kr_seqset *set) { return set ? set->n : 0; }
+
+kr_status kr_seqset_sizes(const kr_seqset *set, uint32_t *sizes) {
+    if (!set || !sizes) return KR_ERR_ARG;
+    kr_ctx *ctx = set->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    kr_status st = fetch_sizes(ctx, const_cast<kr_seqset *>(set));
+    if (st) return st;
+    memcpy(sizes, set->h_sizes.data(), (size_t)set->n * 4);
+    return KR_OK;
+}
+
+kr_status kr_seqset_keys(const kr_seqset *set, uint32_t i, uint64_t *keys, uint32_t cap, uint32_t *n) {
+    if (!set || !n) return KR_ERR_ARG;
+    kr_ctx *ctx = set->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    if (i >= set->n) return fail(ctx, KR_ERR_ARG, "kr_seqset_keys: index %u of %u", i, set->n);
+    kr_status st = fetch_sizes(ctx, const_cast<kr_seqset *>(set));
+    if (st) return st;
+    u32 sz = set->h_sizes[i];
+    *n = sz;
+    if (!keys || cap < sz) return sz ? fail(ctx, KR_ERR_ARG, "kr_seqset_keys: need room for %u keys", sz) : KR_OK;
+    u64 ko;
+    CU(cudaMemcpyAsync(&ko, set->d_koff + i, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(keys, set->d_keys + ko, (size_t)sz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KR_OK;
+}
+
+kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *idx, uint32_t n, kr_seqset **out) {
+    if (!ctx || !set || !out || (!idx && n)) return fail(ctx, KR_ERR_ARG, "kr_seqset_gather: null argument");
+    if (set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_seqset_gather: set belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    return gather_impl(ctx, set, idx, n, out);
+}
+
+kr_status kr_sim_pairs(kr_ctx *ctx, const kr_seqset *A, const uint32_t *ia, const kr_seqset *B, const uint32_t *ib,
+                       uint64_t npairs, int32_t *sim, uint8_t *identical) {
+    if (!ctx || !A || !B || !sim || ((!ia || !ib) && npairs)) return fail(ctx, KR_ERR_ARG, "kr_sim_pairs: null argument");
+    if (A->ctx != ctx || B->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_sim_pairs: set belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    if (!npairs) return KR_OK;
+    for (u64 p = 0; p < npairs; ++p)
+        if (ia[p] >= A->n || ib[p] >= B->n) return fail(ctx, KR_ERR_ARG, "kr_sim_pairs: pair %llu index out of range", (unsigned long long)p);
+    u32 *d_ia, *d_ib; int *d_sim; u8 *d_id;
+    CU(dalloc(ctx, &d_ia, npairs)); CU(dalloc(ctx, &d_ib, npairs)); CU(dalloc(ctx, &d_sim, npairs)); CU(dalloc(ctx, &d_id, npairs));
+    CU(cudaMemcpyAsync(d_ia, ia, npairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_ib, ib, npairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageTimer t(ctx, ST_OTHER);
+        u32 grid = (u32)std::min<u64>((npairs + 7) / 8, (u64)ctx->num_sms * 8);
+        k_sim_pairs<<<grid, 256, 0, ctx->stream>>>(A->d_keys, A->d_koff, A->d_meta, d_ia, B->d_keys, B->d_koff, B->d_meta, d_ib, npairs,
+                                                   ctx->flags, d_sim, d_id);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(sim, d_sim, npairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (identical) CU(cudaMemcpyAsync(identical, d_id, npairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d_ia); dfree(ctx, d_ib); dfree(ctx, d_sim); dfree(ctx, d_id);
+    ctx->st.pairs += npairs; ctx->st.h2d_bytes += npairs * 8; ctx->st.d2h_bytes += npairs * 5;
+    return KR_OK;
+}
+
+uint64_t kr_matrix_elems(uint32_t n_rows, uint32_t n_cols, uint32_t layout, uint32_t row_begin, uint32_t row_end) {
+    if (row_end > n_rows) row_end = n_rows;
+    if (row_begin >= row_end) return 0;
+    return row_start(layout, row_end, n_rows, n_cols) - row_start(layout, row_begin, n_rows, n_cols);
+}
+
+kr_status kr_matrix_stripes(uint32_t n_rows, uint32_t n_cols, uint32_t layout, uint32_t nshards, uint32_t *row_bounds) {
+    if (!row_bounds || nshards == 0 || layout > KR_LAYOUT_BLOCKTRI) return KR_ERR_ARG;
+    u64 total = row_start(layout, n_rows, n_rows, n_cols);
+    u32 nblk = (n_rows + TB - 1) / TB;
+    row_bounds[0] = 0;
+    u32 b = 0;
+    for (u32 s = 1; s < nshards; ++s) {
+        u64 want = total / nshards * s;
+        // first block boundary whose cumulative cell count reaches the target, choosing the closer side
+        while (b < nblk && row_start(layout, std::min<u64>((u64)(b + 1) * TB, n_rows), n_rows, n_cols) <= want) ++b;
+        u64 lo = row_start(layout, std::min<u64>((u64)b * TB, n_rows), n_rows, n_cols);
+        u64 hi = row_start(layout, std::min<u64>((u64)(b + 1) * TB, n_rows), n_rows, n_cols);
+        u32 pick = (b < nblk && hi - want < want - lo) ? b + 1 : b;
+        row_bounds[s] = (u32)std::min<u64>((u64)pick * TB, n_rows);
+        if (row_bounds[s] < row_bounds[s - 1]) row_bounds[s] = row_bounds[s - 1];
+    }
+    row_bounds[nshards] = n_rows;
+    return KR_OK;
+}
+
+kr_status kr_sim_matrix_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, void *out_dev) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    kr_status st = check_desc(ctx, A, B, desc);
+    if (st) return st;
+    if (!out_dev) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_device: null output");
+    CU(cudaSetDevice(ctx->dev));
+    bool self = (B == nullptr || B == A);
+    return matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, out_dev);
+}
+
+kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, void *out_host) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    kr_status st = check_desc(ctx, A, B, desc);
+    if (st) return st;
+    if (!out_host) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix: null output");
+    CU(cudaSetDevice(ctx->dev));
+    bool self = (B == nullptr || B == A);
+    u32 ncols = self ? A->n : B->n;
+    u64 elems = kr_matrix_elems(A->n, ncols, desc->layout, desc->row_begin, desc->row_end);
+    size_t esz = desc->elem == KR_ELEM_U16 ? 2 : 4;
+    if (!elems) return KR_OK;
+    u8 *d_out = nullptr;
+    CU(dalloc(ctx, &d_out, elems * esz + 16));
+    st = matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, d_out);
+    if (st == KR_OK) {
+        cudaError_t e = cudaMemcpyAsync(out_host, d_out, elems * esz, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "matrix copy to host failed: %s", cudaGetErrorString(e));
+        ctx->st.d2h_bytes += elems * esz;
+    }
+    dfree(ctx, d_out);
+    return st;
+}
+
+// ---- database ----------------------------------------------------------------------------------
+kr_status kr_db_create(kr_ctx *ctx, kr_db **out) {
+    if (!ctx || !out) return KR_ERR_ARG;
+    kr_db *db = new kr_db(); db->ctx = ctx; *out = db;
+    return KR_OK;
+}
+void kr_db_free(kr_db *db) {
+    if (!db) return;
+    kr_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->dev);
+    for (auto &sg : db->segs) seqset_destroy(sg.set);
+    db_free_arrays(db);
+    delete db;
+}
+uint32_t kr_db_size(const kr_db *db) { return db ? db->n : 0; }
+
+kr_status kr_db_append(kr_ctx *ctx, kr_db *db, const uint8_t *residues, const uint64_t *offsets, uint32_t nseq) {
+    if (!ctx || !db) return KR_ERR_ARG;
+    if (db->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_db_append: database belongs to another context");
+    kr_seqset *s = nullptr;
+    kr_status st = encode_impl(ctx, residues, false, offsets, nseq, &s);
+    if (st) return st;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    return db_append_owned(ctx, db, s);
+}
+
+kr_status kr_db_append_set(kr_ctx *ctx, kr_db *db, const kr_seqset *set, const uint32_t *idx, uint32_t n) {
+    if (!ctx || !db || !set || (!idx && n)) return fail(ctx, KR_ERR_ARG, "kr_db_append_set: null argument");
+    if (db->ctx != ctx || set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_db_append_set: handle belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    kr_seqset *s = nullptr;
+    kr_status st = gather_impl(ctx, set, idx, n, &s);
+    if (st) return st;
+    return db_append_owned(ctx, db, s);
+}
+
+kr_status kr_db_set_ranks(kr_ctx *ctx, kr_db *db, const uint32_t *rank, uint32_t n) {
+    if (!ctx || !db || (!rank && n)) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n != db->n) return fail(ctx, KR_ERR_ARG, "kr_db_set_ranks: %u ranks for %u representatives", n, db->n);
+    std::vector<u8> seen(n, 0);
+    for (u32 i = 0; i < n; ++i) {
+        if (rank[i] >= n || seen[rank[i]]) return fail(ctx, KR_ERR_ARG, "kr_db_set_ranks: not a permutation at %u", i);
+        seen[rank[i]] = 1;
+    }
+    db->h_rank.assign(rank, rank + n);
+    db->dirty = true;
+    return KR_OK;
+}
+
+kr_status kr_db_find_closest_device(kr_ctx *ctx, const kr_db *db, const kr_seqset *queries, int32_t *d_best_sim,
+                                    uint32_t *d_best_first, uint32_t *d_best_last) {
+    if (!ctx || !db || !queries || !d_best_sim) return fail(ctx, KR_ERR_ARG, "kr_db_find_closest: null argument");
+    if (db->ctx != ctx || queries->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_db_find_closest: handle belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    return find_closest_launch(ctx, const_cast<kr_db *>(db), const_cast<kr_seqset *>(queries), d_best_sim, d_best_first, d_best_last);
+}
+
+kr_status kr_db_find_closest(kr_ctx *ctx, const kr_db *db, const kr_seqset *queries, int32_t *best_sim, uint32_t *best_first,
+                             uint32_t *best_last) {
+    if (!ctx || !db || !queries || !best_sim) return fail(ctx, KR_ERR_ARG, "kr_db_find_closest: null argument");
+    if (db->ctx != ctx || queries->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_db_find_closest: handle belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    u32 nq = queries->n;
+    if (!nq) return KR_OK;
+    int *d_sim; u32 *d_first, *d_last;
+    CU(dalloc(ctx, &d_sim, nq)); CU(dalloc(ctx, &d_first, nq)); CU(dalloc(ctx, &d_last, nq));
+    kr_status st = find_closest_launch(ctx, const_cast<kr_db *>(db), const_cast<kr_seqset *>(queries), d_sim, d_first, d_last);
+    if (st == KR_OK) {
+        cudaError_t e = cudaMemcpyAsync(best_sim, d_sim, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && best_first) e = cudaMemcpyAsync(best_first, d_first, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && best_last) e = cudaMemcpyAsync(best_last, d_last, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "find_closest copy to host failed: %s", cudaGetErrorString(e));
+        ctx->st.d2h_bytes += (u64)nq * 12;
+    }
+    dfree(ctx, d_sim); dfree(ctx, d_first); dfree(ctx, d_last);
+    return st;
+}
+
+kr_status kr_db_any_ge(kr_ctx *ctx, const kr_db *db, const kr_seqset *cands, int32_t threshold, uint8_t *represented) {
+    if (!ctx || !db || !cands || !represented) return fail(ctx, KR_ERR_ARG, "kr_db_any_ge: null argument");
+    std::vector<int32_t> sim(cands->n);
+    kr_status st = kr_db_find_closest(ctx, db, cands, sim.data(), nullptr, nullptr);
+    if (st) return st;
+    for (u32 i = 0; i < cands->n; ++i) represented[i] = sim[i] >= threshold;
+    return KR_OK;
+}
+
+kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_t threshold, uint32_t batch, uint8_t *added) {
+    if (!ctx || !db || !cands || !added) return fail(ctx, KR_ERR_ARG, "kr_greedy_build: null argument");
+    if (db->ctx != ctx || cands->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_greedy_build: handle belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    if (batch == 0) batch = 4096;
+    const u32 C = cands->n;
+    kr_status st = KR_OK;
+    std::vector<u32> idx, surv, acc;
+    std::vector<int32_t> best;
+    std::vector<u16> M;
+    for (u32 pos = 0; pos < C && st == KR_OK; pos += batch) {
+        const u32 n = std::min(batch, C - pos);
+        idx.resize(n);
+        for (u32 i = 0; i < n; ++i) idx[i] = pos + i;
+        surv.clear();
+        if (db->n) {
+            // score the batch against the current representatives
+            kr_seqset *bs = nullptr;
+            if ((st = gather_impl(ctx, cands, idx.data(), n, &bs))) break;
+            int *d_sim = nullptr;
+            cudaError_t e = dalloc(ctx, &d_sim, n);
+            if (e != cudaSuccess) { seqset_destroy(bs); st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
+            st = find_closest_launch(ctx, db, bs, d_sim, nullptr, nullptr);
+            best.resize(n);
+            if (st == KR_OK) {
+                e = cudaMemcpyAsync(best.data(), d_sim, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
+                ctx->st.d2h_bytes += (u64)n * 4;
+            }
+            dfree(ctx, d_sim);
+            seqset_destroy(bs);
+            if (st) break;
+            for (u32 i = 0; i < n; ++i) { if (best[i] < threshold) surv.push_back(pos + i); else added[pos + i] = 0; }
+        } else {
+            surv = idx;
+        }
+        if (surv.empty()) continue;
+        // survivors against one another, then the in-order sweep of checkGenome
+        const u32 S = (u32)surv.size();
+        acc.clear();
+        if (S == 1) {
+            acc.push_back(0);
+        } else {
+            kr_seqset *ss = nullptr;
+            if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) break;
+            kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, S};
+            u16 *d_M = nullptr;
+            cudaError_t e = dalloc(ctx, &d_M, (size_t)S * S + 8);
+            if (e != cudaSuccess) { seqset_destroy(ss); st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
+            st = matrix_launch(ctx, ss, nullptr, true, &d, d_M);
+            M.resize((size_t)S * S);
+            if (st == KR_OK) {
+                e = cudaMemcpyAsync(M.data(), d_M, (size_t)S * S * 2, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
+                ctx->st.d2h_bytes += (u64)S * S * 2;
+            }
+            dfree(ctx, d_M);
+            seqset_destroy(ss);
+            if (st) break;
+            for (u32 s = 0; s < S; ++s) {
+                bool rep = false;
+                const u16 *col = M.data();   // M is symmetric: read row s
+                const u16 *row = col + (size_t)s * S;
+                for (u32 t : acc) if ((int)row[t] >= threshold) { rep = true; break; }
+                if (!rep) acc.push_back(s);
+            }
+        }
+        std::vector<u32> acc_idx(acc.size());
+        for (u32 s = 0; s < S; ++s) added[surv[s]] = 0;
+        for (size_t k = 0; k < acc.size(); ++k) { acc_idx[k] = surv[acc[k]]; added[acc_idx[k]] = 1; }
+        kr_seqset *as = nullptr;
+        if ((st = gather_impl(ctx, cands, acc_idx.data(), (u32)acc_idx.size(), &as))) break;
+        st = db_append_owned(ctx, db, as);
+    }
+    return st;
+}
+
+}  // extern "C"

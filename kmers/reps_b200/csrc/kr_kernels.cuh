@@ -1,0 +1,550 @@
+// kr_kernels.cuh -- sm_100a kernels of the protein k-mer similarity path.
+//
+// Data model (replaces the HashSet<String> of ProteinKmers):
+//   residue  -> 5-bit code; k-mer -> 5K-bit key in a uint64 (K <= 11)
+//   sequence -> sorted array of its DISTINCT keys            ("key list",   K1)
+//   block    -> 256 consecutive sequences; all their (key,lid) entries, key<<8|lid, sorted and
+//               cut into NCHUNK key-range chunks by a fixed prefix table ("block list", K2)
+//   tile     -> block I x block J: one merge-style pass over the two block lists, staged chunk by
+//               chunk into shared memory with 1-D TMA bulk copies, counts the shared keys of all
+//               256x256 sequence pairs at once in a shared-memory count tile                (K3)
+// Every similarity is an exact integer; nothing here is floating point.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kr {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+
+constexpr int TB = 256;          // sequences per block (KR_TILE); lid fits LID_BITS
+constexpr int LID_BITS = 8;
+constexpr u64 LID_MASK = 0xFFull;
+constexpr int NCHUNK = 64;       // key-range chunks per block list
+constexpr int CHUNK_ALIGN = 16;  // chunk starts are multiples of 16 entries (128 B)
+constexpr int STAGE_CAP = 2048;  // entries per side per pipeline stage
+constexpr int NSTAGE = 3;
+constexpr int NCWARP = 16;       // consumer warps of the join kernel (+1 producer warp)
+constexpr int JOIN_THREADS = (NCWARP + 1) * 32;
+constexpr u64 SENT = ~0ull;
+constexpr int KR_INF = 9999;
+constexpr int LUT_BITS = 15;     // chunk table is indexed by the first three residues of the key
+
+constexpr size_t JOIN_SMEM_CNT = (size_t)TB * TB * 2;                         // u16 count tile
+constexpr size_t JOIN_SMEM_STAGE = (size_t)NSTAGE * 2 * STAGE_CAP * 8;
+constexpr size_t JOIN_SMEM_BYTES = JOIN_SMEM_CNT + JOIN_SMEM_STAGE + 64;
+
+struct SeqMeta {   // one per sequence
+    u32 size;      // number of distinct k-mers (SequenceKmers.size())
+    u32 len;       // residues
+    u64 hash;      // 64-bit hash of the residues (pre-filter for the equal-sequence rule)
+    const u8 *res; // the residues themselves (exact check for the equal-sequence rule)
+};
+
+struct BlockRef {   // one per block of 256 sequences
+    const u64 *ent; // first entry of the block list
+    const u32 *off; // NCHUNK+1 chunk starts (entries, relative to ent, multiples of CHUNK_ALIGN)
+    const u32 *cnt; // NCHUNK chunk lengths
+    u32 seq0;       // index of the block's first sequence in its set / database
+    u32 nseq;       // sequences in the block (<= 256)
+};
+
+struct ErrInfo { u32 flag, seq, pos, byte; };
+
+__constant__ u8 c_code[256];   // residue byte -> 5-bit code, 0xFF = not in the alphabet
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31; return x;
+}
+
+__device__ __forceinline__ void cmpswap(u64 *d, u32 i, u32 j) {
+    u64 a = d[i], b = d[j];
+    if (b < a) { d[i] = b; d[j] = a; }
+}
+
+// Bitonic sorting network in its "always ascending" form (flip step + disperse steps), so indices
+// >= n behave as +infinity without being stored: any n, no padding.  Whole CTA must call.
+__device__ void bitonic_sort(u64 *d, u32 n, u32 tid, u32 nthr) {
+    if (n < 2) return;
+    u32 lp = 32 - __clz(n - 1);           // P = 1 << lp >= n
+    u32 halfP = 1u << (lp - 1);
+    for (u32 lk = 1; lk <= lp; ++lk) {    // k = 1 << lk
+        u32 lh = lk - 1;                  // half = k/2
+        for (u32 t = tid; t < halfP; t += nthr) {
+            u32 g = t >> lh, r = t & ((1u << lh) - 1);
+            u32 i = (g << lk) + r, j = (g << lk) + ((1u << lk) - 1 - r);
+            if (j < n) cmpswap(d, i, j);
+        }
+        __syncthreads();
+        for (int lj = (int)lh - 1; lj >= 0; --lj) {
+            for (u32 t = tid; t < halfP; t += nthr) {
+                u32 i = ((t >> lj) << (lj + 1)) + (t & ((1u << lj) - 1));
+                u32 j = i + (1u << lj);
+                if (j < n) cmpswap(d, i, j);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: one CTA per sequence: residues -> codes -> keys -> sort -> distinct keys + size + hash.
+struct EncodeParams {
+    const u8 *res; const u64 *off; const u64 *koff;
+    u64 *keys; SeqMeta *meta; ErrInfo *err;
+    u32 nseq; int K; u32 smem_cap;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_encode_sort(EncodeParams p) {
+    extern __shared__ __align__(16) u64 sk[];
+    __shared__ u64 s_hash, s_prev;
+    __shared__ u32 s_wtot[THREADS / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 s = blockIdx.x;
+    const u8 *r = p.res + p.off[s];
+    const u32 L = (u32)(p.off[s + 1] - p.off[s]);
+    const int K = p.K;
+    const u32 n = L >= (u32)K ? L - K + 1 : 0;
+    u64 *dst = p.keys + p.koff[s];
+    u64 *w = (n <= p.smem_cap) ? sk : dst;
+    if (tid == 0) s_hash = 0;
+    __syncthreads();
+    u64 h = 0;
+    for (u32 i = tid; i < L; i += THREADS) {
+        u8 c = r[i];
+        if (c_code[c] == 0xFF && atomicCAS(&p.err->flag, 0u, 1u) == 0u) { p.err->seq = s; p.err->pos = i; p.err->byte = c; }
+        h += mix64((((u64)i << 8) | c) + 0x9E3779B97F4A7C15ULL);
+    }
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&s_hash), (unsigned long long)h);
+    for (u32 i = tid; i < n; i += THREADS) {
+        u64 key = 0;
+        for (int t = 0; t < K; ++t) key = (key << 5) | (u64)(c_code[r[i + t]] & 31);
+        w[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort(w, n, tid, THREADS);
+    // distinct keys, compacted in order (safe in place: an output index never exceeds its input index)
+    u32 out_base = 0;
+    for (u32 tile = 0; tile < n; tile += THREADS) {
+        u32 i = tile + tid;
+        bool valid = i < n;
+        u64 v = valid ? w[i] : 0;
+        bool flag = valid && (i == 0 || v != (tid == 0 ? s_prev : w[i - 1]));
+        u32 bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_wtot[warp] = __popc(bal);
+        __syncthreads();   // all reads of this tile are done; warp totals visible
+        u32 before = 0, total = 0;
+        for (u32 k = 0; k < THREADS / 32; ++k) { u32 c = s_wtot[k]; if (k < warp) before += c; total += c; }
+        if (flag) dst[out_base + before + __popc(bal & ((1u << lane) - 1))] = v;
+        if (valid && (i == n - 1 || tid == THREADS - 1)) s_prev = v;
+        out_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) { SeqMeta m; m.size = out_base; m.len = L; m.hash = s_hash; m.res = r; p.meta[s] = m; }
+}
+
+// copy the key lists of selected sequences into a new compact arena (kr_seqset_gather)
+__global__ void k_gather_keys(const u64 *src_keys, const u64 *src_koff, const SeqMeta *src_meta, const u32 *idx,
+                              u32 n, const u64 *dst_koff, u64 *dst_keys, SeqMeta *dst_meta) {
+    u32 i = blockIdx.x;
+    if (i >= n) return;
+    u32 s = idx[i];
+    SeqMeta m = src_meta[s];
+    const u64 *a = src_keys + src_koff[s];
+    u64 *d = dst_keys + dst_koff[i];
+    for (u32 t = threadIdx.x; t < m.size; t += blockDim.x) d[t] = a[t];
+    if (threadIdx.x == 0) dst_meta[i] = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: block lists.  count -> offsets -> scatter -> sort each chunk.
+__global__ void __launch_bounds__(256) k_bl_count(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq,
+                                                  const u8 *lut, int shift, u32 *chcnt) {
+    __shared__ u32 hist[NCHUNK];
+    const u32 b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < NCHUNK) hist[tid] = 0;
+    __syncthreads();
+    u32 s0 = b * TB, s1 = min(nseq, s0 + TB);
+    for (u32 s = s0 + warp; s < s1; s += 8) {
+        u32 sz = meta[s].size; const u64 *kp = keys + koff[s];
+        for (u32 i = lane; i < sz; i += 32) atomicAdd(&hist[lut[kp[i] >> shift]], 1u);
+    }
+    __syncthreads();
+    if (tid < NCHUNK) chcnt[b * NCHUNK + tid] = hist[tid];
+}
+
+// one CTA: per-block padded chunk starts, then an exclusive scan of the block totals
+__global__ void __launch_bounds__(1024) k_bl_offsets(const u32 *chcnt, u32 nblk, u32 *choff, u64 *blkbase) {
+    __shared__ u64 part[1024];
+    const u32 tid = threadIdx.x;
+    u32 per = (nblk + 1023) / 1024;
+    u32 b0 = min(nblk, tid * per), b1 = min(nblk, b0 + per);
+    u64 sum = 0;
+    for (u32 b = b0; b < b1; ++b) {
+        u32 o = 0;
+        for (int c = 0; c < NCHUNK; ++c) {
+            choff[b * (NCHUNK + 1) + c] = o;
+            o += (chcnt[b * NCHUNK + c] + CHUNK_ALIGN - 1) / CHUNK_ALIGN * CHUNK_ALIGN;
+        }
+        choff[b * (NCHUNK + 1) + NCHUNK] = o;
+        sum += o;
+    }
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) { u64 run = 0; for (int i = 0; i < 1024; ++i) { u64 v = part[i]; part[i] = run; run += v; } blkbase[nblk] = run; }
+    __syncthreads();
+    u64 run = part[tid];
+    for (u32 b = b0; b < b1; ++b) { blkbase[b] = run; run += choff[b * (NCHUNK + 1) + NCHUNK]; }
+}
+
+__global__ void __launch_bounds__(256) k_bl_scatter(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq,
+                                                    const u8 *lut, int shift, const u32 *chcnt, const u32 *choff,
+                                                    const u64 *blkbase, u64 *ent, BlockRef *refs) {
+    __shared__ u32 cur[NCHUNK];
+    __shared__ u32 so[NCHUNK + 1];
+    const u32 b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < NCHUNK) cur[tid] = 0;
+    if (tid <= NCHUNK) so[tid] = choff[b * (NCHUNK + 1) + tid];
+    __syncthreads();
+    u64 *e = ent + blkbase[b];
+    u32 s0 = b * TB, s1 = min(nseq, s0 + TB);
+    for (u32 s = s0 + warp; s < s1; s += 8) {
+        u32 sz = meta[s].size; const u64 *kp = keys + koff[s];
+        u64 lid = s - s0;
+        for (u32 i = lane; i < sz; i += 32) {
+            u64 key = kp[i];
+            u32 c = lut[key >> shift];
+            u32 pos = atomicAdd(&cur[c], 1u);
+            e[so[c] + pos] = (key << LID_BITS) | lid;
+        }
+    }
+    __syncthreads();
+    // sentinel padding between the end of each chunk and the start of the next
+    for (u32 c = warp; c < NCHUNK; c += 8)
+        for (u32 i = so[c] + chcnt[b * NCHUNK + c] + lane; i < so[c + 1]; i += 32) e[i] = SENT;
+    if (tid == 0) {
+        BlockRef r; r.ent = e; r.off = choff + b * (NCHUNK + 1); r.cnt = chcnt + b * NCHUNK; r.seq0 = s0; r.nseq = s1 - s0;
+        refs[b] = r;
+    }
+}
+
+constexpr int SORT_SMEM_CAP = 4096;
+__global__ void __launch_bounds__(256) k_bl_sort(const BlockRef *refs) {
+    __shared__ __align__(16) u64 sk[SORT_SMEM_CAP];
+    const u32 b = blockIdx.x / NCHUNK, c = blockIdx.x % NCHUNK, tid = threadIdx.x;
+    BlockRef r = refs[b];
+    u32 n = r.cnt[c];
+    if (n < 2) return;
+    u64 *g = const_cast<u64 *>(r.ent) + r.off[c];
+    if (n <= SORT_SMEM_CAP) {
+        for (u32 i = tid; i < n; i += 256) sk[i] = g[i];
+        __syncthreads();
+        bitonic_sort(sk, n, tid, 256);
+        for (u32 i = tid; i < n; i += 256) g[i] = sk[i];
+    } else {
+        bitonic_sort(g, n, tid, 256);   // rare: very long sequences; in place in global memory
+    }
+}
+
+// re-base the block refs of a set into a database-wide array (seq0 += base)
+__global__ void k_copy_refs(const BlockRef *src, u32 n, u32 seq_base, BlockRef *dst) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { BlockRef r = src[i]; r.seq0 += seq_base; dst[i] = r; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCWARP * 32) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// K3: the tile join.
+enum { MODE_MATRIX = 0, MODE_ARGMAX = 1 };
+
+struct JoinParams {
+    const BlockRef *A, *B;
+    const SeqMeta *metaA, *metaB;
+    u32 nA, nB;              // sequences on each side
+    u32 nBblk;
+    const uint2 *tasks; u32 ntasks;   // MATRIX: (I, J).  ARGMAX: (I, split)
+    u32 flags;               // KR_IDENT_IS_INFINITY
+    // MATRIX
+    void *out; u32 elem, layout; u64 origin;
+    // ARGMAX
+    u32 nsplit; const u32 *rankB; int4 *partial;
+};
+
+__device__ __forceinline__ u64 cell_index(u32 layout, u64 i, u64 j, u64 nrows, u64 ncols) {
+    if (layout == 0) return i * ncols + j;
+    if (layout == 1) return i * nrows - i * (i + 1) / 2 + (j - i - 1);
+    u64 I = i >> 8, c0 = I << 8;
+    return 256ull * (I * nrows - 128ull * I * (I - 1)) + (i - c0) * (nrows - c0) + (j - c0);
+}
+
+__device__ __noinline__ bool seq_equal(const SeqMeta &a, const SeqMeta &b) {
+    if (a.len != b.len || a.hash != b.hash) return false;
+    for (u32 i = 0; i < a.len; ++i) if (a.res[i] != b.res[i]) return false;
+    return true;
+}
+
+// all matches of the staged A entries against the staged B entries -> count tile
+__device__ __forceinline__ void join_job(const u64 *__restrict__ sA, u32 na, const u64 *__restrict__ sB, u32 nb,
+                                         u32 *cnt, u32 warp, u32 lane) {
+    for (u32 base = warp * 32; base < na; base += NCWARP * 32) {
+        u32 idx = base + lane;
+        if (idx < na) {
+            u64 e = sA[idx];
+            u64 target = e & ~LID_MASK;
+            u32 a = (u32)(e & LID_MASK);
+            u32 lo = 0, len = nb;
+            while (len) {
+                u32 half = len >> 1;
+                if (sB[lo + half] < target) { lo += half + 1; len -= half + 1; } else len = half;
+            }
+            while (lo < nb) {
+                u64 v = sB[lo];
+                if ((v & ~LID_MASK) != target) break;
+                u32 b = (u32)(v & LID_MASK);
+                atomicAdd(&cnt[(a * TB + b) >> 1], (b & 1) ? 0x10000u : 1u);
+                ++lo;
+            }
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
+    extern __shared__ __align__(128) u8 smem[];
+    u32 *cnt = reinterpret_cast<u32 *>(smem);
+    u64 *stage = reinterpret_cast<u64 *>(smem + JOIN_SMEM_CNT);
+    u64 *full = reinterpret_cast<u64 *>(smem + JOIN_SMEM_CNT + JOIN_SMEM_STAGE);
+    u64 *empty = full + NSTAGE;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == NCWARP;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCWARP); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (u32 i = tid; i < TB * TB / 2; i += JOIN_THREADS) cnt[i] = 0;
+    __syncthreads();
+
+    u32 k = 0;   // pipeline job counter; producer and consumers enumerate the same jobs
+    for (u32 task = blockIdx.x; task < p.ntasks; task += gridDim.x) {
+        uint2 tk = p.tasks[task];
+        const u32 I = tk.x;
+        u32 j0, j1;
+        if (MODE == MODE_MATRIX) { j0 = tk.y; j1 = tk.y + 1; }
+        else { j0 = (u32)((u64)tk.y * p.nBblk / p.nsplit); j1 = (u32)((u64)(tk.y + 1) * p.nBblk / p.nsplit); }
+        const BlockRef a = p.A[I];
+        // ARGMAX: row r of the tile is owned by warp r%16, its running best lives in lane r/16
+        int best_sim = 0; u32 best_first = 0xFFFFFFFFu, best_last = 0;
+
+        for (u32 J = j0; J < j1; ++J) {
+            const BlockRef b = p.B[J];
+            for (int c = 0; c < NCHUNK; ++c) {
+                const u32 nAc = __ldg(a.cnt + c), nBc = __ldg(b.cnt + c);
+                if (nAc == 0 || nBc == 0) continue;
+                const u64 *gA = a.ent + __ldg(a.off + c), *gB = b.ent + __ldg(b.off + c);
+                for (u32 as = 0; as < nAc; as += STAGE_CAP) {
+                    const u32 na = min((u32)STAGE_CAP, nAc - as);
+                    for (u32 bs = 0; bs < nBc; bs += STAGE_CAP) {
+                        const u32 nb = min((u32)STAGE_CAP, nBc - bs);
+                        const u32 s = k % NSTAGE, ph = (k / NSTAGE) & 1;
+                        u64 *sA = stage + (size_t)s * 2 * STAGE_CAP, *sB = sA + STAGE_CAP;
+                        if (producer) {
+                            if (lane == 0) {
+                                mbar_wait(&empty[s], ph ^ 1);
+                                const u32 bytesA = ((na + 1) & ~1u) * 8, bytesB = ((nb + 1) & ~1u) * 8;
+                                mbar_expect_tx(&full[s], bytesA + bytesB);
+                                bulk_g2s(sA, gA + as, bytesA, &full[s]);
+                                bulk_g2s(sB, gB + bs, bytesB, &full[s]);
+                            }
+                        } else {
+                            mbar_wait(&full[s], ph);
+                            join_job(sA, na, sB, nb, cnt, warp, lane);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty[s]);
+                        }
+                        ++k;
+                    }
+                }
+            }
+            if (producer) continue;
+            // ---- epilogue of tile (I,J): consumers only -------------------------------------
+            consumer_bar();
+            const bool ident_inf = (p.flags & 1u) != 0;
+            for (u32 row = warp; row < a.nseq; row += NCWARP) {
+                uint4 *rp = reinterpret_cast<uint4 *>(cnt + row * (TB / 2)) + lane;
+                uint4 v = *rp;
+                *rp = make_uint4(0, 0, 0, 0);
+                int cv[8] = {(int)(v.x & 0xFFFF), (int)(v.x >> 16), (int)(v.y & 0xFFFF), (int)(v.y >> 16),
+                             (int)(v.z & 0xFFFF), (int)(v.z >> 16), (int)(v.w & 0xFFFF), (int)(v.w >> 16)};
+                const u32 i = a.seq0 + row;
+                const u32 jb = b.seq0 + lane * 8;      // first column of this lane
+                if (ident_inf) {
+                    const u32 szA = p.metaA[i].size;
+                    bool cand = false;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) cand |= (cv[t] == (int)szA) && (lane * 8 + t < b.nseq);
+                    if (cand) {
+                        const SeqMeta ma = p.metaA[i];
+                        for (int t = 0; t < 8; ++t)
+                            if (cv[t] == (int)szA && lane * 8 + t < b.nseq) {
+                                const SeqMeta mb = p.metaB[jb + t];
+                                if (mb.size == szA && seq_equal(ma, mb)) cv[t] = KR_INF;
+                            }
+                    }
+                }
+                if (MODE == MODE_MATRIX) {
+                    const u64 N = p.nA, M = p.nB;
+                    // valid columns of this row inside the tile
+                    u32 jlo = b.seq0, jhi = b.seq0 + b.nseq;
+                    if (p.layout == 1 && jlo < i + 1) jlo = i + 1;
+                    if (jlo < jhi && jb + 8 > jlo && jb < jhi) {
+                        const u32 ja = max(jb, jlo);
+                        const u64 idx = cell_index(p.layout, i, ja, N, M) - p.origin - (ja - jb);  // index of column jb
+                        const bool fullv = jb >= jlo && jb + 8 <= jhi;
+                        if (p.elem == 1) {
+                            u16 *o = reinterpret_cast<u16 *>(p.out) + idx;
+                            if (fullv && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                                uint4 w;
+                                w.x = (u32)cv[0] | ((u32)cv[1] << 16); w.y = (u32)cv[2] | ((u32)cv[3] << 16);
+                                w.z = (u32)cv[4] | ((u32)cv[5] << 16); w.w = (u32)cv[6] | ((u32)cv[7] << 16);
+                                *reinterpret_cast<uint4 *>(o) = w;
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) if (jb + t >= jlo && jb + t < jhi) o[t] = (u16)cv[t];
+                            }
+                        } else {
+                            int *o = reinterpret_cast<int *>(p.out) + idx;
+                            if (fullv && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                                reinterpret_cast<int4 *>(o)[0] = make_int4(cv[0], cv[1], cv[2], cv[3]);
+                                reinterpret_cast<int4 *>(o)[1] = make_int4(cv[4], cv[5], cv[6], cv[7]);
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) if (jb + t >= jlo && jb + t < jhi) o[t] = cv[t];
+                            }
+                        }
+                    }
+                } else {
+                    // row maximum with first/last rank among the maxima
+                    int m = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) if (lane * 8 + t < b.nseq) m = max(m, cv[t]);
+                    int wm = m;
+                    for (int o = 16; o > 0; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+                    if (wm > 0) {
+                        u32 rf = 0xFFFFFFFFu, rl = 0;
+                        if (m == wm) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t)
+                                if (lane * 8 + t < b.nseq && cv[t] == wm) { u32 rk = __ldg(p.rankB + jb + t); rf = min(rf, rk); rl = max(rl, rk); }
+                        }
+                        for (int o = 16; o > 0; o >>= 1) {
+                            rf = min(rf, __shfl_xor_sync(0xffffffffu, rf, o));
+                            rl = max(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+                        }
+                        if (lane == (row >> 4)) {
+                            if (wm > best_sim) { best_sim = wm; best_first = rf; best_last = rl; }
+                            else if (wm == best_sim) { best_first = min(best_first, rf); best_last = max(best_last, rl); }
+                        }
+                    }
+                }
+            }
+            consumer_bar();
+        }
+        if (MODE == MODE_ARGMAX && !producer) {
+            const u32 row = warp + 16 * lane;
+            if (lane < 16 && row < a.nseq) p.partial[(size_t)task * TB + row] = make_int4(best_sim, (int)best_first, (int)best_last, 0);
+        }
+    }
+}
+
+// merge the per-split partial maxima of each query; rank -> representative index via `order`
+__global__ void k_argmax_merge(const int4 *partial, u32 nq, u32 nsplit, const u32 *order, int *best_sim, u32 *best_first,
+                               u32 *best_last) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    u32 I = q / TB, row = q % TB;
+    int bs = 0; u32 bf = 0xFFFFFFFFu, bl = 0;
+    for (u32 sp = 0; sp < nsplit; ++sp) {
+        int4 v = partial[((size_t)I * nsplit + sp) * TB + row];
+        if (v.x > bs) { bs = v.x; bf = (u32)v.y; bl = (u32)v.z; }
+        else if (v.x == bs && v.x > 0) { bf = min(bf, (u32)v.y); bl = max(bl, (u32)v.z); }
+    }
+    best_sim[q] = bs;
+    if (best_first) best_first[q] = bs > 0 ? order[bf] : 0xFFFFFFFFu;
+    if (best_last) best_last[q] = bs > 0 ? order[bl] : 0xFFFFFFFFu;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SequenceKmers.similarity for an explicit list of pairs: one warp per pair, the shorter key
+// list probes the longer one by binary search (both lists are L2-resident, sorted, distinct).
+__global__ void __launch_bounds__(256) k_sim_pairs(const u64 *keysA, const u64 *koffA, const SeqMeta *metaA, const u32 *ia,
+                                                   const u64 *keysB, const u64 *koffB, const SeqMeta *metaB, const u32 *ib,
+                                                   u64 npairs, u32 flags, int *sim, u8 *ident) {
+    const u32 lane = threadIdx.x & 31;
+    u64 wid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 p = wid; p < npairs; p += nw) {
+        u32 a = ia[p], b = ib[p];
+        SeqMeta ma = metaA[a], mb = metaB[b];
+        const u64 *la = keysA + koffA[a], *lb = keysB + koffB[b];
+        u32 na = ma.size, nb = mb.size;
+        if (na > nb) { const u64 *t = la; la = lb; lb = t; u32 tn = na; na = nb; nb = tn; }
+        int c = 0;
+        for (u32 i = lane; i < na; i += 32) {
+            u64 key = la[i];
+            u32 lo = 0, len = nb;
+            while (len) { u32 half = len >> 1; if (lb[lo + half] < key) { lo += half + 1; len -= half + 1; } else len = half; }
+            c += (lo < nb && lb[lo] == key);
+        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) {
+            bool same = (c == (int)ma.size && c == (int)mb.size) && seq_equal(ma, mb);
+            if (ident) ident[p] = same;
+            sim[p] = (same && (flags & 1u)) ? KR_INF : c;
+        }
+    }
+}
+
+__global__ void k_fill_u32_iota(u32 *p, u32 n, u32 base) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = base + i;
+}
+
+}  // namespace kr

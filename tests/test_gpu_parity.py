@@ -1,0 +1,273 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of
+libkmersreps_cuda.so (ctypes) and is compared bit-for-bit with the CPU oracle on the same inputs:
+the reference's fixtures (rep50.db, VapbProt.fa, GTO seeds, rickettsia duplicates) and seeded
+synthetic families, including the edge cases the domain has (empty / shorter-than-K sequences,
+identical sequences, ragged last blocks, X-rich sequences, every K the packing supports)."""
+import numpy as np
+import pytest
+
+import kmers.reps_b200 as kr
+from kmers.reps_b200 import synth
+from oracle import kr_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_raw():
+    c = kr.Context(device=0, K=8, flags=0)
+    yield c
+    c.close()
+
+
+def tri_from_full(m):
+    iu = np.triu_indices(m.shape[0], 1)
+    return m[iu]
+
+
+def test_kat_k10(expected):
+    k = expected["kat_k10"]
+    c = kr.Context(device=0, K=10, flags=kr.IDENT_IS_INFINITY)
+    s = c.encode([k["p1"], k["p2"], k["p3"]])
+    assert list(s.sizes()) == [41, 41, 20]
+    m = c.sim_matrix(s)
+    assert m[1, 2] == 3 and m[2, 1] == 3 and m[0, 1] == 0 and m[0, 0] == kr.INFINITY
+    sim, ident = c.sim_pairs(s, [1, 2, 0, 0], s, [2, 1, 1, 0])
+    assert list(sim) == [3, 3, 0, kr.INFINITY] and list(ident) == [0, 0, 0, 1]
+    assert kr.distance(3, 41, 20) == k["dist_p2_p3"] and kr.distance(0, 41, 41) == 1.0 and kr.distance(9999, 1, 1) == 0.0
+    # SequenceKmers.iterator(): decoded keys are exactly the distinct substrings
+    assert sorted(s.kmers(2)) == sorted(ko.py_kmers(k["p3"], 10))
+    c.close()
+
+
+def test_vapb_matrix_all_layouts(ctx, ctx_raw, vapb, oracle, expected):
+    seqs = [s for (_, _, s) in vapb]
+    b = oracle.batch(seqs, K=8)
+    want = oracle.sim_matrix(b, ident_inf=True)
+    want_raw = oracle.sim_matrix(b, ident_inf=False)
+    s = ctx.encode(seqs)
+    assert (s.sizes() == b.sizes()).all()
+    n = len(seqs)
+    for elem in (kr.ELEM_I32, kr.ELEM_U16):
+        full = ctx.sim_matrix(s, elem=elem, layout=kr.LAYOUT_FULL)
+        assert (full == want).all()
+        tri = ctx.sim_matrix(s, elem=elem, layout=kr.LAYOUT_TRIANGLE)
+        assert (tri == tri_from_full(want)).all()
+        bt = ctx.sim_matrix(s, elem=elem, layout=kr.LAYOUT_BLOCKTRI)
+        parts = []
+        for i in range(n):
+            parts.append(want[i, 256 * (i // 256):])
+        assert (bt == np.concatenate(parts)).all()
+    sr = ctx_raw.encode(seqs)
+    raw = ctx_raw.sim_matrix(sr)
+    assert (raw == want_raw).all()
+    e = expected["config2"]
+    t = tri_from_full(raw)
+    assert int(t.sum()) == e["sum_sim"] and int((t > 0).sum()) == e["nonzero_pairs"] and int(t.max()) == e["max_raw_sim"]
+    assert int((tri_from_full(full) == kr.INFINITY).sum()) == e["identical_pairs"] == 11
+
+
+def test_rep50_matrix_and_stripes(ctx, rep50, oracle, expected):
+    seqs = [s for (_, _, s) in rep50["reps"]]
+    b = oracle.batch(seqs, K=8)
+    want = oracle.sim_matrix(b, ident_inf=True, threads=8)
+    s = ctx.encode(seqs)
+    assert (s.sizes() == b.sizes()).all()
+    assert int(s.sizes().sum()) == expected["rep50"]["total_kmers"]
+    full = ctx.sim_matrix(s, elem=kr.ELEM_U16)
+    assert (full == want).all()
+    t = tri_from_full(full.astype(np.int64))
+    assert t.max() == 49 and int((t == 49).sum()) == 92 and int((t > 0).sum()) == expected["rep50"]["nonzero_pairs"]
+    # row stripes (the multi-GPU sharding unit) reassemble to the same matrix, in every layout
+    for layout in (kr.LAYOUT_FULL, kr.LAYOUT_TRIANGLE, kr.LAYOUT_BLOCKTRI):
+        whole = ctx.sim_matrix(s, elem=kr.ELEM_U16, layout=layout).ravel()
+        for nsh in (2, 3):
+            rb = kr.matrix_stripes(len(seqs), len(seqs), layout, nsh)
+            parts = [ctx.sim_matrix(s, elem=kr.ELEM_U16, layout=layout, row_begin=int(rb[k]), row_end=int(rb[k + 1])).ravel()
+                     for k in range(nsh)]
+            assert (np.concatenate(parts) == whole).all()
+
+
+def test_rectangular_matrix_and_pairs(ctx, rep50, gto_seeds, rickettsia, oracle):
+    reps = [s for (_, _, s) in rep50["reps"]][:700]
+    qs = [s for (_, _, s) in gto_seeds] + [p for (_, p) in rickettsia]
+    A, B = ctx.encode(qs), ctx.encode(reps)
+    oa, ob = oracle.batch(qs, K=8), oracle.batch(reps, K=8)
+    want = oracle.sim_matrix(oa, ob, ident_inf=True, threads=4)
+    got = ctx.sim_matrix(A, B)
+    assert got.shape == want.shape and (got == want).all()
+    rng = np.random.default_rng(5)
+    ia = rng.integers(0, len(qs), 5000)
+    ib = rng.integers(0, len(reps), 5000)
+    sim, ident = ctx.sim_pairs(A, ia, B, ib)
+    assert (sim == want[ia, ib]).all() and (ident == (want[ia, ib] == kr.INFINITY)).all()
+    # duplicate-heavy real set against itself: 66 duplicate records -> INFINITY cells
+    R = ctx.encode([p for (_, p) in rickettsia])
+    orr = oracle.batch([p for (_, p) in rickettsia], K=8)
+    assert (ctx.sim_matrix(R) == oracle.sim_matrix(orr, ident_inf=True)).all()
+
+
+def test_config1_find_closest(ctx, rep50, gto_seeds, oracle, expected):
+    reps = [s for (_, _, s) in rep50["reps"]]
+    db = ctx.db()
+    db.append(reps[:1000])
+    db.append(reps[1000:])                  # two segments
+    assert db.size == 1480
+    q = ctx.encode([s for (_, _, s) in gto_seeds])
+    sim, first, last = db.find_closest(q)
+    for i, e in enumerate(expected["config1"]):
+        assert sim[i] == e["sim"] and first[i] == e["rep_index"] == last[i]
+        sz = q.sizes()[i]
+        assert sz == e["size"]
+    # rep50.db queried with its own members: each finds itself with INFINITY
+    qq = ctx.encode(reps)
+    sim, first, last = db.find_closest(qq)
+    assert (sim == kr.INFINITY).all() and (first == np.arange(1480)).all() and (last == first).all()
+    # any_ge is the checkSimilarity of the build loop
+    assert db.any_ge(q, 50).all() and not db.any_ge(q, 400).any()
+
+
+def test_find_closest_ties_and_ranks(ctx_raw, oracle):
+    # duplicates in the database create exact ties; the rank permutation decides first/last
+    res, off, _ = synth.generate(77, 900, 9, dup_per_10k=2500)
+    seqs = synth.to_strings(res, off)
+    reps, qs = seqs[:600], seqs[600:]
+    rng = np.random.default_rng(3)
+    order = rng.permutation(len(reps)).astype(np.int32)       # order[k] = rep visited k-th
+    rank = np.empty(len(reps), dtype=np.uint32)
+    rank[order] = np.arange(len(reps), dtype=np.uint32)
+    db = ctx_raw.db()
+    db.append(reps)
+    db.set_ranks(rank)
+    q = ctx_raw.encode(qs)
+    sim, first, last = db.find_closest(q)
+    orp, oq = oracle.batch(reps, K=8), oracle.batch(qs, K=8)
+    bs, bi = oracle.find_closest(orp, oq, order=order, ident_inf=False)
+    bs2, bi2 = oracle.find_closest(orp, oq, order=order, ident_inf=False, tie_last=True)
+    assert (sim == bs).all() and (sim == bs2).all()
+    assert (first.astype(np.int64) == np.where(bs > 0, bi, kr.NO_REP)).all()
+    assert (last.astype(np.int64) == np.where(bs2 > 0, bi2, kr.NO_REP)).all()
+    assert (first != last).any()            # the case is exercised
+
+
+def test_edge_cases_and_all_k(oracle):
+    seqs = ["", "A", "ACDEFGH", "ACDEFGHI", "ACDEFGHIK", "AAAAAAAAAAAAAAAAAAAA", "ACDEFGHI", "XXXXXXXXXXXXXXXXXXXXXXXXX",
+            "MKV*LL-AAGT*", "BJOUZXBJOUZXBJOUZX", "ACDEFGH", ""]
+    res, off, _ = synth.generate(5, 300, 5)
+    seqs += synth.to_strings(res, off)
+    for K in (3, 5, 8, 11):
+        for flags in (0, kr.IDENT_IS_INFINITY):
+            c = kr.Context(device=0, K=K, flags=flags)
+            s = c.encode(seqs)
+            b = oracle.batch(seqs, K=K)
+            assert (s.sizes() == b.sizes()).all()
+            want = oracle.sim_matrix(b, ident_inf=bool(flags))
+            assert (c.sim_matrix(s) == want).all()
+            for i in (2, 3, 5, 8, 9):
+                assert sorted(s.kmers(i)) == sorted(ko.py_kmers(seqs[i], K))
+            c.close()
+    # empty batch and a batch of only empty sequences
+    c = kr.Context(device=0, K=8)
+    e = c.encode([])
+    assert e.count == 0 and c.sim_matrix(e).size == 0
+    z = c.encode(["", "AC", ""])
+    assert list(z.sizes()) == [0, 0, 0]
+    m = c.sim_matrix(z)
+    assert m[0, 2] == kr.INFINITY and m[0, 1] == 0 and m[1, 1] == kr.INFINITY
+    c.close()
+
+
+def test_error_paths():
+    c = kr.Context(device=0, K=8)
+    with pytest.raises(kr.KrError) as ei:
+        c.encode(["ACDEFGHIK", "ACDEFGHIKacdef"])
+    assert ei.value.code == -4 and "sequence 1 position 9" in str(ei.value) and "'a'" in str(ei.value)
+    # the context stays usable after an error
+    s = c.encode(["ACDEFGHIKL"])
+    assert list(s.sizes()) == [3]
+    with pytest.raises(kr.KrError):
+        kr.Context(device=0, K=12)
+    with pytest.raises(kr.KrError):
+        kr.Context(device=0, K=2)
+    with pytest.raises(kr.KrError):
+        c.sim_matrix(s, layout=kr.LAYOUT_TRIANGLE, row_begin=3)
+    other = kr.Context(device=0, K=8)
+    with pytest.raises(kr.KrError):
+        other.sim_matrix(s)
+    other.close()
+    c.close()
+
+
+def test_long_sequences(oracle):
+    # longer than the shared-memory sort capacity (2048 keys) and than one pipeline stage per chunk
+    rng = np.random.default_rng(9)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    base = alpha[rng.integers(0, 20, 9000)]
+    seqs = []
+    for i in range(6):
+        s = base.copy()
+        pos = rng.integers(0, len(s), 300 * i)
+        s[pos] = alpha[rng.integers(0, 20, len(pos))]
+        seqs.append(s[: 9000 - 500 * i].tobytes().decode())
+    seqs.append("ACDEFGHIKL" * 500)          # 5000 residues, 10 distinct k-mers
+    c = kr.Context(device=0, K=8)
+    s = c.encode(seqs)
+    b = oracle.batch(seqs, K=8)
+    assert (s.sizes() == b.sizes()).all()
+    assert (c.sim_matrix(s) == oracle.sim_matrix(b, ident_inf=True)).all()
+    c.close()
+
+
+def test_synthetic_families_vs_oracle(ctx, oracle):
+    res, off, fam = synth.generate(0x5EED0003, 3000, 60)
+    s = ctx.encode(res=res, off=off)
+    b = oracle.batch(res=res, off=off, K=8)
+    want = oracle.sim_matrix(b, ident_inf=True, threads=8)
+    bt = ctx.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI)
+    parts = [want[i, 256 * (i // 256):] for i in range(3000)]
+    assert (bt == np.concatenate(parts)).all()
+    # encode from a device-resident residue buffer gives the same set
+    import torch
+    d = torch.from_numpy(res).cuda()
+    s2 = ctx.encode_device(d.data_ptr(), off)
+    assert (s2.sizes() == s.sizes()).all()
+    sim, _ = ctx.sim_pairs(s, np.arange(2999), s2, np.arange(1, 3000))
+    assert (sim == want[np.arange(2999), np.arange(1, 3000)]).all()
+
+
+def test_greedy_build_matches_oracle(oracle, rep50, rickettsia):
+    res, off, _ = synth.generate(0x5EED0004, 6000, 150, xrun_per_10k=30)
+    b = oracle.batch(res=res, off=off, K=8)
+    for flags in (kr.IDENT_IS_INFINITY, 0):
+        n, added, _ = oracle.greedy_build(b, 50, ident_inf=bool(flags))
+        for batch in (0, 256, 1000):
+            c = kr.Context(device=0, K=8, flags=flags)
+            cands = c.encode(res=res, off=off)
+            db = c.db()
+            got = db.greedy_build(cands, 50, batch=batch)
+            assert db.size == n and (got == added).all(), (flags, batch)
+            c.close()
+    # the reference's own database rebuilt from its own sequences keeps all 1480 (stingy-add invariant)
+    c = kr.Context(device=0, K=8)
+    reps = [s for (_, _, s) in rep50["reps"]]
+    db = c.db()
+    added = db.greedy_build(c.encode(reps), 50, batch=500)
+    assert added.all() and db.size == 1480
+    # duplicates: 100 PheS of which 34 distinct
+    seqs = [p for (_, p) in rickettsia]
+    n, want, _ = oracle.greedy_build(oracle.batch(seqs, K=8), 50)
+    db2 = c.db()
+    assert (db2.greedy_build(c.encode(seqs), 50, batch=16) == want).all() and db2.size == n
+    # building on top of an existing database
+    db3 = c.db()
+    db3.append(reps[:700])
+    got = db3.greedy_build(c.encode(reps), 50, batch=300)
+    assert not got[:700].any() and got[700:].all() and db3.size == 1480
+    c.close()
