@@ -179,6 +179,10 @@ typedef struct kr_stats {
 } kr_stats;
 kr_status kr_stats_get(kr_ctx *ctx, kr_stats *out); /* synchronises the context's stream */
 kr_status kr_stats_reset(kr_ctx *ctx);
+/* device-time bracket on the context's own stream (CUDA events): begin records, end records,
+ * waits for the stream and returns the elapsed milliseconds in between */
+kr_status kr_timer_begin(kr_ctx *ctx);
+kr_status kr_timer_end(kr_ctx *ctx, double *ms);
 
 /* pinned host memory for callers that want full-speed copies of large matrices */
 kr_status kr_host_alloc(kr_ctx *ctx, size_t bytes, void **out);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
     "kr_db_find_closest", "kr_db_find_closest_device", "kr_db_any_ge", "kr_greedy_build", "kr_stats_get",
-    "kr_stats_reset", "kr_host_alloc", "kr_host_free",
+    "kr_stats_reset", "kr_timer_begin", "kr_timer_end", "kr_host_alloc", "kr_host_free",
 ]
 
 
@@ -102,6 +102,8 @@ def load_library():
     lib.kr_greedy_build.argtypes = [vp, vp, vp, i32, u32, vp]
     lib.kr_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.kr_stats_reset.argtypes = [vp]
+    lib.kr_timer_begin.argtypes = [vp]
+    lib.kr_timer_end.argtypes = [vp, C.POINTER(C.c_double)]
     lib.kr_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.kr_host_free.argtypes = [vp, vp]
     lib.kr_host_free.restype = None
@@ -158,6 +160,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.lib.kr_host_free(self.h, p)
+            self._pinned = []
             self.lib.kr_destroy(self.h)
             self.h = None
 
@@ -230,6 +235,23 @@ class Context:
 
     def stats_reset(self):
         self._ck(self.lib.kr_stats_reset(self.h))
+
+    def timer_begin(self):
+        self._ck(self.lib.kr_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double(0)
+        self._ck(self.lib.kr_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def host_alloc(self, nbytes: int, dtype=np.uint8):
+        """pinned host array (freed when the context closes or by host_free)"""
+        p = C.c_void_p()
+        self._ck(self.lib.kr_host_alloc(self.h, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype)
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
 
 
 class SeqSet:

@@ -39,6 +39,7 @@ struct kr_ctx {
     kr_stats st{};
     std::vector<EvPair> pending;
     std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 struct kr_seqset {
@@ -196,6 +197,7 @@ void kr_destroy(kr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     StageTimer::drain(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_err);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -225,6 +227,27 @@ kr_status kr_stats_reset(kr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     StageTimer::drain(ctx);
     ctx->st = kr_stats{};
+    return KR_OK;
+}
+
+kr_status kr_timer_begin(kr_ctx *ctx) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    if (!ctx->t0) { CU(cudaEventCreate(&ctx->t0)); CU(cudaEventCreate(&ctx->t1)); }
+    CU(cudaEventRecord(ctx->t0, ctx->stream));
+    return KR_OK;
+}
+kr_status kr_timer_end(kr_ctx *ctx, double *ms) {
+    if (!ctx || !ms) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    if (!ctx->t0) return fail(ctx, KR_ERR_STATE, "kr_timer_end without kr_timer_begin");
+    CU(cudaEventRecord(ctx->t1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->t1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
+    *ms = f;
     return KR_OK;
 }
 

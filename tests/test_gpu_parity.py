@@ -152,8 +152,8 @@ def test_find_closest_ties_and_ranks(ctx_raw, oracle):
     bs, bi = oracle.find_closest(orp, oq, order=order, ident_inf=False)
     bs2, bi2 = oracle.find_closest(orp, oq, order=order, ident_inf=False, tie_last=True)
     assert (sim == bs).all() and (sim == bs2).all()
-    assert (first.astype(np.int64) == np.where(bs > 0, bi, kr.NO_REP)).all()
-    assert (last.astype(np.int64) == np.where(bs2 > 0, bi2, kr.NO_REP)).all()
+    assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
+    assert (last.astype(np.int64) == np.where(bs2 > 0, bi2.astype(np.int64), kr.NO_REP)).all()
     assert (first != last).any()            # the case is exercised
 
 
