@@ -46,7 +46,8 @@ class Stats(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(HERE, "libkmersreps_cuda.so")
+    # KR_LIB_PATH lets a tuning run point at another build of the same library (never at a fallback)
+    return os.environ.get("KR_LIB_PATH") or os.path.join(HERE, "libkmersreps_cuda.so")
 
 
 _LIB = None

@@ -55,7 +55,7 @@ struct kr_seqset {
     // block lists (built on first use)
     bool bl_ready = false;
     u32 nblk = 0;
-    u64 *d_ent = nullptr; u32 *d_choff = nullptr, *d_chcnt = nullptr; u64 *d_blkbase = nullptr;
+    u32 *d_hi = nullptr; void *d_lo = nullptr; u32 *d_choff = nullptr, *d_chcnt = nullptr; u64 *d_blkbase = nullptr;
     BlockRef *d_refs = nullptr;
     std::vector<std::shared_ptr<DevMem>> keep;   // parents' residue buffers
 };
@@ -184,8 +184,10 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_err, sizeof(ErrInfo)));
     CUC(cudaMemset(ctx->d_err, 0, sizeof(ErrInfo)));
-    CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JOIN_SMEM_BYTES));
-    CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JOIN_SMEM_BYTES));
+    CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
+    CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
+    CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
+    CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
 #undef CUC
     *out = ctx;
     return KR_OK;
@@ -282,7 +284,7 @@ static void seqset_destroy(kr_seqset *s) {
     kr_ctx *ctx = s->ctx;
     cudaSetDevice(ctx->dev);
     dfree(ctx, s->d_off); dfree(ctx, s->d_koff); dfree(ctx, s->d_keys); dfree(ctx, s->d_meta);
-    dfree(ctx, s->d_ent); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
+    dfree(ctx, s->d_hi); dfree(ctx, (u8 *)s->d_lo); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
     if (s->res || !s->keep.empty()) cudaStreamSynchronize(ctx->stream);   // residue buffers use cudaFree
     delete s;
 }
@@ -345,8 +347,13 @@ static kr_status ensure_blocklists(kr_ctx *ctx, kr_seqset *s) {
     if (s->bl_ready) return KR_OK;
     u32 nblk = (s->n + TB - 1) / TB;
     s->nblk = nblk;
-    u64 cap = s->key_cap + (u64)nblk * NCHUNK * CHUNK_ALIGN + 64;
-    CU(dalloc(ctx, &s->d_ent, cap)); CU(dalloc(ctx, &s->d_choff, (size_t)nblk * (NCHUNK + 1)));
+    // entries + per-chunk alignment padding + the sentinel tail after every block
+    u64 cap = s->key_cap + (u64)nblk * NCHUNK * CHUNK_ALIGN + (u64)nblk * TAILPAD + 64;
+    const int lobits = lo_bits(ctx->K), lo_size = lobits <= 16 ? 2 : 4;
+    u64 *d_ent = nullptr; u8 *d_lo = nullptr;
+    CU(dalloc(ctx, &d_ent, cap)); CU(dalloc(ctx, &s->d_hi, cap)); CU(dalloc(ctx, &d_lo, cap * lo_size));
+    s->d_lo = d_lo;
+    CU(dalloc(ctx, &s->d_choff, (size_t)nblk * (NCHUNK + 1)));
     CU(dalloc(ctx, &s->d_chcnt, (size_t)nblk * NCHUNK)); CU(dalloc(ctx, &s->d_blkbase, nblk + 1)); CU(dalloc(ctx, &s->d_refs, nblk));
     if (nblk) {
         StageTimer t(ctx, ST_BLOCKLIST);
@@ -354,11 +361,12 @@ static kr_status ensure_blocklists(kr_ctx *ctx, kr_seqset *s) {
         k_bl_count<<<nblk, 256, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt);
         k_bl_offsets<<<1, 1024, 0, ctx->stream>>>(s->d_chcnt, nblk, s->d_choff, s->d_blkbase);
         k_bl_scatter<<<nblk, 256, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt, s->d_choff,
-                                                    s->d_blkbase, s->d_ent, s->d_refs);
-        k_bl_sort<<<nblk * NCHUNK, 256, 0, ctx->stream>>>(s->d_refs);
+                                                    s->d_blkbase, d_ent, s->d_hi, s->d_lo, lo_size, s->d_refs);
+        k_bl_sort<<<nblk * NCHUNK, 256, 0, ctx->stream>>>(s->d_refs, s->d_blkbase, d_ent, lobits);
         ctx->st.kernel_launches += 4;
         CU(cudaGetLastError());
     }
+    dfree(ctx, d_ent);   // the unsplit entries were only scratch for the sort
     s->bl_ready = true;
     return KR_OK;
 }
@@ -427,9 +435,15 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
     if (!self && (st = ensure_blocklists(ctx, B))) return st;
     kr_seqset *Bs = self ? A : B;
     u32 rb0 = d->row_begin / TB, rb1 = (d->row_end + TB - 1) / TB;
+    // Tile order: super-tiles of ST x ST blocks, so that the ~150 tiles in flight at any time share
+    // 2*ST block lists (a few MB) and re-reads of a block list hit L2 instead of HBM.
     std::vector<uint2> tasks;
-    for (u32 I = rb0; I < rb1; ++I)
-        for (u32 J = (d->layout == KR_LAYOUT_FULL ? 0 : I); J < Bs->nblk; ++J) tasks.push_back(make_uint2(I, J));
+    const u32 ST = 16;
+    for (u32 SI = rb0; SI < rb1; SI += ST)
+        for (u32 SJ = (d->layout == KR_LAYOUT_FULL ? 0 : SI / ST * ST); SJ < Bs->nblk; SJ += ST)
+            for (u32 I = SI; I < std::min(SI + ST, rb1); ++I)
+                for (u32 J = std::max(SJ, d->layout == KR_LAYOUT_FULL ? 0u : I); J < std::min(SJ + ST, Bs->nblk); ++J)
+                    tasks.push_back(make_uint2(I, J));
     if (tasks.empty()) return KR_OK;
     uint2 *d_tasks = nullptr;
     CU(dalloc(ctx, &d_tasks, tasks.size()));
@@ -443,7 +457,8 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
     {
         StageTimer t(ctx, ST_JOIN);
         u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
-        k_join<MODE_MATRIX><<<grid, JOIN_THREADS, JOIN_SMEM_BYTES, ctx->stream>>>(p);
+        if (lo_bits(ctx->K) <= 16) k_join<MODE_MATRIX, false><<<grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream>>>(p);
+        else k_join<MODE_MATRIX, true><<<grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream>>>(p);
         LAUNCHED(ctx); ctx->st.join_launches++;
         CU(cudaGetLastError());
     }
@@ -593,7 +608,8 @@ static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *
     {
         StageTimer t(ctx, ST_JOIN);
         u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
-        k_join<MODE_ARGMAX><<<grid, JOIN_THREADS, JOIN_SMEM_BYTES, ctx->stream>>>(p);
+        if (lo_bits(ctx->K) <= 16) k_join<MODE_ARGMAX, false><<<grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream>>>(p);
+        else k_join<MODE_ARGMAX, true><<<grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream>>>(p);
         LAUNCHED(ctx); ctx->st.join_launches++;
     }
     {

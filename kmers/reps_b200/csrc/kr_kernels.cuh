@@ -4,7 +4,9 @@
 //   residue  -> 5-bit code; k-mer -> 5K-bit key in a uint64 (K <= 11)
 //   sequence -> sorted array of its DISTINCT keys            ("key list",   K1)
 //   block    -> 256 consecutive sequences; all their (key,lid) entries, key<<8|lid, sorted and
-//               cut into NCHUNK key-range chunks by a fixed prefix table ("block list", K2)
+//               cut into NCHUNK key-range chunks by a fixed prefix table ("block list", K2);
+//               stored split: hi = top 32 bits of the entry (searched), lo = the remaining low
+//               bits (rest of the key + lid; 16 bits for K <= 8, 32 bits for K = 9..11)
 //   tile     -> block I x block J: one merge-style pass over the two block lists, staged chunk by
 //               chunk into shared memory with 1-D TMA bulk copies, counts the shared keys of all
 //               256x256 sequence pairs at once in a shared-memory count tile                (K3)
@@ -23,19 +25,49 @@ typedef uint8_t u8;
 constexpr int TB = 256;          // sequences per block (KR_TILE); lid fits LID_BITS
 constexpr int LID_BITS = 8;
 constexpr u64 LID_MASK = 0xFFull;
-constexpr int NCHUNK = 64;       // key-range chunks per block list
+#ifndef KR_NCHUNK
+#define KR_NCHUNK 64
+#endif
+constexpr int NCHUNK = KR_NCHUNK;  // key-range chunks per block list (32 or 64)
 constexpr int CHUNK_ALIGN = 16;  // chunk starts are multiples of 16 entries (128 B)
-constexpr int STAGE_CAP = 2048;  // entries per side per pipeline stage
-constexpr int NSTAGE = 3;
-constexpr int NCWARP = 16;       // consumer warps of the join kernel (+1 producer warp)
+#ifndef KR_STAGE_CAP
+#define KR_STAGE_CAP 1536
+#endif
+#ifndef KR_NSTAGE
+#define KR_NSTAGE 4
+#endif
+#ifndef KR_NCWARP
+#define KR_NCWARP 24
+#endif
+#ifndef KR_ILP
+#define KR_ILP 2
+#endif
+constexpr int STAGE_CAP = KR_STAGE_CAP;  // entries per side per pipeline stage
+constexpr int NSTAGE = KR_NSTAGE;
+#ifndef KR_STEP_TOP
+#define KR_STEP_TOP 1024
+#endif
+constexpr uint32_t STEP_TOP = KR_STEP_TOP;     // first probe step of the lower bound
+constexpr uint32_t WINDOW = 2 * STEP_TOP;      // hi entries staged per B side: probes reach index WINDOW-2
+constexpr uint32_t TAILPAD = WINDOW;           // sentinel hi entries after every block list
+constexpr uint32_t HI_SENT = 0xFFFFFFFFu;      // above every real hi (top residue code <= 27)
+static_assert(STAGE_CAP <= WINDOW - 1, "a staged B sub-chunk must fit the probe window");
+constexpr int NCWARP = KR_NCWARP;  // consumer warps of the join kernel (+1 producer warp)
+constexpr int ILP = KR_ILP;        // A entries searched together per lane
 constexpr int JOIN_THREADS = (NCWARP + 1) * 32;
 constexpr u64 SENT = ~0ull;
 constexpr int KR_INF = 9999;
 constexpr int LUT_BITS = 15;     // chunk table is indexed by the first three residues of the key
 
 constexpr size_t JOIN_SMEM_CNT = (size_t)TB * TB * 2;                         // u16 count tile
-constexpr size_t JOIN_SMEM_STAGE = (size_t)NSTAGE * 2 * STAGE_CAP * 8;
-constexpr size_t JOIN_SMEM_BYTES = JOIN_SMEM_CNT + JOIN_SMEM_STAGE + 64;
+// one pipeline stage: A hi | B hi window | A lo | B lo
+__host__ __device__ constexpr size_t stage_bytes(bool lo32) { return (size_t)STAGE_CAP * 4 + WINDOW * 4 + 2 * (size_t)STAGE_CAP * (lo32 ? 4 : 2); }
+__host__ __device__ constexpr int nstage(bool lo32) { return lo32 ? NSTAGE - 1 : NSTAGE; }
+__host__ __device__ constexpr size_t join_smem_bytes(bool lo32) { return JOIN_SMEM_CNT + nstage(lo32) * stage_bytes(lo32) + 256; }
+constexpr size_t JOIN_SMEM_BYTES = join_smem_bytes(false) > join_smem_bytes(true) ? join_smem_bytes(false) : join_smem_bytes(true);
+static_assert(JOIN_SMEM_BYTES <= 232448, "join kernel shared memory exceeds 227 KB");
+// low bits of an entry kept in `lo`: the lid plus whatever of the key does not fit the 32-bit hi
+__host__ __device__ constexpr int lo_bits(int K) { return 5 * K + LID_BITS - 32 > LID_BITS ? 5 * K + LID_BITS - 32 : LID_BITS; }
 
 struct SeqMeta {   // one per sequence
     u32 size;      // number of distinct k-mers (SequenceKmers.size())
@@ -44,12 +76,13 @@ struct SeqMeta {   // one per sequence
     const u8 *res; // the residues themselves (exact check for the equal-sequence rule)
 };
 
-struct BlockRef {   // one per block of 256 sequences
-    const u64 *ent; // first entry of the block list
-    const u32 *off; // NCHUNK+1 chunk starts (entries, relative to ent, multiples of CHUNK_ALIGN)
-    const u32 *cnt; // NCHUNK chunk lengths
-    u32 seq0;       // index of the block's first sequence in its set / database
-    u32 nseq;       // sequences in the block (<= 256)
+struct BlockRef {    // one per block of 256 sequences
+    const u32 *hi;   // block list, high words (sorted; sentinel-padded between chunks and after the block)
+    const void *lo;  // block list, low bits (u16 or u32 per entry, same indexing as hi)
+    const u32 *off;  // NCHUNK+1 chunk starts (entries, relative to hi/lo, multiples of CHUNK_ALIGN)
+    const u32 *cnt;  // NCHUNK chunk lengths
+    u32 seq0;        // index of the block's first sequence in its set / database
+    u32 nseq;        // sequences in the block (<= 256)
 };
 
 struct ErrInfo { u32 flag, seq, pos, byte; };
@@ -195,19 +228,19 @@ __global__ void __launch_bounds__(1024) k_bl_offsets(const u32 *chcnt, u32 nblk,
             o += (chcnt[b * NCHUNK + c] + CHUNK_ALIGN - 1) / CHUNK_ALIGN * CHUNK_ALIGN;
         }
         choff[b * (NCHUNK + 1) + NCHUNK] = o;
-        sum += o;
+        sum += o + TAILPAD;
     }
     part[tid] = sum;
     __syncthreads();
     if (tid == 0) { u64 run = 0; for (int i = 0; i < 1024; ++i) { u64 v = part[i]; part[i] = run; run += v; } blkbase[nblk] = run; }
     __syncthreads();
     u64 run = part[tid];
-    for (u32 b = b0; b < b1; ++b) { blkbase[b] = run; run += choff[b * (NCHUNK + 1) + NCHUNK]; }
+    for (u32 b = b0; b < b1; ++b) { blkbase[b] = run; run += choff[b * (NCHUNK + 1) + NCHUNK] + TAILPAD; }
 }
 
 __global__ void __launch_bounds__(256) k_bl_scatter(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq,
                                                     const u8 *lut, int shift, const u32 *chcnt, const u32 *choff,
-                                                    const u64 *blkbase, u64 *ent, BlockRef *refs) {
+                                                    const u64 *blkbase, u64 *ent, u32 *hi, void *lo, int lo_size, BlockRef *refs) {
     __shared__ u32 cur[NCHUNK];
     __shared__ u32 so[NCHUNK + 1];
     const u32 b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,30 +260,44 @@ __global__ void __launch_bounds__(256) k_bl_scatter(const u64 *keys, const u64 *
         }
     }
     __syncthreads();
-    // sentinel padding between the end of each chunk and the start of the next
+    // sentinel hi words between the end of each chunk and the start of the next, and after the block
+    u32 *h = hi + blkbase[b];
     for (u32 c = warp; c < NCHUNK; c += 8)
-        for (u32 i = so[c] + chcnt[b * NCHUNK + c] + lane; i < so[c + 1]; i += 32) e[i] = SENT;
+        for (u32 i = so[c] + chcnt[b * NCHUNK + c] + lane; i < so[c + 1]; i += 32) h[i] = HI_SENT;
+    for (u32 i = so[NCHUNK] + tid; i < so[NCHUNK] + TAILPAD; i += 256) h[i] = HI_SENT;
     if (tid == 0) {
-        BlockRef r; r.ent = e; r.off = choff + b * (NCHUNK + 1); r.cnt = chcnt + b * NCHUNK; r.seq0 = s0; r.nseq = s1 - s0;
+        BlockRef r; r.hi = h; r.lo = (const u8 *)lo + blkbase[b] * lo_size;
+        r.off = choff + b * (NCHUNK + 1); r.cnt = chcnt + b * NCHUNK; r.seq0 = s0; r.nseq = s1 - s0;
         refs[b] = r;
     }
 }
 
+// sort every chunk by the full entry, then store it split into hi / lo
 constexpr int SORT_SMEM_CAP = 4096;
-__global__ void __launch_bounds__(256) k_bl_sort(const BlockRef *refs) {
+__global__ void __launch_bounds__(256) k_bl_sort(const BlockRef *refs, const u64 *blkbase, u64 *ent, int lobits) {
     __shared__ __align__(16) u64 sk[SORT_SMEM_CAP];
     const u32 b = blockIdx.x / NCHUNK, c = blockIdx.x % NCHUNK, tid = threadIdx.x;
     BlockRef r = refs[b];
     u32 n = r.cnt[c];
-    if (n < 2) return;
-    u64 *g = const_cast<u64 *>(r.ent) + r.off[c];
+    if (n == 0) return;
+    u64 *g = ent + blkbase[b] + r.off[c];
+    u64 *src = g;
     if (n <= SORT_SMEM_CAP) {
         for (u32 i = tid; i < n; i += 256) sk[i] = g[i];
         __syncthreads();
         bitonic_sort(sk, n, tid, 256);
-        for (u32 i = tid; i < n; i += 256) g[i] = sk[i];
+        src = sk;
     } else {
         bitonic_sort(g, n, tid, 256);   // rare: very long sequences; in place in global memory
+    }
+    u32 *h = const_cast<u32 *>(r.hi) + r.off[c];
+    const u64 lomask = (1ull << lobits) - 1;
+    if (lobits <= 16) {
+        u16 *l = reinterpret_cast<u16 *>(const_cast<void *>(r.lo)) + r.off[c];
+        for (u32 i = tid; i < n; i += 256) { u64 e = src[i]; h[i] = (u32)(e >> lobits); l[i] = (u16)(e & lomask); }
+    } else {
+        u32 *l = reinterpret_cast<u32 *>(const_cast<void *>(r.lo)) + r.off[c];
+        for (u32 i = tid; i < n; i += 256) { u64 e = src[i]; h[i] = (u32)(e >> lobits); l[i] = (u32)(e & lomask); }
     }
 }
 
@@ -316,181 +363,290 @@ __device__ __forceinline__ u64 cell_index(u32 layout, u64 i, u64 j, u64 nrows, u
 
 __device__ __noinline__ bool seq_equal(const SeqMeta &a, const SeqMeta &b) {
     if (a.len != b.len || a.hash != b.hash) return false;
+    if (a.res == b.res) return true;   // the same stored sequence (diagonal cells)
     for (u32 i = 0; i < a.len; ++i) if (a.res[i] != b.res[i]) return false;
     return true;
 }
 
-// all matches of the staged A entries against the staged B entries -> count tile
-__device__ __forceinline__ void join_job(const u64 *__restrict__ sA, u32 na, const u64 *__restrict__ sB, u32 nb,
-                                         u32 *cnt, u32 warp, u32 lane) {
-    for (u32 base = warp * 32; base < na; base += NCWARP * 32) {
-        u32 idx = base + lane;
-        if (idx < na) {
-            u64 e = sA[idx];
-            u64 target = e & ~LID_MASK;
-            u32 a = (u32)(e & LID_MASK);
-            u32 lo = 0, len = nb;
-            while (len) {
-                u32 half = len >> 1;
-                if (sB[lo + half] < target) { lo += half + 1; len -= half + 1; } else len = half;
-            }
-            while (lo < nb) {
-                u64 v = sB[lo];
-                if ((v & ~LID_MASK) != target) break;
-                u32 b = (u32)(v & LID_MASK);
-                atomicAdd(&cnt[(a * TB + b) >> 1], (b & 1) ? 0x10000u : 1u);
-                ++lo;
+__device__ __forceinline__ u32 lds32(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ u32 lds16(u32 addr) {
+    u32 v;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <bool LO32> __device__ __forceinline__ u32 ldlo(u32 base, u32 i) { return LO32 ? lds32(base + i * 4) : lds16(base + i * 2); }
+
+// All matches of the staged A entries against the staged B sub-chunk -> count tile.
+//   * a pass is 32*ILP consecutive A entries (ILP per lane, searched together); passes are dealt to the
+//     consumer warps round-robin across job boundaries (pass counter `pc`), so consecutive jobs land on
+//     different warps and overlap instead of queueing behind the same ones;
+//   * the lower bound runs on the 32-bit hi words only.  The B window always holds WINDOW staged words and
+//     everything past the sub-chunk is >= every target of this chunk (later chunks, or sentinels), so the
+//     binary lifting needs neither a bounds check nor a clamp; the position is kept as an absolute shared
+//     address, so one probe is LDS [p+imm]; ISETP; @P IADD;
+//   * entries whose hi equals the target are then checked on the low key bits and counted.
+template <bool LO32>
+__device__ __forceinline__ void join_job(u32 sAhi, u32 sAlo, u32 na, u32 sBhi, u32 sBlo, u32 nb, u32 *cnt, u32 warp,
+                                         u32 lane, u32 pc) {
+    const u32 w = (warp + NCWARP - pc % NCWARP) % NCWARP;   // first pass of this job that falls to this warp
+    const u32 sBm = sBhi - 4;
+    for (u32 base = w * (32 * ILP); base < na; base += NCWARP * 32 * ILP) {
+        u32 th[ILP], p[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const u32 i = base + lane + 32 * u;
+            // lanes past the end search for a value no entry has (real hi words are < 0xE0000000)
+            th[u] = i < na ? lds32(sAhi + i * 4) : HI_SENT - 1;
+            p[u] = sBm;
+        }
+#pragma unroll
+        for (u32 step = STEP_TOP; step; step >>= 1) {
+            u32 v[ILP];
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) v[u] = lds32(p[u] + step * 4);
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) if (v[u] < th[u]) p[u] += step * 4;
+        }
+        // p[u] + 4 is the address of the lower-bound entry: a hit needs equal hi words inside the sub-chunk
+        bool hit = false;
+        u32 hv[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) hv[u] = lds32(p[u] + 4);
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) hit |= (hv[u] == th[u]) & (p[u] - sBm < nb * 4);
+        if (__any_sync(0xffffffffu, hit)) {   // rare for unrelated sequences: whole warp skips otherwise
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                u32 idx = (p[u] - sBm) >> 2;
+                if (hv[u] == th[u] && idx < nb) {
+                    const u32 al = ldlo<LO32>(sAlo, base + lane + 32 * u);
+                    const u32 a = al & (u32)LID_MASK;
+                    do {
+                        const u32 bl = ldlo<LO32>(sBlo, idx);
+                        if ((bl >> LID_BITS) == (al >> LID_BITS)) {
+                            const u32 b = bl & (u32)LID_MASK;
+                            atomicAdd(&cnt[(a * TB + b) >> 1], (b & 1) ? 0x10000u : 1u);
+                        }
+                        ++idx;
+                    } while (idx < nb && lds32(sBhi + idx * 4) == th[u]);
+                }
             }
         }
     }
 }
 
-template <int MODE>
+// Job flags published by the producer with every pipeline slot
+constexpr u32 JF_TILE_END = 1;   // slot carries no data: tile (I,J) is complete, run its epilogue
+constexpr u32 JF_TASK_END = 2;   // ... and it was the last J of the task
+constexpr u32 JF_DONE = 4;       // no more work for this CTA
+
+// The kernel is warp-specialised.  Warp NCWARP is the producer: it alone walks tasks -> tiles -> chunk pairs ->
+// sub-chunks, and for every job waits for a free stage, publishes a 16-byte descriptor (na, nb, flags, J) and
+// issues the four TMA bulk copies that complete the stage's full barrier.  The NCWARP consumer warps only wait
+// on full barriers, read the descriptor and search; they meet at a named barrier twice per tile (epilogue).
+template <int MODE, bool LO32>
 __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
     extern __shared__ __align__(128) u8 smem[];
+    constexpr int NST = nstage(LO32);
+    constexpr u32 LOSZ = LO32 ? 4 : 2;
+    constexpr u32 STAGE_B = (u32)stage_bytes(LO32);
+    constexpr u32 OFF_BHI = STAGE_CAP * 4, OFF_ALO = OFF_BHI + WINDOW * 4, OFF_BLO = OFF_ALO + STAGE_CAP * LOSZ;
     u32 *cnt = reinterpret_cast<u32 *>(smem);
-    u64 *stage = reinterpret_cast<u64 *>(smem + JOIN_SMEM_CNT);
-    u64 *full = reinterpret_cast<u64 *>(smem + JOIN_SMEM_CNT + JOIN_SMEM_STAGE);
-    u64 *empty = full + NSTAGE;
+    u8 *stage = smem + JOIN_SMEM_CNT;
+    u64 *full = reinterpret_cast<u64 *>(smem + JOIN_SMEM_CNT + (size_t)NST * STAGE_B);
+    u64 *empty = full + NST;
+    uint4 *desc = reinterpret_cast<uint4 *>(empty + NST);   // 2*NST barriers of 8 bytes: 16-byte aligned
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool producer = warp == NCWARP;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCWARP); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCWARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     for (u32 i = tid; i < TB * TB / 2; i += JOIN_THREADS) cnt[i] = 0;
     __syncthreads();
 
-    u32 k = 0;   // pipeline job counter; producer and consumers enumerate the same jobs
-    for (u32 task = blockIdx.x; task < p.ntasks; task += gridDim.x) {
-        uint2 tk = p.tasks[task];
-        const u32 I = tk.x;
-        u32 j0, j1;
-        if (MODE == MODE_MATRIX) { j0 = tk.y; j1 = tk.y + 1; }
-        else { j0 = (u32)((u64)tk.y * p.nBblk / p.nsplit); j1 = (u32)((u64)(tk.y + 1) * p.nBblk / p.nsplit); }
-        const BlockRef a = p.A[I];
-        // ARGMAX: row r of the tile is owned by warp r%16, its running best lives in lane r/16
-        int best_sim = 0; u32 best_first = 0xFFFFFFFFu, best_last = 0;
-
-        for (u32 J = j0; J < j1; ++J) {
-            const BlockRef b = p.B[J];
-            for (int c = 0; c < NCHUNK; ++c) {
-                const u32 nAc = __ldg(a.cnt + c), nBc = __ldg(b.cnt + c);
-                if (nAc == 0 || nBc == 0) continue;
-                const u64 *gA = a.ent + __ldg(a.off + c), *gB = b.ent + __ldg(b.off + c);
-                for (u32 as = 0; as < nAc; as += STAGE_CAP) {
-                    const u32 na = min((u32)STAGE_CAP, nAc - as);
-                    for (u32 bs = 0; bs < nBc; bs += STAGE_CAP) {
-                        const u32 nb = min((u32)STAGE_CAP, nBc - bs);
-                        const u32 s = k % NSTAGE, ph = (k / NSTAGE) & 1;
-                        u64 *sA = stage + (size_t)s * 2 * STAGE_CAP, *sB = sA + STAGE_CAP;
-                        if (producer) {
-                            if (lane == 0) {
-                                mbar_wait(&empty[s], ph ^ 1);
-                                const u32 bytesA = ((na + 1) & ~1u) * 8, bytesB = ((nb + 1) & ~1u) * 8;
-                                mbar_expect_tx(&full[s], bytesA + bytesB);
-                                bulk_g2s(sA, gA + as, bytesA, &full[s]);
-                                bulk_g2s(sB, gB + bs, bytesB, &full[s]);
-                            }
-                        } else {
-                            mbar_wait(&full[s], ph);
-                            join_job(sA, na, sB, nb, cnt, warp, lane);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&empty[s]);
-                        }
-                        ++k;
-                    }
-                }
-            }
-            if (producer) continue;
-            // ---- epilogue of tile (I,J): consumers only -------------------------------------
-            consumer_bar();
-            const bool ident_inf = (p.flags & 1u) != 0;
-            for (u32 row = warp; row < a.nseq; row += NCWARP) {
-                uint4 *rp = reinterpret_cast<uint4 *>(cnt + row * (TB / 2)) + lane;
-                uint4 v = *rp;
-                *rp = make_uint4(0, 0, 0, 0);
-                int cv[8] = {(int)(v.x & 0xFFFF), (int)(v.x >> 16), (int)(v.y & 0xFFFF), (int)(v.y >> 16),
-                             (int)(v.z & 0xFFFF), (int)(v.z >> 16), (int)(v.w & 0xFFFF), (int)(v.w >> 16)};
-                const u32 i = a.seq0 + row;
-                const u32 jb = b.seq0 + lane * 8;      // first column of this lane
-                if (ident_inf) {
-                    const u32 szA = p.metaA[i].size;
-                    bool cand = false;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) cand |= (cv[t] == (int)szA) && (lane * 8 + t < b.nseq);
-                    if (cand) {
-                        const SeqMeta ma = p.metaA[i];
-                        for (int t = 0; t < 8; ++t)
-                            if (cv[t] == (int)szA && lane * 8 + t < b.nseq) {
-                                const SeqMeta mb = p.metaB[jb + t];
-                                if (mb.size == szA && seq_equal(ma, mb)) cv[t] = KR_INF;
-                            }
-                    }
-                }
-                if (MODE == MODE_MATRIX) {
-                    const u64 N = p.nA, M = p.nB;
-                    // valid columns of this row inside the tile
-                    u32 jlo = b.seq0, jhi = b.seq0 + b.nseq;
-                    if (p.layout == 1 && jlo < i + 1) jlo = i + 1;
-                    if (jlo < jhi && jb + 8 > jlo && jb < jhi) {
-                        const u32 ja = max(jb, jlo);
-                        const u64 idx = cell_index(p.layout, i, ja, N, M) - p.origin - (ja - jb);  // index of column jb
-                        const bool fullv = jb >= jlo && jb + 8 <= jhi;
-                        if (p.elem == 1) {
-                            u16 *o = reinterpret_cast<u16 *>(p.out) + idx;
-                            if (fullv && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                                uint4 w;
-                                w.x = (u32)cv[0] | ((u32)cv[1] << 16); w.y = (u32)cv[2] | ((u32)cv[3] << 16);
-                                w.z = (u32)cv[4] | ((u32)cv[5] << 16); w.w = (u32)cv[6] | ((u32)cv[7] << 16);
-                                *reinterpret_cast<uint4 *>(o) = w;
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < 8; ++t) if (jb + t >= jlo && jb + t < jhi) o[t] = (u16)cv[t];
-                            }
-                        } else {
-                            int *o = reinterpret_cast<int *>(p.out) + idx;
-                            if (fullv && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                                reinterpret_cast<int4 *>(o)[0] = make_int4(cv[0], cv[1], cv[2], cv[3]);
-                                reinterpret_cast<int4 *>(o)[1] = make_int4(cv[4], cv[5], cv[6], cv[7]);
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < 8; ++t) if (jb + t >= jlo && jb + t < jhi) o[t] = cv[t];
-                            }
-                        }
-                    }
+    if (warp == NCWARP) {
+        // ================================ producer ================================================
+        u32 k = 0;
+        auto emit = [&](u32 na, u32 nb, u32 flags, u32 J, const BlockRef &a, const BlockRef &b, u32 posA, u32 posB) {
+            const u32 s = k % NST, ph = (k / NST) & 1;
+            if (lane == 0) {
+                u8 *st = stage + (size_t)s * STAGE_B;
+                mbar_wait(&empty[s], ph ^ 1);
+                desc[s] = make_uint4(na, nb, flags, J);
+#if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 4)
+                if (p.nA != 0xFFFFFFFFu) { mbar_arrive(&full[s]); } else
+#endif
+                if (na) {
+                    const u32 bAhi = ((na + 3) & ~3u) * 4, bAlo = LO32 ? ((na + 3) & ~3u) * 4 : ((na + 7) & ~7u) * 2;
+                    const u32 bBlo = LO32 ? ((nb + 3) & ~3u) * 4 : ((nb + 7) & ~7u) * 2;
+                    mbar_expect_tx(&full[s], bAhi + WINDOW * 4 + bAlo + bBlo);
+                    bulk_g2s(st, a.hi + posA, bAhi, &full[s]);
+                    bulk_g2s(st + OFF_BHI, b.hi + posB, WINDOW * 4, &full[s]);
+                    bulk_g2s(st + OFF_ALO, (const u8 *)a.lo + (size_t)posA * LOSZ, bAlo, &full[s]);
+                    bulk_g2s(st + OFF_BLO, (const u8 *)b.lo + (size_t)posB * LOSZ, bBlo, &full[s]);
                 } else {
-                    // row maximum with first/last rank among the maxima
-                    int m = 0;
+                    mbar_arrive(&full[s]);
+                }
+            }
+            ++k;
+        };
+        static_assert(NCHUNK == 64 || NCHUNK == 32, "chunk tables are held as one or two registers per lane");
+        constexpr int HI = NCHUNK > 32 ? 32 : 0;   // offset of the second table register (unused for 32 chunks)
+        BlockRef a{}, b{};
+        for (u32 task = blockIdx.x; task < p.ntasks; task += gridDim.x) {
+            const uint2 tk = p.tasks[task];
+            u32 j0, j1;
+            if (MODE == MODE_MATRIX) { j0 = tk.y; j1 = tk.y + 1; }
+            else { j0 = (u32)((u64)tk.y * p.nBblk / p.nsplit); j1 = (u32)((u64)(tk.y + 1) * p.nBblk / p.nsplit); }
+            a = p.A[tk.x];
+            // chunk tables live in registers (lane c%32 holds chunk c) and are broadcast by shuffle
+            const u32 tAc0 = __ldg(a.cnt + lane), tAc1 = __ldg(a.cnt + HI + lane), tAo0 = __ldg(a.off + lane), tAo1 = __ldg(a.off + HI + lane);
+            for (u32 J = j0; J < j1; ++J) {
+                b = p.B[J];
+                const u32 tBc0 = __ldg(b.cnt + lane), tBc1 = __ldg(b.cnt + HI + lane), tBo0 = __ldg(b.off + lane), tBo1 = __ldg(b.off + HI + lane);
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const u32 nAc = __shfl_sync(0xffffffffu, c < 32 ? tAc0 : tAc1, c & 31);
+                    const u32 nBc = __shfl_sync(0xffffffffu, c < 32 ? tBc0 : tBc1, c & 31);
+                    if (nAc == 0 || nBc == 0) continue;
+                    const u32 oA = __shfl_sync(0xffffffffu, c < 32 ? tAo0 : tAo1, c & 31);
+                    const u32 oB = __shfl_sync(0xffffffffu, c < 32 ? tBo0 : tBo1, c & 31);
+                    for (u32 as = 0; as < nAc; as += STAGE_CAP)
+                        for (u32 bs = 0; bs < nBc; bs += STAGE_CAP)
+                            emit(min((u32)STAGE_CAP, nAc - as), min((u32)STAGE_CAP, nBc - bs), 0, J, a, b, oA + as, oB + bs);
+                }
+                emit(0, 0, JF_TILE_END | (J + 1 == j1 ? JF_TASK_END : 0), J, a, b, 0, 0);
+            }
+        }
+        emit(0, 0, JF_DONE, 0, a, b, 0, 0);
+        return;
+    }
+
+    // ==================================== consumers ===============================================
+    u32 k = 0, pc = 0;
+    u32 task = blockIdx.x;
+    // ARGMAX: row r of the tile is owned by warp r%NCWARP, its running best lives in lane r/NCWARP
+    int best_sim = 0; u32 best_first = 0xFFFFFFFFu, best_last = 0;
+    for (;;) {
+        const u32 s = k % NST, ph = (k / NST) & 1;
+        mbar_wait(&full[s], ph);
+        const uint4 d = desc[s];
+        if (d.x) {
+            const u32 sb = smem_u32(stage + (size_t)s * STAGE_B);
+#if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 1)
+            if (p.nA == 0xFFFFFFFFu)
+#endif
+            join_job<LO32>(sb, sb + OFF_ALO, d.x, sb + OFF_BHI, sb + OFF_BLO, d.y, cnt, warp, lane, pc);
+            pc += (d.x + 32 * ILP - 1) / (32 * ILP);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        ++k;
+        if (d.z & JF_DONE) break;
+        if (!(d.z & JF_TILE_END)) continue;
+
+        // ---- epilogue of tile (I,J) ----------------------------------------------------------
+        const BlockRef a = p.A[p.tasks[task].x];
+        const BlockRef b = p.B[d.w];
+        const bool ident_inf = (p.flags & 1u) != 0;
+        // sizes of this warp's rows, one per lane (row warp + NCWARP*lane), fetched together
+        u32 my_szA = 0;
+        if (ident_inf && warp + NCWARP * lane < a.nseq) my_szA = p.metaA[a.seq0 + warp + NCWARP * lane].size;
+        consumer_bar();
+        for (u32 row = warp; row < a.nseq; row += NCWARP) {
+            uint4 *rp = reinterpret_cast<uint4 *>(cnt + row * (TB / 2)) + lane;
+            uint4 v = *rp;
+            *rp = make_uint4(0, 0, 0, 0);
+            int cv[8] = {(int)(v.x & 0xFFFF), (int)(v.x >> 16), (int)(v.y & 0xFFFF), (int)(v.y >> 16),
+                         (int)(v.z & 0xFFFF), (int)(v.z >> 16), (int)(v.w & 0xFFFF), (int)(v.w >> 16)};
+            const u32 i = a.seq0 + row;
+            const u32 jb = b.seq0 + lane * 8;      // first column of this lane
+            if (ident_inf) {
+                const u32 szA = __shfl_sync(0xffffffffu, my_szA, row / NCWARP);
+                bool cand = false;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) if (lane * 8 + t < b.nseq) m = max(m, cv[t]);
-                    int wm = m;
-                    for (int o = 16; o > 0; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-                    if (wm > 0) {
-                        u32 rf = 0xFFFFFFFFu, rl = 0;
-                        if (m == wm) {
+                for (int t = 0; t < 8; ++t) cand |= (cv[t] == (int)szA) && (lane * 8 + t < b.nseq);
+                if (cand) {
+                    const SeqMeta ma = p.metaA[i];
+                    for (int t = 0; t < 8; ++t)
+                        if (cv[t] == (int)szA && lane * 8 + t < b.nseq) {
+                            const SeqMeta mb = p.metaB[jb + t];
+                            if (mb.size == szA && seq_equal(ma, mb)) cv[t] = KR_INF;
+                        }
+                }
+            }
+#if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 2)
+            if (p.nA == 0xFFFFFFFFu)
+#endif
+            if (MODE == MODE_MATRIX) {
+                const u64 N = p.nA, M = p.nB;
+                // valid columns of this row inside the tile
+                u32 jlo = b.seq0, jhi = b.seq0 + b.nseq;
+                if (p.layout == 1 && jlo < i + 1) jlo = i + 1;
+                if (jlo < jhi && jb + 8 > jlo && jb < jhi) {
+                    const u32 ja = max(jb, jlo);
+                    const u64 idx = cell_index(p.layout, i, ja, N, M) - p.origin - (ja - jb);  // index of column jb
+                    const bool fullv = jb >= jlo && jb + 8 <= jhi;
+                    if (p.elem == 1) {
+                        u16 *o = reinterpret_cast<u16 *>(p.out) + idx;
+                        if (fullv && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                            uint4 w;
+                            w.x = (u32)cv[0] | ((u32)cv[1] << 16); w.y = (u32)cv[2] | ((u32)cv[3] << 16);
+                            w.z = (u32)cv[4] | ((u32)cv[5] << 16); w.w = (u32)cv[6] | ((u32)cv[7] << 16);
+                            *reinterpret_cast<uint4 *>(o) = w;
+                        } else {
 #pragma unroll
-                            for (int t = 0; t < 8; ++t)
-                                if (lane * 8 + t < b.nseq && cv[t] == wm) { u32 rk = __ldg(p.rankB + jb + t); rf = min(rf, rk); rl = max(rl, rk); }
+                            for (int t = 0; t < 8; ++t) if (jb + t >= jlo && jb + t < jhi) o[t] = (u16)cv[t];
                         }
-                        for (int o = 16; o > 0; o >>= 1) {
-                            rf = min(rf, __shfl_xor_sync(0xffffffffu, rf, o));
-                            rl = max(rl, __shfl_xor_sync(0xffffffffu, rl, o));
-                        }
-                        if (lane == (row >> 4)) {
-                            if (wm > best_sim) { best_sim = wm; best_first = rf; best_last = rl; }
-                            else if (wm == best_sim) { best_first = min(best_first, rf); best_last = max(best_last, rl); }
+                    } else {
+                        int *o = reinterpret_cast<int *>(p.out) + idx;
+                        if (fullv && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                            reinterpret_cast<int4 *>(o)[0] = make_int4(cv[0], cv[1], cv[2], cv[3]);
+                            reinterpret_cast<int4 *>(o)[1] = make_int4(cv[4], cv[5], cv[6], cv[7]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) if (jb + t >= jlo && jb + t < jhi) o[t] = cv[t];
                         }
                     }
                 }
+            } else {
+                // row maximum with first/last rank among the maxima
+                int m = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) if (lane * 8 + t < b.nseq) m = max(m, cv[t]);
+                int wm = m;
+                for (int o = 16; o > 0; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+                if (wm > 0) {
+                    u32 rf = 0xFFFFFFFFu, rl = 0;
+                    if (m == wm) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (lane * 8 + t < b.nseq && cv[t] == wm) { u32 rk = __ldg(p.rankB + jb + t); rf = min(rf, rk); rl = max(rl, rk); }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        rf = min(rf, __shfl_xor_sync(0xffffffffu, rf, o));
+                        rl = max(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+                    }
+                    if (lane == row / NCWARP) {
+                        if (wm > best_sim) { best_sim = wm; best_first = rf; best_last = rl; }
+                        else if (wm == best_sim) { best_first = min(best_first, rf); best_last = max(best_last, rl); }
+                    }
+                }
             }
-            consumer_bar();
         }
-        if (MODE == MODE_ARGMAX && !producer) {
-            const u32 row = warp + 16 * lane;
-            if (lane < 16 && row < a.nseq) p.partial[(size_t)task * TB + row] = make_int4(best_sim, (int)best_first, (int)best_last, 0);
+        consumer_bar();
+        if (d.z & JF_TASK_END) {
+            if (MODE == MODE_ARGMAX) {
+                const u32 row = warp + NCWARP * lane;
+                if (row < a.nseq) p.partial[(size_t)task * TB + row] = make_int4(best_sim, (int)best_first, (int)best_last, 0);
+                best_sim = 0; best_first = 0xFFFFFFFFu; best_last = 0;
+            }
+            task += gridDim.x;
         }
     }
 }
