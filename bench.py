@@ -137,8 +137,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nseq", type=int, default=100000)
-    ap.add_argument("--ref-sample", type=int, default=6000)
-    ap.add_argument("--cpu-sample", type=int, default=5000)
+    ap.add_argument("--ref-sample", type=int, default=10000)
+    ap.add_argument("--cpu-sample", type=int, default=16000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

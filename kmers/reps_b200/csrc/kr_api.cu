@@ -24,14 +24,16 @@ enum { ST_ENCODE = 0, ST_BLOCKLIST = 1, ST_JOIN = 2, ST_OTHER = 3 };
 
 struct DevMem {   // refcounted device allocation (residue buffers are shared by gathered sets)
     void *p = nullptr;
-    ~DevMem() { if (p) cudaFree(p); }
+    cudaStream_t stream = nullptr;
+    ~DevMem() { if (p) cudaFreeAsync(p, stream); }   // stream-ordered: safe after every kernel already queued
 };
 
 struct kr_ctx {
     int dev = 0, K = 8;
     u32 flags = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     std::mutex mu;
     std::string err;
     u8 *d_lut = nullptr;
@@ -173,6 +175,11 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
 #define CUC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(nullptr, KR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); delete ctx; return KR_ERR_CUDA; } } while (0)
     CUC(cudaSetDevice(device));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUC(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    }
     cudaMemPool_t pool;
     CUC(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long keep = ~0ull;
@@ -201,6 +208,8 @@ void kr_destroy(kr_ctx *ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_err);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -285,8 +294,7 @@ static void seqset_destroy(kr_seqset *s) {
     cudaSetDevice(ctx->dev);
     dfree(ctx, s->d_off); dfree(ctx, s->d_koff); dfree(ctx, s->d_keys); dfree(ctx, s->d_meta);
     dfree(ctx, s->d_hi); dfree(ctx, (u8 *)s->d_lo); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
-    if (s->res || !s->keep.empty()) cudaStreamSynchronize(ctx->stream);   // residue buffers use cudaFree
-    delete s;
+    delete s;   // residue buffers are released stream-ordered by ~DevMem
 }
 
 static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, const u64 *offsets, u32 nseq, kr_seqset **out) {
@@ -311,7 +319,8 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
     std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
     s->ctx = ctx; s->n = nseq; s->key_cap = kc;
     s->res = std::make_shared<DevMem>();
-    CU(cudaMalloc(&s->res->p, total + 16));
+    s->res->stream = ctx->stream;
+    CU(cudaMallocAsync(&s->res->p, total + 16, ctx->stream));
     if (on_device) CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyDeviceToDevice, ctx->stream));
     else { CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream)); ctx->st.h2d_bytes += total; }
     CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_koff, nseq + 1));
@@ -750,21 +759,43 @@ kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, con
     if (st) return st;
     if (!out_host) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix: null output");
     CU(cudaSetDevice(ctx->dev));
-    bool self = (B == nullptr || B == A);
-    u32 ncols = self ? A->n : B->n;
-    u64 elems = kr_matrix_elems(A->n, ncols, desc->layout, desc->row_begin, desc->row_end);
-    size_t esz = desc->elem == KR_ELEM_U16 ? 2 : 4;
-    if (!elems) return KR_OK;
-    u8 *d_out = nullptr;
-    CU(dalloc(ctx, &d_out, elems * esz + 16));
-    st = matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, d_out);
-    if (st == KR_OK) {
-        cudaError_t e = cudaMemcpyAsync(out_host, d_out, elems * esz, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "matrix copy to host failed: %s", cudaGetErrorString(e));
+    const bool self = (B == nullptr || B == A);
+    const u32 ncols = self ? A->n : B->n;
+    const size_t esz = desc->elem == KR_ELEM_U16 ? 2 : 4;
+    if (!kr_matrix_elems(A->n, ncols, desc->layout, desc->row_begin, desc->row_end)) return KR_OK;
+    // Row stripes of a few hundred MB are computed into two device buffers in turn while the previous stripe
+    // travels to the host on the copy stream, so the D2H of a large matrix overlaps the join.
+    const u64 target = 256ull << 20;
+    u64 per_blockrow = (u64)TB * ncols * esz;
+    u32 stripe_rows = (u32)std::max<u64>(1, target / std::max<u64>(per_blockrow, 1)) * TB;
+    u64 max_elems = 0;
+    for (u32 r = desc->row_begin; r < desc->row_end; r += stripe_rows)
+        max_elems = std::max<u64>(max_elems, kr_matrix_elems(A->n, ncols, desc->layout, r, std::min(desc->row_end, r + stripe_rows)));
+    u8 *d_buf[2] = {nullptr, nullptr};
+    CU(dalloc(ctx, &d_buf[0], max_elems * esz + 16));
+    CU(dalloc(ctx, &d_buf[1], max_elems * esz + 16));
+    CU(cudaStreamSynchronize(ctx->stream));   // the buffers exist before the copy stream touches them
+    u64 done_elems = 0;
+    int k = 0;
+    for (u32 r = desc->row_begin; r < desc->row_end && st == KR_OK; r += stripe_rows, ++k) {
+        const int b = k & 1;
+        kr_matrix_desc sub = *desc;
+        sub.row_begin = r; sub.row_end = std::min(desc->row_end, r + stripe_rows);
+        const u64 elems = kr_matrix_elems(A->n, ncols, desc->layout, sub.row_begin, sub.row_end);
+        if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));   // buffer b has left for the host
+        st = matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, &sub, d_buf[b]);
+        if (st) break;
+        CU(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        CU(cudaMemcpyAsync((u8 *)out_host + done_elems * esz, d_buf[b], elems * esz, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        done_elems += elems;
         ctx->st.d2h_bytes += elems * esz;
     }
-    dfree(ctx, d_out);
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess && st == KR_OK) st = fail(ctx, KR_ERR_CUDA, "matrix copy to host failed: %s", cudaGetErrorString(e));
+    dfree(ctx, d_buf[0]); dfree(ctx, d_buf[1]);
     return st;
 }
 
