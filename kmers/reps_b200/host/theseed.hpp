@@ -1,0 +1,632 @@
+// theseed.hpp -- C++17 host-side mirror of the reference's Java classes for the protein k-mer path.
+//
+// The reference's host language is Java; this image has no JDK, so the host side above the C ABI
+// (include/kmersreps.h) is written in C++ with the reference's names, argument meaning and error
+// behaviour, so that callers (tools.cpp) read like the reference's processors:
+//
+//   org.theseed.sequence.Sequence / FastaInputStream / FastaOutputStream
+//   org.theseed.sequence.SequenceKmers / ProteinKmers      (similarity, distance, size, INFINITY, static K)
+//   org.theseed.proteins.kmers.reps.RepGenome / RepGenomeDb / RepGenomeDb.Representation
+//   org.theseed.proteins.kmers.KmerCollectionGroup
+//
+// All of them live in the un-vendored org.theseed:shared:1.0.0 (reference pom.xml:80-94); each member
+// below cites the reference call site that fixes its meaning.  Similarities are ALWAYS computed by
+// libkmersreps_cuda.so; there is no CPU path here.  Batched overloads (findClosest(vector), checkGenomes,
+// SimilarityMatrix) are the additions the rewritten loops call.
+#pragma once
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <regex>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/kmersreps.h"
+
+namespace theseed {
+
+// ---------------------------------------------------------------------------------------------------
+// java.* behaviours the outputs depend on
+namespace java {
+
+inline uint32_t string_hash(const std::string &s) {   // String.hashCode()
+    uint32_t h = 0;
+    for (unsigned char c : s) h = 31u * h + c;
+    return h;
+}
+
+// Iteration order of java.util.HashMap<String,V> (OpenJDK 8+): RepGenomeDb stores its representatives in
+// one keyed by genome id, so save(), every `for (RepGenome rep : repDb)` loop and the tie-breaking of
+// findClosest inherit this order (data/rep50.db is in exactly this order).
+// Tree bins (a 9th key in one bucket at capacity >= 64) are detected and refused, not emulated.
+class HashMapOrder {
+  public:
+    // returns the insertion index of the key (existing or new); *is_new tells which
+    int put(const std::string &key, bool *is_new = nullptr) {
+        auto it = index_.find(key);
+        if (it != index_.end()) { if (is_new) *is_new = false; return it->second; }
+        if (is_new) *is_new = true;
+        int id = (int)keys_.size();
+        uint32_t h = string_hash(key); h ^= h >> 16;
+        keys_.push_back(key); hash_.push_back(h); alive_.push_back(1);
+        index_[key] = id;
+        if (table_.empty()) { table_.assign(16, {}); threshold_ = 12; }
+        auto &bin = table_[h & (table_.size() - 1)];
+        size_t depth = bin.size();
+        bin.push_back(id);
+        if (depth >= 8) {
+            if (table_.size() < 64) resize();
+            else throw std::runtime_error("java.util.HashMap would build a tree bin for key " + key + "; not emulated");
+        }
+        if (++size_ > threshold_) resize();
+        return id;
+    }
+    bool contains(const std::string &key) const { return index_.count(key) != 0; }
+    int find(const std::string &key) const { auto it = index_.find(key); return it == index_.end() ? -1 : it->second; }
+    void remove(const std::string &key) {   // Iterator.remove(): unlink, no reordering
+        auto it = index_.find(key);
+        if (it == index_.end()) return;
+        int id = it->second;
+        auto &bin = table_[hash_[id] & (table_.size() - 1)];
+        bin.erase(std::find(bin.begin(), bin.end(), id));
+        alive_[id] = 0; index_.erase(it); --size_;
+    }
+    size_t size() const { return size_; }
+    std::vector<int> order() const {   // insertion indices in iteration order
+        std::vector<int> o; o.reserve(size_);
+        for (auto &bin : table_) for (int id : bin) o.push_back(id);
+        return o;
+    }
+  private:
+    void resize() {
+        size_t ocap = table_.size();
+        std::vector<std::vector<int>> nt(ocap * 2);
+        for (size_t j = 0; j < ocap; ++j)
+            for (int id : table_[j]) nt[(hash_[id] & ocap) ? j + ocap : j].push_back(id);   // lo/hi split keeps order
+        table_.swap(nt);
+        threshold_ *= 2;
+    }
+    std::vector<std::string> keys_;
+    std::vector<uint32_t> hash_;
+    std::vector<char> alive_;
+    std::unordered_map<std::string, int> index_;
+    std::vector<std::vector<int>> table_;
+    size_t size_ = 0, threshold_ = 0;
+};
+
+// String.format("%<width>.<prec>f", x): Java rounds the shortest round-trip decimal of the double HALF_UP,
+// unlike C printf (exact binary value, half-even).  DistanceMatrixProcessor.java:82 (%8.6f),
+// GtoRepGenomeProcessor.java (%8.4f), ClassifyProcessor.java:117 (%12.8f).
+inline std::string format_fixed(double x, int width, int prec) {
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::fixed);   // shortest repr, fixed notation
+    std::string s(buf, r.ptr);
+    bool neg = !s.empty() && s[0] == '-';
+    if (neg) s.erase(0, 1);
+    size_t dot = s.find('.');
+    std::string ip = dot == std::string::npos ? s : s.substr(0, dot);
+    std::string fp = dot == std::string::npos ? "" : s.substr(dot + 1);
+    bool up = (int)fp.size() > prec && fp[prec] >= '5';
+    fp.resize(prec, '0');
+    std::string digits = ip + fp;
+    if (up) {
+        int i = (int)digits.size() - 1;
+        while (i >= 0 && digits[i] == '9') digits[i--] = '0';
+        if (i >= 0) digits[i]++; else digits.insert(digits.begin(), '1');
+    }
+    size_t il = digits.size() - prec;
+    std::string out = digits.substr(0, il);
+    if (prec > 0) out += "." + digits.substr(il);
+    if (neg && out.find_first_not_of("0.") != std::string::npos) out = "-" + out;
+    if ((int)out.size() < width) out = std::string(width - out.size(), ' ') + out;
+    return out;
+}
+
+// Double.toString(x) (NeighborProcessor.java:225-226): shortest repr; plain for 1e-3 <= |x| < 1e7, else d.dddE[-]n
+inline std::string double_to_string(double x) {
+    if (x == 0) return std::signbit(x) ? "-0.0" : "0.0";
+    double ax = x < 0 ? -x : x;
+    char buf[64];
+    if (ax >= 1e-3 && ax < 1e7) {
+        auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::fixed);
+        std::string s(buf, r.ptr);
+        if (s.find('.') == std::string::npos) s += ".0";
+        return s;
+    }
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);
+    std::string s(buf, r.ptr);   // d.ddde+XX
+    size_t e = s.find('e');
+    std::string mant = s.substr(0, e);
+    int ex = std::atoi(s.c_str() + e + 1);
+    if (mant.find('.') == std::string::npos) mant += ".0";
+    return mant + "E" + std::to_string(ex);
+}
+
+}  // namespace java
+
+// ---------------------------------------------------------------------------------------------------
+struct Sequence {   // org.theseed.sequence.Sequence: label, comment, sequence
+    std::string label, comment, sequence;
+    const std::string &getLabel() const { return label; }
+    const std::string &getComment() const { return comment; }
+    const std::string &getSequence() const { return sequence; }
+};
+
+// Feature.genomeOf(fid) / RepGenome.getGenomeId(): the "digits.digits" of fig|G.peg.N
+inline std::string genomeOf(const std::string &fid) {
+    static const std::regex re("fig\\|(\\d+\\.\\d+)\\.");
+    std::smatch m;
+    if (std::regex_search(fid, m, re) && m.position(0) == 0) return m[1];
+    return fid;
+}
+
+class FastaInputStream {   // iterates Sequence records; a header with no sequence lines gives an empty sequence
+  public:
+    explicit FastaInputStream(std::istream &in) : in_(&in) {}
+    explicit FastaInputStream(const std::string &file) : owned_(new std::ifstream(file)), in_(owned_.get()) {
+        if (!*owned_) throw std::runtime_error("java.io.FileNotFoundException: " + file);
+    }
+    bool next(Sequence &out) {
+        std::string line;
+        if (!have_header_) {
+            while (std::getline(*in_, line)) { chomp(line); if (!line.empty() && line[0] == '>') { header_ = line; have_header_ = true; break; } }
+            if (!have_header_) return false;
+        }
+        out = Sequence();
+        size_t sp = header_.find_first_of(" \t", 1);
+        out.label = header_.substr(1, sp == std::string::npos ? std::string::npos : sp - 1);
+        if (sp != std::string::npos) { size_t b = header_.find_first_not_of(" \t", sp); if (b != std::string::npos) out.comment = trim(header_.substr(b)); }
+        have_header_ = false;
+        while (std::getline(*in_, line)) {
+            chomp(line);
+            if (!line.empty() && line[0] == '>') { header_ = line; have_header_ = true; break; }
+            out.sequence += trim(line);
+        }
+        return true;
+    }
+    std::vector<Sequence> readAll() { std::vector<Sequence> v; Sequence s; while (next(s)) v.push_back(s); return v; }
+  private:
+    static void chomp(std::string &s) { while (!s.empty() && (s.back() == '\r' || s.back() == '\n')) s.pop_back(); }
+    static std::string trim(const std::string &s) {
+        size_t a = s.find_first_not_of(" \t"), b = s.find_last_not_of(" \t");
+        return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+    }
+    std::unique_ptr<std::ifstream> owned_;
+    std::istream *in_;
+    std::string header_;
+    bool have_header_ = false;
+};
+
+class FastaOutputStream {   // ">label comment", sequence wrapped at 60, LF (format of data/rep50.db)
+  public:
+    explicit FastaOutputStream(std::ostream &out) : out_(&out) {}
+    void write(const Sequence &s) { write(s.label, s.comment, s.sequence); }
+    void write(const std::string &label, const std::string &comment, const std::string &seq) {
+        *out_ << '>' << label;
+        if (!comment.empty()) *out_ << ' ' << comment;
+        *out_ << '\n';
+        for (size_t i = 0; i < seq.size(); i += 60) *out_ << seq.substr(i, 60) << '\n';
+    }
+  private:
+    std::ostream *out_;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// The GPU engine behind the classes: one kr_ctx per k-mer size on device $KR_DEVICE (default 0).
+class KmerEngine {
+  public:
+    static kr_ctx *ctx(int K) {
+        auto &m = map();
+        auto it = m.find(K);
+        if (it != m.end()) return it->second;
+        const char *d = std::getenv("KR_DEVICE");
+        uint32_t flags = KR_IDENT_IS_INFINITY;
+        if (const char *f = std::getenv("KR_FLAGS")) flags = (uint32_t)std::atoi(f);
+        kr_ctx *c = nullptr;
+        if (kr_create(d ? std::atoi(d) : 0, K, flags, &c) != KR_OK)
+            throw std::runtime_error(std::string("kmersreps: ") + kr_last_error(nullptr));   // RuntimeException, App.java:129
+        m[K] = c;
+        return c;
+    }
+    static void check(kr_ctx *c, kr_status st) { if (st != KR_OK) throw std::runtime_error(std::string("kmersreps: ") + kr_last_error(c)); }
+  private:
+    static std::map<int, kr_ctx *> &map() { static std::map<int, kr_ctx *> m; return m; }
+};
+
+struct SetHandle {   // shared ownership of an encoded batch
+    kr_ctx *ctx; kr_seqset *set; int K;
+    SetHandle(kr_ctx *c, kr_seqset *s, int k) : ctx(c), set(s), K(k) {}
+    ~SetHandle() { kr_seqset_free(set); }
+};
+
+inline std::shared_ptr<SetHandle> encodeStrings(int K, const std::vector<const std::string *> &seqs) {
+    std::string flat; std::vector<uint64_t> off(seqs.size() + 1, 0);
+    for (size_t i = 0; i < seqs.size(); ++i) { flat += *seqs[i]; off[i + 1] = flat.size(); }
+    kr_ctx *c = KmerEngine::ctx(K);
+    kr_seqset *s = nullptr;
+    static const uint8_t none = 0;
+    KmerEngine::check(c, kr_encode(c, flat.empty() ? &none : (const uint8_t *)flat.data(), off.data(), (uint32_t)seqs.size(), &s));
+    return std::make_shared<SetHandle>(c, s, K);
+}
+
+// ---------------------------------------------------------------------------------------------------
+class SequenceKmers {
+  public:
+    static constexpr int INFINITY_ = KR_INFINITY;   // SequenceKmers.INFINITY (RepGenomeDbProcessor.java:249)
+    virtual ~SequenceKmers() = default;
+};
+
+class ProteinKmers : public SequenceKmers {
+  public:
+    static void setKmerSize(int k) { K() = k; }   // process-global, as in the reference (RepGenomeDbProcessor.java:77-80)
+    static int kmerSize() { return K(); }
+
+    ProteinKmers() = default;
+    explicit ProteinKmers(std::string protein) : protein_(std::move(protein)), k_(K()) {}   // SequenceInfo.java:47
+    const std::string &getProtein() const { return protein_; }
+
+    // number of distinct k-mers (ScoreCouplingReporter.java:73)
+    int size() const { ensure(); return (int)size_; }
+    // number of shared distinct k-mers, INFINITY for equal sequences (DistanceMatrixProcessor.java:76)
+    int similarity(const ProteinKmers &other) const {
+        ensure(); other.ensure();
+        int32_t sim = 0; uint32_t ia = idx_, ib = other.idx_;
+        KmerEngine::check(set_->ctx, kr_sim_pairs(set_->ctx, set_->set, &ia, other.set_->set, &ib, 1, &sim, nullptr));
+        return sim;
+    }
+    // Jaccard distance (SequenceInfo.java:75, DistanceMatrixProcessor.java:75)
+    double distance(const ProteinKmers &other) const { return distance(similarity(other), *this, other); }
+    static double distance(int sim, const ProteinKmers &a, const ProteinKmers &b) {   // SsuRepresentation.java:47
+        return kr_distance(sim, (uint32_t)a.size(), (uint32_t)b.size());
+    }
+    // the k-mers themselves (SequenceKmers.iterator(), TargetProcessor.java:193)
+    std::vector<std::string> kmers() const {
+        ensure();
+        std::vector<uint64_t> keys(size_ ? size_ : 1); uint32_t n = 0;
+        KmerEngine::check(set_->ctx, kr_seqset_keys(set_->set, idx_, keys.data(), (uint32_t)keys.size(), &n));
+        std::vector<std::string> out(n, std::string((size_t)k_, ' '));
+        for (uint32_t i = 0; i < n; ++i) kr_key_decode(set_->ctx, keys[i], out[i].data());
+        return out;
+    }
+
+    // Encode many objects in one launch (the constructor itself never touches the device: it is called from
+    // parallel streams, GtoRepBuildProcessor.java:127).  Objects already encoded are left alone.
+    template <class It> static void encodeBatch(It first, It last) {
+        std::vector<const ProteinKmers *> todo; std::vector<const std::string *> seqs;
+        for (It it = first; it != last; ++it) { const ProteinKmers &p = deref(*it); if (!p.set_) { todo.push_back(&p); seqs.push_back(&p.protein_); } }
+        if (todo.empty()) return;
+        int k = todo[0]->k_;
+        auto h = encodeStrings(k, seqs);
+        std::vector<uint32_t> sizes(todo.size());
+        KmerEngine::check(h->ctx, kr_seqset_sizes(h->set, sizes.data()));
+        for (size_t i = 0; i < todo.size(); ++i) { todo[i]->set_ = h; todo[i]->idx_ = (uint32_t)i; todo[i]->size_ = sizes[i]; }
+    }
+    const std::shared_ptr<SetHandle> &handle() const { ensure(); return set_; }
+    uint32_t index() const { ensure(); return idx_; }
+    int k() const { return k_; }
+
+  protected:
+    static int &K() { static int k = 8; return k; }
+    static const ProteinKmers &deref(const ProteinKmers &p) { return p; }
+    static const ProteinKmers &deref(const ProteinKmers *p) { return *p; }
+    template <class T> static const ProteinKmers &deref(const std::unique_ptr<T> &p) { return *p; }
+    template <class T> static const ProteinKmers &deref(const std::shared_ptr<T> &p) { return *p; }
+    void ensure() const { if (!set_) { const ProteinKmers *self = this; encodeBatch(&self, &self + 1); } }
+    std::string protein_;
+    int k_ = 8;
+    mutable std::shared_ptr<SetHandle> set_;
+    mutable uint32_t idx_ = 0, size_ = 0;
+};
+
+// All-vs-all similarities of a list of ProteinKmers (the rewritten double loops of
+// DistanceMatrixProcessor.java:71-76 and RepMatrixProcessor.java:88-93).
+class SimilarityMatrix {
+  public:
+    template <class It> static SimilarityMatrix compute(It first, It last) {
+        ProteinKmers::encodeBatch(first, last);
+        SimilarityMatrix m;
+        std::vector<const ProteinKmers *> v;
+        for (It it = first; it != last; ++it) v.push_back(&ref(*it));
+        m.n_ = v.size();
+        if (!m.n_) return m;
+        // gather into one set if the objects come from different batches
+        std::shared_ptr<SetHandle> h = v[0]->handle();
+        bool same = true;
+        for (size_t i = 0; i < v.size(); ++i) same = same && v[i]->handle() == h && v[i]->index() == i;
+        if (!same) { std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getProtein()); h = encodeStrings(v[0]->k(), s); }
+        m.sizes_.resize(m.n_);
+        KmerEngine::check(h->ctx, kr_seqset_sizes(h->set, m.sizes_.data()));
+        m.sim_.resize(m.n_ * m.n_);
+        kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_FULL, 0, (uint32_t)m.n_};
+        KmerEngine::check(h->ctx, kr_sim_matrix(h->ctx, h->set, nullptr, &d, m.sim_.data()));
+        return m;
+    }
+    int similarity(size_t i, size_t j) const { return sim_[i * n_ + j]; }
+    double distance(size_t i, size_t j) const { return kr_distance(sim_[i * n_ + j], sizes_[i], sizes_[j]); }
+    size_t size() const { return n_; }
+  private:
+    static const ProteinKmers &ref(const ProteinKmers &p) { return p; }
+    static const ProteinKmers &ref(const ProteinKmers *p) { return *p; }
+    template <class T> static const ProteinKmers &ref(const std::unique_ptr<T> &p) { return *p; }
+    size_t n_ = 0;
+    std::vector<int32_t> sim_;
+    std::vector<uint32_t> sizes_;
+};
+
+// ---------------------------------------------------------------------------------------------------
+class RepGenome : public ProteinKmers {   // a representative: (fid, name, protein)
+  public:
+    RepGenome() = default;
+    explicit RepGenome(const Sequence &seq) : RepGenome(seq.label, seq.comment, seq.sequence) {}   // RepGenomeDbProcessor.java:161
+    RepGenome(std::string fid, std::string name, std::string protein)                               // BaseGenomeProcessor.java:201-202
+        : ProteinKmers(std::move(protein)), fid_(std::move(fid)), name_(std::move(name)), genomeId_(genomeOf(fid_)) {}
+    const std::string &getFid() const { return fid_; }
+    const std::string &getName() const { return name_; }
+    const std::string &getGenomeId() const { return genomeId_; }
+    // used only to visit each unordered pair once (DistanceMatrixProcessor.java:74); order of genome-id strings
+    int compareTo(const RepGenome &o) const { return genomeId_.compare(o.genomeId_); }
+    std::string toString() const { return genomeId_ + " (" + name_ + ")"; }
+  private:
+    std::string fid_, name_, genomeId_;
+};
+
+class RepGenomeDb {
+  public:
+    static constexpr const char *DEFAULT_PROTEIN = "Phenylalanyl-tRNA synthetase alpha chain";   // RepGenomeDbProcessor.java:184
+
+    // RepGenomeDb.Representation (RepGenomeDbProcessor.java:237-252, GtoRepGenomeProcessor.java:271-292)
+    class Representation {
+      public:
+        Representation() = default;
+        Representation(const RepGenomeDb *db, const RepGenome *rep, int sim, double dist) : db_(db), rep_(rep), sim_(sim), dist_(dist) {}
+        int getSimilarity() const { return sim_; }
+        double getDistance() const { return dist_; }
+        const RepGenome *getRepresentative() const { return rep_; }
+        std::string getGenomeId() const { return rep_ ? rep_->getGenomeId() : std::string(); }
+        bool isRepresented() const { return db_ && sim_ >= db_->getThreshold(); }
+      private:
+        const RepGenomeDb *db_ = nullptr; const RepGenome *rep_ = nullptr; int sim_ = 0; double dist_ = 1.0;
+    };
+
+    explicit RepGenomeDb(int threshold, std::string protName = DEFAULT_PROTEIN)   // RepGenomeDbProcessor.java:122
+        : threshold_(threshold), kmerSize_(ProteinKmers::kmerSize()), protName_(std::move(protName)) {}
+    ~RepGenomeDb() { if (db_) kr_db_free(db_); }
+    RepGenomeDb(const RepGenomeDb &) = delete;
+    RepGenomeDb &operator=(const RepGenomeDb &) = delete;
+
+    int getThreshold() const { return threshold_; }
+    int getKmerSize() const { return kmerSize_; }
+    const std::string &getProtName() const { return protName_; }
+    size_t size() const { return order_.size(); }
+    bool contains(const std::string &genomeId) const { return order_.contains(genomeId); }
+    const RepGenome *get(const std::string &genomeId) const { int i = order_.find(genomeId); return i < 0 ? nullptr : reps_[i].get(); }
+    std::string getListFileName() const { return "rep" + std::to_string(threshold_) + ".list.tbl"; }   // BaseGenomeProcessor.java:357
+    std::string toString() const { return "RepGen" + std::to_string(threshold_); }
+
+    // iteration in java.util.HashMap order by genome id
+    std::vector<const RepGenome *> all() const { std::vector<const RepGenome *> v; for (int i : order_.order()) v.push_back(reps_[i].get()); return v; }
+    std::vector<const RepGenome *> sorted() const {   // SortedSet<RepGenome> (RepGenomeDbProcessor.java:214)
+        auto v = all();
+        std::sort(v.begin(), v.end(), [](const RepGenome *a, const RepGenome *b) { return a->compareTo(*b) < 0; });
+        return v;
+    }
+
+    // put(genomeId, rep): a second rep for the same genome replaces the first in place (CopyTest.java:16-27)
+    void addRep(const RepGenome &rep) {
+        bool is_new = false;
+        int id = order_.put(rep.getGenomeId(), &is_new);
+        if (is_new) reps_.push_back(std::make_unique<RepGenome>(rep));
+        else { *reps_[id] = rep; rebuild_ = true; }
+        ranks_dirty_ = true;
+    }
+    void remove(const std::string &genomeId) {   // iterator().remove() (UpdateProcessor.java:96-103)
+        if (order_.contains(genomeId)) { order_.remove(genomeId); rebuild_ = true; ranks_dirty_ = true; }
+    }
+
+    // findClosest(ProteinKmers | Sequence | RepGenome): best similarity over all reps, first strict maximum
+    // in iteration order; (0, null, 1.0) when nothing shares a k-mer (GtoRepGenomeProcessor.java:277-282)
+    Representation findClosest(const ProteinKmers &q) const { const ProteinKmers *p = &q; return findClosest(&p, &p + 1)[0]; }
+    Representation findClosest(const Sequence &seq) const { ProteinKmers q(seq.sequence); return findClosest(q); }   // RepGenomeDbProcessor.java:237
+    template <class It> std::vector<Representation> findClosest(It first, It last) const {
+        std::vector<Representation> out;
+        ProteinKmers::encodeBatch(first, last);
+        std::vector<const ProteinKmers *> v;
+        for (It it = first; it != last; ++it) v.push_back(ptr(*it));
+        if (v.empty()) return out;
+        sync();
+        auto h = batchOf(v);
+        std::vector<int32_t> sim(v.size()); std::vector<uint32_t> f(v.size()), l(v.size());
+        KmerEngine::check(ctx(), kr_db_find_closest(ctx(), db_, h->set, sim.data(), f.data(), l.data()));
+        for (size_t i = 0; i < v.size(); ++i) {
+            uint32_t pick = tie_last_ ? l[i] : f[i];
+            if (sim[i] == 0 || pick == KR_NO_REP) { out.emplace_back(this, nullptr, 0, 1.0); continue; }
+            const RepGenome *rep = reps_[dev2host_[pick]].get();
+            out.emplace_back(this, rep, sim[i], ProteinKmers::distance(sim[i], *v[i], *rep));
+        }
+        return out;
+    }
+
+    // checkSimilarity(ProteinKmers, sim): is some rep at least this similar? (BaseGenomeProcessor.java:203)
+    bool checkSimilarity(const ProteinKmers &q, int sim) const {
+        if (size() == 0) return false;
+        sync();
+        uint8_t r = 0;
+        const ProteinKmers *p = &q; auto h = batchOf(std::vector<const ProteinKmers *>{p});
+        KmerEngine::check(ctx(), kr_db_any_ge(ctx(), db_, h->set, sim, &r));
+        return r != 0;
+    }
+    // checkGenome(rep): add it unless it is represented; returns true when added (RepGenomeDbProcessor.java:162)
+    bool checkGenome(const RepGenome &rep) { std::vector<RepGenome> one{rep}; return checkGenomes(one)[0]; }
+    // the same for a list, in list order, with the exact sequential semantics (batched on the GPU)
+    std::vector<bool> checkGenomes(const std::vector<RepGenome> &cands, uint32_t batch = 0) {
+        std::vector<bool> added(cands.size(), false);
+        if (cands.empty()) return added;
+        sync();
+        ProteinKmers::encodeBatch(cands.begin(), cands.end());
+        std::vector<const ProteinKmers *> v; for (auto &c : cands) v.push_back(&c);
+        auto h = batchOf(v);
+        std::vector<uint8_t> a(cands.size());
+        KmerEngine::check(ctx(), kr_greedy_build(ctx(), db_, h->set, threshold_, batch, a.data()));
+        for (size_t i = 0; i < cands.size(); ++i)
+            if (a[i]) {
+                added[i] = true;
+                bool is_new = false;
+                int id = order_.put(cands[i].getGenomeId(), &is_new);
+                if (is_new) { reps_.push_back(std::make_unique<RepGenome>(cands[i])); dev2host_.push_back(id); }
+                else { *reps_[id] = cands[i]; rebuild_ = true; }   // duplicate genome id: replaced in place
+            }
+        synced_ = reps_.size();
+        ranks_dirty_ = true;
+        return added;
+    }
+
+    // save(File) / load(File): header ">Rep<thr>,K=<K> <protName>" with no sequence, then one record per rep
+    // in iteration order (data/rep50.db:1-8; RepGenomeDbProcessor.java:152,209)
+    void save(std::ostream &out) const {
+        out << ">Rep" << threshold_ << ",K=" << kmerSize_ << ' ' << protName_ << '\n';
+        FastaOutputStream fo(out);
+        for (const RepGenome *r : all()) fo.write(r->getFid(), r->getName(), r->getProtein());
+    }
+    void save(const std::string &file) const {
+        std::ofstream f(file, std::ios::binary);
+        if (!f) throw std::runtime_error("java.io.IOException: cannot write " + file);
+        save(f);
+    }
+    static std::unique_ptr<RepGenomeDb> load(std::istream &in) {
+        FastaInputStream fi(in);
+        Sequence hdr;
+        if (!fi.next(hdr)) throw std::runtime_error("java.io.IOException: empty representative-genome file");
+        static const std::regex re("Rep(\\d+),K=(\\d+)");
+        std::smatch m;
+        if (!std::regex_match(hdr.label, m, re)) throw std::runtime_error("java.io.IOException: invalid rep-genome header " + hdr.label);
+        ProteinKmers::setKmerSize(std::stoi(m[2]));
+        auto db = std::make_unique<RepGenomeDb>(std::stoi(m[1]), hdr.comment);
+        Sequence s;
+        while (fi.next(s)) db->addRep(RepGenome(s));
+        return db;
+    }
+    static std::unique_ptr<RepGenomeDb> load(const std::string &file) {
+        std::ifstream f(file, std::ios::binary);
+        if (!f) throw std::runtime_error("java.io.FileNotFoundException: " + file);
+        return load(f);
+    }
+    void setTieLast(bool v) { tie_last_ = v; }
+
+  private:
+    static const ProteinKmers *ptr(const ProteinKmers &p) { return &p; }
+    static const ProteinKmers *ptr(const ProteinKmers *p) { return p; }
+    kr_ctx *ctx() const { return KmerEngine::ctx(kmerSize_); }
+    // one set holding exactly these objects, in order
+    static std::shared_ptr<SetHandle> batchOf(const std::vector<const ProteinKmers *> &v) {
+        std::shared_ptr<SetHandle> h = v[0]->handle();
+        bool same = true; uint32_t n = kr_seqset_count(h->set);
+        for (size_t i = 0; i < v.size(); ++i) same = same && v[i]->handle() == h && v[i]->index() == i;
+        if (same && n == v.size()) return h;
+        std::vector<uint32_t> idx; bool one = true;
+        for (auto p : v) { one = one && p->handle() == h; idx.push_back(p->index()); }
+        if (one) {
+            kr_seqset *g = nullptr;
+            KmerEngine::check(h->ctx, kr_seqset_gather(h->ctx, h->set, idx.data(), (uint32_t)idx.size(), &g));
+            return std::make_shared<SetHandle>(h->ctx, g, h->K);
+        }
+        std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getProtein());
+        return encodeStrings(v[0]->k(), s);
+    }
+    // bring the device copy of the database up to date: append new reps, refresh iteration ranks
+    void sync() const {
+        kr_ctx *c = ctx();
+        if (rebuild_ && db_) { kr_db_free(db_); db_ = nullptr; synced_ = 0; dev2host_.clear(); }
+        if (!db_) KmerEngine::check(c, kr_db_create(c, &db_));
+        if (rebuild_) {   // replaced / removed reps: re-append the live ones
+            std::string flat; std::vector<uint64_t> off{0};
+            for (int i : order_.order()) { flat += reps_[i]->getProtein(); off.push_back(flat.size()); dev2host_.push_back(i); }
+            if (off.size() > 1) KmerEngine::check(c, kr_db_append(c, db_, (const uint8_t *)flat.data(), off.data(), (uint32_t)off.size() - 1));
+            synced_ = reps_.size(); rebuild_ = false; ranks_dirty_ = true;
+        } else if (synced_ < reps_.size()) {
+            std::string flat; std::vector<uint64_t> off{0};
+            for (size_t i = synced_; i < reps_.size(); ++i) { flat += reps_[i]->getProtein(); off.push_back(flat.size()); dev2host_.push_back((int)i); }
+            KmerEngine::check(c, kr_db_append(c, db_, (const uint8_t *)flat.data(), off.data(), (uint32_t)off.size() - 1));
+            synced_ = reps_.size(); ranks_dirty_ = true;
+        }
+        if (ranks_dirty_ && !dev2host_.empty()) {
+            std::vector<int> ord = order_.order();
+            std::vector<uint32_t> rank_of_host(reps_.size(), 0), rank(dev2host_.size());
+            for (size_t k = 0; k < ord.size(); ++k) rank_of_host[ord[k]] = (uint32_t)k;
+            for (size_t d = 0; d < dev2host_.size(); ++d) rank[d] = rank_of_host[dev2host_[d]];
+            KmerEngine::check(c, kr_db_set_ranks(c, db_, rank.data(), (uint32_t)rank.size()));
+        }
+        ranks_dirty_ = false;
+    }
+
+    int threshold_, kmerSize_;
+    std::string protName_;
+    java::HashMapOrder order_;
+    std::vector<std::unique_ptr<RepGenome>> reps_;   // by insertion index
+    mutable kr_db *db_ = nullptr;
+    mutable size_t synced_ = 0;                      // reps_[0..synced_) are on the device
+    mutable std::vector<int> dev2host_;              // device rep index -> insertion index
+    mutable bool rebuild_ = false, ranks_dirty_ = true;
+    bool tie_last_ = false;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// org.theseed.proteins.kmers.KmerCollectionGroup (ClassifyProcessor.java:95,108,116): named groups of
+// ProteinKmers; getDistance(seq, group) = smallest distance from seq to any member of the group
+// (1.0 for an unknown or empty group).
+class KmerCollectionGroup {
+  public:
+    void addSequence(const Sequence &seq, const std::string &group) { groups_[group].emplace_back(seq.sequence); dirty_.insert(group); }
+    size_t size() const { return groups_.size(); }
+    double getDistance(const Sequence &seq, const std::string &group) {
+        std::vector<std::pair<const Sequence *, std::string>> one{{&seq, group}};
+        return getDistances(one)[0];
+    }
+    // batched form: every (sequence, group) query in one pass per group
+    std::vector<double> getDistances(const std::vector<std::pair<const Sequence *, std::string>> &queries) {
+        std::vector<double> out(queries.size(), 1.0);
+        std::map<std::string, std::vector<size_t>> by_group;
+        for (size_t i = 0; i < queries.size(); ++i) by_group[queries[i].second].push_back(i);
+        for (auto &g : by_group) {
+            auto it = groups_.find(g.first);
+            if (it == groups_.end() || it->second.empty()) continue;
+            auto &members = it->second;
+            ProteinKmers::encodeBatch(members.begin(), members.end());
+            std::vector<ProteinKmers> qs;
+            for (size_t qi : g.second) qs.emplace_back(queries[qi].first->sequence);
+            ProteinKmers::encodeBatch(qs.begin(), qs.end());
+            std::vector<const std::string *> ms; for (auto &m : members) ms.push_back(&m.getProtein());
+            auto hm = members[0].handle();
+            bool same = true; for (size_t i = 0; i < members.size(); ++i) same = same && members[i].handle() == hm && members[i].index() == i;
+            if (!same || kr_seqset_count(hm->set) != members.size()) hm = encodeStrings(members[0].k(), ms);
+            auto hq = qs[0].handle();
+            std::vector<int32_t> sim(qs.size() * members.size());
+            kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_FULL, 0, (uint32_t)qs.size()};
+            KmerEngine::check(hq->ctx, kr_sim_matrix(hq->ctx, hq->set, hm->set, &d, sim.data()));
+            for (size_t q = 0; q < qs.size(); ++q) {
+                double best = 1.0;
+                for (size_t m = 0; m < members.size(); ++m)
+                    best = std::min(best, kr_distance(sim[q * members.size() + m], (uint32_t)qs[q].size(), (uint32_t)members[m].size()));
+                out[g.second[q]] = best;
+            }
+        }
+        return out;
+    }
+  private:
+    std::map<std::string, std::vector<ProteinKmers>> groups_;
+    std::set<std::string> dirty_;
+};
+
+}  // namespace theseed

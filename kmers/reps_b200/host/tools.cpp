@@ -1,0 +1,264 @@
+// tools.cpp -- the reference's hot-path commands, rewritten over the batched host classes of theseed.hpp.
+//
+//   kmers_reps repdb      RepGenomeDbProcessor.java      create / load a rep DB, report closest reps of stdin FASTA
+//   kmers_reps distances  DistanceMatrixProcessor.java   all-vs-all distances of the reps of a DB
+//   kmers_reps group      RepMatrixProcessor.java        incremental all-vs-all + greedy grouping by distance
+//   kmers_reps classify   ClassifyProcessor.java         min distance of each input sequence to its named group
+//
+// Same options, same output text.  What changed is only what north_star lists: the
+// per-pair / per-query loops became batched calls; every similarity comes from the GPU library.
+#include "theseed.hpp"
+
+#include <chrono>
+#include <cmath>
+
+using namespace theseed;
+
+static void usage() {
+    std::cerr << "usage: kmers_reps <repdb|distances|group|classify> [options]\n"
+                 "  repdb     [-m sim] [-K k] [-p role] [--create fasta] [-x maxErr] [--list file] [--stats file] [--null] [--batch n] dbFile < input.fa\n"
+                 "  distances dbFile\n"
+                 "  group     [-K k] [-i fasta] [-m maxDist]\n"
+                 "  classify  [-K k] [-i fasta] [-m maxDist] controlFile\n";
+}
+
+struct Args {
+    std::map<std::string, std::string> opt;
+    std::set<std::string> flag;
+    std::vector<std::string> pos;
+};
+// aliases -> canonical option name; value-taking options listed in `valued`
+static Args parse(int argc, char **argv, int first, const std::map<std::string, std::string> &alias, const std::set<std::string> &valued) {
+    Args a;
+    for (int i = first; i < argc; ++i) {
+        std::string s = argv[i];
+        if (s.size() > 1 && s[0] == '-' && !(s.size() > 1 && std::isdigit((unsigned char)s[1]))) {
+            auto it = alias.find(s);
+            if (it == alias.end()) throw std::runtime_error("ParseFailureException: \"" + s + "\" is not a valid option");
+            if (valued.count(it->second)) {
+                if (i + 1 >= argc) throw std::runtime_error("ParseFailureException: option " + s + " takes an operand");
+                a.opt[it->second] = argv[++i];
+            } else a.flag.insert(it->second);
+        } else a.pos.push_back(s);
+    }
+    return a;
+}
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ---- repdb (RepGenomeDbProcessor.java:119-283) ------------------------------------------------------
+static int cmd_repdb(int argc, char **argv) {
+    Args a = parse(argc, argv, 2,
+                   {{"-m", "m"}, {"--sim", "m"}, {"--minScore", "m"}, {"-K", "K"}, {"--kmer", "K"}, {"-p", "p"}, {"--prot", "p"}, {"--role", "p"},
+                    {"--create", "create"}, {"--list", "list"}, {"--stats", "stats"}, {"--null", "null"}, {"-x", "x"}, {"--maxErr", "x"},
+                    {"--dna", "dna"}, {"--batch", "batch"}, {"-v", "v"}, {"--verbose", "v"}},
+                   {"m", "K", "p", "create", "list", "stats", "x", "batch"});
+    if (a.pos.size() != 1) throw std::runtime_error("ParseFailureException: Argument \"repDbFile\" is required");
+    if (a.flag.count("dna")) throw std::runtime_error("--dna is outside the accelerated path (DnaKmers, SURVEY.md 8f-4)");
+    const std::string dbFile = a.pos[0];
+    int threshold = a.opt.count("m") ? std::stoi(a.opt["m"]) : 100;      // setDefaults :183
+    if (a.opt.count("K")) ProteinKmers::setKmerSize(std::stoi(a.opt["K"]));
+    std::string protName = a.opt.count("p") ? a.opt["p"] : RepGenomeDb::DEFAULT_PROTEIN;
+    int maxErr = a.opt.count("x") ? std::stoi(a.opt["x"]) : 20;
+    uint32_t batch = a.opt.count("batch") ? (uint32_t)std::stoul(a.opt["batch"]) : 0;
+    const bool verbose = a.flag.count("v") != 0;
+    std::unique_ptr<RepGenomeDb> repDB;
+    double t0 = now_s();
+    if (a.opt.count("create")) {
+        // createRepDb :119-153: candidates in file order, sequences with >= maxErr 'X' deferred to a second pass
+        repDB = std::make_unique<RepGenomeDb>(threshold, protName);
+        FastaInputStream in(a.opt["create"]);
+        std::vector<RepGenome> order, deferred;
+        Sequence s;
+        while (in.next(s)) {
+            long bad = std::count(s.sequence.begin(), s.sequence.end(), 'X');
+            (bad >= maxErr ? deferred : order).emplace_back(s);
+        }
+        size_t nmain = order.size();
+        for (auto &d : deferred) order.push_back(std::move(d));
+        auto added = repDB->checkGenomes(order, batch);
+        if (verbose)
+            std::cerr << order.size() << " total genomes input (" << order.size() - nmain << " deferred), " << repDB->size() << " kept ("
+                      << (long)(order.size() / std::max(1e-9, now_s() - t0)) << " genomes/second).\n";
+        repDB->save(dbFile);
+    } else {
+        std::ifstream probe(dbFile);
+        if (!probe) throw std::runtime_error("java.io.FileNotFoundException: Create not specified and specified repDB file not found.");
+        repDB = RepGenomeDb::load(dbFile);
+    }
+    if (a.opt.count("list")) {   // :212-222
+        std::ofstream ls(a.opt["list"]);
+        ls << "genome_id\tname\n";
+        for (const RepGenome *r : repDB->sorted()) ls << r->getGenomeId() << '\t' << r->getName() << '\n';
+    }
+    if (!a.flag.count("null")) {   // :224-262
+        std::cout << "genome_id\tname\trep_id\tscore\n";
+        FastaInputStream in(std::cin);
+        std::vector<Sequence> seqs = in.readAll();
+        std::vector<ProteinKmers> qs;
+        for (auto &q : seqs) qs.emplace_back(q.sequence);
+        std::vector<const ProteinKmers *> qp;
+        for (auto &q : qs) qp.push_back(&q);
+        t0 = now_s();
+        auto res = repDB->findClosest(qp.begin(), qp.end());
+        std::map<const RepGenome *, std::pair<int, int>> counts;   // QualityCountMap: good, bad
+        int outliers = 0;
+        for (size_t i = 0; i < seqs.size(); ++i) {
+            const auto &r = res[i];
+            if (!r.isRepresented()) { ++outliers; if (r.getRepresentative()) counts[r.getRepresentative()].second++; }
+            else counts[r.getRepresentative()].first++;
+            int sim = r.getSimilarity();
+            std::cout << genomeOf(seqs[i].label) << '\t' << seqs[i].comment << '\t' << r.getGenomeId() << '\t'
+                      << (sim == SequenceKmers::INFINITY_ ? std::string("MAX") : std::to_string(sim)) << '\n';
+        }
+        if (verbose)
+            std::cerr << seqs.size() << " genomes processed, " << outliers << " outliers, "
+                      << (long)(seqs.size() / std::max(1e-9, now_s() - t0)) << " genomes/second.\n";
+        if (a.opt.count("stats")) {   // :263-278; bestKeys(): most represented first, ties by genome id
+            std::ofstream st(a.opt["stats"]);
+            st << "rep_id\trep_name\trepresented\toutliers\n";
+            std::vector<std::pair<const RepGenome *, std::pair<int, int>>> v(counts.begin(), counts.end());
+            std::sort(v.begin(), v.end(), [](auto &x, auto &y) {
+                if (x.second.first != y.second.first) return x.second.first > y.second.first;
+                if (x.second.second != y.second.second) return x.second.second < y.second.second;
+                return x.first->compareTo(*y.first) < 0;
+            });
+            for (auto &e : v) st << e.first->getGenomeId() << '\t' << e.first->getName() << '\t' << e.second.first << '\t' << e.second.second << '\n';
+        }
+    }
+    return 0;
+}
+
+// ---- distances (DistanceMatrixProcessor.java:54-101) -----------------------------------------------
+static int cmd_distances(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-v", "v"}, {"--verbose", "v"}}, {});
+    if (a.pos.size() != 1) throw std::runtime_error("ParseFailureException: Argument \"repDbFile\" is required");
+    auto repDB = RepGenomeDb::load(a.pos[0]);
+    std::cout << "genome_1\tgenome_2\tdistance\tsim\n";
+    auto reps = repDB->all();
+    double t0 = now_s();
+    SimilarityMatrix m = SimilarityMatrix::compute(reps.begin(), reps.end());
+    long processed = 0, zeroes = 0;
+    double distSum = 0, distSqSum = 0, simSum = 0, simSqSum = 0;
+    std::string line;
+    for (size_t i = 0; i < reps.size(); ++i)
+        for (size_t j = 0; j < reps.size(); ++j)
+            if (reps[i]->compareTo(*reps[j]) < 0) {   // each unordered pair once, in the reference's loop order
+                double distance = m.distance(i, j);
+                int sim = m.similarity(i, j);
+                distSum += distance; distSqSum += distance * distance; simSum += sim; simSqSum += (double)sim * sim;
+                if (sim == 0) zeroes++;
+                std::cout << reps[i]->getGenomeId() << '\t' << reps[j]->getGenomeId() << '\t' << java::format_fixed(distance, 8, 6) << '\t' << sim << '\n';
+                processed++;
+            }
+    if (a.flag.count("v")) {
+        double distMean = distSum / processed, simMean = simSum / processed;
+        std::cerr << processed << " pairs processed in " << (now_s() - t0) << " seconds.\n"
+                  << "Mean distance is " << java::double_to_string(distMean) << " with standard deviation "
+                  << java::double_to_string(std::sqrt(distSqSum / processed - distMean * distMean)) << ".\n"
+                  << "Mean similarity is " << java::double_to_string(simMean) << " with standard deviation "
+                  << java::double_to_string(std::sqrt(simSqSum / processed - simMean * simMean)) << ".\n"
+                  << zeroes << " pairs had 0 similarity.\n";
+    }
+    return 0;
+}
+
+// ---- group (RepMatrixProcessor.java:83-130 + SequenceInfo.java) -----------------------------------------
+namespace {
+struct SequenceInfo {   // SequenceInfo.java:30-149: running distance statistics in the reference's order
+    Sequence original;
+    int distCount = 0;
+    double distSum = 0, distSquareSum = 0, distMax = 0, distMin = 1.7976931348623157e308;
+    void addDistance(double dist) {   // :83-89
+        distCount++; distSum += dist; distSquareSum += dist * dist;
+        if (dist > distMax) distMax = dist;
+        if (dist < distMin) distMin = dist;
+    }
+    double getSDev() const {   // :103-110
+        double Nm1 = distCount - 1, N = distCount;
+        return N > 1.0 ? std::sqrt(distSquareSum / Nm1 - distSum * distSum / (N * Nm1)) : 0.0;
+    }
+};
+int double_compare(double a, double b) { return a < b ? -1 : a > b ? 1 : 0; }   // Double.compare on finite values
+}  // namespace
+
+static int cmd_group(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--kmer", "K"}, {"-i", "i"}, {"--input", "i"}, {"-m", "m"}, {"--max", "m"}, {"--maxDist", "m"}, {"-v", "v"}},
+                   {"K", "i", "m"});
+    ProteinKmers::setKmerSize(a.opt.count("K") ? std::stoi(a.opt["K"]) : 8);
+    double maxDist = a.opt.count("m") ? std::stod(a.opt["m"]) : 0.995;
+    std::vector<Sequence> seqs = a.opt.count("i") ? FastaInputStream(a.opt["i"]).readAll() : FastaInputStream(std::cin).readAll();
+    std::vector<ProteinKmers> km;
+    for (auto &s : seqs) km.emplace_back(s.sequence);
+    SimilarityMatrix m = SimilarityMatrix::compute(km.begin(), km.end());
+    std::vector<SequenceInfo> info(seqs.size());
+    for (size_t i = 0; i < seqs.size(); ++i) {   // :88-95: each new sequence against all previous ones, in order
+        info[i].original = seqs[i];
+        for (size_t j = 0; j < i; ++j) { double d = m.distance(i, j); info[i].addDistance(d); info[j].addDistance(d); }
+    }
+    std::vector<size_t> sorted(seqs.size());
+    for (size_t i = 0; i < sorted.size(); ++i) sorted[i] = i;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](size_t x, size_t y) {   // SequenceInfo.compareTo :140-148
+        int c = double_compare(info[x].distSum, info[y].distSum);
+        if (c == 0) c = double_compare(info[x].getSDev(), info[y].getSDev());
+        if (c == 0) c = info[x].original.label.compare(info[y].original.label);
+        return c < 0;
+    });
+    FastaOutputStream out(std::cout);
+    std::vector<size_t> kept;
+    for (size_t x : sorted) {   // :102-124
+        if (info[x].distMin > maxDist) continue;   // singleton group: not written
+        bool found = false;
+        for (size_t y : kept) if (m.distance(x, y) <= maxDist) { found = true; break; }
+        if (!found) { kept.push_back(x); out.write(info[x].original); }
+    }
+    std::cerr << kept.size() << " sequences form the representation set.\n";
+    return 0;
+}
+
+// ---- classify (ClassifyProcessor.java:99-126) ---------------------------------------------------------
+static int cmd_classify(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--kmer", "K"}, {"-i", "i"}, {"--input", "i"}, {"-m", "m"}, {"--max", "m"}, {"--maxDist", "m"}, {"-v", "v"}},
+                   {"K", "i", "m"});
+    if (a.pos.size() != 1) throw std::runtime_error("ParseFailureException: Argument \"controlFile\" is required");
+    ProteinKmers::setKmerSize(a.opt.count("K") ? std::stoi(a.opt["K"]) : 8);
+    double maxDist = a.opt.count("m") ? std::stod(a.opt["m"]) : 0.995;
+    KmerCollectionGroup groups;
+    std::ifstream ctl(a.pos[0]);
+    if (!ctl) throw std::runtime_error("java.io.FileNotFoundException: " + a.pos[0]);
+    std::string line;
+    while (std::getline(ctl, line)) {   // headerless, two tab-separated fields: group, FASTA file
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        size_t tab = line.find('\t');
+        if (tab == std::string::npos) throw std::runtime_error("java.io.IOException: control file line needs 2 fields: " + line);
+        FastaInputStream fs(line.substr(tab + 1));
+        Sequence s;
+        while (fs.next(s)) groups.addSequence(s, line.substr(0, tab));
+    }
+    std::cout << "seq_id\tgroup\tdistance\n";
+    std::vector<Sequence> seqs = a.opt.count("i") ? FastaInputStream(a.opt["i"]).readAll() : FastaInputStream(std::cin).readAll();
+    std::vector<std::pair<const Sequence *, std::string>> q;
+    for (auto &s : seqs) q.emplace_back(&s, s.comment);
+    std::vector<double> d = groups.getDistances(q);
+    for (size_t i = 0; i < seqs.size(); ++i)
+        if (d[i] <= maxDist) std::cout << seqs[i].label << '\t' << seqs[i].comment << '\t' << java::format_fixed(d[i], 12, 8) << '\n';
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) { usage(); return 2; }
+    std::ios::sync_with_stdio(false);
+    try {
+        std::string cmd = argv[1];
+        if (cmd == "repdb") return cmd_repdb(argc, argv);
+        if (cmd == "distances") return cmd_distances(argc, argv);
+        if (cmd == "group") return cmd_group(argc, argv);
+        if (cmd == "classify") return cmd_classify(argc, argv);
+        usage();
+        return 2;
+    } catch (const std::exception &e) {   // App.java:129: print the error, exit non-zero
+        std::cerr << "Error: " << e.what() << '\n';
+        return 1;
+    }
+}

@@ -1,0 +1,129 @@
+"""TEST INFRASTRUCTURE ONLY -- expected text output of the reference's hot-path commands, restated in
+Python on top of the CPU oracle, for byte-level comparison with kmers/reps_b200/host/kmers_reps.
+
+Follows (all under src/main/java/org/theseed/proteins/kmers/reps/):
+  repdb      RepGenomeDbProcessor.java:119-169 (create: file order, >= maxErr 'X' deferred), :224-252 (report)
+  distances  DistanceMatrixProcessor.java:59,71-83
+  group      RepMatrixProcessor.java:88-125 + SequenceInfo.java:62-148 (double accumulation in that exact order)
+  classify   ClassifyProcessor.java:112-120
+"""
+import math
+
+import numpy as np
+
+from . import kr_oracle as ko
+
+
+def repdb_create(records, threshold, K=8, prot_name="Phenylalanyl-tRNA synthetase alpha chain", max_err=20, ident_inf=True):
+    """records: [(fid, name, seq)] in file order -> bytes of the saved DB"""
+    o = ko.get()
+    main = [r for r in records if r[2].count("X") < max_err]
+    deferred = [r for r in records if r[2].count("X") >= max_err]
+    order = main + deferred
+    b = o.batch([r[2] for r in order], K=K)
+    n, added, _ = o.greedy_build(b, threshold, ident_inf=ident_inf)
+    kept = [order[i] for i in np.nonzero(added)[0]]
+    # HashMap<genomeId, RepGenome>: a later rep of the same genome replaces the earlier one in place
+    ids, by_id = [], {}
+    for r in kept:
+        g = ko.genome_id_of(r[0])
+        if g not in by_id:
+            ids.append(g)
+        by_id[g] = r
+    it = o.java_hashmap_order(ids)
+    reps = [by_id[ids[i]] for i in it]
+    return ko.save_repdb(threshold, K, prot_name, reps), reps
+
+
+def repdb_report(db_reps, threshold, queries, K=8, ident_inf=True):
+    """db_reps in iteration (file) order; queries: [(label, comment, seq)] -> report text"""
+    o = ko.get()
+    rb = o.batch([r[2] for r in db_reps], K=K)
+    qb = o.batch([q[2] for q in queries], K=K)
+    bs, bi = o.find_closest(rb, qb, ident_inf=ident_inf)
+    out = ["genome_id\tname\trep_id\tscore"]
+    for q, s, i in zip(queries, bs, bi):
+        rep_id = ko.genome_id_of(db_reps[i][0]) if s > 0 else ""
+        out.append("%s\t%s\t%s\t%s" % (ko.genome_id_of(q[0]), q[1], rep_id, "MAX" if s == ko.INFINITY else str(s)))
+    return "\n".join(out) + "\n"
+
+
+def distances(db_reps, K=8, ident_inf=True):
+    o = ko.get()
+    b = o.batch([r[2] for r in db_reps], K=K)
+    m = o.sim_matrix(b, ident_inf=ident_inf, threads=4)
+    sz = b.sizes()
+    ids = [ko.genome_id_of(r[0]) for r in db_reps]
+    out = ["genome_1\tgenome_2\tdistance\tsim"]
+    for i in range(len(ids)):
+        for j in range(len(ids)):
+            if ids[i] < ids[j]:
+                d = o.distance(m[i, j], sz[i], sz[j])
+                out.append("%s\t%s\t%s\t%d" % (ids[i], ids[j], ko.java_fixed(d, 8, 6), m[i, j]))
+    return "\n".join(out) + "\n"
+
+
+def group(records, max_dist=0.995, K=8, ident_inf=True):
+    """-> (fasta text of kept sequences, count)"""
+    o = ko.get()
+    b = o.batch([r[2] for r in records], K=K)
+    m = o.sim_matrix(b, ident_inf=ident_inf, threads=4)
+    sz = b.sizes()
+    n = len(records)
+    cnt = [0] * n
+    s1 = [0.0] * n
+    s2 = [0.0] * n
+    mx = [0.0] * n
+    mn = [1.7976931348623157e308] * n
+
+    def add(k, d):
+        cnt[k] += 1
+        s1[k] += d
+        s2[k] += d * d
+        if d > mx[k]:
+            mx[k] = d
+        if d < mn[k]:
+            mn[k] = d
+
+    def dist(i, j):
+        return o.distance(m[i, j], sz[i], sz[j])
+
+    for i in range(n):
+        for j in range(i):
+            d = dist(i, j)
+            add(i, d)
+            add(j, d)
+
+    def sdev(k):
+        N = float(cnt[k])
+        Nm1 = N - 1
+        return math.sqrt(s2[k] / Nm1 - s1[k] * s1[k] / (N * Nm1)) if N > 1.0 else 0.0
+
+    order = sorted(range(n), key=lambda k: (s1[k], sdev(k), records[k][0]))
+    kept, out = [], []
+    for x in order:
+        if mn[x] > max_dist:
+            continue
+        if not any(dist(x, y) <= max_dist for y in kept):
+            kept.append(x)
+            out.append(ko.write_fasta_record(*records[x]).decode())
+    return "".join(out), len(kept)
+
+
+def classify(groups, queries, max_dist=0.995, K=8, ident_inf=True):
+    """groups: {name: [seq,...]}; queries: [(label, comment(group), seq)]"""
+    o = ko.get()
+    out = ["seq_id\tgroup\tdistance"]
+    for (label, comment, seq) in queries:
+        best = 1.0
+        members = groups.get(comment, [])
+        if members:
+            qb = o.batch([seq], K=K)
+            mb = o.batch(members, K=K)
+            m = o.sim_matrix(qb, mb, ident_inf=ident_inf)
+            qs, ms = qb.sizes(), mb.sizes()
+            for k in range(len(members)):
+                best = min(best, o.distance(m[0, k], qs[0], ms[k]))
+        if best <= max_dist:
+            out.append("%s\t%s\t%s" % (label, comment, ko.java_fixed(best, 12, 8)))
+    return "\n".join(out) + "\n"

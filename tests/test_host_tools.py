@@ -1,0 +1,125 @@
+"""GPU tests of the host layer (C++ mirror of the reference's Java classes + commands): the text the tools
+print and the database files they write are compared byte for byte with the restatement in
+oracle/ref_commands.py and with the reference's own data/rep50.db."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from kmers.reps_b200 import synth
+from oracle import kr_oracle as ko
+from oracle import ref_commands as rc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "kmers", "reps_b200", "host", "kmers_reps")
+
+
+def run(args, stdin=b"", check=True):
+    p = subprocess.run([TOOL] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    if check:
+        assert p.returncode == 0, p.stderr.decode()
+    return p
+
+
+def fasta(records):
+    return b"".join(ko.write_fasta_record(*r) for r in records)
+
+
+def test_tool_is_built():
+    assert os.path.exists(TOOL), "run __graft_entry__.build()"
+
+
+def test_repdb_load_report_and_list(tmp_path, rep50, gto_seeds, expected):
+    db = tmp_path / "rep50.db"
+    db.write_bytes(rep50["raw"])
+    lst = tmp_path / "list.tbl"
+    p = run(["repdb", "--list", str(lst), str(db)], stdin=fasta(gto_seeds))
+    assert p.stdout.decode() == rc.repdb_report(rep50["reps"], 50, gto_seeds)
+    rows = p.stdout.decode().split("\n")[1:-1]
+    for row, e in zip(rows, expected["config1"]):
+        g, name, rep, score = row.split("\t")
+        assert (g, rep, int(score)) == (e["genome"], e["rep"], e["sim"])
+    want = sorted((ko.genome_id_of(f), n) for (f, n, _) in rep50["reps"])
+    got = [tuple(l.split("\t")) for l in lst.read_text().split("\n")[1:-1]]
+    assert got == want
+    # a member of the database finds itself with score MAX
+    p = run(["repdb", str(db)], stdin=fasta(rep50["reps"][:5]))
+    assert [l.split("\t")[3] for l in p.stdout.decode().split("\n")[1:-1]] == ["MAX"] * 5
+
+
+def test_repdb_create_reproduces_rep50_byte_for_byte(tmp_path, rep50):
+    # every pair of rep50's reps is below the threshold, so a build at 50 keeps them all; fed in the file's own
+    # order the saved file (java.util.HashMap order by genome id, bins in insertion order) is the reference's
+    # file again, byte for byte
+    src = tmp_path / "in.fa"
+    src.write_bytes(fasta(rep50["reps"]))
+    out = tmp_path / "out.db"
+    run(["repdb", "--create", str(src), "-m", "50", "--null", "--batch", "400", str(out)])
+    assert out.read_bytes() == rep50["raw"]
+    # any other input order changes the order inside hash bins exactly as java.util.HashMap would
+    rng = np.random.default_rng(17)
+    shuffled = [rep50["reps"][i] for i in rng.permutation(len(rep50["reps"]))]
+    src.write_bytes(fasta(shuffled))
+    run(["repdb", "--create", str(src), "-m", "50", "--null", str(out)])
+    want, reps = rc.repdb_create(shuffled, 50)
+    assert len(reps) == 1480 and out.read_bytes() == want and want != rep50["raw"]
+
+
+def test_repdb_create_synthetic_with_deferral(tmp_path):
+    res, off, _ = synth.generate(0x5EED0004, 3000, 75, xrun_per_10k=200)
+    seqs = synth.to_strings(res, off)
+    recs = [("fig|%d.%d.peg.%d" % (1000 + 7 * i, 1 + i % 9, i), "Synthetic genome %d" % i, s) for i, s in enumerate(seqs)]
+    assert sum(s.count("X") >= 20 for s in seqs) > 10
+    src = tmp_path / "cands.fa"
+    src.write_bytes(fasta(recs))
+    for thr in (50, 100):
+        out = tmp_path / ("syn%d.db" % thr)
+        run(["repdb", "--create", str(src), "-m", str(thr), "--null", "--batch", "512", str(out)])
+        want, reps = rc.repdb_create(recs, thr)
+        assert out.read_bytes() == want
+        assert 0 < len(reps) < len(recs)
+
+
+def test_distances(tmp_path, rep50):
+    reps = rep50["reps"][:300]
+    db = tmp_path / "small.db"
+    db.write_bytes(ko.save_repdb(50, 8, rep50["prot_name"], reps))
+    p = run(["distances", str(db)])
+    assert p.stdout.decode() == rc.distances(reps)
+
+
+def test_group_vapb(vapb):
+    p = run(["group"], stdin=fasta(vapb))
+    want, n = rc.group(vapb)
+    assert p.stdout.decode() == want
+    assert p.stderr.decode().strip().endswith("%d sequences form the representation set." % n)
+    p2 = run(["group", "-m", "0.9", "-K", "6"], stdin=fasta(vapb))
+    want2, n2 = rc.group(vapb, max_dist=0.9, K=6)
+    assert p2.stdout.decode() == want2 and n2 != n
+
+
+def test_classify(tmp_path, vapb, rickettsia):
+    ga = [r for r in vapb[:120]]
+    gb = [("r%d" % i, "", p) for i, (_, p) in enumerate(rickettsia[:40])]
+    (tmp_path / "a.fa").write_bytes(fasta(ga))
+    (tmp_path / "b.fa").write_bytes(fasta(gb))
+    ctl = tmp_path / "control.tbl"
+    ctl.write_text("anti\t%s\nphes\t%s\n" % (tmp_path / "a.fa", tmp_path / "b.fa"))
+    queries = [(l, "anti", s) for (l, _, s) in vapb[100:160]] + [("q%d" % i, "phes", p) for i, (_, p) in enumerate(rickettsia[30:60])]
+    queries += [("lost", "nogroup", vapb[0][2])]
+    p = run(["classify", str(ctl)], stdin=fasta(queries))
+    want = rc.classify({"anti": [s for (_, _, s) in ga], "phes": [s for (_, _, s) in gb]}, queries)
+    assert p.stdout.decode() == want and want.count("\n") > 20
+
+
+def test_error_behaviour(tmp_path):
+    p = run(["repdb", str(tmp_path / "missing.db")], check=False)
+    assert p.returncode == 1 and "FileNotFoundException" in p.stderr.decode()
+    p = run(["repdb", "--bogus", "x"], check=False)
+    assert p.returncode == 1 and "not a valid option" in p.stderr.decode()
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b">fig|1.1.peg.1 x\nACDEFGHIKLMNPQRSTVWYacd\n")
+    p = run(["repdb", "--create", str(bad), "--null", str(tmp_path / "o.db")], check=False)
+    assert p.returncode == 1 and "outside" in p.stderr.decode()
