@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--elem", default="u16", choices=["u16", "i32"])
+    ap.add_argument("--gather-matrix", action="store_true",
+                    help="N>1: also all-gather the whole matrix onto every GPU after the timed region and report its cost")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,9 +166,8 @@ def main():
     elem = kr.ELEM_U16 if args.elem == "u16" else kr.ELEM_I32
     esz = 2 if elem == kr.ELEM_U16 else 4
     layout = kr.LAYOUT_BLOCKTRI
-    rb = kr.matrix_stripes(N, N, layout, world)
-    r0, r1 = int(rb[rank]), int(rb[rank + 1])
-    my_elems = kr.matrix_elems(N, N, layout, r0, r1)
+    from kmers.reps_b200 import sharding
+    r0, r1, my_elems, _ = sharding.my_stripe(N, layout, rank, world)
     d_res = torch.from_numpy(res).cuda()
     d_out = torch.empty(my_elems * esz + 16, dtype=torch.uint8, device="cuda")
     total_pairs = N * (N - 1) // 2
@@ -209,6 +210,23 @@ def main():
     ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
     value = total_pairs / (ms_per_step / 1e3)
+
+    gather = None
+    if args.gather_matrix and world > 1:
+        # what it would cost to also leave the WHOLE matrix on every GPU (not part of the headline: DESIGN.md 5)
+        local = d_out[: my_elems * esz].view(torch.int16 if esz == 2 else torch.int32)
+        whole = torch.empty(kr.matrix_elems(N, N, layout), dtype=local.dtype, device="cuda")
+        sharding.allgather_stripes(local, N, layout, dist, out=whole)   # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sharding.allgather_stripes(local, N, layout, dist, out=whole)
+        e1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"ms": float(tg.item()), "bytes_per_rank": int(whole.numel() * esz)}
+        del whole
 
     # ---- check a sample of this rank's cells against the oracle (outside the timed region) -----
     from oracle import kr_oracle as ko
@@ -303,6 +321,8 @@ def main():
             "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
             "verified": "400 sampled cells per rank equal the oracle",
         }
+        if gather:
+            line["matrix_allgather"] = gather
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

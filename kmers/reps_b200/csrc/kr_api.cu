@@ -42,6 +42,9 @@ struct kr_ctx {
     std::vector<EvPair> pending;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool err_pending = false;   // an encode launched by a _device call has not had its error flag read yet
+    // cached tile list of the last matrix launch (the same stripes are usually computed again and again)
+    uint2 *d_tasks_cache = nullptr; u32 tasks_cache_n = 0; u32 tasks_key[5] = {0, 0, 0, 0, 0xFFFFFFFFu};
 };
 
 struct kr_seqset {
@@ -208,17 +211,21 @@ void kr_destroy(kr_ctx *ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_err);
+    if (ctx->d_tasks_cache) cudaFree(ctx->d_tasks_cache);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
+static kr_status check_alphabet(kr_ctx *ctx);
+
 kr_status kr_synchronize(kr_ctx *ctx) {
     if (!ctx) return KR_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->dev));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->err_pending) return check_alphabet(ctx);
     return KR_OK;
 }
 
@@ -259,6 +266,7 @@ kr_status kr_timer_end(kr_ctx *ctx, double *ms) {
     float f = 0;
     CU(cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
     *ms = f;
+    if (ctx->err_pending) return check_alphabet(ctx);
     return KR_OK;
 }
 
@@ -295,6 +303,20 @@ static void seqset_destroy(kr_seqset *s) {
     dfree(ctx, s->d_off); dfree(ctx, s->d_koff); dfree(ctx, s->d_keys); dfree(ctx, s->d_meta);
     dfree(ctx, s->d_hi); dfree(ctx, (u8 *)s->d_lo); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
     delete s;   // residue buffers are released stream-ordered by ~DevMem
+}
+
+// read (and clear) the device-side "residue outside the alphabet" flag; synchronises the stream
+static kr_status check_alphabet(kr_ctx *ctx) {
+    ErrInfo ei;
+    CU(cudaMemcpyAsync(&ei, ctx->d_err, sizeof ei, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->err_pending = false;
+    if (ei.flag) {
+        cudaMemsetAsync(ctx->d_err, 0, sizeof(ErrInfo), ctx->stream);
+        return fail(ctx, KR_ERR_ALPHABET, "kr_encode: sequence %u position %u: residue 0x%02x ('%c') is outside 'A'..'Z', '*', '-'",
+                    ei.seq, ei.pos, ei.byte, (ei.byte >= 32 && ei.byte < 127) ? (char)ei.byte : '?');
+    }
+    return KR_OK;
 }
 
 static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, const u64 *offsets, u32 nseq, kr_seqset **out) {
@@ -339,14 +361,13 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
         LAUNCHED(ctx);
         CU(cudaGetLastError());
     }
-    ErrInfo ei;
-    CU(cudaMemcpyAsync(&ei, ctx->d_err, sizeof ei, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (ei.flag) {
-        cudaMemsetAsync(ctx->d_err, 0, sizeof(ErrInfo), ctx->stream);
-        return fail(ctx, KR_ERR_ALPHABET, "kr_encode: sequence %u position %u: residue 0x%02x ('%c') is outside 'A'..'Z', '*', '-'",
-                    ei.seq, ei.pos, ei.byte, (ei.byte >= 32 && ei.byte < 127) ? (char)ei.byte : '?');
+    if (on_device) {   // "_device" calls do not synchronise the host: the flag is read at the next call that does
+        ctx->err_pending = true;
+        *out = s.release();
+        return KR_OK;
     }
+    kr_status st = check_alphabet(ctx);
+    if (st) return st;
     *out = s.release();
     return KR_OK;
 }
@@ -385,6 +406,7 @@ static kr_status fetch_sizes(kr_ctx *ctx, kr_seqset *s) {
     std::vector<SeqMeta> m(s->n);
     CU(cudaMemcpyAsync(m.data(), s->d_meta, (size_t)s->n * sizeof(SeqMeta), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->err_pending) { kr_status st = check_alphabet(ctx); if (st) return st; }
     ctx->st.d2h_bytes += (u64)s->n * sizeof(SeqMeta);
     s->h_sizes.resize(s->n);
     for (u32 i = 0; i < s->n; ++i) s->h_sizes[i] = m[i].size;
@@ -446,21 +468,27 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
     u32 rb0 = d->row_begin / TB, rb1 = (d->row_end + TB - 1) / TB;
     // Tile order: super-tiles of ST x ST blocks, so that the ~150 tiles in flight at any time share
     // 2*ST block lists (a few MB) and re-reads of a block list hit L2 instead of HBM.
-    std::vector<uint2> tasks;
-    const u32 ST = 16;
-    for (u32 SI = rb0; SI < rb1; SI += ST)
-        for (u32 SJ = (d->layout == KR_LAYOUT_FULL ? 0 : SI / ST * ST); SJ < Bs->nblk; SJ += ST)
-            for (u32 I = SI; I < std::min(SI + ST, rb1); ++I)
-                for (u32 J = std::max(SJ, d->layout == KR_LAYOUT_FULL ? 0u : I); J < std::min(SJ + ST, Bs->nblk); ++J)
-                    tasks.push_back(make_uint2(I, J));
-    if (tasks.empty()) return KR_OK;
-    uint2 *d_tasks = nullptr;
-    CU(dalloc(ctx, &d_tasks, tasks.size()));
-    CU(cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    const u32 key[5] = {rb0, rb1, A->nblk, Bs->nblk, d->layout == KR_LAYOUT_FULL ? 0u : 1u};
+    if (memcmp(key, ctx->tasks_key, sizeof key) != 0 || !ctx->d_tasks_cache) {
+        std::vector<uint2> tasks;
+        const u32 ST = 16;
+        for (u32 SI = rb0; SI < rb1; SI += ST)
+            for (u32 SJ = (d->layout == KR_LAYOUT_FULL ? 0 : SI / ST * ST); SJ < Bs->nblk; SJ += ST)
+                for (u32 I = SI; I < std::min(SI + ST, rb1); ++I)
+                    for (u32 J = std::max(SJ, d->layout == KR_LAYOUT_FULL ? 0u : I); J < std::min(SJ + ST, Bs->nblk); ++J)
+                        tasks.push_back(make_uint2(I, J));
+        dfree(ctx, ctx->d_tasks_cache);
+        ctx->d_tasks_cache = nullptr; ctx->tasks_cache_n = (u32)tasks.size();
+        CU(dalloc(ctx, &ctx->d_tasks_cache, tasks.size()));
+        CU(cudaMemcpyAsync(ctx->d_tasks_cache, tasks.data(), tasks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        memcpy(ctx->tasks_key, key, sizeof key);
+    }
+    if (ctx->tasks_cache_n == 0) return KR_OK;
+    uint2 *d_tasks = ctx->d_tasks_cache;
     JoinParams p{};
     p.A = A->d_refs; p.B = Bs->d_refs; p.metaA = A->d_meta; p.metaB = Bs->d_meta;
     p.nA = A->n; p.nB = Bs->n; p.nBblk = Bs->nblk;
-    p.tasks = d_tasks; p.ntasks = (u32)tasks.size(); p.flags = ctx->flags;
+    p.tasks = d_tasks; p.ntasks = ctx->tasks_cache_n; p.flags = ctx->flags;
     p.out = out_dev; p.elem = d->elem; p.layout = d->layout;
     p.origin = row_start(d->layout, d->row_begin, A->n, Bs->n);
     {
@@ -471,7 +499,6 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
         LAUNCHED(ctx); ctx->st.join_launches++;
         CU(cudaGetLastError());
     }
-    dfree(ctx, d_tasks);   // stream-ordered; the pageable task list was staged before the copy call returned
     u64 rows = d->row_end - d->row_begin;
     if (d->layout == KR_LAYOUT_FULL) ctx->st.pairs += rows * (u64)Bs->n;
     else ctx->st.pairs += kr_matrix_elems(A->n, A->n, KR_LAYOUT_TRIANGLE, d->row_begin, d->row_end);

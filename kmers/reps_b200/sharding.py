@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): how the path shards and what is exchanged.
+
+The path has no data-path collective: all-vs-all shards the 256-row stripes of the result, findClosest shards
+the queries against a replicated database.  The only exchanges are result gathers, done here with plain
+torch.distributed collectives (NCCL on GPUs; gloo in the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import binding as kr
+
+
+def my_stripe(n: int, layout: int, rank: int, world: int):
+    """rows [r0, r1) of an n x n self matrix owned by `rank`, their cell count and the offset of the first cell
+    in the whole matrix (cells of lower-ranked stripes)"""
+    rb = kr.matrix_stripes(n, n, layout, world)
+    r0, r1 = int(rb[rank]), int(rb[rank + 1])
+    return r0, r1, kr.matrix_elems(n, n, layout, r0, r1), kr.matrix_elems(n, n, layout, 0, r0)
+
+
+def stripe_table(n: int, layout: int, world: int):
+    rb = kr.matrix_stripes(n, n, layout, world)
+    counts = [kr.matrix_elems(n, n, layout, int(rb[k]), int(rb[k + 1])) for k in range(world)]
+    return rb, counts
+
+
+def allgather_stripes(local, n: int, layout: int, dist, out=None):
+    """Every rank ends up with the whole matrix (1-D, `layout` order).  `local` is this rank's stripe as a 1-D
+    torch tensor.  Stripes differ slightly in size (block granularity), so each rank broadcasts its own into its
+    slice of the result."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    rb, counts = stripe_table(n, layout, world)
+    total = int(sum(counts))
+    if out is None:
+        out = torch.empty(total, dtype=local.dtype, device=local.device)
+    pos = 0
+    for k in range(world):
+        sl = out[pos:pos + counts[k]]
+        if k == rank:
+            sl.copy_(local[: counts[k]])
+        if counts[k]:
+            dist.broadcast(sl.view(torch.uint8), src=k)   # bytes: NCCL has no 16-bit integer type
+        pos += counts[k]
+    return out
+
+
+def shard_range(n: int, rank: int, world: int):
+    """contiguous query range of `rank`: sizes differ by at most one"""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allgather_ranges(local, n: int, dist):
+    """gather per-query results sharded by shard_range back into query order on every rank"""
+    import torch
+    world = dist.get_world_size()
+    base, extra = divmod(n, world)
+    width = base + (1 if extra else 0)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    out = []
+    for k in range(world):
+        lo, hi = shard_range(n, k, world)
+        out.append(parts[k][: hi - lo])
+    return torch.cat(out, 0)
+
+
+def blocktri_from_full(full: np.ndarray) -> np.ndarray:
+    """KR_LAYOUT_BLOCKTRI cells of a full n x n matrix (row i keeps columns >= 256*(i//256))"""
+    n = full.shape[0]
+    return np.concatenate([full[i, 256 * (i // 256):] for i in range(n)]) if n else full.reshape(0)
