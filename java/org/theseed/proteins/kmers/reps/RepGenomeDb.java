@@ -1,0 +1,232 @@
+package org.theseed.proteins.kmers.reps;
+
+import java.io.File;
+import java.io.IOException;
+import java.io.PrintWriter;
+import java.lang.foreign.Arena;
+import java.lang.foreign.MemorySegment;
+import java.nio.charset.StandardCharsets;
+import java.util.ArrayList;
+import java.util.Collection;
+import java.util.HashMap;
+import java.util.Iterator;
+import java.util.List;
+import java.util.SortedSet;
+import java.util.TreeSet;
+
+import org.theseed.sequence.FastaInputStream;
+import org.theseed.sequence.KmersRepsNative;
+import org.theseed.sequence.ProteinKmers;
+import org.theseed.sequence.Sequence;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_BYTE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+/**
+ * Drop-in for org.theseed.proteins.kmers.reps.RepGenomeDb (org.theseed:shared): same public members as used by
+ * kmers.reps (SURVEY.md appendix C), with the scan and build loops batched on the GPU.  The representatives stay
+ * in a java.util.HashMap keyed by genome id, exactly as upstream, so save() order and findClosest tie-breaking
+ * are the JVM's own; the device copy is told each representative's position in that iteration order
+ * (kr_db_set_ranks).  New entry points: findClosest(Collection), checkGenomes(List).
+ * COMPILE-UNVERIFIED (no JDK in the build container); the same logic is implemented and tested in
+ * kmers/reps_b200/host/theseed.hpp (class RepGenomeDb).
+ */
+public class RepGenomeDb implements Iterable<RepGenome> {
+
+    public static final String DEFAULT_PROTEIN = "Phenylalanyl-tRNA synthetase alpha chain";
+
+    private final HashMap<String, RepGenome> genomeMap = new HashMap<>();
+    private final int threshold;
+    private final int kmerSize;
+    private final String protName;
+    // device mirror
+    private MemorySegment db = MemorySegment.NULL;
+    private final List<RepGenome> onDevice = new ArrayList<>();   // device index -> rep
+    private boolean rebuild = false, ranksDirty = true;
+
+    public class Representation {
+        private final int similarity;
+        private final RepGenome representative;
+        private final double distance;
+
+        public Representation() { this(null, 0, 1.0); }
+        public Representation(RepGenome rep, ProteinKmers query) {   // NeighborProcessor.java:168
+            this(rep, rep.similarity(query), rep.distance(query));
+        }
+        Representation(RepGenome rep, int sim, double dist) { this.representative = rep; this.similarity = sim; this.distance = dist; }
+        public int getSimilarity() { return similarity; }
+        public double getDistance() { return distance; }
+        public RepGenome getRepresentative() { return representative; }
+        public String getGenomeId() { return representative == null ? null : representative.getGenomeId(); }
+        public boolean isRepresented() { return similarity >= threshold; }
+    }
+
+    public RepGenomeDb(int threshold, String... protNames) {
+        this.threshold = threshold;
+        this.kmerSize = ProteinKmers.kmerSize();
+        this.protName = protNames.length > 0 ? protNames[0] : DEFAULT_PROTEIN;
+    }
+
+    public int getThreshold() { return threshold; }
+    public int getKmerSize() { return kmerSize; }
+    public String getProtName() { return protName; }
+    public int size() { return genomeMap.size(); }
+    public RepGenome get(String genomeId) { return genomeMap.get(genomeId); }
+    public boolean contains(String genomeId) { return genomeMap.containsKey(genomeId); }
+    public Collection<RepGenome> all() { return genomeMap.values(); }
+    public SortedSet<RepGenome> sorted() { return new TreeSet<>(genomeMap.values()); }
+    public String getListFileName() { return String.format("rep%d.list.tbl", threshold); }
+    @Override public String toString() { return "RepGen" + threshold; }
+
+    @Override
+    public Iterator<RepGenome> iterator() {
+        Iterator<RepGenome> it = genomeMap.values().iterator();
+        return new Iterator<>() {   // remove() must also invalidate the device copy (UpdateProcessor.java:96-103)
+            public boolean hasNext() { return it.hasNext(); }
+            public RepGenome next() { return it.next(); }
+            public void remove() { it.remove(); rebuild = true; ranksDirty = true; }
+        };
+    }
+
+    public void addRep(RepGenome rep) {
+        if (genomeMap.put(rep.getGenomeId(), rep) != null) rebuild = true;   // replaced in place
+        ranksDirty = true;
+    }
+
+    public Representation findClosest(ProteinKmers query) { return findClosest(List.of(query)).get(0); }
+    public Representation findClosest(Sequence seq) { return findClosest(new ProteinKmers(seq.getSequence())); }
+
+    /** The batched scan: one launch for the whole list (RepGenomeDbProcessor.java:235-252 rewritten). */
+    public List<Representation> findClosest(Collection<? extends ProteinKmers> queries) {
+        List<Representation> out = new ArrayList<>(queries.size());
+        if (queries.isEmpty()) return out;
+        sync();
+        List<ProteinKmers> q = new ArrayList<>(queries);
+        List<String> prots = new ArrayList<>();
+        for (ProteinKmers p : q) prots.add(p.getProtein());
+        try (Arena a = Arena.ofConfined(); KmersRepsNative.SeqSet set = KmersRepsNative.encode(kmerSize, prots)) {
+            MemorySegment sim = a.allocate(JAVA_INT, q.size()), first = a.allocate(JAVA_INT, q.size());
+            MemorySegment ctx = KmersRepsNative.context(kmerSize);
+            KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_find_closest.invokeExact(ctx, db, set.handle(), sim, first, MemorySegment.NULL));
+            for (int i = 0; i < q.size(); i++) {
+                int s = sim.getAtIndex(JAVA_INT, i), f = first.getAtIndex(JAVA_INT, i);
+                if (s == 0 || f == KmersRepsNative.NO_REP) { out.add(new Representation()); continue; }
+                RepGenome rep = onDevice.get(f);
+                out.add(new Representation(rep, s, KmersRepsNative.distance(s, set.sizeOf(i), rep.size())));
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+        return out;
+    }
+
+    public boolean checkSimilarity(ProteinKmers query, int sim) {
+        return size() > 0 && findClosest(query).getSimilarity() >= sim;
+    }
+
+    public boolean checkGenome(RepGenome rep) { return checkGenomes(List.of(rep))[0]; }
+
+    /** The greedy build for a list of candidates in list order (RepGenomeDbProcessor.java:134-147 rewritten). */
+    public boolean[] checkGenomes(List<RepGenome> cands) {
+        boolean[] added = new boolean[cands.size()];
+        if (cands.isEmpty()) return added;
+        sync();
+        List<String> prots = new ArrayList<>();
+        for (RepGenome c : cands) prots.add(c.getProtein());
+        try (Arena a = Arena.ofConfined(); KmersRepsNative.SeqSet set = KmersRepsNative.encode(kmerSize, prots)) {
+            MemorySegment flags = a.allocate(JAVA_BYTE, cands.size());
+            MemorySegment ctx = KmersRepsNative.context(kmerSize);
+            KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_greedy_build.invokeExact(ctx, db, set.handle(), threshold, 0, flags));
+            for (int i = 0; i < added.length; i++)
+                if (flags.get(JAVA_BYTE, i) != 0) {
+                    added[i] = true;
+                    RepGenome c = cands.get(i);
+                    if (genomeMap.put(c.getGenomeId(), c) != null) rebuild = true; else onDevice.add(c);
+                }
+            ranksDirty = true;
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+        return added;
+    }
+
+    /** FASTA: ">Rep<thr>,K=<K> <protName>" with no sequence, then one record per representative (data/rep50.db). */
+    public void save(File saveFile) throws IOException {
+        try (PrintWriter out = new PrintWriter(saveFile, StandardCharsets.US_ASCII)) {
+            out.print(String.format(">Rep%d,K=%d %s\n", threshold, kmerSize, protName));
+            for (RepGenome rep : this) {
+                out.print(">" + rep.getFid() + " " + rep.getName() + "\n");
+                String p = rep.getProtein();
+                for (int i = 0; i < p.length(); i += 60) out.print(p.substring(i, Math.min(p.length(), i + 60)) + "\n");
+            }
+        }
+    }
+
+    public static RepGenomeDb load(File loadFile) throws IOException {
+        try (FastaInputStream in = new FastaInputStream(loadFile)) {
+            Iterator<Sequence> it = in.iterator();
+            Sequence header = it.next();
+            String[] parts = header.getLabel().substring(3).split(",K=");
+            ProteinKmers.setKmerSize(Integer.parseInt(parts[1]));
+            RepGenomeDb db = new RepGenomeDb(Integer.parseInt(parts[0]), header.getComment());
+            while (it.hasNext()) db.addRep(new RepGenome(it.next()));
+            return db;
+        }
+    }
+
+    /** Bring the device copy up to date: append new representatives, refresh iteration ranks. */
+    private void sync() {
+        MemorySegment ctx = KmersRepsNative.context(kmerSize);
+        try (Arena a = Arena.ofConfined()) {
+            if (rebuild && !db.equals(MemorySegment.NULL)) {
+                KmersRepsNative.kr_db_free.invokeExact(db);
+                db = MemorySegment.NULL; onDevice.clear();
+            }
+            if (db.equals(MemorySegment.NULL)) {
+                MemorySegment out = a.allocate(ADDRESS);
+                KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_create.invokeExact(ctx, out));
+                db = out.get(ADDRESS, 0);
+            }
+            rebuild = false;
+            java.util.Set<RepGenome> have = java.util.Collections.newSetFromMap(new java.util.IdentityHashMap<>());
+            have.addAll(onDevice);
+            List<RepGenome> fresh = new ArrayList<>();
+            for (RepGenome r : genomeMap.values()) if (!have.contains(r)) fresh.add(r);
+            if (!fresh.isEmpty()) {
+                long total = 0;
+                for (RepGenome r : fresh) total += r.getProtein().length();
+                MemorySegment res = a.allocate(Math.max(total, 1)), off = a.allocate(JAVA_LONG, fresh.size() + 1L);
+                long pos = 0;
+                for (int i = 0; i < fresh.size(); i++) {
+                    byte[] b = fresh.get(i).getProtein().getBytes(StandardCharsets.ISO_8859_1);
+                    MemorySegment.copy(b, 0, res, JAVA_BYTE, pos, b.length);
+                    off.setAtIndex(JAVA_LONG, i, pos);
+                    pos += b.length;
+                }
+                off.setAtIndex(JAVA_LONG, fresh.size(), pos);
+                KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_append.invokeExact(ctx, db, res, off, fresh.size()));
+                onDevice.addAll(fresh);
+                ranksDirty = true;
+            }
+            if (ranksDirty && !onDevice.isEmpty()) {
+                java.util.IdentityHashMap<RepGenome, Integer> rankOf = new java.util.IdentityHashMap<>();
+                int k = 0;
+                for (RepGenome r : genomeMap.values()) rankOf.put(r, k++);   // the JVM's own HashMap order
+                MemorySegment rank = a.allocate(JAVA_INT, onDevice.size());
+                for (int d = 0; d < onDevice.size(); d++) rank.setAtIndex(JAVA_INT, d, rankOf.get(onDevice.get(d)));
+                KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_set_ranks.invokeExact(ctx, db, rank, onDevice.size()));
+                ranksDirty = false;
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+    }
+}
