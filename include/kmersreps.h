@@ -56,6 +56,10 @@ typedef int32_t kr_status;
 /* context flags (policy switches for the semantics SURVEY.md 8c could not verify against a JVM) */
 #define KR_IDENT_IS_INFINITY 1u /* similarity of two equal sequences is KR_INFINITY, not the raw count */
 #define KR_TIE_LAST 2u          /* findClosest keeps the last maximum in iteration order, not the first */
+/* findClosest has two exact device paths: the tile join (any size) and the inverted index (large query
+ * batches).  The library picks by batch size; these flags pin one of them (used by the parity tests). */
+#define KR_FORCE_JOIN 4u
+#define KR_FORCE_INDEX 8u
 
 #define KR_MIN_K 3
 #define KR_MAX_K 11 /* 5 bits per residue + 8 bits of block-local sequence id in one 64-bit key */

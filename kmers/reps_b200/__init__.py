@@ -7,7 +7,7 @@ There is no CPU fallback: importing works anywhere, but creating a Context witho
 library or without a CUDA device raises.
 """
 from .binding import (  # noqa: F401
-    INFINITY, NO_REP, IDENT_IS_INFINITY, TIE_LAST, ELEM_I32, ELEM_U16, LAYOUT_FULL, LAYOUT_TRIANGLE,
+    INFINITY, NO_REP, IDENT_IS_INFINITY, TIE_LAST, FORCE_JOIN, FORCE_INDEX, ELEM_I32, ELEM_U16, LAYOUT_FULL, LAYOUT_TRIANGLE,
     LAYOUT_BLOCKTRI, TILE, Context, SeqSet, RepDb, KrError, lib_path, load_library, distance,
     matrix_elems, matrix_stripes, flat,
 )

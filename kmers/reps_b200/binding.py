@@ -11,6 +11,8 @@ INFINITY = 9999
 NO_REP = 0xFFFFFFFF
 IDENT_IS_INFINITY = 1
 TIE_LAST = 2
+FORCE_JOIN = 4
+FORCE_INDEX = 8
 ELEM_I32, ELEM_U16 = 0, 1
 LAYOUT_FULL, LAYOUT_TRIANGLE, LAYOUT_BLOCKTRI = 0, 1, 2
 TILE = 256

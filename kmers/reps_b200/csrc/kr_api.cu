@@ -66,6 +66,10 @@ struct kr_seqset {
 };
 
 struct DbSegment { kr_seqset *set; u32 base; };
+struct DbIndexSlab {   // inverted index over representatives [base, base + n)
+    u32 base = 0, n = 0, mask = 0;
+    unsigned long long *tab_key = nullptr; u32 *tab_off = nullptr, *tab_cnt = nullptr, *postings = nullptr;
+};
 struct kr_db {
     kr_ctx *ctx = nullptr;
     std::vector<DbSegment> segs;
@@ -75,6 +79,10 @@ struct kr_db {
     SeqMeta *d_meta = nullptr; BlockRef *d_refs = nullptr; u32 *d_rank = nullptr, *d_order = nullptr;
     u32 nblk = 0, cap = 0, cap_blk = 0;
     std::vector<u32> h_rank;   // empty = append order
+    // inverted index (built on first use by a large query batch, dropped when the database changes)
+    bool index_ready = false;
+    std::vector<DbIndexSlab> slabs;
+    u32 *d_empty_reps = nullptr; u32 nempty = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -194,6 +202,7 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_err, sizeof(ErrInfo)));
     CUC(cudaMemset(ctx->d_err, 0, sizeof(ErrInfo)));
+    CUC(cudaFuncSetAttribute(k_idx_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDX_SMEM));
     CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
     CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
     CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
@@ -523,8 +532,17 @@ static void db_free_arrays(kr_db *db) {
 }
 
 // (re)build the database-wide meta / block-ref / rank arrays after a change
+static void db_free_index(kr_db *db) {
+    kr_ctx *ctx = db->ctx;
+    for (auto &sl : db->slabs) { dfree(ctx, sl.tab_key); dfree(ctx, sl.tab_off); dfree(ctx, sl.tab_cnt); dfree(ctx, sl.postings); }
+    db->slabs.clear();
+    dfree(ctx, db->d_empty_reps); db->d_empty_reps = nullptr; db->nempty = 0;
+    db->index_ready = false;
+}
+
 static kr_status db_refresh(kr_ctx *ctx, kr_db *db) {
     if (!db->dirty) return KR_OK;
+    db_free_index(db);
     kr_status st;
     u32 nblk = 0;
     for (auto &sg : db->segs) { if ((st = ensure_blocklists(ctx, sg.set))) return st; nblk += sg.set->nblk; }
@@ -617,12 +635,113 @@ static kr_status db_append_owned(kr_ctx *ctx, kr_db *db, kr_seqset *s) {
     return db_compact(ctx, db);
 }
 
+// K4: build the inverted index of the database, one slab of at most IDX_SLAB representatives at a time
+static kr_status db_build_index(kr_ctx *ctx, kr_db *db) {
+    if (db->index_ready) return KR_OK;
+    kr_status st;
+    for (auto &sg : db->segs) if ((st = fetch_sizes(ctx, sg.set))) return st;
+    StageTimer t(ctx, ST_OTHER);
+    for (u32 base = 0; base < db->n; base += IDX_SLAB) {
+        DbIndexSlab sl; sl.base = base; sl.n = std::min<u32>(IDX_SLAB, db->n - base);
+        u64 entries = 0;
+        for (auto &sg : db->segs) {
+            u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
+            for (u32 g = lo; g < hi; ++g) entries += sg.set->h_sizes[g - sg.base];
+        }
+        u64 cap = 1024; while (cap < 2 * entries) cap <<= 1;
+        if (cap > (1ull << 31)) return fail(ctx, KR_ERR_ARG, "inverted index slab too large (%llu entries)", (unsigned long long)entries);
+        sl.mask = (u32)(cap - 1);
+        u32 *d_cur = nullptr, *d_sums = nullptr;
+        u32 ntile = (u32)((cap + SCAN_TILE - 1) / SCAN_TILE);
+        CU(dalloc(ctx, &sl.tab_key, cap)); CU(dalloc(ctx, &sl.tab_off, cap)); CU(dalloc(ctx, &sl.tab_cnt, cap));
+        CU(dalloc(ctx, &sl.postings, entries + 1)); CU(dalloc(ctx, &d_cur, cap)); CU(dalloc(ctx, &d_sums, ntile));
+        CU(cudaMemsetAsync(sl.tab_key, 0xFF, cap * 8, ctx->stream));
+        CU(cudaMemsetAsync(sl.tab_cnt, 0, cap * 4, ctx->stream));
+        CU(cudaMemsetAsync(d_cur, 0, cap * 4, ctx->stream));
+        for (auto &sg : db->segs) {
+            u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
+            if (lo >= hi) continue;
+            kr_seqset *s = sg.set; u32 l = lo - sg.base;
+            k_idx_insert<<<hi - lo, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, sl.tab_key, sl.tab_cnt, sl.mask);
+            LAUNCHED(ctx);
+        }
+        k_scan_tile_sums<<<ntile, 256, 0, ctx->stream>>>(sl.tab_cnt, cap, d_sums);
+        k_scan_sums<<<1, 1024, 0, ctx->stream>>>(d_sums, ntile);
+        k_scan_tiles<<<ntile, 256, 0, ctx->stream>>>(sl.tab_cnt, cap, d_sums, sl.tab_off);
+        ctx->st.kernel_launches += 3;
+        for (auto &sg : db->segs) {
+            u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
+            if (lo >= hi) continue;
+            kr_seqset *s = sg.set; u32 l = lo - sg.base;
+            k_idx_fill<<<hi - lo, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, lo, sl.tab_key, sl.tab_off, d_cur,
+                                                          sl.mask, sl.postings);
+            LAUNCHED(ctx);
+        }
+        CU(cudaGetLastError());
+        dfree(ctx, d_cur); dfree(ctx, d_sums);
+        db->slabs.push_back(sl);
+    }
+    // representatives without any k-mer (shorter than K): only the equal-sequence rule can match them
+    u32 *d_count = nullptr;
+    CU(dalloc(ctx, &db->d_empty_reps, db->n)); CU(dalloc(ctx, &d_count, 1));
+    CU(cudaMemsetAsync(d_count, 0, 4, ctx->stream));
+    k_collect_empty<<<(db->n + 255) / 256, 256, 0, ctx->stream>>>(db->d_meta, db->n, db->d_empty_reps, d_count);
+    LAUNCHED(ctx);
+    CU(cudaMemcpyAsync(&db->nempty, d_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d_count);
+    db->index_ready = true;
+    return KR_OK;
+}
+
+// K5: queries against the inverted index
+static kr_status find_closest_index(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *d_sim, u32 *d_first, u32 *d_last) {
+    kr_status st = db_build_index(ctx, db);
+    if (st) return st;
+    const u32 nslab = (u32)db->slabs.size();
+    int4 *d_partial = nullptr; u32 *d_next = nullptr;
+    CU(dalloc(ctx, &d_partial, (size_t)nslab * Q->n)); CU(dalloc(ctx, &d_next, nslab));
+    CU(cudaMemsetAsync(d_next, 0, 4 * nslab, ctx->stream));
+    {
+        StageTimer t(ctx, ST_JOIN);
+        for (u32 k = 0; k < nslab; ++k) {
+            const DbIndexSlab &sl = db->slabs[k];
+            IdxQueryParams p{};
+            p.qkeys = Q->d_keys; p.qkoff = Q->d_koff; p.qmeta = Q->d_meta; p.nq = Q->n;
+            p.tab_key = sl.tab_key; p.tab_off = sl.tab_off; p.tab_cnt = sl.tab_cnt; p.mask = sl.mask; p.postings = sl.postings;
+            p.rmeta = db->d_meta; p.rank = db->d_rank; p.slab_base = sl.base; p.slab_n = sl.n; p.flags = ctx->flags;
+            p.partial = d_partial + (size_t)k * Q->n; p.next = d_next + k;
+            u32 grid = std::min<u32>(Q->n, 2 * (u32)ctx->num_sms);
+            k_idx_query<<<grid, IDX_THREADS, ((size_t)sl.n + 1) / 2 * 4, ctx->stream>>>(p);
+            LAUNCHED(ctx); ctx->st.join_launches++;
+        }
+        if ((ctx->flags & KR_IDENT_IS_INFINITY) && db->nempty) {
+            k_idx_empty_queries<<<(Q->n * 32 + 255) / 256, 256, 0, ctx->stream>>>(Q->d_meta, Q->n, db->d_meta, db->d_rank, db->d_empty_reps,
+                                                                                  db->nempty, d_partial);
+            LAUNCHED(ctx);
+        }
+    }
+    {
+        StageTimer t(ctx, ST_OTHER);
+        k_idx_merge<<<(Q->n + 255) / 256, 256, 0, ctx->stream>>>(d_partial, Q->n, nslab, db->d_order, d_sim, d_first, d_last);
+        LAUNCHED(ctx);
+    }
+    CU(cudaGetLastError());
+    dfree(ctx, d_partial); dfree(ctx, d_next);
+    ctx->st.pairs += (u64)Q->n * db->n;
+    return KR_OK;
+}
+
 // queries x database: per-query best similarity with first/last rank (device outputs)
 static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *d_sim, u32 *d_first, u32 *d_last) {
     kr_status st;
     if ((st = db_refresh(ctx, db))) return st;
-    if ((st = ensure_blocklists(ctx, Q))) return st;
     if (Q->n == 0) return KR_OK;
+    // large query batches go through the inverted index (work ~ postings touched); small ones through the tile
+    // join (no index to build); both are exact
+    const bool use_index = db->n > 0 && !(ctx->flags & KR_FORCE_JOIN) && ((ctx->flags & KR_FORCE_INDEX) || Q->n >= 8192);
+    if (use_index) return find_closest_index(ctx, db, Q, d_sim, d_first, d_last);
+    if ((st = ensure_blocklists(ctx, Q))) return st;
     if (db->n == 0) {
         CU(cudaMemsetAsync(d_sim, 0, (size_t)Q->n * 4, ctx->stream));
         if (d_first) CU(cudaMemsetAsync(d_first, 0xFF, (size_t)Q->n * 4, ctx->stream));
@@ -839,6 +958,7 @@ void kr_db_free(kr_db *db) {
     cudaSetDevice(ctx->dev);
     for (auto &sg : db->segs) seqset_destroy(sg.set);
     db_free_arrays(db);
+    db_free_index(db);
     delete db;
 }
 uint32_t kr_db_size(const kr_db *db) { return db ? db->n : 0; }

@@ -704,3 +704,230 @@ __global__ void k_fill_u32_iota(u32 *p, u32 n, u32 base) {
 }
 
 }  // namespace kr
+
+// =============================================================================================
+// K4 / K5: inverted index (key -> posting list of representative indices) for query-vs-database scans.
+//
+//   table   open addressing, linear probing, capacity = power of two >= 2 x entries:
+//           tab_key[c] (uint64, EMPTY = ~0), tab_off[c] / tab_cnt[c] (uint32): postings[off .. off+cnt)
+//   query   one CTA per query at a time; a uint16 score per representative of the slab lives in shared
+//           memory (two per 32-bit word, same packing as the join's count tile).  Three walks over the
+//           posting lists of the query's keys: accumulate, find (max, first rank, last rank), clear.
+// A database larger than IDX_SLAB representatives is indexed in slabs; per-slab results are merged.
+namespace kr {
+
+constexpr u32 IDX_SLAB = 53248;                 // representatives per slab: 104 KB of scores, 2 CTAs per SM
+constexpr u32 IDX_THREADS = 256;
+constexpr u64 IDX_EMPTY = ~0ull;
+constexpr size_t IDX_SMEM = (size_t)IDX_SLAB * 2;
+
+__device__ __forceinline__ u32 idx_hash(u64 key, u32 mask) { return (u32)(mix64(key) >> 20) & mask; }
+
+// pass 1: claim a slot per distinct key and count its postings.  One CTA per representative.
+__global__ void __launch_bounds__(128) k_idx_insert(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq,
+                                                    unsigned long long *tab_key, u32 *tab_cnt, u32 mask) {
+    const u32 s = blockIdx.x;
+    if (s >= nseq) return;
+    const u32 n = meta[s].size;
+    const u64 *kp = keys + koff[s];
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+        const u64 key = kp[i];
+        u32 slot = idx_hash(key, mask);
+        for (;;) {
+            unsigned long long old = atomicCAS(&tab_key[slot], (unsigned long long)IDX_EMPTY, (unsigned long long)key);
+            if (old == IDX_EMPTY || old == key) { atomicAdd(&tab_cnt[slot], 1u); break; }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+// exclusive scan of tab_cnt -> tab_off in three kernels (tile sums, scan of the sums, tile scan)
+constexpr u32 SCAN_TILE = 4096;
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const u32 *in, u64 n, u32 *sums) {
+    __shared__ u32 ws[8];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE;
+    u32 acc = 0;
+    for (u32 i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) acc += in[base + i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { u32 t = 0; for (int k = 0; k < 8; ++k) t += ws[k]; sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(u32 *sums, u32 n) {   // in place, exclusive; one CTA
+    __shared__ u32 part[1024];
+    const u32 tid = threadIdx.x, per = (n + 1023) / 1024;
+    const u32 b0 = min(n, tid * per), b1 = min(n, b0 + per);
+    u32 acc = 0;
+    for (u32 i = b0; i < b1; ++i) acc += sums[i];
+    part[tid] = acc;
+    __syncthreads();
+    if (tid == 0) { u32 run = 0; for (int i = 0; i < 1024; ++i) { u32 v = part[i]; part[i] = run; run += v; } }
+    __syncthreads();
+    u32 run = part[tid];
+    for (u32 i = b0; i < b1; ++i) { u32 v = sums[i]; sums[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(256) k_scan_tiles(const u32 *in, u64 n, const u32 *sums, u32 *out) {
+    __shared__ u32 wtot[8];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // thread t owns 16 consecutive elements
+    u32 v[16], acc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { u64 i = base + tid * 16 + k; v[k] = i < n ? in[i] : 0; acc += v[k]; }
+    u32 incl = acc;
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    u32 wbase = 0;
+    for (u32 k = 0; k < warp; ++k) wbase += wtot[k];
+    u32 run = sums[blockIdx.x] + wbase + incl - acc;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { u64 i = base + tid * 16 + k; if (i < n) out[i] = run; run += v[k]; }
+}
+
+// pass 2: write the postings (order inside a list is arbitrary; only counts matter)
+__global__ void __launch_bounds__(128) k_idx_fill(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq, u32 rep_base,
+                                                  const unsigned long long *tab_key, const u32 *tab_off, u32 *tab_cur, u32 mask,
+                                                  u32 *postings) {
+    const u32 s = blockIdx.x;
+    if (s >= nseq) return;
+    const u32 n = meta[s].size;
+    const u64 *kp = keys + koff[s];
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+        const u64 key = kp[i];
+        u32 slot = idx_hash(key, mask);
+        while (tab_key[slot] != key) slot = (slot + 1) & mask;
+        postings[tab_off[slot] + atomicAdd(&tab_cur[slot], 1u)] = rep_base + s;
+    }
+}
+
+struct IdxQueryParams {
+    const u64 *qkeys; const u64 *qkoff; const SeqMeta *qmeta; u32 nq;
+    const unsigned long long *tab_key; const u32 *tab_off; const u32 *tab_cnt; u32 mask; const u32 *postings;
+    const SeqMeta *rmeta; const u32 *rank;   // database-wide arrays
+    u32 slab_base, slab_n;                   // representatives [slab_base, slab_base + slab_n) are in this index
+    u32 flags;
+    int4 *partial;                           // [nq] (sim, first rank, last rank)
+    u32 *next;                               // work counter
+};
+
+__global__ void __launch_bounds__(IDX_THREADS, 2) k_idx_query(IdxQueryParams p) {
+    extern __shared__ __align__(16) u32 score[];   // (slab_n + 1) / 2 words, zero between queries
+    __shared__ u32 s_q;
+    __shared__ unsigned long long s_first[IDX_THREADS / 32], s_last[IDX_THREADS / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 i = tid; i < (p.slab_n + 1) / 2; i += IDX_THREADS) score[i] = 0;
+    const bool ident_inf = (p.flags & 1u) != 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_q = atomicAdd(p.next, 1u);
+        __syncthreads();
+        const u32 q = s_q;
+        if (q >= p.nq) break;
+        const SeqMeta qm = p.qmeta[q];
+        const u32 n = qm.size;
+        const u64 *kp = p.qkeys + p.qkoff[q];
+        // walk 1: accumulate
+        for (u32 i = tid; i < n; i += IDX_THREADS) {
+            const u64 key = kp[i];
+            u32 slot = idx_hash(key, p.mask);
+            unsigned long long k2;
+            while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
+            if (k2 == key) {
+                const u32 off = p.tab_off[slot], c = p.tab_cnt[slot];
+                for (u32 t = 0; t < c; ++t) {
+                    const u32 r = p.postings[off + t] - p.slab_base;
+                    atomicAdd(&score[r >> 1], (r & 1) ? 0x10000u : 1u);
+                }
+            }
+        }
+        __syncthreads();
+        // walk 2: maximum with first / last rank among the maxima; packed as (sim << 32) | key so one max finds both
+        unsigned long long bf = 0, bl = 0;   // first: key = ~rank (smaller rank wins), last: key = rank
+        for (u32 i = tid; i < n; i += IDX_THREADS) {
+            const u64 key = kp[i];
+            u32 slot = idx_hash(key, p.mask);
+            unsigned long long k2;
+            while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
+            if (k2 == key) {
+                const u32 off = p.tab_off[slot], c = p.tab_cnt[slot];
+                for (u32 t = 0; t < c; ++t) {
+                    const u32 g = p.postings[off + t], r = g - p.slab_base;
+                    u32 s = (score[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
+                    // the equal-sequence rule: an identical representative holds every key of the query, so it is
+                    // enough to test it while walking the query's first key
+                    if (ident_inf && i == 0 && s == n) { const SeqMeta rm = p.rmeta[g]; if (rm.size == n && seq_equal(qm, rm)) s = KR_INF; }
+                    if (s >= (u32)(bf >> 32)) {
+                        const u32 rk = p.rank[g];
+                        const unsigned long long cf = ((unsigned long long)s << 32) | (0xFFFFFFFFu - rk);
+                        const unsigned long long cl = ((unsigned long long)s << 32) | rk;
+                        bf = cf > bf ? cf : bf; bl = cl > bl ? cl : bl;
+                    }
+                }
+            }
+        }
+        // an identical representative of a query shorter than K shares no key with it: handled by the caller
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long t1 = __shfl_xor_sync(0xffffffffu, bf, o), t2 = __shfl_xor_sync(0xffffffffu, bl, o);
+            bf = t1 > bf ? t1 : bf; bl = t2 > bl ? t2 : bl;
+        }
+        if (lane == 0) { s_first[warp] = bf; s_last[warp] = bl; }
+        __syncthreads();
+        if (tid == 0) {
+            for (u32 k = 1; k < IDX_THREADS / 32; ++k) { bf = s_first[k] > bf ? s_first[k] : bf; bl = s_last[k] > bl ? s_last[k] : bl; }
+            const int sim = (int)(bf >> 32);
+            p.partial[q] = make_int4(sim, sim ? (int)(0xFFFFFFFFu - (u32)bf) : -1, sim ? (int)(u32)bl : 0, 0);
+        }
+        // walk 3: clear the touched scores
+        for (u32 i = tid; i < n; i += IDX_THREADS) {
+            const u64 key = kp[i];
+            u32 slot = idx_hash(key, p.mask);
+            unsigned long long k2;
+            while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
+            if (k2 == key) {
+                const u32 off = p.tab_off[slot], c = p.tab_cnt[slot];
+                for (u32 t = 0; t < c; ++t) { const u32 r = p.postings[off + t] - p.slab_base; score[r >> 1] = 0; }
+            }
+        }
+    }
+}
+
+// queries with no k-mer at all (shorter than K): under the equal-sequence rule they still match an identical
+// representative.  One warp per such query scans the (few) representatives that are also empty.
+__global__ void k_idx_empty_queries(const SeqMeta *qmeta, u32 nq, const SeqMeta *rmeta, const u32 *rank, const u32 *empty_reps,
+                                    u32 nempty, int4 *partial) {
+    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const SeqMeta qm = qmeta[q];
+    if (qm.size != 0) return;
+    u32 rf = 0xFFFFFFFFu, rl = 0; bool any = false;
+    for (u32 e = lane; e < nempty; e += 32) {
+        const u32 g = empty_reps[e];
+        if (seq_equal(qm, rmeta[g])) { any = true; rf = min(rf, rank[g]); rl = max(rl, rank[g]); }
+    }
+    any = __any_sync(0xffffffffu, any);
+    for (int o = 16; o > 0; o >>= 1) { rf = min(rf, __shfl_xor_sync(0xffffffffu, rf, o)); rl = max(rl, __shfl_xor_sync(0xffffffffu, rl, o)); }
+    if (lane == 0 && any) partial[q] = make_int4(KR_INF, (int)rf, (int)rl, 0);
+}
+
+// merge per-slab partials (partial[slab * nq + q]) and turn ranks into representative indices
+__global__ void k_idx_merge(const int4 *partial, u32 nq, u32 nslab, const u32 *order, int *best_sim, u32 *best_first, u32 *best_last) {
+    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int bs = 0; u32 bf = 0xFFFFFFFFu, bl = 0;
+    for (u32 s = 0; s < nslab; ++s) {
+        const int4 v = partial[(size_t)s * nq + q];
+        if (v.x > bs) { bs = v.x; bf = (u32)v.y; bl = (u32)v.z; }
+        else if (v.x == bs && v.x > 0) { bf = min(bf, (u32)v.y); bl = max(bl, (u32)v.z); }
+    }
+    best_sim[q] = bs;
+    if (best_first) best_first[q] = bs > 0 ? order[bf] : 0xFFFFFFFFu;
+    if (best_last) best_last[q] = bs > 0 ? order[bl] : 0xFFFFFFFFu;
+}
+
+__global__ void k_collect_empty(const SeqMeta *meta, u32 n, u32 *out, u32 *count) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && meta[i].size == 0) out[atomicAdd(count, 1u)] = i;
+}
+
+}  // namespace kr

@@ -271,3 +271,76 @@ def test_greedy_build_matches_oracle(oracle, rep50, rickettsia):
     got = db3.greedy_build(c.encode(reps), 50, batch=300)
     assert not got[:700].any() and got[700:].all() and db3.size == 1480
     c.close()
+
+
+# ---- inverted index path of findClosest (K4/K5) ------------------------------------------------------
+def test_index_path_matches_join_and_oracle(rep50, gto_seeds, rickettsia, oracle, expected):
+    reps = [s for (_, _, s) in rep50["reps"]]
+    qs = [s for (_, _, s) in gto_seeds] + [p for (_, p) in rickettsia] + reps[:300] + ["", "ACD", "MKV"]
+    orp, oq = oracle.batch(reps, K=8), oracle.batch(qs, K=8)
+    for flags in (kr.IDENT_IS_INFINITY, 0):
+        bs, bi = oracle.find_closest(orp, oq, ident_inf=bool(flags), threads=8)
+        want_first = np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)
+        for force in (kr.FORCE_INDEX, kr.FORCE_JOIN):
+            c = kr.Context(device=0, K=8, flags=flags | force)
+            db = c.db()
+            db.append(reps[:900])
+            db.append(reps[900:])
+            sim, first, last = db.find_closest(c.encode(qs))
+            assert (sim == bs).all(), (flags, force)
+            assert (first.astype(np.int64) == want_first).all(), (flags, force)
+            c.close()
+    for i, e in enumerate(expected["config1"]):
+        assert bs[i] == e["sim"]
+
+
+def test_index_path_ties_ranks_and_short_sequences(oracle):
+    res, off, _ = synth.generate(78, 1500, 15, dup_per_10k=2500)
+    seqs = synth.to_strings(res, off)
+    reps = seqs[:1000] + ["", "ACDE", "ACDE", "MKVLAAG"]          # representatives shorter than K
+    qs = seqs[1000:] + ["ACDE", "", "MKVLAAG", "MKVLAAH", seqs[5]]
+    rng = np.random.default_rng(4)
+    order = rng.permutation(len(reps)).astype(np.int32)
+    rank = np.empty(len(reps), dtype=np.uint32)
+    rank[order] = np.arange(len(reps), dtype=np.uint32)
+    orp, oq = oracle.batch(reps, K=8), oracle.batch(qs, K=8)
+    for flags in (0, kr.IDENT_IS_INFINITY):
+        bs, bi = oracle.find_closest(orp, oq, order=order, ident_inf=bool(flags))
+        bs2, bi2 = oracle.find_closest(orp, oq, order=order, ident_inf=bool(flags), tie_last=True)
+        for force in (kr.FORCE_INDEX, kr.FORCE_JOIN):
+            c = kr.Context(device=0, K=8, flags=flags | force)
+            db = c.db()
+            db.append(reps)
+            db.set_ranks(rank)
+            sim, first, last = db.find_closest(c.encode(qs))
+            assert (sim == bs).all() and (sim == bs2).all(), (flags, force)
+            assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), (flags, force)
+            assert (last.astype(np.int64) == np.where(bs2 > 0, bi2.astype(np.int64), kr.NO_REP)).all(), (flags, force)
+            c.close()
+    assert (first != last).any()
+
+
+def test_index_path_multi_slab_large_batch(oracle):
+    # more representatives than one index slab (53,248) and a batch large enough to take the index path by itself
+    res, off, _ = synth.generate(0x5EED0005, 80000, 1600)
+    nrep = 60000
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    db = c.db()
+    db.append(res=res[: int(off[nrep])], off=off[: nrep + 1])
+    q = c.encode(res=res[int(off[nrep]):], off=off[nrep:] - off[nrep])
+    assert q.count >= 8192
+    sim, first, last = db.find_closest(q)
+    cj = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_JOIN)
+    dbj = cj.db()
+    dbj.append(res=res[: int(off[nrep])], off=off[: nrep + 1])
+    simj, firstj, lastj = dbj.find_closest(cj.encode(res=res[int(off[nrep]):], off=off[nrep:] - off[nrep]))
+    assert (sim == simj).all() and (first == firstj).all() and (last == lastj).all()
+    # and a sample of them against the oracle
+    pick = np.random.default_rng(8).choice(q.count, 150, replace=False)
+    orp = oracle.batch(res=res[: int(off[nrep])], off=off[: nrep + 1], K=8)
+    qsel = [res[int(off[nrep + i]): int(off[nrep + i + 1])].tobytes().decode() for i in pick]
+    bs, bi = oracle.find_closest(orp, oracle.batch(qsel, K=8), threads=16)
+    assert (sim[pick] == bs).all()
+    assert (first[pick].astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
+    c.close()
+    cj.close()
