@@ -130,8 +130,132 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_findclosest(args, rank, world, local):
+    """Secondary workloads (BASELINE configs[3] and [4]): greedy rep-DB build at threshold 50 over synthetic
+    candidates, then findClosest of synthetic queries against the first --nrep representatives.  Queries are
+    sharded by rank against a replicated database; per-query results are all-gathered (12 B/query)."""
+    import torch
+    import torch.distributed as dist
+    import kmers.reps_b200 as kr
+    from kmers.reps_b200 import sharding, synth
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ncand, nq, nrep = args.ncand, args.nq, args.nrep
+    t0 = time.perf_counter()
+    res, off, fam = synth.generate(0x5EED0005, ncand + nq, max(1, ncand // 50), xrun_per_10k=10)
+    gen_s = time.perf_counter() - t0
+    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY)
+    # ---- config 4: greedy build (replicated on every rank: the accept/reject sweep is sequential) ----
+    cands = ctx.encode(res=res[: int(off[ncand])], off=off[: ncand + 1])
+    db = ctx.db()
+    ctx.synchronize()
+    ctx.stats_reset()
+    t0 = time.perf_counter()
+    added = db.greedy_build(cands, 50, batch=args.build_batch)
+    build_s = time.perf_counter() - t0
+    st_build = ctx.stats()
+    nreps_built = int(added.sum())
+    acc = np.nonzero(added)[0][:nrep].astype(np.uint32)
+    qdb = ctx.db()
+    qdb.append_set(cands, acc)
+    R = qdb.size
+    # ---- config 5: findClosest, queries sharded by rank --------------------------------------------
+    lo, hi = sharding.shard_range(nq, rank, world)
+    q_res = torch.from_numpy(res[int(off[ncand + lo]): int(off[ncand + hi])]).cuda()
+    q_off = off[ncand + lo: ncand + hi + 1] - off[ncand + lo]
+    myq = hi - lo
+    d_sim = torch.empty(myq, dtype=torch.int32, device="cuda")
+    d_first = torch.empty(myq, dtype=torch.int32, device="cuda")
+    d_last = torch.empty(myq, dtype=torch.int32, device="cuda")
+    chunk = args.q_chunk
+
+    def step():
+        sets = []
+        for a in range(0, myq, chunk):
+            b = min(myq, a + chunk)
+            qs = ctx.encode_device(q_res.data_ptr() + int(q_off[a]), q_off[a: b + 1] - q_off[a])
+            qdb.find_closest_device(qs, d_sim.data_ptr() + 4 * a, d_first.data_ptr() + 4 * a, d_last.data_ptr() + 4 * a)
+            sets.append(qs)
+        return sets
+
+    for s_ in step():
+        s_.free()
+    ctx.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ctx.stats_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.timer_begin()
+    allsets = []
+    for _ in range(args.steps):
+        allsets += step()
+    ms = ctx.timer_end()
+    clocks = sampler.stop() if rank == 0 else None
+    st = ctx.stats()
+    for s_ in allsets:
+        s_.free()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    gather_ms = None
+    if world > 1:
+        local_res = torch.stack([d_sim, d_first, d_last], 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        allres = sharding.allgather_ranges(local_res, nq, dist)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = e0.elapsed_time(e1)
+        assert allres.shape[0] == nq
+    # verify a sample against the oracle
+    from oracle import kr_oracle as ko
+    o = ko.get()
+    rep_idx = acc
+    reps_b = o.batch([res[int(off[i]): int(off[i + 1])].tobytes().decode() for i in rep_idx], K=8)
+    pick = np.random.default_rng(5 + rank).choice(myq, min(100, myq), replace=False)
+    qsel = [res[int(off[ncand + lo + i]): int(off[ncand + lo + i + 1])].tobytes().decode() for i in pick]
+    bs, bi = o.find_closest(reps_b, o.batch(qsel, K=8), threads=os.cpu_count() or 1)
+    got_sim = d_sim[torch.from_numpy(pick).cuda()].cpu().numpy()
+    got_first = d_first[torch.from_numpy(pick).cuda()].cpu().numpy()
+    ok = (got_sim == bs).all() and (got_first == np.where(bs > 0, bi, -1)).all()
+    if not ok:
+        raise SystemExit("bench: findClosest differs from the oracle on sampled queries")
+    if rank == 0:
+        line = {
+            "metric": "findClosest queries/sec", "value": nq / (ms_per_step / 1e3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": 1, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "findClosest of %d synthetic queries against a %d-rep DB (BASELINE configs[4]); DB = first %d reps of a "
+                                   "greedy build at threshold 50 over %d synthetic candidates (configs[3])" % (nq, R, R, ncand),
+                       "K": 8, "path": "inverted index" if chunk >= 8192 else "tile join", "query_chunk": chunk,
+                       "sharding": "queries split over %d rank(s), DB replicated, results all-gathered" % world},
+            "pair_equivalents_per_s": nq * R / (ms_per_step / 1e3),
+            "greedy_build": {"candidates": ncand, "reps": nreps_built, "seconds": build_s, "candidates_per_s": ncand / build_s,
+                             "pair_equivalents": int(st_build["pairs"]), "kernel_ms": {k: st_build[k] for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
+                             "launches": int(st_build["kernel_launches"])},
+            "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
+            "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "result_allgather_ms": gather_ms,
+            "generate_s": gen_s, "verified": "100 sampled queries per rank equal the oracle",
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="allvsall", choices=["allvsall", "findclosest"])
+    ap.add_argument("--ncand", type=int, default=1000000)
+    ap.add_argument("--nq", type=int, default=10000000)
+    ap.add_argument("--nrep", type=int, default=50000)
+    ap.add_argument("--q-chunk", type=int, default=1000000)
+    ap.add_argument("--build-batch", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -151,6 +275,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "findclosest":
+        run_findclosest(args, rank, world, local)
         return
 
     import torch

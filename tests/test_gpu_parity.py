@@ -344,3 +344,42 @@ def test_index_path_multi_slab_large_batch(oracle):
     assert (first[pick].astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
     c.close()
     cj.close()
+
+
+def test_greedy_build_properties_at_scale():
+    """Sizes the oracle cannot reach: the domain's own invariants.  (a) stingy-add: no two representatives reach
+    the threshold; (b) every rejected candidate is represented; (c) the result does not depend on the batch size;
+    (d) all-vs-all at this size agrees with the independent per-pair kernel and is symmetric."""
+    import torch
+    n, thr = 120000, 50
+    res, off, _ = synth.generate(0x5EED0004, n, n // 50, xrun_per_10k=10)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    cands = c.encode(res=res, off=off)
+    db = c.db()
+    added = db.greedy_build(cands, thr)
+    db2 = c.db()
+    assert (db2.greedy_build(cands, thr, batch=1500) == added).all()              # (c)
+    rep_idx = np.nonzero(added)[0].astype(np.uint32)
+    R = len(rep_idx)
+    assert db.size == R and 5000 < R < n
+    reps = cands.gather(rep_idx)
+    ne = kr.matrix_elems(R, R, kr.LAYOUT_FULL)
+    out = torch.empty(ne, dtype=torch.int16, device="cuda")
+    c.sim_matrix_device(reps, None, out.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL)
+    c.synchronize()
+    m = out.view(R, R)
+    assert bool((m == m.T).all())                                                  # (d) symmetry
+    assert bool((torch.diagonal(m) == kr.INFINITY).all())
+    offdiag = m.clone()
+    offdiag.fill_diagonal_(0)
+    assert int(offdiag.max()) < thr                                                # (a)
+    rng = np.random.default_rng(2)
+    ia, ib = rng.integers(0, R, 20000), rng.integers(0, R, 20000)
+    sim, _ = c.sim_pairs(reps, ia, reps, ib)
+    got = m[torch.from_numpy(ia).cuda(), torch.from_numpy(ib).cuda()].cpu().numpy().astype(np.int32)
+    assert (sim == got).all()                                                      # (d) two kernels agree
+    del m, offdiag, out
+    rej = np.nonzero(added == 0)[0].astype(np.uint32)
+    best, first, _ = db.find_closest(cands.gather(rej))
+    assert (best >= thr).all()                                                     # (b)
+    c.close()
