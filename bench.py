@@ -171,16 +171,13 @@ def run_findclosest(args, rank, world, local):
     chunk = args.q_chunk
 
     def step():
-        sets = []
         for a in range(0, myq, chunk):
             b = min(myq, a + chunk)
             qs = ctx.encode_device(q_res.data_ptr() + int(q_off[a]), q_off[a: b + 1] - q_off[a])
             qdb.find_closest_device(qs, d_sim.data_ptr() + 4 * a, d_first.data_ptr() + 4 * a, d_last.data_ptr() + 4 * a)
-            sets.append(qs)
-        return sets
+            qs.free()        # stream-ordered
 
-    for s_ in step():
-        s_.free()
+    step()
     ctx.synchronize()
     if world > 1:
         dist.barrier()
@@ -190,14 +187,11 @@ def run_findclosest(args, rank, world, local):
     if rank == 0:
         sampler.start()
     ctx.timer_begin()
-    allsets = []
     for _ in range(args.steps):
-        allsets += step()
+        step()
     ms = ctx.timer_end()
     clocks = sampler.stop() if rank == 0 else None
     st = ctx.stats()
-    for s_ in allsets:
-        s_.free()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -309,13 +303,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sets = [step() for _ in range(args.warmup)]
+    prev = None
+    for _ in range(args.warmup):
+        cur = step()
+        if prev is not None:
+            prev.free()
+        prev = cur
     ctx.synchronize()
-    for s in sets[:-1]:
-        s.free()
-    last_set = sets[-1]
-    sizes = last_set.sizes().astype(np.int64)
-    last_set.free()
+    sizes = prev.sizes().astype(np.int64)
 
     # ---- timed region: device-resident inputs --------------------------------------------------
     barrier()
@@ -324,13 +319,15 @@ def main():
     if rank == 0:
         sampler.start()
     ctx.timer_begin()
-    sets = [step() for _ in range(args.steps)]
+    for _ in range(args.steps):
+        cur = step()
+        prev.free()          # stream-ordered: the previous step's set goes back to the pool, as a real caller would
+        prev = cur
     ms = ctx.timer_end()
     clocks = sampler.stop() if rank == 0 else None
     barrier()
     st = ctx.stats()
-    for s in sets:
-        s.free()
+    prev.free()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -31,7 +31,7 @@ constexpr u64 LID_MASK = 0xFFull;
 constexpr int NCHUNK = KR_NCHUNK;  // key-range chunks per block list (32 or 64)
 constexpr int CHUNK_ALIGN = 16;  // chunk starts are multiples of 16 entries (128 B)
 #ifndef KR_STAGE_CAP
-#define KR_STAGE_CAP 1536
+#define KR_STAGE_CAP 2040
 #endif
 #ifndef KR_NSTAGE
 #define KR_NSTAGE 4
@@ -40,9 +40,11 @@ constexpr int CHUNK_ALIGN = 16;  // chunk starts are multiples of 16 entries (12
 #define KR_NCWARP 24
 #endif
 #ifndef KR_ILP
-#define KR_ILP 2
+#define KR_ILP 4
 #endif
-constexpr int STAGE_CAP = KR_STAGE_CAP;  // entries per side per pipeline stage
+constexpr int STAGE_CAP = KR_STAGE_CAP;  // entries per side per job (a multiple of 8 so sub-chunk starts stay 16-byte aligned)
+constexpr int STAGE_BUF = (STAGE_CAP + 7) / 8 * 8;   // entries reserved per side in a stage
+static_assert(STAGE_CAP % 8 == 0, "sub-chunk starts must stay 16-byte aligned for the TMA copies");
 constexpr int NSTAGE = KR_NSTAGE;
 #ifndef KR_STEP_TOP
 #define KR_STEP_TOP 1024
@@ -55,13 +57,19 @@ static_assert(STAGE_CAP <= WINDOW - 1, "a staged B sub-chunk must fit the probe 
 constexpr int NCWARP = KR_NCWARP;  // consumer warps of the join kernel (+1 producer warp)
 constexpr int ILP = KR_ILP;        // A entries searched together per lane
 constexpr int JOIN_THREADS = (NCWARP + 1) * 32;
+#ifndef KR_NGROUP
+#define KR_NGROUP 2
+#endif
+constexpr int NGROUP = KR_NGROUP;  // consumer warp groups; the jobs of a tile are dealt to the groups round-robin
+constexpr int GW = NCWARP / NGROUP;
+static_assert(NCWARP % NGROUP == 0, "consumer warps must split evenly into groups");
 constexpr u64 SENT = ~0ull;
 constexpr int KR_INF = 9999;
 constexpr int LUT_BITS = 15;     // chunk table is indexed by the first three residues of the key
 
 constexpr size_t JOIN_SMEM_CNT = (size_t)TB * TB * 2;                         // u16 count tile
 // one pipeline stage: A hi | B hi window | A lo | B lo
-__host__ __device__ constexpr size_t stage_bytes(bool lo32) { return (size_t)STAGE_CAP * 4 + WINDOW * 4 + 2 * (size_t)STAGE_CAP * (lo32 ? 4 : 2); }
+__host__ __device__ constexpr size_t stage_bytes(bool lo32) { return (size_t)STAGE_BUF * 4 + WINDOW * 4 + 2 * (size_t)STAGE_BUF * (lo32 ? 4 : 2); }
 __host__ __device__ constexpr int nstage(bool lo32) { return lo32 ? NSTAGE - 1 : NSTAGE; }
 __host__ __device__ constexpr size_t join_smem_bytes(bool lo32) { return JOIN_SMEM_CNT + nstage(lo32) * stage_bytes(lo32) + 256; }
 constexpr size_t JOIN_SMEM_BYTES = join_smem_bytes(false) > join_smem_bytes(true) ? join_smem_bytes(false) : join_smem_bytes(true);
@@ -316,19 +324,34 @@ __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
 __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(u64 *bar, u32 count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(u64 *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Wait for the phase of the given parity.  try_wait suspends in hardware, so the loop turns slowly; a wait that
+// does not end within ~2^24 polls (seconds) is a protocol bug: trap (the launch fails) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 done;
+    const u32 addr = smem_u32(bar);
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    for (u32 spins = 0;; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) __trap();
+    }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -381,9 +404,9 @@ __device__ __forceinline__ u32 lds16(u32 addr) {
 template <bool LO32> __device__ __forceinline__ u32 ldlo(u32 base, u32 i) { return LO32 ? lds32(base + i * 4) : lds16(base + i * 2); }
 
 // All matches of the staged A entries against the staged B sub-chunk -> count tile.
-//   * a pass is 32*ILP consecutive A entries (ILP per lane, searched together); passes are dealt to the
-//     consumer warps round-robin across job boundaries (pass counter `pc`), so consecutive jobs land on
-//     different warps and overlap instead of queueing behind the same ones;
+//   * a pass is 32*ILP consecutive A entries (ILP per lane, searched together); the passes of a job are dealt
+//     round-robin to the GW warps of the group that owns the job, continuing across the group's jobs
+//     (pass counter `pc`);
 //   * the lower bound runs on the 32-bit hi words only.  The B window always holds WINDOW staged words and
 //     everything past the sub-chunk is >= every target of this chunk (later chunks, or sentinels), so the
 //     binary lifting needs neither a bounds check nor a clamp; the position is kept as an absolute shared
@@ -392,9 +415,9 @@ template <bool LO32> __device__ __forceinline__ u32 ldlo(u32 base, u32 i) { retu
 template <bool LO32>
 __device__ __forceinline__ void join_job(u32 sAhi, u32 sAlo, u32 na, u32 sBhi, u32 sBlo, u32 nb, u32 *cnt, u32 warp,
                                          u32 lane, u32 pc) {
-    const u32 w = (warp + NCWARP - pc % NCWARP) % NCWARP;   // first pass of this job that falls to this warp
+    const u32 w = (warp + GW - pc % GW) % GW;   // first pass of this job that falls to this warp (warp = index in group)
     const u32 sBm = sBhi - 4;
-    for (u32 base = w * (32 * ILP); base < na; base += NCWARP * 32 * ILP) {
+    for (u32 base = w * (32 * ILP); base < na; base += GW * 32 * ILP) {
         u32 th[ILP], p[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
@@ -440,21 +463,22 @@ __device__ __forceinline__ void join_job(u32 sAhi, u32 sAlo, u32 na, u32 sBhi, u
 }
 
 // Job flags published by the producer with every pipeline slot
-constexpr u32 JF_TILE_END = 1;   // slot carries no data: tile (I,J) is complete, run its epilogue
-constexpr u32 JF_TASK_END = 2;   // ... and it was the last J of the task
-constexpr u32 JF_DONE = 4;       // no more work for this CTA
+constexpr u32 JF_TASK_END = 2;   // head slot: this tile is the last J of its task
+constexpr u32 JF_DONE = 4;       // head slot: no more work for this CTA
 
 // The kernel is warp-specialised.  Warp NCWARP is the producer: it alone walks tasks -> tiles -> chunk pairs ->
-// sub-chunks, and for every job waits for a free stage, publishes a 16-byte descriptor (na, nb, flags, J) and
-// issues the four TMA bulk copies that complete the stage's full barrier.  The NCWARP consumer warps only wait
-// on full barriers, read the descriptor and search; they meet at a named barrier twice per tile (epilogue).
+// sub-chunks.  Per tile it first publishes a HEAD slot (number of jobs of the tile, J, flags) that every consumer
+// warp reads, then one slot per job: wait for a free stage, write a 16-byte descriptor (na, nb) and issue the four
+// TMA bulk copies that complete the stage's full barrier.  The NCWARP consumer warps form NGROUP groups; job r of
+// a tile belongs to group r % NGROUP, so only GW warps pay the wait/arrive cost of a job and the groups work on
+// different jobs at the same time.  All consumers meet at a named barrier twice per tile (epilogue).
 template <int MODE, bool LO32>
 __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
     extern __shared__ __align__(128) u8 smem[];
     constexpr int NST = nstage(LO32);
     constexpr u32 LOSZ = LO32 ? 4 : 2;
     constexpr u32 STAGE_B = (u32)stage_bytes(LO32);
-    constexpr u32 OFF_BHI = STAGE_CAP * 4, OFF_ALO = OFF_BHI + WINDOW * 4, OFF_BLO = OFF_ALO + STAGE_CAP * LOSZ;
+    constexpr u32 OFF_BHI = STAGE_BUF * 4, OFF_ALO = OFF_BHI + WINDOW * 4, OFF_BLO = OFF_ALO + STAGE_BUF * LOSZ;
     u32 *cnt = reinterpret_cast<u32 *>(smem);
     u8 *stage = smem + JOIN_SMEM_CNT;
     u64 *full = reinterpret_cast<u64 *>(smem + JOIN_SMEM_CNT + (size_t)NST * STAGE_B);
@@ -482,7 +506,7 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
 #if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 4)
                 if (p.nA != 0xFFFFFFFFu) { mbar_arrive(&full[s]); } else
 #endif
-                if (na) {
+                if (na && !(flags & 1u)) {
                     const u32 bAhi = ((na + 3) & ~3u) * 4, bAlo = LO32 ? ((na + 3) & ~3u) * 4 : ((na + 7) & ~7u) * 2;
                     const u32 bBlo = LO32 ? ((nb + 3) & ~3u) * 4 : ((nb + 7) & ~7u) * 2;
                     mbar_expect_tx(&full[s], bAhi + WINDOW * 4 + bAlo + bBlo);
@@ -496,6 +520,7 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
             }
             ++k;
         };
+        constexpr u32 HEAD = 1u;   // descriptor flag bit 0: head slot (x = jobs of the tile, w = J)
         static_assert(NCHUNK == 64 || NCHUNK == 32, "chunk tables are held as one or two registers per lane");
         constexpr int HI = NCHUNK > 32 ? 32 : 0;   // offset of the second table register (unused for 32 chunks)
         BlockRef a{}, b{};
@@ -510,6 +535,15 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
             for (u32 J = j0; J < j1; ++J) {
                 b = p.B[J];
                 const u32 tBc0 = __ldg(b.cnt + lane), tBc1 = __ldg(b.cnt + HI + lane), tBo0 = __ldg(b.off + lane), tBo1 = __ldg(b.off + HI + lane);
+                // jobs of this tile: each lane counts the sub-chunk pairs of its one or two chunks
+                u32 mine = 0;
+                {
+                    const u32 x0 = (tAc0 + STAGE_CAP - 1) / STAGE_CAP * ((tBc0 + STAGE_CAP - 1) / STAGE_CAP);
+                    const u32 x1 = (tAc1 + STAGE_CAP - 1) / STAGE_CAP * ((tBc1 + STAGE_CAP - 1) / STAGE_CAP);
+                    mine = x0 + (NCHUNK > 32 ? x1 : 0);
+                }
+                for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+                emit(mine, 0, HEAD | (J + 1 == j1 ? JF_TASK_END : 0), J, a, b, 0, 0);
                 for (int c = 0; c < NCHUNK; ++c) {
                     const u32 nAc = __shfl_sync(0xffffffffu, c < 32 ? tAc0 : tAc1, c & 31);
                     const u32 nBc = __shfl_sync(0xffffffffu, c < 32 ? tBc0 : tBc1, c & 31);
@@ -520,35 +554,45 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
                         for (u32 bs = 0; bs < nBc; bs += STAGE_CAP)
                             emit(min((u32)STAGE_CAP, nAc - as), min((u32)STAGE_CAP, nBc - bs), 0, J, a, b, oA + as, oB + bs);
                 }
-                emit(0, 0, JF_TILE_END | (J + 1 == j1 ? JF_TASK_END : 0), J, a, b, 0, 0);
             }
         }
-        emit(0, 0, JF_DONE, 0, a, b, 0, 0);
+        emit(0, 0, HEAD | JF_DONE, 0, a, b, 0, 0);
         return;
     }
 
     // ==================================== consumers ===============================================
     u32 k = 0, pc = 0;
     u32 task = blockIdx.x;
+    const u32 grp = warp / GW, gw = warp % GW;
     // ARGMAX: row r of the tile is owned by warp r%NCWARP, its running best lives in lane r/NCWARP
     int best_sim = 0; u32 best_first = 0xFFFFFFFFu, best_last = 0;
     for (;;) {
-        const u32 s = k % NST, ph = (k / NST) & 1;
-        mbar_wait(&full[s], ph);
-        const uint4 d = desc[s];
-        if (d.x) {
+        // head slot of the next tile: read by every consumer warp
+        uint4 d;
+        {
+            const u32 s = k % NST, ph = (k / NST) & 1;
+            mbar_wait(&full[s], ph);
+            d = desc[s];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            ++k;
+        }
+        if (d.z & JF_DONE) break;
+        // this group's jobs of the tile
+        for (u32 r = grp; r < d.x; r += NGROUP) {
+            const u32 kk = k + r, s = kk % NST, ph = (kk / NST) & 1;
+            mbar_wait(&full[s], ph);
+            const uint4 dj = desc[s];
             const u32 sb = smem_u32(stage + (size_t)s * STAGE_B);
 #if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 1)
             if (p.nA == 0xFFFFFFFFu)
 #endif
-            join_job<LO32>(sb, sb + OFF_ALO, d.x, sb + OFF_BHI, sb + OFF_BLO, d.y, cnt, warp, lane, pc);
-            pc += (d.x + 32 * ILP - 1) / (32 * ILP);
+            join_job<LO32>(sb, sb + OFF_ALO, dj.x, sb + OFF_BHI, sb + OFF_BLO, dj.y, cnt, gw, lane, pc);
+            pc += (dj.x + 32 * ILP - 1) / (32 * ILP);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_n(&empty[s], NGROUP);   // the GW owners stand in for all NCWARP warps
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        ++k;
-        if (d.z & JF_DONE) break;
-        if (!(d.z & JF_TILE_END)) continue;
+        k += d.x;
 
         // ---- epilogue of tile (I,J) ----------------------------------------------------------
         const BlockRef a = p.A[p.tasks[task].x];
