@@ -261,6 +261,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--elem", default="u16", choices=["u16", "i32"])
+    ap.add_argument("--replicated-encode", action="store_true", help="N>1: every rank encodes all sequences (no block-list all-gather)")
     ap.add_argument("--gather-matrix", action="store_true",
                     help="N>1: also all-gather the whole matrix onto every GPU after the timed region and report its cost")
     args = ap.parse_args()
@@ -293,8 +294,12 @@ def main():
     d_out = torch.empty(my_elems * esz + 16, dtype=torch.uint8, device="cuda")
     total_pairs = N * (N - 1) // 2
 
+    sharded_encode = world > 1 and not args.replicated_encode
+
     def step():
-        s = ctx.encode_device(d_res.data_ptr(), off)
+        # N>1: each rank encodes 1/N of the sequences and the block lists are all-gathered over NVLink (the one
+        # exchange step of the path); N=1 or --replicated-encode: every rank encodes everything
+        s = sharding.encode_sharded(ctx, d_res, off, dist) if sharded_encode else ctx.encode_device(d_res.data_ptr(), off)
         ctx.sim_matrix_device(s, None, d_out.data_ptr(), elem=elem, layout=layout, row_begin=r0, row_end=r1)
         return s
 
@@ -310,7 +315,12 @@ def main():
             prev.free()
         prev = cur
     ctx.synchronize()
-    sizes = prev.sizes().astype(np.int64)
+    if sharded_encode:   # an imported set has no per-sequence arrays to ask for sizes: encode once more, plainly
+        tmp = ctx.encode_device(d_res.data_ptr(), off)
+        sizes = tmp.sizes().astype(np.int64)
+        tmp.free()
+    else:
+        sizes = prev.sizes().astype(np.int64)
 
     # ---- timed region: device-resident inputs --------------------------------------------------
     barrier()
@@ -438,7 +448,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": "all-vs-all 8-mer similarity, %d synthetic ~300-aa seed proteins, %d families (BASELINE configs[2])" % (N, nfam),
                        "K": 8, "nseq": N, "pairs": total_pairs, "result": "%s block-triangle, %d bytes on this rank" % (args.elem, my_elems * esz),
-                       "sharding": "256-row stripes of the result over %d rank(s), keys replicated, no data-path collective" % world,
+                       "sharding": ("256-row stripes of the result over %d rank(s); " % world) +
+                                   ("each rank encodes 1/%d of the sequences, block lists all-gathered (NCCL)" % world if sharded_encode
+                                    else "keys replicated, no data-path collective"),
                        "cache": "inputs+outputs larger than L2 (key lists %d MB, result %d MB per rank)" % (ssum * 8 >> 20, my_elems * esz >> 20)},
             "roofline": roofline, "roofline_design": design, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]), "clocks": clocks,

@@ -92,6 +92,32 @@ kr_status kr_key_decode(const kr_ctx *ctx, uint64_t key, char *out /* K bytes, n
 /* new set holding sequences idx[0..n) of `set` (used to batch sub-lists of ProteinKmers objects) */
 kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *idx, uint32_t n, kr_seqset **out);
 
+/* ---- multi-GPU: exchanging encoded block lists ------------------------------------------------
+ * The tile join reads only a set's block lists.  With several GPUs each one encodes a contiguous slice of the
+ * batch (kr_encode_device on offsets + begin; slices must start at multiples of KR_TILE), exports its block
+ * lists as flat device arrays, the caller all-gathers those arrays (NCCL), and every GPU imports the
+ * concatenation as one set.  An imported set supports kr_sim_matrix* and kr_db_find_closest* as queries via the
+ * join; it has no per-sequence key lists (kr_sim_pairs, kr_seqset_keys, kr_seqset_gather refuse it). */
+typedef struct kr_blocklists {
+    uint32_t nseq;      /* sequences in the shard */
+    uint32_t nblk;      /* blocks of KR_TILE sequences */
+    uint64_t entries;   /* length of hi / lo, including padding */
+    uint32_t lo_size;   /* bytes per lo element (2 or 4) */
+    uint32_t nchunk;    /* key-range chunks per block */
+    const void *hi;        /* uint32[entries] */
+    const void *lo;        /* lo_size * entries bytes */
+    const void *chunk_off; /* uint32[nblk * (nchunk + 1)] */
+    const void *chunk_cnt; /* uint32[nblk * nchunk] */
+    const void *blk_base;  /* uint64[nblk + 1], relative to hi / lo */
+    const void *meta;      /* 24 bytes per sequence: size, length, hash, (residue pointer: rewritten on import) */
+} kr_blocklists;
+/* device pointers into the set's own arrays; valid until the set is freed; synchronises the host */
+kr_status kr_seqset_export_blocklists(kr_ctx *ctx, kr_seqset *set, kr_blocklists *out);
+/* shards: nshards descriptors whose pointers are on this context's device, in batch order; residues / offsets
+ * describe the WHOLE batch (d_residues on the device, offsets on the host) */
+kr_status kr_seqset_import_blocklists(kr_ctx *ctx, const kr_blocklists *shards, uint32_t nshards, const uint8_t *d_residues,
+                                      const uint64_t *offsets, uint32_t nseq, kr_seqset **out);
+
 /* ---- SequenceKmers.similarity / distance ---------------------------------------------------
  * Replaces: a.similarity(b) for a list of pairs (DistanceMatrixProcessor.java:76,
  * ScoreCouplingReporter.java:66-70, NeighborProcessor.java:168, KmerCollectionGroup.getDistance

@@ -20,7 +20,7 @@ TILE = 256
 # every symbol include/kmersreps.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_synchronize", "kr_encode", "kr_encode_device",
-    "kr_seqset_free", "kr_seqset_count", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
+    "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
     "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
     "kr_db_find_closest", "kr_db_find_closest_device", "kr_db_any_ge", "kr_greedy_build", "kr_stats_get",
@@ -36,6 +36,18 @@ class KrError(RuntimeError):
 
 class MatrixDesc(C.Structure):
     _fields_ = [("elem", C.c_uint32), ("layout", C.c_uint32), ("row_begin", C.c_uint32), ("row_end", C.c_uint32)]
+
+
+class BlockLists(C.Structure):
+    _fields_ = [("nseq", C.c_uint32), ("nblk", C.c_uint32), ("entries", C.c_uint64), ("lo_size", C.c_uint32), ("nchunk", C.c_uint32),
+                ("hi", C.c_void_p), ("lo", C.c_void_p), ("chunk_off", C.c_void_p), ("chunk_cnt", C.c_void_p), ("blk_base", C.c_void_p),
+                ("meta", C.c_void_p)]
+
+    def arrays(self):
+        """name -> (device pointer, bytes) of every exchanged array"""
+        return {"hi": (self.hi, self.entries * 4), "lo": (self.lo, self.entries * self.lo_size),
+                "chunk_off": (self.chunk_off, self.nblk * (self.nchunk + 1) * 4), "chunk_cnt": (self.chunk_cnt, self.nblk * self.nchunk * 4),
+                "blk_base": (self.blk_base, (self.nblk + 1) * 8), "meta": (self.meta, self.nseq * 24)}
 
 
 class Stats(C.Structure):
@@ -79,6 +91,8 @@ def load_library():
     lib.kr_seqset_free.restype = None
     lib.kr_seqset_count.argtypes = [vp]
     lib.kr_seqset_count.restype = u32
+    lib.kr_seqset_export_blocklists.argtypes = [vp, vp, C.POINTER(BlockLists)]
+    lib.kr_seqset_import_blocklists.argtypes = [vp, C.POINTER(BlockLists), u32, vp, vp, u32, C.POINTER(vp)]
     lib.kr_seqset_sizes.argtypes = [vp, vp]
     lib.kr_seqset_keys.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
     lib.kr_key_decode.argtypes = [vp, u64, C.c_char_p]
@@ -192,6 +206,18 @@ class Context:
         off = np.ascontiguousarray(off, dtype=np.uint64)
         h = C.c_void_p()
         self._ck(self.lib.kr_encode_device(self.h, d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return SeqSet(self, h)
+
+    def export_blocklists(self, s: "SeqSet") -> BlockLists:
+        b = BlockLists()
+        self._ck(self.lib.kr_seqset_export_blocklists(self.h, s.h, C.byref(b)))
+        return b
+
+    def import_blocklists(self, shards, d_res_ptr: int, off) -> "SeqSet":
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        arr = (BlockLists * len(shards))(*shards)
+        h = C.c_void_p()
+        self._ck(self.lib.kr_seqset_import_blocklists(self.h, arr, len(shards), d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
         return SeqSet(self, h)
 
     def key_decode(self, key: int) -> str:

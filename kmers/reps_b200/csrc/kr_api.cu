@@ -424,6 +424,7 @@ static kr_status fetch_sizes(kr_ctx *ctx, kr_seqset *s) {
 
 static kr_status gather_impl(kr_ctx *ctx, const kr_seqset *src_c, const u32 *idx, u32 n, kr_seqset **out) {
     kr_seqset *src = const_cast<kr_seqset *>(src_c);
+    if (!src->d_keys && src->n) return fail(ctx, KR_ERR_STATE, "this set was imported from block lists and has no key lists");
     kr_status st = fetch_sizes(ctx, src);
     if (st) return st;
     std::vector<u64> koff(n + 1);
@@ -739,7 +740,7 @@ static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *
     if (Q->n == 0) return KR_OK;
     // large query batches go through the inverted index (work ~ postings touched); small ones through the tile
     // join (no index to build); both are exact
-    const bool use_index = db->n > 0 && !(ctx->flags & KR_FORCE_JOIN) && ((ctx->flags & KR_FORCE_INDEX) || Q->n >= 8192);
+    const bool use_index = db->n > 0 && Q->d_keys && !(ctx->flags & KR_FORCE_JOIN) && ((ctx->flags & KR_FORCE_INDEX) || Q->n >= 8192);
     if (use_index) return find_closest_index(ctx, db, Q, d_sim, d_first, d_last);
     if ((st = ensure_blocklists(ctx, Q))) return st;
     if (db->n == 0) {
@@ -811,6 +812,7 @@ kr_status kr_seqset_keys(const kr_seqset *set, uint32_t i, uint64_t *keys, uint3
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->dev));
     if (i >= set->n) return fail(ctx, KR_ERR_ARG, "kr_seqset_keys: index %u of %u", i, set->n);
+    if (!set->d_keys) return fail(ctx, KR_ERR_STATE, "kr_seqset_keys: a set imported from block lists has no key lists");
     kr_status st = fetch_sizes(ctx, const_cast<kr_seqset *>(set));
     if (st) return st;
     u32 sz = set->h_sizes[i];
@@ -832,10 +834,80 @@ kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *id
     return gather_impl(ctx, set, idx, n, out);
 }
 
+kr_status kr_seqset_export_blocklists(kr_ctx *ctx, kr_seqset *set, kr_blocklists *out) {
+    if (!ctx || !set || !out) return fail(ctx, KR_ERR_ARG, "kr_seqset_export_blocklists: null argument");
+    if (set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_seqset_export_blocklists: set belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    kr_status st = ensure_blocklists(ctx, set);
+    if (st) return st;
+    u64 total = 0;
+    if (set->nblk) CU(cudaMemcpyAsync(&total, set->d_blkbase + set->nblk, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->err_pending && (st = check_alphabet(ctx))) return st;
+    out->nseq = set->n; out->nblk = set->nblk; out->entries = total;
+    out->lo_size = lo_bits(ctx->K) <= 16 ? 2 : 4; out->nchunk = NCHUNK;
+    out->hi = set->d_hi; out->lo = set->d_lo; out->chunk_off = set->d_choff; out->chunk_cnt = set->d_chcnt;
+    out->blk_base = set->d_blkbase; out->meta = set->d_meta;
+    return KR_OK;
+}
+
+kr_status kr_seqset_import_blocklists(kr_ctx *ctx, const kr_blocklists *shards, uint32_t nshards, const uint8_t *d_residues,
+                                      const uint64_t *offsets, uint32_t nseq, kr_seqset **out) {
+    if (!ctx || !shards || !nshards || !out || !offsets) return fail(ctx, KR_ERR_ARG, "kr_seqset_import_blocklists: null argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    const u32 lo_size = lo_bits(ctx->K) <= 16 ? 2 : 4;
+    u64 entries = 0; u32 nblk = 0, n = 0;
+    for (u32 k = 0; k < nshards; ++k) {
+        const kr_blocklists &sh = shards[k];
+        if (sh.nchunk != NCHUNK || sh.lo_size != lo_size) return fail(ctx, KR_ERR_ARG, "import: shard %u was built with another chunking / K", k);
+        if (k + 1 < nshards && sh.nseq % TB) return fail(ctx, KR_ERR_ARG, "import: shard %u has %u sequences; inner shards must hold multiples of %d", k, sh.nseq, TB);
+        if (sh.nblk != (sh.nseq + TB - 1) / TB) return fail(ctx, KR_ERR_ARG, "import: shard %u block count", k);
+        entries += sh.entries; nblk += sh.nblk; n += sh.nseq;
+    }
+    if (n != nseq) return fail(ctx, KR_ERR_ARG, "import: shards hold %u sequences, batch has %u", n, nseq);
+    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
+    s->ctx = ctx; s->n = nseq; s->nblk = nblk;
+    const u64 total_res = offsets[nseq] - offsets[0];
+    std::vector<u64> off(nseq + 1);
+    for (u32 i = 0; i <= nseq; ++i) off[i] = offsets[i] - offsets[0];
+    s->res = std::make_shared<DevMem>(); s->res->stream = ctx->stream;
+    CU(cudaMallocAsync(&s->res->p, total_res + 16, ctx->stream));
+    CU(cudaMemcpyAsync(s->res->p, d_residues + offsets[0], total_res, cudaMemcpyDeviceToDevice, ctx->stream));
+    u8 *d_lo = nullptr;
+    CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_meta, nseq));
+    CU(dalloc(ctx, &s->d_hi, entries + 16)); CU(dalloc(ctx, &d_lo, (entries + 16) * lo_size)); s->d_lo = d_lo;
+    CU(dalloc(ctx, &s->d_choff, (size_t)nblk * (NCHUNK + 1))); CU(dalloc(ctx, &s->d_chcnt, (size_t)nblk * NCHUNK));
+    CU(dalloc(ctx, &s->d_refs, nblk));
+    CU(cudaMemcpyAsync(s->d_off, off.data(), (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    u64 e0 = 0; u32 b0 = 0, s0 = 0;
+    for (u32 k = 0; k < nshards; ++k) {
+        const kr_blocklists &sh = shards[k];
+        if (sh.nseq == 0) continue;
+        CU(cudaMemcpyAsync(s->d_hi + e0, sh.hi, sh.entries * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_lo + e0 * lo_size, sh.lo, sh.entries * lo_size, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(s->d_choff + (size_t)b0 * (NCHUNK + 1), sh.chunk_off, (size_t)sh.nblk * (NCHUNK + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(s->d_chcnt + (size_t)b0 * NCHUNK, sh.chunk_cnt, (size_t)sh.nblk * NCHUNK * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(s->d_meta + s0, sh.meta, (size_t)sh.nseq * sizeof(SeqMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+        k_import_refs<<<(sh.nblk + 127) / 128, 128, 0, ctx->stream>>>(sh.nblk, b0, s0, sh.nseq, s->d_hi, d_lo, lo_size, s->d_choff, s->d_chcnt,
+                                                                     (const u64 *)sh.blk_base, e0, s->d_refs);
+        LAUNCHED(ctx);
+        e0 += sh.entries; b0 += sh.nblk; s0 += sh.nseq;
+    }
+    if (nseq) { k_import_meta<<<(nseq + 255) / 256, 256, 0, ctx->stream>>>(s->d_meta, nseq, (const u8 *)s->res->p, s->d_off); LAUNCHED(ctx); }
+    CU(cudaGetLastError());
+    s->bl_ready = true;
+    *out = s.release();
+    return KR_OK;
+}
+
 kr_status kr_sim_pairs(kr_ctx *ctx, const kr_seqset *A, const uint32_t *ia, const kr_seqset *B, const uint32_t *ib,
                        uint64_t npairs, int32_t *sim, uint8_t *identical) {
     if (!ctx || !A || !B || !sim || ((!ia || !ib) && npairs)) return fail(ctx, KR_ERR_ARG, "kr_sim_pairs: null argument");
     if (A->ctx != ctx || B->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_sim_pairs: set belongs to another context");
+    if ((!A->d_keys && A->n) || (!B->d_keys && B->n)) return fail(ctx, KR_ERR_STATE, "kr_sim_pairs: a set imported from block lists has no key lists");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->dev));
     if (!npairs) return KR_OK;

@@ -309,6 +309,23 @@ __global__ void __launch_bounds__(256) k_bl_sort(const BlockRef *refs, const u64
     }
 }
 
+// import of exchanged block lists: block refs of one shard inside the concatenated arrays, residue pointers
+__global__ void k_import_refs(u32 nblk, u32 blk0, u32 seq0, u32 nseq_shard, const u32 *hi, const u8 *lo, u32 lo_size,
+                              const u32 *choff, const u32 *chcnt, const u64 *blkbase_local, u64 ent0, BlockRef *refs) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    BlockRef r;
+    const u64 base = ent0 + blkbase_local[b];
+    r.hi = hi + base; r.lo = lo + base * lo_size;
+    r.off = choff + (size_t)(blk0 + b) * (NCHUNK + 1); r.cnt = chcnt + (size_t)(blk0 + b) * NCHUNK;
+    r.seq0 = seq0 + b * TB; r.nseq = min((u32)TB, nseq_shard - b * TB);
+    refs[blk0 + b] = r;
+}
+__global__ void k_import_meta(SeqMeta *meta, u32 n, const u8 *res, const u64 *off) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) meta[i].res = res + off[i];
+}
+
 // re-base the block refs of a set into a database-wide array (seq0 += base)
 __global__ void k_copy_refs(const BlockRef *src, u32 n, u32 seq_base, BlockRef *dst) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -73,3 +73,57 @@ def blocktri_from_full(full: np.ndarray) -> np.ndarray:
     """KR_LAYOUT_BLOCKTRI cells of a full n x n matrix (row i keeps columns >= 256*(i//256))"""
     n = full.shape[0]
     return np.concatenate([full[i, 256 * (i // 256):] for i in range(n)]) if n else full.reshape(0)
+
+
+# ---- sharded encode: every rank encodes a slice, block lists are all-gathered (NCCL) ----------------------
+class _DevPtr:
+    """zero-copy view of library-owned device memory for torch (CUDA array interface)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def block_shards(nseq: int, world: int):
+    """contiguous sequence ranges, one per rank, cut at multiples of 256 sequences"""
+    nblk = (nseq + kr.TILE - 1) // kr.TILE
+    return [min(nseq, kr.TILE * ((nblk * k) // world)) for k in range(world)] + [nseq]
+
+
+def encode_sharded(ctx, d_res, off, dist):
+    """Encode the whole batch cooperatively: this rank encodes and block-lists its slice, the slices' block
+    lists are exchanged with all_gather, and the result is imported as one set on every rank.
+    d_res: torch uint8 CUDA tensor with ALL residues (replicated, 1 B/residue); off: host offsets."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nseq = len(off) - 1
+    cuts = block_shards(nseq, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    local = ctx.encode_device(d_res.data_ptr(), off[lo: hi + 1])
+    bl = ctx.export_blocklists(local)                      # synchronises: the arrays are complete
+    mine = torch.tensor([bl.entries, bl.nblk, bl.nseq], dtype=torch.int64, device=d_res.device)
+    sizes = torch.empty(world * 3, dtype=torch.int64, device=d_res.device)
+    dist.all_gather_into_tensor(sizes, mine)
+    sizes = sizes.cpu().numpy().reshape(world, 3)
+    shards = [kr.BlockLists() for _ in range(world)]
+    for k in range(world):
+        shards[k].entries, shards[k].nblk, shards[k].nseq = int(sizes[k, 0]), int(sizes[k, 1]), int(sizes[k, 2])
+        shards[k].lo_size, shards[k].nchunk = bl.lo_size, bl.nchunk
+    keep = []
+    my_arrays = bl.arrays()
+    for name in ("hi", "lo", "chunk_off", "chunk_cnt", "blk_base", "meta"):
+        per = [shards[k].arrays()[name][1] for k in range(world)]
+        width = (max(per) + 255) // 256 * 256
+        send = torch.empty(width, dtype=torch.uint8, device=d_res.device)
+        ptr, nbytes = my_arrays[name]
+        if nbytes:
+            send[:nbytes].copy_(torch.as_tensor(_DevPtr(ptr, nbytes), device=d_res.device))
+        recv = torch.empty(world * width, dtype=torch.uint8, device=d_res.device)
+        dist.all_gather_into_tensor(recv, send)
+        keep.append(recv)
+        for k in range(world):
+            setattr(shards[k], name, recv.data_ptr() + k * width)
+    torch.cuda.current_stream().synchronize()              # the gathered arrays are complete before the library reads them
+    full = ctx.import_blocklists(shards, d_res.data_ptr(), off)
+    ctx.synchronize()                                      # ... and copied before the receive buffers are released
+    local.free()
+    return full
