@@ -111,6 +111,9 @@ typedef struct kr_blocklists {
     const void *blk_base;  /* uint64[nblk + 1], relative to hi / lo */
     const void *meta;      /* 24 bytes per sequence: size, length, hash, (residue pointer: rewritten on import) */
 } kr_blocklists;
+/* allocated length (elements) of the hi / lo arrays of a set encoded from these offsets: an upper bound of
+ * `entries` every GPU can compute without communication (pure host arithmetic) */
+uint64_t kr_blocklist_capacity(const kr_ctx *ctx, const uint64_t *offsets, uint32_t nseq);
 /* device pointers into the set's own arrays; valid until the set is freed; synchronises the host */
 kr_status kr_seqset_export_blocklists(kr_ctx *ctx, kr_seqset *set, kr_blocklists *out);
 /* shards: nshards descriptors whose pointers are on this context's device, in batch order; residues / offsets

@@ -20,7 +20,7 @@ TILE = 256
 # every symbol include/kmersreps.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_synchronize", "kr_encode", "kr_encode_device",
-    "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
+    "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_blocklist_capacity", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
     "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
     "kr_db_find_closest", "kr_db_find_closest_device", "kr_db_any_ge", "kr_greedy_build", "kr_stats_get",
@@ -91,6 +91,8 @@ def load_library():
     lib.kr_seqset_free.restype = None
     lib.kr_seqset_count.argtypes = [vp]
     lib.kr_seqset_count.restype = u32
+    lib.kr_blocklist_capacity.argtypes = [vp, vp, u32]
+    lib.kr_blocklist_capacity.restype = u64
     lib.kr_seqset_export_blocklists.argtypes = [vp, vp, C.POINTER(BlockLists)]
     lib.kr_seqset_import_blocklists.argtypes = [vp, C.POINTER(BlockLists), u32, vp, vp, u32, C.POINTER(vp)]
     lib.kr_seqset_sizes.argtypes = [vp, vp]
@@ -208,6 +210,10 @@ class Context:
         self._ck(self.lib.kr_encode_device(self.h, d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
         return SeqSet(self, h)
 
+    def blocklist_capacity(self, off) -> int:
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        return int(self.lib.kr_blocklist_capacity(self.h, off.ctypes.data, len(off) - 1))
+
     def export_blocklists(self, s: "SeqSet") -> BlockLists:
         b = BlockLists()
         self._ck(self.lib.kr_seqset_export_blocklists(self.h, s.h, C.byref(b)))
@@ -292,6 +298,7 @@ class SeqSet:
         if self.h:
             self.ctx.lib.kr_seqset_free(self.h)
             self.h = None
+        self._keep = None   # buffers an imported set was built from
 
     def __del__(self):
         try:

@@ -381,13 +381,15 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
     return KR_OK;
 }
 
+// entries + per-chunk alignment padding + the sentinel tail after every block
+static u64 blocklist_capacity(u64 key_cap, u32 nblk) { return key_cap + (u64)nblk * NCHUNK * CHUNK_ALIGN + (u64)nblk * TAILPAD + 64; }
+
 // block lists of a set (K2), built on first use
 static kr_status ensure_blocklists(kr_ctx *ctx, kr_seqset *s) {
     if (s->bl_ready) return KR_OK;
     u32 nblk = (s->n + TB - 1) / TB;
     s->nblk = nblk;
-    // entries + per-chunk alignment padding + the sentinel tail after every block
-    u64 cap = s->key_cap + (u64)nblk * NCHUNK * CHUNK_ALIGN + (u64)nblk * TAILPAD + 64;
+    u64 cap = blocklist_capacity(s->key_cap, nblk);
     const int lobits = lo_bits(ctx->K), lo_size = lobits <= 16 ? 2 : 4;
     u64 *d_ent = nullptr; u8 *d_lo = nullptr;
     CU(dalloc(ctx, &d_ent, cap)); CU(dalloc(ctx, &s->d_hi, cap)); CU(dalloc(ctx, &d_lo, cap * lo_size));
@@ -834,6 +836,13 @@ kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *id
     return gather_impl(ctx, set, idx, n, out);
 }
 
+uint64_t kr_blocklist_capacity(const kr_ctx *ctx, const uint64_t *offsets, uint32_t nseq) {
+    if (!ctx || (!offsets && nseq)) return 0;
+    u64 kc = 0;
+    for (u32 i = 0; i < nseq; ++i) { u64 L = offsets[i + 1] - offsets[i]; if (L >= (u64)ctx->K) kc += L - ctx->K + 1; }
+    return blocklist_capacity(kc, (nseq + TB - 1) / TB);
+}
+
 kr_status kr_seqset_export_blocklists(kr_ctx *ctx, kr_seqset *set, kr_blocklists *out) {
     if (!ctx || !set || !out) return fail(ctx, KR_ERR_ARG, "kr_seqset_export_blocklists: null argument");
     if (set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_seqset_export_blocklists: set belongs to another context");
@@ -865,7 +874,7 @@ kr_status kr_seqset_import_blocklists(kr_ctx *ctx, const kr_blocklists *shards, 
         if (sh.nchunk != NCHUNK || sh.lo_size != lo_size) return fail(ctx, KR_ERR_ARG, "import: shard %u was built with another chunking / K", k);
         if (k + 1 < nshards && sh.nseq % TB) return fail(ctx, KR_ERR_ARG, "import: shard %u has %u sequences; inner shards must hold multiples of %d", k, sh.nseq, TB);
         if (sh.nblk != (sh.nseq + TB - 1) / TB) return fail(ctx, KR_ERR_ARG, "import: shard %u block count", k);
-        entries += sh.entries; nblk += sh.nblk; n += sh.nseq;
+        entries += (sh.entries + 63) / 64 * 64; nblk += sh.nblk; n += sh.nseq;   // every shard starts 256-byte aligned (TMA sources)
     }
     if (n != nseq) return fail(ctx, KR_ERR_ARG, "import: shards hold %u sequences, batch has %u", n, nseq);
     std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
@@ -894,7 +903,7 @@ kr_status kr_seqset_import_blocklists(kr_ctx *ctx, const kr_blocklists *shards, 
         k_import_refs<<<(sh.nblk + 127) / 128, 128, 0, ctx->stream>>>(sh.nblk, b0, s0, sh.nseq, s->d_hi, d_lo, lo_size, s->d_choff, s->d_chcnt,
                                                                      (const u64 *)sh.blk_base, e0, s->d_refs);
         LAUNCHED(ctx);
-        e0 += sh.entries; b0 += sh.nblk; s0 += sh.nseq;
+        e0 += (sh.entries + 63) / 64 * 64; b0 += sh.nblk; s0 += sh.nseq;
     }
     if (nseq) { k_import_meta<<<(nseq + 255) / 256, 256, 0, ctx->stream>>>(s->d_meta, nseq, (const u8 *)s->res->p, s->d_off); LAUNCHED(ctx); }
     CU(cudaGetLastError());

@@ -91,8 +91,10 @@ def block_shards(nseq: int, world: int):
 
 def encode_sharded(ctx, d_res, off, dist):
     """Encode the whole batch cooperatively: this rank encodes and block-lists its slice, the slices' block
-    lists are exchanged with all_gather, and the result is imported as one set on every rank.
-    d_res: torch uint8 CUDA tensor with ALL residues (replicated, 1 B/residue); off: host offsets."""
+    lists are exchanged with ONE all_gather, and the result is imported as one set on every rank.
+    d_res: torch uint8 CUDA tensor with ALL residues (replicated, 1 B/residue); off: host offsets.
+    Every rank lays its six arrays out in a segment whose field sizes are capacity bounds all ranks compute
+    from the offsets alone, so no size exchange is needed."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     nseq = len(off) - 1
@@ -100,30 +102,31 @@ def encode_sharded(ctx, d_res, off, dist):
     lo, hi = cuts[rank], cuts[rank + 1]
     local = ctx.encode_device(d_res.data_ptr(), off[lo: hi + 1])
     bl = ctx.export_blocklists(local)                      # synchronises: the arrays are complete
-    mine = torch.tensor([bl.entries, bl.nblk, bl.nseq], dtype=torch.int64, device=d_res.device)
-    sizes = torch.empty(world * 3, dtype=torch.int64, device=d_res.device)
-    dist.all_gather_into_tensor(sizes, mine)
-    sizes = sizes.cpu().numpy().reshape(world, 3)
-    shards = [kr.BlockLists() for _ in range(world)]
+    shards = []
     for k in range(world):
-        shards[k].entries, shards[k].nblk, shards[k].nseq = int(sizes[k, 0]), int(sizes[k, 1]), int(sizes[k, 2])
-        shards[k].lo_size, shards[k].nchunk = bl.lo_size, bl.nchunk
-    keep = []
-    my_arrays = bl.arrays()
-    for name in ("hi", "lo", "chunk_off", "chunk_cnt", "blk_base", "meta"):
-        per = [shards[k].arrays()[name][1] for k in range(world)]
-        width = (max(per) + 255) // 256 * 256
-        send = torch.empty(width, dtype=torch.uint8, device=d_res.device)
-        ptr, nbytes = my_arrays[name]
+        b = kr.BlockLists()
+        b.nseq = cuts[k + 1] - cuts[k]
+        b.nblk = (b.nseq + kr.TILE - 1) // kr.TILE
+        b.entries = ctx.blocklist_capacity(off[cuts[k]: cuts[k + 1] + 1])
+        b.lo_size, b.nchunk = bl.lo_size, bl.nchunk
+        shards.append(b)
+    names = ("hi", "lo", "chunk_off", "chunk_cnt", "blk_base", "meta")
+    field, width = {}, 0
+    for name in names:                                     # common segment layout: field sizes = max over ranks
+        field[name] = width
+        width += (max(shards[k].arrays()[name][1] for k in range(world)) + 255) // 256 * 256
+    send = torch.empty(width, dtype=torch.uint8, device=d_res.device)
+    mine = shards[rank]
+    for name in names:
+        nbytes = mine.arrays()[name][1]
         if nbytes:
-            send[:nbytes].copy_(torch.as_tensor(_DevPtr(ptr, nbytes), device=d_res.device))
-        recv = torch.empty(world * width, dtype=torch.uint8, device=d_res.device)
-        dist.all_gather_into_tensor(recv, send)
-        keep.append(recv)
-        for k in range(world):
-            setattr(shards[k], name, recv.data_ptr() + k * width)
+            send[field[name]: field[name] + nbytes].copy_(torch.as_tensor(_DevPtr(getattr(bl, name), nbytes), device=d_res.device))
+    recv = torch.empty(world * width, dtype=torch.uint8, device=d_res.device)
+    dist.all_gather_into_tensor(recv, send)
+    for k in range(world):
+        for name in names:
+            setattr(shards[k], name, recv.data_ptr() + k * width + field[name])
     torch.cuda.current_stream().synchronize()              # the gathered arrays are complete before the library reads them
     full = ctx.import_blocklists(shards, d_res.data_ptr(), off)
-    ctx.synchronize()                                      # ... and copied before the receive buffers are released
-    local.free()
+    full._keep = (recv, local)   # released with the set: by then the import's copies have long completed
     return full
