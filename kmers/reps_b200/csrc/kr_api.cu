@@ -127,13 +127,6 @@ struct StageTimer {   // device time of a group of launches, resolved lazily in 
 };
 #define LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
 
-// residue byte -> code: 'A'..'Z' -> 0..25, '*' -> 26, '-' -> 27
-static void make_code_table(u8 *t) {
-    memset(t, 0xFF, 256);
-    for (int c = 'A'; c <= 'Z'; ++c) t[c] = (u8)(c - 'A');
-    t['*'] = 26; t['-'] = 27;
-}
-
 // Chunk table: the 32^3 three-residue key prefixes, in key order, are cut into NCHUNK contiguous
 // groups of about equal expected mass under the background residue frequencies of seed proteins
 // (counts measured on data/rep50.db).  It only balances work; any monotone table is
@@ -195,8 +188,6 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long keep = ~0ull;
     CUC(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    u8 code[256]; make_code_table(code);
-    CUC(cudaMemcpyToSymbol(c_code, code, 256));
     std::vector<u8> lut(1 << LUT_BITS); make_chunk_lut(lut.data());
     CUC(cudaMalloc(&ctx->d_lut, lut.size()));
     CUC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
@@ -366,7 +357,7 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
         p.err = ctx->d_err; p.nseq = nseq; p.K = K; p.smem_cap = 2048;
         // proteins are a few hundred residues: one 128-thread CTA sorts up to 2048 keys in 16 KB of shared
         // memory; longer sequences (rare) sort in place in global memory inside the same kernel
-        k_encode_sort<128><<<nseq, 128, p.smem_cap * 8, ctx->stream>>>(p);
+        k_encode_sort<128><<<nseq, 128, p.smem_cap * 8 + p.smem_cap + 16, ctx->stream>>>(p);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
     }

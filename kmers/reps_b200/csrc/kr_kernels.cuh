@@ -95,7 +95,6 @@ struct BlockRef {    // one per block of 256 sequences
 
 struct ErrInfo { u32 flag, seq, pos, byte; };
 
-__constant__ u8 c_code[256];   // residue byte -> 5-bit code, 0xFF = not in the alphabet
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ u64 mix64(u64 x) {
@@ -142,9 +141,15 @@ struct EncodeParams {
     u32 nseq; int K; u32 smem_cap;
 };
 
+// residue byte -> 5-bit code without a table: 'A'..'Z' -> 0..25, '*' -> 26, '-' -> 27, anything else 0xFF
+__device__ __forceinline__ u32 residue_code(u32 c) {
+    const u32 letter = c - 'A';
+    return letter < 26u ? letter : (c == '*' ? 26u : (c == '-' ? 27u : 0xFFu));
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_encode_sort(EncodeParams p) {
-    extern __shared__ __align__(16) u64 sk[];
+    extern __shared__ __align__(16) u64 sk[];          // smem_cap keys, then smem_cap + 16 code bytes
     __shared__ u64 s_hash, s_prev;
     __shared__ u32 s_wtot[THREADS / 32];
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -154,21 +159,34 @@ __global__ void __launch_bounds__(THREADS) k_encode_sort(EncodeParams p) {
     const int K = p.K;
     const u32 n = L >= (u32)K ? L - K + 1 : 0;
     u64 *dst = p.keys + p.koff[s];
-    u64 *w = (n <= p.smem_cap) ? sk : dst;
+    const bool small = n <= p.smem_cap && L <= p.smem_cap + 16;
+    u64 *w = small ? sk : dst;
+    u8 *codes = reinterpret_cast<u8 *>(sk + p.smem_cap);
     if (tid == 0) s_hash = 0;
     __syncthreads();
     u64 h = 0;
     for (u32 i = tid; i < L; i += THREADS) {
-        u8 c = r[i];
-        if (c_code[c] == 0xFF && atomicCAS(&p.err->flag, 0u, 1u) == 0u) { p.err->seq = s; p.err->pos = i; p.err->byte = c; }
+        const u32 c = r[i];
+        const u32 code = residue_code(c);
+        if (code == 0xFFu && atomicCAS(&p.err->flag, 0u, 1u) == 0u) { p.err->seq = s; p.err->pos = i; p.err->byte = c; }
+        if (small) codes[i] = (u8)code;
         h += mix64((((u64)i << 8) | c) + 0x9E3779B97F4A7C15ULL);
     }
     for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
     if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&s_hash), (unsigned long long)h);
-    for (u32 i = tid; i < n; i += THREADS) {
-        u64 key = 0;
-        for (int t = 0; t < K; ++t) key = (key << 5) | (u64)(c_code[r[i + t]] & 31);
-        w[i] = key;
+    __syncthreads();
+    if (small) {
+        for (u32 i = tid; i < n; i += THREADS) {
+            u64 key = 0;
+            for (int t = 0; t < K; ++t) key = (key << 5) | (u64)(codes[i + t] & 31);
+            w[i] = key;
+        }
+    } else {
+        for (u32 i = tid; i < n; i += THREADS) {
+            u64 key = 0;
+            for (int t = 0; t < K; ++t) key = (key << 5) | (u64)(residue_code(r[i + t]) & 31);
+            w[i] = key;
+        }
     }
     __syncthreads();
     bitonic_sort(w, n, tid, THREADS);
@@ -772,12 +790,12 @@ __global__ void k_fill_u32_iota(u32 *p, u32 n, u32 base) {
 //   table   open addressing, linear probing, capacity = power of two >= 2 x entries:
 //           tab_key[c] (uint64, EMPTY = ~0), tab_off[c] / tab_cnt[c] (uint32): postings[off .. off+cnt)
 //   query   one CTA per query at a time; a uint16 score per representative of the slab lives in shared
-//           memory (two per 32-bit word, same packing as the join's count tile).  Three walks over the
-//           posting lists of the query's keys: accumulate, find (max, first rank, last rank), clear.
+//           memory (two per 32-bit word, same packing as the join's count tile).  Two walks over the
+//           posting lists of the query's keys: accumulate + maximum in one, then clear.
 // A database larger than IDX_SLAB representatives is indexed in slabs; per-slab results are merged.
 namespace kr {
 
-constexpr u32 IDX_SLAB = 53248;                 // representatives per slab: 104 KB of scores, 2 CTAs per SM
+constexpr u32 IDX_SLAB = 51200;                 // representatives per slab: 100 KB of scores, 2 CTAs per SM
 constexpr u32 IDX_THREADS = 256;
 constexpr u64 IDX_EMPTY = ~0ull;
 constexpr size_t IDX_SMEM = (size_t)IDX_SLAB * 2;
@@ -872,10 +890,16 @@ struct IdxQueryParams {
     u32 *next;                               // work counter
 };
 
+// One walk accumulates AND finds the maximum: atomicAdd returns the previous score, and a representative whose
+// final score is M sees the value M exactly once (its last increment), so tracking the largest value seen --
+// with the smallest / largest rank among the entries that showed it -- yields (max, first, last) without a
+// second pass.  The (offset, count) of each key's posting list is kept in shared memory for the clearing walk.
+constexpr u32 IDX_KEYCACHE = 512;    // posting ranges cached per query; longer queries re-probe when clearing
 __global__ void __launch_bounds__(IDX_THREADS, 2) k_idx_query(IdxQueryParams p) {
     extern __shared__ __align__(16) u32 score[];   // (slab_n + 1) / 2 words, zero between queries
     __shared__ u32 s_q;
     __shared__ unsigned long long s_first[IDX_THREADS / 32], s_last[IDX_THREADS / 32];
+    __shared__ uint2 s_range[IDX_KEYCACHE];
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (u32 i = tid; i < (p.slab_n + 1) / 2; i += IDX_THREADS) score[i] = 0;
     const bool ident_inf = (p.flags & 1u) != 0;
@@ -888,67 +912,52 @@ __global__ void __launch_bounds__(IDX_THREADS, 2) k_idx_query(IdxQueryParams p) 
         const SeqMeta qm = p.qmeta[q];
         const u32 n = qm.size;
         const u64 *kp = p.qkeys + p.qkoff[q];
-        // walk 1: accumulate
+        unsigned long long bf = 0, bl = 0;   // (score << 32) | ~rank  and  (score << 32) | rank
         for (u32 i = tid; i < n; i += IDX_THREADS) {
             const u64 key = kp[i];
             u32 slot = idx_hash(key, p.mask);
             unsigned long long k2;
             while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
-            if (k2 == key) {
-                const u32 off = p.tab_off[slot], c = p.tab_cnt[slot];
-                for (u32 t = 0; t < c; ++t) {
-                    const u32 r = p.postings[off + t] - p.slab_base;
-                    atomicAdd(&score[r >> 1], (r & 1) ? 0x10000u : 1u);
+            uint2 rg = make_uint2(0, 0);
+            if (k2 == key) rg = make_uint2(p.tab_off[slot], p.tab_cnt[slot]);
+            if (i < IDX_KEYCACHE) s_range[i] = rg;
+            for (u32 t = 0; t < rg.y; ++t) {
+                const u32 g = p.postings[rg.x + t], r = g - p.slab_base;
+                const u32 old = atomicAdd(&score[r >> 1], (r & 1) ? 0x10000u : 1u);
+                u32 sc = ((old >> ((r & 1) * 16)) & 0xFFFFu) + 1;
+                // the equal-sequence rule: only a representative holding every key of the query can be identical
+                if (ident_inf && sc == n) { const SeqMeta rm = p.rmeta[g]; if (rm.size == n && seq_equal(qm, rm)) sc = KR_INF; }
+                if (sc >= (u32)(bf >> 32)) {
+                    const u32 rk = p.rank[g];
+                    const unsigned long long cf = ((unsigned long long)sc << 32) | (0xFFFFFFFFu - rk);
+                    const unsigned long long cl = ((unsigned long long)sc << 32) | rk;
+                    bf = cf > bf ? cf : bf; bl = cl > bl ? cl : bl;
                 }
             }
         }
-        __syncthreads();
-        // walk 2: maximum with first / last rank among the maxima; packed as (sim << 32) | key so one max finds both
-        unsigned long long bf = 0, bl = 0;   // first: key = ~rank (smaller rank wins), last: key = rank
-        for (u32 i = tid; i < n; i += IDX_THREADS) {
-            const u64 key = kp[i];
-            u32 slot = idx_hash(key, p.mask);
-            unsigned long long k2;
-            while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
-            if (k2 == key) {
-                const u32 off = p.tab_off[slot], c = p.tab_cnt[slot];
-                for (u32 t = 0; t < c; ++t) {
-                    const u32 g = p.postings[off + t], r = g - p.slab_base;
-                    u32 s = (score[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
-                    // the equal-sequence rule: an identical representative holds every key of the query, so it is
-                    // enough to test it while walking the query's first key
-                    if (ident_inf && i == 0 && s == n) { const SeqMeta rm = p.rmeta[g]; if (rm.size == n && seq_equal(qm, rm)) s = KR_INF; }
-                    if (s >= (u32)(bf >> 32)) {
-                        const u32 rk = p.rank[g];
-                        const unsigned long long cf = ((unsigned long long)s << 32) | (0xFFFFFFFFu - rk);
-                        const unsigned long long cl = ((unsigned long long)s << 32) | rk;
-                        bf = cf > bf ? cf : bf; bl = cl > bl ? cl : bl;
-                    }
-                }
-            }
-        }
-        // an identical representative of a query shorter than K shares no key with it: handled by the caller
         for (int o = 16; o > 0; o >>= 1) {
             unsigned long long t1 = __shfl_xor_sync(0xffffffffu, bf, o), t2 = __shfl_xor_sync(0xffffffffu, bl, o);
             bf = t1 > bf ? t1 : bf; bl = t2 > bl ? t2 : bl;
         }
         if (lane == 0) { s_first[warp] = bf; s_last[warp] = bl; }
-        __syncthreads();
+        __syncthreads();   // all increments done, per-warp maxima and cached ranges visible
         if (tid == 0) {
             for (u32 k = 1; k < IDX_THREADS / 32; ++k) { bf = s_first[k] > bf ? s_first[k] : bf; bl = s_last[k] > bl ? s_last[k] : bl; }
             const int sim = (int)(bf >> 32);
             p.partial[q] = make_int4(sim, sim ? (int)(0xFFFFFFFFu - (u32)bf) : -1, sim ? (int)(u32)bl : 0, 0);
         }
-        // walk 3: clear the touched scores
+        // clear the touched scores
         for (u32 i = tid; i < n; i += IDX_THREADS) {
-            const u64 key = kp[i];
-            u32 slot = idx_hash(key, p.mask);
-            unsigned long long k2;
-            while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
-            if (k2 == key) {
-                const u32 off = p.tab_off[slot], c = p.tab_cnt[slot];
-                for (u32 t = 0; t < c; ++t) { const u32 r = p.postings[off + t] - p.slab_base; score[r >> 1] = 0; }
+            uint2 rg;
+            if (i < IDX_KEYCACHE) rg = s_range[i];
+            else {
+                const u64 key = kp[i];
+                u32 slot = idx_hash(key, p.mask);
+                unsigned long long k2;
+                while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
+                rg = k2 == key ? make_uint2(p.tab_off[slot], p.tab_cnt[slot]) : make_uint2(0, 0);
             }
+            for (u32 t = 0; t < rg.y; ++t) { const u32 r = p.postings[rg.x + t] - p.slab_base; score[r >> 1] = 0; }
         }
     }
 }

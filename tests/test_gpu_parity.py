@@ -321,7 +321,7 @@ def test_index_path_ties_ranks_and_short_sequences(oracle):
 
 
 def test_index_path_multi_slab_large_batch(oracle):
-    # more representatives than one index slab (53,248) and a batch large enough to take the index path by itself
+    # more representatives than one index slab (51,200) and a batch large enough to take the index path by itself
     res, off, _ = synth.generate(0x5EED0005, 80000, 1600)
     nrep = 60000
     c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
