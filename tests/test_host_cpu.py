@@ -1,0 +1,139 @@
+"""CPU tests of the C++ host layer's pure-host parts (kmers/reps_b200/host/selftest makes no GPU call):
+java.util.HashMap order emulation, Java number formatting, FASTA I/O and the RepGenomeDb load->save round trip,
+each against the oracle's independent implementation or the reference's own data file."""
+import os
+import subprocess
+from decimal import Decimal
+
+import numpy as np
+import pytest
+
+from oracle import kr_oracle as ko
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "kmers", "reps_b200", "host", "selftest")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(TOOL):
+        import __graft_entry__ as g
+        g.build()
+    assert os.path.exists(TOOL)
+
+
+def run(args, text="", check=True):
+    p = subprocess.run([TOOL] + args, input=text.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    if check:
+        assert p.returncode == 0, p.stderr.decode()
+    return p
+
+
+def test_hashmap_order_matches_oracle_and_rep50(rep50, oracle):
+    ids = [ko.genome_id_of(f) for (f, _, _) in rep50["reps"]]
+    got = [int(x) for x in run(["order"], "\n".join(ids) + "\n").stdout.split()]
+    assert got == list(range(len(ids)))                    # file order is iteration order: a fixed point
+    rng = np.random.default_rng(21)
+    for trial in range(6):
+        n = int(rng.integers(1, 5000))
+        keys = ["%d.%d" % (rng.integers(1, 3000000), rng.integers(1, 400)) for _ in range(n)]
+        keys += keys[: n // 10]                            # re-put of existing keys keeps their position
+        try:
+            want = list(oracle.java_hashmap_order(keys))
+        except ValueError:
+            p = run(["order"], "\n".join(keys) + "\n", check=False)
+            assert p.returncode == 1 and "tree bin" in p.stderr.decode()
+            continue
+        got = [int(x) for x in run(["order"], "\n".join(keys) + "\n").stdout.split()]
+        assert got == want
+        assert got == ko.py_java_hashmap_order(keys)
+
+
+def test_hashmap_tree_bin_is_refused_not_mis_ordered(oracle):
+    # 16 keys with the same String.hashCode ("Aa" and "BB" hash alike): the 11th lands in a full bin of a 64-slot
+    # table, where java.util.HashMap builds a tree; both emulations must refuse rather than guess an order
+    import itertools
+    keys = ["".join(p) for p in itertools.product(("Aa", "BB"), repeat=4)]
+    assert len({ko.java_string_hash(k) for k in keys}) == 1
+    with pytest.raises(ValueError):
+        oracle.java_hashmap_order(keys)
+    p = run(["order"], "\n".join(keys) + "\n", check=False)
+    assert p.returncode == 1 and "tree bin" in p.stderr.decode()
+
+
+def test_hashmap_remove_keeps_order():
+    keys = ["k%d" % i for i in range(200)]
+    script = keys + ["-k%d" % i for i in range(0, 200, 3)]
+    got = [int(x) for x in run(["order-remove"], "\n".join(script) + "\n").stdout.split()]
+    full = ko.py_java_hashmap_order(keys)
+    assert got == [i for i in full if i % 3 != 0]
+
+
+def py_double_to_string(x: float) -> str:
+    if x == 0:
+        return "0.0"
+    d = Decimal(repr(x))
+    sign, digits, exp = d.as_tuple()
+    digits = list(digits)
+    while len(digits) > 1 and digits[-1] == 0:
+        digits.pop()
+        exp += 1
+    e10 = len(digits) - 1 + exp
+    s = "-" if sign else ""
+    if 1e-3 <= abs(x) < 1e7:
+        t = format(d, "f")
+        if "." not in t:
+            t += ".0"
+        elif t.endswith("0") and not t.endswith(".0"):
+            t = t.rstrip("0")
+            if t.endswith("."):
+                t += "0"
+        return t
+    return s + str(digits[0]) + "." + ("".join(map(str, digits[1:])) or "0") + "E" + str(e10)
+
+
+def test_java_number_formatting():
+    rng = np.random.default_rng(5)
+    vals = list(rng.random(3000)) + [0.125, 0.375, 0.0005, 0.9999995, 1.0, 0.0, 0.5110619469026549, 0.06470588235294117,
+                                     2.5, 0.045, 0.005, 0.015, 0.025, 1e-9, 123456.789]
+    text = "\n".join(repr(float(v)) for v in vals) + "\n"
+    for (w, p) in ((8, 6), (8, 4), (12, 8), (4, 2), (1, 0)):
+        got = run(["fixed", str(w), str(p)], text).stdout.decode().split("\n")[:-1]
+        assert got == [ko.java_fixed(float(v), w, p) for v in vals], (w, p)
+    dv = vals + [1e7, 9999999.0, 1.2345678e7, 1e-3, 9.99e-4, 2.5e-5, 1e21, 343.7, 100.0, 1234567.125]
+    got = run(["dtos"], "\n".join(repr(float(v)) for v in dv) + "\n").stdout.decode().split("\n")[:-1]
+    assert got == [py_double_to_string(float(v)) for v in dv]
+    assert py_double_to_string(1.2345678e7) == "1.2345678E7" and py_double_to_string(2.5e-5) == "2.5E-5"
+
+
+def test_repdb_load_save_is_byte_identical(tmp_path, rep50):
+    src, out = tmp_path / "rep50.db", tmp_path / "resaved.db"
+    src.write_bytes(rep50["raw"])
+    p = run(["resave", str(src), str(out)])
+    assert out.read_bytes() == rep50["raw"]
+    assert p.stdout.decode().strip() == "1480 50 8 Phenylalanyl-tRNA synthetase alpha chain"
+    # a database whose records arrive in another order is re-ordered exactly as java.util.HashMap would
+    rng = np.random.default_rng(3)
+    shuffled = [rep50["reps"][i] for i in rng.permutation(1480)]
+    src.write_bytes(ko.save_repdb(50, 8, rep50["prot_name"], shuffled))
+    run(["resave", str(src), str(out)])
+    ids = [ko.genome_id_of(f) for (f, _, _) in shuffled]
+    want = ko.save_repdb(50, 8, rep50["prot_name"], [shuffled[i] for i in ko.py_java_hashmap_order(ids)])
+    assert out.read_bytes() == want
+    bad = tmp_path / "bad.db"
+    bad.write_bytes(b">NotARepDb\n>fig|1.1.peg.1 x\nACD\n")
+    p = run(["resave", str(bad), str(out)], check=False)
+    assert p.returncode == 1 and "invalid rep-genome header" in p.stderr.decode()
+
+
+def test_fasta_reader_and_genome_ids(vapb, rep50):
+    from tests.conftest import golden_bytes
+    got = [l.split("\t") for l in run(["fasta"], golden_bytes("VapbProt.fa").decode()).stdout.decode().split("\n")[:-1]]
+    assert [tuple(g) for g in got] == [tuple(r) for r in vapb]
+    # CRLF input, blank lines, a header without sequence, trailing record without newline
+    txt = ">a first one\r\nACD\r\n\r\nEFG\r\n>empty\r\n>b\r\nKLM"
+    got = run(["fasta"], txt).stdout.decode().split("\n")[:-1]
+    assert got == ["a\tfirst one\tACDEFG", "empty\t\t", "b\t\tKLM"]
+    fids = [f for (f, _, _) in rep50["reps"][:50]] + ["fig|83333.1.peg.4", "notafig", "fig|12.peg.1"]
+    got = run(["genomeof"], "\n".join(fids) + "\n").stdout.decode().split("\n")[:-1]
+    assert got == [ko.genome_id_of(f) for f in fids]
