@@ -83,3 +83,16 @@ def test_shard_range_partition():
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_block_shards_cut_at_tiles():
+    from kmers.reps_b200 import sharding
+    for n in (1, 255, 256, 257, 100000, 1480):
+        for w in (1, 2, 3, 4, 8):
+            cuts = sharding.block_shards(n, w)
+            assert cuts[0] == 0 and cuts[-1] == n and len(cuts) == w + 1
+            assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+            assert all(c % 256 == 0 for c in cuts[:-1])          # inner shards hold whole 256-sequence blocks
+    cuts = sharding.block_shards(100000, 8)
+    sizes = [b - a for a, b in zip(cuts, cuts[1:])]
+    assert max(sizes) - min(sizes) <= 256 + 160
