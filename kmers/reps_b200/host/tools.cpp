@@ -4,6 +4,9 @@
 //   kmers_reps distances  DistanceMatrixProcessor.java   all-vs-all distances of the reps of a DB
 //   kmers_reps group      RepMatrixProcessor.java        incremental all-vs-all + greedy grouping by distance
 //   kmers_reps classify   ClassifyProcessor.java         min distance of each input sequence to its named group
+//   kmers_reps buildsets  GenomeProcessor.java + BaseGenomeProcessor.java:151-214,348-407,433-442
+//                                                       the hot part of the `genomes` pipeline: hierarchical rep sets at
+//                                                       several thresholds, saved as rep<thr>.ser + rep<thr>.list.tbl
 //
 // Same options, same output text.  What changed is only what north_star lists: the
 // per-pair / per-query loops became batched calls; every similarity comes from the GPU library.
@@ -19,7 +22,8 @@ static void usage() {
                  "  repdb     [-m sim] [-K k] [-p role] [--create fasta] [-x maxErr] [--list file] [--stats file] [--null] [--batch n] dbFile < input.fa\n"
                  "  distances dbFile\n"
                  "  group     [-K k] [-i fasta] [-m maxDist]\n"
-                 "  classify  [-K k] [-i fasta] [-m maxDist] controlFile\n";
+                 "  classify  [-K k] [-i fasta] [-m maxDist] controlFile\n"
+                 "  buildsets [-K k] [-t 10,50,100,200] [-p role] [--batch n] outDir input.fa\n";
 }
 
 struct Args {
@@ -246,6 +250,56 @@ static int cmd_classify(int argc, char **argv) {
     return 0;
 }
 
+// ---- buildsets: the similarity work of the `genomes` pipeline ------------------------------------------
+// Input: one FASTA record per genome (label = seed-protein feature id, comment = genome name, sequence = seed
+// protein) in master-list order (ProteinDataFactory orders by rating, score, id; that ordering needs PATRIC
+// metadata and is done upstream of this command).  For every threshold, smallest first: the reps of the previous
+// set are copied in (copyReps, BaseGenomeProcessor.java:172-176), then every genome is offered in master order
+// (buildRepGenSet :184-214).  Outputs per threshold: rep<thr>.ser (saveRepGenSets :433-442) and rep<thr>.list.tbl
+// (writeListFiles :348-407) without the three taxonomy columns, which are PATRIC metadata.
+static int cmd_buildsets(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--kmer", "K"}, {"-t", "t"}, {"--repSizes", "t"}, {"-p", "p"}, {"--prot", "p"}, {"--batch", "batch"}, {"-v", "v"}},
+                   {"K", "t", "p", "batch"});
+    if (a.pos.size() != 2) throw std::runtime_error("ParseFailureException: Arguments \"outDir\" and \"inFile\" are required");
+    ProteinKmers::setKmerSize(a.opt.count("K") ? std::stoi(a.opt["K"]) : 8);
+    std::string protName = a.opt.count("p") ? a.opt["p"] : RepGenomeDb::DEFAULT_PROTEIN;
+    uint32_t batch = a.opt.count("batch") ? (uint32_t)std::stoul(a.opt["batch"]) : 0;
+    std::vector<int> sizes;
+    {
+        std::stringstream ss(a.opt.count("t") ? a.opt["t"] : "10,50,100,200");   // GenomeProcessor.java:62
+        std::string tok;
+        while (std::getline(ss, tok, ',')) sizes.push_back(std::stoi(tok));
+        for (size_t i = 1; i < sizes.size(); ++i)
+            if (sizes[i] <= sizes[i - 1]) throw std::runtime_error("ParseFailureException: thresholds must increase");
+    }
+    const std::string outDir = a.pos[0];
+    std::vector<Sequence> seqs = FastaInputStream(a.pos[1]).readAll();
+    std::vector<RepGenome> genomes;
+    for (auto &s : seqs) genomes.emplace_back(s);
+    std::vector<std::unique_ptr<RepGenomeDb>> sets;
+    for (int sz : sizes) sets.push_back(std::make_unique<RepGenomeDb>(sz, protName));
+    for (size_t k = 0; k < sets.size(); ++k) {   // collateGenomes :151-164
+        if (k > 0) for (const RepGenome *r : sets[k - 1]->all()) sets[k]->addRep(*r);
+        sets[k]->checkGenomes(genomes, batch);
+        if (a.flag.count("v")) std::cerr << sets[k]->toString() << ": " << sets[k]->size() << " representatives.\n";
+    }
+    std::vector<const ProteinKmers *> qp;
+    for (auto &g : genomes) qp.push_back(&g);
+    for (auto &db : sets) {
+        db->save(outDir + "/rep" + std::to_string(db->getThreshold()) + ".ser");
+        std::ofstream lf(outDir + "/" + db->getListFileName());
+        if (!lf) throw std::runtime_error("java.io.FileNotFoundException: " + outDir + "/" + db->getListFileName());
+        lf << "genome_id\tgenome_name\trep_id\tscore\tdistance\n";
+        auto res = db->findClosest(qp.begin(), qp.end());
+        for (size_t i = 0; i < genomes.size(); ++i) {
+            const auto &r = res[i];
+            lf << genomes[i].getGenomeId() << '\t' << genomes[i].getName() << '\t' << (r.getRepresentative() ? r.getGenomeId() : std::string("null")) << '\t'
+               << r.getSimilarity() << '\t' << java::format_fixed(r.getDistance(), 4, 2) << '\n';
+        }
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { usage(); return 2; }
     std::ios::sync_with_stdio(false);
@@ -255,6 +309,7 @@ int main(int argc, char **argv) {
         if (cmd == "distances") return cmd_distances(argc, argv);
         if (cmd == "group") return cmd_group(argc, argv);
         if (cmd == "classify") return cmd_classify(argc, argv);
+        if (cmd == "buildsets") return cmd_buildsets(argc, argv);
         usage();
         return 2;
     } catch (const std::exception &e) {   // App.java:129: print the error, exit non-zero

@@ -6,6 +6,7 @@ Follows (all under src/main/java/org/theseed/proteins/kmers/reps/):
   distances  DistanceMatrixProcessor.java:59,71-83
   group      RepMatrixProcessor.java:88-125 + SequenceInfo.java:62-148 (double accumulation in that exact order)
   classify   ClassifyProcessor.java:112-120
+  buildsets  BaseGenomeProcessor.java:151-214 (collateGenomes / copyReps / buildRepGenSet), :348-407 (list files)
 """
 import math
 
@@ -127,3 +128,36 @@ def classify(groups, queries, max_dist=0.995, K=8, ident_inf=True):
         if best <= max_dist:
             out.append("%s\t%s\t%s" % (label, comment, ko.java_fixed(best, 12, 8)))
     return "\n".join(out) + "\n"
+
+
+def buildsets(records, thresholds, K=8, prot_name="Phenylalanyl-tRNA synthetase alpha chain", ident_inf=True):
+    """records: [(fid, name, seq)] in master order -> {thr: (db bytes, list-file text)}"""
+    o = ko.get()
+    out = {}
+    prev = []                                     # reps of the previous (smaller) set, in its iteration order
+    qb = o.batch([r[2] for r in records], K=K)
+    qs = qb.sizes()
+    for thr in thresholds:
+        order = prev + list(records)              # copyReps first, then every genome in master order
+        b = o.batch([r[2] for r in order], K=K)
+        n, added, _ = o.greedy_build(b, thr, ident_inf=ident_inf)
+        kept = [order[i] for i in np.nonzero(added)[0]]
+        ids, by_id = [], {}
+        for r in kept:
+            g = ko.genome_id_of(r[0])
+            if g not in by_id:
+                ids.append(g)
+            by_id[g] = r
+        reps = [by_id[ids[i]] for i in o.java_hashmap_order(ids)]
+        db_bytes = ko.save_repdb(thr, K, prot_name, reps)
+        rb = o.batch([r[2] for r in reps], K=K)
+        rs = rb.sizes()
+        bs, bi = o.find_closest(rb, qb, ident_inf=ident_inf, threads=4)
+        lines = ["genome_id\tgenome_name\trep_id\tscore\tdistance"]
+        for q, (rec, s, i) in enumerate(zip(records, bs, bi)):
+            rep_id = ko.genome_id_of(reps[i][0]) if s > 0 else "null"
+            d = o.distance(s, qs[q], rs[i]) if s > 0 else 1.0
+            lines.append("%s\t%s\t%s\t%d\t%s" % (ko.genome_id_of(rec[0]), rec[1], rep_id, s, ko.java_fixed(d, 4, 2)))
+        out[thr] = (db_bytes, "\n".join(lines) + "\n")
+        prev = reps
+    return out

@@ -51,3 +51,30 @@ def test_chunks_longer_than_a_stage(oracle, length, n):
     want10 = oracle.sim_matrix(oracle.batch(seqs[:260], K=10), ident_inf=False, threads=8)
     assert (c10.sim_matrix(s10) == want10).all()
     c10.close()
+
+
+def test_buildsets_hierarchy(tmp_path):
+    """the `genomes` pipeline's similarity work (multi-threshold hierarchical rep sets) against its restatement"""
+    import os
+    import subprocess
+    from kmers.reps_b200 import synth
+    from oracle import ref_commands as rc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "kmers", "reps_b200", "host", "kmers_reps")
+    res, off, _ = synth.generate(0x5EED0006, 1500, 30)
+    seqs = synth.to_strings(res, off)
+    recs = [("fig|%d.%d.peg.%d" % (2000 + 3 * i, 1 + i % 7, 10 + i), "Synthetic genome %d" % i, s) for i, s in enumerate(seqs)]
+    src = tmp_path / "master.fa"
+    src.write_bytes(b"".join(ko.write_fasta_record(*r) for r in recs))
+    thresholds = [10, 50, 100, 200]
+    p = subprocess.run([tool, "buildsets", "-t", ",".join(map(str, thresholds)), str(tmp_path), str(src)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()
+    want = rc.buildsets(recs, thresholds)
+    sizes = []
+    for thr in thresholds:
+        db_bytes, listing = want[thr]
+        assert (tmp_path / ("rep%d.ser" % thr)).read_bytes() == db_bytes
+        assert (tmp_path / ("rep%d.list.tbl" % thr)).read_text() == listing
+        sizes.append(db_bytes.count(b">") - 1)
+    assert sizes == sorted(sizes) and sizes[0] < sizes[-1]            # larger thresholds keep more representatives
