@@ -459,6 +459,48 @@ class RepGenomeDb {
         return out;
     }
 
+    // Similarity of every query to EVERY representative: row q holds `new Representation(rep, query).getSimilarity()`
+    // for the reps in iteration order (the rewritten `for (RepGenome rep : this.reps)` loop of
+    // NeighborProcessor.java:165-168).  reps_out receives that order.  One rectangular GPU matrix per query chunk.
+    template <class It> std::vector<int32_t> similarities(It first, It last, std::vector<const RepGenome *> *reps_out) const {
+        std::vector<const RepGenome *> reps = all();
+        if (reps_out) *reps_out = reps;
+        ProteinKmers::encodeBatch(first, last);
+        std::vector<const ProteinKmers *> v;
+        for (It it = first; it != last; ++it) v.push_back(ptr(*it));
+        std::vector<int32_t> out(v.size() * reps.size());
+        if (v.empty() || reps.empty()) return out;
+        ProteinKmers::encodeBatch(reps.begin(), reps.end());   // one launch; the reps keep their sizes for distance()
+        auto hr = batchOf(std::vector<const ProteinKmers *>(reps.begin(), reps.end()));
+        const size_t R = reps.size(), chunk = std::max<size_t>(256, ((size_t)1 << 26) / R / 256 * 256);   // <= 64M cells per launch
+        for (size_t q0 = 0; q0 < v.size(); q0 += chunk) {
+            const size_t n = std::min(chunk, v.size() - q0);
+            std::vector<const ProteinKmers *> part(v.begin() + q0, v.begin() + q0 + n);
+            auto hq = batchOf(part);
+            kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_FULL, 0, (uint32_t)n};
+            KmerEngine::check(hq->ctx, kr_sim_matrix(hq->ctx, hq->set, hr->set, &d, out.data() + q0 * R));
+        }
+        return out;
+    }
+    // The N closest representatives of one query, with the reference's tie retention (NeighborProcessor.java:161-193):
+    // an insertion-sorted list, descending by similarity; a new result goes BEFORE the entries it ties with; when the
+    // list outgrows `num` it is cut back to `num` only if the entry at the break beats the one after it, so ties
+    // across the break are all kept.  `row` = similarities in iteration order; returns positions into it.
+    static std::vector<size_t> closestN(const int32_t *row, size_t R, int num, int minSim) {
+        std::vector<size_t> found;
+        for (size_t r = 0; r < R; ++r) {
+            const int sim = row[r];
+            if (sim < minSim) continue;
+            size_t idx = 0; const size_t n = found.size();
+            while (idx < n && row[found[idx]] > sim) idx++;
+            if (idx < n || n < (size_t)num) {
+                found.insert(found.begin() + idx, r);
+                if (found.size() > (size_t)num && row[found[num - 1]] > row[found[num]]) found.resize(num);
+            }
+        }
+        return found;
+    }
+
     // checkSimilarity(ProteinKmers, sim): is some rep at least this similar? (BaseGenomeProcessor.java:203)
     bool checkSimilarity(const ProteinKmers &q, int sim) const {
         if (size() == 0) return false;

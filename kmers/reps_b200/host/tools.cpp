@@ -4,6 +4,7 @@
 //   kmers_reps distances  DistanceMatrixProcessor.java   all-vs-all distances of the reps of a DB
 //   kmers_reps group      RepMatrixProcessor.java        incremental all-vs-all + greedy grouping by distance
 //   kmers_reps classify   ClassifyProcessor.java         min distance of each input sequence to its named group
+//   kmers_reps neighbors  NeighborProcessor.java          the N closest representatives of each input genome, ties retained
 //   kmers_reps buildsets  GenomeProcessor.java + BaseGenomeProcessor.java:151-214,348-407,433-442
 //                                                       the hot part of the `genomes` pipeline: hierarchical rep sets at
 //                                                       several thresholds, saved as rep<thr>.ser + rep<thr>.list.tbl
@@ -23,6 +24,7 @@ static void usage() {
                  "  distances dbFile\n"
                  "  group     [-K k] [-i fasta] [-m maxDist]\n"
                  "  classify  [-K k] [-i fasta] [-m maxDist] controlFile\n"
+                 "  neighbors [-n num] [--min sim] dbFile seeds.tbl\n"
                  "  buildsets [-K k] [-t 10,50,100,200] [-p role] [--batch n] outDir input.fa\n";
 }
 
@@ -250,6 +252,54 @@ static int cmd_classify(int argc, char **argv) {
     return 0;
 }
 
+// ---- neighbors (NeighborProcessor.java:130-230) ---------------------------------------------------------
+// The reference reads genomes from a GenomeSource and takes each one's seed protein and DNA length; GTO ingest is
+// outside the path, so the input here is a tab-delimited file with a header line and the columns
+// seed_fid, genome_name, dna_size, seed_protein.  Output text is the reference's, row for row.
+static int cmd_neighbors(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-n", "n"}, {"--num", "n"}, {"--min", "min"}, {"-v", "v"}}, {"n", "min"});
+    if (a.pos.size() != 2) throw std::runtime_error("ParseFailureException: Arguments \"repDbFile\" and \"inFile\" are required");
+    int num = a.opt.count("n") ? std::stoi(a.opt["n"]) : 5, minSim = a.opt.count("min") ? std::stoi(a.opt["min"]) : 1;   // :106-109
+    if (num <= 0) throw std::runtime_error("ParseFailureException: Close-genome count (num) must be at least 1.");   // :115
+    if (minSim < 0) throw std::runtime_error("ParseFailureException: Minimum similarity cannot be zero.");            // :118
+    { std::ifstream probe(a.pos[0]); if (!probe) throw std::runtime_error("java.io.FileNotFoundException: Repgen database file " + a.pos[0] + " is not found or unreadable."); }
+    auto repDb = RepGenomeDb::load(a.pos[0]);
+    std::ifstream in(a.pos[1]);
+    if (!in) throw std::runtime_error("java.io.FileNotFoundException: Input genome source " + a.pos[1] + " does not exist.");
+    std::vector<RepGenome> seeds; std::vector<long> dnaSize;
+    std::string line;
+    std::getline(in, line);   // header
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        std::vector<std::string> f; size_t b = 0;
+        for (size_t t; (t = line.find('\t', b)) != std::string::npos; b = t + 1) f.push_back(line.substr(b, t - b));
+        f.push_back(line.substr(b));
+        if (f.size() < 4) throw std::runtime_error("java.io.IOException: input line needs 4 fields: " + line);
+        seeds.emplace_back(f[0], f[1], f[3]);
+        dnaSize.push_back(std::stol(f[2]));
+    }
+    std::cout << "genome_id\tgenome_name\tsize\trep_id\trep_name\tsim\tdistance\tclosest\tsignal\n";   // :135
+    std::vector<const RepGenome *> reps;
+    std::vector<int32_t> sims = repDb->similarities(seeds.begin(), seeds.end(), &reps);
+    const size_t R = reps.size();
+    for (size_t g = 0; g < seeds.size(); ++g) {   // processGenome :155-203, writeResults :212-230
+        const int32_t *row = sims.data() + g * R;
+        std::string prefix = seeds[g].getGenomeId() + "\t" + seeds[g].getName() + "\t" + std::to_string(dnaSize[g]);
+        auto found = RepGenomeDb::closestN(row, R, num, minSim);
+        if (found.empty()) { std::cout << prefix << "\t\t\t\t\t\t\n"; continue; }
+        const char *closeFlag = "Y";
+        for (size_t r : found) {
+            double dist = ProteinKmers::distance(row[r], seeds[g], *reps[r]);
+            double signal = (double)dnaSize[g] * (1.0 - dist);
+            std::cout << prefix << '\t' << reps[r]->getGenomeId() << '\t' << reps[r]->getName() << '\t' << row[r] << '\t'
+                      << java::double_to_string(dist) << '\t' << closeFlag << '\t' << java::double_to_string(signal) << '\n';
+            closeFlag = " ";
+        }
+    }
+    return 0;
+}
+
 // ---- buildsets: the similarity work of the `genomes` pipeline ------------------------------------------
 // Input: one FASTA record per genome (label = seed-protein feature id, comment = genome name, sequence = seed
 // protein) in master-list order (ProteinDataFactory orders by rating, score, id; that ordering needs PATRIC
@@ -309,6 +359,7 @@ int main(int argc, char **argv) {
         if (cmd == "distances") return cmd_distances(argc, argv);
         if (cmd == "group") return cmd_group(argc, argv);
         if (cmd == "classify") return cmd_classify(argc, argv);
+        if (cmd == "neighbors") return cmd_neighbors(argc, argv);
         if (cmd == "buildsets") return cmd_buildsets(argc, argv);
         usage();
         return 2;

@@ -6,6 +6,7 @@ Follows (all under src/main/java/org/theseed/proteins/kmers/reps/):
   distances  DistanceMatrixProcessor.java:59,71-83
   group      RepMatrixProcessor.java:88-125 + SequenceInfo.java:62-148 (double accumulation in that exact order)
   classify   ClassifyProcessor.java:112-120
+  neighbors  NeighborProcessor.java:155-230 (insertion-sorted top-N with tie retention; Double.toString columns)
   buildsets  BaseGenomeProcessor.java:151-214 (collateGenomes / copyReps / buildRepGenSet), :348-407 (list files)
 """
 import math
@@ -161,3 +162,63 @@ def buildsets(records, thresholds, K=8, prot_name="Phenylalanyl-tRNA synthetase 
         out[thr] = (db_bytes, "\n".join(lines) + "\n")
         prev = reps
     return out
+
+
+def java_double_to_string(x: float) -> str:
+    """Double.toString (JDK 19+: shortest round-trip digits; plain notation for 1e-3 <= |x| < 1e7)"""
+    from decimal import Decimal
+    if x == 0:
+        return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    digits = list(digits)
+    while len(digits) > 1 and digits[-1] == 0:
+        digits.pop()
+        exp += 1
+    point = len(digits) + exp                      # value = 0.d1d2... * 10**point
+    ds = "".join(map(str, digits))
+    if 1e-3 <= abs(x) < 1e7:
+        if point <= 0:
+            body = "0." + "0" * (-point) + ds
+        elif point >= len(ds):
+            body = ds + "0" * (point - len(ds)) + ".0"
+        else:
+            body = ds[:point] + "." + ds[point:]
+    else:
+        body = ds[0] + "." + (ds[1:] or "0") + "E" + str(point - 1)
+    return ("-" if sign else "") + body
+
+
+def neighbors(db_reps, seeds, num=5, min_sim=1, K=8, ident_inf=True):
+    """db_reps: [(fid, name, seq)] in iteration (file) order; seeds: [(fid, name, dna_size, seq)] -> report text"""
+    o = ko.get()
+    rb = o.batch([r[2] for r in db_reps], K=K)
+    qb = o.batch([q[3] for q in seeds], K=K)
+    m = o.sim_matrix(qb, rb, ident_inf=ident_inf, threads=4)
+    rs, qs = rb.sizes(), qb.sizes()
+    out = ["genome_id\tgenome_name\tsize\trep_id\trep_name\tsim\tdistance\tclosest\tsignal"]
+    for g, (fid, name, dna_size, _) in enumerate(seeds):
+        found = []                                  # (sim, rep index), as the ArrayList of :161
+        for r in range(len(db_reps)):
+            sim = int(m[g, r])
+            if sim >= min_sim:
+                idx, n = 0, len(found)
+                while idx < n and found[idx][0] > sim:
+                    idx += 1
+                if idx < n or n < num:
+                    found.insert(idx, (sim, r))
+                    if len(found) > num:
+                        if found[num - 1][0] > found[num][0]:
+                            while len(found) > num:
+                                del found[num]
+        prefix = "%s\t%s\t%d" % (ko.genome_id_of(fid), name, dna_size)
+        if not found:
+            out.append(prefix + "\t\t\t\t\t\t")
+            continue
+        flag = "Y"
+        for sim, r in found:
+            dist = o.distance(sim, qs[g], rs[r])
+            signal = dna_size * (1.0 - dist)
+            out.append("%s\t%s\t%s\t%d\t%s\t%s\t%s" % (prefix, ko.genome_id_of(db_reps[r][0]), db_reps[r][1], sim,
+                                                     java_double_to_string(dist), flag, java_double_to_string(signal)))
+            flag = " "
+    return "\n".join(out) + "\n"

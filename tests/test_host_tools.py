@@ -123,3 +123,32 @@ def test_error_behaviour(tmp_path):
     bad.write_bytes(b">fig|1.1.peg.1 x\nACDEFGHIKLMNPQRSTVWYacd\n")
     p = run(["repdb", "--create", str(bad), "--null", str(tmp_path / "o.db")], check=False)
     assert p.returncode == 1 and "outside" in p.stderr.decode()
+
+
+def test_neighbors_top_n_with_ties(tmp_path, rep50, gto_seeds, rickettsia, oracle):
+    """`neighbors` (NeighborProcessor.java:155-230): the N closest representatives of each genome with the
+    reference's tie retention.  The database holds 100 Rickettsia seed proteins of which only 34 are distinct, so
+    equal similarities (and equal-sequence INFINITY hits) straddle the cut for most queries."""
+    recs = list(rep50["reps"][:300]) + [("fig|%s.peg.1" % g, "Rickettsia %s" % g, p) for (g, p) in rickettsia]
+    ids = [ko.genome_id_of(r[0]) for r in recs]
+    assert len(set(ids)) == len(ids)
+    db = tmp_path / "mix.db"
+    db.write_bytes(ko.save_repdb(50, 8, "Phenylalanyl-tRNA synthetase alpha chain", recs))
+    it_order = [recs[i] for i in oracle.java_hashmap_order(ids)]          # load() re-inserts in file order
+    seeds = [(f, n, 1000000 + 1234 * k, s) for k, (f, n, s) in enumerate(gto_seeds)]
+    seeds += [("fig|%s.peg.7" % g, "query %s" % g, 1100000 + 77 * k, p) for k, (g, p) in enumerate(rickettsia[:12])]
+    seeds.append(("fig|9.9.peg.1", "nothing close", 5, "MKV" * 30))
+    src = tmp_path / "seeds.tbl"
+    src.write_text("seed_fid\tgenome_name\tdna_size\tseed_protein\n" + "".join("%s\t%s\t%d\t%s\n" % s for s in seeds))
+    for num, min_sim in ((3, 1), (5, 1), (1, 60), (2, 0)):
+        p = run(["neighbors", "-n", str(num), "--min", str(min_sim), str(db), str(src)])
+        want = rc.neighbors(it_order, seeds, num=num, min_sim=min_sim)
+        assert p.stdout.decode() == want
+    text = rc.neighbors(it_order, seeds, num=3, min_sim=1)
+    per = {}
+    for ln in text.split("\n")[1:-1]:
+        per.setdefault(ln.split("\t")[0], []).append(ln.split("\t"))
+    assert max(len(v) for v in per.values()) > 3                          # ties across the cut were kept
+    assert any(r[5] == "9999" and r[6] == "0.0" for v in per.values() for r in v)
+    assert per["9.9"][0][3:] == ["", "", "", "", "", ""]
+    assert run(["neighbors", "-n", "0", str(db), str(src)], check=False).returncode != 0
