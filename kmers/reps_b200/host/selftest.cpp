@@ -4,6 +4,7 @@
 // independent implementations.
 //
 //   selftest order              < keys (one per line)        -> iteration order (insertion indices)
+//   selftest order-remove [every] < keys, -key, ~key           -> order after puts / Iterator.remove / Map.remove, + invariants
 //   selftest fixed W P          < doubles (one per line)     -> String.format("%W.Pf")
 //   selftest dtos               < doubles                    -> Double.toString
 //   selftest resave IN OUT                                   -> RepGenomeDb::load(IN)->save(OUT)
@@ -25,8 +26,16 @@ int main(int argc, char **argv) {
         } else if (cmd == "order-remove") {   // keys; lines starting with '-' remove that key
             java::HashMapOrder m;
             std::string line;
-            while (std::getline(std::cin, line)) { if (!line.empty() && line[0] == '-') m.remove(line.substr(1)); else m.put(line); }
+            // '-key': Iterator.remove();  '~key': Map.remove(key);  last line: invariants and number of tree bins
+            bool ok = true;
+            while (std::getline(std::cin, line)) {
+                if (!line.empty() && line[0] == '-') m.remove(line.substr(1), false);
+                else if (!line.empty() && line[0] == '~') m.remove(line.substr(1), true);
+                else m.put(line);
+                if (argc > 2) ok = ok && m.checkInvariants();   // "order-remove every": check after every operation
+            }
             for (int i : m.order()) std::cout << i << '\n';
+            std::cout << "inv=" << (ok && m.checkInvariants()) << " treebins=" << m.treeBins() << '\n';
         } else if (cmd == "fixed" && argc == 4) {
             int w = std::atoi(argv[2]), p = std::atoi(argv[3]);
             std::string line;

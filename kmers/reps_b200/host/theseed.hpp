@@ -51,59 +51,345 @@ inline uint32_t string_hash(const std::string &s) {   // String.hashCode()
 // Iteration order of java.util.HashMap<String,V> (OpenJDK 8+): RepGenomeDb stores its representatives in
 // one keyed by genome id, so save(), every `for (RepGenome rep : repDb)` loop and the tie-breaking of
 // findClosest inherit this order (data/rep50.db is in exactly this order).
-// Tree bins (a 9th key in one bucket at capacity >= 64) are detected and refused, not emulated.
+//
+// This is a structural emulation of java.util.HashMap for String keys, including tree bins:
+// a bin whose 9th node arrives at table capacity >= 64 becomes a red-black tree ordered by (signed spread hash,
+// String.compareTo); its iteration order is the `next` chain, which treeify()/putTreeVal()/moveRootToFront()/
+// split()/untreeify()/removeTreeNode() maintain exactly as OpenJDK's HashMap.java does (restated from the OpenJDK
+// source, which is not part of the reference tree; String keys never need tieBreakOrder(), so the order is
+// deterministic).  Nodes are indexed by insertion number; -1 is null.
 class HashMapOrder {
   public:
-    // returns the insertion index of the key (existing or new); *is_new tells which
+    // put(key, v): returns the insertion index of the key (existing or new); *is_new tells which
     int put(const std::string &key, bool *is_new = nullptr) {
         auto it = index_.find(key);
-        if (it != index_.end()) { if (is_new) *is_new = false; return it->second; }
+        if (it != index_.end()) { if (is_new) *is_new = false; return it->second; }   // existing mapping keeps its place
         if (is_new) *is_new = true;
-        int id = (int)keys_.size();
+        const int x = (int)nd_.size();
         uint32_t h = string_hash(key); h ^= h >> 16;
-        keys_.push_back(key); hash_.push_back(h); alive_.push_back(1);
-        index_[key] = id;
-        if (table_.empty()) { table_.assign(16, {}); threshold_ = 12; }
-        auto &bin = table_[h & (table_.size() - 1)];
-        size_t depth = bin.size();
-        bin.push_back(id);
-        if (depth >= 8) {
-            if (table_.size() < 64) resize();
-            else throw std::runtime_error("java.util.HashMap would build a tree bin for key " + key + "; not emulated");
+        nd_.push_back(Node{}); nd_[x].hash = (int32_t)h; keys_.push_back(key);
+        index_[key] = x;
+        if (tab_.empty()) { tab_.assign(16, -1); threshold_ = 12; }
+        const size_t i = h & (tab_.size() - 1);
+        int p = tab_[i];
+        if (p < 0) tab_[i] = x;
+        else if (nd_[p].tree) putTreeVal(p, x);
+        else {
+            for (int binCount = 0;; ++binCount) {
+                const int e = nd_[p].next;
+                if (e < 0) {
+                    nd_[p].next = x;
+                    if (binCount >= TREEIFY_THRESHOLD - 1) treeifyBin(h);
+                    break;
+                }
+                p = e;
+            }
         }
         if (++size_ > threshold_) resize();
-        return id;
+        return x;
     }
     bool contains(const std::string &key) const { return index_.count(key) != 0; }
     int find(const std::string &key) const { auto it = index_.find(key); return it == index_.end() ? -1 : it->second; }
-    void remove(const std::string &key) {   // Iterator.remove(): unlink, no reordering
+    // Iterator.remove() (movable = false, UpdateProcessor.java:96-103) or Map.remove(key) (movable = true)
+    void remove(const std::string &key, bool movable = false) {
         auto it = index_.find(key);
         if (it == index_.end()) return;
-        int id = it->second;
-        auto &bin = table_[hash_[id] & (table_.size() - 1)];
-        bin.erase(std::find(bin.begin(), bin.end(), id));
-        alive_[id] = 0; index_.erase(it); --size_;
+        const int node = it->second;
+        const size_t i = (uint32_t)nd_[node].hash & (tab_.size() - 1);
+        if (nd_[node].tree) removeTreeNode(node, movable);
+        else if (tab_[i] == node) tab_[i] = nd_[node].next;
+        else { int p = tab_[i]; while (nd_[p].next != node) p = nd_[p].next; nd_[p].next = nd_[node].next; }
+        index_.erase(it); --size_;
     }
     size_t size() const { return size_; }
     std::vector<int> order() const {   // insertion indices in iteration order
         std::vector<int> o; o.reserve(size_);
-        for (auto &bin : table_) for (int id : bin) o.push_back(id);
+        for (int head : tab_) for (int e = head; e >= 0; e = nd_[e].next) o.push_back(e);
         return o;
     }
+    size_t treeBins() const { size_t n = 0; for (int head : tab_) n += head >= 0 && nd_[head].tree; return n; }
+    // structural self-check used by the tests: red-black and ordering invariants of every tree bin, and that each
+    // bin's next chain holds exactly the nodes of its tree
+    bool checkInvariants() const {
+        for (size_t i = 0; i < tab_.size(); ++i) {
+            int head = tab_[i];
+            if (head < 0 || !nd_[head].tree) { for (int e = head; e >= 0; e = nd_[e].next) if (((uint32_t)nd_[e].hash & (tab_.size() - 1)) != i) return false; continue; }
+            int root = head; while (nd_[root].parent >= 0) root = nd_[root].parent;
+            size_t chain = 0; int prev = -1;
+            for (int e = head; e >= 0; prev = e, e = nd_[e].next) { if (nd_[e].prev != prev || !nd_[e].tree) return false; ++chain; }
+            size_t cnt = 0; int bh = -1;
+            if (nd_[root].red || !checkTree(root, 0, &bh, &cnt) || cnt != chain) return false;
+        }
+        return true;
+    }
   private:
+    static constexpr int TREEIFY_THRESHOLD = 8, UNTREEIFY_THRESHOLD = 6, MIN_TREEIFY_CAPACITY = 64;
+    struct Node { int32_t hash = 0; int next = -1, prev = -1, parent = -1, left = -1, right = -1; bool red = false, tree = false; };
+
+    // order inside a tree bin: signed hash, then String.compareTo (never 0 for two distinct keys)
+    int dirOf(int x, int p) const {
+        if (nd_[p].hash > nd_[x].hash) return -1;
+        if (nd_[p].hash < nd_[x].hash) return 1;
+        return keys_[x].compare(keys_[p]) < 0 ? -1 : 1;
+    }
+    int rootOf(int r) const { while (nd_[r].parent >= 0) r = nd_[r].parent; return r; }
+
+    void treeifyBin(uint32_t hash) {
+        if (tab_.size() < (size_t)MIN_TREEIFY_CAPACITY) { resize(); return; }
+        const size_t index = hash & (tab_.size() - 1);
+        int tl = -1;
+        for (int e = tab_[index]; e >= 0; e = nd_[e].next) {   // replacementTreeNode keeps the list order
+            Node &n = nd_[e]; n.tree = true; n.prev = tl; n.parent = n.left = n.right = -1; n.red = false; tl = e;
+        }
+        treeify(tab_[index]);
+    }
+    void treeify(int head) {
+        int root = -1;
+        for (int x = head, next; x >= 0; x = next) {
+            next = nd_[x].next;
+            nd_[x].left = nd_[x].right = -1;
+            if (root < 0) { nd_[x].parent = -1; nd_[x].red = false; root = x; continue; }
+            for (int p = root;;) {
+                const int dir = dirOf(x, p), xp = p;
+                p = dir <= 0 ? nd_[p].left : nd_[p].right;
+                if (p < 0) {
+                    nd_[x].parent = xp;
+                    if (dir <= 0) nd_[xp].left = x; else nd_[xp].right = x;
+                    root = balanceInsertion(root, x);
+                    break;
+                }
+            }
+        }
+        moveRootToFront(root);
+    }
+    void untreeify(int head) { for (int q = head; q >= 0; q = nd_[q].next) { Node &n = nd_[q]; n.tree = false; n.prev = n.parent = n.left = n.right = -1; n.red = false; } }
+    void putTreeVal(int first, int x) {
+        const int root = nd_[first].parent >= 0 ? rootOf(first) : first;
+        for (int p = root;;) {
+            const int dir = dirOf(x, p), xp = p;
+            p = dir <= 0 ? nd_[p].left : nd_[p].right;
+            if (p < 0) {
+                const int xpn = nd_[xp].next;
+                Node &n = nd_[x]; n.tree = true; n.next = xpn;
+                if (dir <= 0) nd_[xp].left = x; else nd_[xp].right = x;
+                nd_[xp].next = x;
+                n.parent = n.prev = xp;
+                if (xpn >= 0) nd_[xpn].prev = x;
+                moveRootToFront(balanceInsertion(root, x));
+                return;
+            }
+        }
+    }
+    void moveRootToFront(int root) {
+        if (root < 0 || tab_.empty()) return;
+        const size_t index = (uint32_t)nd_[root].hash & (tab_.size() - 1);
+        const int first = tab_[index];
+        if (root == first) return;
+        tab_[index] = root;
+        const int rp = nd_[root].prev, rn = nd_[root].next;
+        if (rn >= 0) nd_[rn].prev = rp;
+        if (rp >= 0) nd_[rp].next = rn;
+        if (first >= 0) nd_[first].prev = root;
+        nd_[root].next = first;
+        nd_[root].prev = -1;
+    }
+    int rotateLeft(int root, int p) {
+        int r, pp, rl;
+        if (p >= 0 && (r = nd_[p].right) >= 0) {
+            if ((rl = nd_[p].right = nd_[r].left) >= 0) nd_[rl].parent = p;
+            if ((pp = nd_[r].parent = nd_[p].parent) < 0) { root = r; nd_[r].red = false; }
+            else if (nd_[pp].left == p) nd_[pp].left = r;
+            else nd_[pp].right = r;
+            nd_[r].left = p; nd_[p].parent = r;
+        }
+        return root;
+    }
+    int rotateRight(int root, int p) {
+        int l, pp, lr;
+        if (p >= 0 && (l = nd_[p].left) >= 0) {
+            if ((lr = nd_[p].left = nd_[l].right) >= 0) nd_[lr].parent = p;
+            if ((pp = nd_[l].parent = nd_[p].parent) < 0) { root = l; nd_[l].red = false; }
+            else if (nd_[pp].right == p) nd_[pp].right = l;
+            else nd_[pp].left = l;
+            nd_[l].right = p; nd_[p].parent = l;
+        }
+        return root;
+    }
+    int balanceInsertion(int root, int x) {
+        nd_[x].red = true;
+        for (int xp, xpp, xppl, xppr;;) {
+            if ((xp = nd_[x].parent) < 0) { nd_[x].red = false; return x; }
+            if (!nd_[xp].red || (xpp = nd_[xp].parent) < 0) return root;
+            if (xp == (xppl = nd_[xpp].left)) {
+                if ((xppr = nd_[xpp].right) >= 0 && nd_[xppr].red) { nd_[xppr].red = false; nd_[xp].red = false; nd_[xpp].red = true; x = xpp; }
+                else {
+                    if (x == nd_[xp].right) { root = rotateLeft(root, x = xp); xpp = (xp = nd_[x].parent) < 0 ? -1 : nd_[xp].parent; }
+                    if (xp >= 0) { nd_[xp].red = false; if (xpp >= 0) { nd_[xpp].red = true; root = rotateRight(root, xpp); } }
+                }
+            } else {
+                if (xppl >= 0 && nd_[xppl].red) { nd_[xppl].red = false; nd_[xp].red = false; nd_[xpp].red = true; x = xpp; }
+                else {
+                    if (x == nd_[xp].left) { root = rotateRight(root, x = xp); xpp = (xp = nd_[x].parent) < 0 ? -1 : nd_[xp].parent; }
+                    if (xp >= 0) { nd_[xp].red = false; if (xpp >= 0) { nd_[xpp].red = true; root = rotateLeft(root, xpp); } }
+                }
+            }
+        }
+    }
+    bool isRed(int n) const { return n >= 0 && nd_[n].red; }
+    int balanceDeletion(int root, int x) {
+        for (int xp, xpl, xpr;;) {
+            if (x < 0 || x == root) return root;
+            if ((xp = nd_[x].parent) < 0) { nd_[x].red = false; return x; }
+            if (nd_[x].red) { nd_[x].red = false; return root; }
+            if ((xpl = nd_[xp].left) == x) {
+                if ((xpr = nd_[xp].right) >= 0 && nd_[xpr].red) {
+                    nd_[xpr].red = false; nd_[xp].red = true;
+                    root = rotateLeft(root, xp);
+                    xpr = (xp = nd_[x].parent) < 0 ? -1 : nd_[xp].right;
+                }
+                if (xpr < 0) x = xp;
+                else {
+                    int sl = nd_[xpr].left, sr = nd_[xpr].right;
+                    if (!isRed(sr) && !isRed(sl)) { nd_[xpr].red = true; x = xp; }
+                    else {
+                        if (!isRed(sr)) {
+                            if (sl >= 0) nd_[sl].red = false;
+                            nd_[xpr].red = true;
+                            root = rotateRight(root, xpr);
+                            xpr = (xp = nd_[x].parent) < 0 ? -1 : nd_[xp].right;
+                        }
+                        if (xpr >= 0) { nd_[xpr].red = xp < 0 ? false : nd_[xp].red; if ((sr = nd_[xpr].right) >= 0) nd_[sr].red = false; }
+                        if (xp >= 0) { nd_[xp].red = false; root = rotateLeft(root, xp); }
+                        x = root;
+                    }
+                }
+            } else {
+                if (xpl >= 0 && nd_[xpl].red) {
+                    nd_[xpl].red = false; nd_[xp].red = true;
+                    root = rotateRight(root, xp);
+                    xpl = (xp = nd_[x].parent) < 0 ? -1 : nd_[xp].left;
+                }
+                if (xpl < 0) x = xp;
+                else {
+                    int sl = nd_[xpl].left, sr = nd_[xpl].right;
+                    if (!isRed(sl) && !isRed(sr)) { nd_[xpl].red = true; x = xp; }
+                    else {
+                        if (!isRed(sl)) {
+                            if (sr >= 0) nd_[sr].red = false;
+                            nd_[xpl].red = true;
+                            root = rotateLeft(root, xpl);
+                            xpl = (xp = nd_[x].parent) < 0 ? -1 : nd_[xp].left;
+                        }
+                        if (xpl >= 0) { nd_[xpl].red = xp < 0 ? false : nd_[xp].red; if ((sl = nd_[xpl].left) >= 0) nd_[sl].red = false; }
+                        if (xp >= 0) { nd_[xp].red = false; root = rotateRight(root, xp); }
+                        x = root;
+                    }
+                }
+            }
+        }
+    }
+    void removeTreeNode(int p, bool movable) {
+        const size_t index = (uint32_t)nd_[p].hash & (tab_.size() - 1);
+        int first = tab_[index], root = first, rl;
+        const int succ = nd_[p].next, pred = nd_[p].prev;
+        if (pred < 0) tab_[index] = first = succ; else nd_[pred].next = succ;
+        if (succ >= 0) nd_[succ].prev = pred;
+        if (first < 0) return;
+        if (nd_[root].parent >= 0) root = rootOf(root);
+        if (movable && (nd_[root].right < 0 || (rl = nd_[root].left) < 0 || nd_[rl].left < 0)) { untreeify(first); return; }   // too small
+        const int pl = nd_[p].left, pr = nd_[p].right;
+        int replacement;
+        if (pl >= 0 && pr >= 0) {
+            int s = pr, sl;
+            while ((sl = nd_[s].left) >= 0) s = sl;   // successor
+            std::swap(nd_[s].red, nd_[p].red);
+            const int sr = nd_[s].right, pp = nd_[p].parent;
+            if (s == pr) { nd_[p].parent = s; nd_[s].right = p; }
+            else {
+                const int sp = nd_[s].parent;
+                if ((nd_[p].parent = sp) >= 0) { if (s == nd_[sp].left) nd_[sp].left = p; else nd_[sp].right = p; }
+                if ((nd_[s].right = pr) >= 0) nd_[pr].parent = s;
+            }
+            nd_[p].left = -1;
+            if ((nd_[p].right = sr) >= 0) nd_[sr].parent = p;
+            if ((nd_[s].left = pl) >= 0) nd_[pl].parent = s;
+            if ((nd_[s].parent = pp) < 0) root = s;
+            else if (p == nd_[pp].left) nd_[pp].left = s;
+            else nd_[pp].right = s;
+            replacement = sr >= 0 ? sr : p;
+        } else if (pl >= 0) replacement = pl;
+        else if (pr >= 0) replacement = pr;
+        else replacement = p;
+        if (replacement != p) {
+            const int pp = nd_[replacement].parent = nd_[p].parent;
+            if (pp < 0) { root = replacement; nd_[root].red = false; }
+            else if (p == nd_[pp].left) nd_[pp].left = replacement;
+            else nd_[pp].right = replacement;
+            nd_[p].left = nd_[p].right = nd_[p].parent = -1;
+        }
+        const int r = nd_[p].red ? root : balanceDeletion(root, replacement);
+        if (replacement == p) {   // detach
+            const int pp = nd_[p].parent;
+            nd_[p].parent = -1;
+            if (pp >= 0) { if (p == nd_[pp].left) nd_[pp].left = -1; else if (p == nd_[pp].right) nd_[pp].right = -1; }
+        }
+        if (movable) moveRootToFront(r);
+    }
+    // TreeNode.split(): relink into lo and hi lists preserving order, then untreeify (<= 6) or treeify again
+    void split(int b, std::vector<int> &ntab, size_t index, size_t bit) {
+        int loHead = -1, loTail = -1, hiHead = -1, hiTail = -1, lc = 0, hc = 0;
+        for (int e = b, next; e >= 0; e = next) {
+            next = nd_[e].next; nd_[e].next = -1;
+            if (((uint32_t)nd_[e].hash & bit) == 0) { if ((nd_[e].prev = loTail) < 0) loHead = e; else nd_[loTail].next = e; loTail = e; ++lc; }
+            else { if ((nd_[e].prev = hiTail) < 0) hiHead = e; else nd_[hiTail].next = e; hiTail = e; ++hc; }
+        }
+        tab_.swap(ntab);   // treeify()/moveRootToFront() work on the new table
+        if (loHead >= 0) {
+            if (lc <= UNTREEIFY_THRESHOLD) { untreeify(loHead); tab_[index] = loHead; }
+            else { tab_[index] = loHead; if (hiHead >= 0) treeify(loHead); }   // else: is already treeified
+        }
+        if (hiHead >= 0) {
+            if (hc <= UNTREEIFY_THRESHOLD) { untreeify(hiHead); tab_[index + bit] = hiHead; }
+            else { tab_[index + bit] = hiHead; if (loHead >= 0) treeify(hiHead); }
+        }
+        tab_.swap(ntab);
+    }
     void resize() {
-        size_t ocap = table_.size();
-        std::vector<std::vector<int>> nt(ocap * 2);
-        for (size_t j = 0; j < ocap; ++j)
-            for (int id : table_[j]) nt[(hash_[id] & ocap) ? j + ocap : j].push_back(id);   // lo/hi split keeps order
-        table_.swap(nt);
+        const size_t ocap = tab_.size();
+        std::vector<int> nt(ocap * 2, -1);
+        for (size_t j = 0; j < ocap; ++j) {
+            const int e = tab_[j];
+            if (e < 0) continue;
+            tab_[j] = -1;
+            if (nd_[e].next < 0) nt[(uint32_t)nd_[e].hash & (ocap * 2 - 1)] = e;
+            else if (nd_[e].tree) split(e, nt, j, ocap);
+            else {   // lo/hi split keeps the relative order
+                int loHead = -1, loTail = -1, hiHead = -1, hiTail = -1;
+                for (int q = e, next; q >= 0; q = next) {
+                    next = nd_[q].next; nd_[q].next = -1;
+                    if (((uint32_t)nd_[q].hash & ocap) == 0) { if (loTail < 0) loHead = q; else nd_[loTail].next = q; loTail = q; }
+                    else { if (hiTail < 0) hiHead = q; else nd_[hiTail].next = q; hiTail = q; }
+                }
+                nt[j] = loHead; nt[j + ocap] = hiHead;
+            }
+        }
+        tab_.swap(nt);
         threshold_ *= 2;
     }
+    bool checkTree(int t, int blacks, int *bh, size_t *cnt) const {
+        if (t < 0) { if (*bh < 0) *bh = blacks; return *bh == blacks; }
+        const Node &n = nd_[t];
+        ++*cnt;
+        if (n.red && (isRed(n.left) || isRed(n.right))) return false;
+        if (n.left >= 0 && (nd_[n.left].parent != t || dirOf(n.left, t) > 0)) return false;
+        if (n.right >= 0 && (nd_[n.right].parent != t || dirOf(n.right, t) <= 0)) return false;
+        const int b2 = blacks + (n.red ? 0 : 1);
+        return checkTree(n.left, b2, bh, cnt) && checkTree(n.right, b2, bh, cnt);
+    }
     std::vector<std::string> keys_;
-    std::vector<uint32_t> hash_;
-    std::vector<char> alive_;
+    std::vector<Node> nd_;
     std::unordered_map<std::string, int> index_;
-    std::vector<std::vector<int>> table_;
+    std::vector<int> tab_;
     size_t size_ = 0, threshold_ = 0;
 };
 

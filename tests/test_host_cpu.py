@@ -38,33 +38,108 @@ def test_hashmap_order_matches_oracle_and_rep50(rep50, oracle):
         n = int(rng.integers(1, 5000))
         keys = ["%d.%d" % (rng.integers(1, 3000000), rng.integers(1, 400)) for _ in range(n)]
         keys += keys[: n // 10]                            # re-put of existing keys keeps their position
-        try:
-            want = list(oracle.java_hashmap_order(keys))
-        except ValueError:
-            p = run(["order"], "\n".join(keys) + "\n", check=False)
-            assert p.returncode == 1 and "tree bin" in p.stderr.decode()
-            continue
+        want = list(oracle.java_hashmap_order(keys))
         got = [int(x) for x in run(["order"], "\n".join(keys) + "\n").stdout.split()]
         assert got == want
         assert got == ko.py_java_hashmap_order(keys)
 
 
-def test_hashmap_tree_bin_is_refused_not_mis_ordered(oracle):
-    # 16 keys with the same String.hashCode ("Aa" and "BB" hash alike): the 11th lands in a full bin of a 64-slot
-    # table, where java.util.HashMap builds a tree; both emulations must refuse rather than guess an order
+def order_check(script, every=False):
+    out = run(["order-remove"] + (["every"] if every else []), "\n".join(script) + "\n").stdout.decode().split("\n")
+    tail = dict(kv.split("=") for kv in out[-2].split())
+    return [int(x) for x in out[:-2]], int(tail["inv"]), int(tail["treebins"])
+
+
+def colliding_ids(nbits, groups, per_group, seed):
+    """genome-id-like keys whose spread hashes agree in their low `nbits` bits: they share a bin until the table
+    outgrows 2**nbits slots"""
+    rng = np.random.default_rng(seed)
+    by_low, out = {}, []
+    while len(out) < groups:
+        k = "%d.%d" % (rng.integers(1, 4000000), rng.integers(1, 500))
+        low = ko.JavaHashMap.spread(k) & ((1 << nbits) - 1)
+        g = by_low.setdefault(low, [])
+        if k not in g:
+            g.append(k)
+            if len(g) == per_group:
+                out.append(g)
+    return out
+
+
+def test_hashmap_tree_bins_same_hash_keys(oracle):
+    # 32 keys with ONE String.hashCode ("Aa" and "BB" hash alike): the 9th to arrive at a 64-slot table turns the
+    # bin into a red-black tree ordered by String.compareTo; the C++ host emulation and the oracle's Python
+    # restatement of OpenJDK's HashMap must agree on the iteration order at every size
     import itertools
-    keys = ["".join(p) for p in itertools.product(("Aa", "BB"), repeat=4)]
+    keys = ["".join(p) for p in itertools.product(("Aa", "BB"), repeat=5)]
     assert len({ko.java_string_hash(k) for k in keys}) == 1
-    with pytest.raises(ValueError):
-        oracle.java_hashmap_order(keys)
-    p = run(["order"], "\n".join(keys) + "\n", check=False)
-    assert p.returncode == 1 and "tree bin" in p.stderr.decode()
+    rng = np.random.default_rng(5)
+    for trial in range(8):
+        ks = [keys[i] for i in rng.permutation(len(keys))]
+        fill = ["f%d" % i for i in range(int(rng.integers(0, 300)))]
+        seq = [k for pair in itertools.zip_longest(ks, fill) for k in pair if k is not None]
+        for n in (9, 11, 12, 13, 20, len(seq)):
+            got, inv, bins = order_check(seq[:n], every=True)
+            assert inv == 1
+            assert got == ko.py_java_hashmap_order(seq[:n])
+            assert got == list(oracle.java_hashmap_order(seq[:n]))
+        assert bins == 1
+    # the order is NOT insertion order inside the bin (the tree root moves to the front)
+    got, _, _ = order_check(keys[:12])
+    chain = [i for i in got if i < 12]
+    assert sorted(chain) == list(range(12)) and chain != list(range(12))
+
+
+def test_hashmap_tree_bins_split_and_untreeify():
+    # genome-id keys sharing the low 10 bits of their spread hash: trees form at 64..1024 slots, then every further
+    # doubling splits them (TreeNode.split), re-treeifying halves of > 6 nodes and flattening the smaller ones
+    groups = colliding_ids(10, 12, 40, seed=77)
+    rng = np.random.default_rng(78)
+    filler = ["%d.%d" % (rng.integers(1, 4000000), rng.integers(1, 500)) for _ in range(7000)]
+    seq, gi = [], [0] * len(groups)
+    for i, f in enumerate(filler):
+        seq.append(f)
+        g = i % len(groups)
+        if i % 3 == 0 and gi[g] < 40:
+            seq.append(groups[g][gi[g]])
+            gi[g] += 1
+    seen_trees = 0
+    for n in (100, 300, 700, 900, 1500, 1700, 3200, 6500, len(seq)):
+        got, inv, bins = order_check(seq[:n])
+        assert inv == 1
+        assert got == ko.py_java_hashmap_order(seq[:n])
+        seen_trees = max(seen_trees, bins)
+    assert seen_trees >= 6
+
+
+def test_hashmap_tree_bins_removal():
+    # Iterator.remove() ('-', UpdateProcessor.java:96-103: no re-rooting, no untreeify) and Map.remove ('~') on
+    # tree bins, interleaved with more puts
+    groups = colliding_ids(12, 6, 30, seed=91)
+    rng = np.random.default_rng(92)
+    script, removals, live, keys = [], {}, [], []
+    pool = [k for g in groups for k in g] + ["%d.%d" % (rng.integers(1, 4000000), rng.integers(1, 500)) for _ in range(400)]
+    pool = [pool[i] for i in rng.permutation(len(pool))]
+    for k in dict.fromkeys(pool):
+        keys.append(k)
+        script.append(k)
+        live.append(k)
+        if len(live) > 40 and rng.random() < 0.35:
+            victim = live.pop(int(rng.integers(0, len(live))))
+            movable = bool(rng.random() < 0.5)
+            script.append(("~" if movable else "-") + victim)
+            removals.setdefault(len(keys) - 1, []).append((victim, movable))
+    got, inv, bins = order_check(script, every=True)
+    assert inv == 1
+    assert got == ko.py_java_hashmap_order(keys, removals=removals)
+    assert sorted(keys[i] for i in got) == sorted(live)
 
 
 def test_hashmap_remove_keeps_order():
     keys = ["k%d" % i for i in range(200)]
     script = keys + ["-k%d" % i for i in range(0, 200, 3)]
-    got = [int(x) for x in run(["order-remove"], "\n".join(script) + "\n").stdout.split()]
+    got, inv, _ = order_check(script)
+    assert inv == 1
     full = ko.py_java_hashmap_order(keys)
     assert got == [i for i in full if i % 3 != 0]
 
