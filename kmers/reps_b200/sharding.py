@@ -130,3 +130,63 @@ def encode_sharded(ctx, d_res, off, dist):
     full = ctx.import_blocklists(shards, d_res.data_ptr(), off)
     full._keep = (recv, local)   # released with the set: by then the import's copies have long completed
     return full
+
+
+# ---- greedy representative-set build with the candidate-vs-database scoring split over the ranks ------------
+def greedy_build_sharded(n_cands: int, threshold: int, batch: int, dist, score_slice, survivor_matrix, accept, device=None):
+    """RepGenomeDb.checkGenome over `n_cands` candidates in order (RepGenomeDbProcessor.java:160-163,
+    BaseGenomeProcessor.java:203-204), every rank holding a replica of the database.
+
+    Per batch of `batch` candidates: each rank scores its shard_range of the batch against its replica, the best
+    similarities are all-gathered (4 B per candidate), and every rank then runs the same deterministic in-order
+    sweep over the survivors (candidates no current representative covers), so the replicas stay identical without
+    a broadcast.  The sweep's accept/reject chain is sequential by nature: only the scoring scales with the ranks.
+
+        score_slice(lo, hi)      -> int array: best similarity of candidates [lo, hi) to the current database
+        survivor_matrix(idx)     -> (len(idx) x len(idx)) similarities among candidates idx (ascending)
+        accept(idx)              -> append candidates idx to this rank's replica
+        device                   -> where the exchanged tensor lives (a CUDA device for NCCL; None = CPU for gloo)
+    Returns the uint8 `added` flags, identical on every rank."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    added = np.zeros(n_cands, dtype=np.uint8)
+    db_size = 0
+    for pos in range(0, n_cands, batch):
+        n = min(batch, n_cands - pos)
+        if db_size:
+            lo, hi = shard_range(n, rank, world)
+            mine = np.asarray(score_slice(pos + lo, pos + hi), dtype=np.int32).reshape(hi - lo)
+            t = torch.from_numpy(mine)
+            best = allgather_ranges(t if device is None else t.to(device), n, dist).cpu().numpy()
+            surv = pos + np.nonzero(best < threshold)[0]
+        else:
+            surv = pos + np.arange(n)
+        if len(surv) == 0:
+            continue
+        acc = []
+        if len(surv) == 1:
+            acc = [0]
+        else:
+            m = np.asarray(survivor_matrix(surv))
+            for s in range(len(surv)):                       # checkGenome, in candidate order
+                if not acc or not (m[s, acc] >= threshold).any():
+                    acc.append(s)
+        idx = surv[np.asarray(acc, dtype=np.int64)]
+        added[idx] = 1
+        accept(idx.astype(np.uint32))
+        db_size += len(idx)
+    return added
+
+
+def greedy_build_gpu(ctx, db, cands, threshold: int, dist, batch: int = 4096, device=None):
+    """greedy_build_sharded on this rank's GPU: `db` is this rank's replica (kr_db), `cands` the encoded candidates
+    (the same set on every rank)."""
+    def score_slice(lo, hi):
+        if hi <= lo:
+            return np.zeros(0, np.int32)
+        return db.find_closest(cands.gather(np.arange(lo, hi, dtype=np.uint32)))[0]
+
+    def survivor_matrix(idx):
+        return ctx.sim_matrix(cands.gather(idx.astype(np.uint32)), elem=kr.ELEM_U16)
+
+    return greedy_build_sharded(cands.count, threshold, batch, dist, score_slice, survivor_matrix, lambda idx: db.append_set(cands, idx), device=device)

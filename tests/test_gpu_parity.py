@@ -383,3 +383,27 @@ def test_greedy_build_properties_at_scale():
     best, first, _ = db.find_closest(cands.gather(rej))
     assert (best >= thr).all()                                                     # (b)
     c.close()
+
+
+def test_greedy_build_sharded_driver_on_one_gpu(oracle):
+    """sharding.greedy_build_gpu (the N>1 build: scoring split by rank, identical in-order sweep on every replica)
+    with a one-rank gloo group: every GPU call it makes, against kr_greedy_build and the oracle"""
+    import torch.distributed as dist
+    from kmers.reps_b200 import sharding, synth
+    res, off, _ = synth.generate(0x5EED0007, 3000, 40)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    cands = c.encode(res=res, off=off)
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29671", rank=0, world_size=1)
+    try:
+        db = c.db()
+        added = sharding.greedy_build_gpu(c, db, cands, 50, dist, batch=512)
+    finally:
+        if own:
+            dist.destroy_process_group()
+    db2 = c.db()
+    assert (added == db2.greedy_build(cands, 50)).all() and db.size == db2.size == int(added.sum())
+    _, want, _ = oracle.greedy_build(oracle.batch(res=res, off=off, K=8), 50, ident_inf=True)
+    assert (added == want).all()
+    c.close()

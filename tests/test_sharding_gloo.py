@@ -52,6 +52,26 @@ def _worker(rank, world, port, n, q):
             wq = o.batch(res=res[int(off[nrep]):], off=off[nrep:] - off[nrep], K=8)
             ws, wi = o.find_closest(reps, wq)
             assert (allq[:, 0] == ws).all() and (allq[:, 1] == wi).all()
+        # greedy build: replicas of the database on every rank, scoring of each candidate batch split by rank
+        class Replica:                                   # the oracle stands in for this rank's GPU replica
+            def __init__(self):
+                self.idx = []
+        rep = Replica()
+        seqs = synth.to_strings(res, off)
+
+        def score_slice(lo, hi):
+            if hi <= lo:
+                return np.zeros(0, np.int32)
+            return o.find_closest(o.batch([seqs[i] for i in rep.idx], K=8), o.batch(seqs[lo:hi], K=8))[0]
+
+        def survivor_matrix(idx):
+            return o.sim_matrix(o.batch([seqs[i] for i in idx], K=8), ident_inf=True)
+
+        for batch in (64, 257):
+            rep.idx = []
+            added = sharding.greedy_build_sharded(n, 50, batch, dist, score_slice, survivor_matrix, lambda idx: rep.idx.extend(int(i) for i in idx))
+            _, want, _ = o.greedy_build(b, 50, ident_inf=True)
+            assert (added == want).all() and rep.idx == list(np.nonzero(want)[0])
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, "FAIL %r" % (e,)))
