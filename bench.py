@@ -276,6 +276,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sparse-e2e", action="store_true",
+                    help="EXPERIMENTAL library only (KR_LIB_PATH=.../libkmersreps_cuda_exp.so): also time the e2e path that returns only "
+                         "the cells with sim >= 1 (kr_sim_matrix_sparse) and report it as e2e_sparse")
     ap.add_argument("--elem", default="u16", choices=["u16", "i32"])
     ap.add_argument("--replicated-encode", action="store_true", help="N>1: every rank encodes all sequences (no block-list all-gather)")
     ap.add_argument("--gather-matrix", action="store_true",
@@ -305,7 +308,7 @@ def main():
     elem = kr.ELEM_U16 if args.elem == "u16" else kr.ELEM_I32
     esz = 2 if elem == kr.ELEM_U16 else 4
     layout = kr.LAYOUT_BLOCKTRI
-    from kmers.reps_b200 import sharding
+    from kmers.reps_b200 import binding, sharding
     r0, r1, my_elems, _ = sharding.my_stripe(N, layout, rank, world)
     d_res = torch.from_numpy(res).cuda()
     d_out = torch.empty(my_elems * esz + 16, dtype=torch.uint8, device="cuda")
@@ -455,6 +458,28 @@ def main():
                "d2h_bytes_per_step": int(my_elems * esz), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
                "api": "kr_encode + kr_sim_matrix (pinned host buffers)"}
 
+    e2e_sparse = None
+    if args.sparse_e2e and binding.has_experimental():
+        cap = 1 << 24
+        h_cells = ctx.host_alloc(cap * 16, dtype=np.uint32).reshape(cap, 4)
+        h_res = ctx.host_alloc(max(len(res), 1))
+        h_res[: len(res)] = res
+        ncell = [0]
+        def sparse_step():
+            s = ctx.encode(res=h_res[: len(res)], off=off)
+            ncell[0] = len(ctx.sim_matrix_sparse(s, None, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1, out=h_cells))
+            s.free()
+        sparse_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            sparse_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_sparse = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "ms_per_step": 1000 * dt / args.e2e_steps,
+                      "cells_per_step": ncell[0], "d2h_bytes_per_step": 8 + 16 * ncell[0],
+                      "api": "kr_encode + kr_sim_matrix_sparse (experimental build): only cells with sim >= 1 cross PCIe"}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
@@ -472,7 +497,7 @@ def main():
                                    ("each rank encodes 1/%d of the sequences, block lists all-gathered (NCCL)" % world if sharded_encode
                                     else "keys replicated, no data-path collective"),
                        "cache": "inputs+outputs larger than L2 (key lists %d MB, result %d MB per rank)" % (ssum * 8 >> 20, my_elems * esz >> 20)},
-            "roofline": roofline, "roofline_design": design, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "roofline_design": design, "cpu_baseline": cpu, "e2e": e2e, "e2e_sparse": e2e_sparse,
             "gpu_launches": int(st["kernel_launches"]), "clocks": clocks,
             "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
             "verified": "400 sampled cells per rank equal the oracle",

@@ -126,8 +126,15 @@ def load_library():
     lib.kr_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.kr_host_free.argtypes = [vp, vp]
     lib.kr_host_free.restype = None
+    # experimental entry points exist only in builds made with -DKR_EXPERIMENTAL (never the default library)
+    if hasattr(lib, "kr_sim_matrix_sparse"):
+        lib.kr_sim_matrix_sparse.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
     _LIB = lib
     return lib
+
+
+def has_experimental() -> bool:
+    return hasattr(load_library(), "kr_sim_matrix_sparse")
 
 
 def flat(seqs):
@@ -252,6 +259,20 @@ class Context:
         if layout == LAYOUT_FULL:
             return out.reshape(row_end - row_begin, n_cols)
         return out
+
+    def sim_matrix_sparse(self, A: "SeqSet", B: "SeqSet" = None, min_sim=1, layout=LAYOUT_TRIANGLE, row_begin=0, row_end=None, cap=1 << 22, out=None):
+        """EXPERIMENTAL build only: cells (row, col, sim) with sim >= min_sim, unordered, as an (n, 4) uint32 array"""
+        row_end = A.count if row_end is None else row_end
+        d = MatrixDesc(ELEM_I32, layout, row_begin, row_end)
+        while True:
+            cells = out if out is not None else np.zeros((cap, 4), dtype=np.uint32)
+            n = C.c_uint64(0)
+            rc = self.lib.kr_sim_matrix_sparse(self.h, A.h, None if B is None else B.h, C.byref(d), int(min_sim), cells.ctypes.data, len(cells), C.byref(n))
+            if rc == 0:
+                return cells[: n.value]
+            if n.value <= len(cells) or out is not None:
+                self._ck(rc)
+            cap = int(n.value)                     # the library reported how many cells qualify: retry with room
 
     def sim_matrix_device(self, A, B, d_out_ptr: int, elem=ELEM_U16, layout=LAYOUT_FULL, row_begin=0, row_end=None):
         row_end = A.count if row_end is None else row_end

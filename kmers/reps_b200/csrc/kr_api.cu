@@ -198,6 +198,10 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
     CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
     CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
+#ifdef KR_EXPERIMENTAL
+    CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
+    CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
+#endif
 #undef CUC
     *out = ctx;
     return KR_OK;
@@ -463,7 +467,10 @@ static u64 row_start(u32 layout, u64 r, u64 nrows, u64 ncols) {
     return 256ull * (I * nrows - 128ull * I * (I - 1)) + (r - c0) * (nrows - c0);
 }
 
-static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool self, const kr_matrix_desc *d, void *out_dev) {
+struct SparseSink { uint4 *cells; unsigned long long cap; unsigned long long *count; u32 min_sim; };
+
+static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool self, const kr_matrix_desc *d, void *out_dev,
+                               const SparseSink *sparse = nullptr) {
     kr_status st;
     if ((st = ensure_blocklists(ctx, A))) return st;
     if (!self && (st = ensure_blocklists(ctx, B))) return st;
@@ -497,11 +504,19 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
     {
         StageTimer t(ctx, ST_JOIN);
         u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
+#ifdef KR_EXPERIMENTAL
+        if (sparse) {
+            p.cells = sparse->cells; p.cells_cap = sparse->cap; p.cells_count = sparse->count; p.min_sim = sparse->min_sim;
+            if (lo_bits(ctx->K) <= 16) k_join<MODE_SPARSE, false><<<grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream>>>(p);
+            else k_join<MODE_SPARSE, true><<<grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream>>>(p);
+        } else
+#endif
         if (lo_bits(ctx->K) <= 16) k_join<MODE_MATRIX, false><<<grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream>>>(p);
         else k_join<MODE_MATRIX, true><<<grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream>>>(p);
         LAUNCHED(ctx); ctx->st.join_launches++;
         CU(cudaGetLastError());
     }
+    (void)sparse;
     u64 rows = d->row_end - d->row_begin;
     if (d->layout == KR_LAYOUT_FULL) ctx->st.pairs += rows * (u64)Bs->n;
     else ctx->st.pairs += kr_matrix_elems(A->n, A->n, KR_LAYOUT_TRIANGLE, d->row_begin, d->row_end);
@@ -1016,6 +1031,44 @@ kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, con
     dfree(ctx, d_buf[0]); dfree(ctx, d_buf[1]);
     return st;
 }
+
+#ifdef KR_EXPERIMENTAL
+// EXPERIMENTAL (not in include/kmersreps.h, not in the default build; unverified on hardware): the similarity matrix
+// as a list of its cells with sim >= min_sim -- (row, col, sim, 0) as four uint32, in no particular order.  Layout
+// FULL: every column; TRIANGLE (self only): columns j > i.  *count receives the number of qualifying cells even
+// when it exceeds `cap` (then only `cap` cells are returned and the status is KR_ERR_ARG: call again with room).
+kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                               uint32_t *cells_host, uint64_t cap, uint64_t *count) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    kr_status st = check_desc(ctx, A, B, desc);
+    if (st) return st;
+    if (!count || (!cells_host && cap) || min_sim < 1 || desc->layout == KR_LAYOUT_BLOCKTRI)
+        return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: bad argument (min_sim >= 1; layout FULL or TRIANGLE)");
+    CU(cudaSetDevice(ctx->dev));
+    *count = 0;
+    const bool self = (B == nullptr || B == A);
+    uint4 *d_cells = nullptr; unsigned long long *d_count = nullptr;
+    CU(dalloc(ctx, &d_cells, cap)); CU(dalloc(ctx, &d_count, 1));
+    CU(cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+    SparseSink sink{d_cells, cap, d_count, (u32)min_sim};
+    st = matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, d_cells, &sink);
+    unsigned long long n = 0;
+    if (st == KR_OK) {
+        cudaError_t e = cudaMemcpyAsync(&n, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        const unsigned long long take = std::min<unsigned long long>(n, cap);
+        if (e == cudaSuccess && take) e = cudaMemcpyAsync(cells_host, d_cells, take * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "sparse matrix copy to host failed: %s", cudaGetErrorString(e));
+        ctx->st.d2h_bytes += 8 + take * 16;
+        *count = n;
+        if (st == KR_OK && n > cap) st = fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: %llu cells qualify, room for %llu", n, (unsigned long long)cap);
+    }
+    dfree(ctx, d_cells); dfree(ctx, d_count);
+    return st;
+}
+#endif
 
 // ---- database ----------------------------------------------------------------------------------
 kr_status kr_db_create(kr_ctx *ctx, kr_db **out) {

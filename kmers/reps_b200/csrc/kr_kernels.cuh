@@ -397,7 +397,7 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 
 // ---------------------------------------------------------------------------------------------
 // K3: the tile join.
-enum { MODE_MATRIX = 0, MODE_ARGMAX = 1 };
+enum { MODE_MATRIX = 0, MODE_ARGMAX = 1, MODE_SPARSE = 2 };
 
 struct JoinParams {
     const BlockRef *A, *B;
@@ -410,6 +410,10 @@ struct JoinParams {
     void *out; u32 elem, layout; u64 origin;
     // ARGMAX
     u32 nsplit; const u32 *rankB; int4 *partial;
+#ifdef KR_EXPERIMENTAL
+    // SPARSE: cells (row, col, sim, 0) with sim >= min_sim, appended in no particular order
+    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count; u32 min_sim;
+#endif
 };
 
 __device__ __forceinline__ u64 cell_index(u32 layout, u64 i, u64 j, u64 nrows, u64 ncols) {
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
         for (u32 task = blockIdx.x; task < p.ntasks; task += gridDim.x) {
             const uint2 tk = p.tasks[task];
             u32 j0, j1;
-            if (MODE == MODE_MATRIX) { j0 = tk.y; j1 = tk.y + 1; }
+            if (MODE != MODE_ARGMAX) { j0 = tk.y; j1 = tk.y + 1; }
             else { j0 = (u32)((u64)tk.y * p.nBblk / p.nsplit); j1 = (u32)((u64)(tk.y + 1) * p.nBblk / p.nsplit); }
             a = p.A[tk.x];
             // chunk tables live in registers (lane c%32 holds chunk c) and are broadcast by shuffle
@@ -693,7 +697,33 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
                         }
                     }
                 }
-            } else {
+            }
+#ifdef KR_EXPERIMENTAL
+            else if (MODE == MODE_SPARSE) {
+                // only the cells that reach min_sim leave the SM: one atomicAdd per (row, tile) that has any
+                u32 jlo = b.seq0;
+                const u32 jhi = b.seq0 + b.nseq;
+                if (p.layout == 1 && jlo < i + 1) jlo = i + 1;
+                u32 m = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) if (jb + t >= jlo && jb + t < jhi && cv[t] >= (int)p.min_sim) m |= 1u << t;
+                if (__any_sync(0xffffffffu, m != 0)) {
+                    const u32 c = __popc(m);
+                    u32 incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += up; }
+                    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+                    unsigned long long base = 0;
+                    if (lane == 31) base = atomicAdd(p.cells_count, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    unsigned long long pos = base + incl - c;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if ((m >> t) & 1u) { if (pos < p.cells_cap) p.cells[pos] = make_uint4(i, jb + t, (u32)cv[t], 0u); ++pos; }
+                }
+            }
+#endif
+            else {
                 // row maximum with first/last rank among the maxima
                 int m = 0;
 #pragma unroll

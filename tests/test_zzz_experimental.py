@@ -1,0 +1,44 @@
+"""GPU tests of EXPERIMENTAL entry points.  They exist only in a library built with -DKR_EXPERIMENTAL
+(kmers/reps_b200/libkmersreps_cuda_exp.so, never the default library) and were written while GPU access was closed,
+so they are skipped unless KR_LIB_PATH points at such a build:
+
+    KR_LIB_PATH=$PWD/kmers/reps_b200/libkmersreps_cuda_exp.so python -m pytest tests -m gpu -q
+"""
+import numpy as np
+import pytest
+
+import kmers.reps_b200 as kr
+from kmers.reps_b200 import binding, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not binding.has_experimental(), reason="default library: no experimental entry points")]
+
+
+def cells_of(dense, min_sim, triangle):
+    n, m = dense.shape
+    out = set()
+    ii, jj = np.nonzero(dense >= min_sim)
+    for i, j in zip(ii, jj):
+        if not triangle or j > i:
+            out.add((int(i), int(j), int(dense[i, j])))
+    return out
+
+
+@pytest.mark.parametrize("n,nfam", [(700, 12), (1500, 300)])
+def test_sparse_matrix_equals_dense(oracle, n, nfam):
+    res, off, _ = synth.generate(0x5EED0008, n, nfam)
+    want = oracle.sim_matrix(oracle.batch(res=res, off=off, K=8), ident_inf=True, threads=4)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    s = c.encode(res=res, off=off)
+    for min_sim in (1, 50, 9999):
+        got = c.sim_matrix_sparse(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
+        cells = {(int(r), int(cc), int(v)) for r, cc, v, _ in got}
+        assert len(cells) == len(got)                                   # no cell twice
+        assert cells == cells_of(want, min_sim, True)
+    # too little room: the count comes back, the binding retries with enough
+    got = c.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, cap=16)
+    assert {(int(r), int(cc), int(v)) for r, cc, v, _ in got} == cells_of(want, 1, True)
+    # rectangular, FULL layout, a row stripe
+    q = c.encode(res=res[: int(off[300])], off=off[:301])
+    got = c.sim_matrix_sparse(q, s, min_sim=20, layout=kr.LAYOUT_FULL, row_begin=256, row_end=300)
+    assert {(int(r), int(cc), int(v)) for r, cc, v, _ in got} == {t for t in cells_of(want[:300], 20, False) if t[0] >= 256}
+    c.close()
