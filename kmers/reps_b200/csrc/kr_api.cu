@@ -3,6 +3,11 @@
 // that produces a similarity launches a kernel on the context's GPU.
 #include "../../../include/kmersreps.h"
 #include "kr_kernels.cuh"
+#ifdef KR_EXPERIMENTAL
+#include "kr_pairs.cuh"
+#define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
+#define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -63,6 +68,12 @@ struct kr_seqset {
     u32 *d_hi = nullptr; void *d_lo = nullptr; u32 *d_choff = nullptr, *d_chcnt = nullptr; u64 *d_blkbase = nullptr;
     BlockRef *d_refs = nullptr;
     std::vector<std::shared_ptr<DevMem>> keep;   // parents' residue buffers
+#ifdef KR_EXPERIMENTAL
+    // posting lists of the whole set (experimental all-vs-all path), built on first use
+    bool px_ready = false; u64 px_slots = 0;
+    unsigned long long *px_key = nullptr; u32 *px_off = nullptr, *px_cnt = nullptr, *px_post = nullptr;
+    unsigned long long px_work = ~0ull;   // sum of m(m-1)/2, once known
+#endif
 };
 
 struct DbSegment { kr_seqset *set; u32 base; };
@@ -306,6 +317,9 @@ static void seqset_destroy(kr_seqset *s) {
     cudaSetDevice(ctx->dev);
     dfree(ctx, s->d_off); dfree(ctx, s->d_koff); dfree(ctx, s->d_keys); dfree(ctx, s->d_meta);
     dfree(ctx, s->d_hi); dfree(ctx, (u8 *)s->d_lo); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
+#ifdef KR_EXPERIMENTAL
+    dfree(ctx, s->px_key); dfree(ctx, s->px_off); dfree(ctx, s->px_cnt); dfree(ctx, s->px_post);
+#endif
     delete s;   // residue buffers are released stream-ordered by ~DevMem
 }
 
@@ -469,9 +483,95 @@ static u64 row_start(u32 layout, u64 r, u64 nrows, u64 ncols) {
 
 struct SparseSink { uint4 *cells; unsigned long long cap; unsigned long long *count; u32 min_sim; };
 
+#ifdef KR_EXPERIMENTAL
+// EXPERIMENTAL: posting lists of a whole set, with the index kernels of the findClosest path (one table, no slabs)
+static kr_status ensure_postings(kr_ctx *ctx, kr_seqset *s) {
+    if (s->px_ready) return KR_OK;
+    const u64 entries = s->key_cap;   // upper bound of the distinct (key, sequence) entries: no host sync needed
+    u64 cap = 1024; while (cap < 2 * entries) cap <<= 1;
+    if (cap > (1ull << 31)) return fail(ctx, KR_ERR_ARG, "posting-list path: set too large (%llu k-mers)", (unsigned long long)entries);
+    u32 *d_cur = nullptr, *d_sums = nullptr;
+    const u32 ntile = (u32)((cap + SCAN_TILE - 1) / SCAN_TILE), mask = (u32)(cap - 1);
+    CU(dalloc(ctx, &s->px_key, cap)); CU(dalloc(ctx, &s->px_off, cap)); CU(dalloc(ctx, &s->px_cnt, cap));
+    CU(dalloc(ctx, &s->px_post, entries + 1)); CU(dalloc(ctx, &d_cur, cap)); CU(dalloc(ctx, &d_sums, ntile));
+    CU(cudaMemsetAsync(s->px_key, 0xFF, cap * 8, ctx->stream));
+    CU(cudaMemsetAsync(s->px_cnt, 0, cap * 4, ctx->stream));
+    CU(cudaMemsetAsync(d_cur, 0, cap * 4, ctx->stream));
+    if (s->n) {
+        StageTimer t(ctx, ST_BLOCKLIST);
+        k_idx_insert<<<s->n, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, s->px_key, s->px_cnt, mask);
+        k_scan_tile_sums<<<ntile, 256, 0, ctx->stream>>>(s->px_cnt, cap, d_sums);
+        k_scan_sums<<<1, 1024, 0, ctx->stream>>>(d_sums, ntile);
+        k_scan_tiles<<<ntile, 256, 0, ctx->stream>>>(s->px_cnt, cap, d_sums, s->px_off);
+        k_idx_fill<<<s->n, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, 0, s->px_key, s->px_off, d_cur, mask, s->px_post);
+        ctx->st.kernel_launches += 5;
+        CU(cudaGetLastError());
+    }
+    dfree(ctx, d_cur); dfree(ctx, d_sums);
+    s->px_slots = cap; s->px_ready = true;
+    return KR_OK;
+}
+
+// EXPERIMENTAL: rows [row_begin, row_end) of the self matrix of A from its posting lists (kr_pairs.cuh).
+// Returns KR_OK with *done = false when this path declines (AUTO mode and the join is estimated cheaper).
+static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d, void *out_dev, bool *done) {
+    *done = false;
+    kr_status st = ensure_postings(ctx, A);
+    if (st) return st;
+    if (ctx->flags & KR_EXP_PAIRS_AUTO) {
+        if (A->px_work == ~0ull) {
+            unsigned long long *d_work = nullptr;
+            CU(dalloc(ctx, &d_work, 1));
+            CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));
+            k_pairs_work<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A->px_cnt, A->px_slots, d_work);
+            LAUNCHED(ctx);
+            CU(cudaMemcpyAsync(&A->px_work, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            dfree(ctx, d_work);
+        }
+        // the join searches every entry of block I in block J for every tile: ~ tiles x 256 x mean set size probes of 11
+        // steps; one pair increment here costs about one such search.  Decline when the lists are the heavier side.
+        const u64 nblk = (A->n + TB - 1) / TB;
+        const double join_searches = (double)nblk * (nblk + 1) / 2 * ((double)A->key_cap / std::max<u64>(nblk, 1));
+        if ((double)A->px_work > join_searches) return KR_OK;
+    }
+    PairsParams p{};
+    p.tab_cnt = A->px_cnt; p.tab_off = A->px_off; p.postings = A->px_post; p.nslots = A->px_slots;
+    p.out = out_dev; p.elem = d->elem; p.layout = d->layout; p.N = A->n; p.row_begin = d->row_begin; p.row_end = d->row_end; p.flags = ctx->flags & 1u;
+    p.origin = row_start(d->layout, d->row_begin, A->n, A->n);
+    p.total = row_start(d->layout, d->row_end, A->n, A->n) - p.origin;
+    p.meta = A->d_meta;
+    u32 hm = 1024; while (hm < 2 * A->n) hm <<= 1;
+    CU(dalloc(ctx, &p.head, hm)); CU(dalloc(ctx, &p.next, A->n));
+    p.head_mask = hm - 1;
+    const size_t esz = d->elem == KR_ELEM_U16 ? 2 : 4;
+    CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
+    {
+        StageTimer t(ctx, ST_JOIN);
+        CU(cudaMemsetAsync(out_dev, 0, p.total * esz, ctx->stream));
+        k_pairs_emit<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p);
+        k_pairs_dup_insert<<<(A->n + 255) / 256, 256, 0, ctx->stream>>>(p);
+        k_pairs_dup_fix<<<(A->n + 255) / 256, 256, 0, ctx->stream>>>(p);
+        ctx->st.kernel_launches += 3; ctx->st.join_launches++;
+        CU(cudaGetLastError());
+    }
+    dfree(ctx, p.head); dfree(ctx, p.next);
+    ctx->st.pairs += kr_matrix_elems(A->n, A->n, KR_LAYOUT_TRIANGLE, d->row_begin, d->row_end);
+    *done = true;
+    return KR_OK;
+}
+#endif
+
 static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool self, const kr_matrix_desc *d, void *out_dev,
                                const SparseSink *sparse = nullptr) {
     kr_status st;
+#ifdef KR_EXPERIMENTAL
+    if (self && !sparse && (ctx->flags & (KR_EXP_PAIRS | KR_EXP_PAIRS_AUTO)) && A->d_keys && A->n && d->row_end > d->row_begin
+        && (reinterpret_cast<uintptr_t>(out_dev) & 3) == 0) {
+        bool done = false;
+        if ((st = pairs_launch(ctx, A, d, out_dev, &done)) || done) return st;
+    }
+#endif
     if ((st = ensure_blocklists(ctx, A))) return st;
     if (!self && (st = ensure_blocklists(ctx, B))) return st;
     kr_seqset *Bs = self ? A : B;

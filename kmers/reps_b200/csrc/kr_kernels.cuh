@@ -15,12 +15,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kr_types.cuh"
+
 namespace kr {
 
-typedef uint64_t u64;
-typedef uint32_t u32;
-typedef uint16_t u16;
-typedef uint8_t u8;
 
 constexpr int TB = 256;          // sequences per block (KR_TILE); lid fits LID_BITS
 constexpr int LID_BITS = 8;
@@ -64,7 +62,6 @@ constexpr int NGROUP = KR_NGROUP;  // consumer warp groups; the jobs of a tile a
 constexpr int GW = NCWARP / NGROUP;
 static_assert(NCWARP % NGROUP == 0, "consumer warps must split evenly into groups");
 constexpr u64 SENT = ~0ull;
-constexpr int KR_INF = 9999;
 constexpr int LUT_BITS = 15;     // chunk table is indexed by the first three residues of the key
 
 constexpr size_t JOIN_SMEM_CNT = (size_t)TB * TB * 2;                         // u16 count tile
@@ -77,12 +74,6 @@ static_assert(JOIN_SMEM_BYTES <= 232448, "join kernel shared memory exceeds 227 
 // low bits of an entry kept in `lo`: the lid plus whatever of the key does not fit the 32-bit hi
 __host__ __device__ constexpr int lo_bits(int K) { return 5 * K + LID_BITS - 32 > LID_BITS ? 5 * K + LID_BITS - 32 : LID_BITS; }
 
-struct SeqMeta {   // one per sequence
-    u32 size;      // number of distinct k-mers (SequenceKmers.size())
-    u32 len;       // residues
-    u64 hash;      // 64-bit hash of the residues (pre-filter for the equal-sequence rule)
-    const u8 *res; // the residues themselves (exact check for the equal-sequence rule)
-};
 
 struct BlockRef {    // one per block of 256 sequences
     const u32 *hi;   // block list, high words (sorted; sentinel-padded between chunks and after the block)

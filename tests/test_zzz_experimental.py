@@ -42,3 +42,47 @@ def test_sparse_matrix_equals_dense(oracle, n, nfam):
     got = c.sim_matrix_sparse(q, s, min_sim=20, layout=kr.LAYOUT_FULL, row_begin=256, row_end=300)
     assert {(int(r), int(cc), int(v)) for r, cc, v, _ in got} == {t for t in cells_of(want[:300], 20, False) if t[0] >= 256}
     c.close()
+
+
+def blocktri(full):
+    n = full.shape[0]
+    return np.concatenate([full[i, 256 * (i // 256):] for i in range(n)])
+
+
+@pytest.mark.parametrize("flags", [binding.EXP_PAIRS, binding.EXP_PAIRS_AUTO])
+def test_posting_list_all_vs_all_equals_oracle(oracle, vapb, rep50, flags):
+    """the posting-list path (kr_pairs.cuh) must give the join's matrix bit for bit: every layout, element type,
+    row stripe, with and without the equal-sequence rule; VapbProt.fa holds 11 identical-sequence pairs"""
+    sets = [[s for (_, _, s) in vapb], [s for (_, _, s) in rep50["reps"][:700]]]
+    res, off, _ = synth.generate(0x5EED0009, 1300, 25)
+    sets.append(synth.to_strings(res, off))
+    for seqs in sets:
+        n = len(seqs)
+        ob = oracle.batch(seqs, K=8)
+        for ident in (kr.IDENT_IS_INFINITY, 0):
+            want = oracle.sim_matrix(ob, ident_inf=bool(ident), threads=4)
+            c = kr.Context(device=0, K=8, flags=ident | flags)
+            s = c.encode(seqs)
+            assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all()
+            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL) == want).all()
+            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE) == want[np.triu_indices(n, 1)]).all()
+            assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all()
+            if n > 256:
+                lo = c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=0, row_end=256)
+                hi = c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=256, row_end=n)
+                assert (np.concatenate([lo, hi]) == blocktri(want)).all()
+            c.close()
+
+
+def test_posting_list_path_in_greedy_build_and_short_sequences(oracle):
+    res, off, _ = synth.generate(0x5EED000A, 2500, 40)
+    seqs = synth.to_strings(res, off) + ["MKV", "", "MKVLAAGIVG", "MKVLAAGIVG", "MKV"]
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_PAIRS)
+    s = c.encode(seqs)
+    ob = oracle.batch(seqs, K=8)
+    assert (c.sim_matrix(s, elem=kr.ELEM_U16) == oracle.sim_matrix(ob, ident_inf=True, threads=4)).all()
+    db = c.db()
+    added = db.greedy_build(s, 50, batch=600)
+    _, want, _ = oracle.greedy_build(ob, 50, ident_inf=True)
+    assert (added == want).all()
+    c.close()
