@@ -512,6 +512,22 @@ static kr_status ensure_postings(kr_ctx *ctx, kr_seqset *s) {
     return KR_OK;
 }
 
+// sum over the posting lists of m(m-1)/2 (= pair increments = an upper bound of the pairs that share a k-mer);
+// synchronises the host once per set
+static kr_status postings_work(kr_ctx *ctx, kr_seqset *A) {
+    if (A->px_work != ~0ull) return KR_OK;
+    unsigned long long *d_work = nullptr, w = 0;
+    CU(dalloc(ctx, &d_work, 1));
+    CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));
+    k_pairs_work<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A->px_cnt, A->px_slots, d_work);
+    LAUNCHED(ctx);
+    CU(cudaMemcpyAsync(&w, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d_work);
+    A->px_work = w;
+    return KR_OK;
+}
+
 // EXPERIMENTAL: rows [row_begin, row_end) of the self matrix of A from its posting lists (kr_pairs.cuh).
 // Returns KR_OK with *done = false when this path declines (AUTO mode and the join is estimated cheaper).
 static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d, void *out_dev, bool *done) {
@@ -519,16 +535,7 @@ static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d
     kr_status st = ensure_postings(ctx, A);
     if (st) return st;
     if (ctx->flags & KR_EXP_PAIRS_AUTO) {
-        if (A->px_work == ~0ull) {
-            unsigned long long *d_work = nullptr;
-            CU(dalloc(ctx, &d_work, 1));
-            CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));
-            k_pairs_work<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A->px_cnt, A->px_slots, d_work);
-            LAUNCHED(ctx);
-            CU(cudaMemcpyAsync(&A->px_work, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            dfree(ctx, d_work);
-        }
+        if ((st = postings_work(ctx, A))) return st;
         // the join searches every entry of block I in block J for every tile: ~ tiles x 256 x mean set size probes of 11
         // steps; one pair increment here costs about one such search.  Decline when the lists are the heavier side.
         const u64 nblk = (A->n + TB - 1) / TB;
@@ -1151,8 +1158,44 @@ kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
     uint4 *d_cells = nullptr; unsigned long long *d_count = nullptr;
     CU(dalloc(ctx, &d_cells, cap)); CU(dalloc(ctx, &d_count, 1));
     CU(cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+    bool by_lists = false;
+    kr_seqset *As = const_cast<kr_seqset *>(A);
+    if (self && desc->layout == KR_LAYOUT_TRIANGLE && (ctx->flags & (KR_EXP_PAIRS | KR_EXP_PAIRS_AUTO)) && As->d_keys && As->n) {
+        // posting lists -> pair table -> cells: nothing proportional to N^2 is touched
+        if ((st = ensure_postings(ctx, As)) == KR_OK) st = postings_work(ctx, As);
+        // table capacity: every pair that shares a k-mer (<= work) plus the equal-sequence pairs that share none
+        // (sequences shorter than K: e of them give at most e(e-1)/2 such pairs)
+        u64 empties = 0;
+        if (st == KR_OK && (st = fetch_sizes(ctx, As)) == KR_OK) for (u32 v : As->h_sizes) empties += v == 0;
+        const u64 need = As->px_work + empties * (empties ? empties - 1 : 0) / 2;
+        u64 pcap = 1024; while (pcap < 2 * need && pcap <= (1ull << 29)) pcap <<= 1;
+        if (st == KR_OK && pcap <= (1ull << 29)) {   // <= 6 GB of pair table; beyond that the join's epilogue filter is the better tool
+            by_lists = true;
+            PairTabParams p{};
+            p.tab_cnt = As->px_cnt; p.tab_off = As->px_off; p.postings = As->px_post; p.nslots = As->px_slots;
+            p.pt_mask = pcap - 1; p.N = As->n; p.row_begin = desc->row_begin; p.row_end = desc->row_end; p.flags = ctx->flags & 1u; p.min_sim = (u32)min_sim;
+            p.meta = As->d_meta; p.cells = d_cells; p.cells_cap = cap; p.cells_count = d_count;
+            u32 hm = 1024; while (hm < 2 * As->n) hm <<= 1;
+            p.head_mask = hm - 1;
+            CU(dalloc(ctx, &p.pt_key, pcap)); CU(dalloc(ctx, &p.pt_cnt, pcap)); CU(dalloc(ctx, &p.head, hm)); CU(dalloc(ctx, &p.next, As->n));
+            CU(cudaMemsetAsync(p.pt_key, 0xFF, pcap * 8, ctx->stream));
+            CU(cudaMemsetAsync(p.pt_cnt, 0, pcap * 4, ctx->stream));
+            CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
+            {
+                StageTimer t(ctx, ST_JOIN);
+                k_pairs_emit_tab<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p);
+                k_pairs_dup_insert_tab<<<(As->n + 255) / 256, 256, 0, ctx->stream>>>(p);
+                k_pairs_dup_tab<<<(As->n + 255) / 256, 256, 0, ctx->stream>>>(p);
+                k_pairs_compact<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p);
+                ctx->st.kernel_launches += 4; ctx->st.join_launches++;
+                CU(cudaGetLastError());
+            }
+            dfree(ctx, p.pt_key); dfree(ctx, p.pt_cnt); dfree(ctx, p.head); dfree(ctx, p.next);
+            ctx->st.pairs += kr_matrix_elems(As->n, As->n, KR_LAYOUT_TRIANGLE, desc->row_begin, desc->row_end);
+        }
+    }
     SparseSink sink{d_cells, cap, d_count, (u32)min_sim};
-    st = matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, d_cells, &sink);
+    if (st == KR_OK && !by_lists) st = matrix_launch(ctx, As, const_cast<kr_seqset *>(B), self, desc, d_cells, &sink);
     unsigned long long n = 0;
     if (st == KR_OK) {
         cudaError_t e = cudaMemcpyAsync(&n, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);

@@ -151,4 +151,79 @@ KRP_GLOBAL void k_pairs_dup_fix(PairsParams p) {
         pairs_cell_set(p, pairs_cell_index(p.layout, i, i, p.N) - p.origin, (p.flags & 1u) ? (u32)KR_INF : mi.size);
 }
 
+// ---- sparse result: the pairs with similarity >= min_sim as (row, col, sim, 0) cells ------------------------------
+// Same posting lists, but the increments go to a hash table keyed by the pair (i < j, row i inside the stripe)
+// instead of a dense matrix, so nothing proportional to N^2 is ever written: the table holds one slot per pair that
+// shares a k-mer, and a last kernel copies the slots that reach min_sim into the cell list.
+constexpr unsigned long long PAIRTAB_EMPTY = ~0ull;
+
+struct PairTabParams {
+    const u32 *tab_cnt, *tab_off, *postings;
+    u64 nslots;
+    unsigned long long *pt_key; u32 *pt_cnt; u64 pt_mask;   // pair table: capacity pt_mask + 1 (a power of two)
+    u32 N, row_begin, row_end, flags, min_sim;
+    const SeqMeta *meta; u32 *head, *next; u32 head_mask;
+    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;
+};
+
+KRP_DEVICE u64 pairtab_hash(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+// slot of pair (i, j), claiming an empty one if the pair is new
+KRP_DEVICE u64 pairtab_slot(const PairTabParams &p, u32 i, u32 j) {
+    const unsigned long long k = ((unsigned long long)i << 32) | j;
+    u64 slot = pairtab_hash(k) & p.pt_mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(&p.pt_key[slot], PAIRTAB_EMPTY, k);
+        if (old == PAIRTAB_EMPTY || old == k) return slot;
+        slot = (slot + 1) & p.pt_mask;
+    }
+}
+
+KRP_GLOBAL void k_pairs_emit_tab(PairTabParams p) {
+    const u32 lane = threadIdx.x & 31;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 g = warp; g * 8 < p.nslots; g += nwarp) {
+        for (u32 k = 0; k < 8; ++k) {
+            const u64 slot = g * 8 + k;
+            if (slot >= p.nslots) break;
+            const u32 m = p.tab_cnt[slot];
+            if (m < 2) continue;
+            const u32 off = p.tab_off[slot];
+            const u64 P = (u64)m * (m - 1) / 2;
+            for (u64 t = lane; t < P; t += 32) {
+                const u32 b = pairs_tri_row(t), a = (u32)(t - (u64)b * (b - 1) / 2);
+                u32 i = p.postings[off + a], j = p.postings[off + b];
+                if (i > j) { const u32 x = i; i = j; j = x; }
+                if (i >= p.row_begin && i < p.row_end) atomicAdd(&p.pt_cnt[pairtab_slot(p, i, j)], 1u);
+            }
+        }
+    }
+}
+// equal sequences (after every increment has landed: a separate launch): their cell is INFINITY
+KRP_GLOBAL void k_pairs_dup_tab(PairTabParams p) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.N || i < p.row_begin || i >= p.row_end || !(p.flags & 1u)) return;
+    const SeqMeta mi = p.meta[i];
+    for (u32 j = p.head[pairs_head_slot(mi.hash, p.head_mask)]; j != PAIRS_NIL; j = p.next[j])
+        if (j > i && pairs_seq_equal(mi, p.meta[j])) p.pt_cnt[pairtab_slot(p, i, j)] = (u32)KR_INF;
+}
+KRP_GLOBAL void k_pairs_dup_insert_tab(PairTabParams p) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.N) return;
+    p.next[i] = atomicExch(&p.head[pairs_head_slot(p.meta[i].hash, p.head_mask)], i);
+}
+KRP_GLOBAL void k_pairs_compact(PairTabParams p) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (u64)gridDim.x * blockDim.x;
+    for (u64 s = tid; s <= p.pt_mask; s += nthr) {
+        const unsigned long long k = p.pt_key[s];
+        if (k == PAIRTAB_EMPTY) continue;
+        const u32 c = p.pt_cnt[s];
+        if (c < p.min_sim) continue;
+        const unsigned long long pos = atomicAdd(p.cells_count, 1ull);
+        if (pos < p.cells_cap) p.cells[pos] = make_uint4((u32)(k >> 32), (u32)k, c, 0u);
+    }
+}
+
 }  // namespace kr

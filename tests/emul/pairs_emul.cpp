@@ -13,6 +13,7 @@
 #include <map>
 #include <random>
 #include <set>
+#include <tuple>
 #include <vector>
 
 struct Dim3 { unsigned x = 1, y = 1, z = 1; };
@@ -21,6 +22,8 @@ template <class T> static T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return 
 template <class T> static T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 template <class T> static T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
+struct uint4 { uint32_t x, y, z, w; };
+static uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 #define KR_PAIRS_EMUL 1
 #include "../../kmers/reps_b200/csrc/kr_pairs.cuh"
 using namespace kr;
@@ -110,6 +113,39 @@ int main(int argc, char **argv) {
                     }
                 }
                 if (pos != p.total) { printf("FAIL: cell count\n"); return 1; }
+                ++checked;
+            }
+        }
+        // sparse result through the pair table: TRIANGLE cells with sim >= min_sim, per row stripe
+        for (uint32_t flags = 0; flags < 2; ++flags) for (uint32_t min_sim : {1u, 3u, 9999u}) {
+            std::vector<std::pair<uint32_t, uint32_t>> stripes = {{0, N}};
+            if (N > 256) { stripes.push_back({256, N}); stripes.push_back({0, 256}); }
+            for (auto st : stripes) {
+                PairTabParams p{};
+                p.tab_cnt = tab_cnt.data(); p.tab_off = tab_off.data(); p.postings = postings.data(); p.nslots = nslots;
+                uint64_t work = 0; for (auto &kv : inv) work += (uint64_t)kv.second.size() * (kv.second.size() - 1) / 2;
+                uint64_t pcap = 16; while (pcap < 2 * work + 2ull * N) pcap <<= 1;
+                std::vector<unsigned long long> pt_key(pcap, PAIRTAB_EMPTY); std::vector<uint32_t> pt_cnt(pcap, 0);
+                p.pt_key = pt_key.data(); p.pt_cnt = pt_cnt.data(); p.pt_mask = pcap - 1;
+                p.N = N; p.row_begin = st.first; p.row_end = st.second; p.flags = flags; p.min_sim = min_sim;
+                uint32_t hm = 1; while (hm < 2 * N) hm <<= 1;
+                std::vector<uint32_t> head(hm, PAIRS_NIL), next(N, PAIRS_NIL);
+                p.meta = meta.data(); p.head = head.data(); p.next = next.data(); p.head_mask = hm - 1;
+                std::vector<uint4> cells(64); unsigned long long count = 0;
+                p.cells = cells.data(); p.cells_cap = cells.size(); p.cells_count = &count;
+                launch(k_pairs_emit_tab, 3, 64, p);
+                launch(k_pairs_dup_insert_tab, (N + 127) / 128, 128, p);
+                launch(k_pairs_dup_tab, (N + 127) / 128, 128, p);
+                launch(k_pairs_compact, 2, 96, p);
+                if (count > cells.size()) {          // too little room: the count is right, run the compaction again with enough
+                    cells.assign(count, uint4{}); p.cells = cells.data(); p.cells_cap = cells.size(); count = 0;
+                    launch(k_pairs_compact, 2, 96, p);
+                }
+                std::set<std::tuple<uint32_t, uint32_t, uint32_t>> got, want;
+                for (unsigned long long c = 0; c < count; ++c) got.insert({cells[c].x, cells[c].y, cells[c].z});
+                if (got.size() != count) { printf("FAIL: sparse cell listed twice\n"); return 1; }
+                for (uint32_t i = st.first; i < st.second; ++i) for (uint32_t j = i + 1; j < N; ++j) { uint32_t v = sim(i, j, flags != 0); if (v >= min_sim) want.insert({i, j, v}); }
+                if (got != want) { printf("FAIL: sparse cells differ N=%u flags=%u min_sim=%u rows[%u,%u): got %zu want %zu\n", N, flags, min_sim, st.first, st.second, got.size(), want.size()); return 1; }
                 ++checked;
             }
         }

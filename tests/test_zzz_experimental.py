@@ -23,11 +23,18 @@ def cells_of(dense, min_sim, triangle):
     return out
 
 
+@pytest.mark.parametrize("via", [0, binding.EXP_PAIRS])
 @pytest.mark.parametrize("n,nfam", [(700, 12), (1500, 300)])
-def test_sparse_matrix_equals_dense(oracle, n, nfam):
+def test_sparse_matrix_equals_dense(oracle, n, nfam, via):
+    """kr_sim_matrix_sparse through the join's epilogue filter (via = 0) and through posting lists + pair table"""
     res, off, _ = synth.generate(0x5EED0008, n, nfam)
+    seqs = synth.to_strings(res, off)
+    seqs[5] = seqs[9] = "MKV"                                            # equal sequences without any k-mer
+    seqs[11] = ""
+    res, off = kr.flat(seqs)
     want = oracle.sim_matrix(oracle.batch(res=res, off=off, K=8), ident_inf=True, threads=4)
-    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    assert want[5, 9] == 9999
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | via)
     s = c.encode(res=res, off=off)
     for min_sim in (1, 50, 9999):
         got = c.sim_matrix_sparse(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
