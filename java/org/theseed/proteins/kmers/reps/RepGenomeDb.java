@@ -124,6 +124,46 @@ public class RepGenomeDb implements Iterable<RepGenome> {
         return out;
     }
 
+    /**
+     * Similarity of every query to EVERY representative, representatives in iteration order (this.all()): the
+     * rewritten inner loop of NeighborProcessor.processGenome (:165-168), one rectangular GPU matrix for all queries.
+     * Row q, column r = new Representation(all()[r], queries[q]).getSimilarity().
+     */
+    public int[][] similarities(List<? extends ProteinKmers> queries) {
+        RepGenome[] reps = all();
+        int[][] out = new int[queries.size()][reps.length];
+        if (queries.isEmpty() || reps.length == 0) return out;
+        List<String> q = new ArrayList<>(), r = new ArrayList<>();
+        for (ProteinKmers p : queries) q.add(p.getProtein());
+        for (RepGenome g : reps) r.add(g.getProtein());
+        try (KmersRepsNative.SeqSet qs = KmersRepsNative.encode(kmerSize, q); KmersRepsNative.SeqSet rs = KmersRepsNative.encode(kmerSize, r)) {
+            int[] cells = KmersRepsNative.simMatrix(qs, rs);
+            for (int i = 0; i < q.size(); i++) System.arraycopy(cells, i * reps.length, out[i], 0, reps.length);
+        }
+        return out;
+    }
+
+    /**
+     * The N closest representatives of one query with the reference's tie retention (NeighborProcessor.java:161-193):
+     * positions into `row` (similarities in iteration order), best first; a new result goes before the entries it
+     * ties with, and the list is cut back to `num` only when the entry at the break beats the one after it.
+     */
+    public static List<Integer> closestN(int[] row, int num, int minSim) {
+        List<Integer> found = new ArrayList<>(num + 1);
+        for (int r = 0; r < row.length; r++) {
+            int sim = row[r];
+            if (sim < minSim) continue;
+            int idx = 0, n = found.size();
+            while (idx < n && row[found.get(idx)] > sim) idx++;
+            if (idx < n || n < num) {
+                found.add(idx, r);
+                if (found.size() > num && row[found.get(num - 1)] > row[found.get(num)])
+                    while (found.size() > num) found.remove(num);
+            }
+        }
+        return found;
+    }
+
     public boolean checkSimilarity(ProteinKmers query, int sim) {
         return size() > 0 && findClosest(query).getSimilarity() >= sim;
     }
