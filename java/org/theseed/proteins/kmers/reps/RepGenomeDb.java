@@ -75,7 +75,8 @@ public class RepGenomeDb implements Iterable<RepGenome> {
     public int size() { return genomeMap.size(); }
     public RepGenome get(String genomeId) { return genomeMap.get(genomeId); }
     public boolean contains(String genomeId) { return genomeMap.containsKey(genomeId); }
-    public Collection<RepGenome> all() { return genomeMap.values(); }
+    /** the representatives in iteration order, as an array (NeighborProcessor.java:140, ListProcessor.java:62) */
+    public RepGenome[] all() { return genomeMap.values().toArray(new RepGenome[0]); }
     public SortedSet<RepGenome> sorted() { return new TreeSet<>(genomeMap.values()); }
     public String getListFileName() { return String.format("rep%d.list.tbl", threshold); }
     @Override public String toString() { return "RepGen" + threshold; }
