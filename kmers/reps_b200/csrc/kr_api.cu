@@ -21,6 +21,15 @@
 
 using namespace kr;
 
+// Kernel launches go through one macro so that the test emulator (tests/emul/, -DKR_EMUL, g++) can run the same host
+// code; for nvcc it expands to exactly the <<< >>> launch it replaces.
+#define KR_T(...) __VA_ARGS__
+#ifdef KR_EMUL
+#define KR_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+#else
+#define KR_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_create_error;
 
@@ -375,7 +384,7 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
         p.err = ctx->d_err; p.nseq = nseq; p.K = K; p.smem_cap = 2048;
         // proteins are a few hundred residues: one 128-thread CTA sorts up to 2048 keys in 16 KB of shared
         // memory; longer sequences (rare) sort in place in global memory inside the same kernel
-        k_encode_sort<128><<<nseq, 128, p.smem_cap * 8 + p.smem_cap + 16, ctx->stream>>>(p);
+        KR_LAUNCH(KR_T(k_encode_sort<128>), nseq, 128, p.smem_cap * 8 + p.smem_cap + 16, ctx->stream, p);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
     }
@@ -408,11 +417,11 @@ static kr_status ensure_blocklists(kr_ctx *ctx, kr_seqset *s) {
     if (nblk) {
         StageTimer t(ctx, ST_BLOCKLIST);
         int shift = 5 * ctx->K - LUT_BITS;
-        k_bl_count<<<nblk, 256, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt);
-        k_bl_offsets<<<1, 1024, 0, ctx->stream>>>(s->d_chcnt, nblk, s->d_choff, s->d_blkbase);
-        k_bl_scatter<<<nblk, 256, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt, s->d_choff,
+        KR_LAUNCH(KR_T(k_bl_count), nblk, 256, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt);
+        KR_LAUNCH(KR_T(k_bl_offsets), 1, 1024, 0, ctx->stream, s->d_chcnt, nblk, s->d_choff, s->d_blkbase);
+        KR_LAUNCH(KR_T(k_bl_scatter), nblk, 256, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, ctx->d_lut, shift, s->d_chcnt, s->d_choff,
                                                     s->d_blkbase, d_ent, s->d_hi, s->d_lo, lo_size, s->d_refs);
-        k_bl_sort<<<nblk * NCHUNK, 256, 0, ctx->stream>>>(s->d_refs, s->d_blkbase, d_ent, lobits);
+        KR_LAUNCH(KR_T(k_bl_sort), nblk * NCHUNK, 256, 0, ctx->stream, s->d_refs, s->d_blkbase, d_ent, lobits);
         ctx->st.kernel_launches += 4;
         CU(cudaGetLastError());
     }
@@ -455,7 +464,7 @@ static kr_status gather_impl(kr_ctx *ctx, const kr_seqset *src_c, const u32 *idx
     CU(cudaMemcpyAsync(s->d_koff, koff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (n) {
         StageTimer t(ctx, ST_OTHER);
-        k_gather_keys<<<n, 128, 0, ctx->stream>>>(src->d_keys, src->d_koff, src->d_meta, d_idx, n, s->d_koff, s->d_keys, s->d_meta);
+        KR_LAUNCH(KR_T(k_gather_keys), n, 128, 0, ctx->stream, src->d_keys, src->d_koff, src->d_meta, d_idx, n, s->d_koff, s->d_keys, s->d_meta);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
     }
@@ -499,11 +508,11 @@ static kr_status ensure_postings(kr_ctx *ctx, kr_seqset *s) {
     CU(cudaMemsetAsync(d_cur, 0, cap * 4, ctx->stream));
     if (s->n) {
         StageTimer t(ctx, ST_BLOCKLIST);
-        k_idx_insert<<<s->n, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, s->px_key, s->px_cnt, mask);
-        k_scan_tile_sums<<<ntile, 256, 0, ctx->stream>>>(s->px_cnt, cap, d_sums);
-        k_scan_sums<<<1, 1024, 0, ctx->stream>>>(d_sums, ntile);
-        k_scan_tiles<<<ntile, 256, 0, ctx->stream>>>(s->px_cnt, cap, d_sums, s->px_off);
-        k_idx_fill<<<s->n, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff, s->d_meta, s->n, 0, s->px_key, s->px_off, d_cur, mask, s->px_post);
+        KR_LAUNCH(KR_T(k_idx_insert), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, s->px_key, s->px_cnt, mask);
+        KR_LAUNCH(KR_T(k_scan_tile_sums), ntile, 256, 0, ctx->stream, s->px_cnt, cap, d_sums);
+        KR_LAUNCH(KR_T(k_scan_sums), 1, 1024, 0, ctx->stream, d_sums, ntile);
+        KR_LAUNCH(KR_T(k_scan_tiles), ntile, 256, 0, ctx->stream, s->px_cnt, cap, d_sums, s->px_off);
+        KR_LAUNCH(KR_T(k_idx_fill), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, 0, s->px_key, s->px_off, d_cur, mask, s->px_post);
         ctx->st.kernel_launches += 5;
         CU(cudaGetLastError());
     }
@@ -519,7 +528,7 @@ static kr_status postings_work(kr_ctx *ctx, kr_seqset *A) {
     unsigned long long *d_work = nullptr, w = 0;
     CU(dalloc(ctx, &d_work, 1));
     CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));
-    k_pairs_work<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A->px_cnt, A->px_slots, d_work);
+    KR_LAUNCH(KR_T(k_pairs_work), ctx->num_sms * 4, 256, 0, ctx->stream, A->px_cnt, A->px_slots, d_work);
     LAUNCHED(ctx);
     CU(cudaMemcpyAsync(&w, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -556,9 +565,9 @@ static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d
     {
         StageTimer t(ctx, ST_JOIN);
         CU(cudaMemsetAsync(out_dev, 0, p.total * esz, ctx->stream));
-        k_pairs_emit<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p);
-        k_pairs_dup_insert<<<(A->n + 255) / 256, 256, 0, ctx->stream>>>(p);
-        k_pairs_dup_fix<<<(A->n + 255) / 256, 256, 0, ctx->stream>>>(p);
+        KR_LAUNCH(KR_T(k_pairs_emit), ctx->num_sms * 8, 256, 0, ctx->stream, p);
+        KR_LAUNCH(KR_T(k_pairs_dup_insert), (A->n + 255) / 256, 256, 0, ctx->stream, p);
+        KR_LAUNCH(KR_T(k_pairs_dup_fix), (A->n + 255) / 256, 256, 0, ctx->stream, p);
         ctx->st.kernel_launches += 3; ctx->st.join_launches++;
         CU(cudaGetLastError());
     }
@@ -614,12 +623,12 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
 #ifdef KR_EXPERIMENTAL
         if (sparse) {
             p.cells = sparse->cells; p.cells_cap = sparse->cap; p.cells_count = sparse->count; p.min_sim = sparse->min_sim;
-            if (lo_bits(ctx->K) <= 16) k_join<MODE_SPARSE, false><<<grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream>>>(p);
-            else k_join<MODE_SPARSE, true><<<grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream>>>(p);
+            if (lo_bits(ctx->K) <= 16) KR_LAUNCH(KR_T(k_join<MODE_SPARSE, false>), grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream, p);
+            else KR_LAUNCH(KR_T(k_join<MODE_SPARSE, true>), grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream, p);
         } else
 #endif
-        if (lo_bits(ctx->K) <= 16) k_join<MODE_MATRIX, false><<<grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream>>>(p);
-        else k_join<MODE_MATRIX, true><<<grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream>>>(p);
+        if (lo_bits(ctx->K) <= 16) KR_LAUNCH(KR_T(k_join<MODE_MATRIX, false>), grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream, p);
+        else KR_LAUNCH(KR_T(k_join<MODE_MATRIX, true>), grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream, p);
         LAUNCHED(ctx); ctx->st.join_launches++;
         CU(cudaGetLastError());
     }
@@ -670,7 +679,7 @@ static kr_status db_refresh(kr_ctx *ctx, kr_db *db) {
         kr_seqset *s = sg.set;
         if (!s->n) continue;
         CU(cudaMemcpyAsync(db->d_meta + sg.base, s->d_meta, (size_t)s->n * sizeof(SeqMeta), cudaMemcpyDeviceToDevice, ctx->stream));
-        k_copy_refs<<<(s->nblk + 127) / 128, 128, 0, ctx->stream>>>(s->d_refs, s->nblk, sg.base, db->d_refs + bo);
+        KR_LAUNCH(KR_T(k_copy_refs), (s->nblk + 127) / 128, 128, 0, ctx->stream, s->d_refs, s->nblk, sg.base, db->d_refs + bo);
         LAUNCHED(ctx);
         bo += s->nblk;
     }
@@ -683,8 +692,8 @@ static kr_status db_refresh(kr_ctx *ctx, kr_db *db) {
             CU(cudaMemcpyAsync(db->d_order, order.data(), (size_t)db->n * 4, cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         } else {
-            k_fill_u32_iota<<<(db->n + 255) / 256, 256, 0, ctx->stream>>>(db->d_rank, db->n, 0);
-            k_fill_u32_iota<<<(db->n + 255) / 256, 256, 0, ctx->stream>>>(db->d_order, db->n, 0);
+            KR_LAUNCH(KR_T(k_fill_u32_iota), (db->n + 255) / 256, 256, 0, ctx->stream, db->d_rank, db->n, 0);
+            KR_LAUNCH(KR_T(k_fill_u32_iota), (db->n + 255) / 256, 256, 0, ctx->stream, db->d_order, db->n, 0);
             ctx->st.kernel_launches += 2;
         }
     }
@@ -726,8 +735,8 @@ static kr_status db_compact(kr_ctx *ctx, kr_db *db) {
         // gathered / compacted sets have dense key arenas only if built by gather; use the gather kernel for generality
         u32 *d_idx = nullptr;
         CU(dalloc(ctx, &d_idx, g->n));
-        k_fill_u32_iota<<<(g->n + 255) / 256, 256, 0, ctx->stream>>>(d_idx, g->n, 0);
-        k_gather_keys<<<g->n, 128, 0, ctx->stream>>>(g->d_keys, g->d_koff, g->d_meta, d_idx, g->n, s->d_koff + at, s->d_keys, s->d_meta + at);
+        KR_LAUNCH(KR_T(k_fill_u32_iota), (g->n + 255) / 256, 256, 0, ctx->stream, d_idx, g->n, 0);
+        KR_LAUNCH(KR_T(k_gather_keys), g->n, 128, 0, ctx->stream, g->d_keys, g->d_koff, g->d_meta, d_idx, g->n, s->d_koff + at, s->d_keys, s->d_meta + at);
         ctx->st.kernel_launches += 2;
         dfree(ctx, d_idx);
         at += g->n;
@@ -778,18 +787,18 @@ static kr_status db_build_index(kr_ctx *ctx, kr_db *db) {
             u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
             if (lo >= hi) continue;
             kr_seqset *s = sg.set; u32 l = lo - sg.base;
-            k_idx_insert<<<hi - lo, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, sl.tab_key, sl.tab_cnt, sl.mask);
+            KR_LAUNCH(KR_T(k_idx_insert), hi - lo, 128, 0, ctx->stream, s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, sl.tab_key, sl.tab_cnt, sl.mask);
             LAUNCHED(ctx);
         }
-        k_scan_tile_sums<<<ntile, 256, 0, ctx->stream>>>(sl.tab_cnt, cap, d_sums);
-        k_scan_sums<<<1, 1024, 0, ctx->stream>>>(d_sums, ntile);
-        k_scan_tiles<<<ntile, 256, 0, ctx->stream>>>(sl.tab_cnt, cap, d_sums, sl.tab_off);
+        KR_LAUNCH(KR_T(k_scan_tile_sums), ntile, 256, 0, ctx->stream, sl.tab_cnt, cap, d_sums);
+        KR_LAUNCH(KR_T(k_scan_sums), 1, 1024, 0, ctx->stream, d_sums, ntile);
+        KR_LAUNCH(KR_T(k_scan_tiles), ntile, 256, 0, ctx->stream, sl.tab_cnt, cap, d_sums, sl.tab_off);
         ctx->st.kernel_launches += 3;
         for (auto &sg : db->segs) {
             u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
             if (lo >= hi) continue;
             kr_seqset *s = sg.set; u32 l = lo - sg.base;
-            k_idx_fill<<<hi - lo, 128, 0, ctx->stream>>>(s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, lo, sl.tab_key, sl.tab_off, d_cur,
+            KR_LAUNCH(KR_T(k_idx_fill), hi - lo, 128, 0, ctx->stream, s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, lo, sl.tab_key, sl.tab_off, d_cur,
                                                           sl.mask, sl.postings);
             LAUNCHED(ctx);
         }
@@ -801,7 +810,7 @@ static kr_status db_build_index(kr_ctx *ctx, kr_db *db) {
     u32 *d_count = nullptr;
     CU(dalloc(ctx, &db->d_empty_reps, db->n)); CU(dalloc(ctx, &d_count, 1));
     CU(cudaMemsetAsync(d_count, 0, 4, ctx->stream));
-    k_collect_empty<<<(db->n + 255) / 256, 256, 0, ctx->stream>>>(db->d_meta, db->n, db->d_empty_reps, d_count);
+    KR_LAUNCH(KR_T(k_collect_empty), (db->n + 255) / 256, 256, 0, ctx->stream, db->d_meta, db->n, db->d_empty_reps, d_count);
     LAUNCHED(ctx);
     CU(cudaMemcpyAsync(&db->nempty, d_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -828,18 +837,18 @@ static kr_status find_closest_index(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *d
             p.rmeta = db->d_meta; p.rank = db->d_rank; p.slab_base = sl.base; p.slab_n = sl.n; p.flags = ctx->flags;
             p.partial = d_partial + (size_t)k * Q->n; p.next = d_next + k;
             u32 grid = std::min<u32>(Q->n, 2 * (u32)ctx->num_sms);
-            k_idx_query<<<grid, IDX_THREADS, ((size_t)sl.n + 1) / 2 * 4, ctx->stream>>>(p);
+            KR_LAUNCH(KR_T(k_idx_query), grid, IDX_THREADS, ((size_t)sl.n + 1) / 2 * 4, ctx->stream, p);
             LAUNCHED(ctx); ctx->st.join_launches++;
         }
         if ((ctx->flags & KR_IDENT_IS_INFINITY) && db->nempty) {
-            k_idx_empty_queries<<<(Q->n * 32 + 255) / 256, 256, 0, ctx->stream>>>(Q->d_meta, Q->n, db->d_meta, db->d_rank, db->d_empty_reps,
+            KR_LAUNCH(KR_T(k_idx_empty_queries), (Q->n * 32 + 255) / 256, 256, 0, ctx->stream, Q->d_meta, Q->n, db->d_meta, db->d_rank, db->d_empty_reps,
                                                                                   db->nempty, d_partial);
             LAUNCHED(ctx);
         }
     }
     {
         StageTimer t(ctx, ST_OTHER);
-        k_idx_merge<<<(Q->n + 255) / 256, 256, 0, ctx->stream>>>(d_partial, Q->n, nslab, db->d_order, d_sim, d_first, d_last);
+        KR_LAUNCH(KR_T(k_idx_merge), (Q->n + 255) / 256, 256, 0, ctx->stream, d_partial, Q->n, nslab, db->d_order, d_sim, d_first, d_last);
         LAUNCHED(ctx);
     }
     CU(cudaGetLastError());
@@ -879,13 +888,13 @@ static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *
     {
         StageTimer t(ctx, ST_JOIN);
         u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
-        if (lo_bits(ctx->K) <= 16) k_join<MODE_ARGMAX, false><<<grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream>>>(p);
-        else k_join<MODE_ARGMAX, true><<<grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream>>>(p);
+        if (lo_bits(ctx->K) <= 16) KR_LAUNCH(KR_T(k_join<MODE_ARGMAX, false>), grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream, p);
+        else KR_LAUNCH(KR_T(k_join<MODE_ARGMAX, true>), grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream, p);
         LAUNCHED(ctx); ctx->st.join_launches++;
     }
     {
         StageTimer t(ctx, ST_OTHER);
-        k_argmax_merge<<<(Q->n + 255) / 256, 256, 0, ctx->stream>>>(d_partial, Q->n, nsplit, db->d_order, d_sim, d_first, d_last);
+        KR_LAUNCH(KR_T(k_argmax_merge), (Q->n + 255) / 256, 256, 0, ctx->stream, d_partial, Q->n, nsplit, db->d_order, d_sim, d_first, d_last);
         LAUNCHED(ctx);
     }
     CU(cudaGetLastError());
@@ -1013,12 +1022,12 @@ kr_status kr_seqset_import_blocklists(kr_ctx *ctx, const kr_blocklists *shards, 
         CU(cudaMemcpyAsync(s->d_choff + (size_t)b0 * (NCHUNK + 1), sh.chunk_off, (size_t)sh.nblk * (NCHUNK + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         CU(cudaMemcpyAsync(s->d_chcnt + (size_t)b0 * NCHUNK, sh.chunk_cnt, (size_t)sh.nblk * NCHUNK * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         CU(cudaMemcpyAsync(s->d_meta + s0, sh.meta, (size_t)sh.nseq * sizeof(SeqMeta), cudaMemcpyDeviceToDevice, ctx->stream));
-        k_import_refs<<<(sh.nblk + 127) / 128, 128, 0, ctx->stream>>>(sh.nblk, b0, s0, sh.nseq, s->d_hi, d_lo, lo_size, s->d_choff, s->d_chcnt,
+        KR_LAUNCH(KR_T(k_import_refs), (sh.nblk + 127) / 128, 128, 0, ctx->stream, sh.nblk, b0, s0, sh.nseq, s->d_hi, d_lo, lo_size, s->d_choff, s->d_chcnt,
                                                                      (const u64 *)sh.blk_base, e0, s->d_refs);
         LAUNCHED(ctx);
         e0 += (sh.entries + 63) / 64 * 64; b0 += sh.nblk; s0 += sh.nseq;
     }
-    if (nseq) { k_import_meta<<<(nseq + 255) / 256, 256, 0, ctx->stream>>>(s->d_meta, nseq, (const u8 *)s->res->p, s->d_off); LAUNCHED(ctx); }
+    if (nseq) { KR_LAUNCH(KR_T(k_import_meta), (nseq + 255) / 256, 256, 0, ctx->stream, s->d_meta, nseq, (const u8 *)s->res->p, s->d_off); LAUNCHED(ctx); }
     CU(cudaGetLastError());
     s->bl_ready = true;
     *out = s.release();
@@ -1042,7 +1051,7 @@ kr_status kr_sim_pairs(kr_ctx *ctx, const kr_seqset *A, const uint32_t *ia, cons
     {
         StageTimer t(ctx, ST_OTHER);
         u32 grid = (u32)std::min<u64>((npairs + 7) / 8, (u64)ctx->num_sms * 8);
-        k_sim_pairs<<<grid, 256, 0, ctx->stream>>>(A->d_keys, A->d_koff, A->d_meta, d_ia, B->d_keys, B->d_koff, B->d_meta, d_ib, npairs,
+        KR_LAUNCH(KR_T(k_sim_pairs), grid, 256, 0, ctx->stream, A->d_keys, A->d_koff, A->d_meta, d_ia, B->d_keys, B->d_koff, B->d_meta, d_ib, npairs,
                                                    ctx->flags, d_sim, d_id);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
@@ -1183,10 +1192,10 @@ kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
             CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
             {
                 StageTimer t(ctx, ST_JOIN);
-                k_pairs_emit_tab<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p);
-                k_pairs_dup_insert_tab<<<(As->n + 255) / 256, 256, 0, ctx->stream>>>(p);
-                k_pairs_dup_tab<<<(As->n + 255) / 256, 256, 0, ctx->stream>>>(p);
-                k_pairs_compact<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p);
+                KR_LAUNCH(KR_T(k_pairs_emit_tab), ctx->num_sms * 8, 256, 0, ctx->stream, p);
+                KR_LAUNCH(KR_T(k_pairs_dup_insert_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);
+                KR_LAUNCH(KR_T(k_pairs_dup_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);
+                KR_LAUNCH(KR_T(k_pairs_compact), ctx->num_sms * 8, 256, 0, ctx->stream, p);
                 ctx->st.kernel_launches += 4; ctx->st.join_launches++;
                 CU(cudaGetLastError());
             }

@@ -12,7 +12,13 @@
 //               256x256 sequence pairs at once in a shared-memory count tile                (K3)
 // Every similarity is an exact integer; nothing here is floating point.
 #pragma once
+#ifdef KR_EMUL
+#include "cuda_emul.h"   // tests/emul: the same sources compiled with g++ and run on CPU threads (test infrastructure)
+#define KR_DYN_SMEM(type, name, align) type *name = reinterpret_cast<type *>(emu::dyn_smem())
+#else
 #include <cuda_runtime.h>
+#define KR_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
+#endif
 #include <stdint.h>
 
 #include "kr_types.cuh"
@@ -140,7 +146,7 @@ __device__ __forceinline__ u32 residue_code(u32 c) {
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_encode_sort(EncodeParams p) {
-    extern __shared__ __align__(16) u64 sk[];          // smem_cap keys, then smem_cap + 16 code bytes
+    KR_DYN_SMEM(u64, sk, 16);                          // smem_cap keys, then smem_cap + 16 code bytes
     __shared__ u64 s_hash, s_prev;
     __shared__ u32 s_wtot[THREADS / 32];
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -342,6 +348,19 @@ __global__ void k_copy_refs(const BlockRef *src, u32 n, u32 seq_base, BlockRef *
 }
 
 // ---------------------------------------------------------------------------------------------
+#ifdef KR_EMUL
+// the same primitives on the CPU emulator (tests/emul/cuda_emul.h)
+__device__ __forceinline__ u32 smem_u32(const void *p) { return emu::smem_addr(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) { emu::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_arrive_n(u64 *bar, u32 count) { emu::mbar_arrive(bar, count); }
+__device__ __forceinline__ void mbar_arrive(u64 *bar) { emu::mbar_arrive(bar, 1); }
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    for (u32 spins = 0; !emu::mbar_try_wait(bar, parity); ++spins) if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) { emu::bulk_g2s(dst, src, bytes, bar); }
+__device__ __forceinline__ void consumer_bar();
+#else
 // mbarrier / TMA bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP)
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
@@ -385,6 +404,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
                  : "memory");
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCWARP * 32) : "memory"); }
+#endif
+#ifdef KR_EMUL
+__device__ __forceinline__ void consumer_bar() { emu::named_barrier(1, NCWARP * 32); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K3: the tile join.
@@ -421,6 +444,10 @@ __device__ __noinline__ bool seq_equal(const SeqMeta &a, const SeqMeta &b) {
     return true;
 }
 
+#ifdef KR_EMUL
+__device__ __forceinline__ u32 lds32(u32 addr) { return *reinterpret_cast<const u32 *>(emu::smem_ptr(addr)); }
+__device__ __forceinline__ u32 lds16(u32 addr) { return *reinterpret_cast<const u16 *>(emu::smem_ptr(addr)); }
+#else
 __device__ __forceinline__ u32 lds32(u32 addr) {
     u32 v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -431,6 +458,7 @@ __device__ __forceinline__ u32 lds16(u32 addr) {
     asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr));
     return v;
 }
+#endif
 template <bool LO32> __device__ __forceinline__ u32 ldlo(u32 base, u32 i) { return LO32 ? lds32(base + i * 4) : lds16(base + i * 2); }
 
 // All matches of the staged A entries against the staged B sub-chunk -> count tile.
@@ -504,7 +532,7 @@ constexpr u32 JF_DONE = 4;       // head slot: no more work for this CTA
 // different jobs at the same time.  All consumers meet at a named barrier twice per tile (epilogue).
 template <int MODE, bool LO32>
 __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
-    extern __shared__ __align__(128) u8 smem[];
+    KR_DYN_SMEM(u8, smem, 128);
     constexpr int NST = nstage(LO32);
     constexpr u32 LOSZ = LO32 ? 4 : 2;
     constexpr u32 STAGE_B = (u32)stage_bytes(LO32);
@@ -518,8 +546,10 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCWARP); }
+#ifndef KR_EMUL
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
     }
     for (u32 i = tid; i < TB * TB / 2; i += JOIN_THREADS) cnt[i] = 0;
     __syncthreads();
@@ -917,7 +947,7 @@ struct IdxQueryParams {
 // second pass.  The (offset, count) of each key's posting list is kept in shared memory for the clearing walk.
 constexpr u32 IDX_KEYCACHE = 512;    // posting ranges cached per query; longer queries re-probe when clearing
 __global__ void __launch_bounds__(IDX_THREADS, 2) k_idx_query(IdxQueryParams p) {
-    extern __shared__ __align__(16) u32 score[];   // (slab_n + 1) / 2 words, zero between queries
+    KR_DYN_SMEM(u32, score, 16);                   // (slab_n + 1) / 2 words, zero between queries
     __shared__ u32 s_q;
     __shared__ unsigned long long s_first[IDX_THREADS / 32], s_last[IDX_THREADS / 32];
     __shared__ uint2 s_range[IDX_KEYCACHE];

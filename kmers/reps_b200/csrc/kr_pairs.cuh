@@ -18,7 +18,11 @@
 #pragma once
 #include "kr_types.cuh"
 
-#ifndef KR_PAIRS_EMUL
+#if defined(KR_EMUL)
+#include "cuda_emul.h"
+#define KRP_DEVICE __device__ __forceinline__
+#define KRP_GLOBAL __global__
+#elif !defined(KR_PAIRS_EMUL)
 #include <cuda_runtime.h>
 #define KRP_DEVICE __device__ __forceinline__
 #define KRP_GLOBAL __global__

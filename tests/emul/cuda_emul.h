@@ -1,0 +1,311 @@
+// cuda_emul.h -- TEST INFRASTRUCTURE ONLY: a functional emulation of the small part of CUDA that
+// kmers/reps_b200/csrc uses, so that the product's kernel and host sources can be compiled with g++
+// (-DKR_EMUL) and EXECUTED on CPU threads by the tests in a container without a GPU.
+//
+// It is a simulator for checking logic (indexing, protocols, host orchestration), never a product path and never
+// a fallback: only tests/ builds it (tests/emul/Makefile -> tests/emul/_build/libkmersreps_emul.so) and loads it
+// through KR_LIB_PATH.  One CUDA thread = one fiber of the launching OS thread; CTAs of a launch run one after another;
+// streams are synchronous.  What it models:
+//   threadIdx/blockIdx/blockDim/gridDim, __shared__ (static and dynamic), __syncthreads, named barriers,
+//   warp shuffles / votes (lock-step exchange through a per-warp buffer), global and shared atomics,
+//   mbarrier (init / arrive / expect_tx / try_wait.parity) and 1-D bulk copies completing a transaction count
+//   (with the alignment rules of cp.async.bulk CHECKED: 16-byte aligned source, destination and size),
+//   cudaMalloc/Memcpy/Memset/streams/events as plain host operations.
+// What it cannot show: performance, memory-ordering races, register pressure.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include <ucontext.h>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static
+#define __restrict__
+
+struct uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a) : x(a) {} };
+
+namespace emu {
+
+// One CUDA thread = one fiber (ucontext); the fibers of a CTA are run round-robin by the launching OS thread, so
+// execution is single-threaded and deterministic, a blocked fiber just yields, and a CTA in which every fiber is
+// blocked is reported as a deadlock instead of hanging.
+struct Fiber { ucontext_t ctx; dim3 tid; bool done = false; std::vector<uint8_t> stack; };
+struct Sched {
+    ucontext_t main;
+    std::vector<Fiber> fibers;
+    unsigned cur = 0;
+    unsigned long long idle_yields = 0;   // yields since the last sign of progress
+};
+inline Sched *&sched() { static Sched *s = nullptr; return s; }
+inline void progress() { sched()->idle_yields = 0; }
+inline void yield() {
+    Sched *s = sched();
+    if (++s->idle_yields > 50000000ull) { fprintf(stderr, "cuda_emul: deadlock (every thread of the CTA is waiting)\n"); abort(); }
+    swapcontext(&s->fibers[s->cur].ctx, &s->main);
+}
+
+// a reusable counting barrier whose party count can shrink (threads that leave the kernel early)
+class Barrier {
+  public:
+    explicit Barrier(unsigned n) : parties_(n), waiting_(0), gen_(0) {}
+    void arrive_and_wait() {
+        const unsigned g = gen_;
+        if (++waiting_ >= parties_) { waiting_ = 0; ++gen_; progress(); return; }
+        while (gen_ == g) yield();
+    }
+    void drop() {
+        --parties_;
+        if (parties_ && waiting_ >= parties_) { waiting_ = 0; ++gen_; progress(); }
+    }
+  private:
+    unsigned parties_, waiting_, gen_;
+};
+
+struct Warp { Barrier bar; uint64_t buf[32]; unsigned n; explicit Warp(unsigned k) : bar(k), n(k) {} };
+
+struct Block {
+    unsigned nthreads;
+    Barrier sync;
+    std::vector<std::unique_ptr<Warp>> warps;
+    std::map<int, std::unique_ptr<Barrier>> named;
+    explicit Block(unsigned n) : nthreads(n), sync(n) {
+        for (unsigned w = 0; w * 32 < n; ++w) warps.emplace_back(new Warp(std::min(32u, n - w * 32)));
+    }
+};
+
+inline Block *&cur_block() { static Block *b = nullptr; return b; }
+inline uint8_t *&dyn_smem() { static uint8_t *p = nullptr; return p; }
+inline size_t &dyn_smem_size() { static size_t n = 0; return n; }
+inline std::mutex &launch_lock() { static std::mutex m; return m; }   // one launch at a time per process
+struct Trap {};
+inline std::function<void()> *&cur_body() { static std::function<void()> *f = nullptr; return f; }
+inline bool &trapped() { static bool t = false; return t; }
+
+inline void fiber_main() {
+    Sched *s = sched();
+    Fiber &f = s->fibers[s->cur];
+    try { (*cur_body())(); } catch (Trap &) { trapped() = true; }
+    f.done = true;
+    progress();
+    cur_block()->sync.drop();                      // a thread that has left the kernel no longer takes part
+    cur_block()->warps[f.tid.x >> 5]->bar.drop();
+    swapcontext(&f.ctx, &s->main);
+}
+
+}  // namespace emu
+
+inline dim3 blockIdx, blockDim, gridDim;
+#define threadIdx (emu::sched()->fibers[emu::sched()->cur].tid)
+
+namespace emu {
+
+inline Warp &my_warp() { return *cur_block()->warps[threadIdx.x >> 5]; }
+
+template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
+    std::lock_guard<std::mutex> lk(launch_lock());
+    gridDim = grid; blockDim = block;
+    std::vector<uint8_t> smem(smem_bytes + 2048);
+    uint8_t *base = smem.data() + (1024 - (reinterpret_cast<uintptr_t>(smem.data()) & 1023));
+    dyn_smem() = base; dyn_smem_size() = smem_bytes;
+    std::function<void()> fn = body;
+    cur_body() = &fn;
+    Sched sc;
+    sc.fibers.resize(block.x);
+    const size_t stack_bytes = 96 * 1024;
+    for (auto &f : sc.fibers) f.stack.resize(stack_bytes);
+    sched() = &sc;
+    trapped() = false;
+    for (unsigned b = 0; b < grid.x; ++b) {
+        Block blk(block.x);
+        cur_block() = &blk;
+        blockIdx.x = b;
+        for (unsigned t = 0; t < block.x; ++t) {
+            Fiber &f = sc.fibers[t];
+            f.done = false; f.tid = dim3(t);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack.data(); f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = &sc.main;
+            makecontext(&f.ctx, (void (*)())fiber_main, 0);
+        }
+        sc.idle_yields = 0;
+        for (unsigned live = block.x; live;) {
+            live = 0;
+            for (unsigned t = 0; t < block.x; ++t) {
+                if (sc.fibers[t].done) continue;
+                sc.cur = t;
+                swapcontext(&sc.main, &sc.fibers[t].ctx);
+                if (!sc.fibers[t].done) ++live;
+            }
+        }
+        cur_block() = nullptr;
+        if (trapped()) { fprintf(stderr, "cuda_emul: kernel trapped in block %u\n", b); abort(); }
+    }
+    sched() = nullptr;
+}
+
+}  // namespace emu
+
+// ---- device-side intrinsics ------------------------------------------------------------------------------------
+inline void __syncthreads() { emu::cur_block()->sync.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::my_warp().bar.arrive_and_wait(); }
+inline void __trap() { throw emu::Trap(); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline T min(T a, T b) { return a < b ? a : b; }
+template <class T> inline T max(T a, T b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
+
+namespace emu {
+template <class T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+// every thread of the warp publishes its value, then reads the lane it wants
+template <class T> inline T exchange(T v, unsigned src_lane, bool keep_own_if_out_of_range) {
+    Warp &w = my_warp();
+    const unsigned lane = threadIdx.x & 31;
+    w.buf[lane] = to_bits(v);
+    w.bar.arrive_and_wait();
+    T r = (src_lane < w.n) ? from_bits<T>(w.buf[src_lane]) : v;
+    (void)keep_own_if_out_of_range;
+    w.bar.arrive_and_wait();
+    return r;
+}
+}  // namespace emu
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, (unsigned)src & 31, true); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask) { return emu::exchange(v, (threadIdx.x & 31) ^ (unsigned)mask, true); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+    const unsigned lane = threadIdx.x & 31;
+    return emu::exchange(v, lane >= d ? lane - d : lane, true);
+}
+inline unsigned __ballot_sync(unsigned, bool pred) {
+    emu::Warp &w = emu::my_warp();
+    const unsigned lane = threadIdx.x & 31;
+    w.buf[lane] = pred ? 1 : 0;
+    w.bar.arrive_and_wait();
+    unsigned r = 0;
+    for (unsigned l = 0; l < w.n; ++l) if (w.buf[l]) r |= 1u << l;
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
+
+// atomics (global or shared memory alike)
+template <class T> inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned *p, int v) { return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long v) { return __atomic_fetch_add(p, (unsigned long long)v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicCAS(T *p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+
+// ---- mbarrier + bulk copy (the PTX wrappers of kr_kernels.cuh call these under KR_EMUL) -------------------------------
+namespace emu {
+struct MBar { uint32_t phase : 1, pending : 15, expected : 15; int32_t tx; };
+static_assert(sizeof(MBar) == 8, "an mbarrier is 64 bits");
+inline void mbar_check(MBar *b) { if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->expected; progress(); } }
+inline void mbar_init(void *bar, uint32_t count) { MBar *b = (MBar *)bar; b->phase = 0; b->pending = b->expected = count; b->tx = 0; }
+inline void mbar_arrive(void *bar, uint32_t n) {
+    MBar *b = (MBar *)bar;
+    if (b->pending < n) { fprintf(stderr, "cuda_emul: mbarrier over-arrival\n"); abort(); }
+    b->pending -= n; mbar_check(b);
+}
+inline void mbar_expect_tx(void *bar, uint32_t bytes) {   // arrive.expect_tx: one arrival + a transaction count
+    MBar *b = (MBar *)bar;
+    b->tx += (int32_t)bytes;
+    if (b->pending < 1) { fprintf(stderr, "cuda_emul: mbarrier over-arrival\n"); abort(); }
+    b->pending -= 1; mbar_check(b);
+}
+inline void mbar_complete_tx(void *bar, uint32_t bytes) { MBar *b = (MBar *)bar; b->tx -= (int32_t)bytes; mbar_check(b); }
+inline bool mbar_try_wait(void *bar, uint32_t parity) {
+    const bool done = ((MBar *)bar)->phase != (parity & 1);
+    if (!done) yield();
+    return done;
+}
+inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || (bytes & 15)) {
+        fprintf(stderr, "cuda_emul: cp.async.bulk needs 16-byte aligned dst/src/size (dst %p src %p bytes %u): this faults on hardware\n", dst, src, bytes);
+        abort();
+    }
+    if ((uint8_t *)dst < dyn_smem() || (uint8_t *)dst + bytes > dyn_smem() + dyn_smem_size()) { fprintf(stderr, "cuda_emul: bulk copy outside shared memory\n"); abort(); }
+    memcpy(dst, src, bytes);
+    mbar_complete_tx(bar, bytes);
+}
+inline void named_barrier(int id, unsigned count) {
+    Block *blk = cur_block();
+    Barrier *b;
+    { auto &slot = blk->named[id]; if (!slot) slot.reset(new Barrier(count)); b = slot.get(); }
+    b->arrive_and_wait();
+}
+// shared-memory "addresses" are offsets into the dynamic buffer (+ a bias so that 0 is never valid)
+inline uint32_t smem_addr(const void *p) {
+    const uint8_t *q = (const uint8_t *)p;
+    if (q < dyn_smem() || q > dyn_smem() + dyn_smem_size()) { fprintf(stderr, "cuda_emul: address is not in dynamic shared memory\n"); abort(); }
+    return (uint32_t)(q - dyn_smem()) + 4096;
+}
+inline void *smem_ptr(uint32_t a) {
+    if (a < 4096 || a - 4096 + 4 > dyn_smem_size() + 16) { fprintf(stderr, "cuda_emul: shared load outside the CTA's shared memory (offset %u of %zu)\n", a - 4096, dyn_smem_size()); abort(); }
+    return dyn_smem() + (a - 4096);
+}
+}  // namespace emu
+
+// ---- the runtime API subset kr_api.cu uses (single device, synchronous streams) -------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorEmul = 1 };
+typedef struct CUstream_st { int id; } *cudaStream_t;
+typedef struct CUevent_st { std::chrono::steady_clock::time_point t; } *cudaEvent_t;
+typedef int cudaMemPool_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyHostToHost };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaMemPoolAttrReleaseThreshold = 4,
+       cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 4; size_t sharedMemPerBlockOptin = 232448; char name[64] = "cuda_emul"; };
+inline const char *cudaGetErrorString(cudaError_t e) { return e ? "emulated error" : "no error"; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp(); if (const char *s = getenv("KR_EMUL_SMS")) p->multiProcessorCount = atoi(s); return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new CUstream_st{0}; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new CUevent_st(); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t *p, int) { *p = 0; return cudaSuccess; }
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+// allocations are 256-byte aligned like cudaMalloc's and poisoned so that reads of uninitialised device memory show
+inline cudaError_t cudaMalloc(void **p, size_t n) { if (posix_memalign(p, 256, n ? n : 1)) return cudaErrorEmul; memset(*p, 0xCD, n); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
+inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorEmul; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { return cudaMemset(d, v, n); }

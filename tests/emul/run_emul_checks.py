@@ -1,0 +1,202 @@
+"""TEST INFRASTRUCTURE: runs the product's device + host code on the CPU emulator (tests/emul/cuda_emul.h) and
+compares with the oracle.  Started by tests/test_emul_device_code.py in a subprocess with KR_LIB_PATH pointing at
+tests/emul/_build/libkmersreps_emul.so (the product sources compiled by g++ with -DKR_EMUL -DKR_EXPERIMENTAL).
+
+    python tests/emul/run_emul_checks.py <case>
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import kmers.reps_b200 as kr                      # noqa: E402
+from kmers.reps_b200 import binding, synth        # noqa: E402
+from oracle import kr_oracle as ko                # noqa: E402
+
+assert "libkmersreps_emul" in kr.lib_path(), "these checks are for the emulator build only"
+O = ko.get()
+
+
+def family(seed, n, nfam, lo=None, hi=None):
+    res, off, _ = synth.generate(seed, n, nfam)
+    seqs = synth.to_strings(res, off)
+    if lo is not None:                                # trim to keep the emulated kernels quick
+        rng = np.random.default_rng(seed)
+        seqs = [s[: int(rng.integers(lo, hi))] for s in seqs]
+    return seqs
+
+
+def blocktri(full):
+    n = full.shape[0]
+    return np.concatenate([full[i, 256 * (i // 256):] for i in range(n)])
+
+
+def cells(arr):
+    return {(int(r), int(c), int(v)) for r, c, v, _ in arr}
+
+
+def want_cells(dense, min_sim, triangle, row0=0):
+    ii, jj = np.nonzero(dense >= min_sim)
+    return {(int(i) + row0, int(j), int(dense[i, j])) for i, j in zip(ii, jj) if not triangle or j > i + row0}
+
+
+def case_matrix_layouts():
+    """encode + block lists + TMA-staged tile join: every layout / element type, two blocks, the equal-sequence rule"""
+    seqs = family(11, 300, 6, 60, 140) + ["MKV", "", "MKVLAAGIVG", "MKVLAAGIVG"]
+    seqs[7] = seqs[290]                               # equal sequences in different blocks
+    for ident in (kr.IDENT_IS_INFINITY, 0):
+        want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=bool(ident), threads=4)
+        c = kr.Context(device=0, K=8, flags=ident)
+        s = c.encode(seqs)
+        assert (s.sizes() == O.batch(seqs, K=8).sizes()).all()
+        assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all()
+        assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE) == want[np.triu_indices(len(seqs), 1)]).all()
+        assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all()
+        hi = c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_BLOCKTRI, row_begin=256, row_end=len(seqs))
+        assert (hi == blocktri(want)[-len(hi):]).all()
+        c.close()
+
+
+def case_k10_rectangular_pairs():
+    """32-bit low words (K = 10, three pipeline stages), rectangular matrix, explicit pairs, key decoding"""
+    seqs = family(12, 90, 3, 50, 120)
+    c = kr.Context(device=0, K=10, flags=0)
+    a, b = c.encode(seqs[:40]), c.encode(seqs[30:])
+    oa, ob = O.batch(seqs[:40], K=10), O.batch(seqs[30:], K=10)
+    assert (c.sim_matrix(a, b) == O.sim_matrix(oa, ob, ident_inf=False)).all()
+    ia, ib = np.arange(40, dtype=np.uint32), np.arange(40, dtype=np.uint32)[::-1].copy()
+    sim, ident = c.sim_pairs(a, ia, b, ib)
+    full = O.sim_matrix(oa, ob, ident_inf=False)
+    assert (sim == full[ia, ib]).all()
+    assert sorted(a.kmers(3)) == sorted(ko.py_kmers(seqs[3], 10))
+    c.close()
+
+
+def case_find_closest_and_build():
+    """ARGMAX join, inverted index (forced), ranks / ties, greedy build with database compaction"""
+    seqs = family(13, 330, 8, 60, 130)
+    reps, qs = seqs[:270], seqs[270:] + [seqs[5], "MKV"]
+    ob, oq = O.batch(reps, K=8), O.batch(qs, K=8)
+    rng = np.random.default_rng(3)
+    rank = rng.permutation(len(reps)).astype(np.uint32)
+    order = np.argsort(rank)
+    bs, bi = O.find_closest(ob, oq, order=order.astype(np.int32), ident_inf=True)
+    for force in (kr.FORCE_JOIN, kr.FORCE_INDEX):
+        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | force)
+        db = c.db()
+        db.append(reps[:100]); db.append(reps[100:])
+        db.set_ranks(rank)
+        sim, first, last = db.find_closest(c.encode(qs))
+        assert (sim == bs).all(), force
+        assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), force
+        c.close()
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    db = c.db()
+    added = db.greedy_build(c.encode(seqs), 30, batch=40)      # many small segments: db_compact runs
+    _, want, _ = O.greedy_build(O.batch(seqs, K=8), 30, ident_inf=True)
+    assert (added == want).all() and db.size == int(want.sum())
+    c.close()
+
+
+def case_subchunks():
+    """key-range chunks longer than one pipeline stage (2040 entries): several (A sub-chunk x B sub-chunk) jobs"""
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    roots = [alpha[rng.integers(0, 20, 900)] for _ in range(4)]
+    seqs = []
+    for i in range(262):
+        s = roots[i % 4].copy()
+        pos = rng.integers(0, 900, 20 + 15 * (i % 5))
+        s[pos] = alpha[rng.integers(0, 20, len(pos))]
+        seqs.append(s[: int(rng.integers(700, 901))].tobytes().decode())
+    assert np.mean([len(s) for s in seqs]) * 256 / 64 > 2200
+    want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=True, threads=8)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    s = c.encode(seqs)
+    assert (c.sim_matrix(s, elem=kr.ELEM_U16) == want).all()
+    db = c.db()
+    db.append(seqs[:250])
+    sim, first, _ = db.find_closest(c.encode(seqs[250:]))
+    bs, bi = O.find_closest(O.batch(seqs[:250], K=8), O.batch(seqs[250:], K=8))
+    assert (sim == bs).all() and (first == bi).all()
+    c.close()
+
+
+def case_sharded_import():
+    """export / import of block lists (the N > 1 encode): two and three shards re-assembled into one set"""
+    seqs = family(14, 700, 9, 40, 90)
+    res, off = kr.flat(seqs)
+    want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=True, threads=4)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    from kmers.reps_b200 import sharding
+    for world in (2, 3):
+        cuts = sharding.block_shards(len(seqs), world)
+        parts, shards = [], []
+        for k in range(world):
+            lo, hi = cuts[k], cuts[k + 1]
+            p = c.encode_device(res.ctypes.data, off[lo: hi + 1])          # "device" memory is host memory here
+            parts.append(p)
+            bl = c.export_blocklists(p)
+            assert bl.entries <= c.blocklist_capacity(off[lo: hi + 1])
+            shards.append(bl)
+        full = c.import_blocklists(shards, res.ctypes.data, off)
+        got = c.sim_matrix(full, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI)
+        assert (got == blocktri(want)).all(), world
+    c.close()
+
+
+def case_exp_sparse_join():
+    """EXPERIMENTAL: sparse result from the join's epilogue filter"""
+    seqs = family(15, 300, 6, 60, 120)
+    seqs[5] = seqs[280] = "MKV"
+    want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=True, threads=4)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    s = c.encode(seqs)
+    for min_sim in (1, 20, 9999):
+        got = c.sim_matrix_sparse(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
+        assert len(cells(got)) == len(got) and cells(got) == want_cells(want, min_sim, True)
+    got = c.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, cap=16)       # too little room: retried
+    assert cells(got) == want_cells(want, 1, True)
+    q = c.encode(seqs[:290])
+    got = c.sim_matrix_sparse(q, s, min_sim=10, layout=kr.LAYOUT_FULL, row_begin=256, row_end=290)
+    assert cells(got) == want_cells(want[256:290], 10, False, row0=256)
+    c.close()
+
+
+def case_exp_pairs():
+    """EXPERIMENTAL: posting-list all-vs-all (dense, every layout) and the pair-table sparse result, end to end"""
+    seqs = family(16, 300, 6, 60, 120) + ["MKV", "", "MKVLAAGIVG", "MKVLAAGIVG", "MKV"]
+    seqs[7] = seqs[290]
+    n = len(seqs)
+    for ident in (kr.IDENT_IS_INFINITY, 0):
+        want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=bool(ident), threads=4)
+        for mode in (binding.EXP_PAIRS, binding.EXP_PAIRS_AUTO):
+            c = kr.Context(device=0, K=8, flags=ident | mode)
+            s = c.encode(seqs)
+            assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all()
+            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE) == want[np.triu_indices(n, 1)]).all()
+            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all()
+            lo = c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=0, row_end=256)
+            hi = c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=256, row_end=n)
+            assert (np.concatenate([lo, hi]) == blocktri(want)).all()
+            if ident:
+                for min_sim in (1, 15):
+                    got = c.sim_matrix_sparse(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
+                    assert len(cells(got)) == len(got) and cells(got) == want_cells(want, min_sim, True)
+                got = c.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=256, row_end=n)
+                assert cells(got) == want_cells(want[256:], 1, True, row0=256)
+                db = c.db()
+                added = db.greedy_build(s, 30, batch=64)                 # survivor matrices through the same path
+                _, w2, _ = O.greedy_build(O.batch(seqs, K=8), 30, ident_inf=True)
+                assert (added == w2).all()
+            c.close()
+
+
+CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
+
+if __name__ == "__main__":
+    name = sys.argv[1]
+    CASES[name]()
+    print("OK", name)

