@@ -5,6 +5,8 @@
 #include "kr_kernels.cuh"
 #ifdef KR_EXPERIMENTAL
 #include "kr_pairs.cuh"
+#include "kr_encode2.cuh"
+#define KR_EXP_ENCODE 0x400u       /* context flag (experimental builds): K1 with one warp per sequence */
 #define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
 #define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
 #endif
@@ -384,6 +386,11 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
         p.err = ctx->d_err; p.nseq = nseq; p.K = K; p.smem_cap = 2048;
         // proteins are a few hundred residues: one 128-thread CTA sorts up to 2048 keys in 16 KB of shared
         // memory; longer sequences (rare) sort in place in global memory inside the same kernel
+#ifdef KR_EXPERIMENTAL
+        if ((ctx->flags & KR_EXP_ENCODE) && maxn <= 512) KR_LAUNCH(KR_T(k_encode_sort_warp<16>), (nseq + ENC2_WARPS - 1) / ENC2_WARPS, ENC2_WARPS * 32, 0, ctx->stream, p);
+        else if (ctx->flags & KR_EXP_ENCODE) KR_LAUNCH(KR_T(k_encode_sort_warp<32>), (nseq + ENC2_WARPS - 1) / ENC2_WARPS, ENC2_WARPS * 32, 0, ctx->stream, p);
+        else
+#endif
         KR_LAUNCH(KR_T(k_encode_sort<128>), nseq, 128, p.smem_cap * 8 + p.smem_cap + 16, ctx->stream, p);
         LAUNCHED(ctx);
         CU(cudaGetLastError());

@@ -1,0 +1,187 @@
+// kr_encode2.cuh -- EXPERIMENTAL (compiled only with -DKR_EXPERIMENTAL; checked on the CPU emulator, unverified on
+// hardware when written): K1 with one WARP per sequence.
+//
+// k_encode_sort gives a whole 128-thread CTA to one sequence and sorts its ~300 keys with ~45 barrier-separated
+// bitonic stages in shared memory (15 ns per sequence at 100k).  A seed protein has at most a few hundred k-mers, so
+// here a warp keeps them in registers -- R consecutive elements per lane, R = 2..32 chosen from the sequence length --
+// and runs the same network with register compare-exchanges for strides below R and warp shuffles for the rest: no
+// block barrier, no shared-memory traffic in the sort, four sequences per CTA in flight.  Sequences with more than
+// 1024 k-mers (rare) are sorted in place in global memory by their warp.
+// Output is identical to k_encode_sort's: sorted distinct keys, size, length, the same 64-bit hash, the error flag.
+#pragma once
+#include "kr_kernels.cuh"
+
+namespace kr {
+
+constexpr int ENC2_WARPS = 4;                    // sequences in flight per CTA
+constexpr u32 ENC2_MAXREG = 32;                  // keys per lane at most: sequences up to 1024 k-mers stay in registers
+constexpr u32 ENC2_CODES = 32 * ENC2_MAXREG + 16;   // residue codes staged per warp
+// The kernel is compiled for two register budgets: MAXR = 16 (batches whose longest sequence has <= 512 k-mers: every
+// seed-protein batch) keeps the register count low enough for 16 warps per SM; MAXR = 32 is picked by the host only
+// when a batch holds longer sequences.
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
+    const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)v, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(v >> 32), m);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_up_u64(u64 v, unsigned d) {
+    const u32 lo = __shfl_up_sync(0xffffffffu, (u32)v, d), hi = __shfl_up_sync(0xffffffffu, (u32)(v >> 32), d);
+    return ((u64)hi << 32) | lo;
+}
+
+// ascending bitonic sort of 32*R elements, element e = lane*R + t held in reg[t] of `lane`
+template <int R>
+__device__ __forceinline__ void warp_bitonic(u64 (&reg)[R], u32 lane) {
+    constexpr int P = 32 * R;
+#pragma unroll
+    for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= R) {
+                const int lm = j / R;                                   // partner lane = lane ^ lm, same register
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const u64 other = shfl_xor_u64(reg[t], lm);
+                    const u32 e = lane * R + t;
+                    const bool up = (e & (u32)k) == 0 || k == P;        // direction of this element's k-block
+                    const bool low = (lane & (u32)lm) == 0;             // this lane holds the lower index of the pair
+                    const bool take_min = (low == up);
+                    const u64 mn = reg[t] < other ? reg[t] : other, mx = reg[t] < other ? other : reg[t];
+                    reg[t] = take_min ? mn : mx;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    if ((t & j) == 0) {
+                        const u32 e = lane * R + t;
+                        const bool up = (e & (u32)k) == 0 || k == P;
+                        const u64 a = reg[t], b = reg[t | j];
+                        const bool sw = up ? (b < a) : (a < b);
+                        reg[t] = sw ? b : a; reg[t | j] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// keys of one sequence from its staged codes -> sorted distinct keys at dst; returns their number (all lanes)
+template <int R>
+__device__ __forceinline__ u32 warp_encode_sort(const u8 *codes, u32 n, int K, u64 *dst, u32 lane) {
+    u64 reg[R];
+    const u64 mask = (K * 5 >= 64) ? ~0ull : ((1ull << (5 * K)) - 1);
+    {
+        const u32 e0 = lane * R;
+        u64 key = 0;
+        if (e0 < n) for (int t = 0; t < K - 1; ++t) key = (key << 5) | (u64)(codes[e0 + t] & 31);
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const u32 e = e0 + t;
+            if (e < n) { key = ((key << 5) | (u64)(codes[e + K - 1] & 31)) & mask; reg[t] = key; }
+            else reg[t] = SENT;
+        }
+    }
+    warp_bitonic<R>(reg, lane);
+    // distinct keys: an element counts when it differs from its predecessor (lane - 1's last register for t = 0)
+    u64 prev = shfl_up_u64(reg[R - 1], 1);
+    u32 flags = 0;
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+        const u64 v = reg[t];
+        const bool first = (lane == 0 && t == 0);
+        if (v != SENT && (first || v != prev)) flags |= 1u << t;
+        prev = v;
+    }
+    const u32 c = __popc(flags);
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += up; }
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    u32 pos = incl - c;
+#pragma unroll
+    for (int t = 0; t < R; ++t) if ((flags >> t) & 1u) dst[pos++] = reg[t];
+    return total;
+}
+
+// in-place bitonic sort in (global) memory by one warp: the slow path of sequences longer than the register budget
+__device__ __forceinline__ void bitonic_sort_warp_mem(u64 *d, u32 n, u32 lane) {
+    if (n < 2) return;
+    const u32 lp = 32 - __clz((int)(n - 1)), halfP = 1u << (lp - 1);
+    for (u32 lk = 1; lk <= lp; ++lk) {
+        const u32 lh = lk - 1;
+        for (u32 t = lane; t < halfP; t += 32) {
+            const u32 g = t >> lh, r = t & ((1u << lh) - 1);
+            const u32 i = (g << lk) + r, j = (g << lk) + ((1u << lk) - 1 - r);
+            if (j < n) cmpswap(d, i, j);
+        }
+        __syncwarp();
+        for (int lj = (int)lh - 1; lj >= 0; --lj) {
+            for (u32 t = lane; t < halfP; t += 32) {
+                const u32 i = ((t >> lj) << (lj + 1)) + (t & ((1u << lj) - 1)), j = i + (1u << lj);
+                if (j < n) cmpswap(d, i, j);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int MAXR>
+__global__ void __launch_bounds__(ENC2_WARPS * 32) k_encode_sort_warp(EncodeParams p) {
+    __shared__ u8 s_codes[ENC2_WARPS][ENC2_CODES];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 s = blockIdx.x * ENC2_WARPS + warp;
+    if (s >= p.nseq) return;                                   // whole warps leave together
+    const u8 *r = p.res + p.off[s];
+    const u32 L = (u32)(p.off[s + 1] - p.off[s]);
+    const int K = p.K;
+    const u32 n = L >= (u32)K ? L - K + 1 : 0;
+    u64 *dst = p.keys + p.koff[s];
+    u8 *codes = s_codes[warp];
+    const bool in_regs = n <= 32u * MAXR;
+    u64 h = 0;
+    for (u32 i = lane; i < L; i += 32) {
+        const u32 c = r[i];
+        const u32 code = residue_code(c);
+        if (code == 0xFFu && atomicCAS(&p.err->flag, 0u, 1u) == 0u) { p.err->seq = s; p.err->pos = i; p.err->byte = c; }
+        if (in_regs) codes[i] = (u8)code;
+        h += mix64((((u64)i << 8) | c) + 0x9E3779B97F4A7C15ULL);
+    }
+    for (int o = 16; o > 0; o >>= 1) h += shfl_xor_u64(h, o);
+    __syncwarp();
+    u32 size;
+    if (in_regs) {
+        if (n <= 64) size = warp_encode_sort<2>(codes, n, K, dst, lane);
+        else if (n <= 128) size = warp_encode_sort<4>(codes, n, K, dst, lane);
+        else if (n <= 256) size = warp_encode_sort<8>(codes, n, K, dst, lane);
+        else if (n <= 512 || MAXR < 32) size = warp_encode_sort<16>(codes, n, K, dst, lane);
+        else size = warp_encode_sort<(MAXR < 32 ? 16 : 32)>(codes, n, K, dst, lane);
+    } else {
+        for (u32 i = lane; i < n; i += 32) {
+            u64 key = 0;
+            for (int t = 0; t < K; ++t) key = (key << 5) | (u64)(residue_code(r[i + t]) & 31);
+            dst[i] = key;
+        }
+        __syncwarp();
+        bitonic_sort_warp_mem(dst, n, lane);
+        // compact the distinct keys in place, 32 at a time (an output index never exceeds its input index)
+        u32 out = 0; u64 last = SENT;
+        for (u32 base = 0; base < n; base += 32) {
+            const u32 i = base + lane;
+            const bool valid = i < n;
+            const u64 v = valid ? dst[i] : SENT;
+            u64 pv = shfl_up_u64(v, 1);
+            if (lane == 0) pv = last;
+            const bool flag = valid && (i == 0 || v != pv);
+            const u32 bal = __ballot_sync(0xffffffffu, flag);
+            last = __shfl_sync(0xffffffffu, (u32)v, 31) | ((u64)__shfl_sync(0xffffffffu, (u32)(v >> 32), 31) << 32);   // lane 31's value
+            __syncwarp();                                       // every read of this group is done before the writes
+            if (flag) dst[out + __popc(bal & ((1u << lane) - 1))] = v;
+            out += __popc(bal);
+            __syncwarp();
+        }
+        size = out;
+    }
+    if (lane == 0) { SeqMeta m; m.size = size; m.len = L; m.hash = h; m.res = r; p.meta[s] = m; }
+}
+
+}  // namespace kr

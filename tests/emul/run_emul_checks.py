@@ -194,6 +194,42 @@ def case_exp_pairs():
             c.close()
 
 
+def case_exp_encode_warp():
+    """EXPERIMENTAL: K1 with one warp per sequence (register bitonic network): every register budget, the in-memory path
+    for very long sequences, repeats, all K"""
+    rng = np.random.default_rng(9)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX*-", dtype=np.uint8)
+    lens = [0, 1, 7, 8, 9, 40, 70, 71, 72, 73, 135, 136, 137, 263, 264, 265, 300, 519, 520, 521, 800, 1031, 1032, 1033, 1100, 2500]
+    seqs = [alpha[rng.integers(0, len(alpha), n)].tobytes().decode() for n in lens]
+    seqs += ["A" * 50, "AC" * 200, "ACDEFGHIK" * 130, seqs[10], seqs[24]]            # repeats (few distinct k-mers), duplicates
+    seqs += family(17, 40, 3, 200, 420)
+    for K in (8, 3, 11):
+        ob = O.batch(seqs, K=K)
+        want = O.sim_matrix(ob, ident_inf=True, threads=4)
+        c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY | binding.EXP_ENCODE)
+        s = c.encode(seqs)
+        assert (s.sizes() == ob.sizes()).all(), K
+        ref = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY)
+        s0 = ref.encode(seqs)
+        for i in range(len(seqs)):
+            assert (s.keys(i) == s0.keys(i)).all(), (K, i)
+        assert (c.sim_matrix(s, elem=kr.ELEM_U16) == want).all(), K                # equal-sequence rule: same hashes
+        c.close(); ref.close()
+    short = [q for q in seqs if len(q) <= 500]                                     # batch served by the 16-register build
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_ENCODE)
+    s = c.encode(short)
+    assert (s.sizes() == O.batch(short, K=8).sizes()).all()
+    assert (c.sim_matrix(s, elem=kr.ELEM_U16) == O.sim_matrix(O.batch(short, K=8), ident_inf=True, threads=4)).all()
+    c.close()
+    c = kr.Context(device=0, K=8, flags=binding.EXP_ENCODE)
+    try:
+        c.encode(["MKVLAAGIVG", "MKVLAbGIVGAAAA"])
+        raise AssertionError("a residue outside the alphabet must fail")
+    except kr.KrError as e:
+        assert e.code == -4 and "sequence 1 position 5" in str(e)
+    c.close()
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":
