@@ -278,6 +278,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exp-pairs", action="store_true",
                     help="EXPERIMENTAL library only: all-vs-all through the posting-list path (context flag EXP_PAIRS)")
+    ap.add_argument("--exp-encode", action="store_true", help="EXPERIMENTAL library only: K1 with one warp per sequence (EXP_ENCODE)")
     ap.add_argument("--sparse-e2e", action="store_true",
                     help="EXPERIMENTAL library only (KR_LIB_PATH=.../libkmersreps_cuda_exp.so): also time the e2e path that returns only "
                          "the cells with sim >= 1 (kr_sim_matrix_sparse) and report it as e2e_sparse")
@@ -307,9 +308,10 @@ def main():
     res, off, nfam = workload(args.nseq)
     N = args.nseq
     from kmers.reps_b200 import binding
-    if args.exp_pairs and not binding.has_experimental():
-        raise SystemExit("--exp-pairs needs KR_LIB_PATH to point at libkmersreps_cuda_exp.so")
-    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | (binding.EXP_PAIRS if args.exp_pairs else 0))
+    if (args.exp_pairs or args.exp_encode) and not binding.has_experimental():
+        raise SystemExit("--exp-pairs / --exp-encode need KR_LIB_PATH to point at libkmersreps_cuda_exp.so")
+    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | (binding.EXP_PAIRS if args.exp_pairs else 0)
+                     | (binding.EXP_ENCODE if args.exp_encode else 0))
     elem = kr.ELEM_U16 if args.elem == "u16" else kr.ELEM_I32
     esz = 2 if elem == kr.ELEM_U16 else 4
     layout = kr.LAYOUT_BLOCKTRI

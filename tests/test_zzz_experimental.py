@@ -93,3 +93,23 @@ def test_posting_list_path_in_greedy_build_and_short_sequences(oracle):
     _, want, _ = oracle.greedy_build(ob, 50, ident_inf=True)
     assert (added == want).all()
     c.close()
+
+
+def test_warp_per_sequence_encode_equals_cta_encode(oracle, rep50, vapb):
+    """EXP_ENCODE (K1 with one warp per sequence) against the default K1 and the oracle: real and synthetic sets, very
+    long sequences (in-memory path), all K"""
+    rng = np.random.default_rng(4)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX*-", dtype=np.uint8)
+    longs = [alpha[rng.integers(0, len(alpha), n)].tobytes().decode() for n in (519, 520, 1031, 1032, 1040, 5000, 30000)]
+    res, off, _ = synth.generate(0x5EED000B, 5000, 80)
+    for seqs in ([s for (_, _, s) in rep50["reps"]], [s for (_, _, s) in vapb] + longs + ["", "MKV", "A" * 400], synth.to_strings(res, off)):
+        for K in (8, 5, 11):
+            c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY | binding.EXP_ENCODE)
+            ref = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY)
+            s, s0 = c.encode(seqs), ref.encode(seqs)
+            assert (s.sizes() == s0.sizes()).all() and (s.sizes() == oracle.batch(seqs, K=K).sizes()).all()
+            for i in rng.choice(len(seqs), min(len(seqs), 200), replace=False):
+                assert (s.keys(int(i)) == s0.keys(int(i))).all()
+            if len(seqs) <= 1500 and K == 8:
+                assert (c.sim_matrix(s, elem=kr.ELEM_U16) == ref.sim_matrix(s0, elem=kr.ELEM_U16)).all()
+            c.close(); ref.close()
