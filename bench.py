@@ -161,7 +161,11 @@ def run_findclosest(args, rank, world, local):
     t0 = time.perf_counter()
     res, off, fam = synth.generate(0x5EED0005, ncand + nq, max(1, ncand // 50), xrun_per_10k=10)
     gen_s = time.perf_counter() - t0
-    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY)
+    from kmers.reps_b200 import binding
+    exp = (binding.EXP_ENCODE if args.exp_encode else 0) | (binding.EXP_IDXQ if args.exp_idxq else 0)
+    if exp and not binding.has_experimental():
+        raise SystemExit("--exp-* flags need KR_LIB_PATH to point at libkmersreps_cuda_exp.so")
+    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | exp)
     # ---- config 4: greedy build (replicated on every rank: the accept/reject sweep is sequential) ----
     cands = ctx.encode(res=res[: int(off[ncand])], off=off[: ncand + 1])
     db = ctx.db()
@@ -279,6 +283,7 @@ def main():
     ap.add_argument("--exp-pairs", action="store_true",
                     help="EXPERIMENTAL library only: all-vs-all through the posting-list path (context flag EXP_PAIRS)")
     ap.add_argument("--exp-encode", action="store_true", help="EXPERIMENTAL library only: K1 with one warp per sequence (EXP_ENCODE)")
+    ap.add_argument("--exp-idxq", action="store_true", help="EXPERIMENTAL library only: K5 with one warp per query (EXP_IDXQ; findclosest workload)")
     ap.add_argument("--sparse-e2e", action="store_true",
                     help="EXPERIMENTAL library only (KR_LIB_PATH=.../libkmersreps_cuda_exp.so): also time the e2e path that returns only "
                          "the cells with sim >= 1 (kr_sim_matrix_sparse) and report it as e2e_sparse")

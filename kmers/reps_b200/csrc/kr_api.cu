@@ -7,6 +7,8 @@
 #include "kr_pairs.cuh"
 #include "kr_encode2.cuh"
 #define KR_EXP_ENCODE 0x400u       /* context flag (experimental builds): K1 with one warp per sequence */
+#include "kr_idxq2.cuh"
+#define KR_EXP_IDXQ 0x800u         /* context flag (experimental builds): K5 with one warp per query where it pays */
 #define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
 #define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
 #endif
@@ -91,6 +93,9 @@ struct DbSegment { kr_seqset *set; u32 base; };
 struct DbIndexSlab {   // inverted index over representatives [base, base + n)
     u32 base = 0, n = 0, mask = 0;
     unsigned long long *tab_key = nullptr; u32 *tab_off = nullptr, *tab_cnt = nullptr, *postings = nullptr;
+#ifdef KR_EXPERIMENTAL
+    uint4 *packed = nullptr; u64 entries = 0; unsigned long long nonempty = 0;   // packed slots for k_idx_query_warp
+#endif
 };
 struct kr_db {
     kr_ctx *ctx = nullptr;
@@ -223,6 +228,7 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
 #ifdef KR_EXPERIMENTAL
     CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
     CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
+    CUC(cudaFuncSetAttribute(k_idx_query_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDXQ2_DENSE_MAX * 2 * IDXQ2_WARPS + 256)));
 #endif
 #undef CUC
     *out = ctx;
@@ -666,7 +672,12 @@ static void db_free_arrays(kr_db *db) {
 // (re)build the database-wide meta / block-ref / rank arrays after a change
 static void db_free_index(kr_db *db) {
     kr_ctx *ctx = db->ctx;
-    for (auto &sl : db->slabs) { dfree(ctx, sl.tab_key); dfree(ctx, sl.tab_off); dfree(ctx, sl.tab_cnt); dfree(ctx, sl.postings); }
+    for (auto &sl : db->slabs) {
+        dfree(ctx, sl.tab_key); dfree(ctx, sl.tab_off); dfree(ctx, sl.tab_cnt); dfree(ctx, sl.postings);
+#ifdef KR_EXPERIMENTAL
+        dfree(ctx, sl.packed);
+#endif
+    }
     db->slabs.clear();
     dfree(ctx, db->d_empty_reps); db->d_empty_reps = nullptr; db->nempty = 0;
     db->index_ready = false;
@@ -811,6 +822,19 @@ static kr_status db_build_index(kr_ctx *ctx, kr_db *db) {
         }
         CU(cudaGetLastError());
         dfree(ctx, d_cur); dfree(ctx, d_sums);
+#ifdef KR_EXPERIMENTAL
+        if (ctx->flags & KR_EXP_IDXQ) {   // packed slots + the number of distinct keys (mean posting length picks the query kernel)
+            unsigned long long *d_ne = nullptr;
+            CU(dalloc(ctx, &sl.packed, cap)); CU(dalloc(ctx, &d_ne, 1));
+            CU(cudaMemsetAsync(d_ne, 0, 8, ctx->stream));
+            KR_LAUNCH(KR_T(k_idx_pack), ctx->num_sms * 8, 256, 0, ctx->stream, sl.tab_key, sl.tab_off, sl.tab_cnt, cap, sl.packed, d_ne);
+            LAUNCHED(ctx);
+            CU(cudaMemcpyAsync(&sl.nonempty, d_ne, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            dfree(ctx, d_ne);
+            sl.entries = entries;
+        }
+#endif
         db->slabs.push_back(sl);
     }
     // representatives without any k-mer (shorter than K): only the equal-sequence rule can match them
@@ -843,6 +867,20 @@ static kr_status find_closest_index(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *d
             p.tab_key = sl.tab_key; p.tab_off = sl.tab_off; p.tab_cnt = sl.tab_cnt; p.mask = sl.mask; p.postings = sl.postings;
             p.rmeta = db->d_meta; p.rank = db->d_rank; p.slab_base = sl.base; p.slab_n = sl.n; p.flags = ctx->flags;
             p.partial = d_partial + (size_t)k * Q->n; p.next = d_next + k;
+#ifdef KR_EXPERIMENTAL
+            // one warp per query where a query touches few representatives: small slabs (dense per-warp scores) or short
+            // posting lists (per-warp hash); otherwise the CTA-per-query kernel with its slab-wide score array
+            if (sl.packed && (sl.n <= IDXQ2_DENSE_MAX || sl.entries <= 8 * sl.nonempty)) {
+                IdxQuery2Params pp{p, sl.packed};
+                const bool dense = sl.n <= IDXQ2_DENSE_MAX;
+                const size_t words = dense ? (((size_t)sl.n + 1) / 2 + 3) / 4 * 4 : IDXQ2_HASH;
+                const u32 grid2 = std::min<u32>((Q->n + IDXQ2_WARPS - 1) / IDXQ2_WARPS, (u32)ctx->num_sms * (dense ? 3 : 6));
+                if (dense) KR_LAUNCH(KR_T(k_idx_query_warp<true>), grid2, IDXQ2_WARPS * 32, words * 4 * IDXQ2_WARPS, ctx->stream, pp);
+                else KR_LAUNCH(KR_T(k_idx_query_warp<false>), grid2, IDXQ2_WARPS * 32, words * 4 * IDXQ2_WARPS, ctx->stream, pp);
+                LAUNCHED(ctx); ctx->st.join_launches++;
+                continue;
+            }
+#endif
             u32 grid = std::min<u32>(Q->n, 2 * (u32)ctx->num_sms);
             KR_LAUNCH(KR_T(k_idx_query), grid, IDX_THREADS, ((size_t)sl.n + 1) / 2 * 4, ctx->stream, p);
             LAUNCHED(ctx); ctx->st.join_launches++;

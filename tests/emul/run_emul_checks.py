@@ -230,6 +230,44 @@ def case_exp_encode_warp():
     c.close()
 
 
+def case_exp_idxq_warp():
+    """EXPERIMENTAL: K5 with one warp per query -- dense per-warp scores (small database), per-warp hash (large database,
+    short posting lists), and the multi-pass path of a query that touches more representatives than the hash holds"""
+    rng = np.random.default_rng(21)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    rnd = lambda n: alpha[rng.integers(0, 20, n)].tobytes().decode()
+    # (a) dense: a family-structured database of 300, ties and ranks, identical and k-mer-less queries
+    seqs = family(18, 340, 8, 60, 130)
+    reps, qs = seqs[:300], seqs[300:] + [seqs[5], "MKV", ""]
+    reps[20] = "MKV"
+    rank = rng.permutation(len(reps)).astype(np.uint32)
+    bs, bi = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(rank).astype(np.int32), ident_inf=True)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_INDEX | binding.EXP_IDXQ)
+    db = c.db(); db.append(reps); db.set_ranks(rank)
+    sim, first, last = db.find_closest(c.encode(qs))
+    assert (sim == bs).all() and (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
+    bs2, bl2 = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(rank).astype(np.int32), ident_inf=True, tie_last=True)
+    assert (last.astype(np.int64) == np.where(bs2 > 0, bl2.astype(np.int64), kr.NO_REP)).all()
+    c.close()
+    # (b) hash: 4,300 short representatives (> IDXQ2_DENSE_MAX), 1,150 of which share one 8-mer with the hub queries
+    hub = "MKVLAAGI"
+    reps = [rnd(24) for _ in range(3150)] + [rnd(8) + hub + rnd(8) for _ in range(1150)]
+    fam = [reps[i][:12] + rnd(6) + reps[i][18:] for i in (5, 17, 3300, 4000)]          # near copies: clear best matches
+    qs = fam + [rnd(10) + hub + rnd(10), hub, reps[77], rnd(30), reps[3200][8:16] + rnd(5)]
+    order = rng.permutation(len(reps)).astype(np.uint32)
+    bs, bi = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(order).astype(np.int32), ident_inf=True, threads=4)
+    bs2, bl2 = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(order).astype(np.int32), ident_inf=True, tie_last=True, threads=4)
+    for flags in (binding.EXP_IDXQ, 0):                                              # 0: the CTA kernel, same expectations
+        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_INDEX | flags)
+        db = c.db(); db.append(reps); db.set_ranks(order)
+        sim, first, last = db.find_closest(c.encode(qs))
+        assert (sim == bs).all(), flags
+        assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), flags
+        assert (last.astype(np.int64) == np.where(bs2 > 0, bl2.astype(np.int64), kr.NO_REP)).all(), flags
+        c.close()
+    assert bs[5] == 1 and bi[5] != bl2[5], (bs, bi, bl2)                             # the hub query ties over 1,150 representatives
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -113,3 +113,31 @@ def test_warp_per_sequence_encode_equals_cta_encode(oracle, rep50, vapb):
             if len(seqs) <= 1500 and K == 8:
                 assert (c.sim_matrix(s, elem=kr.ELEM_U16) == ref.sim_matrix(s0, elem=kr.ELEM_U16)).all()
             c.close(); ref.close()
+
+
+def test_warp_per_query_index_equals_cta_index(oracle, rep50, gto_seeds, rickettsia):
+    """EXP_IDXQ (K5 with one warp per query): dense per-warp scores on rep50.db, the per-warp hash on a 60,000-rep
+    synthetic database (two slabs), against the default index kernel and the oracle"""
+    reps = [s for (_, _, s) in rep50["reps"]]
+    qs = [s for (_, _, s) in gto_seeds] + [p for (_, p) in rickettsia] + reps[:50] + ["MKV", ""]
+    rng = np.random.default_rng(8)
+    rank = rng.permutation(len(reps)).astype(np.uint32)
+    out = []
+    for flags in (binding.EXP_IDXQ, 0):
+        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_INDEX | flags)
+        db = c.db(); db.append(reps); db.set_ranks(rank)
+        out.append(db.find_closest(c.encode(qs)))
+        c.close()
+    for a, b in zip(*out):
+        assert (a == b).all()
+    bs, bi = oracle.find_closest(oracle.batch(reps, K=8), oracle.batch(qs, K=8), order=np.argsort(rank).astype(np.int32), ident_inf=True, threads=8)
+    assert (out[0][0] == bs).all() and (out[0][1].astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
+    res, off, _ = synth.generate(0x5EED000C, 90000, 1500)
+    out = []
+    for flags in (binding.EXP_IDXQ, 0):
+        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_INDEX | flags)
+        db = c.db(); db.append(res=res[: int(off[60000])], off=off[:60001])
+        out.append(db.find_closest(c.encode(res=res[int(off[60000]):], off=off[60000:] - off[60000])))
+        c.close()
+    for a, b in zip(*out):
+        assert (a == b).all()
