@@ -331,7 +331,10 @@ def main():
     def step():
         # N>1: each rank encodes 1/N of the sequences and the block lists are all-gathered over NVLink (the one
         # exchange step of the path); N=1 or --replicated-encode: every rank encodes everything
-        s = sharding.encode_sharded(ctx, d_res, off, dist) if sharded_encode else ctx.encode_device(d_res.data_ptr(), off)
+        if sharded_encode and args.exp_pairs:      # the posting-list path needs key lists: exchange those instead of block lists
+            s = sharding.encode_sharded_keys(ctx, d_res, off, dist)
+        else:
+            s = sharding.encode_sharded(ctx, d_res, off, dist) if sharded_encode else ctx.encode_device(d_res.data_ptr(), off)
         ctx.sim_matrix_device(s, None, d_out.data_ptr(), elem=elem, layout=layout, row_begin=r0, row_end=r1)
         return s
 
@@ -347,7 +350,7 @@ def main():
             prev.free()
         prev = cur
     ctx.synchronize()
-    if sharded_encode:   # an imported set has no per-sequence arrays to ask for sizes: encode once more, plainly
+    if sharded_encode and not args.exp_pairs:   # a set imported from block lists has no per-sequence arrays: encode once more, plainly
         tmp = ctx.encode_device(d_res.data_ptr(), off)
         sizes = tmp.sizes().astype(np.int64)
         tmp.free()

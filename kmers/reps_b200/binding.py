@@ -54,6 +54,10 @@ class BlockLists(C.Structure):
                 "blk_base": (self.blk_base, (self.nblk + 1) * 8), "meta": (self.meta, self.nseq * 24)}
 
 
+class KeyLists(C.Structure):   # experimental builds: kr_seqset_export_keys / kr_seqset_import_keys
+    _fields_ = [("nseq", C.c_uint32), ("capacity", C.c_uint64), ("keys", C.c_void_p), ("meta", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs", C.c_uint64), ("encode_ms", C.c_double),
                 ("blocklist_ms", C.c_double), ("join_ms", C.c_double), ("other_ms", C.c_double),
@@ -133,6 +137,11 @@ def load_library():
     # experimental entry points exist only in builds made with -DKR_EXPERIMENTAL (never the default library)
     if hasattr(lib, "kr_sim_matrix_sparse"):
         lib.kr_sim_matrix_sparse.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
+    if hasattr(lib, "kr_seqset_import_keys"):
+        lib.kr_keylist_capacity.argtypes = [vp, vp, u32]
+        lib.kr_keylist_capacity.restype = u64
+        lib.kr_seqset_export_keys.argtypes = [vp, vp, C.POINTER(KeyLists)]
+        lib.kr_seqset_import_keys.argtypes = [vp, C.POINTER(KeyLists), u32, vp, vp, u32, C.POINTER(vp)]
     _LIB = lib
     return lib
 
@@ -235,6 +244,23 @@ class Context:
         arr = (BlockLists * len(shards))(*shards)
         h = C.c_void_p()
         self._ck(self.lib.kr_seqset_import_blocklists(self.h, arr, len(shards), d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return SeqSet(self, h)
+
+    # ---- experimental builds only -----------------------------------------------------------------
+    def keylist_capacity(self, off) -> int:
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        return int(self.lib.kr_keylist_capacity(self.h, off.ctypes.data, len(off) - 1))
+
+    def export_keys(self, s: "SeqSet") -> KeyLists:
+        k = KeyLists()
+        self._ck(self.lib.kr_seqset_export_keys(self.h, s.h, C.byref(k)))
+        return k
+
+    def import_keys(self, shards, d_res_ptr: int, off) -> "SeqSet":
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        arr = (KeyLists * len(shards))(*shards)
+        h = C.c_void_p()
+        self._ck(self.lib.kr_seqset_import_keys(self.h, arr, len(shards), d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
         return SeqSet(self, h)
 
     def key_decode(self, key: int) -> str:

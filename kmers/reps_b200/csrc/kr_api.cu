@@ -1194,6 +1194,76 @@ kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, con
 }
 
 #ifdef KR_EXPERIMENTAL
+// EXPERIMENTAL: exchange of per-sequence KEY LISTS between GPUs (the posting-list path needs them; block lists do not
+// carry them).  Each GPU encodes a contiguous slice of the batch, exports its key arena and per-sequence records, the
+// caller all-gathers both, and every GPU imports the concatenation as one ordinary set (key lists, sizes, hashes;
+// block lists are built on demand).  The arena of a slice has one slot per k-mer position (capacity), so its size and
+// every sequence's offset follow from the residue offsets alone: no size exchange.
+struct kr_keylists {
+    uint32_t nseq;
+    uint64_t capacity;    /* uint64 slots of the key arena: sum over sequences of max(0, L - K + 1) */
+    const void *keys;     /* uint64[capacity]: sequence i's sorted distinct keys start at its capacity offset */
+    const void *meta;     /* 24 bytes per sequence */
+};
+uint64_t kr_keylist_capacity(const kr_ctx *ctx, const uint64_t *offsets, uint32_t nseq) {
+    if (!ctx || (!offsets && nseq)) return 0;
+    u64 kc = 0;
+    for (u32 i = 0; i < nseq; ++i) { u64 L = offsets[i + 1] - offsets[i]; if (L >= (u64)ctx->K) kc += L - ctx->K + 1; }
+    return kc;
+}
+kr_status kr_seqset_export_keys(kr_ctx *ctx, kr_seqset *set, kr_keylists *out) {
+    if (!ctx || !set || !out) return fail(ctx, KR_ERR_ARG, "kr_seqset_export_keys: null argument");
+    if (set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_seqset_export_keys: set belongs to another context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    if (!set->d_keys && set->n) return fail(ctx, KR_ERR_STATE, "kr_seqset_export_keys: this set has no key lists");
+    CU(cudaStreamSynchronize(ctx->stream));
+    kr_status st;
+    if (ctx->err_pending && (st = check_alphabet(ctx))) return st;
+    out->nseq = set->n; out->capacity = set->key_cap; out->keys = set->d_keys; out->meta = set->d_meta;
+    return KR_OK;
+}
+kr_status kr_seqset_import_keys(kr_ctx *ctx, const kr_keylists *shards, uint32_t nshards, const uint8_t *d_residues,
+                                const uint64_t *offsets, uint32_t nseq, kr_seqset **out) {
+    if (!ctx || !shards || !nshards || !out || !offsets) return fail(ctx, KR_ERR_ARG, "kr_seqset_import_keys: null argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    const int K = ctx->K;
+    std::vector<u64> off(nseq + 1), koff(nseq + 1);
+    u64 kc = 0;
+    for (u32 i = 0; i < nseq; ++i) {
+        off[i] = offsets[i] - offsets[0]; koff[i] = kc;
+        const u64 L = offsets[i + 1] - offsets[i];
+        if (L >= (u64)K) kc += L - K + 1;
+    }
+    off[nseq] = offsets[nseq] - offsets[0]; koff[nseq] = kc;
+    u32 n = 0; u64 cap = 0;
+    for (u32 k = 0; k < nshards; ++k) { n += shards[k].nseq; cap += shards[k].capacity; }
+    if (n != nseq || cap != kc) return fail(ctx, KR_ERR_ARG, "import: shards hold %u sequences / %llu key slots, batch has %u / %llu", n, (unsigned long long)cap, nseq, (unsigned long long)kc);
+    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
+    s->ctx = ctx; s->n = nseq; s->key_cap = kc;
+    s->res = std::make_shared<DevMem>(); s->res->stream = ctx->stream;
+    CU(cudaMallocAsync(&s->res->p, off[nseq] + 16, ctx->stream));
+    CU(cudaMemcpyAsync(s->res->p, d_residues + offsets[0], off[nseq], cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_koff, nseq + 1));
+    CU(dalloc(ctx, &s->d_keys, kc + 16)); CU(dalloc(ctx, &s->d_meta, nseq));
+    CU(cudaMemcpyAsync(s->d_off, off.data(), (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s->d_koff, koff.data(), (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    u64 k0 = 0; u32 s0 = 0;
+    for (u32 k = 0; k < nshards; ++k) {
+        const kr_keylists &sh = shards[k];
+        if (sh.capacity) CU(cudaMemcpyAsync(s->d_keys + k0, sh.keys, sh.capacity * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (sh.nseq) CU(cudaMemcpyAsync(s->d_meta + s0, sh.meta, (size_t)sh.nseq * sizeof(SeqMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+        k0 += sh.capacity; s0 += sh.nseq;
+    }
+    if (nseq) { KR_LAUNCH(KR_T(k_import_meta), (nseq + 255) / 256, 256, 0, ctx->stream, s->d_meta, nseq, (const u8 *)s->res->p, s->d_off); LAUNCHED(ctx); }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));   // off / koff are stack-lifetime staging buffers
+    *out = s.release();
+    return KR_OK;
+}
+
 // EXPERIMENTAL (not in include/kmersreps.h, not in the default build; unverified on hardware): the similarity matrix
 // as a list of its cells with sim >= min_sim -- (row, col, sim, 0) as four uint32, in no particular order.  Layout
 // FULL: every column; TRIANGLE (self only): columns j > i.  *count receives the number of qualifying cells even

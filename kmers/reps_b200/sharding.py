@@ -83,6 +83,21 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+def _view(ptr: int, nbytes: int, device):
+    """library-owned memory as a uint8 torch tensor on `device` (CUDA; or CPU when the library is the test emulator)"""
+    import torch
+    if torch.device(device).type == "cuda":
+        return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
+    import ctypes
+    return torch.frombuffer((ctypes.c_uint8 * int(nbytes)).from_address(int(ptr)), dtype=torch.uint8)
+
+
+def _sync(device):
+    import torch
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream().synchronize()
+
+
 def block_shards(nseq: int, world: int):
     """contiguous sequence ranges, one per rank, cut at multiples of 256 sequences"""
     nblk = (nseq + kr.TILE - 1) // kr.TILE
@@ -120,15 +135,51 @@ def encode_sharded(ctx, d_res, off, dist):
     for name in names:
         nbytes = mine.arrays()[name][1]
         if nbytes:
-            send[field[name]: field[name] + nbytes].copy_(torch.as_tensor(_DevPtr(getattr(bl, name), nbytes), device=d_res.device))
+            send[field[name]: field[name] + nbytes].copy_(_view(getattr(bl, name), nbytes, d_res.device))
     recv = torch.empty(world * width, dtype=torch.uint8, device=d_res.device)
     dist.all_gather_into_tensor(recv, send)
     for k in range(world):
         for name in names:
             setattr(shards[k], name, recv.data_ptr() + k * width + field[name])
-    torch.cuda.current_stream().synchronize()              # the gathered arrays are complete before the library reads them
+    _sync(d_res.device)                                    # the gathered arrays are complete before the library reads them
     full = ctx.import_blocklists(shards, d_res.data_ptr(), off)
     full._keep = (recv, local)   # released with the set: by then the import's copies have long completed
+    return full
+
+
+def encode_sharded_keys(ctx, d_res, off, dist):
+    """EXPERIMENTAL library only.  Like encode_sharded, but what is exchanged are the per-sequence KEY LISTS (the
+    posting-list all-vs-all path needs them): this rank encodes its slice, ONE all_gather moves every slice's key arena
+    and per-sequence records, and the result is imported as one ordinary set on every rank.  Arena sizes are capacities
+    (one slot per k-mer position) every rank computes from the offsets, so no size exchange is needed."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nseq = len(off) - 1
+    cuts = block_shards(nseq, world)
+    local = ctx.encode_device(d_res.data_ptr(), off[cuts[rank]: cuts[rank + 1] + 1])
+    kl = ctx.export_keys(local)                            # synchronises: the arrays are complete
+    shards = []
+    for k in range(world):
+        b = kr.KeyLists()
+        b.nseq = cuts[k + 1] - cuts[k]
+        b.capacity = ctx.keylist_capacity(off[cuts[k]: cuts[k + 1] + 1])
+        shards.append(b)
+    assert kl.capacity == shards[rank].capacity and kl.nseq == shards[rank].nseq
+    kbytes = (max(b.capacity for b in shards) * 8 + 255) // 256 * 256
+    mbytes = (max(b.nseq for b in shards) * 24 + 255) // 256 * 256
+    send = torch.empty(kbytes + mbytes, dtype=torch.uint8, device=d_res.device)
+    if kl.capacity:
+        send[: kl.capacity * 8].copy_(_view(kl.keys, kl.capacity * 8, d_res.device))
+    if kl.nseq:
+        send[kbytes: kbytes + kl.nseq * 24].copy_(_view(kl.meta, kl.nseq * 24, d_res.device))
+    recv = torch.empty(world * (kbytes + mbytes), dtype=torch.uint8, device=d_res.device)
+    dist.all_gather_into_tensor(recv, send)
+    for k in range(world):
+        shards[k].keys = recv.data_ptr() + k * (kbytes + mbytes)
+        shards[k].meta = recv.data_ptr() + k * (kbytes + mbytes) + kbytes
+    _sync(d_res.device)
+    full = ctx.import_keys(shards, d_res.data_ptr(), off)  # copies out of `recv` and synchronises
+    local.free()
     return full
 
 

@@ -35,3 +35,13 @@ def test_device_code_on_the_emulator(emul_lib, case):
     p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        timeout=900)
     assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_paths_end_to_end_on_the_emulator(emul_lib, world):
+    """gloo ranks, one emulator context each, run sharding.encode_sharded (block-list all-gather + import) and
+    sharding.encode_sharded_keys (key-list all-gather + import, posting-list path) and compute their result stripes"""
+    env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2")
+    p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_sharded.py"), str(world)], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=1500)
+    assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK sharded %d" % world), p.stdout.decode()[-3000:]
