@@ -162,7 +162,7 @@ def run_findclosest(args, rank, world, local):
     res, off, fam = synth.generate(0x5EED0005, ncand + nq, max(1, ncand // 50), xrun_per_10k=10)
     gen_s = time.perf_counter() - t0
     from kmers.reps_b200 import binding
-    exp = (binding.EXP_ENCODE if args.exp_encode else 0) | (binding.EXP_IDXQ if args.exp_idxq else 0)
+    exp = (binding.EXP_ENCODE if args.exp_encode else 0) | (binding.EXP_IDXQ if args.exp_idxq else 0) | (binding.EXP_GIDX if args.exp_gidx else 0)
     if exp and not binding.has_experimental():
         raise SystemExit("--exp-* flags need KR_LIB_PATH to point at libkmersreps_cuda_exp.so")
     ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | exp)
@@ -284,6 +284,7 @@ def main():
                     help="EXPERIMENTAL library only: all-vs-all through the posting-list path (context flag EXP_PAIRS)")
     ap.add_argument("--exp-encode", action="store_true", help="EXPERIMENTAL library only: K1 with one warp per sequence (EXP_ENCODE)")
     ap.add_argument("--exp-idxq", action="store_true", help="EXPERIMENTAL library only: K5 with one warp per query (EXP_IDXQ; findclosest workload)")
+    ap.add_argument("--exp-gidx", action="store_true", help="EXPERIMENTAL library only: greedy build through the growing index (EXP_GIDX; findclosest workload)")
     ap.add_argument("--sparse-e2e", action="store_true",
                     help="EXPERIMENTAL library only (KR_LIB_PATH=.../libkmersreps_cuda_exp.so): also time the e2e path that returns only "
                          "the cells with sim >= 1 (kr_sim_matrix_sparse) and report it as e2e_sparse")

@@ -9,6 +9,8 @@
 #define KR_EXP_ENCODE 0x400u       /* context flag (experimental builds): K1 with one warp per sequence */
 #include "kr_idxq2.cuh"
 #define KR_EXP_IDXQ 0x800u         /* context flag (experimental builds): K5 with one warp per query where it pays */
+#include "kr_gidx.cuh"
+#define KR_EXP_GIDX 0x1000u        /* context flag (experimental builds): greedy build scores candidates through a growing index */
 #define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
 #define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
 #endif
@@ -229,6 +231,7 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
     CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
     CUC(cudaFuncSetAttribute(k_idx_query_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDXQ2_DENSE_MAX * 2 * IDXQ2_WARPS + 256)));
+    CUC(cudaFuncSetAttribute(k_gidx_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIDX_SMEM));
 #endif
 #undef CUC
     *out = ctx;
@@ -1432,12 +1435,54 @@ kr_status kr_db_any_ge(kr_ctx *ctx, const kr_db *db, const kr_seqset *cands, int
     return KR_OK;
 }
 
+#ifdef KR_EXPERIMENTAL
+// EXPERIMENTAL: the growing index of kr_gidx.cuh, sized once for everything this call can add
+struct GrowIndex {
+    kr_ctx *ctx; GIdx g{}; bool ok = false;
+    explicit GrowIndex(kr_ctx *c) : ctx(c) {}
+    ~GrowIndex() {
+        dfree(ctx, g.key); dfree(ctx, g.head); dfree(ctx, g.nodes); dfree(ctx, g.node_count); dfree(ctx, g.rmeta);
+        dfree(ctx, g.empty_reps); dfree(ctx, g.empty_count);
+    }
+    kr_status create(u64 entries, u32 reps) {
+        u64 cap = 1024; while (cap < 2 * entries) cap <<= 1;
+        if (entries >= 0xFFFFFFF0ull) return fail(ctx, KR_ERR_ARG, "growing index: too many k-mers (%llu)", (unsigned long long)entries);
+        CU(dalloc(ctx, &g.key, cap)); CU(dalloc(ctx, &g.head, cap)); CU(dalloc(ctx, &g.nodes, entries + 1)); CU(dalloc(ctx, &g.node_count, 1));
+        CU(dalloc(ctx, &g.rmeta, reps + 1)); CU(dalloc(ctx, &g.empty_reps, reps + 1)); CU(dalloc(ctx, &g.empty_count, 1));
+        CU(cudaMemsetAsync(g.key, 0xFF, cap * 8, ctx->stream)); CU(cudaMemsetAsync(g.head, 0xFF, cap * 4, ctx->stream));
+        CU(cudaMemsetAsync(g.node_count, 0, 4, ctx->stream)); CU(cudaMemsetAsync(g.empty_count, 0, 4, ctx->stream));
+        g.mask = cap - 1; g.node_cap = (u32)entries + 1; ok = true;
+        return KR_OK;
+    }
+    kr_status insert(const kr_seqset *s, u32 rep_base) {
+        if (!s->n) return KR_OK;
+        KR_LAUNCH(KR_T(k_gidx_insert), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, rep_base, g);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        return KR_OK;
+    }
+};
+#endif
+
 kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_t threshold, uint32_t batch, uint8_t *added) {
     if (!ctx || !db || !cands || !added) return fail(ctx, KR_ERR_ARG, "kr_greedy_build: null argument");
     if (db->ctx != ctx || cands->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_greedy_build: handle belongs to another context");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->dev));
     if (batch == 0) batch = 4096;
+#ifdef KR_EXPERIMENTAL
+    GrowIndex gi(ctx);
+    if ((ctx->flags & KR_EXP_GIDX) && cands->d_keys && cands->n) {
+        u64 entries = cands->key_cap;
+        bool keyed = true;
+        for (auto &sg : db->segs) { entries += sg.set->key_cap; keyed = keyed && (sg.set->d_keys || !sg.set->n); }
+        if (keyed) {
+            kr_status st0 = gi.create(entries, db->n + cands->n);
+            for (auto &sg : db->segs) if (st0 == KR_OK) st0 = gi.insert(sg.set, sg.base);
+            if (st0) return st0;
+        }
+    }
+#endif
     const u32 C = cands->n;
     kr_status st = KR_OK;
     std::vector<u32> idx, surv, acc;
@@ -1448,6 +1493,31 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
         idx.resize(n);
         for (u32 i = 0; i < n; ++i) idx[i] = pos + i;
         surv.clear();
+#ifdef KR_EXPERIMENTAL
+        if (gi.ok) {
+            // score the batch through the growing index: no gather, no block lists, nothing rebuilt
+            int *d_sim = nullptr; u32 *d_next = nullptr;
+            cudaError_t e = dalloc(ctx, &d_sim, n);
+            if (e == cudaSuccess) e = dalloc(ctx, &d_next, 1);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_next, 0, 4, ctx->stream);
+            if (e != cudaSuccess) { st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
+            {
+                StageTimer t(ctx, ST_JOIN);
+                const u32 grid = std::min<u32>((n + GIDX_WARPS - 1) / GIDX_WARPS, (u32)ctx->num_sms * 3);
+                KR_LAUNCH(KR_T(k_gidx_query), grid, GIDX_WARPS * 32, GIDX_SMEM, ctx->stream, cands->d_keys, cands->d_koff + pos, cands->d_meta + pos, n, gi.g,
+                          ctx->flags, d_sim, d_next);
+                LAUNCHED(ctx); ctx->st.join_launches++;
+            }
+            best.resize(n);
+            e = cudaMemcpyAsync(best.data(), d_sim, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
+            ctx->st.d2h_bytes += (u64)n * 4; ctx->st.pairs += (u64)n * db->n;
+            dfree(ctx, d_sim); dfree(ctx, d_next);
+            if (st) break;
+            for (u32 i = 0; i < n; ++i) { if (best[i] < threshold) surv.push_back(pos + i); else added[pos + i] = 0; }
+        } else
+#endif
         if (db->n) {
             // score the batch against the current representatives
             kr_seqset *bs = nullptr;
@@ -1507,6 +1577,9 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
         for (size_t k = 0; k < acc.size(); ++k) { acc_idx[k] = surv[acc[k]]; added[acc_idx[k]] = 1; }
         kr_seqset *as = nullptr;
         if ((st = gather_impl(ctx, cands, acc_idx.data(), (u32)acc_idx.size(), &as))) break;
+#ifdef KR_EXPERIMENTAL
+        if (gi.ok && (st = gi.insert(as, db->n))) { seqset_destroy(as); break; }   // stream-ordered before any later free of `as`
+#endif
         st = db_append_owned(ctx, db, as);
     }
     return st;

@@ -268,6 +268,37 @@ def case_exp_idxq_warp():
     assert bs[5] == 1 and bi[5] != bl2[5], (bs, bi, bl2)                             # the hub query ties over 1,150 representatives
 
 
+def case_exp_gidx_build():
+    """EXPERIMENTAL: greedy build through the growing index -- against the oracle and the default build, starting from a
+    non-empty database, with k-mer-less and duplicate candidates, several batch sizes, and a candidate whose k-mers
+    reach more representatives than the per-warp table holds (multi-pass path)"""
+    rng = np.random.default_rng(31)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    rnd = lambda n: alpha[rng.integers(0, 20, n)].tobytes().decode()
+    seqs = family(19, 420, 9, 60, 130)
+    seqs[50:50] = ["MKV", "MKV", "", "MKVLAAGIVG", "MKVLAAGIVG"]
+    first, rest = seqs[:120], seqs[120:] + ["MKV", seqs[3]]
+    for thr in (30, 10):
+        _, w0, _ = O.greedy_build(O.batch(first + rest, K=8), thr, ident_inf=True)
+        for batch in (37, 4096):
+            c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_GIDX)
+            db = c.db()
+            a0 = db.greedy_build(c.encode(first), thr, batch=batch)             # fills the database ...
+            a1 = db.greedy_build(c.encode(rest), thr, batch=batch)              # ... which the second call must index first
+            assert (np.concatenate([a0, a1]) == w0).all(), (thr, batch)
+            assert db.size == int(w0.sum())
+            c.close()
+    hub = "MKVLAAGI"
+    crowd = [rnd(9) + hub + rnd(9) for _ in range(1150)]                        # pairwise similarity 1: all become representatives
+    cands = crowd + [rnd(5) + hub + rnd(30), crowd[7][:20] + rnd(4), rnd(40)]
+    _, want, _ = O.greedy_build(O.batch(cands, K=8), 5, ident_inf=True)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_GIDX)
+    db = c.db()
+    got = db.greedy_build(c.encode(cands), 5, batch=400)
+    assert (got == want).all() and want.sum() > 1100 and not want[1151]      # > 1024 representatives on the hub k-mer's list
+    c.close()
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -141,3 +141,27 @@ def test_warp_per_query_index_equals_cta_index(oracle, rep50, gto_seeds, rickett
         c.close()
     for a, b in zip(*out):
         assert (a == b).all()
+
+
+def test_greedy_build_through_the_growing_index(oracle, rep50, rickettsia):
+    """EXP_GIDX: kr_greedy_build scoring candidates through the appendable index, against the default build and the
+    oracle: synthetic families at two thresholds and batch sizes, rep50.db's own sequences (all kept), duplicates"""
+    res, off, _ = synth.generate(0x5EED000D, 30000, 500, xrun_per_10k=10)
+    seqs = synth.to_strings(res, off)
+    for thr, batch in ((50, 0), (100, 1000)):
+        outs = []
+        for flags in (binding.EXP_GIDX, 0):
+            c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | flags)
+            db = c.db()
+            a0 = db.greedy_build(c.encode(seqs[:5000]), thr, batch=batch)
+            a1 = db.greedy_build(c.encode(seqs[5000:]), thr, batch=batch)
+            outs.append(np.concatenate([a0, a1]))
+            c.close()
+        assert (outs[0] == outs[1]).all()
+    _, want, _ = oracle.greedy_build(oracle.batch(seqs[:6000], K=8), 50, ident_inf=True)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_GIDX)
+    assert (c.db().greedy_build(c.encode(seqs[:6000]), 50) == want).all()
+    reps = [s for (_, _, s) in rep50["reps"]] + [p for (_, p) in rickettsia] + ["MKV", "MKV", ""]
+    _, want, _ = oracle.greedy_build(oracle.batch(reps, K=8), 50, ident_inf=True)
+    assert (c.db().greedy_build(c.encode(reps), 50, batch=300) == want).all() and want[:1480].all()
+    c.close()

@@ -16,7 +16,7 @@ KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --exp
 KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --exp-encode --exp-pairs --sparse-e2e > gpurun_out/exp_bench_pairs.json 2> gpurun_out/exp_bench_pairs.err
 KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --sparse-e2e > gpurun_out/exp_bench_sparse_join.json 2> gpurun_out/exp_bench_sparse_join.err
 timeout 600 python bench.py --workload findclosest --steps 2 > gpurun_out/exp_fc_default.json 2> gpurun_out/exp_fc_default.err
-KR_LIB_PATH=$EXP timeout 600 python bench.py --workload findclosest --steps 2 --exp-encode --exp-idxq > gpurun_out/exp_fc_exp.json 2> gpurun_out/exp_fc_exp.err
+KR_LIB_PATH=$EXP timeout 600 python bench.py --workload findclosest --steps 2 --exp-encode --exp-idxq --exp-gidx > gpurun_out/exp_fc_exp.json 2> gpurun_out/exp_fc_exp.err
 tail -c 600 gpurun_out/exp_pytest_default.log gpurun_out/exp_pytest_exp.log
 for f in gpurun_out/exp_bench_*.json gpurun_out/exp_fc_*.json; do echo $f; python - "$f" <<'PY'
 import json, sys
