@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exp-pairs", action="store_true",
                     help="EXPERIMENTAL library only: all-vs-all through the posting-list path (context flag EXP_PAIRS)")
+    ap.add_argument("--exp-buckets", action="store_true", help="EXPERIMENTAL library only, with --exp-pairs: group by key in shared memory after a bucket partition")
     ap.add_argument("--exp-encode", action="store_true", help="EXPERIMENTAL library only: K1 with one warp per sequence (EXP_ENCODE)")
     ap.add_argument("--exp-idxq", action="store_true", help="EXPERIMENTAL library only: K5 with one warp per query (EXP_IDXQ; findclosest workload)")
     ap.add_argument("--exp-gidx", action="store_true", help="EXPERIMENTAL library only: greedy build through the growing index (EXP_GIDX; findclosest workload)")
@@ -317,7 +318,7 @@ def main():
     if (args.exp_pairs or args.exp_encode) and not binding.has_experimental():
         raise SystemExit("--exp-pairs / --exp-encode need KR_LIB_PATH to point at libkmersreps_cuda_exp.so")
     ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | (binding.EXP_PAIRS if args.exp_pairs else 0)
-                     | (binding.EXP_ENCODE if args.exp_encode else 0))
+                     | (binding.EXP_ENCODE if args.exp_encode else 0) | (binding.EXP_BUCKETS if args.exp_buckets else 0))
     elem = kr.ELEM_U16 if args.elem == "u16" else kr.ELEM_I32
     esz = 2 if elem == kr.ELEM_U16 else 4
     layout = kr.LAYOUT_BLOCKTRI

@@ -13,6 +13,7 @@
 #define KR_EXP_GIDX 0x1000u        /* context flag (experimental builds): greedy build scores candidates through a growing index */
 #define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
 #define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
+#define KR_EXP_BUCKETS 0x2000u     /* posting-list path: group by key in shared memory after a bucket partition (no HBM hash table) */
 #endif
 
 #include <algorithm>
@@ -88,6 +89,9 @@ struct kr_seqset {
     bool px_ready = false; u64 px_slots = 0;
     unsigned long long *px_key = nullptr; u32 *px_off = nullptr, *px_cnt = nullptr, *px_post = nullptr;
     unsigned long long px_work = ~0ull;   // sum of m(m-1)/2, once known
+    // the same entries partitioned into buckets by key hash (KR_EXP_BUCKETS)
+    bool bk_ready = false; u32 bk_nb = 0;
+    u32 *bk_base = nullptr, *bk_eseq = nullptr, *bk_post = nullptr; u64 *bk_ekey = nullptr;
 #endif
 };
 
@@ -232,6 +236,9 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
     CUC(cudaFuncSetAttribute(k_idx_query_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDXQ2_DENSE_MAX * 2 * IDXQ2_WARPS + 256)));
     CUC(cudaFuncSetAttribute(k_gidx_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIDX_SMEM));
+    CUC(cudaFuncSetAttribute(k_bk_pairs<DenseSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
+    CUC(cudaFuncSetAttribute(k_bk_pairs<TableSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
+    CUC(cudaFuncSetAttribute(k_bk_pairs<WorkSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
 #endif
 #undef CUC
     *out = ctx;
@@ -339,6 +346,7 @@ static void seqset_destroy(kr_seqset *s) {
     dfree(ctx, s->d_hi); dfree(ctx, (u8 *)s->d_lo); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
 #ifdef KR_EXPERIMENTAL
     dfree(ctx, s->px_key); dfree(ctx, s->px_off); dfree(ctx, s->px_cnt); dfree(ctx, s->px_post);
+    dfree(ctx, s->bk_base); dfree(ctx, s->bk_eseq); dfree(ctx, s->bk_post); dfree(ctx, s->bk_ekey);
 #endif
     delete s;   // residue buffers are released stream-ordered by ~DevMem
 }
@@ -537,6 +545,33 @@ static kr_status ensure_postings(kr_ctx *ctx, kr_seqset *s) {
     return KR_OK;
 }
 
+// EXPERIMENTAL: the (key, sequence) entries of a set partitioned into buckets of ~1,000 by key hash (kr_pairs.cuh)
+static kr_status ensure_buckets(kr_ctx *ctx, kr_seqset *s) {
+    if (s->bk_ready) return KR_OK;
+    const u64 entries = s->key_cap;
+    if (entries >= 0xFFFFFFF0ull) return fail(ctx, KR_ERR_ARG, "posting-list path: set too large (%llu k-mers)", (unsigned long long)entries);
+    u32 nb = 1; while ((u64)nb * 1024 < entries && nb < (1u << 22)) nb <<= 1;
+    u32 *d_hist = nullptr, *d_cursor = nullptr;
+    CU(dalloc(ctx, &d_hist, nb)); CU(dalloc(ctx, &d_cursor, nb)); CU(dalloc(ctx, &s->bk_base, nb + 1));
+    CU(dalloc(ctx, &s->bk_ekey, entries + 1)); CU(dalloc(ctx, &s->bk_eseq, entries + 1)); CU(dalloc(ctx, &s->bk_post, entries + 1));
+    CU(cudaMemsetAsync(d_hist, 0, (size_t)nb * 4, ctx->stream)); CU(cudaMemsetAsync(d_cursor, 0, (size_t)nb * 4, ctx->stream));
+    {
+        StageTimer t(ctx, ST_BLOCKLIST);
+        if (s->n) KR_LAUNCH(KR_T(k_bk_count), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, d_hist);
+        KR_LAUNCH(KR_T(k_bk_scan), 1, 1024, 0, ctx->stream, d_hist, nb, s->bk_base);
+        if (s->n) KR_LAUNCH(KR_T(k_bk_scatter), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, s->bk_base, d_cursor, s->bk_ekey, s->bk_eseq);
+        ctx->st.kernel_launches += 3;
+        CU(cudaGetLastError());
+    }
+    dfree(ctx, d_hist); dfree(ctx, d_cursor);
+    s->bk_nb = nb; s->bk_ready = true;
+    return KR_OK;
+}
+static BucketParams bucket_params(const kr_seqset *s) {
+    BucketParams bp{}; bp.base = s->bk_base; bp.nb = s->bk_nb; bp.ekey = s->bk_ekey; bp.eseq = s->bk_eseq; bp.post = s->bk_post;
+    return bp;
+}
+
 // sum over the posting lists of m(m-1)/2 (= pair increments = an upper bound of the pairs that share a k-mer);
 // synchronises the host once per set
 static kr_status postings_work(kr_ctx *ctx, kr_seqset *A) {
@@ -544,6 +579,10 @@ static kr_status postings_work(kr_ctx *ctx, kr_seqset *A) {
     unsigned long long *d_work = nullptr, w = 0;
     CU(dalloc(ctx, &d_work, 1));
     CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));
+    if (ctx->flags & KR_EXP_BUCKETS) {
+        WorkSink ws{d_work};
+        KR_LAUNCH(KR_T(k_bk_pairs<WorkSink>), std::min<u32>(A->bk_nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bucket_params(A), ws);
+    } else
     KR_LAUNCH(KR_T(k_pairs_work), ctx->num_sms * 4, 256, 0, ctx->stream, A->px_cnt, A->px_slots, d_work);
     LAUNCHED(ctx);
     CU(cudaMemcpyAsync(&w, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -557,7 +596,8 @@ static kr_status postings_work(kr_ctx *ctx, kr_seqset *A) {
 // Returns KR_OK with *done = false when this path declines (AUTO mode and the join is estimated cheaper).
 static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d, void *out_dev, bool *done) {
     *done = false;
-    kr_status st = ensure_postings(ctx, A);
+    const bool buckets = (ctx->flags & KR_EXP_BUCKETS) != 0;
+    kr_status st = buckets ? ensure_buckets(ctx, A) : ensure_postings(ctx, A);
     if (st) return st;
     if (ctx->flags & KR_EXP_PAIRS_AUTO) {
         if ((st = postings_work(ctx, A))) return st;
@@ -581,6 +621,10 @@ static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d
     {
         StageTimer t(ctx, ST_JOIN);
         CU(cudaMemsetAsync(out_dev, 0, p.total * esz, ctx->stream));
+        if (buckets) {
+            DenseSink ds{p};
+            KR_LAUNCH(KR_T(k_bk_pairs<DenseSink>), std::min<u32>(A->bk_nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bucket_params(A), ds);
+        } else
         KR_LAUNCH(KR_T(k_pairs_emit), ctx->num_sms * 8, 256, 0, ctx->stream, p);
         KR_LAUNCH(KR_T(k_pairs_dup_insert), (A->n + 255) / 256, 256, 0, ctx->stream, p);
         KR_LAUNCH(KR_T(k_pairs_dup_fix), (A->n + 255) / 256, 256, 0, ctx->stream, p);
@@ -1289,7 +1333,8 @@ kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
     kr_seqset *As = const_cast<kr_seqset *>(A);
     if (self && desc->layout == KR_LAYOUT_TRIANGLE && (ctx->flags & (KR_EXP_PAIRS | KR_EXP_PAIRS_AUTO)) && As->d_keys && As->n) {
         // posting lists -> pair table -> cells: nothing proportional to N^2 is touched
-        if ((st = ensure_postings(ctx, As)) == KR_OK) st = postings_work(ctx, As);
+        const bool buckets = (ctx->flags & KR_EXP_BUCKETS) != 0;
+        if ((st = buckets ? ensure_buckets(ctx, As) : ensure_postings(ctx, As)) == KR_OK) st = postings_work(ctx, As);
         // table capacity: every pair that shares a k-mer (<= work) plus the equal-sequence pairs that share none
         // (sequences shorter than K: e of them give at most e(e-1)/2 such pairs)
         u64 empties = 0;
@@ -1310,6 +1355,10 @@ kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
             CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
             {
                 StageTimer t(ctx, ST_JOIN);
+                if (buckets) {
+                    TableSink tsink{p};
+                    KR_LAUNCH(KR_T(k_bk_pairs<TableSink>), std::min<u32>(As->bk_nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bucket_params(As), tsink);
+                } else
                 KR_LAUNCH(KR_T(k_pairs_emit_tab), ctx->num_sms * 8, 256, 0, ctx->stream, p);
                 KR_LAUNCH(KR_T(k_pairs_dup_insert_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);
                 KR_LAUNCH(KR_T(k_pairs_dup_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);

@@ -231,3 +231,184 @@ KRP_GLOBAL void k_pairs_compact(PairTabParams p) {
 }
 
 }  // namespace kr
+
+// =====================================================================================================================
+// Bucketed grouping (second generation of the posting-list path).  Building one big hash table in HBM costs about four
+// random DRAM accesses per (key, sequence) entry.  Here the entries are first PARTITIONED by a hash of the key into
+// buckets of ~1,000 entries with two streaming passes (count, scatter), and one CTA per bucket then groups its entries
+// in SHARED memory (a 4,096-slot table key -> count / offset), writes the sequence numbers grouped by key back into
+// the bucket's own region, and walks the groups emitting pair increments -- grouping and pair enumeration fused, all
+// random access on chip.  A bucket whose distinct keys do not fit the table is redone in 2, 4, 8 ... sub-passes by a
+// second hash, so any input is handled exactly.
+// These kernels need the block barrier, so they are checked on the full emulator (tests/emul/cuda_emul.h), not on the
+// thread-by-thread shim.
+#ifndef KR_PAIRS_EMUL
+namespace kr {
+
+#ifndef KR_BK_SLOTS
+#define KR_BK_SLOTS 4096
+#endif
+constexpr u32 BK_SLOTS = KR_BK_SLOTS;                // shared-memory table slots per CTA (the tests also build a 256-slot variant)
+constexpr u32 BK_THREADS = 256;
+constexpr size_t BK_SMEM = (size_t)BK_SLOTS * (8 + 4 + 4);
+constexpr unsigned long long BK_EMPTY = ~0ull;
+static_assert(BK_SLOTS >= BK_THREADS && (BK_SLOTS & (BK_SLOTS - 1)) == 0, "the scan gives every thread BK_SLOTS / BK_THREADS slots");
+
+__device__ __forceinline__ u64 bk_mix(u64 x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31; return x;
+}
+__device__ __forceinline__ u32 bk_bucket(u64 key, u32 nb_mask) { return (u32)(bk_mix(key) >> 40) & nb_mask; }
+
+// pass A: bucket sizes.  One CTA per sequence.
+__global__ void __launch_bounds__(128) k_bk_count(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq, u32 nb_mask, u32 *hist) {
+    const u32 s = blockIdx.x;
+    if (s >= nseq) return;
+    const u32 n = meta[s].size;
+    const u64 *kp = keys + koff[s];
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[bk_bucket(kp[i], nb_mask)], 1u);
+}
+// exclusive scan of the bucket sizes (one CTA); base[nb] = total
+__global__ void __launch_bounds__(1024) k_bk_scan(const u32 *hist, u32 nb, u32 *base) {
+    __shared__ u32 part[1024];
+    const u32 tid = threadIdx.x, per = (nb + 1023) / 1024;
+    const u32 b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
+    u32 acc = 0;
+    for (u32 b = b0; b < b1; ++b) acc += hist[b];
+    part[tid] = acc;
+    __syncthreads();
+    if (tid == 0) { u32 run = 0; for (int i = 0; i < 1024; ++i) { const u32 v = part[i]; part[i] = run; run += v; } base[nb] = run; }
+    __syncthreads();
+    u32 run = part[tid];
+    for (u32 b = b0; b < b1; ++b) { base[b] = run; run += hist[b]; }
+}
+// pass B: entries into their buckets (order inside a bucket is arbitrary)
+__global__ void __launch_bounds__(128) k_bk_scatter(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq, u32 nb_mask, const u32 *base,
+                                                    u32 *cursor, u64 *ekey, u32 *eseq) {
+    const u32 s = blockIdx.x;
+    if (s >= nseq) return;
+    const u32 n = meta[s].size;
+    const u64 *kp = keys + koff[s];
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+        const u64 key = kp[i];
+        const u32 b = bk_bucket(key, nb_mask);
+        const u32 pos = base[b] + atomicAdd(&cursor[b], 1u);
+        ekey[pos] = key; eseq[pos] = s;
+    }
+}
+
+struct BucketParams {
+    const u32 *base; u32 nb;               // bucket b holds entries [base[b], base[b + 1])
+    const u64 *ekey; const u32 *eseq; u32 *post;   // post: sequence numbers grouped by key, same indexing as the entries
+};
+
+struct DenseSink {    // result cells in HBM (kr_pairs_emit's target)
+    static constexpr bool COUNT_ONLY = false;
+    PairsParams p;
+    __device__ __forceinline__ void add(u32 i, u32 j) const { pairs_touch<false>(p, i, j, 0); }
+    __device__ __forceinline__ void group(u64) const {}
+};
+struct TableSink {    // pair hash table (the sparse result)
+    static constexpr bool COUNT_ONLY = false;
+    PairTabParams p;
+    __device__ __forceinline__ void add(u32 i, u32 j) const { if (i >= p.row_begin && i < p.row_end) atomicAdd(&p.pt_cnt[pairtab_slot(p, i, j)], 1u); }
+    __device__ __forceinline__ void group(u64) const {}
+};
+struct WorkSink {     // only the number of pair increments (the host's work estimate); nothing is emitted
+    static constexpr bool COUNT_ONLY = true;
+    unsigned long long *work;
+    __device__ __forceinline__ void add(u32, u32) const {}
+    __device__ __forceinline__ void group(u64 pairs) const { atomicAdd(work, (unsigned long long)pairs); }
+};
+
+// count phase of one sub-pass: clear the table, then key -> number of entries.  Returns false (for the whole CTA) when
+// the distinct keys of this sub-pass do not fit the table.
+__device__ __forceinline__ bool bk_count_pass(const BucketParams &bp, u32 e0, u32 n, u32 pass, u32 npass, unsigned long long *tkey, u32 *tcnt,
+                                              u32 *s_ovf, u32 tid) {
+    for (u32 i = tid; i < BK_SLOTS; i += BK_THREADS) { tkey[i] = BK_EMPTY; tcnt[i] = 0; }
+    if (tid == 0) *s_ovf = 0;
+    __syncthreads();
+    for (u32 i = tid; i < n; i += BK_THREADS) {
+        const u64 key = bp.ekey[e0 + i];
+        const u64 h = bk_mix(key ^ 0x9E3779B97F4A7C15ULL);
+        if (npass > 1 && ((h >> 32) & (npass - 1)) != pass) continue;
+        u32 slot = (u32)h & (BK_SLOTS - 1), probes = 0;
+        for (;;) {
+            const unsigned long long old = atomicCAS(&tkey[slot], BK_EMPTY, (unsigned long long)key);
+            if (old == BK_EMPTY || old == key) { atomicAdd(&tcnt[slot], 1u); break; }
+            slot = (slot + 1) & (BK_SLOTS - 1);
+            if (++probes >= BK_SLOTS) { *s_ovf = 1; break; }
+        }
+    }
+    __syncthreads();
+    const bool ok = *s_ovf == 0;
+    __syncthreads();                                                     // everyone has read the flag before it is reset
+    return ok;
+}
+
+// pass C: one CTA per bucket (grid-stride): group in shared memory, emit the pairs of every group
+template <class SINK>
+__global__ void __launch_bounds__(BK_THREADS) k_bk_pairs(BucketParams bp, SINK sink) {
+    KR_DYN_SMEM(u8, bk_smem, 16);
+    unsigned long long *tkey = reinterpret_cast<unsigned long long *>(bk_smem);
+    u32 *tcnt = reinterpret_cast<u32 *>(bk_smem + (size_t)BK_SLOTS * 8), *toff = tcnt + BK_SLOTS;
+    __shared__ u32 s_ovf, s_wsum[BK_THREADS / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 b = blockIdx.x; b < bp.nb; b += gridDim.x) {
+        const u32 e0 = bp.base[b], n = bp.base[b + 1] - e0;
+        if (n < 2) continue;                                            // uniform for the CTA
+        // Nothing may be emitted before the number of sub-passes is settled (an emitted pair cannot be taken back):
+        // the common case is one pass whose count phase doubles as the check
+        u32 npass = 1;
+        if (!bk_count_pass(bp, e0, n, 0, 1, tkey, tcnt, &s_ovf, tid)) {
+            for (npass = 2;; npass *= 2) {
+                bool ok = true;
+                for (u32 pass = 0; pass < npass && ok; ++pass) ok = bk_count_pass(bp, e0, n, pass, npass, tkey, tcnt, &s_ovf, tid);
+                if (ok) break;
+                if (npass >= (1u << 20)) __trap();                       // cannot happen: one key per pass long before
+            }
+        }
+        for (u32 pass = 0; pass < npass; ++pass) {
+            if (npass > 1) bk_count_pass(bp, e0, n, pass, npass, tkey, tcnt, &s_ovf, tid);
+            // exclusive scan of the counts -> toff (BK_SLOTS / BK_THREADS consecutive slots per thread)
+            constexpr u32 PER = BK_SLOTS / BK_THREADS;
+            u32 acc = 0;
+            for (u32 k = 0; k < PER; ++k) acc += tcnt[tid * PER + k];
+            u32 incl = acc;
+            for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += up; }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            u32 run = incl - acc;
+            for (u32 w = 0; w < warp; ++w) run += s_wsum[w];
+            for (u32 k = 0; k < PER; ++k) { toff[tid * PER + k] = run; run += tcnt[tid * PER + k]; }
+            __syncthreads();
+            // fill: sequence numbers grouped by key (toff advances to the end of each group)
+            for (u32 i = tid; i < n; i += BK_THREADS) {
+                const u64 key = bp.ekey[e0 + i];
+                const u64 h = bk_mix(key ^ 0x9E3779B97F4A7C15ULL);
+                if (npass > 1 && ((h >> 32) & (npass - 1)) != pass) continue;
+                u32 slot = (u32)h & (BK_SLOTS - 1);
+                while (tkey[slot] != key) slot = (slot + 1) & (BK_SLOTS - 1);
+                bp.post[e0 + atomicAdd(&toff[slot], 1u)] = bp.eseq[e0 + i];
+            }
+            __syncthreads();                                             // the groups are complete (block-wide visibility)
+            // emit: a warp per group, lanes over its pairs
+            for (u32 slot = warp; slot < BK_SLOTS; slot += BK_THREADS / 32) {
+                const u32 m = tcnt[slot];
+                if (m < 2) continue;
+                const u32 g0 = e0 + toff[slot] - m;
+                const u64 P = (u64)m * (m - 1) / 2;
+                if (SINK::COUNT_ONLY) { if (lane == 0) sink.group(P); continue; }
+                for (u64 t = lane; t < P; t += 32) {
+                    const u32 bb = pairs_tri_row(t), aa = (u32)(t - (u64)bb * (bb - 1) / 2);
+                    u32 i = bp.post[g0 + aa], j = bp.post[g0 + bb];
+                    if (i > j) { const u32 x = i; i = j; j = x; }
+                    sink.add(i, j);
+                }
+            }
+            __syncthreads();                                             // before the table is cleared for the next pass / bucket
+        }
+    }
+}
+
+}  // namespace kr
+#endif

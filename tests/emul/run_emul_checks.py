@@ -172,7 +172,9 @@ def case_exp_pairs():
     n = len(seqs)
     for ident in (kr.IDENT_IS_INFINITY, 0):
         want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=bool(ident), threads=4)
-        for mode in (binding.EXP_PAIRS, binding.EXP_PAIRS_AUTO):
+        for mode in (binding.EXP_PAIRS, binding.EXP_PAIRS_AUTO, binding.EXP_PAIRS | binding.EXP_BUCKETS, binding.EXP_PAIRS_AUTO | binding.EXP_BUCKETS):
+            if os.environ.get("KR_EMUL_ONLY_BUCKETS") and not (mode & binding.EXP_BUCKETS):
+                continue
             c = kr.Context(device=0, K=8, flags=ident | mode)
             s = c.encode(seqs)
             assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all()

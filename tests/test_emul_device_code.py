@@ -28,6 +28,25 @@ def emul_lib():
     return LIB
 
 
+def build_variant(name, *defines):
+    out = os.path.join(EMUL, "_build", name)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMUL, "cuda_emul.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-DKR_EMUL", "-DKR_EXPERIMENTAL", *defines,
+                        "-I" + EMUL, "-Wno-unknown-pragmas", "-o", out, os.path.join(CSRC, "kr_api.cu")], check=True, timeout=600)
+    return out
+
+
+def test_bucket_grouping_sub_passes_on_the_emulator(emul_lib):
+    """the bucketed posting-list path with a 256-slot shared-memory table: every bucket holds more distinct keys than
+    fit, so each one is grouped in several sub-passes (the exactness path a real run almost never takes)"""
+    lib = build_variant("libkmersreps_emul_bk256.so", "-DKR_BK_SLOTS=256")
+    env = dict(os.environ, KR_LIB_PATH=lib, KR_EMUL_SMS="2", KR_EMUL_ONLY_BUCKETS="1")
+    p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), "exp_pairs"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=900)
+    assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK exp_pairs"), p.stdout.decode()[-3000:]
+
+
 @pytest.mark.parametrize("case", ["matrix_layouts", "k10_rectangular_pairs", "find_closest_and_build", "subchunks", "sharded_import",
                                   "exp_sparse_join", "exp_pairs", "exp_encode_warp", "exp_idxq_warp", "exp_gidx_build"])
 def test_device_code_on_the_emulator(emul_lib, case):

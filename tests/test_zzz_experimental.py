@@ -23,7 +23,7 @@ def cells_of(dense, min_sim, triangle):
     return out
 
 
-@pytest.mark.parametrize("via", [0, binding.EXP_PAIRS])
+@pytest.mark.parametrize("via", [0, binding.EXP_PAIRS, binding.EXP_PAIRS | binding.EXP_BUCKETS])
 @pytest.mark.parametrize("n,nfam", [(700, 12), (1500, 300)])
 def test_sparse_matrix_equals_dense(oracle, n, nfam, via):
     """kr_sim_matrix_sparse through the join's epilogue filter (via = 0) and through posting lists + pair table"""
@@ -56,7 +56,7 @@ def blocktri(full):
     return np.concatenate([full[i, 256 * (i // 256):] for i in range(n)])
 
 
-@pytest.mark.parametrize("flags", [binding.EXP_PAIRS, binding.EXP_PAIRS_AUTO])
+@pytest.mark.parametrize("flags", [binding.EXP_PAIRS, binding.EXP_PAIRS_AUTO, binding.EXP_PAIRS | binding.EXP_BUCKETS, binding.EXP_PAIRS_AUTO | binding.EXP_BUCKETS])
 def test_posting_list_all_vs_all_equals_oracle(oracle, vapb, rep50, flags):
     """the posting-list path (kr_pairs.cuh) must give the join's matrix bit for bit: every layout, element type,
     row stripe, with and without the equal-sequence rule; VapbProt.fa holds 11 identical-sequence pairs"""

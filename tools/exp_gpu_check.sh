@@ -14,6 +14,7 @@ KR_LIB_PATH=$EXP timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 >
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/exp_bench_default.json 2> gpurun_out/exp_bench_default.err
 KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --exp-encode > gpurun_out/exp_bench_encode.json 2> gpurun_out/exp_bench_encode.err
 KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --exp-encode --exp-pairs --sparse-e2e > gpurun_out/exp_bench_pairs.json 2> gpurun_out/exp_bench_pairs.err
+KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --exp-encode --exp-pairs --exp-buckets --sparse-e2e > gpurun_out/exp_bench_buckets.json 2> gpurun_out/exp_bench_buckets.err
 KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --sparse-e2e > gpurun_out/exp_bench_sparse_join.json 2> gpurun_out/exp_bench_sparse_join.err
 timeout 600 python bench.py --workload findclosest --steps 2 > gpurun_out/exp_fc_default.json 2> gpurun_out/exp_fc_default.err
 KR_LIB_PATH=$EXP timeout 600 python bench.py --workload findclosest --steps 2 --exp-encode --exp-idxq --exp-gidx > gpurun_out/exp_fc_exp.json 2> gpurun_out/exp_fc_exp.err
