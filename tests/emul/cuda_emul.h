@@ -53,9 +53,37 @@ namespace emu {
 // One CUDA thread = one fiber (ucontext); the fibers of a CTA are run round-robin by the launching OS thread, so
 // execution is single-threaded and deterministic, a blocked fiber just yields, and a CTA in which every fiber is
 // blocked is reported as a deadlock instead of hanging.
-struct Fiber { ucontext_t ctx; dim3 tid; bool done = false; std::vector<uint8_t> stack; };
+// Context switch: on x86-64 a few instructions of assembly (callee-saved registers + stack pointer); swapcontext()
+// elsewhere (it makes a signal-mask system call per switch, which dominates the run time of barrier-heavy kernels).
+#if defined(__x86_64__)
+#define KR_EMU_ASM_SWITCH 1
+extern "C" void kr_emu_switch(void **save_sp, void *new_sp);
+__asm__(".text\n.weak kr_emu_switch\n.type kr_emu_switch,@function\nkr_emu_switch:\n"
+        "pushq %rbp\npushq %rbx\npushq %r12\npushq %r13\npushq %r14\npushq %r15\n"
+        "movq %rsp, (%rdi)\nmovq %rsi, %rsp\n"
+        "popq %r15\npopq %r14\npopq %r13\npopq %r12\npopq %rbx\npopq %rbp\nret\n"
+        ".size kr_emu_switch, .-kr_emu_switch\n");
+struct Ctx { void *sp = nullptr; };
+inline void ctx_switch(Ctx *from, Ctx *to) { kr_emu_switch(&from->sp, to->sp); }
+inline void ctx_make(Ctx *c, uint8_t *stack, size_t bytes, void (*entry)()) {
+    uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~uintptr_t(15);
+    void **sp = reinterpret_cast<void **>(top);
+    *--sp = nullptr;                                   // return address of `entry` (it never returns)
+    *--sp = reinterpret_cast<void *>(entry);           // popped by the `ret` of the first switch
+    for (int i = 0; i < 6; ++i) *--sp = nullptr;       // rbp rbx r12 r13 r14 r15
+    c->sp = sp;
+}
+#else
+struct Ctx { ucontext_t uc; };
+inline void ctx_switch(Ctx *from, Ctx *to) { swapcontext(&from->uc, &to->uc); }
+inline void ctx_make(Ctx *c, uint8_t *stack, size_t bytes, void (*entry)()) {
+    getcontext(&c->uc); c->uc.uc_stack.ss_sp = stack; c->uc.uc_stack.ss_size = bytes; c->uc.uc_link = nullptr;
+    makecontext(&c->uc, entry, 0);
+}
+#endif
+struct Fiber { Ctx ctx; dim3 tid; bool done = false; std::vector<uint8_t> stack; };
 struct Sched {
-    ucontext_t main;
+    Ctx main;
     std::vector<Fiber> fibers;
     unsigned cur = 0;
     unsigned long long idle_yields = 0;   // yields since the last sign of progress
@@ -65,7 +93,7 @@ inline void progress() { sched()->idle_yields = 0; }
 inline void yield() {
     Sched *s = sched();
     if (++s->idle_yields > 50000000ull) { fprintf(stderr, "cuda_emul: deadlock (every thread of the CTA is waiting)\n"); abort(); }
-    swapcontext(&s->fibers[s->cur].ctx, &s->main);
+    ctx_switch(&s->fibers[s->cur].ctx, &s->main);
 }
 
 // a reusable counting barrier whose party count can shrink (threads that leave the kernel early)
@@ -113,7 +141,8 @@ inline void fiber_main() {
     progress();
     cur_block()->sync.drop();                      // a thread that has left the kernel no longer takes part
     cur_block()->warps[f.tid.x >> 5]->bar.drop();
-    swapcontext(&f.ctx, &s->main);
+    ctx_switch(&f.ctx, &s->main);
+    abort();                                       // a finished fiber is never resumed
 }
 
 }  // namespace emu
@@ -146,9 +175,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
         for (unsigned t = 0; t < block.x; ++t) {
             Fiber &f = sc.fibers[t];
             f.done = false; f.tid = dim3(t);
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack.data(); f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = &sc.main;
-            makecontext(&f.ctx, (void (*)())fiber_main, 0);
+            ctx_make(&f.ctx, f.stack.data(), stack_bytes, fiber_main);
         }
         sc.idle_yields = 0;
         for (unsigned live = block.x; live;) {
@@ -156,7 +183,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
             for (unsigned t = 0; t < block.x; ++t) {
                 if (sc.fibers[t].done) continue;
                 sc.cur = t;
-                swapcontext(&sc.main, &sc.fibers[t].ctx);
+                ctx_switch(&sc.main, &sc.fibers[t].ctx);
                 if (!sc.fibers[t].done) ++live;
             }
         }
