@@ -283,6 +283,8 @@ def main():
     ap.add_argument("--exp-pairs", action="store_true",
                     help="EXPERIMENTAL library only: all-vs-all through the posting-list path (context flag EXP_PAIRS)")
     ap.add_argument("--exp-buckets", action="store_true", help="EXPERIMENTAL library only, with --exp-pairs: group by key in shared memory after a bucket partition")
+    ap.add_argument("--key-partition", action="store_true",
+                    help="EXPERIMENTAL library only, N>1 with --exp-pairs: count pairs by key partition and all-to-all the partial counts")
     ap.add_argument("--exp-encode", action="store_true", help="EXPERIMENTAL library only: K1 with one warp per sequence (EXP_ENCODE)")
     ap.add_argument("--exp-idxq", action="store_true", help="EXPERIMENTAL library only: K5 with one warp per query (EXP_IDXQ; findclosest workload)")
     ap.add_argument("--exp-gidx", action="store_true", help="EXPERIMENTAL library only: greedy build through the growing index (EXP_GIDX; findclosest workload)")
@@ -335,6 +337,9 @@ def main():
         # exchange step of the path); N=1 or --replicated-encode: every rank encodes everything
         if sharded_encode and args.exp_pairs:      # the posting-list path needs key lists: exchange those instead of block lists
             s = sharding.encode_sharded_keys(ctx, d_res, off, dist)
+            if args.key_partition:                 # ... and split the pair counting by key, not only the result by row
+                sharding.allvsall_by_key_partition(ctx, s, d_out, dist, elem=elem, layout=layout)
+                return s
         else:
             s = sharding.encode_sharded(ctx, d_res, off, dist) if sharded_encode else ctx.encode_device(d_res.data_ptr(), off)
         ctx.sim_matrix_device(s, None, d_out.data_ptr(), elem=elem, layout=layout, row_begin=r0, row_end=r1)

@@ -144,6 +144,11 @@ def load_library():
         lib.kr_keylist_capacity.restype = u64
         lib.kr_seqset_export_keys.argtypes = [vp, vp, C.POINTER(KeyLists)]
         lib.kr_seqset_import_keys.argtypes = [vp, C.POINTER(KeyLists), u32, vp, vp, u32, C.POINTER(vp)]
+    if hasattr(lib, "kr_pairs_partial"):
+        lib.kr_pairs_partial.argtypes = [vp, vp, u32, u32, vp, C.POINTER(vp), vp]
+        lib.kr_pairs_partial_free.argtypes = [vp, vp]
+        lib.kr_pairs_partial_free.restype = None
+        lib.kr_pairs_apply.argtypes = [vp, vp, C.POINTER(MatrixDesc), vp, u64, vp]
     _LIB = lib
     return lib
 
@@ -264,6 +269,23 @@ class Context:
         h = C.c_void_p()
         self._ck(self.lib.kr_seqset_import_keys(self.h, arr, len(shards), d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
         return SeqSet(self, h)
+
+    def pairs_partial(self, s: "SeqSet", part: int, nparts: int, row_bounds):
+        """-> (device pointer to the uint4 cells grouped by destination, per-destination cell counts)"""
+        rb = np.ascontiguousarray(row_bounds, dtype=np.uint32)
+        counts = np.zeros(nparts, dtype=np.uint64)
+        cells = C.c_void_p()
+        self._ck(self.lib.kr_pairs_partial(self.h, s.h, part, nparts, rb.ctypes.data, C.byref(cells), counts.ctypes.data))
+        return cells.value or 0, counts
+
+    def pairs_partial_free(self, d_cells: int):
+        if d_cells:
+            self.lib.kr_pairs_partial_free(self.h, d_cells)
+
+    def pairs_apply(self, s: "SeqSet", d_cells: int, ncells: int, d_out_ptr: int, elem=ELEM_U16, layout=LAYOUT_BLOCKTRI, row_begin=0, row_end=None):
+        row_end = s.count if row_end is None else row_end
+        d = MatrixDesc(elem, layout, row_begin, row_end)
+        self._ck(self.lib.kr_pairs_apply(self.h, s.h, C.byref(d), d_cells, int(ncells), d_out_ptr))
 
     def key_decode(self, key: int) -> str:
         buf = C.create_string_buffer(self.K)

@@ -545,26 +545,41 @@ static kr_status ensure_postings(kr_ctx *ctx, kr_seqset *s) {
     return KR_OK;
 }
 
-// EXPERIMENTAL: the (key, sequence) entries of a set partitioned into buckets of ~1,000 by key hash (kr_pairs.cuh)
-static kr_status ensure_buckets(kr_ctx *ctx, kr_seqset *s) {
-    if (s->bk_ready) return KR_OK;
-    const u64 entries = s->key_cap;
-    if (entries >= 0xFFFFFFF0ull) return fail(ctx, KR_ERR_ARG, "posting-list path: set too large (%llu k-mers)", (unsigned long long)entries);
-    u32 nb = 1; while ((u64)nb * 1024 < entries && nb < (1u << 22)) nb <<= 1;
+// EXPERIMENTAL: the (key, sequence) entries of a set -- all of them, or those of key partition `part` of `nparts` --
+// partitioned into buckets of ~1,000 by key hash (kr_pairs.cuh)
+struct Buckets {
+    u32 nb = 0; u32 *base = nullptr, *eseq = nullptr, *post = nullptr; u64 *ekey = nullptr;
+    BucketParams params() const { BucketParams bp{}; bp.base = base; bp.nb = nb; bp.ekey = ekey; bp.eseq = eseq; bp.post = post; return bp; }
+    void release(kr_ctx *ctx) { dfree(ctx, base); dfree(ctx, eseq); dfree(ctx, post); dfree(ctx, ekey); base = eseq = post = nullptr; ekey = nullptr; }
+};
+static kr_status build_buckets(kr_ctx *ctx, const kr_seqset *s, u32 part, u32 nparts, Buckets *bk) {
+    const u64 entries = s->key_cap / std::max(1u, nparts) + s->key_cap / 8 + 1024;   // a partition's share, with slack for imbalance
+    const u64 cap = nparts > 1 ? std::min<u64>(entries, s->key_cap) : s->key_cap;
+    if (s->key_cap >= 0xFFFFFFF0ull) return fail(ctx, KR_ERR_ARG, "posting-list path: set too large (%llu k-mers)", (unsigned long long)s->key_cap);
+    u32 nb = 1; while ((u64)nb * 1024 < cap && nb < (1u << 22)) nb <<= 1;
     u32 *d_hist = nullptr, *d_cursor = nullptr;
-    CU(dalloc(ctx, &d_hist, nb)); CU(dalloc(ctx, &d_cursor, nb)); CU(dalloc(ctx, &s->bk_base, nb + 1));
-    CU(dalloc(ctx, &s->bk_ekey, entries + 1)); CU(dalloc(ctx, &s->bk_eseq, entries + 1)); CU(dalloc(ctx, &s->bk_post, entries + 1));
+    // the arrays are sized for every entry of the set: a partition can never need more, whatever the hash does
+    CU(dalloc(ctx, &d_hist, nb)); CU(dalloc(ctx, &d_cursor, nb)); CU(dalloc(ctx, &bk->base, nb + 1));
+    CU(dalloc(ctx, &bk->ekey, s->key_cap + 1)); CU(dalloc(ctx, &bk->eseq, s->key_cap + 1)); CU(dalloc(ctx, &bk->post, s->key_cap + 1));
     CU(cudaMemsetAsync(d_hist, 0, (size_t)nb * 4, ctx->stream)); CU(cudaMemsetAsync(d_cursor, 0, (size_t)nb * 4, ctx->stream));
     {
         StageTimer t(ctx, ST_BLOCKLIST);
-        if (s->n) KR_LAUNCH(KR_T(k_bk_count), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, d_hist);
-        KR_LAUNCH(KR_T(k_bk_scan), 1, 1024, 0, ctx->stream, d_hist, nb, s->bk_base);
-        if (s->n) KR_LAUNCH(KR_T(k_bk_scatter), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, s->bk_base, d_cursor, s->bk_ekey, s->bk_eseq);
+        if (s->n) KR_LAUNCH(KR_T(k_bk_count), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, d_hist, part, nparts);
+        KR_LAUNCH(KR_T(k_bk_scan), 1, 1024, 0, ctx->stream, d_hist, nb, bk->base);
+        if (s->n) KR_LAUNCH(KR_T(k_bk_scatter), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, bk->base, d_cursor, bk->ekey, bk->eseq, part, nparts);
         ctx->st.kernel_launches += 3;
         CU(cudaGetLastError());
     }
     dfree(ctx, d_hist); dfree(ctx, d_cursor);
-    s->bk_nb = nb; s->bk_ready = true;
+    bk->nb = nb;
+    return KR_OK;
+}
+static kr_status ensure_buckets(kr_ctx *ctx, kr_seqset *s) {
+    if (s->bk_ready) return KR_OK;
+    Buckets bk;
+    kr_status st = build_buckets(ctx, s, 0, 1, &bk);
+    if (st) { bk.release(ctx); return st; }
+    s->bk_nb = bk.nb; s->bk_base = bk.base; s->bk_ekey = bk.ekey; s->bk_eseq = bk.eseq; s->bk_post = bk.post; s->bk_ready = true;
     return KR_OK;
 }
 static BucketParams bucket_params(const kr_seqset *s) {
@@ -1308,6 +1323,108 @@ kr_status kr_seqset_import_keys(kr_ctx *ctx, const kr_keylists *shards, uint32_t
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));   // off / koff are stack-lifetime staging buffers
     *out = s.release();
+    return KR_OK;
+}
+
+// EXPERIMENTAL: all-vs-all over several GPUs by KEY partition (posting-list path).  kr_pairs_partial counts, for the
+// keys of partition `part` of `nparts`, the pairs (i < j) over ALL rows in a pair table and returns its cells grouped by
+// the destination that owns row i (row_bounds[0 .. nparts]: destination d owns rows [row_bounds[d], row_bounds[d+1]));
+// the caller exchanges the groups (all-to-all) and hands what it received to kr_pairs_apply, which zero-fills its stripe
+// of the result, adds the partial counts, and applies the equal-sequence rule and the diagonal.
+kr_status kr_pairs_partial(kr_ctx *ctx, const kr_seqset *set, uint32_t part, uint32_t nparts, const uint32_t *row_bounds,
+                           void **d_cells, uint64_t *counts) {
+    if (!ctx || !set || !row_bounds || !d_cells || !counts || !nparts || part >= nparts || nparts > PT_MAXDEST)
+        return fail(ctx, KR_ERR_ARG, "kr_pairs_partial: bad argument (1 <= nparts <= %u)", PT_MAXDEST);
+    if (set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_pairs_partial: set belongs to another context");
+    if (!set->d_keys && set->n) return fail(ctx, KR_ERR_STATE, "kr_pairs_partial: this set has no key lists");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    *d_cells = nullptr;
+    for (u32 k = 0; k < nparts; ++k) counts[k] = 0;
+    Buckets bk;
+    kr_status st = build_buckets(ctx, set, part, nparts, &bk);
+    unsigned long long *d_work = nullptr, work = 0;
+    if (st == KR_OK) {   // table capacity from this partition's pair increments
+        CU(dalloc(ctx, &d_work, 1 + 2 * PT_MAXDEST));
+        CU(cudaMemsetAsync(d_work, 0, 8 * (1 + 2 * PT_MAXDEST), ctx->stream));
+        WorkSink ws{d_work};
+        KR_LAUNCH(KR_T(k_bk_pairs<WorkSink>), std::min<u32>(bk.nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bk.params(), ws);
+        LAUNCHED(ctx);
+        CU(cudaMemcpyAsync(&work, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    u64 pcap = 1024; while (pcap < 2 * work && pcap <= (1ull << 30)) pcap <<= 1;
+    if (st == KR_OK && pcap > (1ull << 30)) st = fail(ctx, KR_ERR_ARG, "kr_pairs_partial: %llu pair increments in one partition: use the tile join", work);
+    PairTabParams p{};
+    uint4 *cells = nullptr;
+    if (st == KR_OK) {
+        p.pt_mask = pcap - 1; p.N = set->n; p.row_begin = 0; p.row_end = set->n; p.min_sim = 1;
+        CU(dalloc(ctx, &p.pt_key, pcap)); CU(dalloc(ctx, &p.pt_cnt, pcap));
+        CU(cudaMemsetAsync(p.pt_key, 0xFF, pcap * 8, ctx->stream));
+        CU(cudaMemsetAsync(p.pt_cnt, 0, pcap * 4, ctx->stream));
+        DestParams dp{}; dp.nd = nparts;
+        for (u32 k = 0; k <= nparts; ++k) dp.rb[k] = row_bounds[k];
+        unsigned long long *d_count = d_work + 1, *d_cursor = d_work + 1 + PT_MAXDEST;
+        {
+            StageTimer t(ctx, ST_JOIN);
+            TableSink tsink{p};
+            KR_LAUNCH(KR_T(k_bk_pairs<TableSink>), std::min<u32>(bk.nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bk.params(), tsink);
+            KR_LAUNCH(KR_T(k_pt_count_dest), ctx->num_sms * 4, 256, 0, ctx->stream, p, dp, d_count);
+            ctx->st.kernel_launches += 2; ctx->st.join_launches++;
+        }
+        unsigned long long h_count[PT_MAXDEST], h_offs[PT_MAXDEST];
+        CU(cudaMemcpyAsync(h_count, d_count, 8 * nparts, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        u64 total = 0;
+        for (u32 k = 0; k < nparts; ++k) { h_offs[k] = total; total += h_count[k]; counts[k] = h_count[k]; }
+        unsigned long long *d_offs = nullptr;
+        CU(dalloc(ctx, &cells, total + 1)); CU(dalloc(ctx, &d_offs, nparts));
+        CU(cudaMemcpyAsync(d_offs, h_offs, 8 * nparts, cudaMemcpyHostToDevice, ctx->stream));
+        KR_LAUNCH(KR_T(k_pt_fill_dest), ctx->num_sms * 4, 256, 0, ctx->stream, p, dp, d_offs, d_cursor, cells);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));   // h_offs is a stack buffer; the caller reads `cells` from another stream
+        dfree(ctx, d_offs);
+        *d_cells = cells;
+    }
+    dfree(ctx, p.pt_key); dfree(ctx, p.pt_cnt); dfree(ctx, d_work);
+    bk.release(ctx);
+    return st;
+}
+void kr_pairs_partial_free(kr_ctx *ctx, void *d_cells) {
+    if (!ctx || !d_cells) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->dev);
+    dfree(ctx, (uint4 *)d_cells);
+}
+kr_status kr_pairs_apply(kr_ctx *ctx, const kr_seqset *set, const kr_matrix_desc *desc, const void *d_cells, uint64_t ncells, void *out_dev) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    kr_status st = check_desc(ctx, set, nullptr, desc);
+    if (st) return st;
+    if (!out_dev || (!d_cells && ncells) || desc->layout == KR_LAYOUT_FULL || (reinterpret_cast<uintptr_t>(out_dev) & 3))
+        return fail(ctx, KR_ERR_ARG, "kr_pairs_apply: bad argument (layout TRIANGLE or BLOCKTRI; output 4-byte aligned)");
+    CU(cudaSetDevice(ctx->dev));
+    PairsParams p{};
+    p.out = out_dev; p.elem = desc->elem; p.layout = desc->layout; p.N = set->n; p.row_begin = desc->row_begin; p.row_end = desc->row_end; p.flags = ctx->flags & 1u;
+    p.origin = row_start(desc->layout, desc->row_begin, set->n, set->n);
+    p.total = row_start(desc->layout, desc->row_end, set->n, set->n) - p.origin;
+    p.meta = set->d_meta;
+    u32 hm = 1024; while (hm < 2 * set->n) hm <<= 1;
+    CU(dalloc(ctx, &p.head, hm)); CU(dalloc(ctx, &p.next, set->n));
+    p.head_mask = hm - 1;
+    CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
+    {
+        StageTimer t(ctx, ST_JOIN);
+        CU(cudaMemsetAsync(out_dev, 0, p.total * (desc->elem == KR_ELEM_U16 ? 2 : 4), ctx->stream));
+        if (ncells) KR_LAUNCH(KR_T(k_cells_apply), ctx->num_sms * 8, 256, 0, ctx->stream, p, (const uint4 *)d_cells, (u64)ncells);
+        KR_LAUNCH(KR_T(k_pairs_dup_insert), (set->n + 255) / 256, 256, 0, ctx->stream, p);
+        KR_LAUNCH(KR_T(k_pairs_dup_fix), (set->n + 255) / 256, 256, 0, ctx->stream, p);
+        ctx->st.kernel_launches += 3; ctx->st.join_launches++;
+        CU(cudaGetLastError());
+    }
+    dfree(ctx, p.head); dfree(ctx, p.next);
+    ctx->st.pairs += kr_matrix_elems(set->n, set->n, KR_LAYOUT_TRIANGLE, desc->row_begin, desc->row_end);
     return KR_OK;
 }
 

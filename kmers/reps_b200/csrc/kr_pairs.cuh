@@ -63,18 +63,18 @@ KRP_DEVICE u32 pairs_tri_row(u64 t) {
     return (u32)b;
 }
 
-KRP_DEVICE void pairs_cell_add(const PairsParams &p, u64 idx) {
+KRP_DEVICE void pairs_cell_add(const PairsParams &p, u64 idx, u32 v = 1) {
     if (p.elem == 1) {
         u16 *c = reinterpret_cast<u16 *>(p.out) + idx;
         if ((idx & 1) == 0 && idx + 1 >= p.total) {
             // the last cell of an odd-sized result has no upper half word inside the buffer: 16-bit CAS loop
             unsigned short old = *c, assumed;
-            do { assumed = old; old = atomicCAS(reinterpret_cast<unsigned short *>(c), assumed, (unsigned short)(assumed + 1)); } while (old != assumed);
+            do { assumed = old; old = atomicCAS(reinterpret_cast<unsigned short *>(c), assumed, (unsigned short)(assumed + v)); } while (old != assumed);
         } else {
-            atomicAdd(reinterpret_cast<u32 *>(p.out) + (idx >> 1), (idx & 1) ? 0x10000u : 1u);
+            atomicAdd(reinterpret_cast<u32 *>(p.out) + (idx >> 1), (idx & 1) ? (v << 16) : v);
         }
     } else {
-        atomicAdd(reinterpret_cast<int *>(p.out) + idx, 1);
+        atomicAdd(reinterpret_cast<int *>(p.out) + idx, (int)v);
     }
 }
 KRP_DEVICE void pairs_cell_set(const PairsParams &p, u64 idx, u32 v) {
@@ -88,11 +88,11 @@ template <bool SET>
 KRP_DEVICE void pairs_touch(const PairsParams &p, u32 i, u32 j, u32 v) {
     if (i >= p.row_begin && i < p.row_end) {
         const u64 idx = pairs_cell_index(p.layout, i, j, p.N) - p.origin;
-        if (SET) pairs_cell_set(p, idx, v); else pairs_cell_add(p, idx);
+        if (SET) pairs_cell_set(p, idx, v); else pairs_cell_add(p, idx, v);
     }
     if (p.layout != 1 && j >= p.row_begin && j < p.row_end && (p.layout == 0 || (i >> 8) == (j >> 8))) {
         const u64 idx = pairs_cell_index(p.layout, j, i, p.N) - p.origin;
-        if (SET) pairs_cell_set(p, idx, v); else pairs_cell_add(p, idx);
+        if (SET) pairs_cell_set(p, idx, v); else pairs_cell_add(p, idx, v);
     }
 }
 
@@ -113,7 +113,7 @@ KRP_GLOBAL void k_pairs_emit(PairsParams p) {
                 const u32 b = pairs_tri_row(t), a = (u32)(t - (u64)b * (b - 1) / 2);
                 u32 i = p.postings[off + a], j = p.postings[off + b];
                 if (i > j) { const u32 x = i; i = j; j = x; }
-                pairs_touch<false>(p, i, j, 0);
+                pairs_touch<false>(p, i, j, 1);
             }
         }
     }
@@ -260,12 +260,16 @@ __device__ __forceinline__ u64 bk_mix(u64 x) {
 __device__ __forceinline__ u32 bk_bucket(u64 key, u32 nb_mask) { return (u32)(bk_mix(key) >> 40) & nb_mask; }
 
 // pass A: bucket sizes.  One CTA per sequence.
-__global__ void __launch_bounds__(128) k_bk_count(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq, u32 nb_mask, u32 *hist) {
+// With several GPUs each one groups only the keys of its own partition (part of nparts; 0 of 1 = everything).
+__device__ __forceinline__ bool bk_mine(u64 key, u32 part, u32 nparts) { return nparts <= 1 || (u32)((bk_mix(key) >> 12) & 0xFFFFFFu) % nparts == part; }
+
+__global__ void __launch_bounds__(128) k_bk_count(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq, u32 nb_mask, u32 *hist,
+                                                  u32 part, u32 nparts) {
     const u32 s = blockIdx.x;
     if (s >= nseq) return;
     const u32 n = meta[s].size;
     const u64 *kp = keys + koff[s];
-    for (u32 i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[bk_bucket(kp[i], nb_mask)], 1u);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) if (bk_mine(kp[i], part, nparts)) atomicAdd(&hist[bk_bucket(kp[i], nb_mask)], 1u);
 }
 // exclusive scan of the bucket sizes (one CTA); base[nb] = total
 __global__ void __launch_bounds__(1024) k_bk_scan(const u32 *hist, u32 nb, u32 *base) {
@@ -283,13 +287,14 @@ __global__ void __launch_bounds__(1024) k_bk_scan(const u32 *hist, u32 nb, u32 *
 }
 // pass B: entries into their buckets (order inside a bucket is arbitrary)
 __global__ void __launch_bounds__(128) k_bk_scatter(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq, u32 nb_mask, const u32 *base,
-                                                    u32 *cursor, u64 *ekey, u32 *eseq) {
+                                                    u32 *cursor, u64 *ekey, u32 *eseq, u32 part, u32 nparts) {
     const u32 s = blockIdx.x;
     if (s >= nseq) return;
     const u32 n = meta[s].size;
     const u64 *kp = keys + koff[s];
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
         const u64 key = kp[i];
+        if (!bk_mine(key, part, nparts)) continue;
         const u32 b = bk_bucket(key, nb_mask);
         const u32 pos = base[b] + atomicAdd(&cursor[b], 1u);
         ekey[pos] = key; eseq[pos] = s;
@@ -304,7 +309,7 @@ struct BucketParams {
 struct DenseSink {    // result cells in HBM (kr_pairs_emit's target)
     static constexpr bool COUNT_ONLY = false;
     PairsParams p;
-    __device__ __forceinline__ void add(u32 i, u32 j) const { pairs_touch<false>(p, i, j, 0); }
+    __device__ __forceinline__ void add(u32 i, u32 j) const { pairs_touch<false>(p, i, j, 1); }
     __device__ __forceinline__ void group(u64) const {}
 };
 struct TableSink {    // pair hash table (the sparse result)
@@ -408,6 +413,57 @@ __global__ void __launch_bounds__(BK_THREADS) k_bk_pairs(BucketParams bp, SINK s
             __syncthreads();                                             // before the table is cleared for the next pass / bucket
         }
     }
+}
+
+// ---- several GPUs: partial pair counts travel to the owner of their row ----------------------------------------------
+// Every GPU counts the pairs of ITS key partition in a pair table (k_bk_pairs<TableSink> over all rows), sorts the
+// table's cells by the rank that owns row i (row stripes), the cells are exchanged (all-to-all), and each owner adds
+// the partial counts it received into its stripe of the result.
+constexpr u32 PT_MAXDEST = 64;
+struct DestParams { u32 nd; u32 rb[PT_MAXDEST + 1]; };     // destination d owns rows [rb[d], rb[d + 1])
+__device__ __forceinline__ u32 pt_dest(const DestParams &d, u32 row) { u32 k = 0; while (k + 1 < d.nd && row >= d.rb[k + 1]) ++k; return k; }
+
+// cells per destination (block-aggregated counters)
+__global__ void __launch_bounds__(256) k_pt_count_dest(PairTabParams p, DestParams d, unsigned long long *count) {
+    __shared__ u32 s_cnt[PT_MAXDEST];
+    if (threadIdx.x < PT_MAXDEST) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (u64)gridDim.x * blockDim.x;
+    for (u64 s = tid; s <= p.pt_mask; s += nthr) {
+        const unsigned long long k = p.pt_key[s];
+        if (k != PAIRTAB_EMPTY && p.pt_cnt[s]) atomicAdd(&s_cnt[pt_dest(d, (u32)(k >> 32))], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < d.nd && s_cnt[threadIdx.x]) atomicAdd(&count[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+// cells grouped by destination: destination k's cells start at offs[k]; each CTA owns a contiguous range of slots,
+// counts it, reserves its share of every destination's region with one atomic each, then writes
+__global__ void __launch_bounds__(256) k_pt_fill_dest(PairTabParams p, DestParams d, const unsigned long long *offs, unsigned long long *cursor, uint4 *cells) {
+    __shared__ u32 s_cnt[PT_MAXDEST];
+    __shared__ unsigned long long s_base[PT_MAXDEST];
+    const u64 nslots = p.pt_mask + 1, per = (nslots + gridDim.x - 1) / gridDim.x;
+    const u64 s0 = (u64)blockIdx.x * per, s1 = s0 + per < nslots ? s0 + per : nslots;
+    if (threadIdx.x < PT_MAXDEST) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (u64 s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const unsigned long long k = p.pt_key[s];
+        if (k != PAIRTAB_EMPTY && p.pt_cnt[s]) atomicAdd(&s_cnt[pt_dest(d, (u32)(k >> 32))], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < d.nd) { s_base[threadIdx.x] = offs[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]); s_cnt[threadIdx.x] = 0; }
+    __syncthreads();
+    for (u64 s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const unsigned long long k = p.pt_key[s];
+        const u32 c = p.pt_cnt[s];
+        if (k == PAIRTAB_EMPTY || !c) continue;
+        const u32 dd = pt_dest(d, (u32)(k >> 32));
+        cells[s_base[dd] + atomicAdd(&s_cnt[dd], 1u)] = make_uint4((u32)(k >> 32), (u32)k, c, 0u);
+    }
+}
+// the owner adds the partial counts it received (several ranks may send the same pair)
+__global__ void __launch_bounds__(256) k_cells_apply(PairsParams p, const uint4 *cells, u64 n) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (u64)gridDim.x * blockDim.x;
+    for (u64 k = tid; k < n; k += nthr) { const uint4 c = cells[k]; pairs_touch<false>(p, c.x, c.y, c.z); }
 }
 
 }  // namespace kr

@@ -183,6 +183,39 @@ def encode_sharded_keys(ctx, d_res, off, dist):
     return full
 
 
+def allvsall_by_key_partition(ctx, s, d_out, dist, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI):
+    """EXPERIMENTAL library only.  All-vs-all of the set `s` (the same on every rank, with key lists: encode_sharded_keys)
+    over the ranks by KEY partition: this rank counts the pairs of its share of the k-mers over all rows
+    (kr_pairs_partial), the partial counts are exchanged with one all_to_all so that every cell reaches the rank that
+    owns its row stripe, and the owner adds them up into `d_out` (its stripe, `layout` order; kr_pairs_apply).  Every
+    step scales with 1 / world; what is exchanged is proportional to the number of pairs that share a k-mer, not to N^2.
+    Returns (row_begin, row_end) of this rank's stripe."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = s.count
+    rb = kr.matrix_stripes(n, n, layout, world)
+    d_cells, counts = ctx.pairs_partial(s, rank, world, rb)
+    dev = d_out.device
+    send_counts = torch.from_numpy(counts.astype(np.int64))
+    recv_counts = torch.empty(world, dtype=torch.int64)
+    if torch.device(dev).type == "cuda":
+        sc, rc = send_counts.to(dev), recv_counts.to(dev)
+        dist.all_to_all_single(rc, sc)
+        recv_counts = rc.cpu()
+    else:
+        dist.all_to_all_single(recv_counts, send_counts)
+    total_send, total_recv = int(counts.sum()), int(recv_counts.sum())
+    send = _view(d_cells, total_send * 16, dev) if total_send else torch.empty(0, dtype=torch.uint8, device=dev)
+    recv = torch.empty(total_recv * 16, dtype=torch.uint8, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * 16 for c in recv_counts], input_split_sizes=[int(c) * 16 for c in counts])
+    _sync(dev)
+    ctx.pairs_partial_free(d_cells)
+    r0, r1 = int(rb[rank]), int(rb[rank + 1])
+    ctx.pairs_apply(s, recv.data_ptr(), total_recv, d_out.data_ptr(), elem=elem, layout=layout, row_begin=r0, row_end=r1)
+    ctx.synchronize()                                      # `recv` may be released once the kernels that read it are done
+    return r0, r1
+
+
 # ---- greedy representative-set build with the candidate-vs-database scoring split over the ranks ------------
 def greedy_build_sharded(n_cands: int, threshold: int, batch: int, dist, score_slice, survivor_matrix, accept, device=None):
     """RepGenomeDb.checkGenome over `n_cands` candidates in order (RepGenomeDbProcessor.java:160-163,

@@ -47,6 +47,16 @@ def worker(rank, world, port, q):
             assert (whole.numpy().view(np.uint16) == want).all(), (mode, rank)
             if mode == "keys+pairs":
                 assert (s.sizes() == o.batch(seqs, K=8).sizes()).all()
+            if mode == "keys+pairs":
+                # the same result by KEY partition: partial pair counts travel to the owner of their row (all_to_all)
+                out2 = torch.zeros(elems + 8, dtype=torch.int16)
+                assert sharding.allvsall_by_key_partition(ctx, s, out2, dist, elem=kr.ELEM_U16, layout=layout) == (r0, r1)
+                assert (out2[:elems].numpy().view(np.uint16) == want[first:first + elems]).all(), ("key partition", rank)
+                tri = o.sim_matrix(o.batch(seqs, K=8), ident_inf=True, threads=2)[np.triu_indices(n, 1)]
+                t0, t1, telems, tfirst = sharding.my_stripe(n, kr.LAYOUT_TRIANGLE, rank, world)
+                out3 = torch.zeros(telems + 8, dtype=torch.int32)
+                sharding.allvsall_by_key_partition(ctx, s, out3, dist, elem=kr.ELEM_I32, layout=kr.LAYOUT_TRIANGLE)
+                assert (out3[:telems].numpy() == tri[tfirst:tfirst + telems]).all(), ("key partition, triangle", rank)
             ctx.close()
         q.put((rank, "ok"))
     except Exception as e:
