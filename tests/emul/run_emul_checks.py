@@ -147,6 +147,49 @@ def case_sharded_import():
     c.close()
 
 
+def case_api_misc():
+    """the rest of the ABI on small inputs: row stripes of a FULL matrix over three blocks, gathers of gathers, append_set,
+    any_ge, the deferred alphabet error of the device encode, statistics"""
+    seqs = family(20, 600, 9, 40, 90)
+    ob = O.batch(seqs, K=8)
+    want = O.sim_matrix(ob, ident_inf=True, threads=4)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    s = c.encode(seqs)
+    for (r0, r1) in ((0, 256), (256, 600), (512, 600)):
+        assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL, row_begin=r0, row_end=r1) == want[r0:r1]).all()
+        tri = c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1)
+        assert (tri == np.concatenate([want[i, i + 1:] for i in range(r0, r1)])).all()
+    idx = np.array([599, 3, 3, 258, 0, 511, 300], dtype=np.uint32)
+    g1 = s.gather(idx)
+    g2 = g1.gather(np.array([6, 0, 2], dtype=np.uint32))
+    assert (g1.sizes() == ob.sizes()[idx]).all()
+    assert (c.sim_matrix(g1, g2) == want[np.ix_(idx, idx[[6, 0, 2]])]).all()
+    assert (c.sim_matrix(g2, s)[1] == want[599]).all()
+    db = c.db()
+    db.append_set(s, np.arange(100, 400, dtype=np.uint32))
+    db.append_set(g1, np.array([0, 4], dtype=np.uint32))                # 599 and 0
+    assert db.size == 302
+    rep_rows = list(range(100, 400)) + [599, 0]
+    sim, first, last = db.find_closest(s)
+    sub = want[:, rep_rows]
+    assert (sim == sub.max(1)).all()
+    assert (first == np.where(sub.max(1) > 0, sub.argmax(1), kr.NO_REP)).all()
+    assert (db.any_ge(s, 40) == (sub.max(1) >= 40)).all()
+    st = c.stats()
+    assert st["kernel_launches"] > 10 and st["pairs"] > 0 and st["join_launches"] > 0
+    # a residue outside the alphabet in a device-side encode is reported at the next call that synchronises
+    bad, boff = kr.flat(["MKVLAAGIVGLAAA", "MKVLA#GIVGAAAA"])
+    sd = c.encode_device(bad.ctypes.data, boff)
+    try:
+        c.synchronize()
+        raise AssertionError("expected the alphabet error")
+    except kr.KrError as e:
+        assert e.code == -4 and "sequence 1 position 5" in str(e)
+    sd.free()
+    assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL, row_begin=512, row_end=600) == want[512:]).all()   # still usable
+    c.close()
+
+
 def case_exp_sparse_join():
     """EXPERIMENTAL: sparse result from the join's epilogue filter"""
     seqs = family(15, 300, 6, 60, 120)

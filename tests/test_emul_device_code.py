@@ -47,7 +47,7 @@ def test_bucket_grouping_sub_passes_on_the_emulator(emul_lib):
     assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK exp_pairs"), p.stdout.decode()[-3000:]
 
 
-@pytest.mark.parametrize("case", ["matrix_layouts", "k10_rectangular_pairs", "find_closest_and_build", "subchunks", "sharded_import",
+@pytest.mark.parametrize("case", ["matrix_layouts", "k10_rectangular_pairs", "find_closest_and_build", "subchunks", "sharded_import", "api_misc",
                                   "exp_sparse_join", "exp_pairs", "exp_encode_warp", "exp_idxq_warp", "exp_gidx_build"])
 def test_device_code_on_the_emulator(emul_lib, case):
     env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2")
@@ -64,3 +64,16 @@ def test_sharded_paths_end_to_end_on_the_emulator(emul_lib, world):
     p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_sharded.py"), str(world)], env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, timeout=1500)
     assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK sharded %d" % world), p.stdout.decode()[-3000:]
+
+
+def test_host_tools_on_the_emulator(emul_lib, tmp_path):
+    """the C++ host layer and its commands (tests/test_host_tools.py, byte-level output checks) with the emulator build
+    standing in for libkmersreps_cuda.so: the same test file the GPU box runs, here as a logic check of host + device code"""
+    d = tmp_path / "as_cuda"
+    d.mkdir()
+    os.symlink(emul_lib, d / "libkmersreps_cuda.so")
+    env = dict(os.environ, KR_LIB_PATH=str(d / "libkmersreps_cuda.so"), LD_LIBRARY_PATH=str(d), KR_EMUL_SMS="2")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_host_tools.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "neighbors or classify or distances or group or error_behaviour or load_report"], env=env, cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200)
+    assert p.returncode == 0, p.stdout.decode()[-3000:]
