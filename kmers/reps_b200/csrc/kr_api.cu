@@ -1479,7 +1479,7 @@ kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
                 KR_LAUNCH(KR_T(k_pairs_emit_tab), ctx->num_sms * 8, 256, 0, ctx->stream, p);
                 KR_LAUNCH(KR_T(k_pairs_dup_insert_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);
                 KR_LAUNCH(KR_T(k_pairs_dup_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);
-                KR_LAUNCH(KR_T(k_pairs_compact), ctx->num_sms * 8, 256, 0, ctx->stream, p);
+                KR_LAUNCH(KR_T(k_pairs_compact_blk), ctx->num_sms * 8, 256, 0, ctx->stream, p);
                 ctx->st.kernel_launches += 4; ctx->st.join_launches++;
                 CU(cudaGetLastError());
             }

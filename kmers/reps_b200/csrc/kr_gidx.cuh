@@ -43,6 +43,9 @@ __global__ void __launch_bounds__(128) k_gidx_insert(const u64 *keys, const u64 
         g.rmeta[rep_base + s] = m;
         if (m.size == 0) g.empty_reps[atomicAdd(g.empty_count, 1u)] = rep_base + s;
     }
+    __shared__ u32 s_node0;
+    if (threadIdx.x == 0) s_node0 = atomicAdd(g.node_count, m.size);   // one reservation per representative, not one per key
+    __syncthreads();
     const u64 *kp = keys + koff[s];
     for (u32 i = threadIdx.x; i < m.size; i += blockDim.x) {
         const u64 key = kp[i];
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(128) k_gidx_insert(const u64 *keys, const u64 
             if (old == IDX_EMPTY || old == key) break;
             slot = (slot + 1) & g.mask;
         }
-        const u32 node = atomicAdd(g.node_count, 1u);
+        const u32 node = s_node0 + i;
         if (node < g.node_cap) g.nodes[node] = make_uint2(rep_base + s, atomicExch(&g.head[slot], node));
     }
 }

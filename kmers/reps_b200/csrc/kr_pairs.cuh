@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_bk_pairs(BucketParams bp, SINK s
     u32 *tcnt = reinterpret_cast<u32 *>(bk_smem + (size_t)BK_SLOTS * 8), *toff = tcnt + BK_SLOTS;
     __shared__ u32 s_ovf, s_wsum[BK_THREADS / 32];
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u64 work_acc = 0;                                                   // COUNT_ONLY: pair increments seen by this warp
     for (u32 b = blockIdx.x; b < bp.nb; b += gridDim.x) {
         const u32 e0 = bp.base[b], n = bp.base[b + 1] - e0;
         if (n < 2) continue;                                            // uniform for the CTA
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_bk_pairs(BucketParams bp, SINK s
                 if (m < 2) continue;
                 const u32 g0 = e0 + toff[slot] - m;
                 const u64 P = (u64)m * (m - 1) / 2;
-                if (SINK::COUNT_ONLY) { if (lane == 0) sink.group(P); continue; }
+                if (SINK::COUNT_ONLY) { work_acc += P; continue; }           // (every lane keeps the same sum; lane 0 reports it)
                 for (u64 t = lane; t < P; t += 32) {
                     const u32 bb = pairs_tri_row(t), aa = (u32)(t - (u64)bb * (bb - 1) / 2);
                     u32 i = bp.post[g0 + aa], j = bp.post[g0 + bb];
@@ -412,6 +413,36 @@ __global__ void __launch_bounds__(BK_THREADS) k_bk_pairs(BucketParams bp, SINK s
             }
             __syncthreads();                                             // before the table is cleared for the next pass / bucket
         }
+    }
+    if (SINK::COUNT_ONLY && lane == 0 && work_acc) sink.group(work_acc);   // one atomic per warp, not one per group
+}
+
+// block-aggregated form of k_pairs_compact (one global atomic per 2,048 slots instead of one per cell)
+__global__ void __launch_bounds__(256) k_pairs_compact_blk(PairTabParams p) {
+    __shared__ u32 s_n;
+    __shared__ unsigned long long s_base;
+    constexpr u32 PER = 8;
+    const u64 nslots = p.pt_mask + 1, chunk = (u64)blockDim.x * PER;
+    for (u64 c0 = (u64)blockIdx.x * chunk; c0 < nslots; c0 += (u64)gridDim.x * chunk) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        u32 pos[PER]; unsigned long long key[PER]; u32 cnt[PER];
+#pragma unroll
+        for (u32 k = 0; k < PER; ++k) {
+            const u64 s = c0 + (u64)k * blockDim.x + threadIdx.x;            // coalesced: consecutive threads, consecutive slots
+            pos[k] = 0xFFFFFFFFu;
+            if (s < nslots) {
+                key[k] = p.pt_key[s];
+                if (key[k] != PAIRTAB_EMPTY) { cnt[k] = p.pt_cnt[s]; if (cnt[k] >= p.min_sim) pos[k] = atomicAdd(&s_n, 1u); }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_n) s_base = atomicAdd(p.cells_count, (unsigned long long)s_n);
+        __syncthreads();
+#pragma unroll
+        for (u32 k = 0; k < PER; ++k)
+            if (pos[k] != 0xFFFFFFFFu && s_base + pos[k] < p.cells_cap) p.cells[s_base + pos[k]] = make_uint4((u32)(key[k] >> 32), (u32)key[k], cnt[k], 0u);
+        __syncthreads();
     }
 }
 
