@@ -403,12 +403,15 @@ __global__ void __launch_bounds__(BK_THREADS) k_bk_pairs(BucketParams bp, SINK s
                 if (m < 2) continue;
                 const u32 g0 = e0 + toff[slot] - m;
                 const u64 P = (u64)m * (m - 1) / 2;
-                if (SINK::COUNT_ONLY) { work_acc += P; continue; }           // (every lane keeps the same sum; lane 0 reports it)
-                for (u64 t = lane; t < P; t += 32) {
-                    const u32 bb = pairs_tri_row(t), aa = (u32)(t - (u64)bb * (bb - 1) / 2);
-                    u32 i = bp.post[g0 + aa], j = bp.post[g0 + bb];
-                    if (i > j) { const u32 x = i; i = j; j = x; }
-                    sink.add(i, j);
+                if (SINK::COUNT_ONLY) {
+                    work_acc += P;                                       // (every lane keeps the same sum; lane 0 reports it)
+                } else {
+                    for (u64 t = lane; t < P; t += 32) {
+                        const u32 bb = pairs_tri_row(t), aa = (u32)(t - (u64)bb * (bb - 1) / 2);
+                        u32 i = bp.post[g0 + aa], j = bp.post[g0 + bb];
+                        if (i > j) { const u32 x = i; i = j; j = x; }
+                        sink.add(i, j);
+                    }
                 }
             }
             __syncthreads();                                             // before the table is cleared for the next pass / bucket
