@@ -13,6 +13,7 @@
 #define KR_EXP_GIDX 0x1000u        /* context flag (experimental builds): greedy build scores candidates through a growing index */
 #define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
 #define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
+#define KR_LEGACY_PATHS 0x8000u    /* with -DKR_DEFAULTS_V2: keep this context on the hardware-verified round-1 paths */
 #define KR_EXP_BUCKETS 0x2000u     /* posting-list path: group by key in shared memory after a bucket partition (no HBM hash table) */
 #endif
 
@@ -207,6 +208,11 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
         return fail(nullptr, KR_ERR_NODEVICE, "kr_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     if ((size_t)prop.sharedMemPerBlockOptin < JOIN_SMEM_BYTES)
         return fail(nullptr, KR_ERR_NODEVICE, "kr_create: device offers %zu B shared memory per block, need %zu", (size_t)prop.sharedMemPerBlockOptin, JOIN_SMEM_BYTES);
+#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
+    // Build switch for the round after hardware validation: the experimental paths become what every context uses
+    // (the posting-list path only where its work estimate beats the tile join's); KR_LEGACY_PATHS opts a context out.
+    if (!(flags & KR_LEGACY_PATHS)) flags |= KR_EXP_PAIRS_AUTO | KR_EXP_BUCKETS | KR_EXP_ENCODE | KR_EXP_IDXQ | KR_EXP_GIDX;
+#endif
     ctx = new kr_ctx();
     ctx->dev = device; ctx->K = K; ctx->flags = flags; ctx->num_sms = prop.multiProcessorCount;
 #define CUC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(nullptr, KR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); delete ctx; return KR_ERR_CUDA; } } while (0)

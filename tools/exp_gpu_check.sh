@@ -10,6 +10,11 @@ EXP=$PWD/kmers/reps_b200/libkmersreps_cuda_exp.so
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/exp_pytest_default.log
 # 2. the experimental library: the same suite + tests/test_zzz_experimental.py
 KR_LIB_PATH=$EXP timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/exp_pytest_exp.log
+# 2b. the library with the experimental paths as DEFAULTS for every context (what the default becomes after this check):
+#     the whole suite again, host tools included (they find the library through LD_LIBRARY_PATH)
+V2DIR=$(mktemp -d); ln -s $PWD/kmers/reps_b200/libkmersreps_cuda_v2.so $V2DIR/libkmersreps_cuda.so
+KR_LIB_PATH=$V2DIR/libkmersreps_cuda.so LD_LIBRARY_PATH=$V2DIR timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/exp_pytest_v2.log
+KR_LIB_PATH=$V2DIR/libkmersreps_cuda.so timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --sparse-e2e > gpurun_out/exp_bench_v2.json 2> gpurun_out/exp_bench_v2.err
 # 3. timings: default, then each experimental path
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/exp_bench_default.json 2> gpurun_out/exp_bench_default.err
 KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --exp-encode > gpurun_out/exp_bench_encode.json 2> gpurun_out/exp_bench_encode.err
@@ -18,7 +23,7 @@ KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --exp
 KR_LIB_PATH=$EXP timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --sparse-e2e > gpurun_out/exp_bench_sparse_join.json 2> gpurun_out/exp_bench_sparse_join.err
 timeout 600 python bench.py --workload findclosest --steps 2 > gpurun_out/exp_fc_default.json 2> gpurun_out/exp_fc_default.err
 KR_LIB_PATH=$EXP timeout 600 python bench.py --workload findclosest --steps 2 --exp-encode --exp-idxq --exp-gidx > gpurun_out/exp_fc_exp.json 2> gpurun_out/exp_fc_exp.err
-tail -c 600 gpurun_out/exp_pytest_default.log gpurun_out/exp_pytest_exp.log
+tail -c 600 gpurun_out/exp_pytest_default.log gpurun_out/exp_pytest_exp.log gpurun_out/exp_pytest_v2.log
 for f in gpurun_out/exp_bench_*.json gpurun_out/exp_fc_*.json; do echo $f; python - "$f" <<'PY'
 import json, sys
 try:
