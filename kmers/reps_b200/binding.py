@@ -18,6 +18,7 @@ EXP_PAIRS_AUTO = 0x200   # ... only when its work estimate beats the tile join's
 EXP_ENCODE = 0x400       # experimental builds only: K1 with one warp per sequence
 EXP_IDXQ = 0x800         # experimental builds only: K5 with one warp per query where it pays
 EXP_BUCKETS = 0x2000     # experimental builds only: posting-list path groups by key in shared memory (bucket partition)
+ALPHABET_DNA = 0x4000    # experimental builds only: DnaKmers contexts (K-mers of both strands, K = 5..18)
 EXP_GIDX = 0x1000        # experimental builds only: greedy build scores candidates through a growing index
 ELEM_I32, ELEM_U16 = 0, 1
 LAYOUT_FULL, LAYOUT_TRIANGLE, LAYOUT_BLOCKTRI = 0, 1, 2

@@ -10,6 +10,8 @@
 #include "kr_idxq2.cuh"
 #define KR_EXP_IDXQ 0x800u         /* context flag (experimental builds): K5 with one warp per query where it pays */
 #include "kr_gidx.cuh"
+#include "kr_dna.cuh"
+#define KR_ALPHABET_DNA 0x4000u    /* context flag (experimental builds): DnaKmers -- K-mers of both strands, K = 5..18 */
 #define KR_EXP_GIDX 0x1000u        /* context flag (experimental builds): greedy build scores candidates through a growing index */
 #define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
 #define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
@@ -51,6 +53,7 @@ struct DevMem {   // refcounted device allocation (residue buffers are shared by
 };
 
 struct kr_ctx {
+    int dnaK = 0;   // experimental DNA contexts: the DNA k-mer size (K below is then the key width in 5-bit units)
     int dev = 0, K = 8;
     u32 flags = 0;
     int num_sms = 0;
@@ -126,6 +129,11 @@ static kr_status fail(kr_ctx *ctx, kr_status code, const char *fmt, ...) {
     if (ctx) ctx->err = buf; else g_create_error = buf;
     return code;
 }
+// key slots a sequence of L residues can need (one per k-mer position; both strands for DNA contexts)
+static inline u64 kmer_slots(const kr_ctx *ctx, u64 L) {
+    if (ctx->dnaK) return L >= (u64)ctx->dnaK ? 2 * (L - ctx->dnaK + 1) : 0;
+    return L >= (u64)ctx->K ? L - ctx->K + 1 : 0;
+}
 #define CU(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -188,12 +196,21 @@ static void make_chunk_lut(u8 *lut) {
 extern "C" {
 
 const char *kr_last_error(const kr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
-int kr_kmer_size(const kr_ctx *ctx) { return ctx ? ctx->K : 0; }
+int kr_kmer_size(const kr_ctx *ctx) { return ctx ? (ctx->dnaK ? ctx->dnaK : ctx->K) : 0; }
 
 kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     kr_ctx *ctx = nullptr;
     if (!out) return fail(nullptr, KR_ERR_ARG, "kr_create: out is null");
     *out = nullptr;
+    int dnaK = 0;
+#ifdef KR_EXPERIMENTAL
+    if (flags & KR_ALPHABET_DNA) {
+        if (K < 5 || K > 18) return fail(nullptr, KR_ERR_ARG, "kr_create: DNA K=%d outside [5,18] (3 bits per base + 8-bit sequence id in 64 bits)", K);
+        dnaK = K; K = (3 * K + 4) / 5;    // key width in five-bit units
+    }
+#else
+    if (flags & 0xFF00u) return fail(nullptr, KR_ERR_ARG, "kr_create: flags 0x%x are experimental and need a library built with -DKR_EXPERIMENTAL", flags & 0xFF00u);
+#endif
     if (K < KR_MIN_K || K > KR_MAX_K)
         return fail(nullptr, KR_ERR_ARG, "kr_create: K=%d outside [%d,%d] (5-bit packing + 8-bit sequence id in 64 bits)", K, KR_MIN_K, KR_MAX_K);
     int ndev = 0;
@@ -214,7 +231,7 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     if (!(flags & KR_LEGACY_PATHS)) flags |= KR_EXP_PAIRS_AUTO | KR_EXP_BUCKETS | KR_EXP_ENCODE | KR_EXP_IDXQ | KR_EXP_GIDX;
 #endif
     ctx = new kr_ctx();
-    ctx->dev = device; ctx->K = K; ctx->flags = flags; ctx->num_sms = prop.multiProcessorCount;
+    ctx->dev = device; ctx->K = K; ctx->dnaK = dnaK; ctx->flags = flags; ctx->num_sms = prop.multiProcessorCount;
 #define CUC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(nullptr, KR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); delete ctx; return KR_ERR_CUDA; } } while (0)
     CUC(cudaSetDevice(device));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -242,6 +259,7 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
     CUC(cudaFuncSetAttribute(k_idx_query_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDXQ2_DENSE_MAX * 2 * IDXQ2_WARPS + 256)));
     CUC(cudaFuncSetAttribute(k_gidx_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIDX_SMEM));
+    CUC(cudaFuncSetAttribute(k_encode_dna<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 9 + 16));
     CUC(cudaFuncSetAttribute(k_bk_pairs<DenseSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
     CUC(cudaFuncSetAttribute(k_bk_pairs<TableSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
     CUC(cudaFuncSetAttribute(k_bk_pairs<WorkSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
@@ -334,6 +352,10 @@ double kr_distance(int32_t sim, uint32_t size_a, uint32_t size_b) {
 
 kr_status kr_key_decode(const kr_ctx *ctx, uint64_t key, char *out) {
     if (!ctx || !out) return KR_ERR_ARG;
+    if (ctx->dnaK) {
+        for (int i = ctx->dnaK - 1; i >= 0; --i) { const int c = (int)(key & 7); key >>= 3; out[i] = "acgtnu??"[c]; }
+        return KR_OK;
+    }
     for (int i = ctx->K - 1; i >= 0; --i) {
         int c = (int)(key & 31); key >>= 5;
         out[i] = c < 26 ? (char)('A' + c) : c == 26 ? '*' : c == 27 ? '-' : '?';
@@ -365,8 +387,9 @@ static kr_status check_alphabet(kr_ctx *ctx) {
     ctx->err_pending = false;
     if (ei.flag) {
         cudaMemsetAsync(ctx->d_err, 0, sizeof(ErrInfo), ctx->stream);
-        return fail(ctx, KR_ERR_ALPHABET, "kr_encode: sequence %u position %u: residue 0x%02x ('%c') is outside 'A'..'Z', '*', '-'",
-                    ei.seq, ei.pos, ei.byte, (ei.byte >= 32 && ei.byte < 127) ? (char)ei.byte : '?');
+        return fail(ctx, KR_ERR_ALPHABET, "kr_encode: sequence %u position %u: residue 0x%02x ('%c') is outside %s",
+                    ei.seq, ei.pos, ei.byte, (ei.byte >= 32 && ei.byte < 127) ? (char)ei.byte : '?',
+                    ctx->dnaK ? "a c g t n u (either case)" : "'A'..'Z', '*', '-'");
     }
     return KR_OK;
 }
@@ -384,9 +407,9 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
     for (u32 i = 0; i < nseq; ++i) {
         if (offsets[i + 1] < offsets[i]) return fail(ctx, KR_ERR_ARG, "kr_encode: offsets not monotone at %u", i);
         u64 L = offsets[i + 1] - offsets[i];
-        if (L > 65535u + (u64)K - 1) return fail(ctx, KR_ERR_ARG, "kr_encode: sequence %u has %llu residues; at most %u are supported", i, (unsigned long long)L, 65535u + K - 1);
+        if (kmer_slots(ctx, L) > 65535u) return fail(ctx, KR_ERR_ARG, "kr_encode: sequence %u has %llu residues; at most 65535 k-mers per sequence are supported", i, (unsigned long long)L);
         off[i] = offsets[i] - offsets[0]; koff[i] = kc;
-        u32 n = L >= (u64)K ? (u32)(L - K + 1) : 0;
+        u32 n = (u32)kmer_slots(ctx, L);
         kc += n; maxn = std::max(maxn, n);
     }
     off[nseq] = total; koff[nseq] = kc;
@@ -406,10 +429,16 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
         StageTimer t(ctx, ST_ENCODE);
         EncodeParams p;
         p.res = (const u8 *)s->res->p; p.off = s->d_off; p.koff = s->d_koff; p.keys = s->d_keys; p.meta = s->d_meta;
-        p.err = ctx->d_err; p.nseq = nseq; p.K = K; p.smem_cap = 2048;
+        p.err = ctx->d_err; p.nseq = nseq; p.K = ctx->dnaK ? ctx->dnaK : K; p.smem_cap = 2048;
         // proteins are a few hundred residues: one 128-thread CTA sorts up to 2048 keys in 16 KB of shared
         // memory; longer sequences (rare) sort in place in global memory inside the same kernel
 #ifdef KR_EXPERIMENTAL
+        if (ctx->dnaK) {   // DnaKmers: lower-case the library's copy, then the keys of both strands
+            p.smem_cap = 4096;                          // an SSU rRNA gene (~1,500 bases, ~3,000 keys) sorts in shared memory
+            KR_LAUNCH(KR_T(k_dna_lowercase), ctx->num_sms * 4, 256, 0, ctx->stream, (u8 *)s->res->p, total);
+            KR_LAUNCH(KR_T(k_encode_dna<128>), nseq, 128, p.smem_cap * 8 + p.smem_cap + 16, ctx->stream, p);
+            LAUNCHED(ctx);
+        } else
         if ((ctx->flags & KR_EXP_ENCODE) && maxn <= 512) KR_LAUNCH(KR_T(k_encode_sort_warp<16>), (nseq + ENC2_WARPS - 1) / ENC2_WARPS, ENC2_WARPS * 32, 0, ctx->stream, p);
         else if (ctx->flags & KR_EXP_ENCODE) KR_LAUNCH(KR_T(k_encode_sort_warp<32>), (nseq + ENC2_WARPS - 1) / ENC2_WARPS, ENC2_WARPS * 32, 0, ctx->stream, p);
         else
@@ -1074,7 +1103,7 @@ kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *id
 uint64_t kr_blocklist_capacity(const kr_ctx *ctx, const uint64_t *offsets, uint32_t nseq) {
     if (!ctx || (!offsets && nseq)) return 0;
     u64 kc = 0;
-    for (u32 i = 0; i < nseq; ++i) { u64 L = offsets[i + 1] - offsets[i]; if (L >= (u64)ctx->K) kc += L - ctx->K + 1; }
+    for (u32 i = 0; i < nseq; ++i) kc += kmer_slots(ctx, offsets[i + 1] - offsets[i]);
     return blocklist_capacity(kc, (nseq + TB - 1) / TB);
 }
 
@@ -1276,7 +1305,7 @@ struct kr_keylists {
 uint64_t kr_keylist_capacity(const kr_ctx *ctx, const uint64_t *offsets, uint32_t nseq) {
     if (!ctx || (!offsets && nseq)) return 0;
     u64 kc = 0;
-    for (u32 i = 0; i < nseq; ++i) { u64 L = offsets[i + 1] - offsets[i]; if (L >= (u64)ctx->K) kc += L - ctx->K + 1; }
+    for (u32 i = 0; i < nseq; ++i) kc += kmer_slots(ctx, offsets[i + 1] - offsets[i]);
     return kc;
 }
 kr_status kr_seqset_export_keys(kr_ctx *ctx, kr_seqset *set, kr_keylists *out) {
@@ -1302,8 +1331,7 @@ kr_status kr_seqset_import_keys(kr_ctx *ctx, const kr_keylists *shards, uint32_t
     u64 kc = 0;
     for (u32 i = 0; i < nseq; ++i) {
         off[i] = offsets[i] - offsets[0]; koff[i] = kc;
-        const u64 L = offsets[i + 1] - offsets[i];
-        if (L >= (u64)K) kc += L - K + 1;
+        kc += kmer_slots(ctx, offsets[i + 1] - offsets[i]);
     }
     off[nseq] = offsets[nseq] - offsets[0]; koff[nseq] = kc;
     u32 n = 0; u64 cap = 0;

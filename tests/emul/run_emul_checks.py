@@ -344,6 +344,61 @@ def case_exp_gidx_build():
     c.close()
 
 
+def dna_family(seed, n, length):
+    rng = np.random.default_rng(seed)
+    alpha = np.frombuffer(b"acgt", dtype=np.uint8)
+    roots = [alpha[rng.integers(0, 4, length)] for _ in range(4)]
+    seqs = []
+    for i in range(n):
+        s = roots[i % 4].copy()
+        pos = rng.integers(0, length, 2 + 6 * (i % 5))
+        s[pos] = alpha[rng.integers(0, 4, len(pos))]
+        t = s[: int(rng.integers(length * 2 // 3, length + 1))].tobytes().decode()
+        if i % 7 == 3:
+            t = ko.py_dna_revcomp(t)                       # the other strand of a relative: same k-mer set
+        if i % 5 == 1:
+            t = t.upper()                                 # case does not matter
+        if i % 11 == 4:
+            t = t[:40] + "n" + t[41:]
+        seqs.append(t)
+    return seqs
+
+
+def case_exp_dna():
+    """EXPERIMENTAL: DnaKmers contexts -- K-mers of both strands through the unchanged join / index / posting-list paths"""
+    seqs = dna_family(51, 60, 420) + ["acgtacgtac", "", "ACGTACGTAC", "acgu" * 12, "tttttttttttttttttttttttttttt", "aaaaaaaaaaaaaaaaaaaaaaaaaaaa"]
+    seqs[9] = seqs[2].upper()                              # equal sequences up to case: INFINITY
+    for K in (18, 15, 7):
+        want = np.array([[ko.py_dna_similarity(a, b, K, True) for b in seqs] for a in seqs], dtype=np.int64)
+        sizes = np.array([len(ko.py_dna_kmers(q, K)) for q in seqs])
+        for extra in (0, binding.EXP_PAIRS | binding.EXP_BUCKETS):
+            c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY | binding.ALPHABET_DNA | extra)
+            s = c.encode(seqs)
+            assert (s.sizes() == sizes).all(), (K, extra)
+            assert (c.sim_matrix(s, elem=kr.ELEM_I32) == want).all(), (K, extra)
+            assert sorted(s.kmers(0)) == sorted(ko.py_dna_kmers(seqs[0], K))
+            db = c.db()
+            db.append(seqs[:40])
+            sim, first, _ = db.find_closest(c.encode(seqs[40:]))
+            sub = want[40:, :40]
+            assert (sim == sub.max(1)).all() and (first == np.where(sub.max(1) > 0, sub.argmax(1), kr.NO_REP)).all()
+            c.close()
+    assert want[-2, -1] == len(ko.py_dna_kmers("t" * 28, 7)) == 2      # poly-t and poly-a are each other's reverse complement
+    c = kr.Context(device=0, K=15, flags=binding.ALPHABET_DNA)
+    try:
+        c.encode(["acgtacgtacgtacgtacgt", "acgtacgtrcgtacgtacgt"])
+        raise AssertionError("an ambiguity code must fail")
+    except kr.KrError as e:
+        assert e.code == -4 and "sequence 1 position 8" in str(e)
+    c.close()
+    for badK in (4, 19):
+        try:
+            kr.Context(device=0, K=badK, flags=binding.ALPHABET_DNA)
+            raise AssertionError("K outside [5,18] must fail")
+        except kr.KrError:
+            pass
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -48,7 +48,7 @@ def test_bucket_grouping_sub_passes_on_the_emulator(emul_lib):
 
 
 @pytest.mark.parametrize("case", ["matrix_layouts", "k10_rectangular_pairs", "find_closest_and_build", "subchunks", "sharded_import", "api_misc",
-                                  "exp_sparse_join", "exp_pairs", "exp_encode_warp", "exp_idxq_warp", "exp_gidx_build"])
+                                  "exp_sparse_join", "exp_pairs", "exp_encode_warp", "exp_idxq_warp", "exp_gidx_build", "exp_dna"])
 def test_device_code_on_the_emulator(emul_lib, case):
     env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2")
     p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,

@@ -165,3 +165,37 @@ def test_greedy_build_through_the_growing_index(oracle, rep50, rickettsia):
     _, want, _ = oracle.greedy_build(oracle.batch(reps, K=8), 50, ident_inf=True)
     assert (c.db().greedy_build(c.encode(reps), 50, batch=300) == want).all() and want[:1480].all()
     c.close()
+
+
+def test_dna_kmers_both_strands():
+    """ALPHABET_DNA contexts (DnaKmers: K-mers of the lower-cased sequence and of its reverse complement) against the
+    Python restatement: SSU-sized sequences at K = 18 and 15, other strand / other case / 'n' / RNA 'u', the join and the
+    posting-list path, and the alphabet error"""
+    from oracle import kr_oracle as ko
+    rng = np.random.default_rng(6)
+    alpha = np.frombuffer(b"acgt", dtype=np.uint8)
+    roots = [alpha[rng.integers(0, 4, 1500)] for _ in range(5)]
+    seqs = []
+    for i in range(300):
+        s = roots[i % 5].copy()
+        pos = rng.integers(0, 1500, 5 + 25 * (i % 6))
+        s[pos] = alpha[rng.integers(0, 4, len(pos))]
+        t = s[: int(rng.integers(1100, 1501))].tobytes().decode()
+        t = ko.py_dna_revcomp(t) if i % 7 == 3 else t
+        t = t.upper() if i % 5 == 1 else t
+        t = t[:300] + "nn" + t[302:] if i % 11 == 4 else t
+        seqs.append(t)
+    seqs += ["acgtacgtacgtacgtacgtacgt", "", "ACGU" * 10, seqs[3].upper()]
+    for K in (18, 15):
+        sets = [ko.py_dna_kmers(q, K) for q in seqs]
+        want = np.array([[9999 if seqs[a].lower() == seqs[b].lower() else len(sets[a] & sets[b]) for b in range(len(seqs))] for a in range(len(seqs))])
+        for extra in (0, binding.EXP_PAIRS | binding.EXP_BUCKETS):
+            c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY | binding.ALPHABET_DNA | extra)
+            s = c.encode(seqs)
+            assert (s.sizes() == [len(x) for x in sets]).all()
+            assert (c.sim_matrix(s, elem=kr.ELEM_U16) == want).all()
+            c.close()
+    c = kr.Context(device=0, K=15, flags=binding.ALPHABET_DNA)
+    with pytest.raises(kr.KrError):
+        c.encode(["acgtacgtacgtacgtacgt", "acgtacgtrcgtacgtacgt"])
+    c.close()
