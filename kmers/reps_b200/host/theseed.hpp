@@ -511,20 +511,25 @@ class FastaOutputStream {   // ">label comment", sequence wrapped at 60, LF (for
 };
 
 // ---------------------------------------------------------------------------------------------------
-// The GPU engine behind the classes: one kr_ctx per k-mer size on device $KR_DEVICE (default 0).
+// The GPU engine behind the classes: one kr_ctx per (k-mer size, alphabet) on device $KR_DEVICE (default 0).
+// An "engine key" is the k-mer size, plus 1000 for DNA contexts (DnaKmers: both strands; these need a library built
+// with the experimental DNA encoder -- the default library refuses the flag and says so).
 class KmerEngine {
   public:
-    static kr_ctx *ctx(int K) {
+    static constexpr int DNA_KEY = 1000;
+    static constexpr uint32_t ALPHABET_DNA = 0x4000u;
+    static kr_ctx *ctx(int key) {
         auto &m = map();
-        auto it = m.find(K);
+        auto it = m.find(key);
         if (it != m.end()) return it->second;
         const char *d = std::getenv("KR_DEVICE");
         uint32_t flags = KR_IDENT_IS_INFINITY;
         if (const char *f = std::getenv("KR_FLAGS")) flags = (uint32_t)std::atoi(f);
+        if (key >= DNA_KEY) flags |= ALPHABET_DNA;
         kr_ctx *c = nullptr;
-        if (kr_create(d ? std::atoi(d) : 0, K, flags, &c) != KR_OK)
+        if (kr_create(d ? std::atoi(d) : 0, key % DNA_KEY, flags, &c) != KR_OK)
             throw std::runtime_error(std::string("kmersreps: ") + kr_last_error(nullptr));   // RuntimeException, App.java:129
-        m[K] = c;
+        m[key] = c;
         return c;
     }
     static void check(kr_ctx *c, kr_status st) { if (st != KR_OK) throw std::runtime_error(std::string("kmersreps: ") + kr_last_error(c)); }
@@ -538,44 +543,38 @@ struct SetHandle {   // shared ownership of an encoded batch
     ~SetHandle() { kr_seqset_free(set); }
 };
 
-inline std::shared_ptr<SetHandle> encodeStrings(int K, const std::vector<const std::string *> &seqs) {
+inline std::shared_ptr<SetHandle> encodeStrings(int key, const std::vector<const std::string *> &seqs) {
     std::string flat; std::vector<uint64_t> off(seqs.size() + 1, 0);
     for (size_t i = 0; i < seqs.size(); ++i) { flat += *seqs[i]; off[i + 1] = flat.size(); }
-    kr_ctx *c = KmerEngine::ctx(K);
+    kr_ctx *c = KmerEngine::ctx(key);
     kr_seqset *s = nullptr;
     static const uint8_t none = 0;
     KmerEngine::check(c, kr_encode(c, flat.empty() ? &none : (const uint8_t *)flat.data(), off.data(), (uint32_t)seqs.size(), &s));
-    return std::make_shared<SetHandle>(c, s, K);
+    return std::make_shared<SetHandle>(c, s, key);
 }
 
 // ---------------------------------------------------------------------------------------------------
+// org.theseed.sequence.SequenceKmers: what ProteinKmers and DnaKmers share -- the k-mer set of one sequence,
+// similarity / distance / size / INFINITY.  The set itself lives on the GPU (a batch handle + an index into it).
 class SequenceKmers {
   public:
     static constexpr int INFINITY_ = KR_INFINITY;   // SequenceKmers.INFINITY (RepGenomeDbProcessor.java:249)
     virtual ~SequenceKmers() = default;
-};
-
-class ProteinKmers : public SequenceKmers {
-  public:
-    static void setKmerSize(int k) { K() = k; }   // process-global, as in the reference (RepGenomeDbProcessor.java:77-80)
-    static int kmerSize() { return K(); }
-
-    ProteinKmers() = default;
-    explicit ProteinKmers(std::string protein) : protein_(std::move(protein)), k_(K()) {}   // SequenceInfo.java:47
-    const std::string &getProtein() const { return protein_; }
+    SequenceKmers() = default;
+    const std::string &getSequence() const { return sequence_; }
 
     // number of distinct k-mers (ScoreCouplingReporter.java:73)
     int size() const { ensure(); return (int)size_; }
     // number of shared distinct k-mers, INFINITY for equal sequences (DistanceMatrixProcessor.java:76)
-    int similarity(const ProteinKmers &other) const {
+    int similarity(const SequenceKmers &other) const {
         ensure(); other.ensure();
         int32_t sim = 0; uint32_t ia = idx_, ib = other.idx_;
         KmerEngine::check(set_->ctx, kr_sim_pairs(set_->ctx, set_->set, &ia, other.set_->set, &ib, 1, &sim, nullptr));
         return sim;
     }
     // Jaccard distance (SequenceInfo.java:75, DistanceMatrixProcessor.java:75)
-    double distance(const ProteinKmers &other) const { return distance(similarity(other), *this, other); }
-    static double distance(int sim, const ProteinKmers &a, const ProteinKmers &b) {   // SsuRepresentation.java:47
+    double distance(const SequenceKmers &other) const { return distance(similarity(other), *this, other); }
+    static double distance(int sim, const SequenceKmers &a, const SequenceKmers &b) {   // SsuRepresentation.java:47
         return kr_distance(sim, (uint32_t)a.size(), (uint32_t)b.size());
     }
     // the k-mers themselves (SequenceKmers.iterator(), TargetProcessor.java:193)
@@ -588,33 +587,67 @@ class ProteinKmers : public SequenceKmers {
         return out;
     }
 
-    // Encode many objects in one launch (the constructor itself never touches the device: it is called from
-    // parallel streams, GtoRepBuildProcessor.java:127).  Objects already encoded are left alone.
+    // Encode many objects in one launch (the constructors never touch the device: they are called from parallel
+    // streams, GtoRepBuildProcessor.java:127).  Objects already encoded are left alone.
     template <class It> static void encodeBatch(It first, It last) {
-        std::vector<const ProteinKmers *> todo; std::vector<const std::string *> seqs;
-        for (It it = first; it != last; ++it) { const ProteinKmers &p = deref(*it); if (!p.set_) { todo.push_back(&p); seqs.push_back(&p.protein_); } }
+        std::vector<const SequenceKmers *> todo; std::vector<const std::string *> seqs;
+        for (It it = first; it != last; ++it) { const SequenceKmers &p = deref(*it); if (!p.set_) { todo.push_back(&p); seqs.push_back(&p.sequence_); } }
         if (todo.empty()) return;
-        int k = todo[0]->k_;
-        auto h = encodeStrings(k, seqs);
+        auto h = encodeStrings(todo[0]->k(), seqs);
         std::vector<uint32_t> sizes(todo.size());
         KmerEngine::check(h->ctx, kr_seqset_sizes(h->set, sizes.data()));
         for (size_t i = 0; i < todo.size(); ++i) { todo[i]->set_ = h; todo[i]->idx_ = (uint32_t)i; todo[i]->size_ = sizes[i]; }
     }
     const std::shared_ptr<SetHandle> &handle() const { ensure(); return set_; }
     uint32_t index() const { ensure(); return idx_; }
-    int k() const { return k_; }
+    int k() const { return k_ + (dna_ ? KmerEngine::DNA_KEY : 0); }   // engine key: k-mer size (+ DNA_KEY for DNA)
 
   protected:
-    static int &K() { static int k = 8; return k; }
-    static const ProteinKmers &deref(const ProteinKmers &p) { return p; }
-    static const ProteinKmers &deref(const ProteinKmers *p) { return *p; }
-    template <class T> static const ProteinKmers &deref(const std::unique_ptr<T> &p) { return *p; }
-    template <class T> static const ProteinKmers &deref(const std::shared_ptr<T> &p) { return *p; }
-    void ensure() const { if (!set_) { const ProteinKmers *self = this; encodeBatch(&self, &self + 1); } }
-    std::string protein_;
+    SequenceKmers(std::string seq, int k, bool dna) : sequence_(std::move(seq)), k_(k), dna_(dna) {}
+    static const SequenceKmers &deref(const SequenceKmers &p) { return p; }
+    static const SequenceKmers &deref(const SequenceKmers *p) { return *p; }
+    template <class T> static const SequenceKmers &deref(const std::unique_ptr<T> &p) { return *p; }
+    template <class T> static const SequenceKmers &deref(const std::shared_ptr<T> &p) { return *p; }
+    void ensure() const { if (!set_) { const SequenceKmers *self = this; encodeBatch(&self, &self + 1); } }
+    std::string sequence_;
     int k_ = 8;
+    bool dna_ = false;
     mutable std::shared_ptr<SetHandle> set_;
     mutable uint32_t idx_ = 0, size_ = 0;
+};
+
+class ProteinKmers : public SequenceKmers {
+  public:
+    static void setKmerSize(int k) { K() = k; }   // process-global, as in the reference (RepGenomeDbProcessor.java:77-80)
+    static int kmerSize() { return K(); }
+    ProteinKmers() = default;
+    explicit ProteinKmers(std::string protein) : SequenceKmers(std::move(protein), K(), false) {}   // SequenceInfo.java:47
+    const std::string &getProtein() const { return sequence_; }
+  protected:
+    static int &K() { static int k = 8; return k; }
+};
+
+// org.theseed.sequence.DnaKmers: the K-mers of the (lower-cased) DNA sequence and of its reverse complement
+// (SsuRepGenomeProcessor.java:88, SeqCompProcessor.java:102, TargetProcessor.java:162-193)
+class DnaKmers : public SequenceKmers {
+  public:
+    static void setKmerSize(int k) { K() = k; }   // SeqCompProcessor.java:102
+    static int kmerSize() { return K(); }
+    DnaKmers() = default;
+    explicit DnaKmers(std::string dna) : SequenceKmers(std::move(dna), K(), true) {}   // TargetProcessor.java:162
+    const std::string &getDna() const { return sequence_; }
+  protected:
+    static int &K() { static int k = 15; return k; }
+};
+
+// org.theseed.sequence.SsuGenome (SsuGenome.java:22-60): the SSU rRNA k-mers of a genome, with its id and name
+class SsuGenome : public DnaKmers {
+  public:
+    SsuGenome(std::string genomeId, std::string name, std::string dna) : DnaKmers(std::move(dna)), genomeId_(std::move(genomeId)), name_(std::move(name)) {}
+    const std::string &getGenomeId() const { return genomeId_; }
+    const std::string &getName() const { return name_; }
+  private:
+    std::string genomeId_, name_;
 };
 
 // All-vs-all similarities of a list of ProteinKmers (the rewritten double loops of
@@ -622,9 +655,9 @@ class ProteinKmers : public SequenceKmers {
 class SimilarityMatrix {
   public:
     template <class It> static SimilarityMatrix compute(It first, It last) {
-        ProteinKmers::encodeBatch(first, last);
+        SequenceKmers::encodeBatch(first, last);
         SimilarityMatrix m;
-        std::vector<const ProteinKmers *> v;
+        std::vector<const SequenceKmers *> v;
         for (It it = first; it != last; ++it) v.push_back(&ref(*it));
         m.n_ = v.size();
         if (!m.n_) return m;
@@ -632,7 +665,7 @@ class SimilarityMatrix {
         std::shared_ptr<SetHandle> h = v[0]->handle();
         bool same = true;
         for (size_t i = 0; i < v.size(); ++i) same = same && v[i]->handle() == h && v[i]->index() == i;
-        if (!same) { std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getProtein()); h = encodeStrings(v[0]->k(), s); }
+        if (!same) { std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getSequence()); h = encodeStrings(v[0]->k(), s); }
         m.sizes_.resize(m.n_);
         KmerEngine::check(h->ctx, kr_seqset_sizes(h->set, m.sizes_.data()));
         m.sim_.resize(m.n_ * m.n_);
@@ -644,9 +677,9 @@ class SimilarityMatrix {
     double distance(size_t i, size_t j) const { return kr_distance(sim_[i * n_ + j], sizes_[i], sizes_[j]); }
     size_t size() const { return n_; }
   private:
-    static const ProteinKmers &ref(const ProteinKmers &p) { return p; }
-    static const ProteinKmers &ref(const ProteinKmers *p) { return *p; }
-    template <class T> static const ProteinKmers &ref(const std::unique_ptr<T> &p) { return *p; }
+    static const SequenceKmers &ref(const SequenceKmers &p) { return p; }
+    static const SequenceKmers &ref(const SequenceKmers *p) { return *p; }
+    template <class T> static const SequenceKmers &ref(const std::unique_ptr<T> &p) { return *p; }
     size_t n_ = 0;
     std::vector<int32_t> sim_;
     std::vector<uint32_t> sizes_;
@@ -724,12 +757,12 @@ class RepGenomeDb {
 
     // findClosest(ProteinKmers | Sequence | RepGenome): best similarity over all reps, first strict maximum
     // in iteration order; (0, null, 1.0) when nothing shares a k-mer (GtoRepGenomeProcessor.java:277-282)
-    Representation findClosest(const ProteinKmers &q) const { const ProteinKmers *p = &q; return findClosest(&p, &p + 1)[0]; }
+    Representation findClosest(const SequenceKmers &q) const { const SequenceKmers *p = &q; return findClosest(&p, &p + 1)[0]; }
     Representation findClosest(const Sequence &seq) const { ProteinKmers q(seq.sequence); return findClosest(q); }   // RepGenomeDbProcessor.java:237
     template <class It> std::vector<Representation> findClosest(It first, It last) const {
         std::vector<Representation> out;
-        ProteinKmers::encodeBatch(first, last);
-        std::vector<const ProteinKmers *> v;
+        SequenceKmers::encodeBatch(first, last);
+        std::vector<const SequenceKmers *> v;
         for (It it = first; it != last; ++it) v.push_back(ptr(*it));
         if (v.empty()) return out;
         sync();
@@ -740,7 +773,7 @@ class RepGenomeDb {
             uint32_t pick = tie_last_ ? l[i] : f[i];
             if (sim[i] == 0 || pick == KR_NO_REP) { out.emplace_back(this, nullptr, 0, 1.0); continue; }
             const RepGenome *rep = reps_[dev2host_[pick]].get();
-            out.emplace_back(this, rep, sim[i], ProteinKmers::distance(sim[i], *v[i], *rep));
+            out.emplace_back(this, rep, sim[i], SequenceKmers::distance(sim[i], *v[i], *rep));
         }
         return out;
     }
@@ -751,17 +784,17 @@ class RepGenomeDb {
     template <class It> std::vector<int32_t> similarities(It first, It last, std::vector<const RepGenome *> *reps_out) const {
         std::vector<const RepGenome *> reps = all();
         if (reps_out) *reps_out = reps;
-        ProteinKmers::encodeBatch(first, last);
-        std::vector<const ProteinKmers *> v;
+        SequenceKmers::encodeBatch(first, last);
+        std::vector<const SequenceKmers *> v;
         for (It it = first; it != last; ++it) v.push_back(ptr(*it));
         std::vector<int32_t> out(v.size() * reps.size());
         if (v.empty() || reps.empty()) return out;
-        ProteinKmers::encodeBatch(reps.begin(), reps.end());   // one launch; the reps keep their sizes for distance()
-        auto hr = batchOf(std::vector<const ProteinKmers *>(reps.begin(), reps.end()));
+        SequenceKmers::encodeBatch(reps.begin(), reps.end());   // one launch; the reps keep their sizes for distance()
+        auto hr = batchOf(std::vector<const SequenceKmers *>(reps.begin(), reps.end()));
         const size_t R = reps.size(), chunk = std::max<size_t>(256, ((size_t)1 << 26) / R / 256 * 256);   // <= 64M cells per launch
         for (size_t q0 = 0; q0 < v.size(); q0 += chunk) {
             const size_t n = std::min(chunk, v.size() - q0);
-            std::vector<const ProteinKmers *> part(v.begin() + q0, v.begin() + q0 + n);
+            std::vector<const SequenceKmers *> part(v.begin() + q0, v.begin() + q0 + n);
             auto hq = batchOf(part);
             kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_FULL, 0, (uint32_t)n};
             KmerEngine::check(hq->ctx, kr_sim_matrix(hq->ctx, hq->set, hr->set, &d, out.data() + q0 * R));
@@ -788,11 +821,11 @@ class RepGenomeDb {
     }
 
     // checkSimilarity(ProteinKmers, sim): is some rep at least this similar? (BaseGenomeProcessor.java:203)
-    bool checkSimilarity(const ProteinKmers &q, int sim) const {
+    bool checkSimilarity(const SequenceKmers &q, int sim) const {
         if (size() == 0) return false;
         sync();
         uint8_t r = 0;
-        const ProteinKmers *p = &q; auto h = batchOf(std::vector<const ProteinKmers *>{p});
+        const SequenceKmers *p = &q; auto h = batchOf(std::vector<const SequenceKmers *>{p});
         KmerEngine::check(ctx(), kr_db_any_ge(ctx(), db_, h->set, sim, &r));
         return r != 0;
     }
@@ -803,8 +836,8 @@ class RepGenomeDb {
         std::vector<bool> added(cands.size(), false);
         if (cands.empty()) return added;
         sync();
-        ProteinKmers::encodeBatch(cands.begin(), cands.end());
-        std::vector<const ProteinKmers *> v; for (auto &c : cands) v.push_back(&c);
+        SequenceKmers::encodeBatch(cands.begin(), cands.end());
+        std::vector<const SequenceKmers *> v; for (auto &c : cands) v.push_back(&c);
         auto h = batchOf(v);
         std::vector<uint8_t> a(cands.size());
         KmerEngine::check(ctx(), kr_greedy_build(ctx(), db_, h->set, threshold_, batch, a.data()));
@@ -854,11 +887,11 @@ class RepGenomeDb {
     void setTieLast(bool v) { tie_last_ = v; }
 
   private:
-    static const ProteinKmers *ptr(const ProteinKmers &p) { return &p; }
-    static const ProteinKmers *ptr(const ProteinKmers *p) { return p; }
+    static const SequenceKmers *ptr(const SequenceKmers &p) { return &p; }
+    static const SequenceKmers *ptr(const SequenceKmers *p) { return p; }
     kr_ctx *ctx() const { return KmerEngine::ctx(kmerSize_); }
     // one set holding exactly these objects, in order
-    static std::shared_ptr<SetHandle> batchOf(const std::vector<const ProteinKmers *> &v) {
+    static std::shared_ptr<SetHandle> batchOf(const std::vector<const SequenceKmers *> &v) {
         std::shared_ptr<SetHandle> h = v[0]->handle();
         bool same = true; uint32_t n = kr_seqset_count(h->set);
         for (size_t i = 0; i < v.size(); ++i) same = same && v[i]->handle() == h && v[i]->index() == i;
@@ -870,7 +903,7 @@ class RepGenomeDb {
             KmerEngine::check(h->ctx, kr_seqset_gather(h->ctx, h->set, idx.data(), (uint32_t)idx.size(), &g));
             return std::make_shared<SetHandle>(h->ctx, g, h->K);
         }
-        std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getProtein());
+        std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getSequence());
         return encodeStrings(v[0]->k(), s);
     }
     // bring the device copy of the database up to date: append new reps, refresh iteration ranks
@@ -931,10 +964,10 @@ class KmerCollectionGroup {
             auto it = groups_.find(g.first);
             if (it == groups_.end() || it->second.empty()) continue;
             auto &members = it->second;
-            ProteinKmers::encodeBatch(members.begin(), members.end());
+            SequenceKmers::encodeBatch(members.begin(), members.end());
             std::vector<ProteinKmers> qs;
             for (size_t qi : g.second) qs.emplace_back(queries[qi].first->sequence);
-            ProteinKmers::encodeBatch(qs.begin(), qs.end());
+            SequenceKmers::encodeBatch(qs.begin(), qs.end());
             std::vector<const std::string *> ms; for (auto &m : members) ms.push_back(&m.getProtein());
             auto hm = members[0].handle();
             bool same = true; for (size_t i = 0; i < members.size(); ++i) same = same && members[i].handle() == hm && members[i].index() == i;

@@ -5,6 +5,7 @@
 //   kmers_reps group      RepMatrixProcessor.java        incremental all-vs-all + greedy grouping by distance
 //   kmers_reps classify   ClassifyProcessor.java         min distance of each input sequence to its named group
 //   kmers_reps neighbors  NeighborProcessor.java          the N closest representatives of each input genome, ties retained
+//   kmers_reps seqcomp    SeqCompProcessor.java           seed-protein distance against SSU-rRNA distance for every genome pair
 //   kmers_reps buildsets  GenomeProcessor.java + BaseGenomeProcessor.java:151-214,348-407,433-442
 //                                                       the hot part of the `genomes` pipeline: hierarchical rep sets at
 //                                                       several thresholds, saved as rep<thr>.ser + rep<thr>.list.tbl
@@ -25,6 +26,7 @@ static void usage() {
                  "  group     [-K k] [-i fasta] [-m maxDist]\n"
                  "  classify  [-K k] [-i fasta] [-m maxDist] controlFile\n"
                  "  neighbors [-n num] [--min sim] dbFile seeds.tbl\n"
+                 "  seqcomp   [-K protK] [-k dnaK] seqTable.tbl      (DNA k-mers: needs a library with the DNA encoder)\n"
                  "  buildsets [-K k] [-t 10,50,100,200] [-p role] [--batch n] outDir input.fa\n";
 }
 
@@ -300,6 +302,49 @@ static int cmd_neighbors(int argc, char **argv) {
     return 0;
 }
 
+// ---- seqcomp (SeqCompProcessor.java:105-160) -------------------------------------------------------------
+// Input: the table SeqTableProcessor writes (:69,91): header, then genome_id, genome_name, seed protein, SSU rRNA.
+// Every pair of genomes (a genome with itself included, :112) in the order of GenomeDescriptorSet -- an un-vendored class
+// whose iteration is taken to be ascending genome id -- gets its protein k-mer distance and its DNA k-mer distance:
+// two all-vs-all matrices instead of two similarity() calls per pair.
+static int cmd_seqcomp(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--protKmer", "K"}, {"-k", "k"}, {"--dnaKmer", "k"}, {"-v", "v"}}, {"K", "k"});
+    if (a.pos.size() != 1) throw std::runtime_error("ParseFailureException: Argument \"inFile\" is required");
+    const int protK = a.opt.count("K") ? std::stoi(a.opt["K"]) : 8, dnaK = a.opt.count("k") ? std::stoi(a.opt["k"]) : 15;   // :83-84
+    if (protK < 3) throw std::runtime_error("ParseFailureException: Protein kmer size must be at least 3.");
+    if (dnaK < 4) throw std::runtime_error("ParseFailureException: DNA kmer size must be at least 4.");
+    ProteinKmers::setKmerSize(protK);
+    DnaKmers::setKmerSize(dnaK);
+    std::ifstream in(a.pos[0]);
+    if (!in) throw std::runtime_error("java.io.FileNotFoundException: Input file " + a.pos[0] + " is not found or unreadable.");
+    struct Row { std::string id, name; };
+    std::vector<Row> rows; std::vector<ProteinKmers> seeds; std::vector<DnaKmers> rnas;
+    std::string line;
+    std::getline(in, line);   // header
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        std::vector<std::string> f; size_t b = 0;
+        for (size_t t; (t = line.find('\t', b)) != std::string::npos; b = t + 1) f.push_back(line.substr(b, t - b));
+        f.push_back(line.substr(b));
+        if (f.size() < 4) throw std::runtime_error("java.io.IOException: input line needs 4 fields: " + line);
+        rows.push_back({f[0], f[1]}); seeds.emplace_back(f[2]); rnas.emplace_back(f[3]);
+    }
+    std::vector<size_t> order(rows.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return rows[x].id < rows[y].id; });
+    SimilarityMatrix pm = SimilarityMatrix::compute(seeds.begin(), seeds.end());
+    SimilarityMatrix dm = SimilarityMatrix::compute(rnas.begin(), rnas.end());
+    std::cout << "genome1\tname1\tgenome2\tname2\tseed_dist\trna_dist\n";
+    for (size_t x = 0; x < order.size(); ++x)
+        for (size_t y = x; y < order.size(); ++y) {
+            const size_t i = order[x], j = order[y];
+            std::cout << rows[i].id << '\t' << rows[i].name << '\t' << rows[j].id << '\t' << rows[j].name << '\t'
+                      << java::format_fixed(pm.distance(i, j), 6, 4) << '\t' << java::format_fixed(dm.distance(i, j), 6, 4) << '\n';
+        }
+    return 0;
+}
+
 // ---- buildsets: the similarity work of the `genomes` pipeline ------------------------------------------
 // Input: one FASTA record per genome (label = seed-protein feature id, comment = genome name, sequence = seed
 // protein) in master-list order (ProteinDataFactory orders by rating, score, id; that ordering needs PATRIC
@@ -360,6 +405,7 @@ int main(int argc, char **argv) {
         if (cmd == "group") return cmd_group(argc, argv);
         if (cmd == "classify") return cmd_classify(argc, argv);
         if (cmd == "neighbors") return cmd_neighbors(argc, argv);
+        if (cmd == "seqcomp") return cmd_seqcomp(argc, argv);
         if (cmd == "buildsets") return cmd_buildsets(argc, argv);
         usage();
         return 2;

@@ -7,6 +7,7 @@ Follows (all under src/main/java/org/theseed/proteins/kmers/reps/):
   group      RepMatrixProcessor.java:88-125 + SequenceInfo.java:62-148 (double accumulation in that exact order)
   classify   ClassifyProcessor.java:112-120
   neighbors  NeighborProcessor.java:155-230 (insertion-sorted top-N with tie retention; Double.toString columns)
+  seqcomp    SeqCompProcessor.java:105-137 (every genome pair, self pairs included: protein and DNA k-mer distances)
   buildsets  BaseGenomeProcessor.java:151-214 (collateGenomes / copyReps / buildRepGenSet), :348-407 (list files)
 """
 import math
@@ -221,4 +222,23 @@ def neighbors(db_reps, seeds, num=5, min_sim=1, K=8, ident_inf=True):
             out.append("%s\t%s\t%s\t%d\t%s\t%s\t%s" % (prefix, ko.genome_id_of(db_reps[r][0]), db_reps[r][1], sim,
                                                      java_double_to_string(dist), flag, java_double_to_string(signal)))
             flag = " "
+    return "\n".join(out) + "\n"
+
+
+def seqcomp(rows, K=8, dna_k=15):
+    """rows: [(genome_id, name, seed_protein, ssu_rna)] -> report text.  Pair order: ascending genome id (the iteration
+    order assumed for the un-vendored GenomeDescriptorSet), each genome with itself and with every later one."""
+    o = ko.get()
+    rows = sorted(rows, key=lambda r: r[0])
+    pb = o.batch([r[2] for r in rows], K=K)
+    pm = o.sim_matrix(pb, ident_inf=True, threads=4)
+    ps = pb.sizes()
+    dsets = [ko.py_dna_kmers(r[3], dna_k) for r in rows]
+    out = ["genome1\tname1\tgenome2\tname2\tseed_dist\trna_dist"]
+    for i in range(len(rows)):
+        for j in range(i, len(rows)):
+            pd = o.distance(int(pm[i, j]), ps[i], ps[j])
+            dsim = ko.INFINITY if rows[i][3].lower() == rows[j][3].lower() else len(dsets[i] & dsets[j])
+            dd = o.distance(dsim, len(dsets[i]), len(dsets[j]))
+            out.append("%s\t%s\t%s\t%s\t%s\t%s" % (rows[i][0], rows[i][1], rows[j][0], rows[j][1], ko.java_fixed(pd, 6, 4), ko.java_fixed(dd, 6, 4)))
     return "\n".join(out) + "\n"

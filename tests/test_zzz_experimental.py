@@ -199,3 +199,35 @@ def test_dna_kmers_both_strands():
     with pytest.raises(kr.KrError):
         c.encode(["acgtacgtacgtacgtacgt", "acgtacgtrcgtacgtacgt"])
     c.close()
+
+
+def test_seqcomp_command(tmp_path, rep50):
+    """`kmers_reps seqcomp` (SeqCompProcessor.java:105-137): protein and SSU-rRNA k-mer distances of every genome pair,
+    byte for byte against the restatement.  The host tool finds the library through LD_LIBRARY_PATH, so this needs the
+    experimental build to be the one named libkmersreps_cuda.so there (tools/exp_gpu_check.sh arranges that)."""
+    import os
+    import subprocess
+    from oracle import kr_oracle as ko
+    from oracle import ref_commands as rc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "kmers", "reps_b200", "host", "kmers_reps")
+    rng = np.random.default_rng(12)
+    alpha = np.frombuffer(b"acgt", dtype=np.uint8)
+    roots = [alpha[rng.integers(0, 4, 900)] for _ in range(3)]
+    rows = []
+    for i, (fid, name, prot) in enumerate(rep50["reps"][:40]):
+        d = roots[i % 3].copy()
+        pos = rng.integers(0, 900, 3 + 20 * (i % 4))
+        d[pos] = alpha[rng.integers(0, 4, len(pos))]
+        dna = d.tobytes().decode()
+        dna = ko.py_dna_revcomp(dna) if i % 5 == 2 else (dna.upper() if i % 5 == 1 else dna)
+        rows.append((ko.genome_id_of(fid), name, prot, dna))
+    rows.append((ko.genome_id_of(rep50["reps"][40][0]), "copy", rows[3][2], rows[3][3]))     # equal to genome 3 in both sequences
+    tbl = tmp_path / "seqs.tbl"
+    tbl.write_text("genome_id\tgenome_name\tseed_protein\tssu_rna\n" + "".join("%s\t%s\t%s\t%s\n" % r for r in rows))
+    p = subprocess.run([tool, "seqcomp", "-k", "15", str(tbl)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()
+    want = rc.seqcomp(rows, K=8, dna_k=15)
+    assert p.stdout.decode() == want
+    lines = want.split("\n")[1:-1]
+    assert len(lines) == len(rows) * (len(rows) + 1) // 2 and any(ln.endswith("0.0000\t0.0000") for ln in lines)

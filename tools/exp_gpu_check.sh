@@ -9,7 +9,8 @@ EXP=$PWD/kmers/reps_b200/libkmersreps_cuda_exp.so
 # 1. the default library: the whole GPU suite (includes tests never run on hardware: neighbors, buildsets, sub-chunks)
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/exp_pytest_default.log
 # 2. the experimental library: the same suite + tests/test_zzz_experimental.py
-KR_LIB_PATH=$EXP timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/exp_pytest_exp.log
+EXPDIR=$(mktemp -d); ln -s $EXP $EXPDIR/libkmersreps_cuda.so     # the host tools find the library through LD_LIBRARY_PATH
+KR_LIB_PATH=$EXPDIR/libkmersreps_cuda.so LD_LIBRARY_PATH=$EXPDIR timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/exp_pytest_exp.log
 # 2b. the library with the experimental paths as DEFAULTS for every context (what the default becomes after this check):
 #     the whole suite again, host tools included (they find the library through LD_LIBRARY_PATH)
 V2DIR=$(mktemp -d); ln -s $PWD/kmers/reps_b200/libkmersreps_cuda_v2.so $V2DIR/libkmersreps_cuda.so
