@@ -178,9 +178,21 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
             ctx_make(&f.ctx, f.stack.data(), stack_bytes, fiber_main);
         }
         sc.idle_yields = 0;
+        // Between two synchronisation points a fiber runs undisturbed, so the ORDER in which the fibers of a CTA get
+        // their turn decides which side of a missing barrier wins.  KR_EMUL_ORDER=reverse / random runs them last-to-first /
+        // shuffled per CTA: a kernel that only works because thread 0 happens to run first fails under one of them.
+        static const char *order_mode = getenv("KR_EMUL_ORDER");
+        std::vector<unsigned> order(block.x);
+        for (unsigned t = 0; t < block.x; ++t) order[t] = t;
+        if (order_mode && !strcmp(order_mode, "reverse")) std::reverse(order.begin(), order.end());
+        else if (order_mode && !strcmp(order_mode, "random")) {
+            uint64_t x = 0x9E3779B97F4A7C15ull * (b + 1) + block.x;
+            for (unsigned t = block.x; t > 1; --t) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; std::swap(order[t - 1], order[x % t]); }
+        }
         for (unsigned live = block.x; live;) {
             live = 0;
-            for (unsigned t = 0; t < block.x; ++t) {
+            for (unsigned ti = 0; ti < block.x; ++ti) {
+                const unsigned t = order[ti];
                 if (sc.fibers[t].done) continue;
                 sc.cur = t;
                 ctx_switch(&sc.main, &sc.fibers[t].ctx);

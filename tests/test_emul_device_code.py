@@ -28,6 +28,17 @@ def emul_lib():
     return LIB
 
 
+@pytest.mark.parametrize("order,case", [("reverse", "matrix_layouts"), ("reverse", "subchunks"), ("random", "find_closest_and_build"),
+                                        ("reverse", "exp_pairs"), ("random", "exp_idxq_warp"), ("reverse", "exp_encode_warp")])
+def test_device_code_under_other_thread_orders(emul_lib, order, case):
+    """between synchronisation points an emulated thread runs undisturbed, so the order in which a CTA's threads take
+    their turn decides which side of a missing barrier wins; last-to-first and shuffled orders must give the same results"""
+    env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2", KR_EMUL_ORDER=order)
+    p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=900)
+    assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]
+
+
 def build_variant(name, *defines):
     out = os.path.join(EMUL, "_build", name)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMUL, "cuda_emul.h")]
