@@ -172,6 +172,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
         Block blk(block.x);
         cur_block() = &blk;
         blockIdx.x = b;
+        memset(base, 0xCD, smem_bytes);                // shared memory starts undefined in every CTA: make reliance on zeros show
         for (unsigned t = 0; t < block.x; ++t) {
             Fiber &f = sc.fibers[t];
             f.done = false; f.tid = dim3(t);
