@@ -446,10 +446,11 @@ def main():
               "frac": (out_bytes + list_bytes) / (join_ms / 1e3) / 1e9 / hbm, "output_bytes": out_bytes, "blocklist_bytes": list_bytes,
               "note": "bytes the tile-join design moves per launch: result once + both block lists of every tile once (block lists mostly hit L2)"}
     # ncu --set full capture of this kernel on this workload (profiles/README.md): 3.126 GB read + 10.076 GB written
-    traffic = 13201831000 if (world == 1 and N == 100000 and esz == 2) else None
+    traffic = 13201831000 if (world == 1 and N == 100000 and esz == 2 and not args.exp_pairs) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                 "traffic_unit": "bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_k_join_details.txt)",
-                "kernel": "k_join<MATRIX>", "kernel_ms": join_ms, "peak_source": hbm_src,
+                "kernel": "zero fill + k_bk_pairs / k_pairs_emit + equal-sequence pass (experimental posting-list path)" if args.exp_pairs else "k_join<MATRIX>",
+                "kernel_ms": join_ms, "peak_source": hbm_src,
                 "algorithmic_bytes": key_stream,
                 "note": "contract figure of SURVEY.md 8d.1 (every pair streams both key lists: 8(|A|+|B|)+4 B/pair). The tile join "
                         "shares one pass over two 256-sequence block lists among 65,536 pairs, so this fraction exceeds 1; see "
