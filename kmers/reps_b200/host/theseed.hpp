@@ -562,6 +562,7 @@ class SequenceKmers {
     virtual ~SequenceKmers() = default;
     SequenceKmers() = default;
     const std::string &getSequence() const { return sequence_; }
+    int getLen() const { return (int)sequence_.size(); }   // ProteinDataFactory.java:308
 
     // number of distinct k-mers (ScoreCouplingReporter.java:73)
     int size() const { ensure(); return (int)size_; }
@@ -711,13 +712,15 @@ class RepGenomeDb {
       public:
         Representation() = default;
         Representation(const RepGenomeDb *db, const RepGenome *rep, int sim, double dist) : db_(db), rep_(rep), sim_(sim), dist_(dist) {}
+        // Representation(String repId, int score, double distance): a stored result without the object (ProteinData.java:242)
+        Representation(const RepGenomeDb *db, std::string repId, int score, double dist) : db_(db), sim_(score), dist_(dist), repId_(std::move(repId)) {}
         int getSimilarity() const { return sim_; }
         double getDistance() const { return dist_; }
         const RepGenome *getRepresentative() const { return rep_; }
-        std::string getGenomeId() const { return rep_ ? rep_->getGenomeId() : std::string(); }
+        std::string getGenomeId() const { return rep_ ? rep_->getGenomeId() : repId_; }
         bool isRepresented() const { return db_ && sim_ >= db_->getThreshold(); }
       private:
-        const RepGenomeDb *db_ = nullptr; const RepGenome *rep_ = nullptr; int sim_ = 0; double dist_ = 1.0;
+        const RepGenomeDb *db_ = nullptr; const RepGenome *rep_ = nullptr; int sim_ = 0; double dist_ = 1.0; std::string repId_;
     };
 
     explicit RepGenomeDb(int threshold, std::string protName = DEFAULT_PROTEIN)   // RepGenomeDbProcessor.java:122
@@ -954,6 +957,16 @@ class KmerCollectionGroup {
     double getDistance(const Sequence &seq, const std::string &group) {
         std::vector<std::pair<const Sequence *, std::string>> one{{&seq, group}};
         return getDistances(one)[0];
+    }
+    // getBest(seq) [recalled member of the un-vendored class]: the group closest to the sequence and that distance; ties
+    // go to the group that comes first in name order; ("", 1.0) when there is no group
+    std::pair<std::string, double> getBest(const Sequence &seq) {
+        std::vector<std::pair<const Sequence *, std::string>> q;
+        for (auto &g : groups_) q.emplace_back(&seq, g.first);
+        std::vector<double> d = getDistances(q);
+        std::pair<std::string, double> best{"", 1.0};
+        for (size_t i = 0; i < q.size(); ++i) if (d[i] < best.second) best = {q[i].second, d[i]};
+        return best;
     }
     // batched form: every (sequence, group) query in one pass per group
     std::vector<double> getDistances(const std::vector<std::pair<const Sequence *, std::string>> &queries) {
