@@ -9,7 +9,8 @@
 //   selftest dtos               < doubles                    -> Double.toString
 //   selftest resave IN OUT                                   -> RepGenomeDb::load(IN)->save(OUT)
 //   selftest fasta              < FASTA                      -> "label\tcomment\tsequence" lines
-#include "theseed.hpp"
+//   selftest seed FILE.gto ...                               -> GTO ingest + seed-protein lookup, one line per genome
+#include "genome.hpp"
 
 using namespace theseed;
 
@@ -51,6 +52,13 @@ int main(int argc, char **argv) {
             FastaInputStream in(std::cin);
             Sequence s;
             while (in.next(s)) std::cout << s.label << '\t' << s.comment << '\t' << s.sequence << '\n';
+        } else if (cmd == "seed") {   // GTO files -> "genome id, domain, seed feature id, genome name, seed protein" (no GPU call)
+            for (int i = 2; i < argc; ++i) {
+                Genome g(argv[i]);
+                const std::string fid = findSeed(g);
+                std::cout << g.getId() << '\t' << g.getDomain() << '\t' << fid << '\t' << g.getName() << '\t'
+                          << (fid.empty() ? std::string() : g.getFeature(fid)->getProteinTranslation()) << '\n';
+            }
         } else if (cmd == "genomeof") {
             std::string line;
             while (std::getline(std::cin, line)) std::cout << genomeOf(line) << '\n';

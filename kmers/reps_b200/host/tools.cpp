@@ -4,6 +4,7 @@
 //   kmers_reps distances  DistanceMatrixProcessor.java   all-vs-all distances of the reps of a DB
 //   kmers_reps group      RepMatrixProcessor.java        incremental all-vs-all + greedy grouping by distance
 //   kmers_reps classify   ClassifyProcessor.java         min distance of each input sequence to its named group
+//   kmers_reps gtoclass   GtoClassProcessor.java          closest representative of every genome of a GTO directory (BASELINE configs[0])
 //   kmers_reps neighbors  NeighborProcessor.java          the N closest representatives of each input genome, ties retained
 //   kmers_reps seqcomp    SeqCompProcessor.java           seed-protein distance against SSU-rRNA distance for every genome pair
 //   kmers_reps buildsets  GenomeProcessor.java + BaseGenomeProcessor.java:151-214,348-407,433-442
@@ -12,7 +13,7 @@
 //
 // Same options, same output text.  What changed is only what north_star lists: the
 // per-pair / per-query loops became batched calls; every similarity comes from the GPU library.
-#include "theseed.hpp"
+#include "genome.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -25,6 +26,7 @@ static void usage() {
                  "  distances dbFile\n"
                  "  group     [-K k] [-i fasta] [-m maxDist]\n"
                  "  classify  [-K k] [-i fasta] [-m maxDist] controlFile\n"
+                 "  gtoclass  genomeDir repgen1.db [repgen2.db ...]\n"
                  "  neighbors [-n num] [--min sim] dbFile seeds.tbl\n"
                  "  seqcomp   [-K protK] [-k dnaK] seqTable.tbl      (DNA k-mers: needs a library with the DNA encoder)\n"
                  "  buildsets [-K k] [-t 10,50,100,200] [-p role] [--batch n] outDir input.fa\n";
@@ -254,6 +256,52 @@ static int cmd_classify(int argc, char **argv) {
     return 0;
 }
 
+// ---- gtoclass (GtoClassProcessor.java:100-186) ----------------------------------------------------------------
+// For every genome of the source directory (Bacteria and Archaea only, :118) the seed protein is looked up and its closest
+// representative in each RepGen database is reported, blank when it is not represented (:133-141).  The per-genome
+// findClosest calls become one batched call per database.
+static int cmd_gtoclass(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-v", "v"}, {"--verbose", "v"}, {"-t", "t"}, {"--type", "t"}}, {"t"});
+    if (a.pos.size() < 2) throw std::runtime_error("ParseFailureException: Arguments \"genomeDir\" and \"repgen files\" are required");
+    if (a.opt.count("t") && a.opt["t"] != "DIR") throw std::runtime_error("ParseFailureException: only genome sources of type DIR are read here");
+    std::vector<std::unique_ptr<RepGenomeDb>> repGens;
+    std::string header = "genome_id\tgenome_name";
+    for (size_t i = 1; i < a.pos.size(); ++i) {   // buildRepGens :166-186
+        std::ifstream probe(a.pos[i]);
+        if (!probe) throw std::runtime_error("java.io.FileNotFoundException: RepGen file " + a.pos[i] + " is not found or unreadable.");
+        repGens.push_back(RepGenomeDb::load(a.pos[i]));
+        header += "\tRepGen." + std::to_string(repGens.back()->getThreshold());
+    }
+    std::cout << header << '\n';
+    struct Row { std::string id, name; };
+    std::vector<Row> rows; std::vector<ProteinKmers> seeds;
+    int gCount = 0, noSeed = 0;
+    for (const std::string &file : genomeDirectory(a.pos[0])) {
+        Genome genome(file);
+        ++gCount;
+        if (genome.getDomain() != "Bacteria" && genome.getDomain() != "Archaea") continue;   // LEGAL_DOMAINS :63,118
+        const std::string protId = findSeed(genome);
+        if (protId.empty()) { ++noSeed; continue; }                                           // :123-125
+        rows.push_back({genome.getId(), genome.getName()});
+        seeds.emplace_back(genome.getFeature(protId)->getProteinTranslation());
+    }
+    std::vector<const ProteinKmers *> qp;
+    for (auto &q : seeds) qp.push_back(&q);
+    std::vector<std::vector<RepGenomeDb::Representation>> res;
+    for (auto &db : repGens) res.push_back(db->findClosest(qp.begin(), qp.end()));
+    int foundCount = 0, errorCount = noSeed * (int)repGens.size();
+    for (size_t g = 0; g < rows.size(); ++g) {
+        std::cout << rows[g].id << '\t' << rows[g].name;
+        for (size_t i = 0; i < repGens.size(); ++i) {
+            const auto &r = res[i][g];
+            if (r.isRepresented()) { std::cout << '\t' << r.getGenomeId(); ++foundCount; } else { std::cout << '\t'; ++errorCount; }
+        }
+        std::cout << '\n';
+    }
+    if (a.flag.count("v")) std::cerr << gCount << " genomes processed. " << foundCount << " representatives found; " << errorCount << " failures.\n";
+    return 0;
+}
+
 // ---- neighbors (NeighborProcessor.java:130-230) ---------------------------------------------------------
 // The reference reads genomes from a GenomeSource and takes each one's seed protein and DNA length; GTO ingest is
 // outside the path, so the input here is a tab-delimited file with a header line and the columns
@@ -404,6 +452,7 @@ int main(int argc, char **argv) {
         if (cmd == "distances") return cmd_distances(argc, argv);
         if (cmd == "group") return cmd_group(argc, argv);
         if (cmd == "classify") return cmd_classify(argc, argv);
+        if (cmd == "gtoclass") return cmd_gtoclass(argc, argv);
         if (cmd == "neighbors") return cmd_neighbors(argc, argv);
         if (cmd == "seqcomp") return cmd_seqcomp(argc, argv);
         if (cmd == "buildsets") return cmd_buildsets(argc, argv);

@@ -77,6 +77,31 @@ def main():
         for (fid, name, prot) in seeds:
             f.write(ko.write_fasta_record(fid, name, prot))
 
+    # --- reduced GTOs for the gtoclass command (GtoClassProcessor): identity fields + a dozen features each ------------
+    mini = os.path.join(HERE, "gto_mini")
+    os.makedirs(mini, exist_ok=True)
+    for p in (gtos[0], gtos[1], gtos[6]):                      # 202462.4 (Bacteria), 1001994.6 (Archaea), 1408469.3
+        g = json.load(open(p))
+        gid, best = seed_protein(p)
+        keep = [ft for ft in g["features"] if ft["id"] == best[0]]
+        keep += [ft for ft in g["features"] if ft["id"] != best[0]][:11]
+        feats = [{k: ft.get(k) for k in ("id", "type", "function", "protein_translation")} for ft in keep]
+        if gid == "202462.4":
+            # a shorter feature with the same role written with its EC number and a comment: the longest one must still win
+            feats.insert(0, {"id": "fig|202462.4.peg.9001", "type": "CDS", "function": SEED_FUNCTION + " (EC 6.1.1.20) # fragment",
+                             "protein_translation": best[2][:120]})
+        out = {"id": g["id"], "scientific_name": g["scientific_name"], "domain": g["domain"], "genetic_code": g.get("genetic_code", 11),
+               "features": feats, "contigs": [], "note": "reduced copy of data/%s for tests (tests/golden/make_golden.py)" % os.path.basename(p)}
+        with open(os.path.join(mini, gid + ".gto"), "w") as f:
+            json.dump(out, f, indent=1)
+    euk = {"id": "4932.99", "scientific_name": "Saccharomyces test genome \u00e9", "domain": "Eukaryota",
+           "features": [{"id": "fig|4932.99.peg.1", "type": "CDS", "function": SEED_FUNCTION, "protein_translation": seeds[0][2]}]}
+    json.dump(euk, open(os.path.join(mini, "4932.99.gto"), "w"), indent=1)
+    noseed = {"id": "99999.1", "scientific_name": "Genome without \"seed\" protein", "domain": "Bacteria",
+              "features": [{"id": "fig|99999.1.peg.1", "type": "CDS", "function": "Phenylalanyl-tRNA synthetase beta chain (EC 6.1.1.20)",
+                            "protein_translation": "MKVLAAGIVGLAAA"}, {"id": "fig|99999.1.rna.1", "type": "rna", "function": "tRNA-Thr", "protein_translation": ""}]}
+    json.dump(noseed, open(os.path.join(mini, "99999.1.gto"), "w"), indent=1)
+
     # --- duplicate-heavy real set -------------------------------------------------------
     lines = open(os.path.join(DATA, "rickettsia.roles.tbl")).read().split("\n")
     hdr = lines[0].split("\t")

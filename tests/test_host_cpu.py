@@ -212,3 +212,24 @@ def test_fasta_reader_and_genome_ids(vapb, rep50):
     fids = [f for (f, _, _) in rep50["reps"][:50]] + ["fig|83333.1.peg.4", "notafig", "fig|12.peg.1"]
     got = run(["genomeof"], "\n".join(fids) + "\n").stdout.decode().split("\n")[:-1]
     assert got == [ko.genome_id_of(f) for f in fids]
+
+
+def test_gto_reader_and_seed_lookup(gto_seeds):
+    """genome.hpp: the JSON reader, the GTO fields and GenomeDescriptor.findSeed's rule on the reduced GTOs of tests/golden
+    (escapes, a eukaryote, a genome without seed, a shorter decoy with EC number + comment) -- and, where the reference tree
+    is present (this container, not the GPU box), on the ten bundled full-size GTOs against the golden seed proteins"""
+    gdir = os.path.join(ROOT, "tests", "golden", "gto_mini")
+    files = sorted(os.path.join(gdir, f) for f in os.listdir(gdir))
+    rows = [ln.split("\t") for ln in run(["seed"] + files).stdout.decode().split("\n")[:-1]]
+    by_id = {r[0]: r for r in rows}
+    seeds = {ko.genome_id_of(f): (f, n, s) for (f, n, s) in gto_seeds}
+    for g in ("202462.4", "1001994.6", "1408469.3"):
+        assert by_id[g][2:] == [seeds[g][0], seeds[g][1], seeds[g][2]]
+    assert by_id["1001994.6"][1] == "Archaea" and by_id["4932.99"][1] == "Eukaryota"
+    assert by_id["4932.99"][3] == "Saccharomyces test genome \u00e9"            # \u escape -> UTF-8
+    assert by_id["99999.1"][2] == "" and by_id["99999.1"][3] == 'Genome without "seed" protein'
+    ref = "/root/reference/data"
+    if os.path.isdir(ref):
+        full = [os.path.join(ref, "202462.4.gto")] + sorted(os.path.join(ref, "P3Master", f) for f in os.listdir(os.path.join(ref, "P3Master")) if f.endswith(".gto"))
+        rows = [ln.split("\t") for ln in run(["seed"] + full).stdout.decode().split("\n")[:-1]]
+        assert [(r[2], r[3], r[4]) for r in rows] == [tuple(x) for x in gto_seeds]

@@ -152,3 +152,26 @@ def test_neighbors_top_n_with_ties(tmp_path, rep50, gto_seeds, rickettsia, oracl
     assert any(r[5] == "9999" and r[6] == "0.0" for v in per.values() for r in v)
     assert per["9.9"][0][3:] == ["", "", "", "", "", ""]
     assert run(["neighbors", "-n", "0", str(db), str(src)], check=False).returncode != 0
+
+
+def test_gtoclass_on_reduced_gtos(tmp_path, rep50, gto_seeds, oracle):
+    """`gtoclass` (GtoClassProcessor.java:114-151, BASELINE configs[0]): GTO ingest, seed-protein lookup (longest feature
+    with the role, EC number and comment tolerated), domain filter, one batched findClosest per database; blank column when
+    the genome is not represented.  tests/golden/gto_mini holds reduced copies of three bundled GTOs plus a eukaryote and a
+    genome without seed protein (tests/golden/make_golden.py)."""
+    gdir = os.path.join(ROOT, "tests", "golden", "gto_mini")
+    db50 = tmp_path / "rep50.db"
+    db50.write_bytes(rep50["raw"])
+    db300 = tmp_path / "rep300.db"
+    db300.write_bytes(rep50["raw"].replace(b">Rep50,K=8", b">Rep300,K=8", 1))
+    p = run(["gtoclass", "-v", gdir, str(db50), str(db300)])
+    seeds = {ko.genome_id_of(f): (n, s) for (f, n, s) in gto_seeds}
+    rb = oracle.batch([s for (_, _, s) in rep50["reps"]], K=8)
+    want = ["genome_id\tgenome_name\tRepGen.50\tRepGen.300"]
+    for g in sorted(["202462.4", "1001994.6", "1408469.3"]):                      # directory order: by genome id
+        bs, bi = oracle.find_closest(rb, oracle.batch([seeds[g][1]], K=8))
+        rep = ko.genome_id_of(rep50["reps"][int(bi[0])][0])
+        want.append("%s\t%s\t%s\t%s" % (g, seeds[g][0], rep if bs[0] >= 50 else "", rep if bs[0] >= 300 else ""))
+    assert p.stdout.decode() == "\n".join(want) + "\n"
+    assert "5 genomes processed. 3 representatives found; 5 failures." in p.stderr.decode()   # 3 misses at 300 + the seedless genome twice
+    assert run(["gtoclass", str(tmp_path / "nowhere"), str(db50)], check=False).returncode != 0
