@@ -110,18 +110,19 @@ class Genome {
         const std::string text = ss.str();
         const Json g = JsonParser(text).parse();
         if (g.type != Json::Object) throw std::runtime_error("java.io.IOException: " + file + " is not a genome typed object");
-        id_ = g.text("id"); name_ = g.text("scientific_name"); domain_ = g.text("domain");
+        id_ = g.text("id"); name_ = g.text("scientific_name"); domain_ = g.text("domain"); ssuRRna_ = g.text("ssu_rrna");
         if (const Json *fs = g.get("features"))
             for (const Json &f : fs->arr) features_.push_back(Feature{f.text("id"), f.text("type"), f.text("function"), f.text("protein_translation")});
     }
     const std::string &getId() const { return id_; }
     const std::string &getName() const { return name_; }
     const std::string &getDomain() const { return domain_; }
+    const std::string &getSsuRRna() const { return ssuRRna_; }   // GtoRepGenomeProcessor.java:224
     const std::vector<Feature> &getFeatures() const { return features_; }
     const Feature *getFeature(const std::string &fid) const { for (auto &f : features_) if (f.id == fid) return &f; return nullptr; }
     std::string toString() const { return id_ + " (" + name_ + ")"; }
   private:
-    std::string id_, name_, domain_;
+    std::string id_, name_, domain_, ssuRRna_;
     std::vector<Feature> features_;
 };
 
@@ -145,6 +146,28 @@ inline std::string findSeed(const Genome &genome, const std::string &role = RepG
         if (!best || f.proteinTranslation.size() > best->proteinTranslation.size()) best = &f;
     }
     return best ? best->id : std::string();
+}
+
+// RepGenomeDb.getSeedProtein(genome) (GtoRepGenomeProcessor.java:213): the genome's seed protein as a RepGenome, found by
+// the database's protein name; empty when the genome has none.  (Same rule as GtoRepBuildProcessor.computeRepGenome
+// :176-192: the longest protein feature with the role.)
+inline std::unique_ptr<RepGenome> getSeedProtein(const RepGenomeDb &db, const Genome &genome) {
+    const std::string fid = findSeed(genome, db.getProtName());
+    if (fid.empty()) return nullptr;
+    return std::make_unique<RepGenome>(fid, genome.getName(), genome.getFeature(fid)->getProteinTranslation());
+}
+
+// first column of a tab-delimited file with a header line (TabbedLineReader.readColumn / readSet(file, "1"))
+inline std::vector<std::string> readFirstColumn(const std::string &file) {
+    std::ifstream in(file);
+    if (!in) throw std::runtime_error("java.io.FileNotFoundException: " + file);
+    std::vector<std::string> out; std::string line;
+    std::getline(in, line);
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty()) out.push_back(line.substr(0, line.find('\t')));
+    }
+    return out;
 }
 
 // GenomeSource of type DIR: the *.gto files of a directory, in genome-id order [recalled: GenomeDirectory keeps a sorted set]

@@ -5,6 +5,8 @@
 //   kmers_reps group      RepMatrixProcessor.java        incremental all-vs-all + greedy grouping by distance
 //   kmers_reps classify   ClassifyProcessor.java         min distance of each input sequence to its named group
 //   kmers_reps gtoclass   GtoClassProcessor.java          closest representative of every genome of a GTO directory (BASELINE configs[0])
+//   kmers_reps gtoreps    GtoRepGenomeProcessor.java      closest representative of every genome; --create / --update add the outliers
+//   kmers_reps buildfromgtos GtoRepBuildProcessor.java     greedy representative set from a GTO directory, optional --verify report
 //   kmers_reps neighbors  NeighborProcessor.java          the N closest representatives of each input genome, ties retained
 //   kmers_reps seqcomp    SeqCompProcessor.java           seed-protein distance against SSU-rRNA distance for every genome pair
 //   kmers_reps buildsets  GenomeProcessor.java + BaseGenomeProcessor.java:151-214,348-407,433-442
@@ -27,6 +29,8 @@ static void usage() {
                  "  group     [-K k] [-i fasta] [-m maxDist]\n"
                  "  classify  [-K k] [-i fasta] [-m maxDist] controlFile\n"
                  "  gtoclass  genomeDir repgen1.db [repgen2.db ...]\n"
+                 "  gtoreps   [--create thr] [--update newDb] [--filter ids.tbl] [--blackList ids.tbl] [--rna] [-o out] repDb gtoDir\n"
+                 "  buildfromgtos [-K k] [-m sim] [--verify seeds.fa] [--batch n] gtoDir roleFile outDb\n"
                  "  neighbors [-n num] [--min sim] dbFile seeds.tbl\n"
                  "  seqcomp   [-K protK] [-k dnaK] seqTable.tbl      (DNA k-mers: needs a library with the DNA encoder)\n"
                  "  buildsets [-K k] [-t 10,50,100,200] [-p role] [--batch n] outDir input.fa\n";
@@ -302,6 +306,132 @@ static int cmd_gtoclass(int argc, char **argv) {
     return 0;
 }
 
+// ---- gtoreps (GtoRepGenomeProcessor.java:136-314) --------------------------------------------------------------
+// Report the closest representative of every genome of a GTO directory.  With --create / --update an outlier (nothing
+// close, or below the threshold) is ADDED to the database and the genomes after it see it (:296-303), which makes the scan
+// sequential; it is batched here as: findClosest of all remaining genomes, rows up to and including the first outlier are
+// final, add that outlier, repeat from the next genome.  Without update it is one batched findClosest.
+// Not reproduced: --save (writing outlier GTOs).
+static int cmd_gtoreps(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"--create", "create"}, {"--update", "update"}, {"--filter", "filter"}, {"--blackList", "black"}, {"--rna", "rna"},
+                                   {"-o", "o"}, {"--output", "o"}, {"-t", "t"}, {"--type", "t"}, {"-v", "v"}},
+                   {"create", "update", "filter", "black", "o", "t"});
+    if (a.pos.size() != 2) throw std::runtime_error("ParseFailureException: Arguments \"repDb.ser\" and \"gtoDir\" are required");
+    const std::string repDbFile = a.pos[0], gtoDir = a.pos[1];
+    std::unique_ptr<RepGenomeDb> repDb;
+    std::string updateFile = a.opt.count("update") ? a.opt["update"] : std::string();
+    if (!a.opt.count("create")) {   // :146-153
+        std::ifstream probe(repDbFile);
+        if (!probe) throw std::runtime_error("java.io.FileNotFoundException: Representative-genome database " + repDbFile + " not found or unreadable.");
+        repDb = RepGenomeDb::load(repDbFile);
+    } else if (!updateFile.empty()) {
+        throw std::runtime_error("ParseFailureException: Update file is mutually exclusive with create mode.");   // :155
+    } else {
+        repDb = std::make_unique<RepGenomeDb>(std::stoi(a.opt["create"]));   // :159-160
+        updateFile = repDbFile;
+    }
+    std::vector<std::string> files = genomeDirectory(gtoDir);
+    std::map<std::string, std::string> byId;
+    for (auto &f : files) { std::string id = f.substr(f.find_last_of('/') + 1); byId[id.substr(0, id.size() - 4)] = f; }
+    std::vector<std::string> idList;
+    if (a.opt.count("filter")) idList = readFirstColumn(a.opt["filter"]);   // :166
+    else for (auto &kv : byId) idList.push_back(kv.first);
+    std::set<std::string> blacklist;
+    if (a.opt.count("black")) { auto v = readFirstColumn(a.opt["black"]); blacklist.insert(v.begin(), v.end()); }
+    const bool rnaFlag = a.flag.count("rna") != 0;
+    std::ofstream fout;
+    if (a.opt.count("o")) { fout.open(a.opt["o"]); if (!fout) throw std::runtime_error("java.io.FileNotFoundException: " + a.opt["o"]); }
+    std::ostream &writer = a.opt.count("o") ? static_cast<std::ostream &>(fout) : std::cout;
+    writer << "genome_id\tgenome_name\trep_id\trep_name\tsimilarity\tdistance\toutlier\n";   // :198
+    std::vector<RepGenome> todo, deferrals;
+    int skipCount = 0;
+    for (const std::string &genomeId : idList) {   // :206-241
+        auto it = byId.find(genomeId);
+        if (it == byId.end()) continue;            // "completely acceptable for the genome to not be in the source"
+        Genome genome(it->second);
+        std::unique_ptr<RepGenome> rep = getSeedProtein(*repDb, genome);
+        if (!rep) { ++skipCount; continue; }
+        if (blacklist.count(genome.getId())) { deferrals.push_back(*rep); continue; }
+        if (rnaFlag) {
+            if (genome.getSsuRRna().empty()) { ++skipCount; continue; }
+            if (genome.getSsuRRna().size() < 1400) { deferrals.push_back(*rep); continue; }   // MIN_RNA_LEN :78
+        }
+        todo.push_back(*rep);
+    }
+    for (auto &d : deferrals) todo.push_back(d);   // :243-247
+    int outCount = 0;
+    auto row = [&](const RepGenome &rep, const std::string &repId, const std::string &repName, int sim, double dist, const char *flag) {
+        writer << rep.getGenomeId() << '\t' << rep.getName() << '\t' << repId << '\t' << repName << '\t' << sim << '\t'
+               << java::format_fixed(dist, 8, 4) << '\t' << flag << '\n';
+    };
+    for (size_t pos = 0; pos < todo.size();) {   // processGenome :270-314
+        std::vector<const ProteinKmers *> qp;
+        for (size_t i = pos; i < todo.size(); ++i) qp.push_back(&todo[i]);
+        auto res = repDb->findClosest(qp.begin(), qp.end());
+        size_t i = pos;
+        for (; i < todo.size(); ++i) {
+            const auto &r = res[i - pos];
+            std::string repId, repName; int sim = 0; double dist = 1.0; bool outlier = false;
+            if (r.getSimilarity() == 0) outlier = true;
+            else {
+                repId = r.getGenomeId(); repName = r.getRepresentative()->getName(); sim = r.getSimilarity(); dist = r.getDistance();
+                if (sim < repDb->getThreshold()) outlier = true;
+            }
+            if (outlier) {
+                ++outCount;
+                if (!updateFile.empty()) { repDb->addRep(todo[i]); repId = todo[i].getGenomeId(); sim = 9999; dist = 0.0; }
+            }
+            row(todo[i], repId, repName, sim, dist, outlier ? "*" : "");
+            if (outlier && !updateFile.empty()) { ++i; break; }   // the database changed: the rest must be scored again
+        }
+        pos = i;
+    }
+    if (a.flag.count("v")) std::cerr << outCount << " outliers found, " << skipCount << " skipped due to missing seed protein.\n";
+    if (!updateFile.empty()) repDb->save(updateFile);   // :250-253
+    return 0;
+}
+
+// ---- buildfromgtos (GtoRepBuildProcessor.java:96-163) ------------------------------------------------------------
+// The role definition file (one role; RoleMap.load) is read as: last tab-separated field of its first non-empty line.
+static int cmd_buildfromgtos(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--kmer", "K"}, {"-m", "m"}, {"--sim", "m"}, {"--verify", "verify"}, {"--batch", "batch"}, {"-v", "v"}},
+                   {"K", "m", "verify", "batch"});
+    if (a.pos.size() != 3) throw std::runtime_error("ParseFailureException: Arguments \"gtoDir\", \"role.definitions\" and \"repDb\" are required");
+    const int kmerSize = a.opt.count("K") ? std::stoi(a.opt["K"]) : 8, minSim = a.opt.count("m") ? std::stoi(a.opt["m"]) : 100;   // :78-79
+    if (kmerSize < 2) throw std::runtime_error("ParseFailureException: Kmer size must be at least 2.");
+    if (minSim < 1) throw std::runtime_error("ParseFailureException: Minimum similarity must be at least 1.");
+    uint32_t batch = a.opt.count("batch") ? (uint32_t)std::stoul(a.opt["batch"]) : 0;
+    std::ifstream rf(a.pos[1]);
+    if (!rf) throw std::runtime_error("java.io.IOException: Role definition file is not found or unreadable.");
+    std::vector<std::string> roleLines; std::string line;
+    while (std::getline(rf, line)) { if (!line.empty() && line.back() == '\r') line.pop_back(); if (!line.empty()) roleLines.push_back(line); }
+    if (roleLines.size() != 1) throw std::runtime_error("ParseFailureException: Role definition file must contain exactly 1 role.");   // :101
+    const std::string role = roleLines[0].substr(roleLines[0].find_last_of('\t') == std::string::npos ? 0 : roleLines[0].find_last_of('\t') + 1);
+    if (a.opt.count("verify")) { std::ifstream vf(a.opt["verify"]); if (!vf) throw std::runtime_error("java.io.IOException: Verification file is not found or unreadable."); }
+    ProteinKmers::setKmerSize(kmerSize);
+    RepGenomeDb repDb(minSim, role);
+    std::vector<RepGenome> repGenomes;
+    for (const std::string &file : genomeDirectory(a.pos[0])) {   // computeRepGenome :170-203
+        Genome genome(file);
+        const std::string fid = findSeed(genome, role);
+        if (fid.empty()) continue;
+        repGenomes.emplace_back(fid, genome.getName(), genome.getFeature(fid)->getProteinTranslation());
+    }
+    repDb.checkGenomes(repGenomes, batch);   // :129-137
+    repDb.save(a.pos[2]);
+    if (!a.opt.count("verify")) { std::cout << "No verification requested.\n"; return 0; }   // :144
+    std::cout << "seq_id\tname\tsimilarity\n";
+    std::vector<Sequence> seqs = FastaInputStream(a.opt["verify"]).readAll();
+    std::vector<ProteinKmers> qs;
+    for (auto &q : seqs) qs.emplace_back(q.sequence);
+    std::vector<const ProteinKmers *> qp;
+    for (auto &q : qs) qp.push_back(&q);
+    auto res = repDb.findClosest(qp.begin(), qp.end());
+    for (size_t i = 0; i < seqs.size(); ++i)
+        if (!res[i].isRepresented()) std::cout << seqs[i].label << '\t' << seqs[i].comment << '\t' << res[i].getSimilarity() << '\n';
+    return 0;
+}
+
 // ---- neighbors (NeighborProcessor.java:130-230) ---------------------------------------------------------
 // The reference reads genomes from a GenomeSource and takes each one's seed protein and DNA length; GTO ingest is
 // outside the path, so the input here is a tab-delimited file with a header line and the columns
@@ -453,6 +583,8 @@ int main(int argc, char **argv) {
         if (cmd == "group") return cmd_group(argc, argv);
         if (cmd == "classify") return cmd_classify(argc, argv);
         if (cmd == "gtoclass") return cmd_gtoclass(argc, argv);
+        if (cmd == "gtoreps") return cmd_gtoreps(argc, argv);
+        if (cmd == "buildfromgtos") return cmd_buildfromgtos(argc, argv);
         if (cmd == "neighbors") return cmd_neighbors(argc, argv);
         if (cmd == "seqcomp") return cmd_seqcomp(argc, argv);
         if (cmd == "buildsets") return cmd_buildsets(argc, argv);

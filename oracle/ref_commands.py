@@ -242,3 +242,49 @@ def seqcomp(rows, K=8, dna_k=15):
             dd = o.distance(dsim, len(dsets[i]), len(dsets[j]))
             out.append("%s\t%s\t%s\t%s\t%s\t%s" % (rows[i][0], rows[i][1], rows[j][0], rows[j][1], ko.java_fixed(pd, 6, 4), ko.java_fixed(dd, 6, 4)))
     return "\n".join(out) + "\n"
+
+
+def gtoreps(db_reps, threshold, genomes, update, K=8):
+    """GtoRepGenomeProcessor.java:198,270-314.  db_reps: [(fid, name, seq)] of the loaded database in file order (empty for
+    --create); genomes: [(fid, genome_name, seq)] in processing order (deferrals last); update: outliers are added.
+    -> (report text, final reps in HashMap iteration order)"""
+    o = ko.get()
+    ids, by_id = [], {}
+    for r in db_reps:
+        g = ko.genome_id_of(r[0])
+        if g not in by_id:
+            ids.append(g)
+        by_id[g] = r
+    out = ["genome_id\tgenome_name\trep_id\trep_name\tsimilarity\tdistance\toutlier"]
+    for (fid, name, seq) in genomes:
+        gid = ko.genome_id_of(fid)
+        reps = [by_id[ids[i]] for i in o.java_hashmap_order(ids)] if ids else []
+        rep_id, rep_name, sim, dist, flag = "", "", 0, 1.0, ""
+        if reps:
+            rb, qb = o.batch([r[2] for r in reps], K=K), o.batch([seq], K=K)
+            bs, bi = o.find_closest(rb, qb)
+            if bs[0] > 0:
+                rep_id, rep_name, sim = ko.genome_id_of(reps[bi[0]][0]), reps[bi[0]][1], int(bs[0])
+                dist = o.distance(sim, qb.sizes()[0], rb.sizes()[bi[0]])
+        if sim == 0 or sim < threshold:
+            flag = "*"
+            if update:
+                if gid not in by_id:
+                    ids.append(gid)
+                by_id[gid] = (fid, name, seq)
+                rep_id, sim, dist = gid, 9999, 0.0
+        out.append("%s\t%s\t%s\t%s\t%d\t%s\t%s" % (gid, name, rep_id, rep_name, sim, ko.java_fixed(dist, 8, 4), flag))
+    final = [by_id[ids[i]] for i in o.java_hashmap_order(ids)] if ids else []
+    return "\n".join(out) + "\n", final
+
+
+def buildfromgtos_verify(db_reps, threshold, queries, K=8):
+    """GtoRepBuildProcessor.java:147-160: the sequences of the verification FASTA that the database does not represent"""
+    o = ko.get()
+    out = ["seq_id\tname\tsimilarity"]
+    if queries:
+        bs, _ = o.find_closest(o.batch([r[2] for r in db_reps], K=K), o.batch([q[2] for q in queries], K=K))
+        for q, s in zip(queries, bs):
+            if s < threshold:
+                out.append("%s\t%s\t%d" % (q[0], q[1], s))
+    return "\n".join(out) + "\n"

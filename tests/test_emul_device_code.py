@@ -85,7 +85,7 @@ def test_host_tools_on_the_emulator(emul_lib, tmp_path):
     os.symlink(emul_lib, d / "libkmersreps_cuda.so")
     env = dict(os.environ, KR_LIB_PATH=str(d / "libkmersreps_cuda.so"), LD_LIBRARY_PATH=str(d), KR_EMUL_SMS="2")
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_host_tools.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-                        "-k", "neighbors or classify or distances or group or error_behaviour or load_report or gtoclass"], env=env, cwd=ROOT,
+                        "-k", "neighbors or classify or distances or group or error_behaviour or load_report or gtoclass or gtoreps"], env=env, cwd=ROOT,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200)
     assert p.returncode == 0, p.stdout.decode()[-3000:]
 

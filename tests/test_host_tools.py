@@ -175,3 +175,67 @@ def test_gtoclass_on_reduced_gtos(tmp_path, rep50, gto_seeds, oracle):
     assert p.stdout.decode() == "\n".join(want) + "\n"
     assert "5 genomes processed. 3 representatives found; 5 failures." in p.stderr.decode()   # 3 misses at 300 + the seedless genome twice
     assert run(["gtoclass", str(tmp_path / "nowhere"), str(db50)], check=False).returncode != 0
+
+
+def write_gtos(gdir, genomes, role="Phenylalanyl-tRNA synthetase alpha chain"):
+    """synthetic GTO files: each genome gets its seed protein, a shorter decoy with the same role and an unrelated feature"""
+    import json
+    os.makedirs(gdir, exist_ok=True)
+    for (gid, name, prot, ssu) in genomes:
+        feats = [{"id": "fig|%s.peg.2" % gid, "type": "CDS", "function": role + " (EC 6.1.1.20) ## truncated", "protein_translation": prot[: len(prot) // 2]},
+                 {"id": "fig|%s.peg.7" % gid, "type": "CDS", "function": role, "protein_translation": prot},
+                 {"id": "fig|%s.rna.1" % gid, "type": "rna", "function": "tRNA-Thr", "protein_translation": ""}]
+        json.dump({"id": gid, "scientific_name": name, "domain": "Bacteria", "ssu_rrna": ssu, "features": feats}, open(os.path.join(gdir, gid + ".gto"), "w"))
+
+
+def test_gtoreps_and_buildfromgtos(tmp_path, oracle):
+    """`gtoreps` (GtoRepGenomeProcessor.java:198-314): report mode, --create (every outlier joins the database and is seen by
+    the genomes after it), --update with a black list (deferred genomes go last) and --rna; `buildfromgtos`
+    (GtoRepBuildProcessor.java:96-163) with its --verify report.  Byte for byte against the sequential restatements."""
+    res, off, _ = synth.generate(0x5EED000E, 90, 9)
+    seqs = synth.to_strings(res, off)
+    genomes = [("%d.%d" % (3000 + 7 * i, 1 + i % 3), "Genome number %d" % i, s, "acgt" * (400 if i % 9 else 100)) for i, s in enumerate(seqs)]
+    genomes[13] = (genomes[13][0], genomes[13][1], genomes[13][2], "")                      # no SSU rRNA at all
+    gdir = str(tmp_path / "gtos")
+    write_gtos(gdir, genomes)
+    order = sorted(genomes, key=lambda g: g[0])                                              # directory order: by genome id
+    recs = [("fig|%s.peg.7" % g[0], g[1], g[2]) for g in order]
+    # --create: the database grows while the directory is scanned
+    db = tmp_path / "new.db"
+    p = run(["gtoreps", "--create", "60", "-v", str(db), gdir])
+    text, final = rc.gtoreps([], 60, recs, update=True)
+    assert p.stdout.decode() == text
+    assert db.read_bytes() == ko.save_repdb(60, 8, "Phenylalanyl-tRNA synthetase alpha chain", final)
+    n_out = text.count("\t*\n")
+    assert 5 < n_out < 80 and ("%d outliers found, 0 skipped" % n_out) in p.stderr.decode()
+    # report mode against that database: nothing is added, every genome finds itself or its representative
+    p = run(["gtoreps", str(db), gdir])
+    text2, _ = rc.gtoreps(final, 60, recs, update=False)
+    assert p.stdout.decode() == text2 and "\t*\n" not in text2
+    # --update from a smaller database, black list + --rna: deferred genomes are processed last, the seedless SSU is skipped
+    small = tmp_path / "small.db"
+    small.write_bytes(ko.save_repdb(60, 8, "Phenylalanyl-tRNA synthetase alpha chain", final[:3]))
+    black = tmp_path / "black.tbl"
+    black.write_text("genome_id\tnote\n" + "".join("%s\tx\n" % g[0] for g in order[5:9]))
+    upd = tmp_path / "updated.db"
+    p = run(["gtoreps", "--update", str(upd), "--blackList", str(black), "--rna", "-o", str(tmp_path / "rep.tbl"), str(small), gdir])
+    main = [r for g, r in zip(order, recs) if g[3] != "" and len(g[3]) >= 1400 and g not in order[5:9]]
+    deferred = [r for g, r in zip(order, recs) if g[3] != "" and (g in order[5:9] or len(g[3]) < 1400)]
+    # deferral order: black-listed and short-RNA genomes in directory order
+    deferred = [r for g, r in zip(order, recs) if r in deferred]
+    text3, final3 = rc.gtoreps(final[:3], 60, main + deferred, update=True)
+    assert (tmp_path / "rep.tbl").read_text() == text3
+    assert upd.read_bytes() == ko.save_repdb(60, 8, "Phenylalanyl-tRNA synthetase alpha chain", final3)
+    # buildfromgtos: the same greedy set from the directory, then the verification report
+    roles = tmp_path / "roles.tbl"
+    roles.write_text("PhenTrnaSyntAlph\t\tPhenylalanyl-tRNA synthetase alpha chain\n")
+    ver = tmp_path / "verify.fa"
+    res2, off2, _ = synth.generate(0x5EED000F, 60, 12)
+    vq = [("fig|%d.1.peg.1" % (9000 + i), "query %d" % i, s) for i, s in enumerate(synth.to_strings(res2, off2))] + [recs[0]]
+    ver.write_bytes(fasta(vq))
+    out_db = tmp_path / "built.db"
+    p = run(["buildfromgtos", "-m", "60", "--verify", str(ver), gdir, str(roles), str(out_db)])
+    want_db, reps = rc.repdb_create(recs, 60, max_err=10 ** 9)
+    assert out_db.read_bytes() == want_db
+    assert p.stdout.decode() == rc.buildfromgtos_verify(reps, 60, vq)
+    assert run(["buildfromgtos", gdir, str(roles), str(tmp_path / "x.db")]).stdout.decode() == "No verification requested.\n"
