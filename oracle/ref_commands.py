@@ -288,3 +288,24 @@ def buildfromgtos_verify(db_reps, threshold, queries, K=8):
             if s < threshold:
                 out.append("%s\t%s\t%d" % (q[0], q[1], s))
     return "\n".join(out) + "\n"
+
+
+def ssureps(table, genomes, K=18):
+    """SsuRepGenomeProcessor.java:104-149.  table: [(genome_id, name, ssu_rna)] in file order; genomes: [(genome_id, name,
+    ssu_rna)] in directory order (those without an SSU are skipped).  Smallest distance wins, first in table order on ties."""
+    o = ko.get()
+    tsets = [ko.py_dna_kmers(t[2], K) for t in table]
+    out = ["genome_id\tgenome_name\trep_id\trep_name\tsimilarity\tdistance"]
+    for (gid, name, ssu) in genomes:
+        if not ssu:
+            continue
+        q = ko.py_dna_kmers(ssu, K)
+        best, bi, bsim = 1.0, -1, 0
+        for r, t in enumerate(table):
+            sim = ko.INFINITY if ssu.lower() == t[2].lower() else len(q & tsets[r])
+            d = o.distance(sim, len(q), len(tsets[r]))
+            if d < best:
+                best, bi, bsim = d, r, sim
+        if bi >= 0:
+            out.append("%s\t%s\t%s\t%s\t%d\t%s" % (gid, name, table[bi][0], table[bi][1], bsim, ko.java_fixed(best, 6, 4)))
+    return "\n".join(out) + "\n"

@@ -97,5 +97,5 @@ def test_seqcomp_on_the_emulator(emul_lib, tmp_path):
     os.symlink(emul_lib, d / "libkmersreps_cuda.so")
     env = dict(os.environ, KR_LIB_PATH=str(d / "libkmersreps_cuda.so"), LD_LIBRARY_PATH=str(d), KR_EMUL_SMS="2")
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zzz_experimental.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-                        "-k", "seqcomp"], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200)
+                        "-k", "seqcomp or ssureps"], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200)
     assert p.returncode == 0 and " passed" in p.stdout.decode(), p.stdout.decode()[-3000:]

@@ -231,3 +231,40 @@ def test_seqcomp_command(tmp_path, rep50):
     assert p.stdout.decode() == want
     lines = want.split("\n")[1:-1]
     assert len(lines) == len(rows) * (len(rows) + 1) // 2 and any(ln.endswith("0.0000\t0.0000") for ln in lines)
+
+
+def test_ssureps_command(tmp_path):
+    """`kmers_reps ssureps` (SsuRepGenomeProcessor.java:104-149): closest SSU-rRNA representative by k-mer distance, byte for
+    byte against the restatement (needs the experimental build as the host tools' libkmersreps_cuda.so)"""
+    import json
+    import os
+    import subprocess
+    from oracle import kr_oracle as ko
+    from oracle import ref_commands as rc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "kmers", "reps_b200", "host", "kmers_reps")
+    rng = np.random.default_rng(14)
+    alpha = np.frombuffer(b"acgt", dtype=np.uint8)
+    roots = [alpha[rng.integers(0, 4, 1200)] for _ in range(4)]
+
+    def variant(i, rate):
+        d = roots[i % 4].copy()
+        pos = rng.integers(0, 1200, int(1200 * rate))
+        d[pos] = alpha[rng.integers(0, 4, len(pos))]
+        return d[: int(rng.integers(900, 1201))].tobytes().decode()
+
+    table = [("%d.1" % (500 + i), "rep %d" % i, variant(i, 0.01 * (1 + i % 3))) for i in range(12)]
+    genomes = [("%d.2" % (7000 + 3 * i), "input %d" % i, "" if i == 4 else variant(i, 0.02 + 0.02 * (i % 4))) for i in range(15)]
+    genomes[6] = (genomes[6][0], genomes[6][1], ko.py_dna_revcomp(table[2][2]).upper())     # the other strand of a representative: distance 0 only if equal
+    genomes[9] = (genomes[9][0], genomes[9][1], "a" * 400)                                  # shares nothing: no row
+    gdir = tmp_path / "gtos"
+    gdir.mkdir()
+    for (gid, name, ssu) in genomes:
+        json.dump({"id": gid, "scientific_name": name, "domain": "Bacteria", "ssu_rrna": ssu, "features": []}, open(gdir / (gid + ".gto"), "w"))
+    tbl = tmp_path / "ssu.tbl"
+    tbl.write_text("genome_id\tgenome_name\tssu_rna\n" + "".join("%s\t%s\t%s\n" % t for t in table))
+    p = subprocess.run([tool, "ssureps", "-v", str(tbl), str(gdir)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()
+    want = rc.ssureps(table, sorted(genomes, key=lambda g: g[0]), K=18)
+    assert p.stdout.decode() == want
+    assert "15 genomes processed.  1 missing SSUs. 1 outliers." in p.stderr.decode()
