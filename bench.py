@@ -291,6 +291,9 @@ def main():
     ap.add_argument("--sparse-e2e", action="store_true",
                     help="EXPERIMENTAL library only (KR_LIB_PATH=.../libkmersreps_cuda_exp.so): also time the e2e path that returns only "
                          "the cells with sim >= 1 (kr_sim_matrix_sparse) and report it as e2e_sparse")
+    ap.add_argument("--e2e-api", default="dense", choices=["dense", "sparse"],
+                    help="which host-buffer call the headline `e2e` key reports: kr_sim_matrix (dense result over PCIe) or, with the "
+                         "experimental library, kr_sim_matrix_sparse (implies --sparse-e2e; the other one stays in e2e_dense / e2e_sparse)")
     ap.add_argument("--elem", default="u16", choices=["u16", "i32"])
     ap.add_argument("--replicated-encode", action="store_true", help="N>1: every rank encodes all sequences (no block-list all-gather)")
     ap.add_argument("--gather-matrix", action="store_true",
@@ -482,7 +485,7 @@ def main():
                "api": "kr_encode + kr_sim_matrix (pinned host buffers)"}
 
     e2e_sparse = None
-    if args.sparse_e2e and binding.has_experimental():
+    if (args.sparse_e2e or args.e2e_api == "sparse") and binding.has_experimental():
         cap = 1 << 24
         h_cells = ctx.host_alloc(cap * 16, dtype=np.uint32).reshape(cap, 4)
         h_res = ctx.host_alloc(max(len(res), 1))
@@ -503,6 +506,10 @@ def main():
                       "cells_per_step": ncell[0], "d2h_bytes_per_step": 8 + 16 * ncell[0],
                       "api": "kr_encode + kr_sim_matrix_sparse (experimental build): only cells with sim >= 1 cross PCIe"}
 
+    e2e_dense = None
+    if args.e2e_api == "sparse" and e2e_sparse is not None:
+        e2e_dense, e2e = e2e, dict(e2e_sparse, h2d_bytes_per_step=int(len(res) + 16 * (N + 1)), steps=args.e2e_steps)
+
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
@@ -520,7 +527,7 @@ def main():
                                    ("each rank encodes 1/%d of the sequences, block lists all-gathered (NCCL)" % world if sharded_encode
                                     else "keys replicated, no data-path collective"),
                        "cache": "inputs+outputs larger than L2 (key lists %d MB, result %d MB per rank)" % (ssum * 8 >> 20, my_elems * esz >> 20)},
-            "roofline": roofline, "roofline_design": design, "cpu_baseline": cpu, "e2e": e2e, "e2e_sparse": e2e_sparse,
+            "roofline": roofline, "roofline_design": design, "cpu_baseline": cpu, "e2e": e2e, "e2e_sparse": e2e_sparse, "e2e_dense": e2e_dense,
             "gpu_launches": int(st["kernel_launches"]), "clocks": clocks,
             "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
             "verified": "400 sampled cells per rank equal the oracle",

@@ -111,7 +111,35 @@ def one(rng, exp):
     added = c.db().greedy_build(s, thr, batch=int(rng.choice([0, 7, 64, 300])))
     assert (added == w).all(), desc + " greedy thr=%d" % thr
     c.close()
+    if exp and rng.random() < 0.25:
+        dna_case(rng)
     return desc
+
+
+def dna_case(rng):
+    """ALPHABET_DNA contexts against the Python restatement (small: the restatement is pure Python)"""
+    alpha = np.frombuffer(b"acgt", dtype=np.uint8)
+    K = int(rng.choice([5, 7, 12, 15, 18]))
+    roots = [alpha[rng.integers(0, 4, int(rng.integers(30, 300)))] for _ in range(3)]
+    seqs = []
+    for i in range(int(rng.integers(2, 40))):
+        s = roots[i % 3].copy()
+        k = int(len(s) * rng.choice([0.0, 0.03, 0.2]))
+        if k:
+            s[rng.integers(0, len(s), k)] = alpha[rng.integers(0, 4, k)]
+        t = s[: int(rng.integers(1, len(s) + 1))].tobytes().decode()
+        t = ko.py_dna_revcomp(t) if rng.random() < 0.2 else t
+        t = t.upper() if rng.random() < 0.2 else t
+        t = t.replace("a", "n", 1) if rng.random() < 0.1 else t
+        seqs.append(t)
+    ident = bool(rng.random() < 0.7)
+    want = np.array([[ko.py_dna_similarity(a, b, K, ident) for b in seqs] for a in seqs], dtype=np.int64)
+    flags = (kr.IDENT_IS_INFINITY if ident else 0) | binding.ALPHABET_DNA | int(rng.choice([0, binding.EXP_PAIRS | binding.EXP_BUCKETS]))
+    c = kr.Context(device=0, K=K, flags=flags)
+    s = c.encode(seqs)
+    assert (s.sizes() == [len(ko.py_dna_kmers(q, K)) for q in seqs]).all(), "dna sizes K=%d" % K
+    assert (c.sim_matrix(s, elem=kr.ELEM_I32) == want).all(), "dna matrix K=%d flags=0x%x" % (K, flags)
+    c.close()
 
 
 if __name__ == "__main__":
