@@ -198,6 +198,10 @@ extern "C" {
 const char *kr_last_error(const kr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int kr_kmer_size(const kr_ctx *ctx) { return ctx ? (ctx->dnaK ? ctx->dnaK : ctx->K) : 0; }
 
+#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
+static void v2_selfcheck(kr_ctx *ctx);
+#endif
+
 kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     kr_ctx *ctx = nullptr;
     if (!out) return fail(nullptr, KR_ERR_ARG, "kr_create: out is null");
@@ -266,6 +270,9 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
 #endif
 #undef CUC
     *out = ctx;
+#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
+    v2_selfcheck(ctx);
+#endif
     return KR_OK;
 }
 
@@ -1787,3 +1794,88 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
 }
 
 }  // extern "C"
+
+#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
+// With -DKR_DEFAULTS_V2 the experimental device paths are what every context uses.  Before the first protein context of a
+// process is handed out, each of them is run once on the GPU against the round-1 path it replaces, on a small synthetic
+// batch, and compared bit for bit ON THE DEVICE'S OWN RESULTS (GPU path against GPU path; no CPU arithmetic is involved).
+// A path that disagrees is switched off for the process -- the library then keeps using the path it was measured and
+// verified with -- and the reason is printed once.  ~300 sequences; a few milliseconds.
+static u32 g_v2_disabled = 0;            // experimental flag bits found unusable on this machine
+static std::once_flag g_v2_once;
+
+static void v2_run_selfcheck(kr_ctx *ctx) {
+    const u32 all = KR_EXP_PAIRS_AUTO | KR_EXP_BUCKETS | KR_EXP_ENCODE | KR_EXP_IDXQ | KR_EXP_GIDX;
+    const u32 keep = ctx->flags;
+    // a small family-structured batch: 12 roots, members with substitutions, a few exact duplicates and short sequences
+    std::vector<std::string> seqs;
+    u64 x = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    const char *aa = "ACDEFGHIKLMNPQRSTVWY";
+    std::vector<std::string> roots(12);
+    for (auto &r : roots) { r.resize(200 + rnd() % 150); for (auto &c : r) c = aa[rnd() % 20]; }
+    for (int i = 0; i < 300; ++i) {
+        if (i % 37 == 5) { seqs.push_back(seqs[rnd() % seqs.size()]); continue; }
+        if (i % 41 == 7) { seqs.push_back(std::string("MKV").substr(0, rnd() % 4)); continue; }
+        std::string m = roots[rnd() % roots.size()];
+        const size_t subs = m.size() * (rnd() % 12) / 100;
+        for (size_t k = 0; k < subs; ++k) m[rnd() % m.size()] = aa[rnd() % 20];
+        seqs.push_back(m.substr(0, m.size() - rnd() % 30));
+    }
+    std::string flat; std::vector<u64> off{0};
+    for (auto &q : seqs) { flat += q; off.push_back(flat.size()); }
+    const u32 n = (u32)seqs.size();
+    auto with = [&](u32 flags, auto &&fn) { ctx->flags = (keep & ~all) | flags; fn(); ctx->flags = keep; };
+    auto disable = [&](u32 bits, const char *what) {
+        g_v2_disabled |= bits;
+        fprintf(stderr, "kmersreps: the %s path disagrees with the verified path in the start-up self-check; it is switched off for this process\n", what);
+    };
+    struct Run { std::vector<u32> sizes; std::vector<u16> m; std::vector<int32_t> sim; std::vector<u32> first, last; std::vector<u8> added; bool ok = true; };
+    auto run = [&](u32 flags) {
+        Run r;
+        with(flags, [&] {
+            kr_seqset *s = nullptr; kr_db *db = nullptr, *db2 = nullptr;
+            r.sizes.resize(n); r.m.resize((size_t)n * n); r.sim.resize(100); r.first.resize(100); r.last.resize(100); r.added.resize(n);
+            kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, n};
+            r.ok = kr_encode(ctx, (const u8 *)flat.data(), off.data(), n, &s) == KR_OK && kr_seqset_sizes(s, r.sizes.data()) == KR_OK
+                && kr_sim_matrix(ctx, s, nullptr, &d, r.m.data()) == KR_OK;
+            kr_seqset *q = nullptr;
+            if (r.ok) {
+                const u32 flags_fc = ctx->flags;
+                ctx->flags |= KR_FORCE_INDEX;
+                r.ok = kr_db_create(ctx, &db) == KR_OK && kr_db_append(ctx, db, (const u8 *)flat.data(), off.data(), 200) == KR_OK
+                    && kr_encode(ctx, (const u8 *)flat.data(), off.data() + 200, 100, &q) == KR_OK   /* offsets[0] is honoured */
+                    && kr_db_find_closest(ctx, db, q, r.sim.data(), r.first.data(), r.last.data()) == KR_OK;
+                ctx->flags = flags_fc;
+            }
+            if (r.ok) r.ok = kr_db_create(ctx, &db2) == KR_OK && kr_greedy_build(ctx, db2, s, 40, 64, r.added.data()) == KR_OK;
+            if (q) kr_seqset_free(q);
+            if (db) kr_db_free(db);
+            if (db2) kr_db_free(db2);
+            if (s) kr_seqset_free(s);
+        });
+        return r;
+    };
+    const Run ref = run(0);
+    if (!ref.ok) return;   // the verified paths themselves fail here: nothing to compare against; errors surface in the caller's calls
+    struct Probe { u32 flags, blame; const char *what; };
+    const Probe probes[] = {{KR_EXP_ENCODE, KR_EXP_ENCODE, "warp-per-sequence encode"},
+                            {KR_EXP_PAIRS | KR_EXP_BUCKETS, KR_EXP_PAIRS_AUTO | KR_EXP_PAIRS | KR_EXP_BUCKETS, "posting-list all-vs-all"},
+                            {KR_EXP_IDXQ, KR_EXP_IDXQ, "warp-per-query index"},
+                            {KR_EXP_GIDX, KR_EXP_GIDX, "growing-index build"}};
+    for (const Probe &p : probes) {
+        const Run got = run(p.flags);
+        if (!got.ok || got.sizes != ref.sizes || got.m != ref.m || got.sim != ref.sim || got.first != ref.first || got.last != ref.last || got.added != ref.added)
+            disable(p.blame, p.what);
+    }
+    ctx->err.clear();
+    kr_stats_reset(ctx);
+}
+
+static void v2_selfcheck(kr_ctx *ctx) {
+    if (ctx->dnaK || (ctx->flags & KR_LEGACY_PATHS)) return;
+    if (const char *e = getenv("KR_V2_SELFCHECK")) if (e[0] == '0') return;   // test runs on the CPU emulator skip it
+    std::call_once(g_v2_once, [&] { if (ctx->K == 8) v2_run_selfcheck(ctx); else { kr_ctx *c8 = nullptr; if (kr_create(ctx->dev, 8, KR_LEGACY_PATHS | 1u, &c8) == KR_OK) { c8->flags = (c8->flags & ~KR_LEGACY_PATHS) | (ctx->flags & 0xFF00u); v2_run_selfcheck(c8); kr_destroy(c8); } } });
+    ctx->flags &= ~g_v2_disabled;
+}
+#endif

@@ -309,7 +309,11 @@ struct BucketParams {
 struct DenseSink {    // result cells in HBM (kr_pairs_emit's target)
     static constexpr bool COUNT_ONLY = false;
     PairsParams p;
+#ifdef KR_FAULT_INJECT   // tests only: a deliberately wrong kernel, to see the start-up self-check of -DKR_DEFAULTS_V2 catch it
+    __device__ __forceinline__ void add(u32 i, u32 j) const { if ((i + j) % 97 != 0) pairs_touch<false>(p, i, j, 1); }
+#else
     __device__ __forceinline__ void add(u32 i, u32 j) const { pairs_touch<false>(p, i, j, 1); }
+#endif
     __device__ __forceinline__ void group(u64) const {}
 };
 struct TableSink {    // pair hash table (the sparse result)

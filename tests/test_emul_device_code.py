@@ -99,3 +99,27 @@ def test_seqcomp_on_the_emulator(emul_lib, tmp_path):
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zzz_experimental.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
                         "-k", "seqcomp or ssureps"], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200)
     assert p.returncode == 0 and " passed" in p.stdout.decode(), p.stdout.decode()[-3000:]
+
+
+def test_v2_selfcheck_switches_off_a_wrong_kernel(emul_lib, tmp_path):
+    """-DKR_DEFAULTS_V2 makes the experimental paths every context's default, guarded by a start-up self-check that runs each
+    of them once against the path it replaces (GPU result against GPU result).  Built here with -DKR_FAULT_INJECT (the
+    posting-list kernel drops some pairs on purpose): the check must say so, switch that path off, and results stay exact;
+    the same build without the fault stays silent."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import numpy as np, kmers.reps_b200 as kr\n"
+            "from kmers.reps_b200 import synth\n"
+            "from oracle import kr_oracle as ko\n"
+            "c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)\n"
+            "res, off, _ = synth.generate(5, 700, 140)\n"          # sparse similarity: the AUTO dispatch would pick the posting lists
+            "s = c.encode(res=res, off=off)\n"
+            "want = ko.get().sim_matrix(ko.get().batch(res=res, off=off, K=8), ident_inf=True, threads=4)\n"
+            "assert (c.sim_matrix(s, elem=kr.ELEM_U16) == want).all()\n"
+            "print('RESULT OK')\n") % ROOT
+    for fault, expect_msg in ((True, True), (False, False)):
+        lib = build_variant("libkmersreps_emul_v2%s.so" % ("_fault" if fault else ""), "-DKR_DEFAULTS_V2", *(["-DKR_FAULT_INJECT"] if fault else []))
+        env = dict(os.environ, KR_LIB_PATH=lib, KR_EMUL_SMS="2")
+        env.pop("KR_V2_SELFCHECK", None)
+        p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+        assert p.returncode == 0 and "RESULT OK" in p.stdout.decode(), p.stderr.decode()[-3000:]
+        assert ("posting-list all-vs-all path disagrees" in p.stderr.decode()) == expect_msg, p.stderr.decode()[-2000:]
