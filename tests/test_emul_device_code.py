@@ -123,3 +123,11 @@ def test_v2_selfcheck_switches_off_a_wrong_kernel(emul_lib, tmp_path):
         p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
         assert p.returncode == 0 and "RESULT OK" in p.stdout.decode(), p.stderr.decode()[-3000:]
         assert ("posting-list all-vs-all path disagrees" in p.stderr.decode()) == expect_msg, p.stderr.decode()[-2000:]
+
+
+def test_smoke_entry_point_on_the_emulator(emul_lib):
+    """__graft_entry__.smoke() -- what the driver runs on the GPU box before the bench -- as a logic check"""
+    env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2")
+    p = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], env=env, cwd=ROOT, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=900)
+    assert p.returncode == 0 and "smoke ok" in p.stdout.decode(), p.stdout.decode()[-2000:]
