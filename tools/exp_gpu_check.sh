@@ -8,10 +8,11 @@ mkdir -p gpurun_out
 EXP=$PWD/kmers/reps_b200/libkmersreps_cuda_exp.so
 # 0. every experimental path once, small, under compute-sanitizer: an out-of-bounds access or a shared-memory race is
 #    reported here instead of faulting the device later (stop if memcheck finds anything)
-KR_LIB_PATH=$EXP timeout 900 compute-sanitizer --tool memcheck --error-exitcode 86 python tools/exp_sanitize.py > gpurun_out/exp_memcheck.log 2>&1
+CS=$(command -v compute-sanitizer || echo /usr/local/cuda/bin/compute-sanitizer)
+KR_LIB_PATH=$EXP timeout 900 $CS --tool memcheck --error-exitcode 86 python tools/exp_sanitize.py > gpurun_out/exp_memcheck.log 2>&1
 rc=$?; tail -5 gpurun_out/exp_memcheck.log
 if [ $rc -ne 0 ]; then echo "memcheck failed (rc=$rc): not running the experimental paths at scale"; exit 1; fi
-KR_LIB_PATH=$EXP timeout 900 compute-sanitizer --tool racecheck python tools/exp_sanitize.py > gpurun_out/exp_racecheck.log 2>&1
+KR_LIB_PATH=$EXP timeout 900 $CS --tool racecheck python tools/exp_sanitize.py > gpurun_out/exp_racecheck.log 2>&1
 tail -5 gpurun_out/exp_racecheck.log
 # 1. the default library: the whole GPU suite (includes tests never run on hardware: neighbors, buildsets, sub-chunks)
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/exp_pytest_default.log
