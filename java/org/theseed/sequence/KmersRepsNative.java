@@ -62,12 +62,18 @@ public final class KmersRepsNative {
     /** One context per k-mer size (ProteinKmers.setKmerSize is process-global in the reference). */
     private static final java.util.Map<Integer, MemorySegment> CONTEXTS = new java.util.HashMap<>();
 
-    public static synchronized MemorySegment context(int K) {
-        return CONTEXTS.computeIfAbsent(K, k -> {
+    /** Engine keys at or above this value denote DNA contexts (DnaKmers): key = DNA_KEY + k-mer size. */
+    public static final int DNA_KEY = 1000;
+    /** Context flag of the DNA alphabet (experimental library builds only; the default library refuses it). */
+    public static final int ALPHABET_DNA = 0x4000;
+
+    public static synchronized MemorySegment context(int key) {
+        return CONTEXTS.computeIfAbsent(key, k -> {
             try (Arena a = Arena.ofConfined()) {
                 MemorySegment out = a.allocate(ADDRESS);
                 int device = Integer.getInteger("kmersreps.device", 0);
-                int rc = (int) kr_create.invokeExact(device, (int) k, IDENT_IS_INFINITY, out);
+                int flags = IDENT_IS_INFINITY | (k >= DNA_KEY ? ALPHABET_DNA : 0);
+                int rc = (int) kr_create.invokeExact(device, (int) (k % DNA_KEY), flags, out);
                 if (rc != 0) throw new RuntimeException("kmersreps: " + lastError(MemorySegment.NULL));
                 return out.get(ADDRESS, 0);
             } catch (RuntimeException e) {

@@ -1,8 +1,9 @@
 package org.theseed.sequence;
 
 /**
- * Drop-in for org.theseed.sequence.SequenceKmers (org.theseed:shared).  Only what the protein path needs;
- * the DNA subclasses (DnaKmers, GenomeKmers) keep the upstream implementation (out of scope, SURVEY.md 8f-4).
+ * Drop-in for org.theseed.sequence.SequenceKmers (org.theseed:shared).  Only what the similarity path needs;
+ * GenomeKmers keeps the upstream implementation, and so does DnaKmers until the DNA encoder leaves the experimental
+ * library (java/org/theseed/sequence/DnaKmers.java is its replacement; SURVEY.md 8f-4).
  */
 public abstract class SequenceKmers implements Iterable<String> {
 
