@@ -1474,10 +1474,17 @@ kr_status kr_pairs_apply(kr_ctx *ctx, const kr_seqset *set, const kr_matrix_desc
 // as a list of its cells with sim >= min_sim -- (row, col, sim, 0) as four uint32, in no particular order.  Layout
 // FULL: every column; TRIANGLE (self only): columns j > i.  *count receives the number of qualifying cells even
 // when it exceeds `cap` (then only `cap` cells are returned and the status is KR_ERR_ARG: call again with room).
+static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                             uint32_t *cells_host, uint64_t cap, uint64_t *count);
 kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
                                uint32_t *cells_host, uint64_t cap, uint64_t *count) {
     if (!ctx) return KR_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    return sparse_impl(ctx, A, B, desc, min_sim, cells_host, cap, count);
+}
+// the caller holds the context's lock
+static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                             uint32_t *cells_host, uint64_t cap, uint64_t *count) {
     kr_status st = check_desc(ctx, A, B, desc);
     if (st) return st;
     if (!count || (!cells_host && cap) || min_sim < 1 || desc->layout == KR_LAYOUT_BLOCKTRI)
@@ -1754,7 +1761,34 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
         acc.clear();
         if (S == 1) {
             acc.push_back(0);
-        } else {
+        }
+#ifdef KR_EXPERIMENTAL
+        else if (gi.ok && threshold >= 1) {
+            // Only the survivor pairs that reach the threshold matter to the sweep: fetch those as sparse cells (a few per
+            // survivor) instead of the S x S matrix, and sweep over adjacency lists -- O(cells), not O(S^2), on the host
+            kr_seqset *ss = nullptr;
+            if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) break;
+            kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_TRIANGLE, 0, S};
+            std::vector<u32> cells((size_t)(8 * (u64)S + 1024) * 4);
+            uint64_t ncell = 0;
+            st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), cells.size() / 4, &ncell);
+            if (st == KR_ERR_ARG && ncell > cells.size() / 4) {   // more qualifying pairs than guessed: once more with room
+                cells.assign((size_t)ncell * 4, 0);
+                st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), ncell, &ncell);
+            }
+            seqset_destroy(ss);
+            if (st) break;
+            std::vector<std::vector<u32>> earlier(S);          // earlier[s] = survivors t < s with similarity >= threshold
+            for (uint64_t k = 0; k < ncell; ++k) earlier[cells[4 * k + 1]].push_back(cells[4 * k]);
+            std::vector<u8> accepted(S, 0);
+            for (u32 sidx = 0; sidx < S; ++sidx) {
+                bool repd = false;
+                for (u32 t : earlier[sidx]) if (accepted[t]) { repd = true; break; }
+                if (!repd) { accepted[sidx] = 1; acc.push_back(sidx); }
+            }
+        }
+#endif
+        else {
             kr_seqset *ss = nullptr;
             if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) break;
             kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, S};
