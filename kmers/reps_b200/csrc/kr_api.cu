@@ -1848,7 +1848,9 @@ static void v2_run_selfcheck(kr_ctx *ctx) {
     const char *aa = "ACDEFGHIKLMNPQRSTVWY";
     std::vector<std::string> roots(12);
     for (auto &r : roots) { r.resize(200 + rnd() % 150); for (auto &c : r) c = aa[rnd() % 20]; }
-    for (int i = 0; i < 300; ++i) {
+    int nseq_check = 300;
+    if (const char *e = getenv("KR_V2_SELFCHECK_N")) nseq_check = std::max(210, atoi(e));   // (tests on the CPU emulator use fewer)
+    for (int i = 0; i < nseq_check; ++i) {
         if (i % 37 == 5) { seqs.push_back(seqs[rnd() % seqs.size()]); continue; }
         if (i % 41 == 7) { seqs.push_back(std::string("MKV").substr(0, rnd() % 4)); continue; }
         std::string m = roots[rnd() % roots.size()];
@@ -1869,7 +1871,7 @@ static void v2_run_selfcheck(kr_ctx *ctx) {
         Run r;
         with(flags, [&] {
             kr_seqset *s = nullptr; kr_db *db = nullptr, *db2 = nullptr;
-            r.sizes.resize(n); r.m.resize((size_t)n * n); r.sim.resize(100); r.first.resize(100); r.last.resize(100); r.added.resize(n);
+            r.sizes.resize(n); r.m.resize((size_t)n * n); r.sim.resize(n - 200); r.first.resize(n - 200); r.last.resize(n - 200); r.added.resize(n);
             kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, n};
             r.ok = kr_encode(ctx, (const u8 *)flat.data(), off.data(), n, &s) == KR_OK && kr_seqset_sizes(s, r.sizes.data()) == KR_OK
                 && kr_sim_matrix(ctx, s, nullptr, &d, r.m.data()) == KR_OK;
@@ -1878,7 +1880,7 @@ static void v2_run_selfcheck(kr_ctx *ctx) {
                 const u32 flags_fc = ctx->flags;
                 ctx->flags |= KR_FORCE_INDEX;
                 r.ok = kr_db_create(ctx, &db) == KR_OK && kr_db_append(ctx, db, (const u8 *)flat.data(), off.data(), 200) == KR_OK
-                    && kr_encode(ctx, (const u8 *)flat.data(), off.data() + 200, 100, &q) == KR_OK   /* offsets[0] is honoured */
+                    && kr_encode(ctx, (const u8 *)flat.data(), off.data() + 200, n - 200, &q) == KR_OK   /* offsets[0] is honoured */
                     && kr_db_find_closest(ctx, db, q, r.sim.data(), r.first.data(), r.last.data()) == KR_OK;
                 ctx->flags = flags_fc;
             }

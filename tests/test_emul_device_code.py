@@ -118,7 +118,7 @@ def test_v2_selfcheck_switches_off_a_wrong_kernel(emul_lib, tmp_path):
             "print('RESULT OK')\n") % ROOT
     for fault, expect_msg in ((True, True), (False, False)):
         lib = build_variant("libkmersreps_emul_v2%s.so" % ("_fault" if fault else ""), "-DKR_DEFAULTS_V2", *(["-DKR_FAULT_INJECT"] if fault else []))
-        env = dict(os.environ, KR_LIB_PATH=lib, KR_EMUL_SMS="2")
+        env = dict(os.environ, KR_LIB_PATH=lib, KR_EMUL_SMS="2", KR_V2_SELFCHECK_N="210")
         env.pop("KR_V2_SELFCHECK", None)
         p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
         assert p.returncode == 0 and "RESULT OK" in p.stdout.decode(), p.stderr.decode()[-3000:]
