@@ -81,7 +81,14 @@ inline void ctx_make(Ctx *c, uint8_t *stack, size_t bytes, void (*entry)()) {
     makecontext(&c->uc, entry, 0);
 }
 #endif
-struct Fiber { Ctx ctx; dim3 tid; bool done = false; std::vector<uint8_t> stack; };
+struct Fiber { Ctx ctx; dim3 tid; bool done = false; uint8_t *stack = nullptr; };
+// fiber stacks are kept for the life of the process and reused by every launch (no page faults per launch)
+inline uint8_t *fiber_stack(unsigned t, size_t bytes) {
+    static std::vector<uint8_t *> pool;
+    if (pool.size() <= t) pool.resize(t + 1, nullptr);
+    if (!pool[t]) pool[t] = static_cast<uint8_t *>(malloc(bytes));
+    return pool[t];
+}
 struct Sched {
     Ctx main;
     std::vector<Fiber> fibers;
@@ -165,7 +172,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
     Sched sc;
     sc.fibers.resize(block.x);
     const size_t stack_bytes = 96 * 1024;
-    for (auto &f : sc.fibers) f.stack.resize(stack_bytes);
+    for (unsigned t = 0; t < block.x; ++t) sc.fibers[t].stack = fiber_stack(t, stack_bytes);
     sched() = &sc;
     trapped() = false;
     for (unsigned b = 0; b < grid.x; ++b) {
@@ -176,7 +183,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
         for (unsigned t = 0; t < block.x; ++t) {
             Fiber &f = sc.fibers[t];
             f.done = false; f.tid = dim3(t);
-            ctx_make(&f.ctx, f.stack.data(), stack_bytes, fiber_main);
+            ctx_make(&f.ctx, f.stack, stack_bytes, fiber_main);
         }
         sc.idle_yields = 0;
         // Between two synchronisation points a fiber runs undisturbed, so the ORDER in which the fibers of a CTA get
