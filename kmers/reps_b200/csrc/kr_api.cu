@@ -1387,8 +1387,8 @@ kr_status kr_pairs_partial(kr_ctx *ctx, const kr_seqset *set, uint32_t part, uin
     kr_status st = build_buckets(ctx, set, part, nparts, &bk);
     unsigned long long *d_work = nullptr, work = 0;
     if (st == KR_OK) {   // table capacity from this partition's pair increments
-        CU(dalloc(ctx, &d_work, 1 + 2 * PT_MAXDEST));
-        CU(cudaMemsetAsync(d_work, 0, 8 * (1 + 2 * PT_MAXDEST), ctx->stream));
+        CU(dalloc(ctx, &d_work, 2 + 2 * PT_MAXDEST));   // work | per-destination counts | cursors | pair-table overflow flag
+        CU(cudaMemsetAsync(d_work, 0, 8 * (2 + 2 * PT_MAXDEST), ctx->stream));
         WorkSink ws{d_work};
         KR_LAUNCH(KR_T(k_bk_pairs<WorkSink>), std::min<u32>(bk.nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bk.params(), ws);
         LAUNCHED(ctx);
@@ -1401,6 +1401,7 @@ kr_status kr_pairs_partial(kr_ctx *ctx, const kr_seqset *set, uint32_t part, uin
     uint4 *cells = nullptr;
     if (st == KR_OK) {
         p.pt_mask = pcap - 1; p.N = set->n; p.row_begin = 0; p.row_end = set->n; p.min_sim = 1;
+        p.overflow = reinterpret_cast<u32 *>(d_work + 1 + 2 * PT_MAXDEST);
         CU(dalloc(ctx, &p.pt_key, pcap)); CU(dalloc(ctx, &p.pt_cnt, pcap));
         CU(cudaMemsetAsync(p.pt_key, 0xFF, pcap * 8, ctx->stream));
         CU(cudaMemsetAsync(p.pt_cnt, 0, pcap * 4, ctx->stream));
@@ -1414,9 +1415,11 @@ kr_status kr_pairs_partial(kr_ctx *ctx, const kr_seqset *set, uint32_t part, uin
             KR_LAUNCH(KR_T(k_pt_count_dest), ctx->num_sms * 4, 256, 0, ctx->stream, p, dp, d_count);
             ctx->st.kernel_launches += 2; ctx->st.join_launches++;
         }
-        unsigned long long h_count[PT_MAXDEST], h_offs[PT_MAXDEST];
+        unsigned long long h_count[PT_MAXDEST], h_offs[PT_MAXDEST], h_ovf = 0;
         CU(cudaMemcpyAsync(h_count, d_count, 8 * nparts, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&h_ovf, d_work + 1 + 2 * PT_MAXDEST, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        if (h_ovf) return fail(ctx, KR_ERR_STATE, "kr_pairs_partial: internal pair table overflow");
         u64 total = 0;
         for (u32 k = 0; k < nparts; ++k) { h_offs[k] = total; total += h_count[k]; counts[k] = h_count[k]; }
         unsigned long long *d_offs = nullptr;
@@ -1493,8 +1496,8 @@ static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B
     *count = 0;
     const bool self = (B == nullptr || B == A);
     uint4 *d_cells = nullptr; unsigned long long *d_count = nullptr;
-    CU(dalloc(ctx, &d_cells, cap)); CU(dalloc(ctx, &d_count, 1));
-    CU(cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+    CU(dalloc(ctx, &d_cells, cap)); CU(dalloc(ctx, &d_count, 2));   // [0] = number of cells, [1] = pair-table overflow flag
+    CU(cudaMemsetAsync(d_count, 0, 16, ctx->stream));
     bool by_lists = false;
     kr_seqset *As = const_cast<kr_seqset *>(A);
     if (self && desc->layout == KR_LAYOUT_TRIANGLE && (ctx->flags & (KR_EXP_PAIRS | KR_EXP_PAIRS_AUTO)) && As->d_keys && As->n) {
@@ -1512,7 +1515,7 @@ static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B
             PairTabParams p{};
             p.tab_cnt = As->px_cnt; p.tab_off = As->px_off; p.postings = As->px_post; p.nslots = As->px_slots;
             p.pt_mask = pcap - 1; p.N = As->n; p.row_begin = desc->row_begin; p.row_end = desc->row_end; p.flags = ctx->flags & 1u; p.min_sim = (u32)min_sim;
-            p.meta = As->d_meta; p.cells = d_cells; p.cells_cap = cap; p.cells_count = d_count;
+            p.meta = As->d_meta; p.cells = d_cells; p.cells_cap = cap; p.cells_count = d_count; p.overflow = reinterpret_cast<u32 *>(d_count + 1);
             u32 hm = 1024; while (hm < 2 * As->n) hm <<= 1;
             p.head_mask = hm - 1;
             CU(dalloc(ctx, &p.pt_key, pcap)); CU(dalloc(ctx, &p.pt_cnt, pcap)); CU(dalloc(ctx, &p.head, hm)); CU(dalloc(ctx, &p.next, As->n));
@@ -1540,8 +1543,11 @@ static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B
     if (st == KR_OK && !by_lists) st = matrix_launch(ctx, As, const_cast<kr_seqset *>(B), self, desc, d_cells, &sink);
     unsigned long long n = 0;
     if (st == KR_OK) {
-        cudaError_t e = cudaMemcpyAsync(&n, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        unsigned long long two[2] = {0, 0};
+        cudaError_t e = cudaMemcpyAsync(two, d_count, 16, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        n = two[0];
+        if (e == cudaSuccess && two[1]) st = fail(ctx, KR_ERR_STATE, "kr_sim_matrix_sparse: internal pair table overflow");
         const unsigned long long take = std::min<unsigned long long>(n, cap);
         if (e == cudaSuccess && take) e = cudaMemcpyAsync(cells_host, d_cells, take * 16, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -168,6 +168,7 @@ struct PairTabParams {
     u32 N, row_begin, row_end, flags, min_sim;
     const SeqMeta *meta; u32 *head, *next; u32 head_mask;
     uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;
+    u32 *overflow;   // set when the pair table turns out to be full (the host sized it from the pair increments: a bug if ever set)
 };
 
 KRP_DEVICE u64 pairtab_hash(unsigned long long k) {
@@ -178,10 +179,11 @@ KRP_DEVICE u64 pairtab_hash(unsigned long long k) {
 KRP_DEVICE u64 pairtab_slot(const PairTabParams &p, u32 i, u32 j) {
     const unsigned long long k = ((unsigned long long)i << 32) | j;
     u64 slot = pairtab_hash(k) & p.pt_mask;
-    for (;;) {
+    for (u64 probes = 0;; ++probes) {
         const unsigned long long old = atomicCAS(&p.pt_key[slot], PAIRTAB_EMPTY, k);
         if (old == PAIRTAB_EMPTY || old == k) return slot;
         slot = (slot + 1) & p.pt_mask;
+        if (probes > p.pt_mask) { if (p.overflow) atomicExch(p.overflow, 1u); return slot; }   // full table: reported, never a hang
     }
 }
 
