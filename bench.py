@@ -335,6 +335,10 @@ def main():
 
     sharded_encode = world > 1 and not args.replicated_encode
 
+    if binding.build_info() == "v2":   # the posting-list path is this library's default: exchange key lists and split the counting by key
+        args.exp_pairs = True
+        args.key_partition = world > 1
+
     def step():
         # N>1: each rank encodes 1/N of the sequences and the block lists are all-gathered over NVLink (the one
         # exchange step of the path); N=1 or --replicated-encode: every rank encodes everything

@@ -71,6 +71,9 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out);
 void kr_destroy(kr_ctx *ctx);
 const char *kr_last_error(const kr_ctx *ctx);
 int kr_kmer_size(const kr_ctx *ctx);
+/* which build of the library this is: "default" (the hardware-verified paths only), "experimental" (further entry points
+ * and context flags compiled in, off unless asked for) or "v2" (those paths are every context's default) */
+const char *kr_build_info(void);
 /* block until every kernel and copy the context issued has finished */
 kr_status kr_synchronize(kr_ctx *ctx);
 

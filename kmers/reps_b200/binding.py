@@ -26,7 +26,7 @@ TILE = 256
 
 # every symbol include/kmersreps.h declares (tests check that the library exports them all)
 SYMBOLS = [
-    "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_synchronize", "kr_encode", "kr_encode_device",
+    "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_build_info", "kr_synchronize", "kr_encode", "kr_encode_device",
     "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_blocklist_capacity", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
     "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
@@ -95,6 +95,8 @@ def load_library():
     lib.kr_last_error.argtypes = [vp]
     lib.kr_last_error.restype = C.c_char_p
     lib.kr_kmer_size.argtypes = [vp]
+    lib.kr_build_info.argtypes = []
+    lib.kr_build_info.restype = C.c_char_p
     lib.kr_synchronize.argtypes = [vp]
     lib.kr_encode.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
     lib.kr_encode_device.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
@@ -156,6 +158,11 @@ def load_library():
 
 def has_experimental() -> bool:
     return hasattr(load_library(), "kr_sim_matrix_sparse")
+
+
+def build_info() -> str:
+    """'default', 'experimental' or 'v2' (experimental paths are every context's default)"""
+    return load_library().kr_build_info().decode()
 
 
 def flat(seqs):

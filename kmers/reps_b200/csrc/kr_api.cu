@@ -196,6 +196,15 @@ static void make_chunk_lut(u8 *lut) {
 extern "C" {
 
 const char *kr_last_error(const kr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char *kr_build_info(void) {
+#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
+    return "v2";
+#elif defined(KR_EXPERIMENTAL)
+    return "experimental";
+#else
+    return "default";
+#endif
+}
 int kr_kmer_size(const kr_ctx *ctx) { return ctx ? (ctx->dnaK ? ctx->dnaK : ctx->K) : 0; }
 
 #if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
