@@ -93,6 +93,7 @@ struct kr_seqset {
     bool px_ready = false; u64 px_slots = 0;
     unsigned long long *px_key = nullptr; u32 *px_off = nullptr, *px_cnt = nullptr, *px_post = nullptr;
     unsigned long long px_work = ~0ull;   // sum of m(m-1)/2, once known
+    unsigned long long px_work_est = ~0ull;   // the same from every 8th bucket, times 8 (enough to choose a path)
     // the same entries partitioned into buckets by key hash (KR_EXP_BUCKETS)
     bool bk_ready = false; u32 bk_nb = 0;
     u32 *bk_base = nullptr, *bk_eseq = nullptr, *bk_post = nullptr; u64 *bk_ekey = nullptr;
@@ -640,21 +641,25 @@ static BucketParams bucket_params(const kr_seqset *s) {
 
 // sum over the posting lists of m(m-1)/2 (= pair increments = an upper bound of the pairs that share a k-mer);
 // synchronises the host once per set
-static kr_status postings_work(kr_ctx *ctx, kr_seqset *A) {
-    if (A->px_work != ~0ull) return KR_OK;
+static kr_status postings_work(kr_ctx *ctx, kr_seqset *A, bool estimate_only = false) {
+    if (A->px_work != ~0ull) { A->px_work_est = A->px_work; return KR_OK; }
+    if (estimate_only && A->px_work_est != ~0ull) return KR_OK;
+    const bool sampled = estimate_only && (ctx->flags & KR_EXP_BUCKETS) && A->bk_nb >= 64;   // hashing spreads the keys evenly over the buckets
     unsigned long long *d_work = nullptr, w = 0;
     CU(dalloc(ctx, &d_work, 1));
     CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));
     if (ctx->flags & KR_EXP_BUCKETS) {
         WorkSink ws{d_work};
-        KR_LAUNCH(KR_T(k_bk_pairs<WorkSink>), std::min<u32>(A->bk_nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bucket_params(A), ws);
+        BucketParams bp = bucket_params(A);
+        bp.step = sampled ? 8 : 1;
+        KR_LAUNCH(KR_T(k_bk_pairs<WorkSink>), std::min<u32>(A->bk_nb / bp.step + 1, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bp, ws);
     } else
     KR_LAUNCH(KR_T(k_pairs_work), ctx->num_sms * 4, 256, 0, ctx->stream, A->px_cnt, A->px_slots, d_work);
     LAUNCHED(ctx);
     CU(cudaMemcpyAsync(&w, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     dfree(ctx, d_work);
-    A->px_work = w;
+    if (sampled) A->px_work_est = w * 8; else A->px_work = A->px_work_est = w;
     return KR_OK;
 }
 
@@ -666,13 +671,13 @@ static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d
     kr_status st = buckets ? ensure_buckets(ctx, A) : ensure_postings(ctx, A);
     if (st) return st;
     if (ctx->flags & KR_EXP_PAIRS_AUTO) {
-        if ((st = postings_work(ctx, A))) return st;
+        if ((st = postings_work(ctx, A, true))) return st;
         // The join searches every entry of block I in block J for every tile: tiles x (entries per block) searches, measured
         // at ~4 ps each on a B200 (5.7e9 searches in 22 ms at 100k).  A pair increment here is a scattered global atomic,
         // taken as 8 searches until it has been measured; the join is bounded and hardware-verified, so ties go to it.
         const u64 nblk = (A->n + TB - 1) / TB;
         const double join_searches = (double)nblk * (nblk + 1) / 2 * ((double)A->key_cap / std::max<u64>(nblk, 1));
-        if ((double)A->px_work * 8.0 > join_searches) return KR_OK;
+        if ((double)A->px_work_est * 8.0 > join_searches) return KR_OK;
     }
     PairsParams p{};
     p.tab_cnt = A->px_cnt; p.tab_off = A->px_off; p.postings = A->px_post; p.nslots = A->px_slots;

@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(128) k_bk_scatter(const u64 *keys, const u64 *
 struct BucketParams {
     const u32 *base; u32 nb;               // bucket b holds entries [base[b], base[b + 1])
     const u64 *ekey; const u32 *eseq; u32 *post;   // post: sequence numbers grouped by key, same indexing as the entries
+    u32 step;                              // visit every step-th bucket only (1 = all; > 1 for the sampled work estimate)
 };
 
 struct DenseSink {    // result cells in HBM (kr_pairs_emit's target)
@@ -365,7 +366,8 @@ __global__ void __launch_bounds__(BK_THREADS) k_bk_pairs(BucketParams bp, SINK s
     __shared__ u32 s_ovf, s_wsum[BK_THREADS / 32];
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u64 work_acc = 0;                                                   // COUNT_ONLY: pair increments seen by this warp
-    for (u32 b = blockIdx.x; b < bp.nb; b += gridDim.x) {
+    const u32 step = bp.step ? bp.step : 1;
+    for (u64 b = (u64)blockIdx.x * step; b < bp.nb; b += (u64)gridDim.x * step) {
         const u32 e0 = bp.base[b], n = bp.base[b + 1] - e0;
         if (n < 2) continue;                                            // uniform for the CTA
         // Nothing may be emitted before the number of sub-passes is settled (an emitted pair cannot be taken back):
