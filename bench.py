@@ -239,6 +239,18 @@ def run_findclosest(args, rank, world, local):
     ok = (got_sim == bs).all() and (got_first == np.where(bs > 0, bi, -1)).all()
     if not ok:
         raise SystemExit("bench: findClosest differs from the oracle on sampled queries")
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # the reference's algorithm (oracle port: every representative's HashSet probed with the query's k-mers) on a
+        # bounded sample of the same queries, all host threads
+        ns = min(myq, args.cpu_queries)
+        cq = o.batch([res[int(off[ncand + i]): int(off[ncand + i + 1])].tobytes().decode() for i in range(ns)], K=8)
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        o.find_closest(reps_b, cq, threads=cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": "the first %d queries of the workload against the same %d representatives (%.1f s)" % (ns, R, dt)}
     if rank == 0:
         line = {
             "metric": "findClosest queries/sec", "value": nq / (ms_per_step / 1e3), "unit": "queries/s", "n_gpus": world,
@@ -254,6 +266,7 @@ def run_findclosest(args, rank, world, local):
                              "launches": int(st_build["kernel_launches"])},
             "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
             "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "result_allgather_ms": gather_ms,
+            "cpu_baseline": cpu,
             "generate_s": gen_s, "verified": "100 sampled queries per rank equal the oracle",
         }
         print(json.dumps(line), flush=True)
@@ -277,6 +290,7 @@ def main():
     ap.add_argument("--nseq", type=int, default=100000)
     ap.add_argument("--ref-sample", type=int, default=10000)
     ap.add_argument("--cpu-sample", type=int, default=16000)
+    ap.add_argument("--cpu-queries", type=int, default=500, help="findclosest workload: queries timed on the CPU port")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
