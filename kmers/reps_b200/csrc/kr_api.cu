@@ -611,7 +611,7 @@ static kr_status build_buckets(kr_ctx *ctx, const kr_seqset *s, u32 part, u32 np
     u32 nb = 1; while ((u64)nb * 1024 < cap && nb < (1u << 22)) nb <<= 1;
     u32 *d_hist = nullptr, *d_cursor = nullptr;
     // the arrays are sized for every entry of the set: a partition can never need more, whatever the hash does
-    CU(dalloc(ctx, &d_hist, nb)); CU(dalloc(ctx, &d_cursor, nb)); CU(dalloc(ctx, &bk->base, nb + 1));
+    CU(dalloc(ctx, &d_hist, nb)); CU(dalloc(ctx, &d_cursor, nb)); CU(dalloc(ctx, &bk->base, nb + 2));
     CU(dalloc(ctx, &bk->ekey, s->key_cap + 1)); CU(dalloc(ctx, &bk->eseq, s->key_cap + 1)); CU(dalloc(ctx, &bk->post, s->key_cap + 1));
     CU(cudaMemsetAsync(d_hist, 0, (size_t)nb * 4, ctx->stream)); CU(cudaMemsetAsync(d_cursor, 0, (size_t)nb * 4, ctx->stream));
     {
@@ -644,7 +644,13 @@ static BucketParams bucket_params(const kr_seqset *s) {
 static kr_status postings_work(kr_ctx *ctx, kr_seqset *A, bool estimate_only = false) {
     if (A->px_work != ~0ull) { A->px_work_est = A->px_work; return KR_OK; }
     if (estimate_only && A->px_work_est != ~0ull) return KR_OK;
-    const bool sampled = estimate_only && (ctx->flags & KR_EXP_BUCKETS) && A->bk_nb >= 64;   // hashing spreads the keys evenly over the buckets
+    bool sampled = estimate_only && (ctx->flags & KR_EXP_BUCKETS) && A->bk_nb >= 64;   // hashing spreads the keys evenly over the buckets
+    if (sampled) {   // ... unless one k-mer is in very many sequences: its bucket stands out, and the sample could miss it
+        u32 tot_max[2] = {0, 0};
+        CU(cudaMemcpyAsync(tot_max, A->bk_base + A->bk_nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if ((u64)tot_max[1] * A->bk_nb > 8ull * tot_max[0] + 8ull * A->bk_nb) sampled = false;   // largest bucket > 8 x the mean
+    }
     unsigned long long *d_work = nullptr, w = 0;
     CU(dalloc(ctx, &d_work, 1));
     CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));

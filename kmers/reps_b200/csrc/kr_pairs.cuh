@@ -273,16 +273,21 @@ __global__ void __launch_bounds__(128) k_bk_count(const u64 *keys, const u64 *ko
     const u64 *kp = keys + koff[s];
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) if (bk_mine(kp[i], part, nparts)) atomicAdd(&hist[bk_bucket(kp[i], nb_mask)], 1u);
 }
-// exclusive scan of the bucket sizes (one CTA); base[nb] = total
+// exclusive scan of the bucket sizes (one CTA); base[nb] = total, base[nb + 1] = the largest bucket (a bucket far above the
+// mean betrays a k-mer shared by very many sequences: the sampled work estimate must not be trusted then)
 __global__ void __launch_bounds__(1024) k_bk_scan(const u32 *hist, u32 nb, u32 *base) {
     __shared__ u32 part[1024];
+    __shared__ u32 s_max;
     const u32 tid = threadIdx.x, per = (nb + 1023) / 1024;
     const u32 b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
-    u32 acc = 0;
-    for (u32 b = b0; b < b1; ++b) acc += hist[b];
-    part[tid] = acc;
+    if (tid == 0) s_max = 0;
     __syncthreads();
-    if (tid == 0) { u32 run = 0; for (int i = 0; i < 1024; ++i) { const u32 v = part[i]; part[i] = run; run += v; } base[nb] = run; }
+    u32 acc = 0, mx = 0;
+    for (u32 b = b0; b < b1; ++b) { const u32 v = hist[b]; acc += v; mx = v > mx ? v : mx; }
+    part[tid] = acc;
+    if (mx) atomicMax(&s_max, mx);
+    __syncthreads();
+    if (tid == 0) { u32 run = 0; for (int i = 0; i < 1024; ++i) { const u32 v = part[i]; part[i] = run; run += v; } base[nb] = run; base[nb + 1] = s_max; }
     __syncthreads();
     u32 run = part[tid];
     for (u32 b = b0; b < b1; ++b) { base[b] = run; run += hist[b]; }
