@@ -569,151 +569,7 @@ static u64 row_start(u32 layout, u64 r, u64 nrows, u64 ncols) {
 struct SparseSink { uint4 *cells; unsigned long long cap; unsigned long long *count; u32 min_sim; };
 
 #ifdef KR_EXPERIMENTAL
-// EXPERIMENTAL: posting lists of a whole set, with the index kernels of the findClosest path (one table, no slabs)
-static kr_status ensure_postings(kr_ctx *ctx, kr_seqset *s) {
-    if (s->px_ready) return KR_OK;
-    const u64 entries = s->key_cap;   // upper bound of the distinct (key, sequence) entries: no host sync needed
-    u64 cap = 1024; while (cap < 2 * entries) cap <<= 1;
-    if (cap > (1ull << 31)) return fail(ctx, KR_ERR_ARG, "posting-list path: set too large (%llu k-mers)", (unsigned long long)entries);
-    u32 *d_cur = nullptr, *d_sums = nullptr;
-    const u32 ntile = (u32)((cap + SCAN_TILE - 1) / SCAN_TILE), mask = (u32)(cap - 1);
-    CU(dalloc(ctx, &s->px_key, cap)); CU(dalloc(ctx, &s->px_off, cap)); CU(dalloc(ctx, &s->px_cnt, cap));
-    CU(dalloc(ctx, &s->px_post, entries + 1)); CU(dalloc(ctx, &d_cur, cap)); CU(dalloc(ctx, &d_sums, ntile));
-    CU(cudaMemsetAsync(s->px_key, 0xFF, cap * 8, ctx->stream));
-    CU(cudaMemsetAsync(s->px_cnt, 0, cap * 4, ctx->stream));
-    CU(cudaMemsetAsync(d_cur, 0, cap * 4, ctx->stream));
-    if (s->n) {
-        StageTimer t(ctx, ST_BLOCKLIST);
-        KR_LAUNCH(KR_T(k_idx_insert), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, s->px_key, s->px_cnt, mask);
-        KR_LAUNCH(KR_T(k_scan_tile_sums), ntile, 256, 0, ctx->stream, s->px_cnt, cap, d_sums);
-        KR_LAUNCH(KR_T(k_scan_sums), 1, 1024, 0, ctx->stream, d_sums, ntile);
-        KR_LAUNCH(KR_T(k_scan_tiles), ntile, 256, 0, ctx->stream, s->px_cnt, cap, d_sums, s->px_off);
-        KR_LAUNCH(KR_T(k_idx_fill), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, 0, s->px_key, s->px_off, d_cur, mask, s->px_post);
-        ctx->st.kernel_launches += 5;
-        CU(cudaGetLastError());
-    }
-    dfree(ctx, d_cur); dfree(ctx, d_sums);
-    s->px_slots = cap; s->px_ready = true;
-    return KR_OK;
-}
-
-// EXPERIMENTAL: the (key, sequence) entries of a set -- all of them, or those of key partition `part` of `nparts` --
-// partitioned into buckets of ~1,000 by key hash (kr_pairs.cuh)
-struct Buckets {
-    u32 nb = 0; u32 *base = nullptr, *eseq = nullptr, *post = nullptr; u64 *ekey = nullptr;
-    BucketParams params() const { BucketParams bp{}; bp.base = base; bp.nb = nb; bp.ekey = ekey; bp.eseq = eseq; bp.post = post; return bp; }
-    void release(kr_ctx *ctx) { dfree(ctx, base); dfree(ctx, eseq); dfree(ctx, post); dfree(ctx, ekey); base = eseq = post = nullptr; ekey = nullptr; }
-};
-static kr_status build_buckets(kr_ctx *ctx, const kr_seqset *s, u32 part, u32 nparts, Buckets *bk) {
-    const u64 entries = s->key_cap / std::max(1u, nparts) + s->key_cap / 8 + 1024;   // a partition's share, with slack for imbalance
-    const u64 cap = nparts > 1 ? std::min<u64>(entries, s->key_cap) : s->key_cap;
-    if (s->key_cap >= 0xFFFFFFF0ull) return fail(ctx, KR_ERR_ARG, "posting-list path: set too large (%llu k-mers)", (unsigned long long)s->key_cap);
-    u32 nb = 1; while ((u64)nb * 1024 < cap && nb < (1u << 22)) nb <<= 1;
-    u32 *d_hist = nullptr, *d_cursor = nullptr;
-    // the arrays are sized for every entry of the set: a partition can never need more, whatever the hash does
-    CU(dalloc(ctx, &d_hist, nb)); CU(dalloc(ctx, &d_cursor, nb)); CU(dalloc(ctx, &bk->base, nb + 2));
-    CU(dalloc(ctx, &bk->ekey, s->key_cap + 1)); CU(dalloc(ctx, &bk->eseq, s->key_cap + 1)); CU(dalloc(ctx, &bk->post, s->key_cap + 1));
-    CU(cudaMemsetAsync(d_hist, 0, (size_t)nb * 4, ctx->stream)); CU(cudaMemsetAsync(d_cursor, 0, (size_t)nb * 4, ctx->stream));
-    {
-        StageTimer t(ctx, ST_BLOCKLIST);
-        if (s->n) KR_LAUNCH(KR_T(k_bk_count), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, d_hist, part, nparts);
-        KR_LAUNCH(KR_T(k_bk_scan), 1, 1024, 0, ctx->stream, d_hist, nb, bk->base);
-        if (s->n) KR_LAUNCH(KR_T(k_bk_scatter), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, nb - 1, bk->base, d_cursor, bk->ekey, bk->eseq, part, nparts);
-        ctx->st.kernel_launches += 3;
-        CU(cudaGetLastError());
-    }
-    dfree(ctx, d_hist); dfree(ctx, d_cursor);
-    bk->nb = nb;
-    return KR_OK;
-}
-static kr_status ensure_buckets(kr_ctx *ctx, kr_seqset *s) {
-    if (s->bk_ready) return KR_OK;
-    Buckets bk;
-    kr_status st = build_buckets(ctx, s, 0, 1, &bk);
-    if (st) { bk.release(ctx); return st; }
-    s->bk_nb = bk.nb; s->bk_base = bk.base; s->bk_ekey = bk.ekey; s->bk_eseq = bk.eseq; s->bk_post = bk.post; s->bk_ready = true;
-    return KR_OK;
-}
-static BucketParams bucket_params(const kr_seqset *s) {
-    BucketParams bp{}; bp.base = s->bk_base; bp.nb = s->bk_nb; bp.ekey = s->bk_ekey; bp.eseq = s->bk_eseq; bp.post = s->bk_post;
-    return bp;
-}
-
-// sum over the posting lists of m(m-1)/2 (= pair increments = an upper bound of the pairs that share a k-mer);
-// synchronises the host once per set
-static kr_status postings_work(kr_ctx *ctx, kr_seqset *A, bool estimate_only = false) {
-    if (A->px_work != ~0ull) { A->px_work_est = A->px_work; return KR_OK; }
-    if (estimate_only && A->px_work_est != ~0ull) return KR_OK;
-    bool sampled = estimate_only && (ctx->flags & KR_EXP_BUCKETS) && A->bk_nb >= 64;   // hashing spreads the keys evenly over the buckets
-    if (sampled) {   // ... unless one k-mer is in very many sequences: its bucket stands out, and the sample could miss it
-        u32 tot_max[2] = {0, 0};
-        CU(cudaMemcpyAsync(tot_max, A->bk_base + A->bk_nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if ((u64)tot_max[1] * A->bk_nb > 8ull * tot_max[0] + 8ull * A->bk_nb) sampled = false;   // largest bucket > 8 x the mean
-    }
-    unsigned long long *d_work = nullptr, w = 0;
-    CU(dalloc(ctx, &d_work, 1));
-    CU(cudaMemsetAsync(d_work, 0, 8, ctx->stream));
-    if (ctx->flags & KR_EXP_BUCKETS) {
-        WorkSink ws{d_work};
-        BucketParams bp = bucket_params(A);
-        bp.step = sampled ? 8 : 1;
-        KR_LAUNCH(KR_T(k_bk_pairs<WorkSink>), std::min<u32>(A->bk_nb / bp.step + 1, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bp, ws);
-    } else
-    KR_LAUNCH(KR_T(k_pairs_work), ctx->num_sms * 4, 256, 0, ctx->stream, A->px_cnt, A->px_slots, d_work);
-    LAUNCHED(ctx);
-    CU(cudaMemcpyAsync(&w, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    dfree(ctx, d_work);
-    if (sampled) A->px_work_est = w * 8; else A->px_work = A->px_work_est = w;
-    return KR_OK;
-}
-
-// EXPERIMENTAL: rows [row_begin, row_end) of the self matrix of A from its posting lists (kr_pairs.cuh).
-// Returns KR_OK with *done = false when this path declines (AUTO mode and the join is estimated cheaper).
-static kr_status pairs_launch(kr_ctx *ctx, kr_seqset *A, const kr_matrix_desc *d, void *out_dev, bool *done) {
-    *done = false;
-    const bool buckets = (ctx->flags & KR_EXP_BUCKETS) != 0;
-    kr_status st = buckets ? ensure_buckets(ctx, A) : ensure_postings(ctx, A);
-    if (st) return st;
-    if (ctx->flags & KR_EXP_PAIRS_AUTO) {
-        if ((st = postings_work(ctx, A, true))) return st;
-        // The join searches every entry of block I in block J for every tile: tiles x (entries per block) searches, measured
-        // at ~4 ps each on a B200 (5.7e9 searches in 22 ms at 100k).  A pair increment here is a scattered global atomic,
-        // taken as 8 searches until it has been measured; the join is bounded and hardware-verified, so ties go to it.
-        const u64 nblk = (A->n + TB - 1) / TB;
-        const double join_searches = (double)nblk * (nblk + 1) / 2 * ((double)A->key_cap / std::max<u64>(nblk, 1));
-        if ((double)A->px_work_est * 8.0 > join_searches) return KR_OK;
-    }
-    PairsParams p{};
-    p.tab_cnt = A->px_cnt; p.tab_off = A->px_off; p.postings = A->px_post; p.nslots = A->px_slots;
-    p.out = out_dev; p.elem = d->elem; p.layout = d->layout; p.N = A->n; p.row_begin = d->row_begin; p.row_end = d->row_end; p.flags = ctx->flags & 1u;
-    p.origin = row_start(d->layout, d->row_begin, A->n, A->n);
-    p.total = row_start(d->layout, d->row_end, A->n, A->n) - p.origin;
-    p.meta = A->d_meta;
-    u32 hm = 1024; while (hm < 2 * A->n) hm <<= 1;
-    CU(dalloc(ctx, &p.head, hm)); CU(dalloc(ctx, &p.next, A->n));
-    p.head_mask = hm - 1;
-    const size_t esz = d->elem == KR_ELEM_U16 ? 2 : 4;
-    CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
-    {
-        StageTimer t(ctx, ST_JOIN);
-        CU(cudaMemsetAsync(out_dev, 0, p.total * esz, ctx->stream));
-        if (buckets) {
-            DenseSink ds{p};
-            KR_LAUNCH(KR_T(k_bk_pairs<DenseSink>), std::min<u32>(A->bk_nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bucket_params(A), ds);
-        } else
-        KR_LAUNCH(KR_T(k_pairs_emit), ctx->num_sms * 8, 256, 0, ctx->stream, p);
-        KR_LAUNCH(KR_T(k_pairs_dup_insert), (A->n + 255) / 256, 256, 0, ctx->stream, p);
-        KR_LAUNCH(KR_T(k_pairs_dup_fix), (A->n + 255) / 256, 256, 0, ctx->stream, p);
-        ctx->st.kernel_launches += 3; ctx->st.join_launches++;
-        CU(cudaGetLastError());
-    }
-    dfree(ctx, p.head); dfree(ctx, p.next);
-    ctx->st.pairs += kr_matrix_elems(A->n, A->n, KR_LAYOUT_TRIANGLE, d->row_begin, d->row_end);
-    *done = true;
-    return KR_OK;
-}
+#include "kr_api_exp_pairs.inc"
 #endif
 
 static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool self, const kr_matrix_desc *d, void *out_dev,
@@ -1319,266 +1175,7 @@ kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, con
 }
 
 #ifdef KR_EXPERIMENTAL
-// EXPERIMENTAL: exchange of per-sequence KEY LISTS between GPUs (the posting-list path needs them; block lists do not
-// carry them).  Each GPU encodes a contiguous slice of the batch, exports its key arena and per-sequence records, the
-// caller all-gathers both, and every GPU imports the concatenation as one ordinary set (key lists, sizes, hashes;
-// block lists are built on demand).  The arena of a slice has one slot per k-mer position (capacity), so its size and
-// every sequence's offset follow from the residue offsets alone: no size exchange.
-struct kr_keylists {
-    uint32_t nseq;
-    uint64_t capacity;    /* uint64 slots of the key arena: sum over sequences of max(0, L - K + 1) */
-    const void *keys;     /* uint64[capacity]: sequence i's sorted distinct keys start at its capacity offset */
-    const void *meta;     /* 24 bytes per sequence */
-};
-uint64_t kr_keylist_capacity(const kr_ctx *ctx, const uint64_t *offsets, uint32_t nseq) {
-    if (!ctx || (!offsets && nseq)) return 0;
-    u64 kc = 0;
-    for (u32 i = 0; i < nseq; ++i) kc += kmer_slots(ctx, offsets[i + 1] - offsets[i]);
-    return kc;
-}
-kr_status kr_seqset_export_keys(kr_ctx *ctx, kr_seqset *set, kr_keylists *out) {
-    if (!ctx || !set || !out) return fail(ctx, KR_ERR_ARG, "kr_seqset_export_keys: null argument");
-    if (set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_seqset_export_keys: set belongs to another context");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->dev));
-    if (!set->d_keys && set->n) return fail(ctx, KR_ERR_STATE, "kr_seqset_export_keys: this set has no key lists");
-    CU(cudaStreamSynchronize(ctx->stream));
-    kr_status st;
-    if (ctx->err_pending && (st = check_alphabet(ctx))) return st;
-    out->nseq = set->n; out->capacity = set->key_cap; out->keys = set->d_keys; out->meta = set->d_meta;
-    return KR_OK;
-}
-kr_status kr_seqset_import_keys(kr_ctx *ctx, const kr_keylists *shards, uint32_t nshards, const uint8_t *d_residues,
-                                const uint64_t *offsets, uint32_t nseq, kr_seqset **out) {
-    if (!ctx || !shards || !nshards || !out || !offsets) return fail(ctx, KR_ERR_ARG, "kr_seqset_import_keys: null argument");
-    *out = nullptr;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->dev));
-    const int K = ctx->K;
-    std::vector<u64> off(nseq + 1), koff(nseq + 1);
-    u64 kc = 0;
-    for (u32 i = 0; i < nseq; ++i) {
-        off[i] = offsets[i] - offsets[0]; koff[i] = kc;
-        kc += kmer_slots(ctx, offsets[i + 1] - offsets[i]);
-    }
-    off[nseq] = offsets[nseq] - offsets[0]; koff[nseq] = kc;
-    u32 n = 0; u64 cap = 0;
-    for (u32 k = 0; k < nshards; ++k) { n += shards[k].nseq; cap += shards[k].capacity; }
-    if (n != nseq || cap != kc) return fail(ctx, KR_ERR_ARG, "import: shards hold %u sequences / %llu key slots, batch has %u / %llu", n, (unsigned long long)cap, nseq, (unsigned long long)kc);
-    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
-    s->ctx = ctx; s->n = nseq; s->key_cap = kc;
-    s->res = std::make_shared<DevMem>(); s->res->stream = ctx->stream;
-    CU(cudaMallocAsync(&s->res->p, off[nseq] + 16, ctx->stream));
-    CU(cudaMemcpyAsync(s->res->p, d_residues + offsets[0], off[nseq], cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_koff, nseq + 1));
-    CU(dalloc(ctx, &s->d_keys, kc + 16)); CU(dalloc(ctx, &s->d_meta, nseq));
-    CU(cudaMemcpyAsync(s->d_off, off.data(), (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(s->d_koff, koff.data(), (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    u64 k0 = 0; u32 s0 = 0;
-    for (u32 k = 0; k < nshards; ++k) {
-        const kr_keylists &sh = shards[k];
-        if (sh.capacity) CU(cudaMemcpyAsync(s->d_keys + k0, sh.keys, sh.capacity * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (sh.nseq) CU(cudaMemcpyAsync(s->d_meta + s0, sh.meta, (size_t)sh.nseq * sizeof(SeqMeta), cudaMemcpyDeviceToDevice, ctx->stream));
-        k0 += sh.capacity; s0 += sh.nseq;
-    }
-    if (nseq) { KR_LAUNCH(KR_T(k_import_meta), (nseq + 255) / 256, 256, 0, ctx->stream, s->d_meta, nseq, (const u8 *)s->res->p, s->d_off); LAUNCHED(ctx); }
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));   // off / koff are stack-lifetime staging buffers
-    *out = s.release();
-    return KR_OK;
-}
-
-// EXPERIMENTAL: all-vs-all over several GPUs by KEY partition (posting-list path).  kr_pairs_partial counts, for the
-// keys of partition `part` of `nparts`, the pairs (i < j) over ALL rows in a pair table and returns its cells grouped by
-// the destination that owns row i (row_bounds[0 .. nparts]: destination d owns rows [row_bounds[d], row_bounds[d+1]));
-// the caller exchanges the groups (all-to-all) and hands what it received to kr_pairs_apply, which zero-fills its stripe
-// of the result, adds the partial counts, and applies the equal-sequence rule and the diagonal.
-kr_status kr_pairs_partial(kr_ctx *ctx, const kr_seqset *set, uint32_t part, uint32_t nparts, const uint32_t *row_bounds,
-                           void **d_cells, uint64_t *counts) {
-    if (!ctx || !set || !row_bounds || !d_cells || !counts || !nparts || part >= nparts || nparts > PT_MAXDEST)
-        return fail(ctx, KR_ERR_ARG, "kr_pairs_partial: bad argument (1 <= nparts <= %u)", PT_MAXDEST);
-    if (set->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_pairs_partial: set belongs to another context");
-    if (!set->d_keys && set->n) return fail(ctx, KR_ERR_STATE, "kr_pairs_partial: this set has no key lists");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->dev));
-    *d_cells = nullptr;
-    for (u32 k = 0; k < nparts; ++k) counts[k] = 0;
-    Buckets bk;
-    kr_status st = build_buckets(ctx, set, part, nparts, &bk);
-    unsigned long long *d_work = nullptr, work = 0;
-    if (st == KR_OK) {   // table capacity from this partition's pair increments
-        CU(dalloc(ctx, &d_work, 2 + 2 * PT_MAXDEST));   // work | per-destination counts | cursors | pair-table overflow flag
-        CU(cudaMemsetAsync(d_work, 0, 8 * (2 + 2 * PT_MAXDEST), ctx->stream));
-        WorkSink ws{d_work};
-        KR_LAUNCH(KR_T(k_bk_pairs<WorkSink>), std::min<u32>(bk.nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bk.params(), ws);
-        LAUNCHED(ctx);
-        CU(cudaMemcpyAsync(&work, d_work, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    u64 pcap = 1024; while (pcap < 2 * work && pcap <= (1ull << 30)) pcap <<= 1;
-    if (st == KR_OK && pcap > (1ull << 30)) st = fail(ctx, KR_ERR_ARG, "kr_pairs_partial: %llu pair increments in one partition: use the tile join", work);
-    PairTabParams p{};
-    uint4 *cells = nullptr;
-    if (st == KR_OK) {
-        p.pt_mask = pcap - 1; p.N = set->n; p.row_begin = 0; p.row_end = set->n; p.min_sim = 1;
-        p.overflow = reinterpret_cast<u32 *>(d_work + 1 + 2 * PT_MAXDEST);
-        CU(dalloc(ctx, &p.pt_key, pcap)); CU(dalloc(ctx, &p.pt_cnt, pcap));
-        CU(cudaMemsetAsync(p.pt_key, 0xFF, pcap * 8, ctx->stream));
-        CU(cudaMemsetAsync(p.pt_cnt, 0, pcap * 4, ctx->stream));
-        DestParams dp{}; dp.nd = nparts;
-        for (u32 k = 0; k <= nparts; ++k) dp.rb[k] = row_bounds[k];
-        unsigned long long *d_count = d_work + 1, *d_cursor = d_work + 1 + PT_MAXDEST;
-        {
-            StageTimer t(ctx, ST_JOIN);
-            TableSink tsink{p};
-            KR_LAUNCH(KR_T(k_bk_pairs<TableSink>), std::min<u32>(bk.nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bk.params(), tsink);
-            KR_LAUNCH(KR_T(k_pt_count_dest), ctx->num_sms * 4, 256, 0, ctx->stream, p, dp, d_count);
-            ctx->st.kernel_launches += 2; ctx->st.join_launches++;
-        }
-        unsigned long long h_count[PT_MAXDEST], h_offs[PT_MAXDEST], h_ovf = 0;
-        CU(cudaMemcpyAsync(h_count, d_count, 8 * nparts, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(&h_ovf, d_work + 1 + 2 * PT_MAXDEST, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (h_ovf) return fail(ctx, KR_ERR_STATE, "kr_pairs_partial: internal pair table overflow");
-        u64 total = 0;
-        for (u32 k = 0; k < nparts; ++k) { h_offs[k] = total; total += h_count[k]; counts[k] = h_count[k]; }
-        unsigned long long *d_offs = nullptr;
-        CU(dalloc(ctx, &cells, total + 1)); CU(dalloc(ctx, &d_offs, nparts));
-        CU(cudaMemcpyAsync(d_offs, h_offs, 8 * nparts, cudaMemcpyHostToDevice, ctx->stream));
-        KR_LAUNCH(KR_T(k_pt_fill_dest), ctx->num_sms * 4, 256, 0, ctx->stream, p, dp, d_offs, d_cursor, cells);
-        LAUNCHED(ctx);
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(ctx->stream));   // h_offs is a stack buffer; the caller reads `cells` from another stream
-        dfree(ctx, d_offs);
-        *d_cells = cells;
-    }
-    dfree(ctx, p.pt_key); dfree(ctx, p.pt_cnt); dfree(ctx, d_work);
-    bk.release(ctx);
-    return st;
-}
-void kr_pairs_partial_free(kr_ctx *ctx, void *d_cells) {
-    if (!ctx || !d_cells) return;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaSetDevice(ctx->dev);
-    dfree(ctx, (uint4 *)d_cells);
-}
-kr_status kr_pairs_apply(kr_ctx *ctx, const kr_seqset *set, const kr_matrix_desc *desc, const void *d_cells, uint64_t ncells, void *out_dev) {
-    if (!ctx) return KR_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    kr_status st = check_desc(ctx, set, nullptr, desc);
-    if (st) return st;
-    if (!out_dev || (!d_cells && ncells) || desc->layout == KR_LAYOUT_FULL || (reinterpret_cast<uintptr_t>(out_dev) & 3))
-        return fail(ctx, KR_ERR_ARG, "kr_pairs_apply: bad argument (layout TRIANGLE or BLOCKTRI; output 4-byte aligned)");
-    CU(cudaSetDevice(ctx->dev));
-    PairsParams p{};
-    p.out = out_dev; p.elem = desc->elem; p.layout = desc->layout; p.N = set->n; p.row_begin = desc->row_begin; p.row_end = desc->row_end; p.flags = ctx->flags & 1u;
-    p.origin = row_start(desc->layout, desc->row_begin, set->n, set->n);
-    p.total = row_start(desc->layout, desc->row_end, set->n, set->n) - p.origin;
-    p.meta = set->d_meta;
-    u32 hm = 1024; while (hm < 2 * set->n) hm <<= 1;
-    CU(dalloc(ctx, &p.head, hm)); CU(dalloc(ctx, &p.next, set->n));
-    p.head_mask = hm - 1;
-    CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
-    {
-        StageTimer t(ctx, ST_JOIN);
-        CU(cudaMemsetAsync(out_dev, 0, p.total * (desc->elem == KR_ELEM_U16 ? 2 : 4), ctx->stream));
-        if (ncells) KR_LAUNCH(KR_T(k_cells_apply), ctx->num_sms * 8, 256, 0, ctx->stream, p, (const uint4 *)d_cells, (u64)ncells);
-        KR_LAUNCH(KR_T(k_pairs_dup_insert), (set->n + 255) / 256, 256, 0, ctx->stream, p);
-        KR_LAUNCH(KR_T(k_pairs_dup_fix), (set->n + 255) / 256, 256, 0, ctx->stream, p);
-        ctx->st.kernel_launches += 3; ctx->st.join_launches++;
-        CU(cudaGetLastError());
-    }
-    dfree(ctx, p.head); dfree(ctx, p.next);
-    ctx->st.pairs += kr_matrix_elems(set->n, set->n, KR_LAYOUT_TRIANGLE, desc->row_begin, desc->row_end);
-    return KR_OK;
-}
-
-// EXPERIMENTAL (not in include/kmersreps.h, not in the default build; unverified on hardware): the similarity matrix
-// as a list of its cells with sim >= min_sim -- (row, col, sim, 0) as four uint32, in no particular order.  Layout
-// FULL: every column; TRIANGLE (self only): columns j > i.  *count receives the number of qualifying cells even
-// when it exceeds `cap` (then only `cap` cells are returned and the status is KR_ERR_ARG: call again with room).
-static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
-                             uint32_t *cells_host, uint64_t cap, uint64_t *count);
-kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
-                               uint32_t *cells_host, uint64_t cap, uint64_t *count) {
-    if (!ctx) return KR_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    return sparse_impl(ctx, A, B, desc, min_sim, cells_host, cap, count);
-}
-// the caller holds the context's lock
-static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
-                             uint32_t *cells_host, uint64_t cap, uint64_t *count) {
-    kr_status st = check_desc(ctx, A, B, desc);
-    if (st) return st;
-    if (!count || (!cells_host && cap) || min_sim < 1 || desc->layout == KR_LAYOUT_BLOCKTRI)
-        return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: bad argument (min_sim >= 1; layout FULL or TRIANGLE)");
-    CU(cudaSetDevice(ctx->dev));
-    *count = 0;
-    const bool self = (B == nullptr || B == A);
-    uint4 *d_cells = nullptr; unsigned long long *d_count = nullptr;
-    CU(dalloc(ctx, &d_cells, cap)); CU(dalloc(ctx, &d_count, 2));   // [0] = number of cells, [1] = pair-table overflow flag
-    CU(cudaMemsetAsync(d_count, 0, 16, ctx->stream));
-    bool by_lists = false;
-    kr_seqset *As = const_cast<kr_seqset *>(A);
-    if (self && desc->layout == KR_LAYOUT_TRIANGLE && (ctx->flags & (KR_EXP_PAIRS | KR_EXP_PAIRS_AUTO)) && As->d_keys && As->n) {
-        // posting lists -> pair table -> cells: nothing proportional to N^2 is touched
-        const bool buckets = (ctx->flags & KR_EXP_BUCKETS) != 0;
-        if ((st = buckets ? ensure_buckets(ctx, As) : ensure_postings(ctx, As)) == KR_OK) st = postings_work(ctx, As);
-        // table capacity: every pair that shares a k-mer (<= work) plus the equal-sequence pairs that share none
-        // (sequences shorter than K: e of them give at most e(e-1)/2 such pairs)
-        u64 empties = 0;
-        if (st == KR_OK && (st = fetch_sizes(ctx, As)) == KR_OK) for (u32 v : As->h_sizes) empties += v == 0;
-        const u64 need = As->px_work + empties * (empties ? empties - 1 : 0) / 2;
-        u64 pcap = 1024; while (pcap < 2 * need && pcap <= (1ull << 29)) pcap <<= 1;
-        if (st == KR_OK && pcap <= (1ull << 29)) {   // <= 6 GB of pair table; beyond that the join's epilogue filter is the better tool
-            by_lists = true;
-            PairTabParams p{};
-            p.tab_cnt = As->px_cnt; p.tab_off = As->px_off; p.postings = As->px_post; p.nslots = As->px_slots;
-            p.pt_mask = pcap - 1; p.N = As->n; p.row_begin = desc->row_begin; p.row_end = desc->row_end; p.flags = ctx->flags & 1u; p.min_sim = (u32)min_sim;
-            p.meta = As->d_meta; p.cells = d_cells; p.cells_cap = cap; p.cells_count = d_count; p.overflow = reinterpret_cast<u32 *>(d_count + 1);
-            u32 hm = 1024; while (hm < 2 * As->n) hm <<= 1;
-            p.head_mask = hm - 1;
-            CU(dalloc(ctx, &p.pt_key, pcap)); CU(dalloc(ctx, &p.pt_cnt, pcap)); CU(dalloc(ctx, &p.head, hm)); CU(dalloc(ctx, &p.next, As->n));
-            CU(cudaMemsetAsync(p.pt_key, 0xFF, pcap * 8, ctx->stream));
-            CU(cudaMemsetAsync(p.pt_cnt, 0, pcap * 4, ctx->stream));
-            CU(cudaMemsetAsync(p.head, 0xFF, (size_t)hm * 4, ctx->stream));
-            {
-                StageTimer t(ctx, ST_JOIN);
-                if (buckets) {
-                    TableSink tsink{p};
-                    KR_LAUNCH(KR_T(k_bk_pairs<TableSink>), std::min<u32>(As->bk_nb, (u32)ctx->num_sms * 3), BK_THREADS, BK_SMEM, ctx->stream, bucket_params(As), tsink);
-                } else
-                KR_LAUNCH(KR_T(k_pairs_emit_tab), ctx->num_sms * 8, 256, 0, ctx->stream, p);
-                KR_LAUNCH(KR_T(k_pairs_dup_insert_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);
-                KR_LAUNCH(KR_T(k_pairs_dup_tab), (As->n + 255) / 256, 256, 0, ctx->stream, p);
-                KR_LAUNCH(KR_T(k_pairs_compact_blk), ctx->num_sms * 8, 256, 0, ctx->stream, p);
-                ctx->st.kernel_launches += 4; ctx->st.join_launches++;
-                CU(cudaGetLastError());
-            }
-            dfree(ctx, p.pt_key); dfree(ctx, p.pt_cnt); dfree(ctx, p.head); dfree(ctx, p.next);
-            ctx->st.pairs += kr_matrix_elems(As->n, As->n, KR_LAYOUT_TRIANGLE, desc->row_begin, desc->row_end);
-        }
-    }
-    SparseSink sink{d_cells, cap, d_count, (u32)min_sim};
-    if (st == KR_OK && !by_lists) st = matrix_launch(ctx, As, const_cast<kr_seqset *>(B), self, desc, d_cells, &sink);
-    unsigned long long n = 0;
-    if (st == KR_OK) {
-        unsigned long long two[2] = {0, 0};
-        cudaError_t e = cudaMemcpyAsync(two, d_count, 16, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        n = two[0];
-        if (e == cudaSuccess && two[1]) st = fail(ctx, KR_ERR_STATE, "kr_sim_matrix_sparse: internal pair table overflow");
-        const unsigned long long take = std::min<unsigned long long>(n, cap);
-        if (e == cudaSuccess && take) e = cudaMemcpyAsync(cells_host, d_cells, take * 16, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "sparse matrix copy to host failed: %s", cudaGetErrorString(e));
-        ctx->st.d2h_bytes += 8 + take * 16;
-        *count = n;
-        if (st == KR_OK && n > cap) st = fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: %llu cells qualify, room for %llu", n, (unsigned long long)cap);
-    }
-    dfree(ctx, d_cells); dfree(ctx, d_count);
-    return st;
-}
+#include "kr_api_exp_entry.inc"
 #endif
 
 // ---- database ----------------------------------------------------------------------------------
@@ -1856,88 +1453,5 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
 }  // extern "C"
 
 #if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
-// With -DKR_DEFAULTS_V2 the experimental device paths are what every context uses.  Before the first protein context of a
-// process is handed out, each of them is run once on the GPU against the round-1 path it replaces, on a small synthetic
-// batch, and compared bit for bit ON THE DEVICE'S OWN RESULTS (GPU path against GPU path; no CPU arithmetic is involved).
-// A path that disagrees is switched off for the process -- the library then keeps using the path it was measured and
-// verified with -- and the reason is printed once.  ~300 sequences; a few milliseconds.
-static u32 g_v2_disabled = 0;            // experimental flag bits found unusable on this machine
-static std::once_flag g_v2_once;
-
-static void v2_run_selfcheck(kr_ctx *ctx) {
-    const u32 all = KR_EXP_PAIRS_AUTO | KR_EXP_BUCKETS | KR_EXP_ENCODE | KR_EXP_IDXQ | KR_EXP_GIDX;
-    const u32 keep = ctx->flags;
-    // a small family-structured batch: 12 roots, members with substitutions, a few exact duplicates and short sequences
-    std::vector<std::string> seqs;
-    u64 x = 0x9E3779B97F4A7C15ull;
-    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
-    const char *aa = "ACDEFGHIKLMNPQRSTVWY";
-    std::vector<std::string> roots(12);
-    for (auto &r : roots) { r.resize(200 + rnd() % 150); for (auto &c : r) c = aa[rnd() % 20]; }
-    int nseq_check = 300;
-    if (const char *e = getenv("KR_V2_SELFCHECK_N")) nseq_check = std::max(210, atoi(e));   // (tests on the CPU emulator use fewer)
-    for (int i = 0; i < nseq_check; ++i) {
-        if (i % 37 == 5) { seqs.push_back(seqs[rnd() % seqs.size()]); continue; }
-        if (i % 41 == 7) { seqs.push_back(std::string("MKV").substr(0, rnd() % 4)); continue; }
-        std::string m = roots[rnd() % roots.size()];
-        const size_t subs = m.size() * (rnd() % 12) / 100;
-        for (size_t k = 0; k < subs; ++k) m[rnd() % m.size()] = aa[rnd() % 20];
-        seqs.push_back(m.substr(0, m.size() - rnd() % 30));
-    }
-    std::string flat; std::vector<u64> off{0};
-    for (auto &q : seqs) { flat += q; off.push_back(flat.size()); }
-    const u32 n = (u32)seqs.size();
-    auto with = [&](u32 flags, auto &&fn) { ctx->flags = (keep & ~all) | flags; fn(); ctx->flags = keep; };
-    auto disable = [&](u32 bits, const char *what) {
-        g_v2_disabled |= bits;
-        fprintf(stderr, "kmersreps: the %s path disagrees with the verified path in the start-up self-check; it is switched off for this process\n", what);
-    };
-    struct Run { std::vector<u32> sizes; std::vector<u16> m; std::vector<int32_t> sim; std::vector<u32> first, last; std::vector<u8> added; bool ok = true; };
-    auto run = [&](u32 flags) {
-        Run r;
-        with(flags, [&] {
-            kr_seqset *s = nullptr; kr_db *db = nullptr, *db2 = nullptr;
-            r.sizes.resize(n); r.m.resize((size_t)n * n); r.sim.resize(n - 200); r.first.resize(n - 200); r.last.resize(n - 200); r.added.resize(n);
-            kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, n};
-            r.ok = kr_encode(ctx, (const u8 *)flat.data(), off.data(), n, &s) == KR_OK && kr_seqset_sizes(s, r.sizes.data()) == KR_OK
-                && kr_sim_matrix(ctx, s, nullptr, &d, r.m.data()) == KR_OK;
-            kr_seqset *q = nullptr;
-            if (r.ok) {
-                const u32 flags_fc = ctx->flags;
-                ctx->flags |= KR_FORCE_INDEX;
-                r.ok = kr_db_create(ctx, &db) == KR_OK && kr_db_append(ctx, db, (const u8 *)flat.data(), off.data(), 200) == KR_OK
-                    && kr_encode(ctx, (const u8 *)flat.data(), off.data() + 200, n - 200, &q) == KR_OK   /* offsets[0] is honoured */
-                    && kr_db_find_closest(ctx, db, q, r.sim.data(), r.first.data(), r.last.data()) == KR_OK;
-                ctx->flags = flags_fc;
-            }
-            if (r.ok) r.ok = kr_db_create(ctx, &db2) == KR_OK && kr_greedy_build(ctx, db2, s, 40, 64, r.added.data()) == KR_OK;
-            if (q) kr_seqset_free(q);
-            if (db) kr_db_free(db);
-            if (db2) kr_db_free(db2);
-            if (s) kr_seqset_free(s);
-        });
-        return r;
-    };
-    const Run ref = run(0);
-    if (!ref.ok) return;   // the verified paths themselves fail here: nothing to compare against; errors surface in the caller's calls
-    struct Probe { u32 flags, blame; const char *what; };
-    const Probe probes[] = {{KR_EXP_ENCODE, KR_EXP_ENCODE, "warp-per-sequence encode"},
-                            {KR_EXP_PAIRS | KR_EXP_BUCKETS, KR_EXP_PAIRS_AUTO | KR_EXP_PAIRS | KR_EXP_BUCKETS, "posting-list all-vs-all"},
-                            {KR_EXP_IDXQ, KR_EXP_IDXQ, "warp-per-query index"},
-                            {KR_EXP_GIDX, KR_EXP_GIDX, "growing-index build"}};
-    for (const Probe &p : probes) {
-        const Run got = run(p.flags);
-        if (!got.ok || got.sizes != ref.sizes || got.m != ref.m || got.sim != ref.sim || got.first != ref.first || got.last != ref.last || got.added != ref.added)
-            disable(p.blame, p.what);
-    }
-    ctx->err.clear();
-    kr_stats_reset(ctx);
-}
-
-static void v2_selfcheck(kr_ctx *ctx) {
-    if (ctx->dnaK || (ctx->flags & KR_LEGACY_PATHS)) return;
-    if (const char *e = getenv("KR_V2_SELFCHECK")) if (e[0] == '0') return;   // test runs on the CPU emulator skip it
-    std::call_once(g_v2_once, [&] { if (ctx->K == 8) v2_run_selfcheck(ctx); else { kr_ctx *c8 = nullptr; if (kr_create(ctx->dev, 8, KR_LEGACY_PATHS | 1u, &c8) == KR_OK) { c8->flags = (c8->flags & ~KR_LEGACY_PATHS) | (ctx->flags & 0xFF00u); v2_run_selfcheck(c8); kr_destroy(c8); } } });
-    ctx->flags &= ~g_v2_disabled;
-}
+#include "kr_api_v2check.inc"
 #endif
