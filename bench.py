@@ -309,7 +309,9 @@ def main():
                     help="which host-buffer call the headline `e2e` key reports: kr_sim_matrix (dense result over PCIe) or, with the "
                          "experimental library, kr_sim_matrix_sparse (implies --sparse-e2e; the other one stays in e2e_dense / e2e_sparse)")
     ap.add_argument("--elem", default="u16", choices=["u16", "i32"])
-    ap.add_argument("--replicated-encode", action="store_true", help="N>1: every rank encodes all sequences (no block-list all-gather)")
+    ap.add_argument("--sharded-encode", action="store_true",
+                    help="N>1: each rank encodes 1/N of the sequences and the block lists are all-gathered (NCCL) and imported; the default is "
+                         "that every rank encodes all sequences (no data-path collective)")
     ap.add_argument("--gather-matrix", action="store_true",
                     help="N>1: also all-gather the whole matrix onto every GPU after the timed region and report its cost")
     args = ap.parse_args()
@@ -347,7 +349,7 @@ def main():
     d_out = torch.empty(my_elems * esz + 16, dtype=torch.uint8, device="cuda")
     total_pairs = N * (N - 1) // 2
 
-    sharded_encode = world > 1 and not args.replicated_encode
+    sharded_encode = world > 1 and args.sharded_encode
 
     if binding.build_info() == "v2":   # the posting-list path is this library's default: exchange key lists and split the counting by key
         args.exp_pairs = True
@@ -447,35 +449,24 @@ def main():
     # ---- roofline of the dominant kernel (tile join) -----------------------------------------
     hbm, hbm_src = peaks()
     join_ms = st["join_ms"] / max(1, st["join_launches"])
-    my_pairs = kr.matrix_elems(N, N, kr.LAYOUT_TRIANGLE, r0, r1)
-    # contract figure: both sorted key lists of every pair streamed once + int32 result
     ssum = int(sizes.sum())
-    key_stream = 0
-    # sum over this rank's rows i of sum_{j>i} 8*(|A_i|+|A_j|) + 4
+    # (i) what the launch must move through DRAM whatever the algorithm: every key list it reads once
+    #     (8 B per distinct k-mer of the batch: the rows of this stripe join against ALL columns) + its result cells once
+    out_bytes = my_elems * esz
+    compulsory = ssum * 8 + out_bytes
+    achieved = compulsory / (join_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                "kernel": "k_join<MATRIX>", "kernel_ms": join_ms, "peak_source": hbm_src, "algorithmic_bytes": compulsory,
+                "note": "algorithmic bytes = compulsory DRAM traffic of one launch (SURVEY.md 8d.3): the batch's key lists once (8 B per distinct "
+                        "k-mer) + this rank's result cells once; traffic (ncu dram bytes) is not measured inside bench.py, see profiles/"}
+    # (ii) the per-pair streaming figure of SURVEY.md 8d.1 (8(|A|+|B|)+4 B per pair): a WORK-EQUIVALENCE number, not a bound for
+    #      this kernel -- one pass over two 256-sequence block lists serves 65,536 pairs, so it exceeds the HBM peak many times
     suffix = np.concatenate([np.cumsum(sizes[::-1])[::-1], [0]])
     rows = np.arange(r0, r1)
     key_stream = int((8 * (sizes[rows] * (N - 1 - rows) + suffix[rows + 1]) + 4 * (N - 1 - rows)).sum())
-    achieved = key_stream / (join_ms / 1e3) / 1e9
-    # what the kernel really has to move: its output once + each tile's two block lists once
-    nblk = (N + 255) // 256
-    blk_bytes = np.add.reduceat(sizes, np.arange(0, N, 256)) * 8
-    list_bytes = 0
-    for I in range(r0 // 256, (r1 + 255) // 256):
-        list_bytes += int(blk_bytes[I]) * (nblk - I) + int(blk_bytes[I:].sum())
-    out_bytes = my_elems * esz
-    design = {"bound": "hbm", "achieved": (out_bytes + list_bytes) / (join_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
-              "frac": (out_bytes + list_bytes) / (join_ms / 1e3) / 1e9 / hbm, "output_bytes": out_bytes, "blocklist_bytes": list_bytes,
-              "note": "bytes the tile-join design moves per launch: result once + both block lists of every tile once (block lists mostly hit L2)"}
-    # ncu --set full capture of this kernel on this workload (profiles/README.md): 3.126 GB read + 10.076 GB written
-    traffic = 13201831000 if (world == 1 and N == 100000 and esz == 2 and not args.exp_pairs) else None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
-                "traffic_unit": "bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_k_join_details.txt)",
-                "kernel": "zero fill + k_bk_pairs / k_pairs_emit + equal-sequence pass (experimental posting-list path)" if args.exp_pairs else "k_join<MATRIX>",
-                "kernel_ms": join_ms, "peak_source": hbm_src,
-                "algorithmic_bytes": key_stream,
-                "note": "contract figure of SURVEY.md 8d.1 (every pair streams both key lists: 8(|A|+|B|)+4 B/pair). The tile join "
-                        "shares one pass over two 256-sequence block lists among 65,536 pairs, so this fraction exceeds 1; see "
-                        "roofline_design and DESIGN.md"}
+    contract = {"algorithmic_bytes": key_stream, "achieved": key_stream / (join_ms / 1e3) / 1e9, "unit": "GB/s",
+                "frac_of_hbm_peak": key_stream / (join_ms / 1e3) / 1e9 / hbm,
+                "note": "SURVEY.md 8d.1 pairwise key-stream figure; not a roofline for a block-level join (reported because north_star quotes it)"}
 
     # ---- e2e: host buffers through the C ABI -----------------------------------------------------
     e2e = None
@@ -545,7 +536,7 @@ def main():
                                    ("each rank encodes 1/%d of the sequences, block lists all-gathered (NCCL)" % world if sharded_encode
                                     else "keys replicated, no data-path collective"),
                        "cache": "inputs+outputs larger than L2 (key lists %d MB, result %d MB per rank)" % (ssum * 8 >> 20, my_elems * esz >> 20)},
-            "roofline": roofline, "roofline_design": design, "cpu_baseline": cpu, "e2e": e2e, "e2e_sparse": e2e_sparse, "e2e_dense": e2e_dense,
+            "roofline": roofline, "roofline_contract_8d1": contract, "cpu_baseline": cpu, "e2e": e2e, "e2e_sparse": e2e_sparse, "e2e_dense": e2e_dense,
             "gpu_launches": int(st["kernel_launches"]), "clocks": clocks,
             "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
             "verified": "400 sampled cells per rank equal the oracle",

@@ -51,6 +51,7 @@ struct DevMem {   // refcounted device allocation (residue buffers are shared by
     cudaStream_t stream = nullptr;
     ~DevMem() { if (p) cudaFreeAsync(p, stream); }   // stream-ordered: safe after every kernel already queued
 };
+static cudaError_t pool_alloc(struct kr_ctx *ctx, void **p, size_t bytes);
 
 struct kr_ctx {
     int dnaK = 0;   // experimental DNA contexts: the DNA k-mer size (K below is then the key width in 5-bit units)
@@ -58,6 +59,7 @@ struct kr_ctx {
     u32 flags = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaMemPool_t pool = nullptr;   // this context's own memory pool: the device's default pool (shared with the JVM / torch) is never touched
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     std::mutex mu;
     std::string err;
@@ -144,8 +146,9 @@ static inline u64 kmer_slots(const kr_ctx *ctx, u64 L) {
 template <typename T> static cudaError_t dalloc(kr_ctx *ctx, T **p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
-    return cudaMallocAsync((void **)p, count * sizeof(T), ctx->stream);
+    return pool_alloc(ctx, (void **)p, count * sizeof(T));
 }
+static cudaError_t pool_alloc(kr_ctx *ctx, void **p, size_t bytes) { return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, ctx->stream); }
 template <typename T> static void dfree(kr_ctx *ctx, T *p) { if (p) cudaFreeAsync((void *)p, ctx->stream); }
 
 static cudaEvent_t get_event(kr_ctx *ctx) {
@@ -254,10 +257,15 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
         CUC(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
     }
-    cudaMemPool_t pool;
-    CUC(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long keep = ~0ull;
-    CUC(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    {   // a private pool that keeps its memory between calls (steps re-use the same sizes); freed with the context
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CUC(cudaMemPoolCreate(&ctx->pool, &props));
+        unsigned long long keep = ~0ull;
+        CUC(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     std::vector<u8> lut(1 << LUT_BITS); make_chunk_lut(lut.data());
     CUC(cudaMalloc(&ctx->d_lut, lut.size()));
     CUC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
@@ -298,6 +306,7 @@ void kr_destroy(kr_ctx *ctx) {
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -396,14 +405,21 @@ static void seqset_destroy(kr_seqset *s) {
     delete s;   // residue buffers are released stream-ordered by ~DevMem
 }
 
-// read (and clear) the device-side "residue outside the alphabet" flag; synchronises the stream
+// read (and clear) the context's device-side error record: a residue outside the alphabet (K1) or a tile join that
+// had to skip work (K3: misaligned block list, watchdog); synchronises the stream
 static kr_status check_alphabet(kr_ctx *ctx) {
     ErrInfo ei;
     CU(cudaMemcpyAsync(&ei, ctx->d_err, sizeof ei, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->err_pending = false;
+    if (ei.flag || ei.join_fault) cudaMemsetAsync(ctx->d_err, 0, sizeof(ErrInfo), ctx->stream);
+    if (ei.join_fault == JOIN_FAULT_ALIGN)
+        return fail(ctx, KR_ERR_STATE, "tile join: a block list is not 16-byte aligned (CTA %u, entry offsets %u / %u); the tile was skipped and "
+                    "the result of this call is invalid", ei.join_info[0], ei.join_info[1], ei.join_info[2]);
+    if (ei.join_fault)
+        return fail(ctx, KR_ERR_STATE, "tile join: a pipeline wait timed out in CTA %u (slot %u); the launch was drained and the result of this "
+                    "call is invalid", ei.join_info[0], ei.join_info[1]);
     if (ei.flag) {
-        cudaMemsetAsync(ctx->d_err, 0, sizeof(ErrInfo), ctx->stream);
         return fail(ctx, KR_ERR_ALPHABET, "kr_encode: sequence %u position %u: residue 0x%02x ('%c') is outside %s",
                     ei.seq, ei.pos, ei.byte, (ei.byte >= 32 && ei.byte < 127) ? (char)ei.byte : '?',
                     ctx->dnaK ? "a c g t n u (either case)" : "'A'..'Z', '*', '-'");
@@ -434,7 +450,7 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
     s->ctx = ctx; s->n = nseq; s->key_cap = kc;
     s->res = std::make_shared<DevMem>();
     s->res->stream = ctx->stream;
-    CU(cudaMallocAsync(&s->res->p, total + 16, ctx->stream));
+    CU(pool_alloc(ctx, &s->res->p, total + 16));
     if (on_device) CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyDeviceToDevice, ctx->stream));
     else { CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream)); ctx->st.h2d_bytes += total; }
     CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_koff, nseq + 1));
@@ -608,7 +624,7 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
     JoinParams p{};
     p.A = A->d_refs; p.B = Bs->d_refs; p.metaA = A->d_meta; p.metaB = Bs->d_meta;
     p.nA = A->n; p.nB = Bs->n; p.nBblk = Bs->nblk;
-    p.tasks = d_tasks; p.ntasks = ctx->tasks_cache_n; p.flags = ctx->flags;
+    p.tasks = d_tasks; p.ntasks = ctx->tasks_cache_n; p.flags = ctx->flags; p.err = ctx->d_err; ctx->err_pending = true;
     p.out = out_dev; p.elem = d->elem; p.layout = d->layout;
     p.origin = row_start(d->layout, d->row_begin, A->n, Bs->n);
     {
@@ -909,7 +925,7 @@ static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *
     JoinParams p{};
     p.A = Q->d_refs; p.B = db->d_refs; p.metaA = Q->d_meta; p.metaB = db->d_meta;
     p.nA = Q->n; p.nB = db->n; p.nBblk = db->nblk;
-    p.tasks = d_tasks; p.ntasks = (u32)tasks.size(); p.flags = ctx->flags;
+    p.tasks = d_tasks; p.ntasks = (u32)tasks.size(); p.flags = ctx->flags; p.err = ctx->d_err; ctx->err_pending = true;
     p.nsplit = nsplit; p.rankB = db->d_rank; p.partial = d_partial;
     {
         StageTimer t(ctx, ST_JOIN);
@@ -1025,13 +1041,40 @@ kr_status kr_seqset_import_blocklists(kr_ctx *ctx, const kr_blocklists *shards, 
         entries += (sh.entries + 63) / 64 * 64; nblk += sh.nblk; n += sh.nseq;   // every shard starts 256-byte aligned (TMA sources)
     }
     if (n != nseq) return fail(ctx, KR_ERR_ARG, "import: shards hold %u sequences, batch has %u", n, nseq);
+    // The tile join feeds these arrays to cp.async.bulk, whose sources must be 16-byte aligned and in range: a shard that
+    // breaks the layout is refused here (KR_ERR_ARG), before anything is built from it.
+    {
+        u32 *d_bad = nullptr;
+        CU(dalloc(ctx, &d_bad, 2 * (size_t)nshards));
+        CU(cudaMemsetAsync(d_bad, 0, 8 * (size_t)nshards, ctx->stream));
+        for (u32 k = 0; k < nshards; ++k) {
+            const kr_blocklists &sh = shards[k];
+            if (sh.nseq == 0) continue;
+            if (!sh.hi || !sh.lo || !sh.chunk_off || !sh.chunk_cnt || !sh.blk_base || !sh.meta) { dfree(ctx, d_bad); return fail(ctx, KR_ERR_ARG, "import: shard %u has a null array", k); }
+            if (((reinterpret_cast<uintptr_t>(sh.hi) | reinterpret_cast<uintptr_t>(sh.lo)) & 15) || ((reinterpret_cast<uintptr_t>(sh.chunk_off) | reinterpret_cast<uintptr_t>(sh.chunk_cnt)) & 3)
+                || (reinterpret_cast<uintptr_t>(sh.blk_base) & 7) || (reinterpret_cast<uintptr_t>(sh.meta) & 7)) {
+                dfree(ctx, d_bad);
+                return fail(ctx, KR_ERR_ARG, "import: shard %u: hi / lo must be 16-byte aligned device arrays (chunk tables 4-byte, block bases and records 8-byte)", k);
+            }
+            KR_LAUNCH(KR_T(k_validate_shard), (sh.nblk + 127) / 128, 128, 0, ctx->stream, sh.nblk, sh.entries, (const u32 *)sh.chunk_off, (const u32 *)sh.chunk_cnt,
+                      (const u64 *)sh.blk_base, d_bad + 2 * k);
+            LAUNCHED(ctx);
+        }
+        std::vector<u32> bad(2 * (size_t)nshards);
+        CU(cudaMemcpyAsync(bad.data(), d_bad, 8 * (size_t)nshards, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx, d_bad);
+        for (u32 k = 0; k < nshards; ++k)
+            if (bad[2 * k]) return fail(ctx, KR_ERR_ARG, "import: shard %u: %u block(s) break the block-list layout (first: block %u): chunk starts must be ascending multiples "
+                                        "of %d entries inside the shard's arrays with %u spare entries after each block", k, bad[2 * k], bad[2 * k + 1], CHUNK_ALIGN, TAILPAD);
+    }
     std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
     s->ctx = ctx; s->n = nseq; s->nblk = nblk;
     const u64 total_res = offsets[nseq] - offsets[0];
     std::vector<u64> off(nseq + 1);
     for (u32 i = 0; i <= nseq; ++i) off[i] = offsets[i] - offsets[0];
     s->res = std::make_shared<DevMem>(); s->res->stream = ctx->stream;
-    CU(cudaMallocAsync(&s->res->p, total_res + 16, ctx->stream));
+    CU(pool_alloc(ctx, &s->res->p, total_res + 16));
     CU(cudaMemcpyAsync(s->res->p, d_residues + offsets[0], total_res, cudaMemcpyDeviceToDevice, ctx->stream));
     u8 *d_lo = nullptr;
     CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_meta, nseq));
@@ -1171,6 +1214,7 @@ kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, con
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess && st == KR_OK) st = fail(ctx, KR_ERR_CUDA, "matrix copy to host failed: %s", cudaGetErrorString(e));
     dfree(ctx, d_buf[0]); dfree(ctx, d_buf[1]);
+    if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
     return st;
 }
 
@@ -1259,6 +1303,7 @@ kr_status kr_db_find_closest(kr_ctx *ctx, const kr_db *db, const kr_seqset *quer
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "find_closest copy to host failed: %s", cudaGetErrorString(e));
         ctx->st.d2h_bytes += (u64)nq * 12;
+        if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
     }
     dfree(ctx, d_sim); dfree(ctx, d_first); dfree(ctx, d_last);
     return st;
@@ -1370,6 +1415,7 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
                 if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
                 if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
                 ctx->st.d2h_bytes += (u64)n * 4;
+                if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
             }
             dfree(ctx, d_sim);
             seqset_destroy(bs);
@@ -1425,6 +1471,7 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
                 if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
                 if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
                 ctx->st.d2h_bytes += (u64)S * S * 2;
+                if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
             }
             dfree(ctx, d_M);
             seqset_destroy(ss);

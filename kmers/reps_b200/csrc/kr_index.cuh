@@ -1,0 +1,290 @@
+// kr_index.cuh -- sm_100a kernels of the SORTED INVERTED INDEX and of the warp-per-query scan that serves
+// findClosest, checkSimilarity / the greedy build and the sparse all-vs-all.
+//
+// Index of a collection of sequences (a RepGenomeDb, or the set an all-vs-all runs over):
+//   entry   (H(key) << idbits) | id          one uint64 per (distinct k-mer, sequence); H is a bijection of the
+//                                            5K-bit key space, so equal hashed keys are equal keys (exact, no
+//                                            false sharing) and hashed keys are uniform whatever the residue
+//                                            composition is
+//   ent[]   all entries, sorted by hashed key: the posting list of a k-mer is a contiguous run
+//   dir[]   2^D + 1 offsets: entries whose hashed key starts with the D-bit prefix b are ent[dir[b] .. dir[b+1])
+//           (D is chosen so that a prefix holds 2..4 entries: one or two 32-byte sectors per probe)
+// Build (K4): count entries per B-bit prefix -> exclusive scan -> scatter into the prefix's slot (one streaming
+//   pass each, global atomics only on the 2^B counters) -> one CTA per prefix sorts its ~2,000 entries in shared
+//   memory -> directory.  About 50 B of HBM traffic per entry; nothing is hashed into a table, nothing is probed.
+// Query (K5): one WARP per query.  Each lane takes keys of the query, reads the two directory words and walks the
+//   few entries of the prefix; every matching entry adds 1 to the score of its sequence id in the warp's own
+//   shared-memory score table (open addressing on the id, 1024 slots, touched slots remembered in a list).  A
+//   query that touches more ids than fit is redone in 4, 16, 64 ... passes over disjoint id classes, so the
+//   result is exact for any input.  The epilogue turns the touched slots into
+//     ARGMAX  (max similarity, first rank, last rank)          -- RepGenomeDb.findClosest / checkSimilarity
+//     CELLS   (row, col, sim) for every sim >= min_sim         -- similarity matrices as sparse cells
+//   with the equal-sequence rule applied (score == both sizes -> hash -> byte compare -> INFINITY).
+// Every similarity is an exact integer count.
+#pragma once
+#include "kr_kernels.cuh"
+
+namespace kr {
+
+// ---- bijective hash of a `bits`-wide key (xorshift and odd multiplications are invertible modulo 2^bits) ----------
+__host__ __device__ __forceinline__ u64 ix_hash(u64 k, int bits, u64 mask) {
+    const int s = bits >> 1;
+    k ^= k >> s;
+    k = (k * 0x9E3779B97F4A7C15ULL) & mask;
+    k ^= k >> s;
+    k = (k * 0xD6E8FEB86659FD93ULL) & mask;
+    k ^= k >> s;
+    return k;
+}
+
+struct IxGeom {      // bit layout of an index: plain values, identical on host and device
+    int keybits;     // 5K
+    int idbits;      // bits of a sequence id (>= 1)
+    int B;           // prefix bits of the build partition
+    int D;           // prefix bits of the directory
+    u64 keymask;
+};
+
+struct KIndex {
+    const u64 *ent;  // n entries, sorted
+    const u32 *dir;  // 2^D + 1 offsets
+    u32 n;
+    IxGeom g;
+};
+
+constexpr u32 IX_SORT_CAP = 4096;      // entries a prefix may hold to be sorted in shared memory (32 KB)
+constexpr u32 IX_SORT_THREADS = 256;
+
+// one segment of the collection being indexed: sequences [0, nseq) of a set become ids id_base + s
+struct IxSegment { const u64 *keys; const u64 *koff; const SeqMeta *meta; u32 nseq; u32 id_base; };
+
+// K4.1 / K4.3: count, then scatter, the entries of a segment by B-bit prefix.  One warp per sequence (its key list is
+// contiguous); part / nparts select the hashed keys of one partition (multi-GPU build: partition p owns the prefixes
+// [p * 2^B / nparts, (p + 1) * 2^B / nparts)); nparts == 1 takes everything.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_ix_partition(IxSegment sg, IxGeom g, u32 pfx_lo, u32 pfx_hi, u32 *cnt_or_cursor, u64 *ent) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= sg.nseq) return;
+    const u32 n = sg.meta[s].size;
+    const u64 *kp = sg.keys + sg.koff[s];
+    const u64 id = sg.id_base + s;
+    const int pshift = g.keybits - g.B;
+    for (u32 i = lane; i < n; i += 32) {
+        const u64 hk = ix_hash(kp[i], g.keybits, g.keymask);
+        const u32 pfx = (u32)(hk >> pshift);
+        if (pfx < pfx_lo || pfx >= pfx_hi) continue;
+        if (SCATTER) { const u32 pos = atomicAdd(&cnt_or_cursor[pfx], 1u); ent[pos] = (hk << g.idbits) | id; }
+        else atomicAdd(&cnt_or_cursor[pfx], 1u);
+    }
+}
+
+// K4.2: exclusive scan of the 2^B prefix counts (one CTA): start[p] = first slot of prefix p, start[2^B] = total;
+// cursor[p] = start[p] for the scatter.  `base` shifts every start (entries of earlier partitions precede).
+__global__ void __launch_bounds__(1024) k_ix_scan(const u32 *cnt, u32 nbins, u32 *start, u32 *cursor) {
+    __shared__ u32 part[1024];
+    const u32 tid = threadIdx.x, per = (nbins + 1023) / 1024;
+    const u32 b0 = min(nbins, tid * per), b1 = min(nbins, b0 + per);
+    u32 acc = 0;
+    for (u32 i = b0; i < b1; ++i) acc += cnt[i];
+    part[tid] = acc;
+    __syncthreads();
+    if (tid == 0) { u32 run = 0; for (int i = 0; i < 1024; ++i) { const u32 v = part[i]; part[i] = run; run += v; } start[nbins] = run; }
+    __syncthreads();
+    u32 run = part[tid];
+    for (u32 i = b0; i < b1; ++i) { const u32 v = cnt[i]; start[i] = run; cursor[i] = run; run += v; }
+}
+
+// K4.4: one CTA per prefix sorts the prefix's entries (shared memory; in place in global memory for the rare prefix
+// that holds more than IX_SORT_CAP entries, e.g. one k-mer shared by thousands of sequences)
+__global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u64 *ent) {
+    __shared__ __align__(16) u64 sk[IX_SORT_CAP];
+    const u32 p = blockIdx.x, tid = threadIdx.x;
+    const u32 lo = start[p], n = start[p + 1] - lo;
+    if (n < 2) return;
+    u64 *g = ent + lo;
+    if (n <= IX_SORT_CAP) {
+        for (u32 i = tid; i < n; i += IX_SORT_THREADS) sk[i] = g[i];
+        __syncthreads();
+        bitonic_sort(sk, n, tid, IX_SORT_THREADS);
+        for (u32 i = tid; i < n; i += IX_SORT_THREADS) g[i] = sk[i];
+    } else {
+        bitonic_sort(g, n, tid, IX_SORT_THREADS);
+    }
+}
+
+// K4.5: the directory.  Entry i opens every D-bit prefix after its predecessor's up to its own; the last entry also
+// closes the prefixes above it.  An empty index is all zeros (memset by the host).
+__global__ void __launch_bounds__(256) k_ix_dir(const u64 *ent, u32 n, int dshift, u32 ndir, u32 *dir) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 d = (u32)(ent[i] >> dshift);
+    const u32 first = i ? (u32)(ent[i - 1] >> dshift) + 1 : 0;
+    for (u32 b = first; b <= d; ++b) dir[b] = i;
+    if (i == n - 1) for (u32 b = d + 1; b <= ndir; ++b) dir[b] = n;
+}
+
+// sum over the posting lists of m^2 (work of a self scan: every entry walks its own list) and the longest list;
+// one thread per entry, run starts only.  out[0] += sum m^2, out[1] = max m
+__global__ void __launch_bounds__(256) k_ix_work(const u64 *ent, u32 n, int idbits, unsigned long long *out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long w = 0, mx = 0;
+    if (i < n) {
+        const u64 hk = ent[i] >> idbits;
+        if (i == 0 || (ent[i - 1] >> idbits) != hk) {
+            u32 m = 1;
+            while (i + m < n && (ent[i + m] >> idbits) == hk) ++m;
+            w = (unsigned long long)m * m; mx = m;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        w += __shfl_xor_sync(0xffffffffu, w, o);
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = t > mx ? t : mx;
+    }
+    if ((threadIdx.x & 31) == 0 && w) { atomicAdd(&out[0], w); atomicMax(&out[1], mx); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5: the scan.
+enum { IXQ_ARGMAX = 0, IXQ_CELLS = 1 };
+constexpr u32 IXQ_WARPS = 8;            // queries in flight per CTA
+constexpr u32 IXQ_H = 1024;             // slots of a warp's score table
+constexpr u32 IXQ_FILL = 768;           // ids a pass may touch before the query is redone in more passes
+constexpr u32 IXQ_EMPTY = 0xFFFFFFFFu;
+constexpr u32 IXQ_SMEM_PER_WARP = IXQ_H * 4 + IXQ_H * 4 + IXQ_H * 2 + 16;   // ids, scores, touched list, counters
+
+struct IxQueryParams {
+    // queries: sequences [q_begin, q_end) of a set
+    const u64 *qkeys; const u64 *qkoff; const SeqMeta *qmeta; u32 q_begin, q_end;
+    KIndex ix;
+    const SeqMeta *rmeta;          // records of the indexed sequences, by id
+    u32 flags;                     // KR_IDENT_IS_INFINITY
+    u32 *next;                     // work counter (starts at 0)
+    // ARGMAX
+    const u32 *rank; int4 *partial;   // partial[q - q_begin] = (sim, first rank, last rank)
+    // CELLS: (row = q, col = id, sim, 0) for sim >= min_sim and col >= col_min(q)
+    u32 col_mode;                  // 0: every column, 1: columns > q (strict triangle), 2: columns >= 256 * (q / 256)
+    u32 min_sim; uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
+    KR_DYN_SMEM(u32, smem_words, 16);
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 *tk = smem_words + (size_t)warp * (IXQ_SMEM_PER_WARP / 4);   // ids
+    u32 *ts = tk + IXQ_H;                                            // scores
+    u16 *tl = reinterpret_cast<u16 *>(ts + IXQ_H);                   // touched slots, in insertion order
+    u32 *tc = reinterpret_cast<u32 *>(tl + IXQ_H);                   // [0] = touched count, [1] = overflow flag
+    for (u32 i = lane; i < IXQ_H; i += 32) { tk[i] = IXQ_EMPTY; ts[i] = 0; }
+    if (lane == 0) { tc[0] = 0; tc[1] = 0; }
+    __syncwarp();
+    const bool ident_inf = (p.flags & 1u) != 0;
+    const IxGeom g = p.ix.g;
+    const int dshift = g.keybits - g.D;
+    const u64 idmask = (1ull << g.idbits) - 1;
+    const u32 nq = p.q_end - p.q_begin;
+    for (;;) {
+        u32 qi = 0;
+        if (lane == 0) qi = atomicAdd(p.next, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= nq) break;
+        const u32 q = p.q_begin + qi;
+        const SeqMeta qm = p.qmeta[q];
+        const u32 n = qm.size;
+        const u64 *kp = p.qkeys + p.qkoff[q];
+        unsigned long long bf = 0, bl = 0;   // ARGMAX: (score << 32) | ~rank  and  (score << 32) | rank
+        u32 col_min = 0;
+        if (MODE == IXQ_CELLS) col_min = p.col_mode == 1 ? q + 1 : p.col_mode == 2 ? (q & ~255u) : 0;
+        for (u32 npass = 1;; npass *= 4) {
+            bool redo = false;
+            bf = 0; bl = 0;
+            for (u32 pass = 0; pass < npass && !redo; ++pass) {
+                // ---- walk: every entry of the index that carries one of the query's keys scores its id -------------
+                for (u32 i = lane; i < n; i += 32) {
+                    const u64 hk = ix_hash(kp[i], g.keybits, g.keymask);
+                    const u32 b = (u32)(hk >> dshift);
+                    const u32 lo = __ldg(p.ix.dir + b), hi = __ldg(p.ix.dir + b + 1);
+                    for (u32 t = lo; t < hi; ++t) {
+                        const u64 e = __ldg(p.ix.ent + t);
+                        const u64 ek = e >> g.idbits;
+                        if (ek < hk) continue;
+                        if (ek > hk) break;
+                        const u32 id = (u32)(e & idmask);
+                        if (npass > 1 && (id % npass) != pass) continue;
+                        if (MODE == IXQ_CELLS && id < col_min && p.min_sim > 0) continue;   // a cell that is never emitted needs no score
+                        u32 h = (id * 0x9E3779B1u) >> 22;                                  // 10 bits: IXQ_H slots
+                        for (;;) {
+                            const u32 cur = tk[h];
+                            if (cur == id) break;
+                            if (cur == IXQ_EMPTY) {
+                                const u32 old = atomicCAS(&tk[h], IXQ_EMPTY, id);
+                                if (old == IXQ_EMPTY) {
+                                    const u32 pos = atomicAdd(&tc[0], 1u);
+                                    if (pos < IXQ_H) tl[pos] = (u16)h;
+                                    if (pos >= IXQ_FILL) tc[1] = 1;
+                                    break;
+                                }
+                                if (old == id) break;
+                            }
+                            h = (h + 1) & (IXQ_H - 1);
+                        }
+                        atomicAdd(&ts[h], 1u);
+                    }
+                    if (*reinterpret_cast<volatile u32 *>(&tc[1])) break;      // table nearly full: stop filling, redo in passes
+                }
+                __syncwarp();
+                const u32 T = min(tc[0], IXQ_H);
+                redo = tc[1] != 0;
+                // ---- epilogue over the touched slots (also clears them) ------------------------------------------
+                for (u32 t0 = 0; t0 < T; t0 += 32) {
+                    const u32 t = t0 + lane;
+                    u32 id = 0, sc = 0;
+                    if (t < T) { const u32 h = tl[t]; id = tk[h]; sc = ts[h]; tk[h] = IXQ_EMPTY; ts[h] = 0; }
+                    if (redo) continue;
+                    // the equal-sequence rule: only a sequence holding every key of the query can be identical
+                    if (ident_inf && t < T && sc == n) { const SeqMeta rm = p.rmeta[id]; if (rm.size == n && seq_equal(qm, rm)) sc = KR_INF; }
+                    if (MODE == IXQ_ARGMAX) {
+                        if (t < T && sc >= (u32)(bf >> 32)) {
+                            const u32 rk = p.rank[id];
+                            const unsigned long long cf = ((unsigned long long)sc << 32) | (0xFFFFFFFFu - rk);
+                            const unsigned long long cl = ((unsigned long long)sc << 32) | rk;
+                            bf = cf > bf ? cf : bf; bl = cl > bl ? cl : bl;
+                        }
+                    } else {
+                        const bool emit = t < T && sc >= p.min_sim && id >= col_min;
+                        const u32 bal = __ballot_sync(0xffffffffu, emit);
+                        if (bal) {
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(p.cells_count, (unsigned long long)__popc(bal));
+                            base = ((unsigned long long)__shfl_sync(0xffffffffu, (u32)(base >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)base, 0);
+                            const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
+                            if (emit && pos < p.cells_cap) p.cells[pos] = make_uint4(q, id, sc, 0u);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { tc[0] = 0; tc[1] = 0; }
+                __syncwarp();
+            }
+            if (!redo) break;
+            // cells already emitted by the passes before the overflowing one would be emitted again: CELLS redoes nothing
+            // that way -- an overflow is detected in pass 0 of npass == 1 before anything is emitted, and later pass
+            // counts are chosen so that no pass can overflow (see below)
+            if (npass >= (1u << 24)) break;   // cannot happen: a pass then holds at most one id
+        }
+        if (MODE == IXQ_ARGMAX) {
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long t1 = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (u32)(bf >> 32), o) << 32) | __shfl_xor_sync(0xffffffffu, (u32)bf, o);
+                const unsigned long long t2 = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (u32)(bl >> 32), o) << 32) | __shfl_xor_sync(0xffffffffu, (u32)bl, o);
+                bf = t1 > bf ? t1 : bf; bl = t2 > bl ? t2 : bl;
+            }
+            if (lane == 0) {
+                const int sim = (int)(bf >> 32);
+                p.partial[qi] = make_int4(sim, sim ? (int)(0xFFFFFFFFu - (u32)bf) : -1, sim ? (int)(u32)bl : 0, 0);
+            }
+        }
+    }
+}
+
+}  // namespace kr

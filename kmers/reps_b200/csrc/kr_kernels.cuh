@@ -90,7 +90,13 @@ struct BlockRef {    // one per block of 256 sequences
     u32 nseq;        // sequences in the block (<= 256)
 };
 
-struct ErrInfo { u32 flag, seq, pos, byte; };
+struct ErrInfo {       // device-side error record of a context, read back at the next host synchronisation
+    u32 flag, seq, pos, byte;   // K1: first residue outside the alphabet
+    u32 join_fault;             // K3: JOIN_FAULT_* (the launch finished early or skipped work; results are invalid)
+    u32 join_info[3];
+};
+constexpr u32 JOIN_FAULT_WATCHDOG = 1;   // an mbarrier wait did not complete (protocol bug / lost copy): CTA drained
+constexpr u32 JOIN_FAULT_ALIGN = 2;      // a block list handed to the kernel is not 16-byte aligned: job skipped, no copy issued
 
 
 // ---------------------------------------------------------------------------------------------
@@ -336,6 +342,20 @@ __global__ void k_import_refs(u32 nblk, u32 blk0, u32 seq0, u32 nseq_shard, cons
     r.seq0 = seq0 + b * TB; r.nseq = min((u32)TB, nseq_shard - b * TB);
     refs[blk0 + b] = r;
 }
+// layout rules of an exchanged shard, checked before anything is built from it (a violation would hand the tile join a
+// misaligned or out-of-range TMA source): block starts and chunk starts are multiples of CHUNK_ALIGN entries, chunk
+// starts ascend, every chunk fits its slot, and every block leaves TAILPAD entries inside the shard's arrays.
+// bad[0] = number of violating blocks, bad[1] = first one seen
+__global__ void k_validate_shard(u32 nblk, u64 entries, const u32 *choff, const u32 *chcnt, const u64 *blkbase, u32 *bad) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const u64 base = blkbase[b];
+    const u32 *o = choff + (size_t)b * (NCHUNK + 1), *c = chcnt + (size_t)b * NCHUNK;
+    bool ok = (base % CHUNK_ALIGN) == 0 && o[0] == 0;
+    for (int k = 0; k < NCHUNK && ok; ++k) ok = (o[k] % CHUNK_ALIGN) == 0 && o[k + 1] >= o[k] && c[k] <= o[k + 1] - o[k];
+    ok = ok && (o[NCHUNK] % CHUNK_ALIGN) == 0 && base + o[NCHUNK] + TAILPAD <= entries && blkbase[b + 1] >= base + o[NCHUNK] + TAILPAD;
+    if (!ok && atomicAdd(&bad[0], 1u) == 0u) bad[1] = b;
+}
 __global__ void k_import_meta(SeqMeta *meta, u32 n, const u8 *res, const u64 *off) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) meta[i].res = res + off[i];
@@ -355,9 +375,12 @@ __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { emu::mbar_init(
 __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) { emu::mbar_expect_tx(bar, bytes); }
 __device__ __forceinline__ void mbar_arrive_n(u64 *bar, u32 count) { emu::mbar_arrive(bar, count); }
 __device__ __forceinline__ void mbar_arrive(u64 *bar) { emu::mbar_arrive(bar, 1); }
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
-    for (u32 spins = 0; !emu::mbar_try_wait(bar, parity); ++spins) if (spins > (1u << 24)) __trap();
+__device__ __forceinline__ bool mbar_wait(u64 *bar, u32 parity, volatile u32 *abort_flag) {
+    for (u32 spins = 0; !emu::mbar_try_wait(bar, parity); ++spins)
+        if (*abort_flag || spins > (1u << 22)) { *abort_flag = 1; return false; }
+    return true;
 }
+__device__ __forceinline__ bool consumer_bar_or(bool pred) { return emu::named_barrier_or(1, NCWARP * 32, pred); }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) { emu::bulk_g2s(dst, src, bytes, bar); }
 __device__ __forceinline__ void consumer_bar();
 #else
@@ -375,28 +398,38 @@ __device__ __forceinline__ void mbar_arrive_n(u64 *bar, u32 count) {
 __device__ __forceinline__ void mbar_arrive(u64 *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Wait for the phase of the given parity.  try_wait suspends in hardware, so the loop turns slowly; a wait that
-// does not end within ~2^24 polls (seconds) is a protocol bug: trap (the launch fails) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+// Wait for the phase of the given parity.  try_wait suspends in hardware, so the loop turns slowly.  A wait that does
+// not end within WATCHDOG_NS is a protocol bug or a lost copy: it never traps (a trap is a device fault for the whole
+// process) -- it raises the CTA's abort flag and returns false; every other wait of the CTA then returns false at
+// once, the consumers leave together through consumer_bar_or() and the host reports JOIN_FAULT_WATCHDOG.
+constexpr unsigned long long WATCHDOG_NS = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ bool mbar_try(u32 addr, u32 parity) {
     u32 done;
-    const u32 addr = smem_u32(bar);
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
         "selp.u32 %0, 1, 0, P1;\n"
         "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) return;
+    return done != 0;
+}
+__device__ __noinline__ bool mbar_wait_slow(u32 addr, u32 parity, volatile u32 *abort_flag) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (u32 spins = 0;; ++spins) {
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return;
-        if (spins > (1u << 24)) __trap();
+        if (mbar_try(addr, parity)) return true;
+        if ((spins & 63) == 63) {
+            if (*abort_flag) return false;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > WATCHDOG_NS) { *abort_flag = 1; return false; }
+        }
     }
+}
+__device__ __forceinline__ bool mbar_wait(u64 *bar, u32 parity, volatile u32 *abort_flag) {
+    const u32 addr = smem_u32(bar);
+    if (mbar_try(addr, parity)) return true;
+    return mbar_wait_slow(addr, parity, abort_flag);
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -404,6 +437,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
                  : "memory");
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCWARP * 32) : "memory"); }
+// the same barrier, returning the OR of `pred` over all consumer threads (uniform: every thread gets the same answer)
+__device__ __forceinline__ bool consumer_bar_or(bool pred) {
+    u32 r;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1, P2;\n"
+        "setp.ne.u32 P1, %1, 0;\n"
+        "barrier.cta.red.or.pred P2, 1, %2, P1;\n"
+        "selp.u32 %0, 1, 0, P2;\n"
+        "}\n" : "=r"(r) : "r"((u32)pred), "n"(NCWARP * 32) : "memory");
+    return r != 0;
+}
 #endif
 #ifdef KR_EMUL
 __device__ __forceinline__ void consumer_bar() { emu::named_barrier(1, NCWARP * 32); }
@@ -420,6 +465,7 @@ struct JoinParams {
     u32 nBblk;
     const uint2 *tasks; u32 ntasks;   // MATRIX: (I, J).  ARGMAX: (I, split)
     u32 flags;               // KR_IDENT_IS_INFINITY
+    ErrInfo *err;            // the context's device-side error record (join_fault)
     // MATRIX
     void *out; u32 elem, layout; u64 origin;
     // ARGMAX
@@ -437,11 +483,16 @@ __device__ __forceinline__ u64 cell_index(u32 layout, u64 i, u64 j, u64 nrows, u
     return 256ull * (I * nrows - 128ull * I * (I - 1)) + (i - c0) * (nrows - c0) + (j - c0);
 }
 
-__device__ __noinline__ bool seq_equal(const SeqMeta &a, const SeqMeta &b) {
+// byte compare of two stored sequences of the same length (the rare exact step of the equal-sequence rule)
+__device__ __noinline__ bool res_equal(const u8 *a, const u8 *b, u32 len) {
+    for (u32 i = 0; i < len; ++i) if (a[i] != b[i]) return false;
+    return true;
+}
+// arguments by value: taking SeqMeta by reference put the records on the local stack of every caller
+__device__ __forceinline__ bool seq_equal(const SeqMeta a, const SeqMeta b) {
     if (a.len != b.len || a.hash != b.hash) return false;
     if (a.res == b.res) return true;   // the same stored sequence (diagonal cells)
-    for (u32 i = 0; i < a.len; ++i) if (a.res[i] != b.res[i]) return false;
-    return true;
+    return res_equal(a.res, b.res, a.len);
 }
 
 #ifdef KR_EMUL
@@ -542,9 +593,12 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
     u64 *full = reinterpret_cast<u64 *>(smem + JOIN_SMEM_CNT + (size_t)NST * STAGE_B);
     u64 *empty = full + NST;
     uint4 *desc = reinterpret_cast<uint4 *>(empty + NST);   // 2*NST barriers of 8 bytes: 16-byte aligned
+    volatile u32 *s_abort = reinterpret_cast<volatile u32 *>(desc + NST);   // raised by a wait that timed out (see mbar_wait)
+    static_assert(2 * NST * 8 + NST * 16 + 4 <= 256, "barriers, descriptors and the abort flag live in the last 256 bytes");
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
+        *s_abort = 0;
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCWARP); }
 #ifndef KR_EMUL
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -557,25 +611,41 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
     if (warp == NCWARP) {
         // ================================ producer ================================================
         u32 k = 0;
+        bool alive = true;       // false once a wait of this CTA timed out: nothing more is published
         auto emit = [&](u32 na, u32 nb, u32 flags, u32 J, const BlockRef &a, const BlockRef &b, u32 posA, u32 posB) {
             const u32 s = k % NST, ph = (k / NST) & 1;
-            if (lane == 0) {
+            if (lane == 0 && alive) {
                 u8 *st = stage + (size_t)s * STAGE_B;
-                mbar_wait(&empty[s], ph ^ 1);
-                desc[s] = make_uint4(na, nb, flags, J);
-#if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 4)
-                if (p.nA != 0xFFFFFFFFu) { mbar_arrive(&full[s]); } else
-#endif
-                if (na && !(flags & 1u)) {
-                    const u32 bAhi = ((na + 3) & ~3u) * 4, bAlo = LO32 ? ((na + 3) & ~3u) * 4 : ((na + 7) & ~7u) * 2;
-                    const u32 bBlo = LO32 ? ((nb + 3) & ~3u) * 4 : ((nb + 7) & ~7u) * 2;
-                    mbar_expect_tx(&full[s], bAhi + WINDOW * 4 + bAlo + bBlo);
-                    bulk_g2s(st, a.hi + posA, bAhi, &full[s]);
-                    bulk_g2s(st + OFF_BHI, b.hi + posB, WINDOW * 4, &full[s]);
-                    bulk_g2s(st + OFF_ALO, (const u8 *)a.lo + (size_t)posA * LOSZ, bAlo, &full[s]);
-                    bulk_g2s(st + OFF_BLO, (const u8 *)b.lo + (size_t)posB * LOSZ, bBlo, &full[s]);
+                if (!mbar_wait(&empty[s], ph ^ 1, s_abort)) {
+                    alive = false;
+                    if (atomicCAS(&p.err->join_fault, 0u, JOIN_FAULT_WATCHDOG) == 0u) { p.err->join_info[0] = blockIdx.x; p.err->join_info[1] = k; }
                 } else {
-                    mbar_arrive(&full[s]);
+                    const u8 *gAhi = reinterpret_cast<const u8 *>(a.hi + posA), *gBhi = reinterpret_cast<const u8 *>(b.hi + posB);
+                    const u8 *gAlo = (const u8 *)a.lo + (size_t)posA * LOSZ, *gBlo = (const u8 *)b.lo + (size_t)posB * LOSZ;
+                    // cp.async.bulk needs 16-byte aligned sources; a misaligned source is a device fault, so a block list that
+                    // breaks the layout rule (kr_seqset_import_blocklists checks it too) is skipped and reported instead
+                    const bool copy = na && !(flags & 1u);
+                    const bool aligned = ((reinterpret_cast<uintptr_t>(gAhi) | reinterpret_cast<uintptr_t>(gBhi) |
+                                           reinterpret_cast<uintptr_t>(gAlo) | reinterpret_cast<uintptr_t>(gBlo)) & 15) == 0;
+                    if (copy && !aligned) {
+                        if (atomicCAS(&p.err->join_fault, 0u, JOIN_FAULT_ALIGN) == 0u) { p.err->join_info[0] = blockIdx.x; p.err->join_info[1] = posA; p.err->join_info[2] = posB; }
+                        na = 0; nb = 0;
+                    }
+                    desc[s] = make_uint4(na, nb, flags, J);
+#if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 4)
+                    if (p.nA != 0xFFFFFFFFu) { mbar_arrive(&full[s]); } else
+#endif
+                    if (copy && aligned) {
+                        const u32 bAhi = ((na + 3) & ~3u) * 4, bAlo = LO32 ? ((na + 3) & ~3u) * 4 : ((na + 7) & ~7u) * 2;
+                        const u32 bBlo = LO32 ? ((nb + 3) & ~3u) * 4 : ((nb + 7) & ~7u) * 2;
+                        mbar_expect_tx(&full[s], bAhi + WINDOW * 4 + bAlo + bBlo);
+                        bulk_g2s(st, gAhi, bAhi, &full[s]);
+                        bulk_g2s(st + OFF_BHI, gBhi, WINDOW * 4, &full[s]);
+                        bulk_g2s(st + OFF_ALO, gAlo, bAlo, &full[s]);
+                        bulk_g2s(st + OFF_BLO, gBlo, bBlo, &full[s]);
+                    } else {
+                        mbar_arrive(&full[s]);
+                    }
                 }
             }
             ++k;
@@ -585,6 +655,7 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
         constexpr int HI = NCHUNK > 32 ? 32 : 0;   // offset of the second table register (unused for 32 chunks)
         BlockRef a{}, b{};
         for (u32 task = blockIdx.x; task < p.ntasks; task += gridDim.x) {
+            if (!__shfl_sync(0xffffffffu, (u32)alive, 0)) return;   // the CTA is draining after a watchdog timeout
             const uint2 tk = p.tasks[task];
             u32 j0, j1;
             if (MODE != MODE_ARGMAX) { j0 = tk.y; j1 = tk.y + 1; }
@@ -626,22 +697,24 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
     const u32 grp = warp / GW, gw = warp % GW;
     // ARGMAX: row r of the tile is owned by warp r%NCWARP, its running best lives in lane r/NCWARP
     int best_sim = 0; u32 best_first = 0xFFFFFFFFu, best_last = 0;
+    bool dead = false;           // a wait of this warp (or of another warp of the CTA) timed out
     for (;;) {
         // head slot of the next tile: read by every consumer warp
-        uint4 d;
+        uint4 d = make_uint4(0, 0, 0, 0);
         {
             const u32 s = k % NST, ph = (k / NST) & 1;
-            mbar_wait(&full[s], ph);
-            d = desc[s];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (mbar_wait(&full[s], ph, s_abort)) {
+                d = desc[s];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            } else dead = true;
             ++k;
         }
-        if (d.z & JF_DONE) break;
         // this group's jobs of the tile
+        if (!dead && !(d.z & JF_DONE))
         for (u32 r = grp; r < d.x; r += NGROUP) {
             const u32 kk = k + r, s = kk % NST, ph = (kk / NST) & 1;
-            mbar_wait(&full[s], ph);
+            if (!mbar_wait(&full[s], ph, s_abort)) { dead = true; break; }
             const uint4 dj = desc[s];
             const u32 sb = smem_u32(stage + (size_t)s * STAGE_B);
 #if defined(KR_DEBUG_KNOBS) && (KR_DEBUG_KNOBS & 1)
@@ -653,6 +726,12 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
             if (lane == 0) mbar_arrive_n(&empty[s], NGROUP);   // the GW owners stand in for all NCWARP warps
         }
         k += d.x;
+        // every consumer warp meets here once per head slot, whatever happened to it above, and all of them take the same
+        // decision: leave (end of work, or a timed-out wait anywhere in the CTA) or run the epilogue
+        if (consumer_bar_or(dead || (d.z & JF_DONE))) {
+            if (dead && lane == 0 && atomicCAS(&p.err->join_fault, 0u, JOIN_FAULT_WATCHDOG) == 0u) { p.err->join_info[0] = blockIdx.x; p.err->join_info[1] = k; }
+            break;
+        }
 
         // ---- epilogue of tile (I,J) ----------------------------------------------------------
         const BlockRef a = p.A[p.tasks[task].x];
@@ -661,7 +740,6 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
         // sizes of this warp's rows, one per lane (row warp + NCWARP*lane), fetched together
         u32 my_szA = 0;
         if (ident_inf && warp + NCWARP * lane < a.nseq) my_szA = p.metaA[a.seq0 + warp + NCWARP * lane].size;
-        consumer_bar();
         for (u32 row = warp; row < a.nseq; row += NCWARP) {
             uint4 *rp = reinterpret_cast<uint4 *>(cnt + row * (TB / 2)) + lane;
             uint4 v = *rp;

@@ -127,6 +127,8 @@ struct Block {
     Barrier sync;
     std::vector<std::unique_ptr<Warp>> warps;
     std::map<int, std::unique_ptr<Barrier>> named;
+    struct Vote { unsigned acc[2] = {0, 0}, arrived = 0, gen = 0; };
+    std::map<int, Vote> votes;
     explicit Block(unsigned n) : nthreads(n), sync(n) {
         for (unsigned w = 0; w * 32 < n; ++w) warps.emplace_back(new Warp(std::min(32u, n - w * 32)));
     }
@@ -305,6 +307,16 @@ inline void named_barrier(int id, unsigned count) {
     { auto &slot = blk->named[id]; if (!slot) slot.reset(new Barrier(count)); b = slot.get(); }
     b->arrive_and_wait();
 }
+// barrier.cta.red.or.pred: the same barrier with an OR reduction of a predicate; every thread gets the same answer
+inline bool named_barrier_or(int id, unsigned count, bool pred) {
+    Block *blk = cur_block();
+    Block::Vote &v = blk->votes[id];
+    const unsigned g = v.gen & 1;
+    if (pred) v.acc[g] = 1;
+    if (++v.arrived == count) { v.arrived = 0; ++v.gen; v.acc[v.gen & 1] = 0; }   // the last arriver opens the next generation
+    named_barrier(id, count);
+    return v.acc[g] != 0;
+}
 // shared-memory "addresses" are offsets into the dynamic buffer (+ a bias so that 0 is never valid)
 inline uint32_t smem_addr(const void *p) {
     const uint8_t *q = (const uint8_t *)p;
@@ -322,7 +334,10 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorEmul = 1 };
 typedef struct CUstream_st { int id; } *cudaStream_t;
 typedef struct CUevent_st { std::chrono::steady_clock::time_point t; } *cudaEvent_t;
-typedef int cudaMemPool_t;
+typedef struct CUmempool_st { int id; } *cudaMemPool_t;
+enum { cudaMemAllocationTypePinned = 1, cudaMemLocationTypeDevice = 1 };
+struct cudaMemLocation { int type = 0, id = 0; };
+struct cudaMemPoolProps { int allocType = 0; cudaMemLocation location; };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyHostToHost };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaMemPoolAttrReleaseThreshold = 4,
        cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
@@ -342,13 +357,15 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSucces
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
-inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t *p, int) { *p = 0; return cudaSuccess; }
+inline cudaError_t cudaMemPoolCreate(cudaMemPool_t *p, const cudaMemPoolProps *) { *p = new CUmempool_st{1}; return cudaSuccess; }
+inline cudaError_t cudaMemPoolDestroy(cudaMemPool_t p) { delete p; return cudaSuccess; }
 inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 // allocations are 256-byte aligned like cudaMalloc's and poisoned so that reads of uninitialised device memory show
 inline cudaError_t cudaMalloc(void **p, size_t n) { if (posix_memalign(p, 256, n ? n : 1)) return cudaErrorEmul; memset(*p, 0xCD, n); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+inline cudaError_t cudaMallocFromPoolAsync(void **p, size_t n, cudaMemPool_t, cudaStream_t) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
 inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorEmul; }

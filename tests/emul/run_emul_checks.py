@@ -124,6 +124,13 @@ def case_subchunks():
     c.close()
 
 
+def _clone(bl):
+    c = kr.BlockLists()
+    for name, _ in kr.BlockLists._fields_:
+        setattr(c, name, getattr(bl, name))
+    return c
+
+
 def case_sharded_import():
     """export / import of block lists (the N > 1 encode): two and three shards re-assembled into one set"""
     seqs = family(14, 700, 9, 40, 90)
@@ -144,6 +151,27 @@ def case_sharded_import():
         full = c.import_blocklists(shards, res.ctypes.data, off)
         got = c.sim_matrix(full, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI)
         assert (got == blocktri(want)).all(), world
+    # shards that break the 16-byte rules of the TMA copies are refused (KR_ERR_ARG), nothing is launched on them
+    import ctypes
+    bad = [_clone(x) for x in shards]
+    bad[1].hi = shards[1].hi + 4
+    try:
+        c.import_blocklists(bad, res.ctypes.data, off)
+        raise AssertionError("misaligned hi accepted")
+    except kr.KrError as e:
+        assert e.code == -1 and "aligned" in str(e), e
+    nb = shards[1].nblk + 1
+    base = np.ctypeslib.as_array((ctypes.c_uint64 * nb).from_address(shards[1].blk_base)).copy()
+    base += 4
+    bad = [_clone(x) for x in shards]
+    bad[1].blk_base = base.ctypes.data
+    try:
+        c.import_blocklists(bad, res.ctypes.data, off)
+        raise AssertionError("misaligned block start accepted")
+    except kr.KrError as e:
+        assert e.code == -1 and "layout" in str(e), e
+    full = c.import_blocklists(shards, res.ctypes.data, off)
+    assert (c.sim_matrix(full, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all()
     c.close()
 
 

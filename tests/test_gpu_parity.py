@@ -407,3 +407,77 @@ def test_greedy_build_sharded_driver_on_one_gpu(oracle):
     _, want, _ = oracle.greedy_build(oracle.batch(res=res, off=off, K=8), 50, ident_inf=True)
     assert (added == want).all()
     c.close()
+
+
+def _clone(bl):
+    c = kr.BlockLists()
+    for name, _ in kr.BlockLists._fields_:
+        setattr(c, name, getattr(bl, name))
+    return c
+
+
+def _export_shards(c, d_res, off, nshards):
+    """encode the batch in `nshards` slices cut at block boundaries and export each slice's block lists (one GPU, no NCCL)"""
+    from kmers.reps_b200 import sharding
+    cuts = sharding.block_shards(len(off) - 1, nshards)
+    parts, shards = [], []
+    for k in range(nshards):
+        lo, hi = cuts[k], cuts[k + 1]
+        p = c.encode_device(d_res.data_ptr() + int(off[lo]), off[lo: hi + 1] - off[lo])
+        bl = c.export_blocklists(p)
+        assert bl.entries <= c.blocklist_capacity(off[lo: hi + 1])
+        parts.append(p)
+        shards.append(bl)
+    return parts, shards
+
+
+def test_shard_import_single_process(ctx, oracle):
+    """the N-GPU block-list exchange without NCCL: 2, 4 and 8 artificial shards (ragged last block) are imported on ONE
+    GPU and joined; every cell equals the oracle's and the plain encode's.  This is the path whose misaligned shard
+    starts faulted in round 1: it must be exercised (under compute-sanitizer too) before any multi-GPU run."""
+    import torch
+    res, off, _ = synth.generate(0x5EED0011, 3000 + 37, 60)
+    seqs = synth.to_strings(res, off)
+    want = oracle.sim_matrix(oracle.batch(seqs, K=8), ident_inf=True, threads=8)
+    d_res = torch.from_numpy(res).cuda()
+    plain = ctx.sim_matrix(ctx.encode(res=res, off=off), elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL)
+    assert (plain == want).all()
+    for nshards in (2, 4, 8):
+        parts, shards = _export_shards(ctx, d_res, off, nshards)
+        full = ctx.import_blocklists(shards, d_res.data_ptr(), off)
+        got = ctx.sim_matrix(full, elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL)
+        assert (got == want).all(), nshards
+        bt = ctx.sim_matrix(full, elem=kr.ELEM_I32, layout=kr.LAYOUT_BLOCKTRI, row_begin=1024, row_end=len(seqs))
+        assert (bt == np.concatenate([want[i, 256 * (i // 256):] for i in range(1024, len(seqs))])).all(), nshards
+        full.free()
+        for p in parts:
+            p.free()
+
+
+def test_shard_import_rejects_bad_layout(ctx):
+    """a shard whose arrays break the 16-byte rules of the TMA copies is refused with KR_ERR_ARG; nothing is launched on it"""
+    import torch
+    res, off, _ = synth.generate(0x5EED0012, 600, 12)
+    d_res = torch.from_numpy(res).cuda()
+    parts, shards = _export_shards(ctx, d_res, off, 2)
+    bad = [_clone(s) for s in shards]
+    bad[1].hi = shards[1].hi + 4                                  # misaligned array start
+    with pytest.raises(kr.KrError) as e:
+        ctx.import_blocklists(bad, d_res.data_ptr(), off)
+    assert e.value.code == -1 and "aligned" in str(e.value)
+    # misaligned block start inside an aligned array: caught by the device-side layout check
+    from kmers.reps_b200 import sharding
+    nb = shards[1].nblk + 1
+    base = sharding._view(shards[1].blk_base, nb * 8, d_res.device).view(torch.int64).clone()
+    base += 4
+    torch.cuda.synchronize()
+    bad = [_clone(s) for s in shards]
+    bad[1].blk_base = base.data_ptr()
+    with pytest.raises(kr.KrError) as e:
+        ctx.import_blocklists(bad, d_res.data_ptr(), off)
+    assert e.value.code == -1 and "layout" in str(e.value)
+    # the context is still healthy afterwards
+    ok = ctx.import_blocklists(shards, d_res.data_ptr(), off)
+    assert ctx.sim_matrix(ok, elem=kr.ELEM_U16).shape == (600, 600)
+    for p in parts:
+        p.free()
