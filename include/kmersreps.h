@@ -56,8 +56,10 @@ typedef int32_t kr_status;
 /* context flags (policy switches for the semantics SURVEY.md 8c could not verify against a JVM) */
 #define KR_IDENT_IS_INFINITY 1u /* similarity of two equal sequences is KR_INFINITY, not the raw count */
 #define KR_TIE_LAST 2u          /* findClosest keeps the last maximum in iteration order, not the first */
-/* findClosest has two exact device paths: the tile join (any size) and the inverted index (large query
- * batches).  The library picks by batch size; these flags pin one of them (used by the parity tests). */
+/* Similarity matrices, findClosest and the greedy build each have two exact device paths: the tile join (work
+ * proportional to the number of pairs; any set) and the sorted inverted index with its warp-per-query scan (work
+ * proportional to the k-mers the pairs share; sets that keep key lists, 5K + id bits <= 64).  The library picks per
+ * call from the index's posting-list statistics; these flags pin one path (the parity tests run both). */
 #define KR_FORCE_JOIN 4u
 #define KR_FORCE_INDEX 8u
 
@@ -71,8 +73,7 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out);
 void kr_destroy(kr_ctx *ctx);
 const char *kr_last_error(const kr_ctx *ctx);
 int kr_kmer_size(const kr_ctx *ctx);
-/* which build of the library this is: "default" (the hardware-verified paths only), "experimental" (further entry points
- * and context flags compiled in, off unless asked for) or "v2" (those paths are every context's default) */
+/* build tag of the library ("default": there is one build) */
 const char *kr_build_info(void);
 /* block until every kernel and copy the context issued has finished */
 kr_status kr_synchronize(kr_ctx *ctx);
@@ -164,6 +165,19 @@ kr_status kr_matrix_stripes(uint32_t n_rows, uint32_t n_cols, uint32_t layout, u
 kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, void *out_host);
 kr_status kr_sim_matrix_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, void *out_dev);
 
+/* The same matrix as a list of its cells with sim >= min_sim (min_sim >= 1): four uint32 per cell -- row, column,
+ * similarity, 0 -- in no particular order.  Layout FULL: every column; TRIANGLE (self only): columns j > i.  All other
+ * cells are 0 by definition, so the callers that walk the whole matrix (DistanceMatrixProcessor.java:71-83 prints every
+ * pair, SequenceInfo.java:62-89 sums every distance) regenerate the zero cells on the host in the reference's order
+ * instead of moving N^2 values over PCIe.  *count receives the number of qualifying cells even when it exceeds
+ * `cap`; then only `cap` cells are returned and the status is KR_ERR_ARG (call again with room). */
+kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                               uint32_t *cells_host, uint64_t cap, uint64_t *count);
+/* same, cells left in device memory (16 bytes each; used by the multi-GPU result gather); synchronises the host to
+ * return the count */
+kr_status kr_sim_matrix_sparse_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                                      void *cells_dev, uint64_t cap, uint64_t *count);
+
 /* ---- RepGenomeDb ---------------------------------------------------------------------------
  * Replaces the representative store of RepGenomeDb: new RepGenomeDb(threshold, protName)
  * (RepGenomeDbProcessor.java:122), addRep (BaseGenomeProcessor.java:172-176,204),
@@ -208,10 +222,14 @@ typedef struct kr_stats {
     uint64_t pairs;           /* sequence pairs whose similarity was produced */
     double encode_ms;         /* encode + per-sequence sort/dedupe kernels (device time) */
     double blocklist_ms;      /* block key-list build kernels */
-    double join_ms;           /* tile join kernels (matrix / argmax) */
-    double other_ms;          /* pair, merge and bookkeeping kernels */
+    double join_ms;           /* tile join kernels (matrix / argmax / sparse) */
+    double other_ms;          /* pair, merge, zero-fill and bookkeeping kernels */
     uint64_t join_launches;
     uint64_t h2d_bytes, d2h_bytes;
+    double index_ms;          /* sorted-index build kernels (partition, sort, directory) */
+    double scan_ms;           /* index scan kernels (argmax / cells / dense cells) */
+    uint64_t scan_launches;   /* index scans launched: tells which path served a call */
+    uint64_t index_builds;
 } kr_stats;
 kr_status kr_stats_get(kr_ctx *ctx, kr_stats *out); /* synchronises the context's stream */
 kr_status kr_stats_reset(kr_ctx *ctx);

@@ -13,13 +13,6 @@ IDENT_IS_INFINITY = 1
 TIE_LAST = 2
 FORCE_JOIN = 4
 FORCE_INDEX = 8
-EXP_PAIRS = 0x100        # experimental builds only: self matrices through the posting-list path
-EXP_PAIRS_AUTO = 0x200   # ... only when its work estimate beats the tile join's
-EXP_ENCODE = 0x400       # experimental builds only: K1 with one warp per sequence
-EXP_IDXQ = 0x800         # experimental builds only: K5 with one warp per query where it pays
-EXP_BUCKETS = 0x2000     # experimental builds only: posting-list path groups by key in shared memory (bucket partition)
-ALPHABET_DNA = 0x4000    # experimental builds only: DnaKmers contexts (K-mers of both strands, K = 5..18)
-EXP_GIDX = 0x1000        # experimental builds only: greedy build scores candidates through a growing index
 ELEM_I32, ELEM_U16 = 0, 1
 LAYOUT_FULL, LAYOUT_TRIANGLE, LAYOUT_BLOCKTRI = 0, 1, 2
 TILE = 256
@@ -29,6 +22,7 @@ SYMBOLS = [
     "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_build_info", "kr_synchronize", "kr_encode", "kr_encode_device",
     "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_blocklist_capacity", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
     "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
+    "kr_sim_matrix_sparse", "kr_sim_matrix_sparse_device",
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
     "kr_db_find_closest", "kr_db_find_closest_device", "kr_db_any_ge", "kr_greedy_build", "kr_stats_get",
     "kr_stats_reset", "kr_timer_begin", "kr_timer_end", "kr_host_alloc", "kr_host_free",
@@ -57,14 +51,11 @@ class BlockLists(C.Structure):
                 "blk_base": (self.blk_base, (self.nblk + 1) * 8), "meta": (self.meta, self.nseq * 24)}
 
 
-class KeyLists(C.Structure):   # experimental builds: kr_seqset_export_keys / kr_seqset_import_keys
-    _fields_ = [("nseq", C.c_uint32), ("capacity", C.c_uint64), ("keys", C.c_void_p), ("meta", C.c_void_p)]
-
-
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs", C.c_uint64), ("encode_ms", C.c_double),
                 ("blocklist_ms", C.c_double), ("join_ms", C.c_double), ("other_ms", C.c_double),
-                ("join_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("join_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("index_ms", C.c_double), ("scan_ms", C.c_double), ("scan_launches", C.c_uint64), ("index_builds", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -139,29 +130,13 @@ def load_library():
     lib.kr_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.kr_host_free.argtypes = [vp, vp]
     lib.kr_host_free.restype = None
-    # experimental entry points exist only in builds made with -DKR_EXPERIMENTAL (never the default library)
-    if hasattr(lib, "kr_sim_matrix_sparse"):
-        lib.kr_sim_matrix_sparse.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
-    if hasattr(lib, "kr_seqset_import_keys"):
-        lib.kr_keylist_capacity.argtypes = [vp, vp, u32]
-        lib.kr_keylist_capacity.restype = u64
-        lib.kr_seqset_export_keys.argtypes = [vp, vp, C.POINTER(KeyLists)]
-        lib.kr_seqset_import_keys.argtypes = [vp, C.POINTER(KeyLists), u32, vp, vp, u32, C.POINTER(vp)]
-    if hasattr(lib, "kr_pairs_partial"):
-        lib.kr_pairs_partial.argtypes = [vp, vp, u32, u32, vp, C.POINTER(vp), vp]
-        lib.kr_pairs_partial_free.argtypes = [vp, vp]
-        lib.kr_pairs_partial_free.restype = None
-        lib.kr_pairs_apply.argtypes = [vp, vp, C.POINTER(MatrixDesc), vp, u64, vp]
+    lib.kr_sim_matrix_sparse.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
+    lib.kr_sim_matrix_sparse_device.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
     _LIB = lib
     return lib
 
 
-def has_experimental() -> bool:
-    return hasattr(load_library(), "kr_sim_matrix_sparse")
-
-
 def build_info() -> str:
-    """'default', 'experimental' or 'v2' (experimental paths are every context's default)"""
     return load_library().kr_build_info().decode()
 
 
@@ -261,40 +236,6 @@ class Context:
         self._ck(self.lib.kr_seqset_import_blocklists(self.h, arr, len(shards), d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
         return SeqSet(self, h)
 
-    # ---- experimental builds only -----------------------------------------------------------------
-    def keylist_capacity(self, off) -> int:
-        off = np.ascontiguousarray(off, dtype=np.uint64)
-        return int(self.lib.kr_keylist_capacity(self.h, off.ctypes.data, len(off) - 1))
-
-    def export_keys(self, s: "SeqSet") -> KeyLists:
-        k = KeyLists()
-        self._ck(self.lib.kr_seqset_export_keys(self.h, s.h, C.byref(k)))
-        return k
-
-    def import_keys(self, shards, d_res_ptr: int, off) -> "SeqSet":
-        off = np.ascontiguousarray(off, dtype=np.uint64)
-        arr = (KeyLists * len(shards))(*shards)
-        h = C.c_void_p()
-        self._ck(self.lib.kr_seqset_import_keys(self.h, arr, len(shards), d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
-        return SeqSet(self, h)
-
-    def pairs_partial(self, s: "SeqSet", part: int, nparts: int, row_bounds):
-        """-> (device pointer to the uint4 cells grouped by destination, per-destination cell counts)"""
-        rb = np.ascontiguousarray(row_bounds, dtype=np.uint32)
-        counts = np.zeros(nparts, dtype=np.uint64)
-        cells = C.c_void_p()
-        self._ck(self.lib.kr_pairs_partial(self.h, s.h, part, nparts, rb.ctypes.data, C.byref(cells), counts.ctypes.data))
-        return cells.value or 0, counts
-
-    def pairs_partial_free(self, d_cells: int):
-        if d_cells:
-            self.lib.kr_pairs_partial_free(self.h, d_cells)
-
-    def pairs_apply(self, s: "SeqSet", d_cells: int, ncells: int, d_out_ptr: int, elem=ELEM_U16, layout=LAYOUT_BLOCKTRI, row_begin=0, row_end=None):
-        row_end = s.count if row_end is None else row_end
-        d = MatrixDesc(elem, layout, row_begin, row_end)
-        self._ck(self.lib.kr_pairs_apply(self.h, s.h, C.byref(d), d_cells, int(ncells), d_out_ptr))
-
     def key_decode(self, key: int) -> str:
         buf = C.create_string_buffer(self.K)
         self._ck(self.lib.kr_key_decode(self.h, int(key), buf))
@@ -323,7 +264,7 @@ class Context:
         return out
 
     def sim_matrix_sparse(self, A: "SeqSet", B: "SeqSet" = None, min_sim=1, layout=LAYOUT_TRIANGLE, row_begin=0, row_end=None, cap=1 << 22, out=None):
-        """EXPERIMENTAL build only: cells (row, col, sim) with sim >= min_sim, unordered, as an (n, 4) uint32 array"""
+        """the cells (row, col, sim, 0) with sim >= min_sim, unordered, as an (n, 4) uint32 array"""
         row_end = A.count if row_end is None else row_end
         d = MatrixDesc(ELEM_I32, layout, row_begin, row_end)
         while True:
@@ -335,6 +276,14 @@ class Context:
             if n.value <= len(cells) or out is not None:
                 self._ck(rc)
             cap = int(n.value)                     # the library reported how many cells qualify: retry with room
+
+    def sim_matrix_sparse_device(self, A: "SeqSet", B, d_cells_ptr: int, cap: int, min_sim=1, layout=LAYOUT_TRIANGLE, row_begin=0, row_end=None) -> int:
+        """same, cells left in device memory (16 bytes each); returns how many qualify"""
+        row_end = A.count if row_end is None else row_end
+        d = MatrixDesc(ELEM_I32, layout, row_begin, row_end)
+        n = C.c_uint64(0)
+        self._ck(self.lib.kr_sim_matrix_sparse_device(self.h, A.h, None if B is None else B.h, C.byref(d), int(min_sim), d_cells_ptr, int(cap), C.byref(n)))
+        return int(n.value)
 
     def sim_matrix_device(self, A, B, d_out_ptr: int, elem=ELEM_U16, layout=LAYOUT_FULL, row_begin=0, row_end=None):
         row_end = A.count if row_end is None else row_end

@@ -3,21 +3,8 @@
 // that produces a similarity launches a kernel on the context's GPU.
 #include "../../../include/kmersreps.h"
 #include "kr_kernels.cuh"
-#ifdef KR_EXPERIMENTAL
-#include "kr_pairs.cuh"
-#include "kr_encode2.cuh"
-#define KR_EXP_ENCODE 0x400u       /* context flag (experimental builds): K1 with one warp per sequence */
-#include "kr_idxq2.cuh"
-#define KR_EXP_IDXQ 0x800u         /* context flag (experimental builds): K5 with one warp per query where it pays */
-#include "kr_gidx.cuh"
-#include "kr_dna.cuh"
-#define KR_ALPHABET_DNA 0x4000u    /* context flag (experimental builds): DnaKmers -- K-mers of both strands, K = 5..18 */
-#define KR_EXP_GIDX 0x1000u        /* context flag (experimental builds): greedy build scores candidates through a growing index */
-#define KR_EXP_PAIRS 0x100u        /* context flag (experimental builds): self matrices through the posting-list path */
-#define KR_EXP_PAIRS_AUTO 0x200u   /* ... only when its work estimate beats the tile join's */
-#define KR_LEGACY_PATHS 0x8000u    /* with -DKR_DEFAULTS_V2: keep this context on the hardware-verified round-1 paths */
-#define KR_EXP_BUCKETS 0x2000u     /* posting-list path: group by key in shared memory after a bucket partition (no HBM hash table) */
-#endif
+#include "kr_encode.cuh"
+#include "kr_index.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -44,7 +31,7 @@ using namespace kr;
 static thread_local std::string g_create_error;
 
 struct EvPair { cudaEvent_t a, b; int stage; };
-enum { ST_ENCODE = 0, ST_BLOCKLIST = 1, ST_JOIN = 2, ST_OTHER = 3 };
+enum { ST_ENCODE = 0, ST_BLOCKLIST = 1, ST_JOIN = 2, ST_OTHER = 3, ST_INDEX = 4, ST_SCAN = 5 };
 
 struct DevMem {   // refcounted device allocation (residue buffers are shared by gathered sets)
     void *p = nullptr;
@@ -54,7 +41,6 @@ struct DevMem {   // refcounted device allocation (residue buffers are shared by
 static cudaError_t pool_alloc(struct kr_ctx *ctx, void **p, size_t bytes);
 
 struct kr_ctx {
-    int dnaK = 0;   // experimental DNA contexts: the DNA k-mer size (K below is then the key width in 5-bit units)
     int dev = 0, K = 8;
     u32 flags = 0;
     int num_sms = 0;
@@ -90,26 +76,12 @@ struct kr_seqset {
     u32 *d_hi = nullptr; void *d_lo = nullptr; u32 *d_choff = nullptr, *d_chcnt = nullptr; u64 *d_blkbase = nullptr;
     BlockRef *d_refs = nullptr;
     std::vector<std::shared_ptr<DevMem>> keep;   // parents' residue buffers
-#ifdef KR_EXPERIMENTAL
-    // posting lists of the whole set (experimental all-vs-all path), built on first use
-    bool px_ready = false; u64 px_slots = 0;
-    unsigned long long *px_key = nullptr; u32 *px_off = nullptr, *px_cnt = nullptr, *px_post = nullptr;
-    unsigned long long px_work = ~0ull;   // sum of m(m-1)/2, once known
-    unsigned long long px_work_est = ~0ull;   // the same from every 8th bucket, times 8 (enough to choose a path)
-    // the same entries partitioned into buckets by key hash (KR_EXP_BUCKETS)
-    bool bk_ready = false; u32 bk_nb = 0;
-    u32 *bk_base = nullptr, *bk_eseq = nullptr, *bk_post = nullptr; u64 *bk_ekey = nullptr;
-#endif
+    // sorted inverted index over the set's own sequences (built on first use by a matrix scan), and its k-mer-less sequences
+    struct IndexOwned *ix = nullptr;
+    u32 *d_empty = nullptr, *d_nempty = nullptr;
 };
 
 struct DbSegment { kr_seqset *set; u32 base; };
-struct DbIndexSlab {   // inverted index over representatives [base, base + n)
-    u32 base = 0, n = 0, mask = 0;
-    unsigned long long *tab_key = nullptr; u32 *tab_off = nullptr, *tab_cnt = nullptr, *postings = nullptr;
-#ifdef KR_EXPERIMENTAL
-    uint4 *packed = nullptr; u64 entries = 0; unsigned long long nonempty = 0;   // packed slots for k_idx_query_warp
-#endif
-};
 struct kr_db {
     kr_ctx *ctx = nullptr;
     std::vector<DbSegment> segs;
@@ -119,10 +91,13 @@ struct kr_db {
     SeqMeta *d_meta = nullptr; BlockRef *d_refs = nullptr; u32 *d_rank = nullptr, *d_order = nullptr;
     u32 nblk = 0, cap = 0, cap_blk = 0;
     std::vector<u32> h_rank;   // empty = append order
-    // inverted index (built on first use by a large query batch, dropped when the database changes)
-    bool index_ready = false;
-    std::vector<DbIndexSlab> slabs;
-    u32 *d_empty_reps = nullptr; u32 nempty = 0;
+    bool refs_ready = false;   // block lists / block refs (tile-join path only) are current
+    // Sorted inverted index in at most two levels: `main` over representatives [0, main_n) and `tail` over
+    // [main_n, tail_n).  Representatives are only ever appended, so a level stays valid; the tail is rebuilt when the
+    // database has grown and folded into the main level when it reaches a quarter of it (greedy build).
+    struct IndexOwned *ix_main = nullptr, *ix_tail = nullptr;
+    u32 main_n = 0, tail_n = 0;
+    u32 *d_empty_reps = nullptr, *d_nempty_reps = nullptr; u32 empty_n = 0;   // k-mer-less representatives among [0, empty_n)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -132,9 +107,8 @@ static kr_status fail(kr_ctx *ctx, kr_status code, const char *fmt, ...) {
     if (ctx) ctx->err = buf; else g_create_error = buf;
     return code;
 }
-// key slots a sequence of L residues can need (one per k-mer position; both strands for DNA contexts)
+// key slots a sequence of L residues can need (one per k-mer position)
 static inline u64 kmer_slots(const kr_ctx *ctx, u64 L) {
-    if (ctx->dnaK) return L >= (u64)ctx->dnaK ? 2 * (L - ctx->dnaK + 1) : 0;
     return L >= (u64)ctx->K ? L - ctx->K + 1 : 0;
 }
 #define CU(call)                                                                                         \
@@ -164,7 +138,8 @@ struct StageTimer {   // device time of a group of launches, resolved lazily in 
             cudaEventSynchronize(e.b);
             float ms = 0; cudaEventElapsedTime(&ms, e.a, e.b);
             double *dst = e.stage == ST_ENCODE ? &c->st.encode_ms : e.stage == ST_BLOCKLIST ? &c->st.blocklist_ms
-                        : e.stage == ST_JOIN ? &c->st.join_ms : &c->st.other_ms;
+                        : e.stage == ST_JOIN ? &c->st.join_ms : e.stage == ST_INDEX ? &c->st.index_ms
+                        : e.stage == ST_SCAN ? &c->st.scan_ms : &c->st.other_ms;
             *dst += ms;
             c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b);
         }
@@ -200,34 +175,15 @@ static void make_chunk_lut(u8 *lut) {
 extern "C" {
 
 const char *kr_last_error(const kr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
-const char *kr_build_info(void) {
-#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
-    return "v2";
-#elif defined(KR_EXPERIMENTAL)
-    return "experimental";
-#else
-    return "default";
-#endif
-}
-int kr_kmer_size(const kr_ctx *ctx) { return ctx ? (ctx->dnaK ? ctx->dnaK : ctx->K) : 0; }
+const char *kr_build_info(void) { return "default"; }
+int kr_kmer_size(const kr_ctx *ctx) { return ctx ? ctx->K : 0; }
 
-#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
-static void v2_selfcheck(kr_ctx *ctx);
-#endif
 
 kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     kr_ctx *ctx = nullptr;
     if (!out) return fail(nullptr, KR_ERR_ARG, "kr_create: out is null");
     *out = nullptr;
-    int dnaK = 0;
-#ifdef KR_EXPERIMENTAL
-    if (flags & KR_ALPHABET_DNA) {
-        if (K < 5 || K > 18) return fail(nullptr, KR_ERR_ARG, "kr_create: DNA K=%d outside [5,18] (3 bits per base + 8-bit sequence id in 64 bits)", K);
-        dnaK = K; K = (3 * K + 4) / 5;    // key width in five-bit units
-    }
-#else
-    if (flags & 0xFF00u) return fail(nullptr, KR_ERR_ARG, "kr_create: flags 0x%x are experimental and need a library built with -DKR_EXPERIMENTAL", flags & 0xFF00u);
-#endif
+    if (flags & ~(KR_IDENT_IS_INFINITY | KR_TIE_LAST | KR_FORCE_JOIN | KR_FORCE_INDEX)) return fail(nullptr, KR_ERR_ARG, "kr_create: unknown flags 0x%x", flags);
     if (K < KR_MIN_K || K > KR_MAX_K)
         return fail(nullptr, KR_ERR_ARG, "kr_create: K=%d outside [%d,%d] (5-bit packing + 8-bit sequence id in 64 bits)", K, KR_MIN_K, KR_MAX_K);
     int ndev = 0;
@@ -242,13 +198,8 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
         return fail(nullptr, KR_ERR_NODEVICE, "kr_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     if ((size_t)prop.sharedMemPerBlockOptin < JOIN_SMEM_BYTES)
         return fail(nullptr, KR_ERR_NODEVICE, "kr_create: device offers %zu B shared memory per block, need %zu", (size_t)prop.sharedMemPerBlockOptin, JOIN_SMEM_BYTES);
-#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
-    // Build switch for the round after hardware validation: the experimental paths become what every context uses
-    // (the posting-list path only where its work estimate beats the tile join's); KR_LEGACY_PATHS opts a context out.
-    if (!(flags & KR_LEGACY_PATHS)) flags |= KR_EXP_PAIRS_AUTO | KR_EXP_BUCKETS | KR_EXP_ENCODE | KR_EXP_IDXQ | KR_EXP_GIDX;
-#endif
     ctx = new kr_ctx();
-    ctx->dev = device; ctx->K = K; ctx->dnaK = dnaK; ctx->flags = flags; ctx->num_sms = prop.multiProcessorCount;
+    ctx->dev = device; ctx->K = K; ctx->flags = flags; ctx->num_sms = prop.multiProcessorCount;
 #define CUC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { fail(nullptr, KR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); delete ctx; return KR_ERR_CUDA; } } while (0)
     CUC(cudaSetDevice(device));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -271,26 +222,17 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaMemcpy(ctx->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_err, sizeof(ErrInfo)));
     CUC(cudaMemset(ctx->d_err, 0, sizeof(ErrInfo)));
-    CUC(cudaFuncSetAttribute(k_idx_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IDX_SMEM));
+    CUC(cudaFuncSetAttribute(k_ix_query<IXQ_ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IXQ_SMEM));
+    CUC(cudaFuncSetAttribute(k_ix_query<IXQ_CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IXQ_SMEM));
+    CUC(cudaFuncSetAttribute(k_ix_query<IXQ_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IXQ_SMEM));
+    CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
+    CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
     CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
     CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
     CUC(cudaFuncSetAttribute(k_join<MODE_MATRIX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
     CUC(cudaFuncSetAttribute(k_join<MODE_ARGMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
-#ifdef KR_EXPERIMENTAL
-    CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(false)));
-    CUC(cudaFuncSetAttribute(k_join<MODE_SPARSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem_bytes(true)));
-    CUC(cudaFuncSetAttribute(k_idx_query_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDXQ2_DENSE_MAX * 2 * IDXQ2_WARPS + 256)));
-    CUC(cudaFuncSetAttribute(k_gidx_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIDX_SMEM));
-    CUC(cudaFuncSetAttribute(k_encode_dna<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 9 + 16));
-    CUC(cudaFuncSetAttribute(k_bk_pairs<DenseSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
-    CUC(cudaFuncSetAttribute(k_bk_pairs<TableSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
-    CUC(cudaFuncSetAttribute(k_bk_pairs<WorkSink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
-#endif
 #undef CUC
     *out = ctx;
-#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
-    v2_selfcheck(ctx);
-#endif
     return KR_OK;
 }
 
@@ -378,10 +320,6 @@ double kr_distance(int32_t sim, uint32_t size_a, uint32_t size_b) {
 
 kr_status kr_key_decode(const kr_ctx *ctx, uint64_t key, char *out) {
     if (!ctx || !out) return KR_ERR_ARG;
-    if (ctx->dnaK) {
-        for (int i = ctx->dnaK - 1; i >= 0; --i) { const int c = (int)(key & 7); key >>= 3; out[i] = "acgtnu??"[c]; }
-        return KR_OK;
-    }
     for (int i = ctx->K - 1; i >= 0; --i) {
         int c = (int)(key & 31); key >>= 5;
         out[i] = c < 26 ? (char)('A' + c) : c == 26 ? '*' : c == 27 ? '-' : '?';
@@ -392,16 +330,17 @@ kr_status kr_key_decode(const kr_ctx *ctx, uint64_t key, char *out) {
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
+static kr_status fetch_sizes(kr_ctx *ctx, kr_seqset *s);
+#include "kr_api_index.inc"
+
 static void seqset_destroy(kr_seqset *s) {
     if (!s) return;
     kr_ctx *ctx = s->ctx;
     cudaSetDevice(ctx->dev);
+    if (s->ix) { index_free(ctx, s->ix); delete s->ix; s->ix = nullptr; }
+    dfree(ctx, s->d_empty); dfree(ctx, s->d_nempty);
     dfree(ctx, s->d_off); dfree(ctx, s->d_koff); dfree(ctx, s->d_keys); dfree(ctx, s->d_meta);
     dfree(ctx, s->d_hi); dfree(ctx, (u8 *)s->d_lo); dfree(ctx, s->d_choff); dfree(ctx, s->d_chcnt); dfree(ctx, s->d_blkbase); dfree(ctx, s->d_refs);
-#ifdef KR_EXPERIMENTAL
-    dfree(ctx, s->px_key); dfree(ctx, s->px_off); dfree(ctx, s->px_cnt); dfree(ctx, s->px_post);
-    dfree(ctx, s->bk_base); dfree(ctx, s->bk_eseq); dfree(ctx, s->bk_post); dfree(ctx, s->bk_ekey);
-#endif
     delete s;   // residue buffers are released stream-ordered by ~DevMem
 }
 
@@ -422,7 +361,7 @@ static kr_status check_alphabet(kr_ctx *ctx) {
     if (ei.flag) {
         return fail(ctx, KR_ERR_ALPHABET, "kr_encode: sequence %u position %u: residue 0x%02x ('%c') is outside %s",
                     ei.seq, ei.pos, ei.byte, (ei.byte >= 32 && ei.byte < 127) ? (char)ei.byte : '?',
-                    ctx->dnaK ? "a c g t n u (either case)" : "'A'..'Z', '*', '-'");
+                    "'A'..'Z', '*', '-'");
     }
     return KR_OK;
 }
@@ -462,21 +401,12 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
         StageTimer t(ctx, ST_ENCODE);
         EncodeParams p;
         p.res = (const u8 *)s->res->p; p.off = s->d_off; p.koff = s->d_koff; p.keys = s->d_keys; p.meta = s->d_meta;
-        p.err = ctx->d_err; p.nseq = nseq; p.K = ctx->dnaK ? ctx->dnaK : K; p.smem_cap = 2048;
-        // proteins are a few hundred residues: one 128-thread CTA sorts up to 2048 keys in 16 KB of shared
-        // memory; longer sequences (rare) sort in place in global memory inside the same kernel
-#ifdef KR_EXPERIMENTAL
-        if (ctx->dnaK) {   // DnaKmers: lower-case the library's copy, then the keys of both strands
-            p.smem_cap = 4096;                          // an SSU rRNA gene (~1,500 bases, ~3,000 keys) sorts in shared memory
-            KR_LAUNCH(KR_T(k_dna_lowercase), ctx->num_sms * 4, 256, 0, ctx->stream, (u8 *)s->res->p, total);
-            KR_LAUNCH(KR_T(k_encode_dna<128>), nseq, 128, p.smem_cap * 8 + p.smem_cap + 16, ctx->stream, p);
-            LAUNCHED(ctx);
-        } else
-        if ((ctx->flags & KR_EXP_ENCODE) && maxn <= 512) KR_LAUNCH(KR_T(k_encode_sort_warp<16>), (nseq + ENC2_WARPS - 1) / ENC2_WARPS, ENC2_WARPS * 32, 0, ctx->stream, p);
-        else if (ctx->flags & KR_EXP_ENCODE) KR_LAUNCH(KR_T(k_encode_sort_warp<32>), (nseq + ENC2_WARPS - 1) / ENC2_WARPS, ENC2_WARPS * 32, 0, ctx->stream, p);
-        else
-#endif
-        KR_LAUNCH(KR_T(k_encode_sort<128>), nseq, 128, p.smem_cap * 8 + p.smem_cap + 16, ctx->stream, p);
+        p.err = ctx->d_err; p.nseq = nseq; p.K = K; p.smem_cap = 0;
+        // one warp per sequence, keys sorted in registers; the 16-keys-per-lane build serves every batch whose longest
+        // sequence has at most 512 k-mers (seed proteins), the 32-keys-per-lane build the others
+        const u32 grid = (nseq + ENC2_WARPS - 1) / ENC2_WARPS;
+        if (maxn <= 512) KR_LAUNCH(KR_T(k_encode_sort_warp<16>), grid, ENC2_WARPS * 32, 0, ctx->stream, p);
+        else KR_LAUNCH(KR_T(k_encode_sort_warp<32>), grid, ENC2_WARPS * 32, 0, ctx->stream, p);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
     }
@@ -584,20 +514,33 @@ static u64 row_start(u32 layout, u64 r, u64 nrows, u64 ncols) {
 
 struct SparseSink { uint4 *cells; unsigned long long cap; unsigned long long *count; u32 min_sim; };
 
-#ifdef KR_EXPERIMENTAL
-#include "kr_api_exp_pairs.inc"
-#endif
 
 static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool self, const kr_matrix_desc *d, void *out_dev,
                                const SparseSink *sparse = nullptr) {
     kr_status st;
-#ifdef KR_EXPERIMENTAL
-    if (self && !sparse && (ctx->flags & (KR_EXP_PAIRS | KR_EXP_PAIRS_AUTO)) && A->d_keys && A->n && d->row_end > d->row_begin
-        && (reinterpret_cast<uintptr_t>(out_dev) & 3) == 0) {
-        bool done = false;
-        if ((st = pairs_launch(ctx, A, d, out_dev, &done)) || done) return st;
+    {
+        // sparse collections go through the index scan: zero-fill the result (dense) and write only the cells of pairs
+        // that share a k-mer; dense ones through the tile join below
+        bool use_index = false;
+        kr_seqset *Bx = self ? A : B;
+        if ((st = choose_index_path(ctx, A, Bx, self, &use_index))) return st;
+        if (use_index && d->row_end > d->row_begin) {
+            MatrixTarget tg;
+            const u64 rows = d->row_end - d->row_begin;
+            if (sparse) { tg.cells = sparse->cells; tg.cells_cap = sparse->cap; tg.cells_count = sparse->count; tg.min_sim = sparse->min_sim; }
+            else {
+                tg.out = out_dev; tg.elem = d->elem; tg.layout = d->layout; tg.origin = row_start(d->layout, d->row_begin, A->n, Bx->n); tg.min_sim = 1;
+                const u64 elems = row_start(d->layout, d->row_end, A->n, Bx->n) - tg.origin;
+                StageTimer t(ctx, ST_OTHER);
+                CU(cudaMemsetAsync(out_dev, 0, elems * (d->elem == KR_ELEM_U16 ? 2 : 4), ctx->stream));
+            }
+            if ((st = index_matrix(ctx, A, Bx, self, d->layout, d->row_begin, d->row_end, tg))) return st;
+            if (d->layout == KR_LAYOUT_FULL) ctx->st.pairs += rows * (u64)Bx->n;
+            else ctx->st.pairs += kr_matrix_elems(A->n, A->n, KR_LAYOUT_TRIANGLE, d->row_begin, d->row_end);
+            return KR_OK;
+        }
+        if (use_index) return KR_OK;
     }
-#endif
     if ((st = ensure_blocklists(ctx, A))) return st;
     if (!self && (st = ensure_blocklists(ctx, B))) return st;
     kr_seqset *Bs = self ? A : B;
@@ -630,19 +573,16 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
     {
         StageTimer t(ctx, ST_JOIN);
         u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
-#ifdef KR_EXPERIMENTAL
-        if (sparse) {
+        if (sparse) {   // the join's epilogue keeps only the cells that reach min_sim
             p.cells = sparse->cells; p.cells_cap = sparse->cap; p.cells_count = sparse->count; p.min_sim = sparse->min_sim;
             if (lo_bits(ctx->K) <= 16) KR_LAUNCH(KR_T(k_join<MODE_SPARSE, false>), grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream, p);
             else KR_LAUNCH(KR_T(k_join<MODE_SPARSE, true>), grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream, p);
-        } else
-#endif
-        if (lo_bits(ctx->K) <= 16) KR_LAUNCH(KR_T(k_join<MODE_MATRIX, false>), grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream, p);
+        }
+        else if (lo_bits(ctx->K) <= 16) KR_LAUNCH(KR_T(k_join<MODE_MATRIX, false>), grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream, p);
         else KR_LAUNCH(KR_T(k_join<MODE_MATRIX, true>), grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream, p);
         LAUNCHED(ctx); ctx->st.join_launches++;
         CU(cudaGetLastError());
     }
-    (void)sparse;
     u64 rows = d->row_end - d->row_begin;
     if (d->layout == KR_LAYOUT_FULL) ctx->st.pairs += rows * (u64)Bs->n;
     else ctx->st.pairs += kr_matrix_elems(A->n, A->n, KR_LAYOUT_TRIANGLE, d->row_begin, d->row_end);
@@ -666,39 +606,25 @@ static void db_free_arrays(kr_db *db) {
     db->d_meta = nullptr; db->d_refs = nullptr; db->d_rank = nullptr; db->d_order = nullptr;
 }
 
-// (re)build the database-wide meta / block-ref / rank arrays after a change
 static void db_free_index(kr_db *db) {
     kr_ctx *ctx = db->ctx;
-    for (auto &sl : db->slabs) {
-        dfree(ctx, sl.tab_key); dfree(ctx, sl.tab_off); dfree(ctx, sl.tab_cnt); dfree(ctx, sl.postings);
-#ifdef KR_EXPERIMENTAL
-        dfree(ctx, sl.packed);
-#endif
-    }
-    db->slabs.clear();
-    dfree(ctx, db->d_empty_reps); db->d_empty_reps = nullptr; db->nempty = 0;
-    db->index_ready = false;
+    if (db->ix_main) { index_free(ctx, db->ix_main); delete db->ix_main; db->ix_main = nullptr; }
+    if (db->ix_tail) { index_free(ctx, db->ix_tail); delete db->ix_tail; db->ix_tail = nullptr; }
+    db->main_n = db->tail_n = 0;
+    dfree(ctx, db->d_empty_reps); dfree(ctx, db->d_nempty_reps); db->d_empty_reps = nullptr; db->d_nempty_reps = nullptr; db->empty_n = 0;
 }
 
+// (re)build the database-wide record / rank arrays after a change (block refs only on demand: db_refresh_refs)
 static kr_status db_refresh(kr_ctx *ctx, kr_db *db) {
     if (!db->dirty) return KR_OK;
-    db_free_index(db);
-    kr_status st;
-    u32 nblk = 0;
-    for (auto &sg : db->segs) { if ((st = ensure_blocklists(ctx, sg.set))) return st; nblk += sg.set->nblk; }
     db_free_arrays(db);
-    CU(dalloc(ctx, &db->d_meta, db->n)); CU(dalloc(ctx, &db->d_refs, nblk));
-    CU(dalloc(ctx, &db->d_rank, db->n)); CU(dalloc(ctx, &db->d_order, db->n));
-    u32 bo = 0;
+    db->refs_ready = false;
+    CU(dalloc(ctx, &db->d_meta, db->n)); CU(dalloc(ctx, &db->d_rank, db->n)); CU(dalloc(ctx, &db->d_order, db->n));
     for (auto &sg : db->segs) {
         kr_seqset *s = sg.set;
         if (!s->n) continue;
         CU(cudaMemcpyAsync(db->d_meta + sg.base, s->d_meta, (size_t)s->n * sizeof(SeqMeta), cudaMemcpyDeviceToDevice, ctx->stream));
-        KR_LAUNCH(KR_T(k_copy_refs), (s->nblk + 127) / 128, 128, 0, ctx->stream, s->d_refs, s->nblk, sg.base, db->d_refs + bo);
-        LAUNCHED(ctx);
-        bo += s->nblk;
     }
-    db->nblk = nblk;
     if (db->n) {
         if (db->h_rank.size() == db->n) {
             std::vector<u32> order(db->n);
@@ -714,6 +640,28 @@ static kr_status db_refresh(kr_ctx *ctx, kr_db *db) {
     }
     CU(cudaGetLastError());
     db->dirty = false;
+    return KR_OK;
+}
+
+// block lists of every segment and the database-wide block-ref array (tile-join path)
+static kr_status db_refresh_refs(kr_ctx *ctx, kr_db *db) {
+    if (db->refs_ready) return KR_OK;
+    kr_status st;
+    u32 nblk = 0;
+    for (auto &sg : db->segs) { if ((st = ensure_blocklists(ctx, sg.set))) return st; nblk += sg.set->nblk; }
+    dfree(ctx, db->d_refs); db->d_refs = nullptr;
+    CU(dalloc(ctx, &db->d_refs, nblk));
+    u32 bo = 0;
+    for (auto &sg : db->segs) {
+        kr_seqset *s = sg.set;
+        if (!s->n) continue;
+        KR_LAUNCH(KR_T(k_copy_refs), (s->nblk + 127) / 128, 128, 0, ctx->stream, s->d_refs, s->nblk, sg.base, db->d_refs + bo);
+        LAUNCHED(ctx);
+        bo += s->nblk;
+    }
+    CU(cudaGetLastError());
+    db->nblk = nblk;
+    db->refs_ready = true;
     return KR_OK;
 }
 
@@ -775,127 +723,87 @@ static kr_status db_append_owned(kr_ctx *ctx, kr_db *db, kr_seqset *s) {
     return db_compact(ctx, db);
 }
 
-// K4: build the inverted index of the database, one slab of at most IDX_SLAB representatives at a time
-static kr_status db_build_index(kr_ctx *ctx, kr_db *db) {
-    if (db->index_ready) return KR_OK;
-    kr_status st;
-    for (auto &sg : db->segs) if ((st = fetch_sizes(ctx, sg.set))) return st;
-    StageTimer t(ctx, ST_OTHER);
-    for (u32 base = 0; base < db->n; base += IDX_SLAB) {
-        DbIndexSlab sl; sl.base = base; sl.n = std::min<u32>(IDX_SLAB, db->n - base);
-        u64 entries = 0;
-        for (auto &sg : db->segs) {
-            u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
-            for (u32 g = lo; g < hi; ++g) entries += sg.set->h_sizes[g - sg.base];
-        }
-        u64 cap = 1024; while (cap < 2 * entries) cap <<= 1;
-        if (cap > (1ull << 31)) return fail(ctx, KR_ERR_ARG, "inverted index slab too large (%llu entries)", (unsigned long long)entries);
-        sl.mask = (u32)(cap - 1);
-        u32 *d_cur = nullptr, *d_sums = nullptr;
-        u32 ntile = (u32)((cap + SCAN_TILE - 1) / SCAN_TILE);
-        CU(dalloc(ctx, &sl.tab_key, cap)); CU(dalloc(ctx, &sl.tab_off, cap)); CU(dalloc(ctx, &sl.tab_cnt, cap));
-        CU(dalloc(ctx, &sl.postings, entries + 1)); CU(dalloc(ctx, &d_cur, cap)); CU(dalloc(ctx, &d_sums, ntile));
-        CU(cudaMemsetAsync(sl.tab_key, 0xFF, cap * 8, ctx->stream));
-        CU(cudaMemsetAsync(sl.tab_cnt, 0, cap * 4, ctx->stream));
-        CU(cudaMemsetAsync(d_cur, 0, cap * 4, ctx->stream));
-        for (auto &sg : db->segs) {
-            u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
-            if (lo >= hi) continue;
-            kr_seqset *s = sg.set; u32 l = lo - sg.base;
-            KR_LAUNCH(KR_T(k_idx_insert), hi - lo, 128, 0, ctx->stream, s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, sl.tab_key, sl.tab_cnt, sl.mask);
-            LAUNCHED(ctx);
-        }
-        KR_LAUNCH(KR_T(k_scan_tile_sums), ntile, 256, 0, ctx->stream, sl.tab_cnt, cap, d_sums);
-        KR_LAUNCH(KR_T(k_scan_sums), 1, 1024, 0, ctx->stream, d_sums, ntile);
-        KR_LAUNCH(KR_T(k_scan_tiles), ntile, 256, 0, ctx->stream, sl.tab_cnt, cap, d_sums, sl.tab_off);
-        ctx->st.kernel_launches += 3;
-        for (auto &sg : db->segs) {
-            u32 lo = std::max(base, sg.base), hi = std::min(base + sl.n, sg.base + sg.set->n);
-            if (lo >= hi) continue;
-            kr_seqset *s = sg.set; u32 l = lo - sg.base;
-            KR_LAUNCH(KR_T(k_idx_fill), hi - lo, 128, 0, ctx->stream, s->d_keys, s->d_koff + l, s->d_meta + l, hi - lo, lo, sl.tab_key, sl.tab_off, d_cur,
-                                                          sl.mask, sl.postings);
-            LAUNCHED(ctx);
-        }
-        CU(cudaGetLastError());
-        dfree(ctx, d_cur); dfree(ctx, d_sums);
-#ifdef KR_EXPERIMENTAL
-        if (ctx->flags & KR_EXP_IDXQ) {   // packed slots + the number of distinct keys (mean posting length picks the query kernel)
-            unsigned long long *d_ne = nullptr;
-            CU(dalloc(ctx, &sl.packed, cap)); CU(dalloc(ctx, &d_ne, 1));
-            CU(cudaMemsetAsync(d_ne, 0, 8, ctx->stream));
-            KR_LAUNCH(KR_T(k_idx_pack), ctx->num_sms * 8, 256, 0, ctx->stream, sl.tab_key, sl.tab_off, sl.tab_cnt, cap, sl.packed, d_ne);
-            LAUNCHED(ctx);
-            CU(cudaMemcpyAsync(&sl.nonempty, d_ne, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            dfree(ctx, d_ne);
-            sl.entries = entries;
-        }
-#endif
-        db->slabs.push_back(sl);
+// can the representatives of this database be indexed (every segment keeps key lists; K and size fit the entry layout)?
+static bool db_indexable(const kr_ctx *ctx, const kr_db *db) {
+    u64 cap = 0;
+    for (auto &sg : db->segs) { if (sg.set->n && !sg.set->d_keys) return false; cap += sg.set->key_cap; }
+    IxGeom g;
+    return index_geometry(ctx, std::max<u32>(2 * db->n, 1024), cap, &g);
+}
+
+// K4 for a database: one index level over representatives [lo, hi)
+static kr_status db_build_level(kr_ctx *ctx, kr_db *db, u32 lo, u32 hi, IndexOwned **level) {
+    std::vector<IxSegment> segs;
+    u64 cap = 0;
+    for (auto &sg : db->segs) {
+        const u32 a = std::max(lo, sg.base), b = std::min(hi, sg.base + sg.set->n);
+        if (a >= b) continue;
+        kr_seqset *s = sg.set; const u32 l = a - sg.base;
+        segs.push_back(IxSegment{s->d_keys, s->d_koff + l, s->d_meta + l, b - a, a});
+        if (l == 0 && b - a == s->n) cap += s->key_cap;
+        else { kr_status st = fetch_sizes(ctx, s); if (st) return st; for (u32 k = l; k < l + (b - a); ++k) cap += s->h_sizes[k]; }
     }
-    // representatives without any k-mer (shorter than K): only the equal-sequence rule can match them
-    u32 *d_count = nullptr;
-    CU(dalloc(ctx, &db->d_empty_reps, db->n)); CU(dalloc(ctx, &d_count, 1));
-    CU(cudaMemsetAsync(d_count, 0, 4, ctx->stream));
-    KR_LAUNCH(KR_T(k_collect_empty), (db->n + 255) / 256, 256, 0, ctx->stream, db->d_meta, db->n, db->d_empty_reps, d_count);
-    LAUNCHED(ctx);
-    CU(cudaMemcpyAsync(&db->nempty, d_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    dfree(ctx, d_count);
-    db->index_ready = true;
+    if (!*level) *level = new IndexOwned();
+    // ids of every level share one bit width (that of the largest id the database may reach before the next rebuild)
+    return index_build(ctx, segs, cap, lo, hi, std::max<u32>(2 * db->n, 1024), *level);
+}
+
+// Bring the index up to date with the representatives appended since it was last built: the tail level is rebuilt over
+// everything after the main level, and folded into the main level once it holds a quarter of it.
+static kr_status db_ensure_index(kr_ctx *ctx, kr_db *db) {
+    kr_status st;
+    // an id must still fit the bit width the levels were built with
+    if (db->ix_main && db->ix_main->ok && (db->n > (1ull << db->ix_main->g.idbits))) db_free_index(db);
+    const u32 tail = db->n - db->main_n;
+    if (!db->ix_main || !db->ix_main->ok || db->main_n == 0 || (u64)tail * 4 >= db->main_n) {
+        if (db->ix_tail) { index_free(ctx, db->ix_tail); delete db->ix_tail; db->ix_tail = nullptr; }
+        if ((st = db_build_level(ctx, db, 0, db->n, &db->ix_main))) return st;
+        db->main_n = db->tail_n = db->n;
+    } else if (db->tail_n != db->n) {
+        if ((st = db_build_level(ctx, db, db->main_n, db->n, &db->ix_tail))) return st;
+        db->tail_n = db->n;
+    }
+    // the k-mer-less representatives (equal-sequence rule for k-mer-less queries)
+    if ((ctx->flags & KR_IDENT_IS_INFINITY) && db->empty_n != db->n) {
+        dfree(ctx, db->d_empty_reps); dfree(ctx, db->d_nempty_reps);
+        CU(dalloc(ctx, &db->d_empty_reps, (size_t)db->n + 1)); CU(dalloc(ctx, &db->d_nempty_reps, 1));
+        CU(cudaMemsetAsync(db->d_nempty_reps, 0, 4, ctx->stream));
+        KR_LAUNCH(KR_T(k_collect_empty), (db->n + 255) / 256, 256, 0, ctx->stream, db->d_meta, db->n, db->d_empty_reps, db->d_nempty_reps);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        db->empty_n = db->n;
+    }
     return KR_OK;
 }
 
-// K5: queries against the inverted index
-static kr_status find_closest_index(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *d_sim, u32 *d_first, u32 *d_last) {
-    kr_status st = db_build_index(ctx, db);
+// K5: queries [q0, q1) of Q against the index levels of the database; outputs are indexed by q - q0
+static kr_status find_closest_index(kr_ctx *ctx, kr_db *db, kr_seqset *Q, u32 q0, u32 q1, int *d_sim, u32 *d_first, u32 *d_last) {
+    kr_status st = db_ensure_index(ctx, db);
     if (st) return st;
-    const u32 nslab = (u32)db->slabs.size();
+    const u32 nq = q1 - q0;
+    const bool two = db->ix_tail && db->tail_n > db->main_n;
+    const u32 nlev = two ? 2u : 1u;
     int4 *d_partial = nullptr; u32 *d_next = nullptr;
-    CU(dalloc(ctx, &d_partial, (size_t)nslab * Q->n)); CU(dalloc(ctx, &d_next, nslab));
-    CU(cudaMemsetAsync(d_next, 0, 4 * nslab, ctx->stream));
+    CU(dalloc(ctx, &d_partial, (size_t)nlev * nq)); CU(dalloc(ctx, &d_next, 2));
+    CU(cudaMemsetAsync(d_next, 0, 8, ctx->stream));
     {
-        StageTimer t(ctx, ST_JOIN);
-        for (u32 k = 0; k < nslab; ++k) {
-            const DbIndexSlab &sl = db->slabs[k];
-            IdxQueryParams p{};
-            p.qkeys = Q->d_keys; p.qkoff = Q->d_koff; p.qmeta = Q->d_meta; p.nq = Q->n;
-            p.tab_key = sl.tab_key; p.tab_off = sl.tab_off; p.tab_cnt = sl.tab_cnt; p.mask = sl.mask; p.postings = sl.postings;
-            p.rmeta = db->d_meta; p.rank = db->d_rank; p.slab_base = sl.base; p.slab_n = sl.n; p.flags = ctx->flags;
-            p.partial = d_partial + (size_t)k * Q->n; p.next = d_next + k;
-#ifdef KR_EXPERIMENTAL
-            // one warp per query where a query touches few representatives: small slabs (dense per-warp scores) or short
-            // posting lists (per-warp hash); otherwise the CTA-per-query kernel with its slab-wide score array
-            if (sl.packed && (sl.n <= IDXQ2_DENSE_MAX || sl.entries <= 8 * sl.nonempty)) {
-                IdxQuery2Params pp{p, sl.packed};
-                const bool dense = sl.n <= IDXQ2_DENSE_MAX;
-                const size_t words = dense ? (((size_t)sl.n + 1) / 2 + 3) / 4 * 4 : IDXQ2_HASH;
-                const u32 grid2 = std::min<u32>((Q->n + IDXQ2_WARPS - 1) / IDXQ2_WARPS, (u32)ctx->num_sms * (dense ? 3 : 6));
-                if (dense) KR_LAUNCH(KR_T(k_idx_query_warp<true>), grid2, IDXQ2_WARPS * 32, words * 4 * IDXQ2_WARPS, ctx->stream, pp);
-                else KR_LAUNCH(KR_T(k_idx_query_warp<false>), grid2, IDXQ2_WARPS * 32, words * 4 * IDXQ2_WARPS, ctx->stream, pp);
-                LAUNCHED(ctx); ctx->st.join_launches++;
-                continue;
-            }
-#endif
-            u32 grid = std::min<u32>(Q->n, 2 * (u32)ctx->num_sms);
-            KR_LAUNCH(KR_T(k_idx_query), grid, IDX_THREADS, ((size_t)sl.n + 1) / 2 * 4, ctx->stream, p);
-            LAUNCHED(ctx); ctx->st.join_launches++;
-        }
-        if ((ctx->flags & KR_IDENT_IS_INFINITY) && db->nempty) {
-            KR_LAUNCH(KR_T(k_idx_empty_queries), (Q->n * 32 + 255) / 256, 256, 0, ctx->stream, Q->d_meta, Q->n, db->d_meta, db->d_rank, db->d_empty_reps,
-                                                                                  db->nempty, d_partial);
+        StageTimer t(ctx, ST_SCAN);
+        if ((st = index_argmax(ctx, *db->ix_main, Q, q0, q1, db->d_meta, db->d_rank, d_partial, d_next))) return st;
+        if (two && (st = index_argmax(ctx, *db->ix_tail, Q, q0, q1, db->d_meta, db->d_rank, d_partial + nq, d_next + 1))) return st;
+        if (ctx->flags & KR_IDENT_IS_INFINITY) {
+            KR_LAUNCH(KR_T(k_idx_empty_queries), (nq * 32 + 255) / 256, 256, 0, ctx->stream, Q->d_meta + q0, nq, db->d_meta, db->d_rank, db->d_empty_reps,
+                                                                                  db->d_nempty_reps, d_partial);
             LAUNCHED(ctx);
         }
     }
     {
         StageTimer t(ctx, ST_OTHER);
-        KR_LAUNCH(KR_T(k_idx_merge), (Q->n + 255) / 256, 256, 0, ctx->stream, d_partial, Q->n, nslab, db->d_order, d_sim, d_first, d_last);
+        KR_LAUNCH(KR_T(k_idx_merge), (nq + 255) / 256, 256, 0, ctx->stream, d_partial, nq, nlev, db->d_order, d_sim, d_first, d_last);
         LAUNCHED(ctx);
     }
     CU(cudaGetLastError());
     dfree(ctx, d_partial); dfree(ctx, d_next);
-    ctx->st.pairs += (u64)Q->n * db->n;
+    ctx->st.pairs += (u64)nq * db->n;
     return KR_OK;
 }
 
@@ -904,17 +812,19 @@ static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *
     kr_status st;
     if ((st = db_refresh(ctx, db))) return st;
     if (Q->n == 0) return KR_OK;
-    // large query batches go through the inverted index (work ~ postings touched); small ones through the tile
-    // join (no index to build); both are exact
-    const bool use_index = db->n > 0 && Q->d_keys && !(ctx->flags & KR_FORCE_JOIN) && ((ctx->flags & KR_FORCE_INDEX) || Q->n >= 8192);
-    if (use_index) return find_closest_index(ctx, db, Q, d_sim, d_first, d_last);
-    if ((st = ensure_blocklists(ctx, Q))) return st;
     if (db->n == 0) {
         CU(cudaMemsetAsync(d_sim, 0, (size_t)Q->n * 4, ctx->stream));
         if (d_first) CU(cudaMemsetAsync(d_first, 0xFF, (size_t)Q->n * 4, ctx->stream));
         if (d_last) CU(cudaMemsetAsync(d_last, 0xFF, (size_t)Q->n * 4, ctx->stream));
         return KR_OK;
     }
+    // Two exact paths.  The index scan (work ~ postings the queries touch) serves every batch whose sets keep key lists
+    // and whose K fits the 64-bit entry; the tile join (work ~ queries x representatives) serves the rest: sets
+    // imported from block lists, K > 9 with large databases, and contexts that pin it (KR_FORCE_JOIN).
+    const bool use_index = Q->d_keys && !(ctx->flags & KR_FORCE_JOIN) && db_indexable(ctx, db);
+    if (use_index) return find_closest_index(ctx, db, Q, 0, Q->n, d_sim, d_first, d_last);
+    if ((st = db_refresh_refs(ctx, db))) return st;
+    if ((st = ensure_blocklists(ctx, Q))) return st;
     u32 nI = Q->nblk;
     u32 nsplit = std::max<u32>(1, std::min<u32>(db->nblk, (2 * (u32)ctx->num_sms + nI - 1) / nI));
     std::vector<uint2> tasks;
@@ -1218,9 +1128,54 @@ kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, con
     return st;
 }
 
-#ifdef KR_EXPERIMENTAL
-#include "kr_api_exp_entry.inc"
-#endif
+
+// the caller holds the context's lock
+static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                             uint32_t *cells_host, uint64_t cap, uint64_t *count, void *cells_dev) {
+    kr_status st = check_desc(ctx, A, B, desc);
+    if (st) return st;
+    if (!count || (!cells_host && !cells_dev && cap) || min_sim < 1 || desc->layout == KR_LAYOUT_BLOCKTRI)
+        return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: bad argument (min_sim >= 1; layout FULL or TRIANGLE)");
+    CU(cudaSetDevice(ctx->dev));
+    *count = 0;
+    const bool self = (B == nullptr || B == A);
+    uint4 *d_cells = reinterpret_cast<uint4 *>(cells_dev); unsigned long long *d_count = nullptr;
+    if (!cells_dev) CU(dalloc(ctx, &d_cells, cap));
+    CU(dalloc(ctx, &d_count, 1));
+    CU(cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+    SparseSink sink{d_cells, cap, d_count, (u32)min_sim};
+    st = matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, d_cells, &sink);
+    if (st == KR_OK) {
+        unsigned long long n = 0;
+        cudaError_t e = cudaMemcpyAsync(&n, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        const unsigned long long take = std::min<unsigned long long>(n, cap);
+        if (e == cudaSuccess && take && cells_host) e = cudaMemcpyAsync(cells_host, d_cells, take * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "sparse matrix copy to host failed: %s", cudaGetErrorString(e));
+        ctx->st.d2h_bytes += 8 + (cells_host ? take * 16 : 0);
+        *count = n;
+        if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
+        if (st == KR_OK && n > cap) st = fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: %llu cells qualify, room for %llu", n, (unsigned long long)cap);
+    }
+    if (!cells_dev) dfree(ctx, d_cells);
+    dfree(ctx, d_count);
+    return st;
+}
+
+kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                               uint32_t *cells_host, uint64_t cap, uint64_t *count) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return sparse_impl(ctx, A, B, desc, min_sim, cells_host, cap, count, nullptr);
+}
+kr_status kr_sim_matrix_sparse_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                                      void *cells_dev, uint64_t cap, uint64_t *count) {
+    if (!ctx) return KR_ERR_ARG;
+    if (!cells_dev && cap) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse_device: null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return sparse_impl(ctx, A, B, desc, min_sim, nullptr, cap, count, cells_dev);
+}
 
 // ---- database ----------------------------------------------------------------------------------
 kr_status kr_db_create(kr_ctx *ctx, kr_db **out) {
@@ -1318,97 +1273,44 @@ kr_status kr_db_any_ge(kr_ctx *ctx, const kr_db *db, const kr_seqset *cands, int
     return KR_OK;
 }
 
-#ifdef KR_EXPERIMENTAL
-// EXPERIMENTAL: the growing index of kr_gidx.cuh, sized once for everything this call can add
-struct GrowIndex {
-    kr_ctx *ctx; GIdx g{}; bool ok = false;
-    explicit GrowIndex(kr_ctx *c) : ctx(c) {}
-    ~GrowIndex() {
-        dfree(ctx, g.key); dfree(ctx, g.head); dfree(ctx, g.nodes); dfree(ctx, g.node_count); dfree(ctx, g.rmeta);
-        dfree(ctx, g.empty_reps); dfree(ctx, g.empty_count);
-    }
-    kr_status create(u64 entries, u32 reps) {
-        u64 cap = 1024; while (cap < 2 * entries) cap <<= 1;
-        if (entries >= 0xFFFFFFF0ull) return fail(ctx, KR_ERR_ARG, "growing index: too many k-mers (%llu)", (unsigned long long)entries);
-        CU(dalloc(ctx, &g.key, cap)); CU(dalloc(ctx, &g.head, cap)); CU(dalloc(ctx, &g.nodes, entries + 1)); CU(dalloc(ctx, &g.node_count, 1));
-        CU(dalloc(ctx, &g.rmeta, reps + 1)); CU(dalloc(ctx, &g.empty_reps, reps + 1)); CU(dalloc(ctx, &g.empty_count, 1));
-        CU(cudaMemsetAsync(g.key, 0xFF, cap * 8, ctx->stream)); CU(cudaMemsetAsync(g.head, 0xFF, cap * 4, ctx->stream));
-        CU(cudaMemsetAsync(g.node_count, 0, 4, ctx->stream)); CU(cudaMemsetAsync(g.empty_count, 0, 4, ctx->stream));
-        g.mask = cap - 1; g.node_cap = (u32)entries + 1; ok = true;
-        return KR_OK;
-    }
-    kr_status insert(const kr_seqset *s, u32 rep_base) {
-        if (!s->n) return KR_OK;
-        KR_LAUNCH(KR_T(k_gidx_insert), s->n, 128, 0, ctx->stream, s->d_keys, s->d_koff, s->d_meta, s->n, rep_base, g);
-        LAUNCHED(ctx);
-        CU(cudaGetLastError());
-        return KR_OK;
-    }
-};
-#endif
 
 kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_t threshold, uint32_t batch, uint8_t *added) {
     if (!ctx || !db || !cands || !added) return fail(ctx, KR_ERR_ARG, "kr_greedy_build: null argument");
     if (db->ctx != ctx || cands->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_greedy_build: handle belongs to another context");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->dev));
-    if (batch == 0) batch = 4096;
-#ifdef KR_EXPERIMENTAL
-    GrowIndex gi(ctx);
-    if ((ctx->flags & KR_EXP_GIDX) && cands->d_keys && cands->n) {
-        u64 entries = cands->key_cap;
-        bool keyed = true;
-        for (auto &sg : db->segs) { entries += sg.set->key_cap; keyed = keyed && (sg.set->d_keys || !sg.set->n); }
-        if (keyed) {
-            kr_status st0 = gi.create(entries, db->n + cands->n);
-            for (auto &sg : db->segs) if (st0 == KR_OK) st0 = gi.insert(sg.set, sg.base);
-            if (st0) return st0;
-        }
-    }
-#endif
+    // The accept / reject sweep of checkGenome is sequential; what is batched is the scoring.  Per batch of candidates:
+    //   1. best similarity of every candidate against the representatives so far (index scan straight on the
+    //      candidate set -- no gather -- or the tile join when the sets cannot be indexed);
+    //   2. the candidates below the threshold ("survivors") against one another, as the sparse cells with
+    //      sim >= threshold: a few cells per survivor instead of an S x S matrix;
+    //   3. the sweep in candidate order over those adjacency lists on the host; accepted candidates are appended
+    //      (the database's tail index is rebuilt by the next batch's scan).
+    const bool by_index = cands->d_keys && !(ctx->flags & KR_FORCE_JOIN);
+    if (batch == 0) batch = by_index ? 32768 : 4096;
     const u32 C = cands->n;
     kr_status st = KR_OK;
-    std::vector<u32> idx, surv, acc;
+    std::vector<u32> idx, surv, acc, cells;
     std::vector<int32_t> best;
     std::vector<u16> M;
     for (u32 pos = 0; pos < C && st == KR_OK; pos += batch) {
         const u32 n = std::min(batch, C - pos);
-        idx.resize(n);
-        for (u32 i = 0; i < n; ++i) idx[i] = pos + i;
         surv.clear();
-#ifdef KR_EXPERIMENTAL
-        if (gi.ok) {
-            // score the batch through the growing index: no gather, no block lists, nothing rebuilt
-            int *d_sim = nullptr; u32 *d_next = nullptr;
-            cudaError_t e = dalloc(ctx, &d_sim, n);
-            if (e == cudaSuccess) e = dalloc(ctx, &d_next, 1);
-            if (e == cudaSuccess) e = cudaMemsetAsync(d_next, 0, 4, ctx->stream);
-            if (e != cudaSuccess) { st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
-            {
-                StageTimer t(ctx, ST_JOIN);
-                const u32 grid = std::min<u32>((n + GIDX_WARPS - 1) / GIDX_WARPS, (u32)ctx->num_sms * 3);
-                KR_LAUNCH(KR_T(k_gidx_query), grid, GIDX_WARPS * 32, GIDX_SMEM, ctx->stream, cands->d_keys, cands->d_koff + pos, cands->d_meta + pos, n, gi.g,
-                          ctx->flags, d_sim, d_next);
-                LAUNCHED(ctx); ctx->st.join_launches++;
-            }
-            best.resize(n);
-            e = cudaMemcpyAsync(best.data(), d_sim, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
-            ctx->st.d2h_bytes += (u64)n * 4; ctx->st.pairs += (u64)n * db->n;
-            dfree(ctx, d_sim); dfree(ctx, d_next);
-            if (st) break;
-            for (u32 i = 0; i < n; ++i) { if (best[i] < threshold) surv.push_back(pos + i); else added[pos + i] = 0; }
-        } else
-#endif
         if (db->n) {
-            // score the batch against the current representatives
-            kr_seqset *bs = nullptr;
-            if ((st = gather_impl(ctx, cands, idx.data(), n, &bs))) break;
             int *d_sim = nullptr;
             cudaError_t e = dalloc(ctx, &d_sim, n);
-            if (e != cudaSuccess) { seqset_destroy(bs); st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
-            st = find_closest_launch(ctx, db, bs, d_sim, nullptr, nullptr);
+            if (e != cudaSuccess) { st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
+            if (by_index && db_indexable(ctx, db)) {
+                if ((st = db_refresh(ctx, db)) == KR_OK) st = find_closest_index(ctx, db, const_cast<kr_seqset *>(cands), pos, pos + n, d_sim, nullptr, nullptr);
+            } else {
+                idx.resize(n);
+                for (u32 i = 0; i < n; ++i) idx[i] = pos + i;
+                kr_seqset *bs = nullptr;
+                if ((st = gather_impl(ctx, cands, idx.data(), n, &bs)) == KR_OK) {
+                    st = find_closest_launch(ctx, db, bs, d_sim, nullptr, nullptr);
+                    seqset_destroy(bs);      // stream-ordered release
+                }
+            }
             best.resize(n);
             if (st == KR_OK) {
                 e = cudaMemcpyAsync(best.data(), d_sim, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1418,11 +1320,11 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
                 if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
             }
             dfree(ctx, d_sim);
-            seqset_destroy(bs);
             if (st) break;
             for (u32 i = 0; i < n; ++i) { if (best[i] < threshold) surv.push_back(pos + i); else added[pos + i] = 0; }
         } else {
-            surv = idx;
+            surv.resize(n);
+            for (u32 i = 0; i < n; ++i) surv[i] = pos + i;
         }
         if (surv.empty()) continue;
         // survivors against one another, then the in-order sweep of checkGenome
@@ -1430,34 +1332,33 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
         acc.clear();
         if (S == 1) {
             acc.push_back(0);
-        }
-#ifdef KR_EXPERIMENTAL
-        else if (gi.ok && threshold >= 1) {
-            // Only the survivor pairs that reach the threshold matter to the sweep: fetch those as sparse cells (a few per
-            // survivor) instead of the S x S matrix, and sweep over adjacency lists -- O(cells), not O(S^2), on the host
+        } else if (threshold >= 1) {
             kr_seqset *ss = nullptr;
             if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) break;
             kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_TRIANGLE, 0, S};
-            std::vector<u32> cells((size_t)(8 * (u64)S + 1024) * 4);
-            uint64_t ncell = 0;
-            st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), cells.size() / 4, &ncell);
-            if (st == KR_ERR_ARG && ncell > cells.size() / 4) {   // more qualifying pairs than guessed: once more with room
-                cells.assign((size_t)ncell * 4, 0);
-                st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), ncell, &ncell);
+            uint64_t room = 8 * (uint64_t)S + 1024, ncell = 0;
+            cells.resize((size_t)room * 4);
+            st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), room, &ncell, nullptr);
+            if (st == KR_ERR_ARG && ncell > room) {      // more qualifying pairs than guessed: once more with room for all
+                room = ncell; cells.resize((size_t)room * 4);
+                st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), room, &ncell, nullptr);
             }
             seqset_destroy(ss);
             if (st) break;
-            std::vector<std::vector<u32>> earlier(S);          // earlier[s] = survivors t < s with similarity >= threshold
-            for (uint64_t k = 0; k < ncell; ++k) earlier[cells[4 * k + 1]].push_back(cells[4 * k]);
+            // earlier[s] = survivors t < s with similarity >= threshold (CSR over the cells)
+            std::vector<u32> start(S + 1, 0), adj((size_t)ncell);
+            for (uint64_t k = 0; k < ncell; ++k) start[cells[4 * k + 1] + 1]++;
+            for (u32 v = 0; v < S; ++v) start[v + 1] += start[v];
+            std::vector<u32> fill(start.begin(), start.end() - 1);
+            for (uint64_t k = 0; k < ncell; ++k) adj[fill[cells[4 * k + 1]]++] = cells[4 * k];
             std::vector<u8> accepted(S, 0);
-            for (u32 sidx = 0; sidx < S; ++sidx) {
+            for (u32 v = 0; v < S; ++v) {
                 bool repd = false;
-                for (u32 t : earlier[sidx]) if (accepted[t]) { repd = true; break; }
-                if (!repd) { accepted[sidx] = 1; acc.push_back(sidx); }
+                for (u32 k = start[v]; k < start[v + 1] && !repd; ++k) repd = accepted[adj[k]] != 0;
+                if (!repd) { accepted[v] = 1; acc.push_back(v); }
             }
-        }
-#endif
-        else {
+        } else {
+            // threshold <= 0: every similarity qualifies; the dense survivor matrix keeps the general code path honest
             kr_seqset *ss = nullptr;
             if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) break;
             kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, S};
@@ -1476,22 +1377,18 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
             dfree(ctx, d_M);
             seqset_destroy(ss);
             if (st) break;
-            for (u32 s = 0; s < S; ++s) {
+            for (u32 v = 0; v < S; ++v) {
                 bool rep = false;
-                const u16 *col = M.data();   // M is symmetric: read row s
-                const u16 *row = col + (size_t)s * S;
+                const u16 *row = M.data() + (size_t)v * S;   // M is symmetric
                 for (u32 t : acc) if ((int)row[t] >= threshold) { rep = true; break; }
-                if (!rep) acc.push_back(s);
+                if (!rep) acc.push_back(v);
             }
         }
         std::vector<u32> acc_idx(acc.size());
-        for (u32 s = 0; s < S; ++s) added[surv[s]] = 0;
+        for (u32 v = 0; v < S; ++v) added[surv[v]] = 0;
         for (size_t k = 0; k < acc.size(); ++k) { acc_idx[k] = surv[acc[k]]; added[acc_idx[k]] = 1; }
         kr_seqset *as = nullptr;
         if ((st = gather_impl(ctx, cands, acc_idx.data(), (u32)acc_idx.size(), &as))) break;
-#ifdef KR_EXPERIMENTAL
-        if (gi.ok && (st = gi.insert(as, db->n))) { seqset_destroy(as); break; }   // stream-ordered before any later free of `as`
-#endif
         st = db_append_owned(ctx, db, as);
     }
     return st;
@@ -1499,6 +1396,3 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
 
 }  // extern "C"
 
-#if defined(KR_EXPERIMENTAL) && defined(KR_DEFAULTS_V2)
-#include "kr_api_v2check.inc"
-#endif

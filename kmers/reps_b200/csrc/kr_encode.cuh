@@ -1,13 +1,13 @@
-// kr_encode2.cuh -- EXPERIMENTAL (compiled only with -DKR_EXPERIMENTAL; checked on the CPU emulator, unverified on
-// hardware when written): K1 with one WARP per sequence.
+// kr_encode.cuh -- K1: ProteinKmers(String) for a whole batch, one WARP per sequence.
 //
-// k_encode_sort gives a whole 128-thread CTA to one sequence and sorts its ~300 keys with ~45 barrier-separated
-// bitonic stages in shared memory (15 ns per sequence at 100k).  A seed protein has at most a few hundred k-mers, so
-// here a warp keeps them in registers -- R consecutive elements per lane, R = 2..32 chosen from the sequence length --
-// and runs the same network with register compare-exchanges for strides below R and warp shuffles for the rest: no
-// block barrier, no shared-memory traffic in the sort, four sequences per CTA in flight.  Sequences with more than
-// 1024 k-mers (rare) are sorted in place in global memory by their warp.
-// Output is identical to k_encode_sort's: sorted distinct keys, size, length, the same 64-bit hash, the error flag.
+// A seed protein has a few hundred k-mers, so a warp keeps them in registers -- R consecutive elements per lane,
+// R = 2..32 chosen from the sequence length -- and sorts them with a bitonic network that uses register
+// compare-exchanges for strides below R and warp shuffles for the rest: no block barrier, no shared-memory traffic in
+// the sort, four sequences per CTA in flight.  Residues are read once (coalesced), mapped to 5-bit codes in shared
+// memory, and every lane builds its keys with a rolling 5K-bit window.  Sequences with more than 1024 k-mers (rare)
+// are sorted in place in global memory by their warp.
+// Output per sequence: sorted DISTINCT keys, their number, the length, a 64-bit hash of the residues (pre-filter of the
+// equal-sequence rule); a residue outside the alphabet raises the context's error record.
 #pragma once
 #include "kr_kernels.cuh"
 
@@ -17,8 +17,8 @@ constexpr int ENC2_WARPS = 4;                    // sequences in flight per CTA
 constexpr u32 ENC2_MAXREG = 32;                  // keys per lane at most: sequences up to 1024 k-mers stay in registers
 constexpr u32 ENC2_CODES = 32 * ENC2_MAXREG + 16;   // residue codes staged per warp
 // The kernel is compiled for two register budgets: MAXR = 16 (batches whose longest sequence has <= 512 k-mers: every
-// seed-protein batch) keeps the register count low enough for 16 warps per SM; MAXR = 32 is picked by the host only
-// when a batch holds longer sequences.
+// seed-protein batch) keeps the register count low; MAXR = 32 is picked by the host only when a batch holds longer
+// sequences.
 
 __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
     const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)v, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(v >> 32), m);

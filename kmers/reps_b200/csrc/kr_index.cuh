@@ -46,9 +46,8 @@ struct IxGeom {      // bit layout of an index: plain values, identical on host 
 };
 
 struct KIndex {
-    const u64 *ent;  // n entries, sorted
+    const u64 *ent;  // entries, sorted by hashed key
     const u32 *dir;  // 2^D + 1 offsets
-    u32 n;
     IxGeom g;
 };
 
@@ -115,8 +114,9 @@ __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u
 
 // K4.5: the directory.  Entry i opens every D-bit prefix after its predecessor's up to its own; the last entry also
 // closes the prefixes above it.  An empty index is all zeros (memset by the host).
-__global__ void __launch_bounds__(256) k_ix_dir(const u64 *ent, u32 n, int dshift, u32 ndir, u32 *dir) {
+__global__ void __launch_bounds__(256) k_ix_dir(const u64 *ent, const u32 *total, int dshift, u32 ndir, u32 *dir) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n = *total;      // the number of entries is only known on the device (sum of the distinct-k-mer counts)
     if (i >= n) return;
     const u32 d = (u32)(ent[i] >> dshift);
     const u32 first = i ? (u32)(ent[i - 1] >> dshift) + 1 : 0;
@@ -125,9 +125,11 @@ __global__ void __launch_bounds__(256) k_ix_dir(const u64 *ent, u32 n, int dshif
 }
 
 // sum over the posting lists of m^2 (work of a self scan: every entry walks its own list) and the longest list;
-// one thread per entry, run starts only.  out[0] += sum m^2, out[1] = max m
-__global__ void __launch_bounds__(256) k_ix_work(const u64 *ent, u32 n, int idbits, unsigned long long *out) {
+// one thread per entry, run starts only.  out[0] += sum m^2, out[1] = max m, out[2] = number of entries
+__global__ void __launch_bounds__(256) k_ix_work(const u64 *ent, const u32 *total, int idbits, unsigned long long *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n = *total;
+    if (i == 0) out[2] = n;
     unsigned long long w = 0, mx = 0;
     if (i < n) {
         const u64 hk = ent[i] >> idbits;
@@ -147,12 +149,21 @@ __global__ void __launch_bounds__(256) k_ix_work(const u64 *ent, u32 n, int idbi
 
 // ---------------------------------------------------------------------------------------------------------------
 // K5: the scan.
-enum { IXQ_ARGMAX = 0, IXQ_CELLS = 1 };
+enum { IXQ_ARGMAX = 0, IXQ_CELLS = 1, IXQ_DENSE = 2 };
 constexpr u32 IXQ_WARPS = 8;            // queries in flight per CTA
-constexpr u32 IXQ_H = 1024;             // slots of a warp's score table
-constexpr u32 IXQ_FILL = 768;           // ids a pass may touch before the query is redone in more passes
+#ifndef KR_IXQ_H
+#define KR_IXQ_H 1024
+#endif
+constexpr u32 IXQ_H = KR_IXQ_H;         // slots of a warp's score table (a power of two; the tests also build a 64-slot variant)
+constexpr u32 IXQ_FILL = IXQ_H >= 256 ? IXQ_H * 3 / 4 - 32 : IXQ_H / 4;   // ids a pass may touch before the query is redone in more passes
+constexpr int ixq_log2(u32 v) { return v <= 1 ? 0 : 1 + ixq_log2(v >> 1); }
+constexpr int IXQ_SHIFT = 32 - ixq_log2(IXQ_H);
+static_assert((IXQ_H & (IXQ_H - 1)) == 0 && IXQ_H >= 64, "the score table is indexed by a multiplicative hash");
+static_assert(IXQ_FILL + 33 <= IXQ_H, "after the fill stops, each lane may still add one id");
 constexpr u32 IXQ_EMPTY = 0xFFFFFFFFu;
-constexpr u32 IXQ_SMEM_PER_WARP = IXQ_H * 4 + IXQ_H * 4 + IXQ_H * 2 + 16;   // ids, scores, touched list, counters
+// per warp: ids (u32), scores (u16, two per word), touched-slot list (u16), two counters
+constexpr u32 IXQ_SMEM_PER_WARP = IXQ_H * 4 + IXQ_H * 2 + IXQ_H * 2 + 16;
+constexpr u32 IXQ_SMEM = IXQ_WARPS * IXQ_SMEM_PER_WARP;     // 65,664 B: three CTAs (24 queries) per SM
 
 struct IxQueryParams {
     // queries: sequences [q_begin, q_end) of a set
@@ -163,9 +174,11 @@ struct IxQueryParams {
     u32 *next;                     // work counter (starts at 0)
     // ARGMAX
     const u32 *rank; int4 *partial;   // partial[q - q_begin] = (sim, first rank, last rank)
-    // CELLS: (row = q, col = id, sim, 0) for sim >= min_sim and col >= col_min(q)
+    // CELLS / DENSE: the cells (row = q, col = id) with sim >= min_sim and col >= col_min(q)
     u32 col_mode;                  // 0: every column, 1: columns > q (strict triangle), 2: columns >= 256 * (q / 256)
-    u32 min_sim; uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;
+    u32 min_sim;
+    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;      // CELLS: (row, col, sim, 0), any order
+    void *out; u32 elem, layout; u64 origin; u32 nrows, ncols;                        // DENSE: the zero-filled result
 };
 
 template <int MODE>
@@ -173,10 +186,11 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
     KR_DYN_SMEM(u32, smem_words, 16);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 *tk = smem_words + (size_t)warp * (IXQ_SMEM_PER_WARP / 4);   // ids
-    u32 *ts = tk + IXQ_H;                                            // scores
-    u16 *tl = reinterpret_cast<u16 *>(ts + IXQ_H);                   // touched slots, in insertion order
-    u32 *tc = reinterpret_cast<u32 *>(tl + IXQ_H);                   // [0] = touched count, [1] = overflow flag
-    for (u32 i = lane; i < IXQ_H; i += 32) { tk[i] = IXQ_EMPTY; ts[i] = 0; }
+    u32 *ts = tk + IXQ_H;                                            // scores: slot h is the (h & 1) half of word h >> 1
+    u16 *tl = reinterpret_cast<u16 *>(ts + IXQ_H / 2);               // touched slots, in insertion order
+    volatile u32 *tc = reinterpret_cast<volatile u32 *>(tl + IXQ_H); // [0] = touched count, [1] = "table nearly full"
+    for (u32 i = lane; i < IXQ_H; i += 32) tk[i] = IXQ_EMPTY;
+    for (u32 i = lane; i < IXQ_H / 2; i += 32) ts[i] = 0;
     if (lane == 0) { tc[0] = 0; tc[1] = 0; }
     __syncwarp();
     const bool ident_inf = (p.flags & 1u) != 0;
@@ -195,83 +209,101 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
         const u64 *kp = p.qkeys + p.qkoff[q];
         unsigned long long bf = 0, bl = 0;   // ARGMAX: (score << 32) | ~rank  and  (score << 32) | rank
         u32 col_min = 0;
-        if (MODE == IXQ_CELLS) col_min = p.col_mode == 1 ? q + 1 : p.col_mode == 2 ? (q & ~255u) : 0;
+        if (MODE != IXQ_ARGMAX) col_min = p.col_mode == 1 ? q + 1 : p.col_mode == 2 ? (q & ~255u) : 0;
+        // A pass scores the ids of one class (id % npass == pass).  One pass is the rule; when the ids a query touches
+        // do not fit the table, NOTHING of the overflowing attempt is kept (no cell emitted, no maximum taken) and the
+        // query is redone with four times as many classes, until every class fits.
         for (u32 npass = 1;; npass *= 4) {
             bool redo = false;
             bf = 0; bl = 0;
-            for (u32 pass = 0; pass < npass && !redo; ++pass) {
-                // ---- walk: every entry of the index that carries one of the query's keys scores its id -------------
-                for (u32 i = lane; i < n; i += 32) {
-                    const u64 hk = ix_hash(kp[i], g.keybits, g.keymask);
-                    const u32 b = (u32)(hk >> dshift);
-                    const u32 lo = __ldg(p.ix.dir + b), hi = __ldg(p.ix.dir + b + 1);
-                    for (u32 t = lo; t < hi; ++t) {
-                        const u64 e = __ldg(p.ix.ent + t);
-                        const u64 ek = e >> g.idbits;
-                        if (ek < hk) continue;
-                        if (ek > hk) break;
-                        const u32 id = (u32)(e & idmask);
-                        if (npass > 1 && (id % npass) != pass) continue;
-                        if (MODE == IXQ_CELLS && id < col_min && p.min_sim > 0) continue;   // a cell that is never emitted needs no score
-                        u32 h = (id * 0x9E3779B1u) >> 22;                                  // 10 bits: IXQ_H slots
-                        for (;;) {
-                            const u32 cur = tk[h];
-                            if (cur == id) break;
-                            if (cur == IXQ_EMPTY) {
-                                const u32 old = atomicCAS(&tk[h], IXQ_EMPTY, id);
-                                if (old == IXQ_EMPTY) {
-                                    const u32 pos = atomicAdd(&tc[0], 1u);
-                                    if (pos < IXQ_H) tl[pos] = (u16)h;
-                                    if (pos >= IXQ_FILL) tc[1] = 1;
-                                    break;
+            // emitting modes need every pass of this attempt to fit before the first cell leaves: try the fills first
+            const u32 rounds = (MODE != IXQ_ARGMAX && npass > 1) ? 2 : 1;
+            for (u32 round = 0; round < rounds && !redo; ++round) {
+                const bool dry = (rounds == 2 && round == 0);       // fill and clear only: does every class fit?
+                for (u32 pass = 0; pass < npass && !redo; ++pass) {
+                    // ---- walk: every entry of the index that carries one of the query's keys scores its id -----------
+                    for (u32 i = lane; i < n; i += 32) {
+                        const u64 hk = ix_hash(kp[i], g.keybits, g.keymask);
+                        const u32 b = (u32)(hk >> dshift);
+                        const u32 lo = __ldg(p.ix.dir + b), hi = __ldg(p.ix.dir + b + 1);
+                        for (u32 t = lo; t < hi; ++t) {
+                            const u64 e = __ldg(p.ix.ent + t);
+                            const u64 ek = e >> g.idbits;
+                            if (ek < hk) continue;
+                            if (ek > hk) break;
+                            const u32 id = (u32)(e & idmask);
+                            if (npass > 1 && (id % npass) != pass) continue;
+                            if (MODE != IXQ_ARGMAX && id < col_min) continue;      // a cell that is never emitted needs no score
+                            u32 h = (id * 0x9E3779B1u) >> IXQ_SHIFT;               // multiplicative hash, top log2(IXQ_H) bits
+                            for (;;) {
+                                const u32 cur = *reinterpret_cast<volatile u32 *>(&tk[h]);
+                                if (cur == id) break;
+                                if (cur == IXQ_EMPTY) {
+                                    const u32 old = atomicCAS(&tk[h], IXQ_EMPTY, id);
+                                    if (old == IXQ_EMPTY) {
+                                        const u32 pos = atomicAdd(const_cast<u32 *>(&tc[0]), 1u);
+                                        if (pos < IXQ_H) tl[pos] = (u16)h;
+                                        if (pos >= IXQ_FILL) tc[1] = 1;
+                                        break;
+                                    }
+                                    if (old == id) break;
                                 }
-                                if (old == id) break;
+                                h = (h + 1) & (IXQ_H - 1);
                             }
-                            h = (h + 1) & (IXQ_H - 1);
+                            atomicAdd(&ts[h >> 1], (h & 1) ? 0x10000u : 1u);
+                            if (tc[1]) break;      // table nearly full: stop filling (at most one more id per lane gets in)
                         }
-                        atomicAdd(&ts[h], 1u);
+                        if (tc[1]) break;
                     }
-                    if (*reinterpret_cast<volatile u32 *>(&tc[1])) break;      // table nearly full: stop filling, redo in passes
-                }
-                __syncwarp();
-                const u32 T = min(tc[0], IXQ_H);
-                redo = tc[1] != 0;
-                // ---- epilogue over the touched slots (also clears them) ------------------------------------------
-                for (u32 t0 = 0; t0 < T; t0 += 32) {
-                    const u32 t = t0 + lane;
-                    u32 id = 0, sc = 0;
-                    if (t < T) { const u32 h = tl[t]; id = tk[h]; sc = ts[h]; tk[h] = IXQ_EMPTY; ts[h] = 0; }
-                    if (redo) continue;
-                    // the equal-sequence rule: only a sequence holding every key of the query can be identical
-                    if (ident_inf && t < T && sc == n) { const SeqMeta rm = p.rmeta[id]; if (rm.size == n && seq_equal(qm, rm)) sc = KR_INF; }
-                    if (MODE == IXQ_ARGMAX) {
-                        if (t < T && sc >= (u32)(bf >> 32)) {
-                            const u32 rk = p.rank[id];
-                            const unsigned long long cf = ((unsigned long long)sc << 32) | (0xFFFFFFFFu - rk);
-                            const unsigned long long cl = ((unsigned long long)sc << 32) | rk;
-                            bf = cf > bf ? cf : bf; bl = cl > bl ? cl : bl;
+                    __syncwarp();
+                    const u32 T = min(tc[0], IXQ_H);
+                    redo = tc[1] != 0;
+                    // ---- epilogue over the touched slots (also clears them) ----------------------------------------
+                    for (u32 t0 = 0; t0 < T; t0 += 32) {
+                        const u32 t = t0 + lane;
+                        u32 id = 0, sc = 0;
+                        if (t < T) {
+                            const u32 h = tl[t];
+                            id = tk[h]; sc = (ts[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu;
+                            tk[h] = IXQ_EMPTY;
                         }
-                    } else {
-                        const bool emit = t < T && sc >= p.min_sim && id >= col_min;
-                        const u32 bal = __ballot_sync(0xffffffffu, emit);
-                        if (bal) {
-                            unsigned long long base = 0;
-                            if (lane == 0) base = atomicAdd(p.cells_count, (unsigned long long)__popc(bal));
-                            base = ((unsigned long long)__shfl_sync(0xffffffffu, (u32)(base >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)base, 0);
-                            const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
-                            if (emit && pos < p.cells_cap) p.cells[pos] = make_uint4(q, id, sc, 0u);
+                        if (redo || dry) continue;
+                        // the equal-sequence rule: only a sequence holding every key of the query can be identical
+                        if (ident_inf && t < T && sc == n) { const SeqMeta rm = p.rmeta[id]; if (rm.size == n && seq_equal(qm, rm)) sc = KR_INF; }
+                        if (MODE == IXQ_ARGMAX) {
+                            if (t < T && sc >= (u32)(bf >> 32)) {
+                                const u32 rk = p.rank[id];
+                                const unsigned long long cf = ((unsigned long long)sc << 32) | (0xFFFFFFFFu - rk);
+                                const unsigned long long cl = ((unsigned long long)sc << 32) | rk;
+                                bf = cf > bf ? cf : bf; bl = cl > bl ? cl : bl;
+                            }
+                        } else if (MODE == IXQ_CELLS) {
+                            const bool emit = t < T && sc >= p.min_sim && id >= col_min;
+                            const u32 bal = __ballot_sync(0xffffffffu, emit);
+                            if (bal) {
+                                unsigned long long base = 0;
+                                if (lane == 0) base = atomicAdd(p.cells_count, (unsigned long long)__popc(bal));
+                                base = ((unsigned long long)__shfl_sync(0xffffffffu, (u32)(base >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)base, 0);
+                                const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
+                                if (emit && pos < p.cells_cap) p.cells[pos] = make_uint4(q, id, sc, 0u);
+                            }
+                        } else {
+                            if (t < T && sc >= p.min_sim && id >= col_min && id < p.ncols) {
+                                const u64 idx = cell_index(p.layout, q, id, p.nrows, p.ncols) - p.origin;
+                                if (p.elem == 1) reinterpret_cast<u16 *>(p.out)[idx] = (u16)sc; else reinterpret_cast<int *>(p.out)[idx] = (int)sc;
+                            }
                         }
                     }
+                    __syncwarp();
+                    // two slots share a score word: clear whole words (a word next to a touched slot holds no other live score)
+                    for (u32 t = lane; t < T; t += 32) ts[tl[t] >> 1] = 0;
+                    __syncwarp();
+                    if (lane == 0) { tc[0] = 0; tc[1] = 0; }
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (lane == 0) { tc[0] = 0; tc[1] = 0; }
-                __syncwarp();
             }
             if (!redo) break;
-            // cells already emitted by the passes before the overflowing one would be emitted again: CELLS redoes nothing
-            // that way -- an overflow is detected in pass 0 of npass == 1 before anything is emitted, and later pass
-            // counts are chosen so that no pass can overflow (see below)
-            if (npass >= (1u << 24)) break;   // cannot happen: a pass then holds at most one id
+            if (npass >= (1u << 24)) break;   // cannot happen: a class then holds at most one id
         }
         if (MODE == IXQ_ARGMAX) {
             for (int o = 16; o > 0; o >>= 1) {
@@ -283,6 +315,34 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
                 const int sim = (int)(bf >> 32);
                 p.partial[qi] = make_int4(sim, sim ? (int)(0xFFFFFFFFu - (u32)bf) : -1, sim ? (int)(u32)bl : 0, 0);
             }
+        }
+    }
+}
+
+// Sequences without any k-mer (shorter than K) never meet the index, but two EQUAL ones are still "identical": under
+// KR_IDENT_IS_INFINITY their cell is INFINITY.  rows_e / cols_e list the k-mer-less sequences of the two sides (device
+// counts); one thread per (row, col) candidate pair.  Writes a dense cell (out != null) or appends a sparse cell.
+struct EmptyPairsParams {
+    const u32 *rows_e; const u32 *nrows_e; const u32 *cols_e; const u32 *ncols_e;
+    const SeqMeta *metaA, *metaB;
+    u32 row_begin, row_end, col_mode, min_sim;
+    void *out; u32 elem, layout; u64 origin; u32 nrows, ncols;
+    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;
+};
+__global__ void __launch_bounds__(256) k_ix_empty_pairs(EmptyPairsParams p) {
+    const u64 na = *p.nrows_e, nb = *p.ncols_e, total = na * nb;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x) {
+        const u32 i = p.rows_e[t / nb], j = p.cols_e[t % nb];
+        if (i < p.row_begin || i >= p.row_end) continue;
+        const u32 col_min = p.col_mode == 1 ? i + 1 : p.col_mode == 2 ? (i & ~255u) : 0;
+        if (j < col_min || (u32)KR_INF < p.min_sim) continue;
+        if (!seq_equal(p.metaA[i], p.metaB[j])) continue;
+        if (p.out) {
+            const u64 idx = cell_index(p.layout, i, j, p.nrows, p.ncols) - p.origin;
+            if (p.elem == 1) reinterpret_cast<u16 *>(p.out)[idx] = (u16)KR_INF; else reinterpret_cast<int *>(p.out)[idx] = KR_INF;
+        } else {
+            const unsigned long long pos = atomicAdd(p.cells_count, 1ull);
+            if (pos < p.cells_cap) p.cells[pos] = make_uint4(i, j, (u32)KR_INF, 0u);
         }
     }
 }

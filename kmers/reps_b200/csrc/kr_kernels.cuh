@@ -137,7 +137,7 @@ __device__ void bitonic_sort(u64 *d, u32 n, u32 tid, u32 nthr) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: one CTA per sequence: residues -> codes -> keys -> sort -> distinct keys + size + hash.
+// K1 (kr_encode.cuh): one warp per sequence: residues -> codes -> keys -> sort -> distinct keys + size + hash.
 struct EncodeParams {
     const u8 *res; const u64 *off; const u64 *koff;
     u64 *keys; SeqMeta *meta; ErrInfo *err;
@@ -148,69 +148,6 @@ struct EncodeParams {
 __device__ __forceinline__ u32 residue_code(u32 c) {
     const u32 letter = c - 'A';
     return letter < 26u ? letter : (c == '*' ? 26u : (c == '-' ? 27u : 0xFFu));
-}
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_encode_sort(EncodeParams p) {
-    KR_DYN_SMEM(u64, sk, 16);                          // smem_cap keys, then smem_cap + 16 code bytes
-    __shared__ u64 s_hash, s_prev;
-    __shared__ u32 s_wtot[THREADS / 32];
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 s = blockIdx.x;
-    const u8 *r = p.res + p.off[s];
-    const u32 L = (u32)(p.off[s + 1] - p.off[s]);
-    const int K = p.K;
-    const u32 n = L >= (u32)K ? L - K + 1 : 0;
-    u64 *dst = p.keys + p.koff[s];
-    const bool small = n <= p.smem_cap && L <= p.smem_cap + 16;
-    u64 *w = small ? sk : dst;
-    u8 *codes = reinterpret_cast<u8 *>(sk + p.smem_cap);
-    if (tid == 0) s_hash = 0;
-    __syncthreads();
-    u64 h = 0;
-    for (u32 i = tid; i < L; i += THREADS) {
-        const u32 c = r[i];
-        const u32 code = residue_code(c);
-        if (code == 0xFFu && atomicCAS(&p.err->flag, 0u, 1u) == 0u) { p.err->seq = s; p.err->pos = i; p.err->byte = c; }
-        if (small) codes[i] = (u8)code;
-        h += mix64((((u64)i << 8) | c) + 0x9E3779B97F4A7C15ULL);
-    }
-    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&s_hash), (unsigned long long)h);
-    __syncthreads();
-    if (small) {
-        for (u32 i = tid; i < n; i += THREADS) {
-            u64 key = 0;
-            for (int t = 0; t < K; ++t) key = (key << 5) | (u64)(codes[i + t] & 31);
-            w[i] = key;
-        }
-    } else {
-        for (u32 i = tid; i < n; i += THREADS) {
-            u64 key = 0;
-            for (int t = 0; t < K; ++t) key = (key << 5) | (u64)(residue_code(r[i + t]) & 31);
-            w[i] = key;
-        }
-    }
-    __syncthreads();
-    bitonic_sort(w, n, tid, THREADS);
-    // distinct keys, compacted in order (safe in place: an output index never exceeds its input index)
-    u32 out_base = 0;
-    for (u32 tile = 0; tile < n; tile += THREADS) {
-        u32 i = tile + tid;
-        bool valid = i < n;
-        u64 v = valid ? w[i] : 0;
-        bool flag = valid && (i == 0 || v != (tid == 0 ? s_prev : w[i - 1]));
-        u32 bal = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) s_wtot[warp] = __popc(bal);
-        __syncthreads();   // all reads of this tile are done; warp totals visible
-        u32 before = 0, total = 0;
-        for (u32 k = 0; k < THREADS / 32; ++k) { u32 c = s_wtot[k]; if (k < warp) before += c; total += c; }
-        if (flag) dst[out_base + before + __popc(bal & ((1u << lane) - 1))] = v;
-        if (valid && (i == n - 1 || tid == THREADS - 1)) s_prev = v;
-        out_base += total;
-        __syncthreads();
-    }
-    if (tid == 0) { SeqMeta m; m.size = out_base; m.len = L; m.hash = s_hash; m.res = r; p.meta[s] = m; }
 }
 
 // copy the key lists of selected sequences into a new compact arena (kr_seqset_gather)
@@ -470,10 +407,8 @@ struct JoinParams {
     void *out; u32 elem, layout; u64 origin;
     // ARGMAX
     u32 nsplit; const u32 *rankB; int4 *partial;
-#ifdef KR_EXPERIMENTAL
     // SPARSE: cells (row, col, sim, 0) with sim >= min_sim, appended in no particular order
     uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count; u32 min_sim;
-#endif
 };
 
 __device__ __forceinline__ u64 cell_index(u32 layout, u64 i, u64 j, u64 nrows, u64 ncols) {
@@ -797,7 +732,6 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
                     }
                 }
             }
-#ifdef KR_EXPERIMENTAL
             else if (MODE == MODE_SPARSE) {
                 // only the cells that reach min_sim leave the SM: one atomicAdd per (row, tile) that has any
                 u32 jlo = b.seq0;
@@ -821,7 +755,6 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
                         if ((m >> t) & 1u) { if (pos < p.cells_cap) p.cells[pos] = make_uint4(i, jb + t, (u32)cv[t], 0u); ++pos; }
                 }
             }
-#endif
             else {
                 // row maximum with first/last rank among the maxima
                 int m = 0;
@@ -914,191 +847,18 @@ __global__ void k_fill_u32_iota(u32 *p, u32 n, u32 base) {
 }  // namespace kr
 
 // =============================================================================================
-// K4 / K5: inverted index (key -> posting list of representative indices) for query-vs-database scans.
-//
-//   table   open addressing, linear probing, capacity = power of two >= 2 x entries:
-//           tab_key[c] (uint64, EMPTY = ~0), tab_off[c] / tab_cnt[c] (uint32): postings[off .. off+cnt)
-//   query   one CTA per query at a time; a uint16 score per representative of the slab lives in shared
-//           memory (two per 32-bit word, same packing as the join's count tile).  Two walks over the
-//           posting lists of the query's keys: accumulate + maximum in one, then clear.
-// A database larger than IDX_SLAB representatives is indexed in slabs; per-slab results are merged.
+// Helpers of the index scan (kr_index.cuh) that work on per-query partial results.
 namespace kr {
-
-constexpr u32 IDX_SLAB = 51200;                 // representatives per slab: 100 KB of scores, 2 CTAs per SM
-constexpr u32 IDX_THREADS = 256;
-constexpr u64 IDX_EMPTY = ~0ull;
-constexpr size_t IDX_SMEM = (size_t)IDX_SLAB * 2;
-
-__device__ __forceinline__ u32 idx_hash(u64 key, u32 mask) { return (u32)(mix64(key) >> 20) & mask; }
-
-// pass 1: claim a slot per distinct key and count its postings.  One CTA per representative.
-__global__ void __launch_bounds__(128) k_idx_insert(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq,
-                                                    unsigned long long *tab_key, u32 *tab_cnt, u32 mask) {
-    const u32 s = blockIdx.x;
-    if (s >= nseq) return;
-    const u32 n = meta[s].size;
-    const u64 *kp = keys + koff[s];
-    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
-        const u64 key = kp[i];
-        u32 slot = idx_hash(key, mask);
-        for (;;) {
-            unsigned long long old = atomicCAS(&tab_key[slot], (unsigned long long)IDX_EMPTY, (unsigned long long)key);
-            if (old == IDX_EMPTY || old == key) { atomicAdd(&tab_cnt[slot], 1u); break; }
-            slot = (slot + 1) & mask;
-        }
-    }
-}
-
-// exclusive scan of tab_cnt -> tab_off in three kernels (tile sums, scan of the sums, tile scan)
-constexpr u32 SCAN_TILE = 4096;
-__global__ void __launch_bounds__(256) k_scan_tile_sums(const u32 *in, u64 n, u32 *sums) {
-    __shared__ u32 ws[8];
-    const u64 base = (u64)blockIdx.x * SCAN_TILE;
-    u32 acc = 0;
-    for (u32 i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) acc += in[base + i];
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) { u32 t = 0; for (int k = 0; k < 8; ++k) t += ws[k]; sums[blockIdx.x] = t; }
-}
-__global__ void __launch_bounds__(1024) k_scan_sums(u32 *sums, u32 n) {   // in place, exclusive; one CTA
-    __shared__ u32 part[1024];
-    const u32 tid = threadIdx.x, per = (n + 1023) / 1024;
-    const u32 b0 = min(n, tid * per), b1 = min(n, b0 + per);
-    u32 acc = 0;
-    for (u32 i = b0; i < b1; ++i) acc += sums[i];
-    part[tid] = acc;
-    __syncthreads();
-    if (tid == 0) { u32 run = 0; for (int i = 0; i < 1024; ++i) { u32 v = part[i]; part[i] = run; run += v; } }
-    __syncthreads();
-    u32 run = part[tid];
-    for (u32 i = b0; i < b1; ++i) { u32 v = sums[i]; sums[i] = run; run += v; }
-}
-__global__ void __launch_bounds__(256) k_scan_tiles(const u32 *in, u64 n, const u32 *sums, u32 *out) {
-    __shared__ u32 wtot[8];
-    const u64 base = (u64)blockIdx.x * SCAN_TILE;
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // thread t owns 16 consecutive elements
-    u32 v[16], acc = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { u64 i = base + tid * 16 + k; v[k] = i < n ? in[i] : 0; acc += v[k]; }
-    u32 incl = acc;
-    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) wtot[warp] = incl;
-    __syncthreads();
-    u32 wbase = 0;
-    for (u32 k = 0; k < warp; ++k) wbase += wtot[k];
-    u32 run = sums[blockIdx.x] + wbase + incl - acc;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { u64 i = base + tid * 16 + k; if (i < n) out[i] = run; run += v[k]; }
-}
-
-// pass 2: write the postings (order inside a list is arbitrary; only counts matter)
-__global__ void __launch_bounds__(128) k_idx_fill(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq, u32 rep_base,
-                                                  const unsigned long long *tab_key, const u32 *tab_off, u32 *tab_cur, u32 mask,
-                                                  u32 *postings) {
-    const u32 s = blockIdx.x;
-    if (s >= nseq) return;
-    const u32 n = meta[s].size;
-    const u64 *kp = keys + koff[s];
-    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
-        const u64 key = kp[i];
-        u32 slot = idx_hash(key, mask);
-        while (tab_key[slot] != key) slot = (slot + 1) & mask;
-        postings[tab_off[slot] + atomicAdd(&tab_cur[slot], 1u)] = rep_base + s;
-    }
-}
-
-struct IdxQueryParams {
-    const u64 *qkeys; const u64 *qkoff; const SeqMeta *qmeta; u32 nq;
-    const unsigned long long *tab_key; const u32 *tab_off; const u32 *tab_cnt; u32 mask; const u32 *postings;
-    const SeqMeta *rmeta; const u32 *rank;   // database-wide arrays
-    u32 slab_base, slab_n;                   // representatives [slab_base, slab_base + slab_n) are in this index
-    u32 flags;
-    int4 *partial;                           // [nq] (sim, first rank, last rank)
-    u32 *next;                               // work counter
-};
-
-// One walk accumulates AND finds the maximum: atomicAdd returns the previous score, and a representative whose
-// final score is M sees the value M exactly once (its last increment), so tracking the largest value seen --
-// with the smallest / largest rank among the entries that showed it -- yields (max, first, last) without a
-// second pass.  The (offset, count) of each key's posting list is kept in shared memory for the clearing walk.
-constexpr u32 IDX_KEYCACHE = 512;    // posting ranges cached per query; longer queries re-probe when clearing
-__global__ void __launch_bounds__(IDX_THREADS, 2) k_idx_query(IdxQueryParams p) {
-    KR_DYN_SMEM(u32, score, 16);                   // (slab_n + 1) / 2 words, zero between queries
-    __shared__ u32 s_q;
-    __shared__ unsigned long long s_first[IDX_THREADS / 32], s_last[IDX_THREADS / 32];
-    __shared__ uint2 s_range[IDX_KEYCACHE];
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (u32 i = tid; i < (p.slab_n + 1) / 2; i += IDX_THREADS) score[i] = 0;
-    const bool ident_inf = (p.flags & 1u) != 0;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_q = atomicAdd(p.next, 1u);
-        __syncthreads();
-        const u32 q = s_q;
-        if (q >= p.nq) break;
-        const SeqMeta qm = p.qmeta[q];
-        const u32 n = qm.size;
-        const u64 *kp = p.qkeys + p.qkoff[q];
-        unsigned long long bf = 0, bl = 0;   // (score << 32) | ~rank  and  (score << 32) | rank
-        for (u32 i = tid; i < n; i += IDX_THREADS) {
-            const u64 key = kp[i];
-            u32 slot = idx_hash(key, p.mask);
-            unsigned long long k2;
-            while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
-            uint2 rg = make_uint2(0, 0);
-            if (k2 == key) rg = make_uint2(p.tab_off[slot], p.tab_cnt[slot]);
-            if (i < IDX_KEYCACHE) s_range[i] = rg;
-            for (u32 t = 0; t < rg.y; ++t) {
-                const u32 g = p.postings[rg.x + t], r = g - p.slab_base;
-                const u32 old = atomicAdd(&score[r >> 1], (r & 1) ? 0x10000u : 1u);
-                u32 sc = ((old >> ((r & 1) * 16)) & 0xFFFFu) + 1;
-                // the equal-sequence rule: only a representative holding every key of the query can be identical
-                if (ident_inf && sc == n) { const SeqMeta rm = p.rmeta[g]; if (rm.size == n && seq_equal(qm, rm)) sc = KR_INF; }
-                if (sc >= (u32)(bf >> 32)) {
-                    const u32 rk = p.rank[g];
-                    const unsigned long long cf = ((unsigned long long)sc << 32) | (0xFFFFFFFFu - rk);
-                    const unsigned long long cl = ((unsigned long long)sc << 32) | rk;
-                    bf = cf > bf ? cf : bf; bl = cl > bl ? cl : bl;
-                }
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long t1 = __shfl_xor_sync(0xffffffffu, bf, o), t2 = __shfl_xor_sync(0xffffffffu, bl, o);
-            bf = t1 > bf ? t1 : bf; bl = t2 > bl ? t2 : bl;
-        }
-        if (lane == 0) { s_first[warp] = bf; s_last[warp] = bl; }
-        __syncthreads();   // all increments done, per-warp maxima and cached ranges visible
-        if (tid == 0) {
-            for (u32 k = 1; k < IDX_THREADS / 32; ++k) { bf = s_first[k] > bf ? s_first[k] : bf; bl = s_last[k] > bl ? s_last[k] : bl; }
-            const int sim = (int)(bf >> 32);
-            p.partial[q] = make_int4(sim, sim ? (int)(0xFFFFFFFFu - (u32)bf) : -1, sim ? (int)(u32)bl : 0, 0);
-        }
-        // clear the touched scores
-        for (u32 i = tid; i < n; i += IDX_THREADS) {
-            uint2 rg;
-            if (i < IDX_KEYCACHE) rg = s_range[i];
-            else {
-                const u64 key = kp[i];
-                u32 slot = idx_hash(key, p.mask);
-                unsigned long long k2;
-                while ((k2 = p.tab_key[slot]) != key && k2 != IDX_EMPTY) slot = (slot + 1) & p.mask;
-                rg = k2 == key ? make_uint2(p.tab_off[slot], p.tab_cnt[slot]) : make_uint2(0, 0);
-            }
-            for (u32 t = 0; t < rg.y; ++t) { const u32 r = p.postings[rg.x + t] - p.slab_base; score[r >> 1] = 0; }
-        }
-    }
-}
 
 // queries with no k-mer at all (shorter than K): under the equal-sequence rule they still match an identical
 // representative.  One warp per such query scans the (few) representatives that are also empty.
 __global__ void k_idx_empty_queries(const SeqMeta *qmeta, u32 nq, const SeqMeta *rmeta, const u32 *rank, const u32 *empty_reps,
-                                    u32 nempty, int4 *partial) {
+                                    const u32 *nempty_ptr, int4 *partial) {
     const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= nq) return;
     const SeqMeta qm = qmeta[q];
     if (qm.size != 0) return;
+    const u32 nempty = *nempty_ptr;
     u32 rf = 0xFFFFFFFFu, rl = 0; bool any = false;
     for (u32 e = lane; e < nempty; e += 32) {
         const u32 g = empty_reps[e];
@@ -1109,7 +869,7 @@ __global__ void k_idx_empty_queries(const SeqMeta *qmeta, u32 nq, const SeqMeta 
     if (lane == 0 && any) partial[q] = make_int4(KR_INF, (int)rf, (int)rl, 0);
 }
 
-// merge per-slab partials (partial[slab * nq + q]) and turn ranks into representative indices
+// merge per-level partials (partial[level * nq + q]) and turn ranks into representative indices
 __global__ void k_idx_merge(const int4 *partial, u32 nq, u32 nslab, const u32 *order, int *best_sim, u32 *best_first, u32 *best_last) {
     const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;

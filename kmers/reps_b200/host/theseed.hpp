@@ -511,13 +511,9 @@ class FastaOutputStream {   // ">label comment", sequence wrapped at 60, LF (for
 };
 
 // ---------------------------------------------------------------------------------------------------
-// The GPU engine behind the classes: one kr_ctx per (k-mer size, alphabet) on device $KR_DEVICE (default 0).
-// An "engine key" is the k-mer size, plus 1000 for DNA contexts (DnaKmers: both strands; these need a library built
-// with the experimental DNA encoder -- the default library refuses the flag and says so).
+// The GPU engine behind the classes: one kr_ctx per k-mer size on device $KR_DEVICE (default 0).
 class KmerEngine {
   public:
-    static constexpr int DNA_KEY = 1000;
-    static constexpr uint32_t ALPHABET_DNA = 0x4000u;
     static kr_ctx *ctx(int key) {
         auto &m = map();
         auto it = m.find(key);
@@ -525,9 +521,8 @@ class KmerEngine {
         const char *d = std::getenv("KR_DEVICE");
         uint32_t flags = KR_IDENT_IS_INFINITY;
         if (const char *f = std::getenv("KR_FLAGS")) flags = (uint32_t)std::atoi(f);
-        if (key >= DNA_KEY) flags |= ALPHABET_DNA;
         kr_ctx *c = nullptr;
-        if (kr_create(d ? std::atoi(d) : 0, key % DNA_KEY, flags, &c) != KR_OK)
+        if (kr_create(d ? std::atoi(d) : 0, key, flags, &c) != KR_OK)
             throw std::runtime_error(std::string("kmersreps: ") + kr_last_error(nullptr));   // RuntimeException, App.java:129
         m[key] = c;
         return c;
@@ -554,7 +549,7 @@ inline std::shared_ptr<SetHandle> encodeStrings(int key, const std::vector<const
 }
 
 // ---------------------------------------------------------------------------------------------------
-// org.theseed.sequence.SequenceKmers: what ProteinKmers and DnaKmers share -- the k-mer set of one sequence,
+// org.theseed.sequence.SequenceKmers: the abstract base of ProteinKmers -- the k-mer set of one sequence,
 // similarity / distance / size / INFINITY.  The set itself lives on the GPU (a batch handle + an index into it).
 class SequenceKmers {
   public:
@@ -601,10 +596,10 @@ class SequenceKmers {
     }
     const std::shared_ptr<SetHandle> &handle() const { ensure(); return set_; }
     uint32_t index() const { ensure(); return idx_; }
-    int k() const { return k_ + (dna_ ? KmerEngine::DNA_KEY : 0); }   // engine key: k-mer size (+ DNA_KEY for DNA)
+    int k() const { return k_; }   // engine key: the k-mer size
 
   protected:
-    SequenceKmers(std::string seq, int k, bool dna) : sequence_(std::move(seq)), k_(k), dna_(dna) {}
+    SequenceKmers(std::string seq, int k) : sequence_(std::move(seq)), k_(k) {}
     static const SequenceKmers &deref(const SequenceKmers &p) { return p; }
     static const SequenceKmers &deref(const SequenceKmers *p) { return *p; }
     template <class T> static const SequenceKmers &deref(const std::unique_ptr<T> &p) { return *p; }
@@ -612,7 +607,6 @@ class SequenceKmers {
     void ensure() const { if (!set_) { const SequenceKmers *self = this; encodeBatch(&self, &self + 1); } }
     std::string sequence_;
     int k_ = 8;
-    bool dna_ = false;
     mutable std::shared_ptr<SetHandle> set_;
     mutable uint32_t idx_ = 0, size_ = 0;
 };
@@ -622,33 +616,10 @@ class ProteinKmers : public SequenceKmers {
     static void setKmerSize(int k) { K() = k; }   // process-global, as in the reference (RepGenomeDbProcessor.java:77-80)
     static int kmerSize() { return K(); }
     ProteinKmers() = default;
-    explicit ProteinKmers(std::string protein) : SequenceKmers(std::move(protein), K(), false) {}   // SequenceInfo.java:47
+    explicit ProteinKmers(std::string protein) : SequenceKmers(std::move(protein), K()) {}   // SequenceInfo.java:47
     const std::string &getProtein() const { return sequence_; }
   protected:
     static int &K() { static int k = 8; return k; }
-};
-
-// org.theseed.sequence.DnaKmers: the K-mers of the (lower-cased) DNA sequence and of its reverse complement
-// (SsuRepGenomeProcessor.java:88, SeqCompProcessor.java:102, TargetProcessor.java:162-193)
-class DnaKmers : public SequenceKmers {
-  public:
-    static void setKmerSize(int k) { K() = k; }   // SeqCompProcessor.java:102
-    static int kmerSize() { return K(); }
-    DnaKmers() = default;
-    explicit DnaKmers(std::string dna) : SequenceKmers(std::move(dna), K(), true) {}   // TargetProcessor.java:162
-    const std::string &getDna() const { return sequence_; }
-  protected:
-    static int &K() { static int k = 15; return k; }
-};
-
-// org.theseed.sequence.SsuGenome (SsuGenome.java:22-60): the SSU rRNA k-mers of a genome, with its id and name
-class SsuGenome : public DnaKmers {
-  public:
-    SsuGenome(std::string genomeId, std::string name, std::string dna) : DnaKmers(std::move(dna)), genomeId_(std::move(genomeId)), name_(std::move(name)) {}
-    const std::string &getGenomeId() const { return genomeId_; }
-    const std::string &getName() const { return name_; }
-  private:
-    std::string genomeId_, name_;
 };
 
 // All-vs-all similarities of a list of ProteinKmers (the rewritten double loops of

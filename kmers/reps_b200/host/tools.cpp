@@ -8,8 +8,6 @@
 //   kmers_reps gtoreps    GtoRepGenomeProcessor.java      closest representative of every genome; --create / --update add the outliers
 //   kmers_reps buildfromgtos GtoRepBuildProcessor.java     greedy representative set from a GTO directory, optional --verify report
 //   kmers_reps neighbors  NeighborProcessor.java          the N closest representatives of each input genome, ties retained
-//   kmers_reps ssureps    SsuRepGenomeProcessor.java      closest SSU-rRNA representative (by k-mer distance) of every genome of a GTO directory
-//   kmers_reps seqcomp    SeqCompProcessor.java           seed-protein distance against SSU-rRNA distance for every genome pair
 //   kmers_reps buildsets  GenomeProcessor.java + BaseGenomeProcessor.java:151-214,348-407,433-442
 //                                                       the hot part of the `genomes` pipeline: hierarchical rep sets at
 //                                                       several thresholds, saved as rep<thr>.ser + rep<thr>.list.tbl
@@ -33,8 +31,6 @@ static void usage() {
                  "  gtoreps   [--create thr] [--update newDb] [--filter ids.tbl] [--blackList ids.tbl] [--rna] [-o out] repDb gtoDir\n"
                  "  buildfromgtos [-K k] [-m sim] [--verify seeds.fa] [--batch n] gtoDir roleFile outDb\n"
                  "  neighbors [-n num] [--min sim] dbFile seeds.tbl\n"
-                 "  ssureps   [-K k] seedTable.tbl gtoDir              (DNA k-mers: needs a library with the DNA encoder)\n"
-                 "  seqcomp   [-K protK] [-k dnaK] seqTable.tbl      (DNA k-mers: needs a library with the DNA encoder)\n"
                  "  buildsets [-K k] [-t 10,50,100,200] [-p role] [--batch n] outDir input.fa\n";
 }
 
@@ -482,108 +478,6 @@ static int cmd_neighbors(int argc, char **argv) {
     return 0;
 }
 
-// ---- ssureps (SsuRepGenomeProcessor.java:104-149 + sequence/SsuRepresentation.java:41-55) -----------------------------
-// The seed table has the columns genome_id, genome_name, ssu_rna.  Every genome of the source with an SSU rRNA gets the
-// representative at the smallest k-mer DISTANCE (SSUs vary in length, :31-32); `dist < best` keeps the first minimum, and
-// the reference walks a HashSet<SsuGenome> whose order depends on an un-vendored hashCode, so ties go to table order here.
-static int cmd_ssureps(int argc, char **argv) {
-    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--kmerSize", "K"}, {"-v", "v"}, {"-t", "t"}, {"--type", "t"}}, {"K", "t"});
-    if (a.pos.size() != 2) throw std::runtime_error("ParseFailureException: Arguments \"ssuFile\" and \"inDir\" are required");
-    const int K = a.opt.count("K") ? std::stoi(a.opt["K"]) : 18;   // :80
-    if (K < 3) throw std::runtime_error("ParseFailureException: Kmer size must be at least 3.");
-    DnaKmers::setKmerSize(K);
-    std::ifstream in(a.pos[0]);
-    if (!in) throw std::runtime_error("java.io.FileNotFoundException: SSU input file " + a.pos[0] + " is not found or unreadable.");
-    std::string line;
-    std::getline(in, line);
-    if (!line.empty() && line.back() == '\r') line.pop_back();
-    auto split = [](const std::string &l) { std::vector<std::string> f; size_t b = 0; for (size_t t; (t = l.find('\t', b)) != std::string::npos; b = t + 1) f.push_back(l.substr(b, t - b)); f.push_back(l.substr(b)); return f; };
-    std::vector<std::string> hdr = split(line);
-    auto col = [&](const char *name) { auto it = std::find(hdr.begin(), hdr.end(), name); if (it == hdr.end()) throw std::runtime_error(std::string("java.io.IOException: column ") + name + " not found"); return (size_t)(it - hdr.begin()); };
-    const size_t ssuCol = col("ssu_rna"), nameCol = col("genome_name"), idCol = col("genome_id");
-    std::vector<SsuGenome> ssuList;
-    while (std::getline(in, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty()) continue;
-        auto f = split(line);
-        if (f.size() <= std::max({ssuCol, nameCol, idCol})) throw std::runtime_error("java.io.IOException: short line in " + a.pos[0]);
-        ssuList.emplace_back(f[idCol], f[nameCol], f[ssuCol]);
-    }
-    std::cout << "genome_id\tgenome_name\trep_id\trep_name\tsimilarity\tdistance\n";   // :117
-    std::vector<SsuGenome> inputs;
-    int count = 0, errCount = 0;
-    for (const std::string &file : genomeDirectory(a.pos[1])) {
-        Genome genome(file);
-        ++count;
-        if (genome.getSsuRRna().empty()) { ++errCount; continue; }   // SsuGenome.create == null :124-126
-        inputs.emplace_back(genome.getId(), genome.getName(), genome.getSsuRRna());
-    }
-    int notFound = 0;
-    if (!inputs.empty() && !ssuList.empty()) {
-        SequenceKmers::encodeBatch(inputs.begin(), inputs.end());
-        SequenceKmers::encodeBatch(ssuList.begin(), ssuList.end());
-        auto hi = inputs[0].handle(), hs = ssuList[0].handle();
-        std::vector<int32_t> sim(inputs.size() * ssuList.size());
-        kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_FULL, 0, (uint32_t)inputs.size()};
-        KmerEngine::check(hi->ctx, kr_sim_matrix(hi->ctx, hi->set, hs->set, &d, sim.data()));
-        for (size_t g = 0; g < inputs.size(); ++g) {   // SsuRepresentation.checkSsu over the list
-            double best = 1.0; size_t bi = ssuList.size();
-            for (size_t r = 0; r < ssuList.size(); ++r) {
-                const double dist = SequenceKmers::distance(sim[g * ssuList.size() + r], inputs[g], ssuList[r]);
-                if (dist < best) { best = dist; bi = r; }
-            }
-            if (bi == ssuList.size()) { ++notFound; continue; }   // isEmpty :135-137
-            std::cout << inputs[g].getGenomeId() << '\t' << inputs[g].getName() << '\t' << ssuList[bi].getGenomeId() << '\t' << ssuList[bi].getName() << '\t'
-                      << sim[g * ssuList.size() + bi] << '\t' << java::format_fixed(best, 6, 4) << '\n';
-        }
-    } else notFound = (int)inputs.size();
-    if (a.flag.count("v")) std::cerr << count << " genomes processed.  " << errCount << " missing SSUs. " << notFound << " outliers.\n";
-    return 0;
-}
-
-// ---- seqcomp (SeqCompProcessor.java:105-160) -------------------------------------------------------------
-// Input: the table SeqTableProcessor writes (:69,91): header, then genome_id, genome_name, seed protein, SSU rRNA.
-// Every pair of genomes (a genome with itself included, :112) in the order of GenomeDescriptorSet -- an un-vendored class
-// whose iteration is taken to be ascending genome id -- gets its protein k-mer distance and its DNA k-mer distance:
-// two all-vs-all matrices instead of two similarity() calls per pair.
-static int cmd_seqcomp(int argc, char **argv) {
-    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--protKmer", "K"}, {"-k", "k"}, {"--dnaKmer", "k"}, {"-v", "v"}}, {"K", "k"});
-    if (a.pos.size() != 1) throw std::runtime_error("ParseFailureException: Argument \"inFile\" is required");
-    const int protK = a.opt.count("K") ? std::stoi(a.opt["K"]) : 8, dnaK = a.opt.count("k") ? std::stoi(a.opt["k"]) : 15;   // :83-84
-    if (protK < 3) throw std::runtime_error("ParseFailureException: Protein kmer size must be at least 3.");
-    if (dnaK < 4) throw std::runtime_error("ParseFailureException: DNA kmer size must be at least 4.");
-    ProteinKmers::setKmerSize(protK);
-    DnaKmers::setKmerSize(dnaK);
-    std::ifstream in(a.pos[0]);
-    if (!in) throw std::runtime_error("java.io.FileNotFoundException: Input file " + a.pos[0] + " is not found or unreadable.");
-    struct Row { std::string id, name; };
-    std::vector<Row> rows; std::vector<ProteinKmers> seeds; std::vector<DnaKmers> rnas;
-    std::string line;
-    std::getline(in, line);   // header
-    while (std::getline(in, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty()) continue;
-        std::vector<std::string> f; size_t b = 0;
-        for (size_t t; (t = line.find('\t', b)) != std::string::npos; b = t + 1) f.push_back(line.substr(b, t - b));
-        f.push_back(line.substr(b));
-        if (f.size() < 4) throw std::runtime_error("java.io.IOException: input line needs 4 fields: " + line);
-        rows.push_back({f[0], f[1]}); seeds.emplace_back(f[2]); rnas.emplace_back(f[3]);
-    }
-    std::vector<size_t> order(rows.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return rows[x].id < rows[y].id; });
-    SimilarityMatrix pm = SimilarityMatrix::compute(seeds.begin(), seeds.end());
-    SimilarityMatrix dm = SimilarityMatrix::compute(rnas.begin(), rnas.end());
-    std::cout << "genome1\tname1\tgenome2\tname2\tseed_dist\trna_dist\n";
-    for (size_t x = 0; x < order.size(); ++x)
-        for (size_t y = x; y < order.size(); ++y) {
-            const size_t i = order[x], j = order[y];
-            std::cout << rows[i].id << '\t' << rows[i].name << '\t' << rows[j].id << '\t' << rows[j].name << '\t'
-                      << java::format_fixed(pm.distance(i, j), 6, 4) << '\t' << java::format_fixed(dm.distance(i, j), 6, 4) << '\n';
-        }
-    return 0;
-}
-
 // ---- buildsets: the similarity work of the `genomes` pipeline ------------------------------------------
 // Input: one FASTA record per genome (label = seed-protein feature id, comment = genome name, sequence = seed
 // protein) in master-list order (ProteinDataFactory orders by rating, score, id; that ordering needs PATRIC
@@ -647,8 +541,6 @@ int main(int argc, char **argv) {
         if (cmd == "gtoreps") return cmd_gtoreps(argc, argv);
         if (cmd == "buildfromgtos") return cmd_buildfromgtos(argc, argv);
         if (cmd == "neighbors") return cmd_neighbors(argc, argv);
-        if (cmd == "ssureps") return cmd_ssureps(argc, argv);
-        if (cmd == "seqcomp") return cmd_seqcomp(argc, argv);
         if (cmd == "buildsets") return cmd_buildsets(argc, argv);
         usage();
         return 2;

@@ -1,8 +1,9 @@
 """Multi-GPU plumbing (one process per GPU, torch.distributed): how the path shards and what is exchanged.
 
-The path has no data-path collective: all-vs-all shards the 256-row stripes of the result, findClosest shards
-the queries against a replicated database.  The only exchanges are result gathers, done here with plain
-torch.distributed collectives (NCCL on GPUs; gloo in the CPU tests)."""
+The path has no data-path collective: all-vs-all shards the 256-row stripes of the result (every rank encodes and
+indexes the whole batch, then scans only its rows), findClosest shards the queries against a replicated database.
+The only exchanges are result gathers, done here with plain torch.distributed collectives (NCCL on GPUs; gloo in the
+CPU tests).  encode_sharded() is the optional block-list exchange of the tile-join path."""
 from __future__ import annotations
 
 import numpy as np
@@ -147,73 +148,16 @@ def encode_sharded(ctx, d_res, off, dist):
     return full
 
 
-def encode_sharded_keys(ctx, d_res, off, dist):
-    """EXPERIMENTAL library only.  Like encode_sharded, but what is exchanged are the per-sequence KEY LISTS (the
-    posting-list all-vs-all path needs them): this rank encodes its slice, ONE all_gather moves every slice's key arena
-    and per-sequence records, and the result is imported as one ordinary set on every rank.  Arena sizes are capacities
-    (one slot per k-mer position) every rank computes from the offsets, so no size exchange is needed."""
+def allgather_cells(local_cells, count: int, cap: int, dist):
+    """Sparse result cells of every rank on every rank: ONE all_gather of capacity-padded (cap, 4) uint32 blocks plus
+    one of the counts (north_star: "NCCL allgather of per-shard results").  Returns the (total, 4) tensor."""
     import torch
-    world, rank = dist.get_world_size(), dist.get_rank()
-    nseq = len(off) - 1
-    cuts = block_shards(nseq, world)
-    local = ctx.encode_device(d_res.data_ptr(), off[cuts[rank]: cuts[rank + 1] + 1])
-    kl = ctx.export_keys(local)                            # synchronises: the arrays are complete
-    shards = []
-    for k in range(world):
-        b = kr.KeyLists()
-        b.nseq = cuts[k + 1] - cuts[k]
-        b.capacity = ctx.keylist_capacity(off[cuts[k]: cuts[k + 1] + 1])
-        shards.append(b)
-    assert kl.capacity == shards[rank].capacity and kl.nseq == shards[rank].nseq
-    kbytes = (max(b.capacity for b in shards) * 8 + 255) // 256 * 256
-    mbytes = (max(b.nseq for b in shards) * 24 + 255) // 256 * 256
-    send = torch.empty(kbytes + mbytes, dtype=torch.uint8, device=d_res.device)
-    if kl.capacity:
-        send[: kl.capacity * 8].copy_(_view(kl.keys, kl.capacity * 8, d_res.device))
-    if kl.nseq:
-        send[kbytes: kbytes + kl.nseq * 24].copy_(_view(kl.meta, kl.nseq * 24, d_res.device))
-    recv = torch.empty(world * (kbytes + mbytes), dtype=torch.uint8, device=d_res.device)
-    dist.all_gather_into_tensor(recv, send)
-    for k in range(world):
-        shards[k].keys = recv.data_ptr() + k * (kbytes + mbytes)
-        shards[k].meta = recv.data_ptr() + k * (kbytes + mbytes) + kbytes
-    _sync(d_res.device)
-    full = ctx.import_keys(shards, d_res.data_ptr(), off)  # copies out of `recv` and synchronises
-    local.free()
-    return full
-
-
-def allvsall_by_key_partition(ctx, s, d_out, dist, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI):
-    """EXPERIMENTAL library only.  All-vs-all of the set `s` (the same on every rank, with key lists: encode_sharded_keys)
-    over the ranks by KEY partition: this rank counts the pairs of its share of the k-mers over all rows
-    (kr_pairs_partial), the partial counts are exchanged with one all_to_all so that every cell reaches the rank that
-    owns its row stripe, and the owner adds them up into `d_out` (its stripe, `layout` order; kr_pairs_apply).  Every
-    step scales with 1 / world; what is exchanged is proportional to the number of pairs that share a k-mer, not to N^2.
-    Returns (row_begin, row_end) of this rank's stripe."""
-    import torch
-    world, rank = dist.get_world_size(), dist.get_rank()
-    n = s.count
-    rb = kr.matrix_stripes(n, n, layout, world)
-    d_cells, counts = ctx.pairs_partial(s, rank, world, rb)
-    dev = d_out.device
-    send_counts = torch.from_numpy(counts.astype(np.int64))
-    recv_counts = torch.empty(world, dtype=torch.int64)
-    if torch.device(dev).type == "cuda":
-        sc, rc = send_counts.to(dev), recv_counts.to(dev)
-        dist.all_to_all_single(rc, sc)
-        recv_counts = rc.cpu()
-    else:
-        dist.all_to_all_single(recv_counts, send_counts)
-    total_send, total_recv = int(counts.sum()), int(recv_counts.sum())
-    send = _view(d_cells, total_send * 16, dev) if total_send else torch.empty(0, dtype=torch.uint8, device=dev)
-    recv = torch.empty(total_recv * 16, dtype=torch.uint8, device=dev)
-    dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * 16 for c in recv_counts], input_split_sizes=[int(c) * 16 for c in counts])
-    _sync(dev)
-    ctx.pairs_partial_free(d_cells)
-    r0, r1 = int(rb[rank]), int(rb[rank + 1])
-    ctx.pairs_apply(s, recv.data_ptr(), total_recv, d_out.data_ptr(), elem=elem, layout=layout, row_begin=r0, row_end=r1)
-    ctx.synchronize()                                      # `recv` may be released once the kernels that read it are done
-    return r0, r1
+    world = dist.get_world_size()
+    counts = [torch.zeros(1, dtype=torch.int64, device=local_cells.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([count], dtype=torch.int64, device=local_cells.device))
+    recv = torch.empty((world * cap, 4), dtype=local_cells.dtype, device=local_cells.device)
+    dist.all_gather_into_tensor(recv, local_cells[:cap].contiguous())
+    return torch.cat([recv[k * cap: k * cap + int(counts[k].item())] for k in range(world)], 0)
 
 
 # ---- greedy representative-set build with the candidate-vs-database scoring split over the ranks ------------

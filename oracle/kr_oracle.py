@@ -49,28 +49,6 @@ def py_distance(sim: int, size_a: int, size_b: int) -> float:
     return 1.0 - (sim / float(size_a + size_b - sim))
 
 
-# ---- DnaKmers (org.theseed.sequence.DnaKmers, un-vendored; call sites SsuRepGenomeProcessor.java:88,
-# SeqCompProcessor.java:102, ProteinDataFactory.java:277-300, TargetProcessor.java:162-193).  [recalled] semantics:
-# the sequence is lower-cased; the set holds the K-substrings of the sequence and of its reverse complement
-# (Contig.reverse: a<->t, c<->g, u->a, anything else -> n); similarity / distance / INFINITY as for ProteinKmers.
-_DNA_COMP = {"a": "t", "c": "g", "g": "c", "t": "a", "u": "a"}
-
-
-def py_dna_revcomp(seq: str) -> str:
-    return "".join(_DNA_COMP.get(ch, "n") for ch in reversed(seq.lower()))
-
-
-def py_dna_kmers(seq: str, K: int = 15) -> set:
-    s, r = seq.lower(), py_dna_revcomp(seq)
-    return {s[i:i + K] for i in range(len(s) - K + 1)} | {r[i:i + K] for i in range(len(r) - K + 1)}
-
-
-def py_dna_similarity(a: str, b: str, K: int = 15, ident_inf: bool = True) -> int:
-    if ident_inf and a.lower() == b.lower():
-        return INFINITY
-    return len(py_dna_kmers(a, K) & py_dna_kmers(b, K))
-
-
 def java_string_hash(s: str) -> int:
     h = 0
     for ch in s:

@@ -7,7 +7,6 @@ Follows (all under src/main/java/org/theseed/proteins/kmers/reps/):
   group      RepMatrixProcessor.java:88-125 + SequenceInfo.java:62-148 (double accumulation in that exact order)
   classify   ClassifyProcessor.java:112-120
   neighbors  NeighborProcessor.java:155-230 (insertion-sorted top-N with tie retention; Double.toString columns)
-  seqcomp    SeqCompProcessor.java:105-137 (every genome pair, self pairs included: protein and DNA k-mer distances)
   buildsets  BaseGenomeProcessor.java:151-214 (collateGenomes / copyReps / buildRepGenSet), :348-407 (list files)
 """
 import math
@@ -225,25 +224,6 @@ def neighbors(db_reps, seeds, num=5, min_sim=1, K=8, ident_inf=True):
     return "\n".join(out) + "\n"
 
 
-def seqcomp(rows, K=8, dna_k=15):
-    """rows: [(genome_id, name, seed_protein, ssu_rna)] -> report text.  Pair order: ascending genome id (the iteration
-    order assumed for the un-vendored GenomeDescriptorSet), each genome with itself and with every later one."""
-    o = ko.get()
-    rows = sorted(rows, key=lambda r: r[0])
-    pb = o.batch([r[2] for r in rows], K=K)
-    pm = o.sim_matrix(pb, ident_inf=True, threads=4)
-    ps = pb.sizes()
-    dsets = [ko.py_dna_kmers(r[3], dna_k) for r in rows]
-    out = ["genome1\tname1\tgenome2\tname2\tseed_dist\trna_dist"]
-    for i in range(len(rows)):
-        for j in range(i, len(rows)):
-            pd = o.distance(int(pm[i, j]), ps[i], ps[j])
-            dsim = ko.INFINITY if rows[i][3].lower() == rows[j][3].lower() else len(dsets[i] & dsets[j])
-            dd = o.distance(dsim, len(dsets[i]), len(dsets[j]))
-            out.append("%s\t%s\t%s\t%s\t%s\t%s" % (rows[i][0], rows[i][1], rows[j][0], rows[j][1], ko.java_fixed(pd, 6, 4), ko.java_fixed(dd, 6, 4)))
-    return "\n".join(out) + "\n"
-
-
 def gtoreps(db_reps, threshold, genomes, update, K=8):
     """GtoRepGenomeProcessor.java:198,270-314.  db_reps: [(fid, name, seq)] of the loaded database in file order (empty for
     --create); genomes: [(fid, genome_name, seq)] in processing order (deferrals last); update: outliers are added.
@@ -287,25 +267,4 @@ def buildfromgtos_verify(db_reps, threshold, queries, K=8):
         for q, s in zip(queries, bs):
             if s < threshold:
                 out.append("%s\t%s\t%d" % (q[0], q[1], s))
-    return "\n".join(out) + "\n"
-
-
-def ssureps(table, genomes, K=18):
-    """SsuRepGenomeProcessor.java:104-149.  table: [(genome_id, name, ssu_rna)] in file order; genomes: [(genome_id, name,
-    ssu_rna)] in directory order (those without an SSU are skipped).  Smallest distance wins, first in table order on ties."""
-    o = ko.get()
-    tsets = [ko.py_dna_kmers(t[2], K) for t in table]
-    out = ["genome_id\tgenome_name\trep_id\trep_name\tsimilarity\tdistance"]
-    for (gid, name, ssu) in genomes:
-        if not ssu:
-            continue
-        q = ko.py_dna_kmers(ssu, K)
-        best, bi, bsim = 1.0, -1, 0
-        for r, t in enumerate(table):
-            sim = ko.INFINITY if ssu.lower() == t[2].lower() else len(q & tsets[r])
-            d = o.distance(sim, len(q), len(tsets[r]))
-            if d < best:
-                best, bi, bsim = d, r, sim
-        if bi >= 0:
-            out.append("%s\t%s\t%s\t%s\t%d\t%s" % (gid, name, table[bi][0], table[bi][1], bsim, ko.java_fixed(best, 6, 4)))
     return "\n".join(out) + "\n"

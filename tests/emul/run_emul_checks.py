@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: runs the product's device + host code on the CPU emulator (tests/emul/cuda_emul.h) and
 compares with the oracle.  Started by tests/test_emul_device_code.py in a subprocess with KR_LIB_PATH pointing at
-tests/emul/_build/libkmersreps_emul.so (the product sources compiled by g++ with -DKR_EMUL -DKR_EXPERIMENTAL).
+tests/emul/_build/libkmersreps_emul.so (the product sources compiled by g++ with -DKR_EMUL).
 
     python tests/emul/run_emul_checks.py <case>
 """
@@ -42,61 +42,192 @@ def want_cells(dense, min_sim, triangle, row0=0):
     return {(int(i) + row0, int(j), int(dense[i, j])) for i, j in zip(ii, jj) if not triangle or j > i + row0}
 
 
+PATHS = (kr.FORCE_JOIN, kr.FORCE_INDEX, 0)      # tile join pinned, index scan pinned, the library's own choice
+
+
 def case_matrix_layouts():
-    """encode + block lists + TMA-staged tile join: every layout / element type, two blocks, the equal-sequence rule"""
-    seqs = family(11, 300, 6, 60, 140) + ["MKV", "", "MKVLAAGIVG", "MKVLAAGIVG"]
+    """encode + (block lists + TMA-staged tile join | sorted index + warp scan): every layout / element type, two blocks,
+    the equal-sequence rule incl. k-mer-less equal sequences"""
+    seqs = family(11, 300, 6, 60, 140) + ["MKV", "", "MKVLAAGIVG", "MKVLAAGIVG", "MKV", ""]
     seqs[7] = seqs[290]                               # equal sequences in different blocks
+    n = len(seqs)
     for ident in (kr.IDENT_IS_INFINITY, 0):
         want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=bool(ident), threads=4)
-        c = kr.Context(device=0, K=8, flags=ident)
-        s = c.encode(seqs)
-        assert (s.sizes() == O.batch(seqs, K=8).sizes()).all()
-        assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all()
-        assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE) == want[np.triu_indices(len(seqs), 1)]).all()
-        assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all()
-        hi = c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_BLOCKTRI, row_begin=256, row_end=len(seqs))
-        assert (hi == blocktri(want)[-len(hi):]).all()
-        c.close()
+        for path in PATHS:
+            c = kr.Context(device=0, K=8, flags=ident | path)
+            s = c.encode(seqs)
+            assert (s.sizes() == O.batch(seqs, K=8).sizes()).all()
+            assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all(), (ident, path)
+            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE) == want[np.triu_indices(n, 1)]).all(), (ident, path)
+            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all(), (ident, path)
+            hi = c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_BLOCKTRI, row_begin=256, row_end=n)
+            assert (hi == blocktri(want)[-len(hi):]).all(), (ident, path)
+            lo = c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL, row_begin=0, row_end=256)
+            assert (lo == want[:256]).all(), (ident, path)
+            c.close()
 
 
 def case_k10_rectangular_pairs():
-    """32-bit low words (K = 10, three pipeline stages), rectangular matrix, explicit pairs, key decoding"""
+    """32-bit low words (K = 10, three pipeline stages) in the join; 50-bit keys in the index; rectangular matrix,
+    explicit pairs, key decoding"""
     seqs = family(12, 90, 3, 50, 120)
-    c = kr.Context(device=0, K=10, flags=0)
-    a, b = c.encode(seqs[:40]), c.encode(seqs[30:])
     oa, ob = O.batch(seqs[:40], K=10), O.batch(seqs[30:], K=10)
-    assert (c.sim_matrix(a, b) == O.sim_matrix(oa, ob, ident_inf=False)).all()
-    ia, ib = np.arange(40, dtype=np.uint32), np.arange(40, dtype=np.uint32)[::-1].copy()
-    sim, ident = c.sim_pairs(a, ia, b, ib)
     full = O.sim_matrix(oa, ob, ident_inf=False)
-    assert (sim == full[ia, ib]).all()
-    assert sorted(a.kmers(3)) == sorted(ko.py_kmers(seqs[3], 10))
+    for path in PATHS:
+        c = kr.Context(device=0, K=10, flags=path)
+        a, b = c.encode(seqs[:40]), c.encode(seqs[30:])
+        assert (c.sim_matrix(a, b) == full).all(), path
+        ia, ib = np.arange(40, dtype=np.uint32), np.arange(40, dtype=np.uint32)[::-1].copy()
+        sim, ident = c.sim_pairs(a, ia, b, ib)
+        assert (sim == full[ia, ib]).all()
+        assert sorted(a.kmers(3)) == sorted(ko.py_kmers(seqs[3], 10))
+        c.close()
+    # K = 11: 55-bit keys leave 9 id bits -- a set of 90 fits the index, a database (ids sized for growth) does not
+    c = kr.Context(device=0, K=11, flags=kr.IDENT_IS_INFINITY)
+    s = c.encode(seqs)
+    w11 = O.sim_matrix(O.batch(seqs, K=11), ident_inf=True)
+    assert (c.sim_matrix(s) == w11).all()
+    db = c.db(); db.append(seqs[:60])
+    sim, first, _ = db.find_closest(c.encode(seqs[60:]))
+    bs, bi = O.find_closest(O.batch(seqs[:60], K=11), O.batch(seqs[60:], K=11))
+    assert (sim == bs).all() and (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
     c.close()
 
 
 def case_find_closest_and_build():
-    """ARGMAX join, inverted index (forced), ranks / ties, greedy build with database compaction"""
+    """ARGMAX join and index scan (pinned and chosen), ranks / ties, greedy build with database compaction and the
+    two-level index (main + tail) growing batch by batch"""
     seqs = family(13, 330, 8, 60, 130)
-    reps, qs = seqs[:270], seqs[270:] + [seqs[5], "MKV"]
+    reps, qs = seqs[:270], seqs[270:] + [seqs[5], "MKV", ""]
+    reps[20] = "MKV"
     ob, oq = O.batch(reps, K=8), O.batch(qs, K=8)
     rng = np.random.default_rng(3)
     rank = rng.permutation(len(reps)).astype(np.uint32)
     order = np.argsort(rank)
     bs, bi = O.find_closest(ob, oq, order=order.astype(np.int32), ident_inf=True)
-    for force in (kr.FORCE_JOIN, kr.FORCE_INDEX):
-        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | force)
+    bs2, bl2 = O.find_closest(ob, oq, order=order.astype(np.int32), ident_inf=True, tie_last=True)
+    for path in PATHS:
+        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | path)
         db = c.db()
         db.append(reps[:100]); db.append(reps[100:])
         db.set_ranks(rank)
         sim, first, last = db.find_closest(c.encode(qs))
-        assert (sim == bs).all(), force
-        assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), force
+        assert (sim == bs).all(), path
+        assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), path
+        assert (last.astype(np.int64) == np.where(bs2 > 0, bl2.astype(np.int64), kr.NO_REP)).all(), path
+        assert (db.any_ge(c.encode(qs), 25) == (bs >= 25)).all()
         c.close()
+    cand = list(seqs)
+    cand[50:50] = ["MKV", "MKV", "", "MKVLAAGIVG", "MKVLAAGIVG"]
+    for thr in (30, 10):
+        _, want, _ = O.greedy_build(O.batch(cand, K=8), thr, ident_inf=True)
+        for path in (kr.FORCE_JOIN, 0):
+            for batch in (40, 4096):                                        # 40: many small segments -> db_compact, tail rebuilds
+                c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | path)
+                db = c.db()
+                a0 = db.greedy_build(c.encode(cand[:120]), thr, batch=batch)     # fills the database ...
+                a1 = db.greedy_build(c.encode(cand[120:]), thr, batch=batch)     # ... which the second call extends
+                assert (np.concatenate([a0, a1]) == want).all(), (thr, path, batch)
+                assert db.size == int(want.sum())
+                # the grown database answers like a fresh one
+                sim, first, _ = db.find_closest(c.encode(qs))
+                acc = [cand[i] for i in np.nonzero(want)[0]]
+                bs3, bi3 = O.find_closest(O.batch(acc, K=8), oq, ident_inf=True)
+                assert (sim == bs3).all() and (first.astype(np.int64) == np.where(bs3 > 0, bi3.astype(np.int64), kr.NO_REP)).all(), (thr, path, batch)
+                c.close()
+    _, w0, _ = O.greedy_build(O.batch(cand[:60], K=8), 0, ident_inf=True)   # threshold 0: the first candidate represents everything
     c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
-    db = c.db()
-    added = db.greedy_build(c.encode(seqs), 30, batch=40)      # many small segments: db_compact runs
-    _, want, _ = O.greedy_build(O.batch(seqs, K=8), 30, ident_inf=True)
-    assert (added == want).all() and db.size == int(want.sum())
+    assert (c.db().greedy_build(c.encode(cand[:60]), 0, batch=16) == w0).all() and w0.sum() == 1
+    c.close()
+
+
+def case_index_crowded():
+    """the exactness paths of the index: a k-mer shared by 5,000 sequences (a build prefix larger than the shared-memory
+    sort, a posting list longer than a score table), queries that touch more ids than a table holds (4 / 16 passes),
+    for ARGMAX, sparse cells and dense cells"""
+    rng = np.random.default_rng(21)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    rnd = lambda n: alpha[rng.integers(0, 20, n)].tobytes().decode()
+    hub = "MKVLAAGI"
+    reps = [rnd(24) for _ in range(900)] + [rnd(8) + hub + rnd(8) for _ in range(5000)]
+    fam = [reps[i][:12] + rnd(6) + reps[i][18:] for i in (5, 17, 3300, 4000)]          # near copies: clear best matches
+    qs = fam + [rnd(10) + hub + rnd(10), hub, reps[77], rnd(30), reps[3200][8:16] + rnd(5)]
+    order = rng.permutation(len(reps)).astype(np.uint32)
+    ob, oq = O.batch(reps, K=8), O.batch(qs, K=8)
+    bs, bi = O.find_closest(ob, oq, order=np.argsort(order).astype(np.int32), ident_inf=True, threads=4)
+    bs2, bl2 = O.find_closest(ob, oq, order=np.argsort(order).astype(np.int32), ident_inf=True, tie_last=True, threads=4)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_INDEX)
+    db = c.db(); db.append(reps); db.set_ranks(order)
+    Q = c.encode(qs)
+    sim, first, last = db.find_closest(Q)
+    assert (sim == bs).all()
+    assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
+    assert (last.astype(np.int64) == np.where(bs2 > 0, bl2.astype(np.int64), kr.NO_REP)).all()
+    assert bs[5] == 1 and bi[5] != bl2[5]                                           # the hub query ties over 5,000 representatives
+    # the same crowd as a matrix: 9 query rows x 5,900 columns, dense and sparse
+    R = c.encode(reps)
+    want = O.sim_matrix(oq, ob, ident_inf=True, threads=4)
+    assert (c.sim_matrix(Q, R, elem=kr.ELEM_U16) == want).all()
+    got = c.sim_matrix_sparse(Q, R, min_sim=1, layout=kr.LAYOUT_FULL, cap=1 << 16)
+    assert len(cells(got)) == len(got) and cells(got) == want_cells(want, 1, False)
+    c.close()
+
+
+def case_sparse_matrix():
+    """kr_sim_matrix_sparse through both paths: thresholds, too little room (retried), row stripes, rectangular"""
+    seqs = family(15, 300, 6, 60, 120) + ["MKV", "", "MKV"]
+    seqs[5] = seqs[280] = "MKV"
+    want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=True, threads=4)
+    for path in PATHS:
+        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | path)
+        s = c.encode(seqs)
+        for min_sim in (1, 20, 9999):
+            got = c.sim_matrix_sparse(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
+            assert len(cells(got)) == len(got) and cells(got) == want_cells(want, min_sim, True), (path, min_sim)
+        got = c.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, cap=16)       # too little room: retried
+        assert cells(got) == want_cells(want, 1, True), path
+        got = c.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=256, row_end=len(seqs))
+        assert cells(got) == want_cells(want[256:], 1, True, row0=256), path
+        q = c.encode(seqs[:290])
+        got = c.sim_matrix_sparse(q, s, min_sim=10, layout=kr.LAYOUT_FULL, row_begin=256, row_end=290)
+        assert cells(got) == want_cells(want[256:290], 10, False, row0=256), path
+        c.close()
+
+
+def case_encode_warp():
+    """K1, one warp per sequence (register bitonic network): every register budget, the in-memory path for very long
+    sequences, repeats, all K; keys come back sorted and distinct"""
+    rng = np.random.default_rng(9)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX*-", dtype=np.uint8)
+    lens = [0, 1, 7, 8, 9, 40, 70, 71, 72, 73, 135, 136, 137, 263, 264, 265, 300, 519, 520, 521, 800, 1031, 1032, 1033, 1100, 2500]
+    seqs = [alpha[rng.integers(0, len(alpha), n)].tobytes().decode() for n in lens]
+    seqs += ["A" * 50, "AC" * 200, "ACDEFGHIK" * 130, seqs[10], seqs[24]]            # repeats (few distinct k-mers), duplicates
+    seqs += family(17, 40, 3, 200, 420)
+    for K in (8, 3, 11):
+        ob = O.batch(seqs, K=K)
+        want = O.sim_matrix(ob, ident_inf=True, threads=4)
+        c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY)
+        s = c.encode(seqs)
+        assert (s.sizes() == ob.sizes()).all(), K
+        for i in range(len(seqs)):
+            k = s.keys(i)
+            assert (np.diff(k.astype(np.int64)) > 0).all(), (K, i)                 # sorted, distinct
+            if i % 4 == 0:
+                assert sorted(s.kmers(i)) == sorted(ko.py_kmers(seqs[i], K)), (K, i)
+        assert (c.sim_matrix(s, elem=kr.ELEM_U16) == want).all(), K                # equal-sequence rule: hashes agree
+        c.close()
+    short = [q for q in seqs if len(q) <= 500]                                     # batch served by the 16-register build
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    s = c.encode(short)
+    assert (s.sizes() == O.batch(short, K=8).sizes()).all()
+    assert (c.sim_matrix(s, elem=kr.ELEM_U16) == O.sim_matrix(O.batch(short, K=8), ident_inf=True, threads=4)).all()
+    c.close()
+    c = kr.Context(device=0, K=8, flags=0)
+    try:
+        c.encode(["MKVLAAGIVG", "MKVLAbGIVGAAAA"])
+        raise AssertionError("a residue outside the alphabet must fail")
+    except kr.KrError as e:
+        assert e.code == -4 and "sequence 1 position 5" in str(e)
     c.close()
 
 
@@ -216,215 +347,6 @@ def case_api_misc():
     sd.free()
     assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL, row_begin=512, row_end=600) == want[512:]).all()   # still usable
     c.close()
-
-
-def case_exp_sparse_join():
-    """EXPERIMENTAL: sparse result from the join's epilogue filter"""
-    seqs = family(15, 300, 6, 60, 120)
-    seqs[5] = seqs[280] = "MKV"
-    want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=True, threads=4)
-    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
-    s = c.encode(seqs)
-    for min_sim in (1, 20, 9999):
-        got = c.sim_matrix_sparse(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
-        assert len(cells(got)) == len(got) and cells(got) == want_cells(want, min_sim, True)
-    got = c.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, cap=16)       # too little room: retried
-    assert cells(got) == want_cells(want, 1, True)
-    q = c.encode(seqs[:290])
-    got = c.sim_matrix_sparse(q, s, min_sim=10, layout=kr.LAYOUT_FULL, row_begin=256, row_end=290)
-    assert cells(got) == want_cells(want[256:290], 10, False, row0=256)
-    c.close()
-
-
-def case_exp_pairs():
-    """EXPERIMENTAL: posting-list all-vs-all (dense, every layout) and the pair-table sparse result, end to end"""
-    seqs = family(16, 300, 6, 60, 120) + ["MKV", "", "MKVLAAGIVG", "MKVLAAGIVG", "MKV"]
-    seqs[7] = seqs[290]
-    n = len(seqs)
-    for ident in (kr.IDENT_IS_INFINITY, 0):
-        want = O.sim_matrix(O.batch(seqs, K=8), ident_inf=bool(ident), threads=4)
-        for mode in (binding.EXP_PAIRS, binding.EXP_PAIRS_AUTO, binding.EXP_PAIRS | binding.EXP_BUCKETS, binding.EXP_PAIRS_AUTO | binding.EXP_BUCKETS):
-            if os.environ.get("KR_EMUL_ONLY_BUCKETS") and not (mode & binding.EXP_BUCKETS):
-                continue
-            c = kr.Context(device=0, K=8, flags=ident | mode)
-            s = c.encode(seqs)
-            assert (c.sim_matrix(s, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all()
-            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE) == want[np.triu_indices(n, 1)]).all()
-            assert (c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all()
-            lo = c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=0, row_end=256)
-            hi = c.sim_matrix(s, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=256, row_end=n)
-            assert (np.concatenate([lo, hi]) == blocktri(want)).all()
-            if ident:
-                for min_sim in (1, 15):
-                    got = c.sim_matrix_sparse(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
-                    assert len(cells(got)) == len(got) and cells(got) == want_cells(want, min_sim, True)
-                got = c.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=256, row_end=n)
-                assert cells(got) == want_cells(want[256:], 1, True, row0=256)
-                db = c.db()
-                added = db.greedy_build(s, 30, batch=64)                 # survivor matrices through the same path
-                _, w2, _ = O.greedy_build(O.batch(seqs, K=8), 30, ident_inf=True)
-                assert (added == w2).all()
-            c.close()
-
-
-def case_exp_encode_warp():
-    """EXPERIMENTAL: K1 with one warp per sequence (register bitonic network): every register budget, the in-memory path
-    for very long sequences, repeats, all K"""
-    rng = np.random.default_rng(9)
-    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX*-", dtype=np.uint8)
-    lens = [0, 1, 7, 8, 9, 40, 70, 71, 72, 73, 135, 136, 137, 263, 264, 265, 300, 519, 520, 521, 800, 1031, 1032, 1033, 1100, 2500]
-    seqs = [alpha[rng.integers(0, len(alpha), n)].tobytes().decode() for n in lens]
-    seqs += ["A" * 50, "AC" * 200, "ACDEFGHIK" * 130, seqs[10], seqs[24]]            # repeats (few distinct k-mers), duplicates
-    seqs += family(17, 40, 3, 200, 420)
-    for K in (8, 3, 11):
-        ob = O.batch(seqs, K=K)
-        want = O.sim_matrix(ob, ident_inf=True, threads=4)
-        c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY | binding.EXP_ENCODE)
-        s = c.encode(seqs)
-        assert (s.sizes() == ob.sizes()).all(), K
-        ref = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY)
-        s0 = ref.encode(seqs)
-        for i in range(len(seqs)):
-            assert (s.keys(i) == s0.keys(i)).all(), (K, i)
-        assert (c.sim_matrix(s, elem=kr.ELEM_U16) == want).all(), K                # equal-sequence rule: same hashes
-        c.close(); ref.close()
-    short = [q for q in seqs if len(q) <= 500]                                     # batch served by the 16-register build
-    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_ENCODE)
-    s = c.encode(short)
-    assert (s.sizes() == O.batch(short, K=8).sizes()).all()
-    assert (c.sim_matrix(s, elem=kr.ELEM_U16) == O.sim_matrix(O.batch(short, K=8), ident_inf=True, threads=4)).all()
-    c.close()
-    c = kr.Context(device=0, K=8, flags=binding.EXP_ENCODE)
-    try:
-        c.encode(["MKVLAAGIVG", "MKVLAbGIVGAAAA"])
-        raise AssertionError("a residue outside the alphabet must fail")
-    except kr.KrError as e:
-        assert e.code == -4 and "sequence 1 position 5" in str(e)
-    c.close()
-
-
-def case_exp_idxq_warp():
-    """EXPERIMENTAL: K5 with one warp per query -- dense per-warp scores (small database), per-warp hash (large database,
-    short posting lists), and the multi-pass path of a query that touches more representatives than the hash holds"""
-    rng = np.random.default_rng(21)
-    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
-    rnd = lambda n: alpha[rng.integers(0, 20, n)].tobytes().decode()
-    # (a) dense: a family-structured database of 300, ties and ranks, identical and k-mer-less queries
-    seqs = family(18, 340, 8, 60, 130)
-    reps, qs = seqs[:300], seqs[300:] + [seqs[5], "MKV", ""]
-    reps[20] = "MKV"
-    rank = rng.permutation(len(reps)).astype(np.uint32)
-    bs, bi = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(rank).astype(np.int32), ident_inf=True)
-    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_INDEX | binding.EXP_IDXQ)
-    db = c.db(); db.append(reps); db.set_ranks(rank)
-    sim, first, last = db.find_closest(c.encode(qs))
-    assert (sim == bs).all() and (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
-    bs2, bl2 = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(rank).astype(np.int32), ident_inf=True, tie_last=True)
-    assert (last.astype(np.int64) == np.where(bs2 > 0, bl2.astype(np.int64), kr.NO_REP)).all()
-    c.close()
-    # (b) hash: 4,300 short representatives (> IDXQ2_DENSE_MAX), 1,150 of which share one 8-mer with the hub queries
-    hub = "MKVLAAGI"
-    reps = [rnd(24) for _ in range(3150)] + [rnd(8) + hub + rnd(8) for _ in range(1150)]
-    fam = [reps[i][:12] + rnd(6) + reps[i][18:] for i in (5, 17, 3300, 4000)]          # near copies: clear best matches
-    qs = fam + [rnd(10) + hub + rnd(10), hub, reps[77], rnd(30), reps[3200][8:16] + rnd(5)]
-    order = rng.permutation(len(reps)).astype(np.uint32)
-    bs, bi = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(order).astype(np.int32), ident_inf=True, threads=4)
-    bs2, bl2 = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=np.argsort(order).astype(np.int32), ident_inf=True, tie_last=True, threads=4)
-    for flags in (binding.EXP_IDXQ, 0):                                              # 0: the CTA kernel, same expectations
-        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_INDEX | flags)
-        db = c.db(); db.append(reps); db.set_ranks(order)
-        sim, first, last = db.find_closest(c.encode(qs))
-        assert (sim == bs).all(), flags
-        assert (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), flags
-        assert (last.astype(np.int64) == np.where(bs2 > 0, bl2.astype(np.int64), kr.NO_REP)).all(), flags
-        c.close()
-    assert bs[5] == 1 and bi[5] != bl2[5], (bs, bi, bl2)                             # the hub query ties over 1,150 representatives
-
-
-def case_exp_gidx_build():
-    """EXPERIMENTAL: greedy build through the growing index -- against the oracle and the default build, starting from a
-    non-empty database, with k-mer-less and duplicate candidates, several batch sizes, and a candidate whose k-mers
-    reach more representatives than the per-warp table holds (multi-pass path)"""
-    rng = np.random.default_rng(31)
-    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
-    rnd = lambda n: alpha[rng.integers(0, 20, n)].tobytes().decode()
-    seqs = family(19, 420, 9, 60, 130)
-    seqs[50:50] = ["MKV", "MKV", "", "MKVLAAGIVG", "MKVLAAGIVG"]
-    first, rest = seqs[:120], seqs[120:] + ["MKV", seqs[3]]
-    for thr in (30, 10):
-        _, w0, _ = O.greedy_build(O.batch(first + rest, K=8), thr, ident_inf=True)
-        for batch in (37, 4096):
-            c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_GIDX)
-            db = c.db()
-            a0 = db.greedy_build(c.encode(first), thr, batch=batch)             # fills the database ...
-            a1 = db.greedy_build(c.encode(rest), thr, batch=batch)              # ... which the second call must index first
-            assert (np.concatenate([a0, a1]) == w0).all(), (thr, batch)
-            assert db.size == int(w0.sum())
-            c.close()
-    hub = "MKVLAAGI"
-    crowd = [rnd(9) + hub + rnd(9) for _ in range(1150)]                        # pairwise similarity 1: all become representatives
-    cands = crowd + [rnd(5) + hub + rnd(30), crowd[7][:20] + rnd(4), rnd(40)]
-    _, want, _ = O.greedy_build(O.batch(cands, K=8), 5, ident_inf=True)
-    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | binding.EXP_GIDX)
-    db = c.db()
-    got = db.greedy_build(c.encode(cands), 5, batch=400)
-    assert (got == want).all() and want.sum() > 1100 and not want[1151]      # > 1024 representatives on the hub k-mer's list
-    c.close()
-
-
-def dna_family(seed, n, length):
-    rng = np.random.default_rng(seed)
-    alpha = np.frombuffer(b"acgt", dtype=np.uint8)
-    roots = [alpha[rng.integers(0, 4, length)] for _ in range(4)]
-    seqs = []
-    for i in range(n):
-        s = roots[i % 4].copy()
-        pos = rng.integers(0, length, 2 + 6 * (i % 5))
-        s[pos] = alpha[rng.integers(0, 4, len(pos))]
-        t = s[: int(rng.integers(length * 2 // 3, length + 1))].tobytes().decode()
-        if i % 7 == 3:
-            t = ko.py_dna_revcomp(t)                       # the other strand of a relative: same k-mer set
-        if i % 5 == 1:
-            t = t.upper()                                 # case does not matter
-        if i % 11 == 4:
-            t = t[:40] + "n" + t[41:]
-        seqs.append(t)
-    return seqs
-
-
-def case_exp_dna():
-    """EXPERIMENTAL: DnaKmers contexts -- K-mers of both strands through the unchanged join / index / posting-list paths"""
-    seqs = dna_family(51, 60, 420) + ["acgtacgtac", "", "ACGTACGTAC", "acgu" * 12, "tttttttttttttttttttttttttttt", "aaaaaaaaaaaaaaaaaaaaaaaaaaaa"]
-    seqs[9] = seqs[2].upper()                              # equal sequences up to case: INFINITY
-    for K in (18, 15, 7):
-        want = np.array([[ko.py_dna_similarity(a, b, K, True) for b in seqs] for a in seqs], dtype=np.int64)
-        sizes = np.array([len(ko.py_dna_kmers(q, K)) for q in seqs])
-        for extra in (0, binding.EXP_PAIRS | binding.EXP_BUCKETS):
-            c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY | binding.ALPHABET_DNA | extra)
-            s = c.encode(seqs)
-            assert (s.sizes() == sizes).all(), (K, extra)
-            assert (c.sim_matrix(s, elem=kr.ELEM_I32) == want).all(), (K, extra)
-            assert sorted(s.kmers(0)) == sorted(ko.py_dna_kmers(seqs[0], K))
-            db = c.db()
-            db.append(seqs[:40])
-            sim, first, _ = db.find_closest(c.encode(seqs[40:]))
-            sub = want[40:, :40]
-            assert (sim == sub.max(1)).all() and (first == np.where(sub.max(1) > 0, sub.argmax(1), kr.NO_REP)).all()
-            c.close()
-    assert want[-2, -1] == len(ko.py_dna_kmers("t" * 28, 7)) == 2      # poly-t and poly-a are each other's reverse complement
-    c = kr.Context(device=0, K=15, flags=binding.ALPHABET_DNA)
-    try:
-        c.encode(["acgtacgtacgtacgtacgt", "acgtacgtrcgtacgtacgt"])
-        raise AssertionError("an ambiguity code must fail")
-    except kr.KrError as e:
-        assert e.code == -4 and "sequence 1 position 8" in str(e)
-    c.close()
-    for badK in (4, 19):
-        try:
-            kr.Context(device=0, K=badK, flags=binding.ALPHABET_DNA)
-            raise AssertionError("K outside [5,18] must fail")
-        except kr.KrError:
-            pass
 
 
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}

@@ -34,10 +34,10 @@ def worker(rank, world, port, q):
         d_res = torch.from_numpy(res)
         layout = kr.LAYOUT_BLOCKTRI
         r0, r1, elems, first = sharding.my_stripe(n, layout, rank, world)
-        for mode in ("blocklists", "keys+pairs"):
-            flags = kr.IDENT_IS_INFINITY | (binding.EXP_PAIRS if mode == "keys+pairs" else 0)
+        for mode in ("blocklists", "replicated-join", "replicated-index"):
+            flags = kr.IDENT_IS_INFINITY | (kr.FORCE_INDEX if mode == "replicated-index" else kr.FORCE_JOIN)
             ctx = kr.Context(device=0, K=8, flags=flags)
-            s = sharding.encode_sharded(ctx, d_res, off, dist) if mode == "blocklists" else sharding.encode_sharded_keys(ctx, d_res, off, dist)
+            s = sharding.encode_sharded(ctx, d_res, off, dist) if mode == "blocklists" else ctx.encode_device(d_res.data_ptr(), off)
             out = torch.zeros(elems + 8, dtype=torch.int16)
             ctx.sim_matrix_device(s, None, out.data_ptr(), elem=kr.ELEM_U16, layout=layout, row_begin=r0, row_end=r1)
             ctx.synchronize()
@@ -45,18 +45,16 @@ def worker(rank, world, port, q):
             assert (got == want[first:first + elems]).all(), (mode, rank)
             whole = sharding.allgather_stripes(out[:elems], n, layout, dist)
             assert (whole.numpy().view(np.uint16) == want).all(), (mode, rank)
-            if mode == "keys+pairs":
-                assert (s.sizes() == o.batch(seqs, K=8).sizes()).all()
-            if mode == "keys+pairs":
-                # the same result by KEY partition: partial pair counts travel to the owner of their row (all_to_all)
-                out2 = torch.zeros(elems + 8, dtype=torch.int16)
-                assert sharding.allvsall_by_key_partition(ctx, s, out2, dist, elem=kr.ELEM_U16, layout=layout) == (r0, r1)
-                assert (out2[:elems].numpy().view(np.uint16) == want[first:first + elems]).all(), ("key partition", rank)
-                tri = o.sim_matrix(o.batch(seqs, K=8), ident_inf=True, threads=2)[np.triu_indices(n, 1)]
-                t0, t1, telems, tfirst = sharding.my_stripe(n, kr.LAYOUT_TRIANGLE, rank, world)
-                out3 = torch.zeros(telems + 8, dtype=torch.int32)
-                sharding.allvsall_by_key_partition(ctx, s, out3, dist, elem=kr.ELEM_I32, layout=kr.LAYOUT_TRIANGLE)
-                assert (out3[:telems].numpy() == tri[tfirst:tfirst + telems]).all(), ("key partition, triangle", rank)
+            if mode != "blocklists":
+                # the sparse cells of this rank's stripe, all-gathered: every rank ends up with every cell (j > i, sim >= 1)
+                cap = 1 << 15
+                cells = torch.zeros((cap, 4), dtype=torch.int32)
+                cnt = ctx.sim_matrix_sparse_device(s, None, cells.data_ptr(), cap, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1)
+                ctx.synchronize()
+                allc = sharding.allgather_cells(cells, cnt, cap, dist).numpy()
+                full = o.sim_matrix(o.batch(seqs, K=8), ident_inf=True, threads=2)
+                ii, jj = np.nonzero(np.triu(full, 1))
+                assert {(int(r), int(c), int(v)) for r, c, v, _ in allc} == {(int(i), int(j), int(full[i, j])) for i, j in zip(ii, jj)}, (mode, rank)
             ctx.close()
         q.put((rank, "ok"))
     except Exception as e:

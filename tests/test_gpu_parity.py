@@ -13,16 +13,21 @@ from oracle import kr_oracle as ko
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
-    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+# every test that takes `ctx` / `ctx_raw` runs three times: the library's own path choice, the tile join pinned, and the
+# sorted index + warp scan pinned (include/kmersreps.h, KR_FORCE_*): both device paths must equal the oracle
+PATHS = {"auto": 0, "join": kr.FORCE_JOIN, "index": kr.FORCE_INDEX}
+
+
+@pytest.fixture(scope="module", params=list(PATHS))
+def ctx(request):
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | PATHS[request.param])
     yield c
     c.close()
 
 
-@pytest.fixture(scope="module")
-def ctx_raw():
-    c = kr.Context(device=0, K=8, flags=0)
+@pytest.fixture(scope="module", params=list(PATHS))
+def ctx_raw(request):
+    c = kr.Context(device=0, K=8, flags=PATHS[request.param])
     yield c
     c.close()
 
@@ -47,11 +52,12 @@ def test_kat_k10(expected):
     c.close()
 
 
-def test_vapb_matrix_all_layouts(ctx, ctx_raw, vapb, oracle, expected):
+def test_vapb_matrix_all_layouts(ctx, vapb, oracle, expected):
     seqs = [s for (_, _, s) in vapb]
     b = oracle.batch(seqs, K=8)
     want = oracle.sim_matrix(b, ident_inf=True)
     want_raw = oracle.sim_matrix(b, ident_inf=False)
+    ctx_raw = kr.Context(device=0, K=8, flags=ctx.flags & ~kr.IDENT_IS_INFINITY)
     s = ctx.encode(seqs)
     assert (s.sizes() == b.sizes()).all()
     n = len(seqs)
@@ -72,6 +78,12 @@ def test_vapb_matrix_all_layouts(ctx, ctx_raw, vapb, oracle, expected):
     t = tri_from_full(raw)
     assert int(t.sum()) == e["sum_sim"] and int((t > 0).sum()) == e["nonzero_pairs"] and int(t.max()) == e["max_raw_sim"]
     assert int((tri_from_full(full) == kr.INFINITY).sum()) == e["identical_pairs"] == 11
+    # the same matrix as sparse cells (j > i, sim >= 1): the 1,610 non-zero pairs, INFINITY cells included
+    cells = ctx.sim_matrix_sparse(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE)
+    ii, jj = np.nonzero(np.triu(want, 1))
+    assert {(int(r), int(c), int(v)) for r, c, v, _ in cells} == {(int(i), int(j), int(want[i, j])) for i, j in zip(ii, jj)}
+    assert len(cells) == e["nonzero_pairs"] == 1610
+    ctx_raw.close()
 
 
 def test_rep50_matrix_and_stripes(ctx, rep50, oracle, expected):
@@ -162,14 +174,14 @@ def test_edge_cases_and_all_k(oracle):
             "MKV*LL-AAGT*", "BJOUZXBJOUZXBJOUZX", "ACDEFGH", ""]
     res, off, _ = synth.generate(5, 300, 5)
     seqs += synth.to_strings(res, off)
-    for K in (3, 5, 8, 11):
-        for flags in (0, kr.IDENT_IS_INFINITY):
+    for K, flags in [(K, f | pth) for K in (3, 5, 8, 9, 11) for f in (0, kr.IDENT_IS_INFINITY) for pth in PATHS.values()]:
+        if True:
             c = kr.Context(device=0, K=K, flags=flags)
             s = c.encode(seqs)
             b = oracle.batch(seqs, K=K)
             assert (s.sizes() == b.sizes()).all()
-            want = oracle.sim_matrix(b, ident_inf=bool(flags))
-            assert (c.sim_matrix(s) == want).all()
+            want = oracle.sim_matrix(b, ident_inf=bool(flags & kr.IDENT_IS_INFINITY))
+            assert (c.sim_matrix(s) == want).all(), (K, flags)
             for i in (2, 3, 5, 8, 9):
                 assert sorted(s.kmers(i)) == sorted(ko.py_kmers(seqs[i], K))
             c.close()
@@ -245,10 +257,10 @@ def test_synthetic_families_vs_oracle(ctx, oracle):
 def test_greedy_build_matches_oracle(oracle, rep50, rickettsia):
     res, off, _ = synth.generate(0x5EED0004, 6000, 150, xrun_per_10k=30)
     b = oracle.batch(res=res, off=off, K=8)
-    for flags in (kr.IDENT_IS_INFINITY, 0):
+    for flags, path in [(f, pth) for f in (kr.IDENT_IS_INFINITY, 0) for pth in (0, kr.FORCE_JOIN)]:
         n, added, _ = oracle.greedy_build(b, 50, ident_inf=bool(flags))
         for batch in (0, 256, 1000):
-            c = kr.Context(device=0, K=8, flags=flags)
+            c = kr.Context(device=0, K=8, flags=flags | path)
             cands = c.encode(res=res, off=off)
             db = c.db()
             got = db.greedy_build(cands, 50, batch=batch)
@@ -273,7 +285,7 @@ def test_greedy_build_matches_oracle(oracle, rep50, rickettsia):
     c.close()
 
 
-# ---- inverted index path of findClosest (K4/K5) ------------------------------------------------------
+# ---- sorted-index path of findClosest (K4/K5) against the tile join and the oracle ---------------------------
 def test_index_path_matches_join_and_oracle(rep50, gto_seeds, rickettsia, oracle, expected):
     reps = [s for (_, _, s) in rep50["reps"]]
     qs = [s for (_, _, s) in gto_seeds] + [p for (_, p) in rickettsia] + reps[:300] + ["", "ACD", "MKV"]
@@ -320,16 +332,16 @@ def test_index_path_ties_ranks_and_short_sequences(oracle):
     assert (first != last).any()
 
 
-def test_index_path_multi_slab_large_batch(oracle):
-    # more representatives than one index slab (51,200) and a batch large enough to take the index path by itself
+def test_index_path_large_database_and_batch(oracle):
+    # 60,000 representatives (an index of 17.6 M entries) and 20,000 queries: index scan against the tile join, cell by cell
     res, off, _ = synth.generate(0x5EED0005, 80000, 1600)
     nrep = 60000
     c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
     db = c.db()
     db.append(res=res[: int(off[nrep])], off=off[: nrep + 1])
     q = c.encode(res=res[int(off[nrep]):], off=off[nrep:] - off[nrep])
-    assert q.count >= 8192
     sim, first, last = db.find_closest(q)
+    assert c.stats()["scan_launches"] >= 1 and c.stats()["join_launches"] == 0
     cj = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_JOIN)
     dbj = cj.db()
     dbj.append(res=res[: int(off[nrep])], off=off[: nrep + 1])
@@ -383,6 +395,65 @@ def test_greedy_build_properties_at_scale():
     best, first, _ = db.find_closest(cands.gather(rej))
     assert (best >= thr).all()                                                     # (b)
     c.close()
+
+
+def test_allvsall_full_size_index_equals_join():
+    """BASELINE configs[2] at full size (100,000 sequences, 5e9 pairs): the index scan's dense result equals the tile
+    join's, cell for cell, on the device; the sparse cells are exactly the non-zero cells of the strict triangle; and
+    row stripes of the index path reassemble to the whole (the multi-GPU sharding unit)."""
+    import torch
+    n = 100000
+    res, off, _ = synth.generate(0x5EED0003, n, n // 50)
+    d_res = torch.from_numpy(res).cuda()
+    ne = kr.matrix_elems(n, n, kr.LAYOUT_BLOCKTRI)
+    outs = {}
+    for name, flag in (("join", kr.FORCE_JOIN), ("index", kr.FORCE_INDEX), ("auto", 0)):
+        c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | flag)
+        s = c.encode_device(d_res.data_ptr(), off)
+        out = torch.full((ne + 8,), -1, dtype=torch.int16, device="cuda")
+        c.sim_matrix_device(s, None, out.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI)
+        c.synchronize()
+        st = c.stats()
+        if name == "auto":
+            assert st["scan_launches"] >= 1 and st["join_launches"] == 0      # a family-structured batch belongs to the index
+        if name == "index":
+            # stripes (4 ranks' worth) reassemble to the whole
+            rb = kr.matrix_stripes(n, n, kr.LAYOUT_BLOCKTRI, 4)
+            pos = 0
+            for k in range(4):
+                cnt = kr.matrix_elems(n, n, kr.LAYOUT_BLOCKTRI, int(rb[k]), int(rb[k + 1]))
+                part = torch.full((cnt + 8,), -1, dtype=torch.int16, device="cuda")
+                c.sim_matrix_device(s, None, part.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=int(rb[k]), row_end=int(rb[k + 1]))
+                c.synchronize()
+                assert torch.equal(part[:cnt], out[pos:pos + cnt]), k
+                pos += cnt
+                del part
+            assert pos == ne
+            cap = 1 << 23
+            cells = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+            cnt = c.sim_matrix_sparse_device(s, None, cells.data_ptr(), cap, min_sim=1, layout=kr.LAYOUT_TRIANGLE)
+            c.synchronize()
+            outs["cells"] = cells[:cnt].cpu().numpy()
+        outs[name] = out[:ne]
+        s.free()
+        c.close()
+    assert torch.equal(outs["join"], outs["index"]) and torch.equal(outs["join"], outs["auto"])
+    # sparse cells against the dense result: same count of non-zero strict-triangle cells, and every cell's value
+    cells = outs["cells"]
+    i, j, v = cells[:, 0].astype(np.int64), cells[:, 1].astype(np.int64), cells[:, 2]
+    assert (j > i).all() and len(np.unique(i * n + j)) == len(cells)
+    I = i // 256
+    idx = 256 * (I * n - 128 * I * (I - 1)) + (i - 256 * I) * (n - 256 * I) + (j - 256 * I)
+    dense = outs["join"]
+    assert (dense[torch.from_numpy(idx).cuda()].cpu().numpy().astype(np.int32) == v).all()
+    diag_i = np.arange(n, dtype=np.int64); DI = diag_i // 256
+    didx = 256 * (DI * n - 128 * DI * (DI - 1)) + (diag_i - 256 * DI) * (n - 256 * DI) + (diag_i - 256 * DI)
+    nz_total = int((dense != 0).sum().item())
+    # non-zero cells of the block triangle = the diagonal (INFINITY) + the strict triangle's non-zero cells + the
+    # below-diagonal cells inside the 256 x 256 diagonal blocks (mirror images of cells with j > i in the same block)
+    same_block = int(((i // 256) == (j // 256)).sum())
+    assert bool((dense[torch.from_numpy(didx).cuda()] == kr.INFINITY).all())
+    assert nz_total == n + len(cells) + same_block
 
 
 def test_greedy_build_sharded_driver_on_one_gpu(oracle):

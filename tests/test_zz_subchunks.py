@@ -32,7 +32,7 @@ def test_chunks_longer_than_a_stage(oracle, length, n):
     assert np.mean([len(s) for s in seqs]) * 256 / 64 > 2200          # mean chunk length beyond one stage
     b = oracle.batch(seqs, K=8)
     want = oracle.sim_matrix(b, ident_inf=True, threads=8)
-    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY)
+    c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | kr.FORCE_JOIN)      # this file is about the tile join
     s = c.encode(seqs)
     assert (s.sizes() == b.sizes()).all()
     assert (c.sim_matrix(s, elem=kr.ELEM_U16) == want).all()
@@ -46,7 +46,7 @@ def test_chunks_longer_than_a_stage(oracle, length, n):
     bs, bi = oracle.find_closest(oracle.batch(seqs[: n - 40], K=8), oracle.batch(seqs[n - 40:], K=8))
     assert (sim == bs).all() and (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
     c.close()
-    c10 = kr.Context(device=0, K=10, flags=0)                           # 32-bit low words, 3 stages
+    c10 = kr.Context(device=0, K=10, flags=kr.FORCE_JOIN)                           # 32-bit low words, 3 stages
     s10 = c10.encode(seqs[:260])
     want10 = oracle.sim_matrix(oracle.batch(seqs[:260], K=10), ident_inf=False, threads=8)
     assert (c10.sim_matrix(s10) == want10).all()

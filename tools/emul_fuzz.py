@@ -51,15 +51,13 @@ def batch(rng):
     return seqs
 
 
-def one(rng, exp):
+def one(rng):
     seqs = batch(rng)
     n = len(seqs)
     K = int(rng.choice([3, 5, 8, 8, 8, 9, 10, 11]))
     ident = bool(rng.random() < 0.7)
     flags = kr.IDENT_IS_INFINITY if ident else 0
-    if exp:
-        flags |= int(rng.choice([0, binding.EXP_PAIRS, binding.EXP_PAIRS | binding.EXP_BUCKETS, binding.EXP_PAIRS_AUTO | binding.EXP_BUCKETS]))
-        flags |= int(rng.choice([0, binding.EXP_ENCODE])) | int(rng.choice([0, binding.EXP_IDXQ])) | int(rng.choice([0, binding.EXP_GIDX]))
+    flags |= int(rng.choice([0, kr.FORCE_JOIN, kr.FORCE_INDEX, kr.FORCE_INDEX]))      # the library's choice, or a pinned device path
     desc = "n=%d K=%d ident=%d flags=0x%x" % (n, K, ident, flags)
     ob = O.batch(seqs, K=K)
     want = O.sim_matrix(ob, ident_inf=ident, threads=4)
@@ -80,7 +78,7 @@ def one(rng, exp):
     else:
         exp_cells = np.concatenate([want[i, 256 * (i // 256):] for i in range(r0, r1)])
     assert (np.asarray(got).ravel() == np.asarray(exp_cells).ravel()).all(), desc + " layout=%d elem=%d rows[%d,%d)" % (layout, elem, r0, r1)
-    if exp and rng.random() < 0.5 and n > 1:
+    if rng.random() < 0.5 and n > 1:
         ms = int(rng.choice([1, 2, 5]))
         cells = c.sim_matrix_sparse(s, min_sim=ms, layout=kr.LAYOUT_TRIANGLE, cap=64, row_begin=r0, row_end=r1)
         got_cells = {(int(a), int(b), int(v)) for a, b, v, _ in cells}
@@ -94,7 +92,7 @@ def one(rng, exp):
         bs, bi = O.find_closest(O.batch(seqs[:nrep], K=K), O.batch(seqs[nrep:], K=K), order=np.argsort(rank).astype(np.int32), ident_inf=ident, threads=4)
         bs2, bl = O.find_closest(O.batch(seqs[:nrep], K=K), O.batch(seqs[nrep:], K=K), order=np.argsort(rank).astype(np.int32), ident_inf=ident, tie_last=True, threads=4)
         path = int(rng.choice([kr.FORCE_JOIN, kr.FORCE_INDEX]))
-        c2 = kr.Context(device=0, K=K, flags=flags | path)
+        c2 = kr.Context(device=0, K=K, flags=(flags & ~(kr.FORCE_JOIN | kr.FORCE_INDEX)) | path)
         db = c2.db()
         cut = int(rng.integers(0, nrep + 1))
         db.append(seqs[:cut]) if cut else None
@@ -111,49 +109,20 @@ def one(rng, exp):
     added = c.db().greedy_build(s, thr, batch=int(rng.choice([0, 7, 64, 300])))
     assert (added == w).all(), desc + " greedy thr=%d" % thr
     c.close()
-    if exp and rng.random() < 0.25:
-        dna_case(rng)
     return desc
-
-
-def dna_case(rng):
-    """ALPHABET_DNA contexts against the Python restatement (small: the restatement is pure Python)"""
-    alpha = np.frombuffer(b"acgt", dtype=np.uint8)
-    K = int(rng.choice([5, 7, 12, 15, 18]))
-    roots = [alpha[rng.integers(0, 4, int(rng.integers(30, 300)))] for _ in range(3)]
-    seqs = []
-    for i in range(int(rng.integers(2, 40))):
-        s = roots[i % 3].copy()
-        k = int(len(s) * rng.choice([0.0, 0.03, 0.2]))
-        if k:
-            s[rng.integers(0, len(s), k)] = alpha[rng.integers(0, 4, k)]
-        t = s[: int(rng.integers(1, len(s) + 1))].tobytes().decode()
-        t = ko.py_dna_revcomp(t) if rng.random() < 0.2 else t
-        t = t.upper() if rng.random() < 0.2 else t
-        t = t.replace("a", "n", 1) if rng.random() < 0.1 else t
-        seqs.append(t)
-    ident = bool(rng.random() < 0.7)
-    want = np.array([[ko.py_dna_similarity(a, b, K, ident) for b in seqs] for a in seqs], dtype=np.int64)
-    flags = (kr.IDENT_IS_INFINITY if ident else 0) | binding.ALPHABET_DNA | int(rng.choice([0, binding.EXP_PAIRS | binding.EXP_BUCKETS]))
-    c = kr.Context(device=0, K=K, flags=flags)
-    s = c.encode(seqs)
-    assert (s.sizes() == [len(ko.py_dna_kmers(q, K)) for q in seqs]).all(), "dna sizes K=%d" % K
-    assert (c.sim_matrix(s, elem=kr.ELEM_I32) == want).all(), "dna matrix K=%d flags=0x%x" % (K, flags)
-    c.close()
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=300)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--exp", action="store_true")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
     t0, k = time.time(), 0
     while time.time() - t0 < a.seconds:
         state = rng.bit_generator.state
         try:
-            d = one(rng, a.exp)
+            d = one(rng)
         except Exception:
             print("FAILED at case %d; generator state:\n%r" % (k, state), flush=True)
             raise
