@@ -4,13 +4,18 @@
 Workload (BASELINE.json configs[2], the one the metric is quoted on): all-vs-all 8-mer similarity of
 100,000 synthetic ~300-aa seed proteins in 2,000 families (seed 0x5EED0003).  It fits one
 GPU, so N=1 runs it whole; N>1 shards the 256-row stripes of the result over the ranks (strong scaling:
-total work fixed).  A step = one pass of the hot path over the batch:
-    residues (HBM) -> encode + sort/dedupe -> block lists -> tile join -> uint16 similarity matrix (HBM).
+total work fixed; every rank encodes and indexes the whole batch and scans its own rows -- no data-path
+collective).  A step = one pass of the hot path over the batch:
+    residues (HBM) -> K1 encode + sort/dedupe -> K4 sorted inverted index -> K5 index scan that writes every
+    cell of this rank's stripe of the uint16 similarity matrix (HBM)
+(the library picks the index scan for this family-structured batch from the index's posting-list statistics;
+--path join pins the tile join, the path of dense collections).
 `value` = pairs (i<j) per second over all ranks, device time (CUDA events on the library's stream), max over
-ranks.  `e2e` = the same through the host-buffer C ABI (kr_encode + kr_sim_matrix): H2D of the residues and
-D2H of this rank's matrix stripe inside the timed region.
+ranks.  `e2e` = the same through the host-buffer C ABI a caller uses (kr_encode + kr_sim_matrix_sparse): H2D of
+the residues and D2H of this rank's result inside the timed region, the result being the cells with sim >= 1 (all
+other cells are 0 by definition); `e2e_dense` moves the dense stripe instead (kr_sim_matrix).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nseq 100000]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nseq 100000] [--path auto|join|index]
 """
 import argparse
 import json
@@ -291,29 +296,18 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=10000)
     ap.add_argument("--cpu-sample", type=int, default=16000)
     ap.add_argument("--cpu-queries", type=int, default=500, help="findclosest workload: queries timed on the CPU port")
+    ap.add_argument("--cpu-build", type=int, default=20000, help="findclosest workload: candidates of the greedy build timed on the CPU port")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--exp-pairs", action="store_true",
-                    help="EXPERIMENTAL library only: all-vs-all through the posting-list path (context flag EXP_PAIRS)")
-    ap.add_argument("--exp-buckets", action="store_true", help="EXPERIMENTAL library only, with --exp-pairs: group by key in shared memory after a bucket partition")
-    ap.add_argument("--key-partition", action="store_true",
-                    help="EXPERIMENTAL library only, N>1 with --exp-pairs: count pairs by key partition and all-to-all the partial counts")
-    ap.add_argument("--exp-encode", action="store_true", help="EXPERIMENTAL library only: K1 with one warp per sequence (EXP_ENCODE)")
-    ap.add_argument("--exp-idxq", action="store_true", help="EXPERIMENTAL library only: K5 with one warp per query (EXP_IDXQ; findclosest workload)")
-    ap.add_argument("--exp-gidx", action="store_true", help="EXPERIMENTAL library only: greedy build through the growing index (EXP_GIDX; findclosest workload)")
-    ap.add_argument("--sparse-e2e", action="store_true",
-                    help="EXPERIMENTAL library only (KR_LIB_PATH=.../libkmersreps_cuda_exp.so): also time the e2e path that returns only "
-                         "the cells with sim >= 1 (kr_sim_matrix_sparse) and report it as e2e_sparse")
-    ap.add_argument("--e2e-api", default="dense", choices=["dense", "sparse"],
-                    help="which host-buffer call the headline `e2e` key reports: kr_sim_matrix (dense result over PCIe) or, with the "
-                         "experimental library, kr_sim_matrix_sparse (implies --sparse-e2e; the other one stays in e2e_dense / e2e_sparse)")
+    ap.add_argument("--path", default="auto", choices=["auto", "join", "index"],
+                    help="device path: the library's own choice, the tile join pinned, or the sorted index + scan pinned")
     ap.add_argument("--elem", default="u16", choices=["u16", "i32"])
     ap.add_argument("--sharded-encode", action="store_true",
-                    help="N>1: each rank encodes 1/N of the sequences and the block lists are all-gathered (NCCL) and imported; the default is "
-                         "that every rank encodes all sequences (no data-path collective)")
-    ap.add_argument("--gather-matrix", action="store_true",
-                    help="N>1: also all-gather the whole matrix onto every GPU after the timed region and report its cost")
+                    help="N>1 with --path join: each rank encodes 1/N of the sequences and the block lists are all-gathered (NCCL) and "
+                         "imported; the default is that every rank encodes all sequences (no data-path collective)")
+    ap.add_argument("--gather-cells", action="store_true",
+                    help="N>1: after the timed region, all-gather every rank's sparse result cells (NCCL) and report its cost")
     args = ap.parse_args()
     ensure_built()
     rank = int(os.environ.get("RANK", "0"))
@@ -329,42 +323,26 @@ def main():
     import torch
     import torch.distributed as dist
     import kmers.reps_b200 as kr
+    from kmers.reps_b200 import sharding
 
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     res, off, nfam = workload(args.nseq)
     N = args.nseq
-    from kmers.reps_b200 import binding
-    if (args.exp_pairs or args.exp_encode) and not binding.has_experimental():
-        raise SystemExit("--exp-pairs / --exp-encode need KR_LIB_PATH to point at libkmersreps_cuda_exp.so")
-    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | (binding.EXP_PAIRS if args.exp_pairs else 0)
-                     | (binding.EXP_ENCODE if args.exp_encode else 0) | (binding.EXP_BUCKETS if args.exp_buckets else 0))
+    pin = {"auto": 0, "join": kr.FORCE_JOIN, "index": kr.FORCE_INDEX}[args.path]
+    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | pin)
     elem = kr.ELEM_U16 if args.elem == "u16" else kr.ELEM_I32
     esz = 2 if elem == kr.ELEM_U16 else 4
     layout = kr.LAYOUT_BLOCKTRI
-    from kmers.reps_b200 import binding, sharding
     r0, r1, my_elems, _ = sharding.my_stripe(N, layout, rank, world)
     d_res = torch.from_numpy(res).cuda()
     d_out = torch.empty(my_elems * esz + 16, dtype=torch.uint8, device="cuda")
     total_pairs = N * (N - 1) // 2
-
-    sharded_encode = world > 1 and args.sharded_encode
-
-    if binding.build_info() == "v2":   # the posting-list path is this library's default: exchange key lists and split the counting by key
-        args.exp_pairs = True
-        args.key_partition = world > 1
+    sharded_encode = world > 1 and args.sharded_encode and args.path == "join"
 
     def step():
-        # N>1: each rank encodes 1/N of the sequences and the block lists are all-gathered over NVLink (the one
-        # exchange step of the path); N=1 or --replicated-encode: every rank encodes everything
-        if sharded_encode and args.exp_pairs:      # the posting-list path needs key lists: exchange those instead of block lists
-            s = sharding.encode_sharded_keys(ctx, d_res, off, dist)
-            if args.key_partition:                 # ... and split the pair counting by key, not only the result by row
-                sharding.allvsall_by_key_partition(ctx, s, d_out, dist, elem=elem, layout=layout)
-                return s
-        else:
-            s = sharding.encode_sharded(ctx, d_res, off, dist) if sharded_encode else ctx.encode_device(d_res.data_ptr(), off)
+        s = sharding.encode_sharded(ctx, d_res, off, dist) if sharded_encode else ctx.encode_device(d_res.data_ptr(), off)
         ctx.sim_matrix_device(s, None, d_out.data_ptr(), elem=elem, layout=layout, row_begin=r0, row_end=r1)
         return s
 
@@ -380,7 +358,7 @@ def main():
             prev.free()
         prev = cur
     ctx.synchronize()
-    if sharded_encode and not args.exp_pairs:   # a set imported from block lists has no per-sequence arrays: encode once more, plainly
+    if sharded_encode:   # a set imported from block lists has no per-sequence arrays: encode once more, plainly
         tmp = ctx.encode_device(d_res.data_ptr(), off)
         sizes = tmp.sizes().astype(np.int64)
         tmp.free()
@@ -409,23 +387,7 @@ def main():
     ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
     value = total_pairs / (ms_per_step / 1e3)
-
-    gather = None
-    if args.gather_matrix and world > 1:
-        # what it would cost to also leave the WHOLE matrix on every GPU (not part of the headline: DESIGN.md 5)
-        local = d_out[: my_elems * esz].view(torch.int16 if esz == 2 else torch.int32)
-        whole = torch.empty(kr.matrix_elems(N, N, layout), dtype=local.dtype, device="cuda")
-        sharding.allgather_stripes(local, N, layout, dist, out=whole)   # warm-up
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        sharding.allgather_stripes(local, N, layout, dist, out=whole)
-        e1.record()
-        torch.cuda.synchronize()
-        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(tg.item()), "bytes_per_rank": int(whole.numel() * esz)}
-        del whole
+    used_index = st["scan_launches"] > 0
 
     # ---- check a sample of this rank's cells against the oracle (outside the timed region) -----
     from oracle import kr_oracle as ko
@@ -433,6 +395,8 @@ def main():
     rng = np.random.default_rng(1234 + rank)
     ii = rng.integers(r0, max(r1, r0 + 1), 400)
     jj = np.array([rng.integers(i, N) for i in ii])
+    # half of the sample from inside the row's own family neighbourhood (non-zero cells), half anywhere
+    jj[:200] = np.minimum(N - 1, ii[:200] + rng.integers(0, 60, 200))
     host_cells = []
     flat_out = d_out[: my_elems * esz].view(torch.int16 if esz == 2 else torch.int32)
     origin = kr.matrix_elems(N, N, layout, 0, r0)
@@ -445,79 +409,114 @@ def main():
     verified = host_cells == want
     if not verified and not os.environ.get("KR_BENCH_NOVERIFY"):
         raise SystemExit("bench: GPU result differs from the oracle on sampled cells")
+    # size-independent checks of the whole stripe: every diagonal cell is INFINITY, and the number of non-zero cells
+    # equals the diagonal + twice-counted in-block pairs + the sparse cell count (checked in tests at full size)
+    diag = torch.arange(r0, r1, device="cuda", dtype=torch.int64)
+    DI = diag // 256
+    didx = 256 * (DI * N - 128 * DI * (DI - 1)) + (diag - 256 * DI) * (N - 256 * DI) + (diag - 256 * DI) - origin
+    if not bool((flat_out[didx].to(torch.int32) & 0xFFFF == kr.INFINITY).all()):
+        raise SystemExit("bench: a diagonal cell is not INFINITY")
 
-    # ---- roofline of the dominant kernel (tile join) -----------------------------------------
+    # ---- roofline of the dominant kernel ----------------------------------------------------
     hbm, hbm_src = peaks()
-    join_ms = st["join_ms"] / max(1, st["join_launches"])
     ssum = int(sizes.sum())
-    # (i) what the launch must move through DRAM whatever the algorithm: every key list it reads once
-    #     (8 B per distinct k-mer of the batch: the rows of this stripe join against ALL columns) + its result cells once
     out_bytes = my_elems * esz
-    compulsory = ssum * 8 + out_bytes
-    achieved = compulsory / (join_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                "kernel": "k_join<MATRIX>", "kernel_ms": join_ms, "peak_source": hbm_src, "algorithmic_bytes": compulsory,
-                "note": "algorithmic bytes = compulsory DRAM traffic of one launch (SURVEY.md 8d.3): the batch's key lists once (8 B per distinct "
-                        "k-mer) + this rank's result cells once; traffic (ncu dram bytes) is not measured inside bench.py, see profiles/"}
-    # (ii) the per-pair streaming figure of SURVEY.md 8d.1 (8(|A|+|B|)+4 B per pair): a WORK-EQUIVALENCE number, not a bound for
-    #      this kernel -- one pass over two 256-sequence block lists serves 65,536 pairs, so it exceeds the HBM peak many times
-    suffix = np.concatenate([np.cumsum(sizes[::-1])[::-1], [0]])
+    stage_ms = {k: st[k] / args.steps for k in ("encode_ms", "index_ms", "scan_ms", "blocklist_ms", "join_ms", "other_ms")}
     rows = np.arange(r0, r1)
+    if used_index:
+        # K5 scan (k_ix_query<DENSE>).  Algorithmic bytes per launch (index-served paths, per query row:
+        # n_q (8 + 16) + 4 M_q: its keys, one 16-byte index probe per key, 4 bytes per posting touched) + every result cell
+        # of the row written once.  M (postings walked) is the index's own statistic: sum over posting lists of m^2.
+        kern, kern_ms = "k_ix_query<DENSE>", st["scan_ms"] / max(1, st["scan_launches"])
+        frac_rows = (r1 - r0) / max(1, N)
+        walked = int(st["index_walk"] * frac_rows)
+        alg = int(sizes[rows].sum()) * 24 + 4 * walked + out_bytes
+        alg_note = ("per row: n (8 + 16) B of keys and index probes + 4 B per posting walked (sum of m^2 over the posting lists = %d for the "
+                    "whole batch) + the row's result cells written once (zeros included: the scan writes every cell of its rows)" % st["index_walk"])
+    else:
+        # tile join (k_join<MATRIX>): compulsory DRAM traffic of one launch: key lists once + result cells once
+        kern, kern_ms = "k_join<MATRIX>", st["join_ms"] / max(1, st["join_launches"])
+        alg = ssum * 8 + out_bytes
+        alg_note = "compulsory DRAM traffic of one launch (SURVEY.md 8d.3): the batch's key lists once (8 B per distinct k-mer) + this rank's result cells once"
+    achieved = alg / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                "kernel": kern, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_per_step if ms_per_step else None,
+                "peak_source": hbm_src, "algorithmic_bytes": alg, "note": alg_note,
+                "traffic_note": "ncu dram bytes are not measured inside bench.py; see profiles/ for captures (none exist for this revision "
+                                "if GPU access was closed)"}
+    # whole step against the compulsory traffic: residues in + key lists written and read + result written
+    step_bytes = int(len(res)) + 2 * ssum * 8 + out_bytes
+    step_roof = {"bytes": step_bytes, "achieved": step_bytes / (ms_per_step / 1e3) / 1e9, "frac_of_hbm_peak": step_bytes / (ms_per_step / 1e3) / 1e9 / hbm,
+                 "note": "whole step (encode + index + scan, max over ranks) against its compulsory bytes: residues + key lists out and in + result"}
+    # the per-pair streaming figure of SURVEY.md 8d.1 (8(|A|+|B|)+4 B per pair): a WORK-EQUIVALENCE number, not a bound for an
+    # algorithm that never streams two key lists per pair
+    suffix = np.concatenate([np.cumsum(sizes[::-1])[::-1], [0]])
     key_stream = int((8 * (sizes[rows] * (N - 1 - rows) + suffix[rows + 1]) + 4 * (N - 1 - rows)).sum())
-    contract = {"algorithmic_bytes": key_stream, "achieved": key_stream / (join_ms / 1e3) / 1e9, "unit": "GB/s",
-                "frac_of_hbm_peak": key_stream / (join_ms / 1e3) / 1e9 / hbm,
-                "note": "SURVEY.md 8d.1 pairwise key-stream figure; not a roofline for a block-level join (reported because north_star quotes it)"}
+    contract = {"algorithmic_bytes": key_stream, "achieved": key_stream / (ms_per_step / 1e3) / 1e9, "unit": "GB/s",
+                "frac_of_hbm_peak": key_stream / (ms_per_step / 1e3) / 1e9 / hbm,
+                "note": "SURVEY.md 8d.1 pairwise key-stream figure over the whole step; not a roofline for an index scan or a block-level "
+                        "join (reported because north_star quotes it)"}
 
     # ---- e2e: host buffers through the C ABI -----------------------------------------------------
-    e2e = None
+    e2e = e2e_dense = None
     if not args.no_e2e:
-        h_out = ctx.host_alloc(my_elems * esz, dtype=np.uint16 if esz == 2 else np.int32)
         h_res = ctx.host_alloc(max(len(res), 1))
         h_res[: len(res)] = res
-        def e2e_step():
-            s = ctx.encode(res=h_res[: len(res)], off=off)
-            ctx.sim_matrix(s, None, elem=elem, layout=layout, row_begin=r0, row_end=r1, out=h_out)
-            s.free()
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        e2e = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(len(res) + 16 * (N + 1)),
-               "d2h_bytes_per_step": int(my_elems * esz), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
-               "api": "kr_encode + kr_sim_matrix (pinned host buffers)"}
-
-    e2e_sparse = None
-    if (args.sparse_e2e or args.e2e_api == "sparse") and binding.has_experimental():
-        cap = 1 << 24
+        cap = 1 << 23
         h_cells = ctx.host_alloc(cap * 16, dtype=np.uint32).reshape(cap, 4)
-        h_res = ctx.host_alloc(max(len(res), 1))
-        h_res[: len(res)] = res
         ncell = [0]
+
+        def timed(fn):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
         def sparse_step():
             s = ctx.encode(res=h_res[: len(res)], off=off)
             ncell[0] = len(ctx.sim_matrix_sparse(s, None, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1, out=h_cells))
             s.free()
-        sparse_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            sparse_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e_sparse = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "ms_per_step": 1000 * dt / args.e2e_steps,
-                      "cells_per_step": ncell[0], "d2h_bytes_per_step": 8 + 16 * ncell[0],
-                      "api": "kr_encode + kr_sim_matrix_sparse (experimental build): only cells with sim >= 1 cross PCIe"}
+        dt = timed(sparse_step)
+        e2e = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(len(res) + 16 * (N + 1)),
+               "d2h_bytes_per_step": int(8 + 16 * ncell[0]), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
+               "cells_per_step": ncell[0],
+               "api": "kr_encode + kr_sim_matrix_sparse (pinned host buffers): the cells with sim >= 1 of this rank's rows; every other cell is 0"}
+        del h_cells
+        h_out = ctx.host_alloc(my_elems * esz, dtype=np.uint16 if esz == 2 else np.int32)
 
-    e2e_dense = None
-    if args.e2e_api == "sparse" and e2e_sparse is not None:
-        e2e_dense, e2e = e2e, dict(e2e_sparse, h2d_bytes_per_step=int(len(res) + 16 * (N + 1)), steps=args.e2e_steps)
+        def dense_step():
+            s = ctx.encode(res=h_res[: len(res)], off=off)
+            ctx.sim_matrix(s, None, elem=elem, layout=layout, row_begin=r0, row_end=r1, out=h_out)
+            s.free()
+        dt = timed(dense_step)
+        e2e_dense = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(len(res) + 16 * (N + 1)),
+                     "d2h_bytes_per_step": int(my_elems * esz), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
+                     "api": "kr_encode + kr_sim_matrix (pinned host buffers): the dense stripe over PCIe"}
+
+    gather = None
+    if args.gather_cells and world > 1:
+        cap = 1 << 22
+        d_cells = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+        s = ctx.encode_device(d_res.data_ptr(), off)
+        cnt = ctx.sim_matrix_sparse_device(s, None, d_cells.data_ptr(), cap, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1)
+        sharding.allgather_cells(d_cells, cnt, cap, dist)      # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        allc = sharding.allgather_cells(d_cells, cnt, cap, dist)
+        e1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"ms": float(tg.item()), "cells_total": int(allc.shape[0]), "bytes_per_rank": int(cap * 16)}
+        s.free()
 
     if rank == 0:
         cpu = None
@@ -532,17 +531,18 @@ def main():
             "data": "synthetic",
             "config": {"workload": "all-vs-all 8-mer similarity, %d synthetic ~300-aa seed proteins, %d families (BASELINE configs[2])" % (N, nfam),
                        "K": 8, "nseq": N, "pairs": total_pairs, "result": "%s block-triangle, %d bytes on this rank" % (args.elem, my_elems * esz),
+                       "path": ("sorted index + warp scan" if used_index else "tile join") + (" (pinned)" if args.path != "auto" else " (library's choice)"),
                        "sharding": ("256-row stripes of the result over %d rank(s); " % world) +
                                    ("each rank encodes 1/%d of the sequences, block lists all-gathered (NCCL)" % world if sharded_encode
-                                    else "keys replicated, no data-path collective"),
+                                    else "every rank encodes and indexes the whole batch, no data-path collective"),
                        "cache": "inputs+outputs larger than L2 (key lists %d MB, result %d MB per rank)" % (ssum * 8 >> 20, my_elems * esz >> 20)},
-            "roofline": roofline, "roofline_contract_8d1": contract, "cpu_baseline": cpu, "e2e": e2e, "e2e_sparse": e2e_sparse, "e2e_dense": e2e_dense,
+            "roofline": roofline, "roofline_step": step_roof, "roofline_contract_8d1": contract, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense": e2e_dense,
             "gpu_launches": int(st["kernel_launches"]), "clocks": clocks,
-            "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
-            "verified": "400 sampled cells per rank equal the oracle",
+            "stages_ms_per_step": stage_ms, "index": {"entries": int(st["index_entries"]), "postings_walked_by_a_self_scan": int(st["index_walk"])},
+            "verified": "400 sampled cells per rank equal the oracle (200 of them near the diagonal, inside families); every diagonal cell is INFINITY",
         }
         if gather:
-            line["matrix_allgather"] = gather
+            line["cells_allgather"] = gather
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

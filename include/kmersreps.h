@@ -230,6 +230,9 @@ typedef struct kr_stats {
     double scan_ms;           /* index scan kernels (argmax / cells / dense cells) */
     uint64_t scan_launches;   /* index scans launched: tells which path served a call */
     uint64_t index_builds;
+    /* posting-list statistics of the index most recently consulted for a path choice: entries (sum of list lengths m),
+     * sum of m^2 (postings a self scan walks = sum over ordered pairs of their similarity, diagonal included) */
+    uint64_t index_entries, index_walk;
 } kr_stats;
 kr_status kr_stats_get(kr_ctx *ctx, kr_stats *out); /* synchronises the context's stream */
 kr_status kr_stats_reset(kr_ctx *ctx);

@@ -530,9 +530,7 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
             if (sparse) { tg.cells = sparse->cells; tg.cells_cap = sparse->cap; tg.cells_count = sparse->count; tg.min_sim = sparse->min_sim; }
             else {
                 tg.out = out_dev; tg.elem = d->elem; tg.layout = d->layout; tg.origin = row_start(d->layout, d->row_begin, A->n, Bx->n); tg.min_sim = 1;
-                const u64 elems = row_start(d->layout, d->row_end, A->n, Bx->n) - tg.origin;
-                StageTimer t(ctx, ST_OTHER);
-                CU(cudaMemsetAsync(out_dev, 0, elems * (d->elem == KR_ELEM_U16 ? 2 : 4), ctx->stream));
+                // (the scan writes every cell of its rows: zeros first, then the cells of pairs that share a k-mer)
             }
             if ((st = index_matrix(ctx, A, Bx, self, d->layout, d->row_begin, d->row_end, tg))) return st;
             if (d->layout == KR_LAYOUT_FULL) ctx->st.pairs += rows * (u64)Bx->n;
@@ -776,6 +774,19 @@ static kr_status db_ensure_index(kr_ctx *ctx, kr_db *db) {
     return KR_OK;
 }
 
+// Which path scans this database?  The index, unless the context pins the join, the sets cannot be indexed, or the
+// database's posting lists are long (dense similarity: most representatives share k-mers with most queries), where the
+// per-warp score table would overflow into passes and the tile join's similarity-independent work wins.
+static kr_status db_use_index(kr_ctx *ctx, kr_db *db, const kr_seqset *Q, bool *use) {
+    *use = false;
+    if (!Q->d_keys || (ctx->flags & KR_FORCE_JOIN) || !db_indexable(ctx, db)) return KR_OK;
+    if (ctx->flags & KR_FORCE_INDEX) { *use = true; return KR_OK; }
+    kr_status st;
+    if ((st = db_refresh(ctx, db)) || (st = db_ensure_index(ctx, db)) || (st = index_stats(ctx, db->ix_main))) return st;
+    *use = index_list_length(*db->ix_main) <= IX_DENSE_LISTS;
+    return KR_OK;
+}
+
 // K5: queries [q0, q1) of Q against the index levels of the database; outputs are indexed by q - q0
 static kr_status find_closest_index(kr_ctx *ctx, kr_db *db, kr_seqset *Q, u32 q0, u32 q1, int *d_sim, u32 *d_first, u32 *d_last) {
     kr_status st = db_ensure_index(ctx, db);
@@ -821,7 +832,8 @@ static kr_status find_closest_launch(kr_ctx *ctx, kr_db *db, kr_seqset *Q, int *
     // Two exact paths.  The index scan (work ~ postings the queries touch) serves every batch whose sets keep key lists
     // and whose K fits the 64-bit entry; the tile join (work ~ queries x representatives) serves the rest: sets
     // imported from block lists, K > 9 with large databases, and contexts that pin it (KR_FORCE_JOIN).
-    const bool use_index = Q->d_keys && !(ctx->flags & KR_FORCE_JOIN) && db_indexable(ctx, db);
+    bool use_index = false;
+    if ((st = db_use_index(ctx, db, Q, &use_index))) return st;
     if (use_index) return find_closest_index(ctx, db, Q, 0, Q->n, d_sim, d_first, d_last);
     if ((st = db_refresh_refs(ctx, db))) return st;
     if ((st = ensure_blocklists(ctx, Q))) return st;
@@ -1300,7 +1312,10 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
             int *d_sim = nullptr;
             cudaError_t e = dalloc(ctx, &d_sim, n);
             if (e != cudaSuccess) { st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
-            if (by_index && db_indexable(ctx, db)) {
+            bool use_index = false;
+            if (by_index) st = db_use_index(ctx, db, cands, &use_index);
+            if (st != KR_OK) { dfree(ctx, d_sim); break; }
+            if (use_index) {
                 if ((st = db_refresh(ctx, db)) == KR_OK) st = find_closest_index(ctx, db, const_cast<kr_seqset *>(cands), pos, pos + n, d_sim, nullptr, nullptr);
             } else {
                 idx.resize(n);

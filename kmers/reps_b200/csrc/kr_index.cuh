@@ -14,7 +14,7 @@
 //   memory -> directory.  About 50 B of HBM traffic per entry; nothing is hashed into a table, nothing is probed.
 // Query (K5): one WARP per query.  Each lane takes keys of the query, reads the two directory words and walks the
 //   few entries of the prefix; every matching entry adds 1 to the score of its sequence id in the warp's own
-//   shared-memory score table (open addressing on the id, 1024 slots, touched slots remembered in a list).  A
+//   shared-memory score table (open addressing on the id, 512 slots, touched slots remembered in a list).  A
 //   query that touches more ids than fit is redone in 4, 16, 64 ... passes over disjoint id classes, so the
 //   result is exact for any input.  The epilogue turns the touched slots into
 //     ARGMAX  (max similarity, first rank, last rank)          -- RepGenomeDb.findClosest / checkSimilarity
@@ -125,26 +125,28 @@ __global__ void __launch_bounds__(256) k_ix_dir(const u64 *ent, const u32 *total
 }
 
 // sum over the posting lists of m^2 (work of a self scan: every entry walks its own list) and the longest list;
-// one thread per entry, run starts only.  out[0] += sum m^2, out[1] = max m, out[2] = number of entries
+// one thread per entry, run starts only.  out[0] += sum m^2, out[1] = max m, out[2] = number of entries,
+// out[3] += number of distinct keys
 __global__ void __launch_bounds__(256) k_ix_work(const u64 *ent, const u32 *total, int idbits, unsigned long long *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 n = *total;
     if (i == 0) out[2] = n;
-    unsigned long long w = 0, mx = 0;
+    unsigned long long w = 0, mx = 0, runs = 0;
     if (i < n) {
         const u64 hk = ent[i] >> idbits;
         if (i == 0 || (ent[i - 1] >> idbits) != hk) {
             u32 m = 1;
             while (i + m < n && (ent[i + m] >> idbits) == hk) ++m;
-            w = (unsigned long long)m * m; mx = m;
+            w = (unsigned long long)m * m; mx = m; runs = 1;
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
         w += __shfl_xor_sync(0xffffffffu, w, o);
+        runs += __shfl_xor_sync(0xffffffffu, runs, o);
         const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
         mx = t > mx ? t : mx;
     }
-    if ((threadIdx.x & 31) == 0 && w) { atomicAdd(&out[0], w); atomicMax(&out[1], mx); }
+    if ((threadIdx.x & 31) == 0 && w) { atomicAdd(&out[0], w); atomicMax(&out[1], mx); atomicAdd(&out[3], runs); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) k_ix_work(const u64 *ent, const u32 *tota
 enum { IXQ_ARGMAX = 0, IXQ_CELLS = 1, IXQ_DENSE = 2 };
 constexpr u32 IXQ_WARPS = 8;            // queries in flight per CTA
 #ifndef KR_IXQ_H
-#define KR_IXQ_H 1024
+#define KR_IXQ_H 512
 #endif
 constexpr u32 IXQ_H = KR_IXQ_H;         // slots of a warp's score table (a power of two; the tests also build a 64-slot variant)
 constexpr u32 IXQ_FILL = IXQ_H >= 256 ? IXQ_H * 3 / 4 - 32 : IXQ_H / 4;   // ids a pass may touch before the query is redone in more passes
@@ -163,7 +165,8 @@ static_assert(IXQ_FILL + 33 <= IXQ_H, "after the fill stops, each lane may still
 constexpr u32 IXQ_EMPTY = 0xFFFFFFFFu;
 // per warp: ids (u32), scores (u16, two per word), touched-slot list (u16), two counters
 constexpr u32 IXQ_SMEM_PER_WARP = IXQ_H * 4 + IXQ_H * 2 + IXQ_H * 2 + 16;
-constexpr u32 IXQ_SMEM = IXQ_WARPS * IXQ_SMEM_PER_WARP;     // 65,664 B: three CTAs (24 queries) per SM
+constexpr u32 IXQ_SMEM = IXQ_WARPS * IXQ_SMEM_PER_WARP;     // 32,896 B at 512 slots: six CTAs (48 queries) per SM
+constexpr u32 IXQ_CTAS_PER_SM = (232448u / (IXQ_SMEM + 1024u)) < 8u ? (232448u / (IXQ_SMEM + 1024u)) : 8u;
 
 struct IxQueryParams {
     // queries: sequences [q_begin, q_end) of a set
@@ -210,6 +213,22 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
         unsigned long long bf = 0, bl = 0;   // ARGMAX: (score << 32) | ~rank  and  (score << 32) | rank
         u32 col_min = 0;
         if (MODE != IXQ_ARGMAX) col_min = p.col_mode == 1 ? q + 1 : p.col_mode == 2 ? (q & ~255u) : 0;
+        if (MODE == IXQ_DENSE && p.ncols > col_min) {
+            // The warp owns row q of the result: it writes the whole row as zeros (streaming 16-byte stores; the head and
+            // tail up to the next 16-byte boundary element-wise) and afterwards the few cells that are not zero.  No
+            // separate zero-fill pass over the N^2 result, and the stores overlap the latency-bound walk of other warps.
+            const u32 esz = p.elem == 1 ? 2u : 4u;
+            u8 *bp = reinterpret_cast<u8 *>(p.out) + (cell_index(p.layout, q, col_min, p.nrows, p.ncols) - p.origin) * esz;
+            const u64 bytes = (u64)(p.ncols - col_min) * esz;
+            u64 head = (16 - (reinterpret_cast<uintptr_t>(bp) & 15)) & 15;
+            if (head > bytes) head = bytes;
+            const u64 body = (bytes - head) & ~15ull;
+            for (u64 k = lane * 2; k < head; k += 64) *reinterpret_cast<u16 *>(bp + k) = 0;
+            uint4 *vp = reinterpret_cast<uint4 *>(bp + head);
+            for (u64 k = lane; k < body / 16; k += 32) vp[k] = make_uint4(0u, 0u, 0u, 0u);
+            for (u64 k = head + body + lane * 2; k < bytes; k += 64) *reinterpret_cast<u16 *>(bp + k) = 0;
+            __syncwarp();      // orders the zeros before the cells this warp writes below
+        }
         // A pass scores the ids of one class (id % npass == pass).  One pass is the rule; when the ids a query touches
         // do not fit the table, NOTHING of the overflowing attempt is kept (no cell emitted, no maximum taken) and the
         // query is redone with four times as many classes, until every class fits.
@@ -222,37 +241,49 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
                 const bool dry = (rounds == 2 && round == 0);       // fill and clear only: does every class fit?
                 for (u32 pass = 0; pass < npass && !redo; ++pass) {
                     // ---- walk: every entry of the index that carries one of the query's keys scores its id -----------
-                    for (u32 i = lane; i < n; i += 32) {
-                        const u64 hk = ix_hash(kp[i], g.keybits, g.keymask);
-                        const u32 b = (u32)(hk >> dshift);
-                        const u32 lo = __ldg(p.ix.dir + b), hi = __ldg(p.ix.dir + b + 1);
+                    // (two keys per lane in flight: both directory reads, then both first entries, before either list is walked)
+                    auto score = [&](u32 id) {
+                        if (npass > 1 && (id % npass) != pass) return;
+                        if (MODE != IXQ_ARGMAX && id < col_min) return;             // a cell that is never emitted needs no score
+                        u32 h = (id * 0x9E3779B1u) >> IXQ_SHIFT;                    // multiplicative hash, top log2(IXQ_H) bits
+                        for (;;) {
+                            const u32 cur = *reinterpret_cast<volatile u32 *>(&tk[h]);
+                            if (cur == id) break;
+                            if (cur == IXQ_EMPTY) {
+                                const u32 old = atomicCAS(&tk[h], IXQ_EMPTY, id);
+                                if (old == IXQ_EMPTY) {
+                                    const u32 pos = atomicAdd(const_cast<u32 *>(&tc[0]), 1u);
+                                    if (pos < IXQ_H) tl[pos] = (u16)h;
+                                    if (pos >= IXQ_FILL) tc[1] = 1;
+                                    break;
+                                }
+                                if (old == id) break;
+                            }
+                            h = (h + 1) & (IXQ_H - 1);
+                        }
+                        atomicAdd(&ts[h >> 1], (h & 1) ? 0x10000u : 1u);
+                    };
+                    auto walk = [&](u64 hk, u32 lo, u32 hi, u64 e) {                 // e = ent[lo], already loaded when lo < hi
                         for (u32 t = lo; t < hi; ++t) {
-                            const u64 e = __ldg(p.ix.ent + t);
+                            if (t != lo) e = __ldg(p.ix.ent + t);
                             const u64 ek = e >> g.idbits;
                             if (ek < hk) continue;
                             if (ek > hk) break;
-                            const u32 id = (u32)(e & idmask);
-                            if (npass > 1 && (id % npass) != pass) continue;
-                            if (MODE != IXQ_ARGMAX && id < col_min) continue;      // a cell that is never emitted needs no score
-                            u32 h = (id * 0x9E3779B1u) >> IXQ_SHIFT;               // multiplicative hash, top log2(IXQ_H) bits
-                            for (;;) {
-                                const u32 cur = *reinterpret_cast<volatile u32 *>(&tk[h]);
-                                if (cur == id) break;
-                                if (cur == IXQ_EMPTY) {
-                                    const u32 old = atomicCAS(&tk[h], IXQ_EMPTY, id);
-                                    if (old == IXQ_EMPTY) {
-                                        const u32 pos = atomicAdd(const_cast<u32 *>(&tc[0]), 1u);
-                                        if (pos < IXQ_H) tl[pos] = (u16)h;
-                                        if (pos >= IXQ_FILL) tc[1] = 1;
-                                        break;
-                                    }
-                                    if (old == id) break;
-                                }
-                                h = (h + 1) & (IXQ_H - 1);
-                            }
-                            atomicAdd(&ts[h >> 1], (h & 1) ? 0x10000u : 1u);
+                            score((u32)(e & idmask));
                             if (tc[1]) break;      // table nearly full: stop filling (at most one more id per lane gets in)
                         }
+                    };
+                    for (u32 i = lane; i < n; i += 64) {
+                        const bool two = i + 32 < n;
+                        const u64 hk0 = ix_hash(kp[i], g.keybits, g.keymask);
+                        const u64 hk1 = two ? ix_hash(kp[i + 32], g.keybits, g.keymask) : 0;
+                        const u32 b0 = (u32)(hk0 >> dshift), b1 = (u32)(hk1 >> dshift);
+                        const u32 lo0 = __ldg(p.ix.dir + b0), hi0 = __ldg(p.ix.dir + b0 + 1);
+                        const u32 lo1 = two ? __ldg(p.ix.dir + b1) : 0, hi1 = two ? __ldg(p.ix.dir + b1 + 1) : 0;
+                        const u64 e0 = lo0 < hi0 ? __ldg(p.ix.ent + lo0) : 0, e1 = lo1 < hi1 ? __ldg(p.ix.ent + lo1) : 0;
+                        walk(hk0, lo0, hi0, e0);
+                        if (tc[1]) break;
+                        walk(hk1, lo1, hi1, e1);
                         if (tc[1]) break;
                     }
                     __syncwarp();
