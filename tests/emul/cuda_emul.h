@@ -261,13 +261,26 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 }
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 
+// Lanes of a warp run concurrently on hardware; here a fiber runs undisturbed between synchronisation points.  With
+// KR_EMUL_PREEMPT=<seed> a fiber is also suspended, pseudo-randomly, just BEFORE an atomic operation executes, so the
+// other threads of the CTA interleave inside lock-free sections (a slot seen empty and claimed by somebody else before
+// the compare-and-swap lands, counters bumped between a read and its use).
+namespace emu {
+inline void preempt() {
+    static const long mode = [] { const char *s = getenv("KR_EMUL_PREEMPT"); return s ? atol(s) : 0L; }();
+    if (!mode || !sched()) return;
+    static uint64_t x = 0x2545F4914F6CDD1Dull * (uint64_t)mode + 1;
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    if ((x & 3) == 0) { progress(); yield(); }
+}
+}  // namespace emu
 // atomics (global or shared memory alike)
-template <class T> inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-inline unsigned atomicAdd(unsigned *p, int v) { return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_SEQ_CST); }
-inline unsigned long long atomicAdd(unsigned long long *p, unsigned long v) { return __atomic_fetch_add(p, (unsigned long long)v, __ATOMIC_SEQ_CST); }
-template <class T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }   // (one fiber runs at a time)
-template <class T> inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
-template <class T> inline T atomicCAS(T *p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+template <class T> inline T atomicAdd(T *p, T v) { emu::preempt(); return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned *p, int v) { emu::preempt(); return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long v) { emu::preempt(); return __atomic_fetch_add(p, (unsigned long long)v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicMax(T *p, T v) { emu::preempt(); T o = *p; if (v > o) *p = v; return o; }   // (one fiber runs at a time)
+template <class T> inline T atomicExch(T *p, T v) { emu::preempt(); return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicCAS(T *p, T cmp, T v) { emu::preempt(); __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 
 // ---- mbarrier + bulk copy (the PTX wrappers of kr_kernels.cuh call these under KR_EMUL) -------------------------------
 namespace emu {

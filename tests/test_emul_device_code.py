@@ -39,6 +39,17 @@ def test_device_code_under_other_thread_orders(emul_lib, order, case):
     assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]
 
 
+@pytest.mark.parametrize("seed,case", [("1", "index_crowded"), ("7", "find_closest_and_build"), ("3", "sparse_matrix")])
+def test_device_code_with_preempted_atomics(emul_lib, seed, case):
+    """lanes of a warp run concurrently on hardware; KR_EMUL_PREEMPT suspends a thread pseudo-randomly just before an atomic
+    executes, so the lock-free score table of the index scan (read slot, compare-and-swap, count) and the pair counters are
+    exercised with other lanes getting in between"""
+    env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2", KR_EMUL_PREEMPT=seed)
+    p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=900)
+    assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]
+
+
 def build_variant(name, *defines):
     out = os.path.join(EMUL, "_build", name)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMUL, "cuda_emul.h")]
