@@ -151,6 +151,48 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+class Dev:
+    """Where device buffers live and how ranks talk: cuda:<local> + NCCL.  When KR_LIB_PATH points at the CPU emulator
+    build of the library (tests/test_bench_emul.py: TEST INFRASTRUCTURE that exercises this file's logic in a container
+    without a GPU; its timings mean nothing) "device" memory is host memory and the ranks use gloo."""
+
+    def __init__(self, local):
+        import torch
+        import kmers.reps_b200 as kr
+        self.torch = torch
+        self.emul = "libkmersreps_emul" in os.path.basename(kr.lib_path())
+        self.name = "cpu" if self.emul else "cuda"
+        self.backend = "gloo" if self.emul else "nccl"
+        self.local = local
+        if not self.emul:
+            torch.cuda.set_device(local)
+
+    def init_dist(self, world):
+        if world > 1:
+            import torch.distributed as dist
+            if self.emul:
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=self.torch.device("cuda", self.local))
+
+    def sync(self):
+        if not self.emul:
+            self.torch.cuda.synchronize()
+
+    def timed_ms(self, fn):
+        """device time of fn() on torch's current stream (CUDA events); wall time on the emulator"""
+        if self.emul:
+            t0 = time.perf_counter()
+            r = fn()
+            return 1000 * (time.perf_counter() - t0), r
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.torch.cuda.synchronize()
+        return e0.elapsed_time(e1), r
+
+
 def run_findclosest(args, rank, world, local):
     """Secondary workloads (BASELINE configs[3] and [4]): greedy rep-DB build at threshold 50 over synthetic
     candidates, then findClosest of synthetic queries against the first --nrep representatives.  Queries are
@@ -159,18 +201,14 @@ def run_findclosest(args, rank, world, local):
     import torch.distributed as dist
     import kmers.reps_b200 as kr
     from kmers.reps_b200 import sharding, synth
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = Dev(local)
+    dev.init_dist(world)
     ncand, nq, nrep = args.ncand, args.nq, args.nrep
     t0 = time.perf_counter()
     res, off, fam = synth.generate(0x5EED0005, ncand + nq, max(1, ncand // 50), xrun_per_10k=10)
     gen_s = time.perf_counter() - t0
-    from kmers.reps_b200 import binding
-    exp = (binding.EXP_ENCODE if args.exp_encode else 0) | (binding.EXP_IDXQ if args.exp_idxq else 0) | (binding.EXP_GIDX if args.exp_gidx else 0)
-    if exp and not binding.has_experimental():
-        raise SystemExit("--exp-* flags need KR_LIB_PATH to point at libkmersreps_cuda_exp.so")
-    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | exp)
+    pin = {"auto": 0, "join": kr.FORCE_JOIN, "index": kr.FORCE_INDEX}[args.path]
+    ctx = kr.Context(device=local, K=8, flags=kr.IDENT_IS_INFINITY | pin)
     # ---- config 4: greedy build (replicated on every rank: the accept/reject sweep is sequential) ----
     cands = ctx.encode(res=res[: int(off[ncand])], off=off[: ncand + 1])
     db = ctx.db()
@@ -187,12 +225,12 @@ def run_findclosest(args, rank, world, local):
     R = qdb.size
     # ---- config 5: findClosest, queries sharded by rank --------------------------------------------
     lo, hi = sharding.shard_range(nq, rank, world)
-    q_res = torch.from_numpy(res[int(off[ncand + lo]): int(off[ncand + hi])]).cuda()
+    q_res = torch.from_numpy(res[int(off[ncand + lo]): int(off[ncand + hi])]).to(dev.name)
     q_off = off[ncand + lo: ncand + hi + 1] - off[ncand + lo]
     myq = hi - lo
-    d_sim = torch.empty(myq, dtype=torch.int32, device="cuda")
-    d_first = torch.empty(myq, dtype=torch.int32, device="cuda")
-    d_last = torch.empty(myq, dtype=torch.int32, device="cuda")
+    d_sim = torch.empty(myq, dtype=torch.int32, device=dev.name)
+    d_first = torch.empty(myq, dtype=torch.int32, device=dev.name)
+    d_last = torch.empty(myq, dtype=torch.int32, device=dev.name)
     chunk = args.q_chunk
 
     def step():
@@ -202,11 +240,12 @@ def run_findclosest(args, rank, world, local):
             qdb.find_closest_device(qs, d_sim.data_ptr() + 4 * a, d_first.data_ptr() + 4 * a, d_last.data_ptr() + 4 * a)
             qs.free()        # stream-ordered
 
-    step()
+    for _ in range(max(1, args.warmup)):
+        step()
     ctx.synchronize()
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
+    dev.sync()
     ctx.stats_reset()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -217,62 +256,102 @@ def run_findclosest(args, rank, world, local):
     ms = ctx.timer_end()
     clocks = sampler.stop() if rank == 0 else None
     st = ctx.stats()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms], dtype=torch.float64, device=dev.name)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     gather_ms = None
     if world > 1:
         local_res = torch.stack([d_sim, d_first, d_last], 1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        allres = sharding.allgather_ranges(local_res, nq, dist)
-        e1.record()
-        torch.cuda.synchronize()
-        gather_ms = e0.elapsed_time(e1)
+        gather_ms, allres = dev.timed_ms(lambda: sharding.allgather_ranges(local_res, nq, dist))
         assert allres.shape[0] == nq
     # verify a sample against the oracle
     from oracle import kr_oracle as ko
     o = ko.get()
-    rep_idx = acc
-    reps_b = o.batch([res[int(off[i]): int(off[i + 1])].tobytes().decode() for i in rep_idx], K=8)
+    cores = os.cpu_count() or 1
+    reps_b = o.batch([res[int(off[i]): int(off[i + 1])].tobytes().decode() for i in acc], K=8)
     pick = np.random.default_rng(5 + rank).choice(myq, min(100, myq), replace=False)
-    qsel = [res[int(off[ncand + lo + i]): int(off[ncand + lo + i + 1])].tobytes().decode() for i in pick]
-    bs, bi = o.find_closest(reps_b, o.batch(qsel, K=8), threads=os.cpu_count() or 1)
-    got_sim = d_sim[torch.from_numpy(pick).cuda()].cpu().numpy()
-    got_first = d_first[torch.from_numpy(pick).cuda()].cpu().numpy()
+    qsel = o.batch([res[int(off[ncand + lo + i]): int(off[ncand + lo + i + 1])].tobytes().decode() for i in pick], K=8)
+    bs, bi = o.find_closest(reps_b, qsel, threads=cores)
+    tp = torch.from_numpy(pick).to(dev.name)
+    got_sim = d_sim[tp].cpu().numpy()
+    got_first = d_first[tp].cpu().numpy()
     ok = (got_sim == bs).all() and (got_first == np.where(bs > 0, bi, -1)).all()
     if not ok:
         raise SystemExit("bench: findClosest differs from the oracle on sampled queries")
-    cpu = None
+    used_index = st["scan_launches"] > 0
+    # ---- roofline of the scan kernel (per query n_q (8 + 16) + 4 M_q + 8 bytes) --------------------
+    # n_q is exact (the sampled queries' set sizes scaled to all queries of the rank); M_q = sum over the representatives of
+    # sim(q, rep) = postings the query's keys hold in the index, emitted by the oracle for the verified sample
+    hbm, hbm_src = peaks()
+    raw = o.sim_matrix(qsel, reps_b, ident_inf=False, threads=cores)
+    M_mean = float(raw.sum(axis=1).mean())
+    n_mean = float(qsel.sizes().mean())
+    roofline = None
+    if used_index:
+        per_q = n_mean * 24 + 4 * M_mean + 8
+        kern_ms = st["scan_ms"] / max(1, st["scan_launches"])
+        q_per_launch = myq * args.steps / max(1, st["scan_launches"])
+        alg = per_q * q_per_launch
+        achieved = alg / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                    "kernel": "k_ix_query<ARGMAX>", "kernel_ms": kern_ms, "kernel_share_of_step": st["scan_ms"] / args.steps / ms_per_step if ms_per_step else None,
+                    "peak_source": hbm_src, "algorithmic_bytes": alg, "queries_per_launch": q_per_launch,
+                    "bytes_per_query": per_q, "n_q_mean": n_mean, "M_q_mean": M_mean,
+                    "note": "SURVEY.md 8d: n_q (8 + 16) + 4 M_q + 8 bytes per query; n_q and M_q are the means over the %d oracle-verified "
+                            "sample queries of this rank (M_q = sum of raw similarities to all %d representatives, from the oracle)" % (len(pick), R)}
+    cpu = cpu_build = None
     if rank == 0 and world == 1 and not args.no_cpu:
         # the reference's algorithm (oracle port: every representative's HashSet probed with the query's k-mers) on a
         # bounded sample of the same queries, all host threads
         ns = min(myq, args.cpu_queries)
         cq = o.batch([res[int(off[ncand + i]): int(off[ncand + i + 1])].tobytes().decode() for i in range(ns)], K=8)
-        cores = os.cpu_count() or 1
         t0 = time.perf_counter()
         o.find_closest(reps_b, cq, threads=cores)
         dt = time.perf_counter() - t0
         cpu = {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": "port",
                "sample": "the first %d queries of the workload against the same %d representatives (%.1f s)" % (ns, R, dt)}
+        # the greedy build of the first --cpu-build candidates: the reference's loop is sequential (RepGenomeDbProcessor.java:134-147),
+        # so is the port: one thread.  The GPU library builds the same prefix for a like-for-like pair of numbers.
+        nb = min(ncand, args.cpu_build)
+        if nb:
+            cb = o.batch(res=res[: int(off[nb])], off=off[: nb + 1], K=8)
+            t0 = time.perf_counter()
+            n_cpu, added_cpu, pairs_cpu = o.greedy_build(cb, 50)
+            dt = time.perf_counter() - t0
+            sub = cands.gather(np.arange(nb, dtype=np.uint32))
+            db2 = ctx.db()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            added_gpu = db2.greedy_build(sub, 50, batch=args.build_batch)
+            dt_gpu = time.perf_counter() - t0
+            if not (added_gpu == added_cpu).all():
+                raise SystemExit("bench: greedy build differs from the oracle on the first %d candidates" % nb)
+            db2.free(); sub.free()
+            cpu_build = {"value": nb / dt, "unit": "candidates/s", "cores": 1, "kind": "port",
+                         "sample": "greedy build (threshold 50) of the first %d candidates: %d representatives, %d pair evaluations with early exit, "
+                                   "%.1f s on one thread (the reference's loop is sequential)" % (nb, n_cpu, pairs_cpu, dt),
+                         "gpu_same_prefix": {"seconds": dt_gpu, "candidates_per_s": nb / dt_gpu, "identical_result": True}}
     if rank == 0:
+        stage_keys = ("encode_ms", "index_ms", "scan_ms", "blocklist_ms", "join_ms", "other_ms")
         line = {
             "metric": "findClosest queries/sec", "value": nq / (ms_per_step / 1e3), "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": 1, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "findClosest of %d synthetic queries against a %d-rep DB (BASELINE configs[4]); DB = first %d reps of a "
                                    "greedy build at threshold 50 over %d synthetic candidates (configs[3])" % (nq, R, R, ncand),
-                       "K": 8, "path": "inverted index" if chunk >= 8192 else "tile join", "query_chunk": chunk,
+                       "K": 8, "path": ("sorted index + warp scan" if used_index else "tile join") + (" (pinned)" if args.path != "auto" else " (library's choice)"),
+                       "query_chunk": chunk,
                        "sharding": "queries split over %d rank(s), DB replicated, results all-gathered" % world},
             "pair_equivalents_per_s": nq * R / (ms_per_step / 1e3),
+            "roofline": roofline,
             "greedy_build": {"candidates": ncand, "reps": nreps_built, "seconds": build_s, "candidates_per_s": ncand / build_s,
-                             "pair_equivalents": int(st_build["pairs"]), "kernel_ms": {k: st_build[k] for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
-                             "launches": int(st_build["kernel_launches"])},
-            "stages_ms_per_step": {k: st[k] / args.steps for k in ("encode_ms", "blocklist_ms", "join_ms", "other_ms")},
+                             "pair_equivalents": int(st_build["pairs"]), "kernel_ms": {k: st_build[k] for k in stage_keys},
+                             "launches": int(st_build["kernel_launches"]), "index_builds": int(st_build["index_builds"])},
+            "stages_ms_per_step": {k: st[k] / args.steps for k in stage_keys},
             "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "result_allgather_ms": gather_ms,
-            "cpu_baseline": cpu,
-            "generate_s": gen_s, "verified": "100 sampled queries per rank equal the oracle",
+            "cpu_baseline": cpu, "cpu_baseline_build": cpu_build,
+            "generate_s": gen_s, "verified": "%d sampled queries per rank equal the oracle" % len(pick),
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -325,9 +404,8 @@ def main():
     import kmers.reps_b200 as kr
     from kmers.reps_b200 import sharding
 
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = Dev(local)
+    dev.init_dist(world)
     res, off, nfam = workload(args.nseq)
     N = args.nseq
     pin = {"auto": 0, "join": kr.FORCE_JOIN, "index": kr.FORCE_INDEX}[args.path]
@@ -336,8 +414,8 @@ def main():
     esz = 2 if elem == kr.ELEM_U16 else 4
     layout = kr.LAYOUT_BLOCKTRI
     r0, r1, my_elems, _ = sharding.my_stripe(N, layout, rank, world)
-    d_res = torch.from_numpy(res).cuda()
-    d_out = torch.empty(my_elems * esz + 16, dtype=torch.uint8, device="cuda")
+    d_res = torch.from_numpy(res).to(dev.name)
+    d_out = torch.empty(my_elems * esz + 16, dtype=torch.uint8, device=dev.name)
     total_pairs = N * (N - 1) // 2
     sharded_encode = world > 1 and args.sharded_encode and args.path == "join"
 
@@ -349,7 +427,7 @@ def main():
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        dev.sync()
 
     prev = None
     for _ in range(args.warmup):
@@ -381,7 +459,7 @@ def main():
     barrier()
     st = ctx.stats()
     prev.free()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms], dtype=torch.float64, device=dev.name)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
@@ -411,7 +489,7 @@ def main():
         raise SystemExit("bench: GPU result differs from the oracle on sampled cells")
     # size-independent checks of the whole stripe: every diagonal cell is INFINITY, and the number of non-zero cells
     # equals the diagonal + twice-counted in-block pairs + the sparse cell count (checked in tests at full size)
-    diag = torch.arange(r0, r1, device="cuda", dtype=torch.int64)
+    diag = torch.arange(r0, r1, device=dev.name, dtype=torch.int64)
     DI = diag // 256
     didx = 256 * (DI * N - 128 * DI * (DI - 1)) + (diag - 256 * DI) * (N - 256 * DI) + (diag - 256 * DI) - origin
     if not bool((flat_out[didx].to(torch.int32) & 0xFFFF == kr.INFINITY).all()):
@@ -472,9 +550,9 @@ def main():
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 fn()
-            torch.cuda.synchronize()
+            dev.sync()
             dt = time.perf_counter() - t0
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev.name)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt.item())
@@ -503,17 +581,13 @@ def main():
     gather = None
     if args.gather_cells and world > 1:
         cap = 1 << 22
-        d_cells = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+        d_cells = torch.zeros((cap, 4), dtype=torch.int32, device=dev.name)
         s = ctx.encode_device(d_res.data_ptr(), off)
         cnt = ctx.sim_matrix_sparse_device(s, None, d_cells.data_ptr(), cap, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1)
         sharding.allgather_cells(d_cells, cnt, cap, dist)      # warm-up
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        allc = sharding.allgather_cells(d_cells, cnt, cap, dist)
-        e1.record()
-        torch.cuda.synchronize()
-        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        g_ms, allc = dev.timed_ms(lambda: sharding.allgather_cells(d_cells, cnt, cap, dist))
+        tg = torch.tensor([g_ms], dtype=torch.float64, device=dev.name)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gather = {"ms": float(tg.item()), "cells_total": int(allc.shape[0]), "bytes_per_rank": int(cap * 16)}
         s.free()

@@ -780,10 +780,9 @@ static kr_status db_ensure_index(kr_ctx *ctx, kr_db *db) {
 static kr_status db_use_index(kr_ctx *ctx, kr_db *db, const kr_seqset *Q, bool *use) {
     *use = false;
     if (!Q->d_keys || (ctx->flags & KR_FORCE_JOIN) || !db_indexable(ctx, db)) return KR_OK;
-    if (ctx->flags & KR_FORCE_INDEX) { *use = true; return KR_OK; }
     kr_status st;
     if ((st = db_refresh(ctx, db)) || (st = db_ensure_index(ctx, db)) || (st = index_stats(ctx, db->ix_main))) return st;
-    *use = index_list_length(*db->ix_main) <= IX_DENSE_LISTS;
+    *use = (ctx->flags & KR_FORCE_INDEX) || index_list_length(*db->ix_main) <= IX_DENSE_LISTS;
     return KR_OK;
 }
 

@@ -356,7 +356,7 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefau
        cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 4; size_t sharedMemPerBlockOptin = 232448; char name[64] = "cuda_emul"; };
 inline const char *cudaGetErrorString(cudaError_t e) { return e ? "emulated error" : "no error"; }
-inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { const char *s = getenv("KR_EMUL_DEVICES"); *n = s ? atoi(s) : 1; return cudaSuccess; }   // all "devices" are this host
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp(); if (const char *s = getenv("KR_EMUL_SMS")) p->multiProcessorCount = atoi(s); return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
