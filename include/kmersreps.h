@@ -20,8 +20,10 @@
  *     convention for fatal errors: RuntimeException, App.java:129).
  *   - a kr_ctx is bound to one GPU and is internally serialised: it may be called from any
  *     thread (NeighborProcessor.java:143-145 and GtoRepBuildProcessor.java:127 use parallel
- *     streams).  Multi-GPU jobs use one context per GPU (one process or one thread each) and the
- *     stripe / shard arguments below; nothing in this ABI communicates between GPUs.
+ *     streams).  Several GPUs: either one context per GPU driven by the caller (one process or
+ *     thread each, with the stripe / shard arguments below -- what bench.py does under torchrun),
+ *     or ONE kr_multi handle (last section) that owns a context and a worker thread per GPU and
+ *     shards every call internally.  The path has no data-path exchange between GPUs.
  *   - sequences are passed as one flat residue buffer plus offsets: sequence i is
  *     residues[offsets[i] .. offsets[i+1]).  Residues are the characters of the Java String;
  *     'A'..'Z', '*' and '-' are accepted (5-bit packing must stay injective);
@@ -244,6 +246,51 @@ kr_status kr_timer_end(kr_ctx *ctx, double *ms);
 /* pinned host memory for callers that want full-speed copies of large matrices */
 kr_status kr_host_alloc(kr_ctx *ctx, size_t bytes, void **out);
 void kr_host_free(kr_ctx *ctx, void *p);
+
+/* ---- several GPUs behind one handle ---------------------------------------------------------
+ * "kr_create(const int* devices, int ndev, ...)", one worker thread + stream per
+ * GPU inside, so that one JVM reaches every GPU of the box.  A kr_multi owns one kr_ctx per listed
+ * device (a device may be listed more than once).  Every call below takes HOST buffers, splits the
+ * work (row stripes of a matrix, query ranges of a findClosest, candidate ranges of a build batch),
+ * runs the single-GPU entry point on each context from that context's worker thread and lets each
+ * GPU copy its share of the result into its own slice of the caller's buffer -- the "allgather of
+ * per-shard results" of a caller whose consumer is host code.  Results are identical to the
+ * single-GPU calls.  A kr_multi is internally serialised (one multi call at a time, any thread). */
+typedef struct kr_multi kr_multi;
+typedef struct kr_multi_db kr_multi_db; /* a RepGenomeDb replicated on every GPU of a kr_multi */
+kr_status kr_multi_create(const int *devices, int ndev, int K, uint32_t flags, kr_multi **out);
+void kr_multi_destroy(kr_multi *m);
+int kr_multi_ndev(const kr_multi *m);
+kr_ctx *kr_multi_ctx(kr_multi *m, int i);          /* the i-th context, for single-GPU calls */
+const char *kr_multi_last_error(const kr_multi *m); /* m may be NULL for creation errors */
+/* kr_encode + kr_sim_matrix over all GPUs.  off_b == NULL: all-vs-all of batch A in `layout`
+ * (DistanceMatrixProcessor.java:71-76, RepMatrixProcessor.java:88-93); otherwise rows of A against B,
+ * KR_LAYOUT_FULL (NeighborProcessor.java:165-193).  out_host holds kr_matrix_elems(n_a, n_cols, layout, 0, n_a)
+ * elements of `elem` (KR_ELEM_*). */
+kr_status kr_multi_sim_matrix(kr_multi *m, const uint8_t *res_a, const uint64_t *off_a, uint32_t n_a, const uint8_t *res_b,
+                              const uint64_t *off_b, uint32_t n_b, uint32_t elem, uint32_t layout, void *out_host);
+/* the same as sparse cells (kr_sim_matrix_sparse): (row, col, sim, 0) with sim >= min_sim, unordered;
+ * layout KR_LAYOUT_FULL, or KR_LAYOUT_TRIANGLE for an all-vs-all */
+kr_status kr_multi_sim_matrix_sparse(kr_multi *m, const uint8_t *res_a, const uint64_t *off_a, uint32_t n_a, const uint8_t *res_b,
+                                     const uint64_t *off_b, uint32_t n_b, int32_t min_sim, uint32_t layout, uint32_t *cells_host,
+                                     uint64_t cap, uint64_t *count);
+kr_status kr_multi_db_create(kr_multi *m, kr_multi_db **out);
+void kr_multi_db_free(kr_multi_db *db);
+uint32_t kr_multi_db_size(const kr_multi_db *db);
+kr_status kr_multi_db_append(kr_multi *m, kr_multi_db *db, const uint8_t *residues, const uint64_t *offsets, uint32_t nseq);
+kr_status kr_multi_db_set_ranks(kr_multi *m, kr_multi_db *db, const uint32_t *rank, uint32_t n);
+/* kr_encode + kr_db_find_closest, queries split into one contiguous range per GPU
+ * (RepGenomeDbProcessor.java:235-252, GtoRepGenomeProcessor.java:271) */
+kr_status kr_multi_db_find_closest(kr_multi *m, const kr_multi_db *db, const uint8_t *residues, const uint64_t *offsets, uint32_t nq,
+                                   int32_t *best_sim, uint32_t *best_first, uint32_t *best_last);
+kr_status kr_multi_db_any_ge(kr_multi *m, const kr_multi_db *db, const uint8_t *residues, const uint64_t *offsets, uint32_t nc,
+                             int32_t threshold, uint8_t *represented);
+/* kr_encode + kr_greedy_build: per batch every GPU scores its share of the candidates against its replica, the
+ * survivors are resolved once (first GPU), the accepted ones are appended to every replica
+ * (RepGenomeDbProcessor.java:134-147, 160-163) */
+kr_status kr_multi_greedy_build(kr_multi *m, kr_multi_db *db, const uint8_t *residues, const uint64_t *offsets, uint32_t ncand,
+                                int32_t threshold, uint32_t batch, uint8_t *added);
+kr_status kr_multi_stats_get(kr_multi *m, kr_stats *out); /* sums over the GPUs (times are device-ms summed) */
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,9 @@ SYMBOLS = [
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
     "kr_db_find_closest", "kr_db_find_closest_device", "kr_db_any_ge", "kr_greedy_build", "kr_stats_get",
     "kr_stats_reset", "kr_timer_begin", "kr_timer_end", "kr_host_alloc", "kr_host_free",
+    "kr_multi_create", "kr_multi_destroy", "kr_multi_ndev", "kr_multi_ctx", "kr_multi_last_error", "kr_multi_sim_matrix",
+    "kr_multi_sim_matrix_sparse", "kr_multi_db_create", "kr_multi_db_free", "kr_multi_db_size", "kr_multi_db_append",
+    "kr_multi_db_set_ranks", "kr_multi_db_find_closest", "kr_multi_db_any_ge", "kr_multi_greedy_build", "kr_multi_stats_get",
 ]
 
 
@@ -133,6 +136,27 @@ def load_library():
     lib.kr_host_free.restype = None
     lib.kr_sim_matrix_sparse.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
     lib.kr_sim_matrix_sparse_device.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
+    lib.kr_multi_create.argtypes = [vp, C.c_int, C.c_int, u32, C.POINTER(vp)]
+    lib.kr_multi_destroy.argtypes = [vp]
+    lib.kr_multi_destroy.restype = None
+    lib.kr_multi_ndev.argtypes = [vp]
+    lib.kr_multi_ctx.argtypes = [vp, C.c_int]
+    lib.kr_multi_ctx.restype = vp
+    lib.kr_multi_last_error.argtypes = [vp]
+    lib.kr_multi_last_error.restype = C.c_char_p
+    lib.kr_multi_sim_matrix.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, u32, vp]
+    lib.kr_multi_sim_matrix_sparse.argtypes = [vp, vp, vp, u32, vp, vp, u32, i32, u32, vp, u64, C.POINTER(u64)]
+    lib.kr_multi_db_create.argtypes = [vp, C.POINTER(vp)]
+    lib.kr_multi_db_free.argtypes = [vp]
+    lib.kr_multi_db_free.restype = None
+    lib.kr_multi_db_size.argtypes = [vp]
+    lib.kr_multi_db_size.restype = u32
+    lib.kr_multi_db_append.argtypes = [vp, vp, vp, vp, u32]
+    lib.kr_multi_db_set_ranks.argtypes = [vp, vp, vp, u32]
+    lib.kr_multi_db_find_closest.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
+    lib.kr_multi_db_any_ge.argtypes = [vp, vp, vp, vp, u32, i32, vp]
+    lib.kr_multi_greedy_build.argtypes = [vp, vp, vp, vp, u32, i32, u32, vp]
+    lib.kr_multi_stats_get.argtypes = [vp, C.POINTER(Stats)]
     _LIB = lib
     return lib
 
@@ -417,4 +441,125 @@ class RepDb:
     def greedy_build(self, cands: SeqSet, threshold: int, batch: int = 0):
         added = np.zeros(cands.count, dtype=np.uint8)
         self.ctx._ck(self.ctx.lib.kr_greedy_build(self.ctx.h, self.h, cands.h, threshold, batch, added.ctypes.data))
+        return added
+
+
+def _flat_args(seqs, res, off):
+    if res is None:
+        res, off = flat(seqs)
+    res = np.ascontiguousarray(res, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    return (res if res.size else np.zeros(1, np.uint8)), off
+
+
+class MultiContext:
+    """Several GPUs behind one handle (kr_multi): host buffers in, host buffers out, sharding inside the library."""
+
+    def __init__(self, devices, K=8, flags=IDENT_IS_INFINITY):
+        self.lib = load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.kr_multi_create(devs, len(devices), K, flags, C.byref(h))
+        if rc:
+            raise KrError(rc, self.lib.kr_multi_last_error(None).decode())
+        self.h, self.K, self.flags = h, K, flags
+        self.ndev = int(self.lib.kr_multi_ndev(h))
+
+    def _ck(self, rc):
+        if rc:
+            raise KrError(rc, self.lib.kr_multi_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kr_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sim_matrix(self, seqs=None, res=None, off=None, b_seqs=None, b_res=None, b_off=None, elem=ELEM_I32, layout=LAYOUT_FULL):
+        ra, oa = _flat_args(seqs, res, off)
+        na = len(oa) - 1
+        rect = b_seqs is not None or b_off is not None
+        rb, ob = _flat_args(b_seqs, b_res, b_off) if rect else (None, None)
+        nb = len(ob) - 1 if rect else 0
+        ncols = nb if rect else na
+        out = np.zeros(matrix_elems(na, ncols, layout), dtype=np.uint16 if elem == ELEM_U16 else np.int32)
+        self._ck(self.lib.kr_multi_sim_matrix(self.h, ra.ctypes.data, oa.ctypes.data, na, _ptr(rb), _ptr(ob), nb, elem, layout, out.ctypes.data))
+        return out.reshape(na, ncols) if layout == LAYOUT_FULL else out
+
+    def sim_matrix_sparse(self, seqs=None, res=None, off=None, b_seqs=None, b_res=None, b_off=None, min_sim=1, layout=LAYOUT_TRIANGLE, cap=1 << 20):
+        ra, oa = _flat_args(seqs, res, off)
+        rect = b_seqs is not None or b_off is not None
+        rb, ob = _flat_args(b_seqs, b_res, b_off) if rect else (None, None)
+        while True:
+            cells = np.zeros((cap, 4), dtype=np.uint32)
+            n = C.c_uint64(0)
+            rc = self.lib.kr_multi_sim_matrix_sparse(self.h, ra.ctypes.data, oa.ctypes.data, len(oa) - 1, _ptr(rb), _ptr(ob), len(ob) - 1 if rect else 0,
+                                                     int(min_sim), layout, cells.ctypes.data, cap, C.byref(n))
+            if rc == 0:
+                return cells[: n.value]
+            if n.value <= cap:
+                self._ck(rc)
+            cap = int(n.value)
+
+    def db(self) -> "MultiDb":
+        h = C.c_void_p()
+        self._ck(self.lib.kr_multi_db_create(self.h, C.byref(h)))
+        return MultiDb(self, h)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self.lib.kr_multi_stats_get(self.h, C.byref(s)))
+        return s.asdict()
+
+
+class MultiDb:
+    def __init__(self, m: MultiContext, h):
+        self.m, self.h = m, h
+
+    def free(self):
+        if self.h:
+            self.m.lib.kr_multi_db_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.m.h:
+                self.free()
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        return int(self.m.lib.kr_multi_db_size(self.h))
+
+    def append(self, seqs=None, res=None, off=None):
+        r, o = _flat_args(seqs, res, off)
+        self.m._ck(self.m.lib.kr_multi_db_append(self.m.h, self.h, r.ctypes.data, o.ctypes.data, len(o) - 1))
+
+    def set_ranks(self, rank):
+        rank = np.ascontiguousarray(rank, dtype=np.uint32)
+        self.m._ck(self.m.lib.kr_multi_db_set_ranks(self.m.h, self.h, rank.ctypes.data, len(rank)))
+
+    def find_closest(self, seqs=None, res=None, off=None):
+        r, o = _flat_args(seqs, res, off)
+        n = len(o) - 1
+        sim, first, last = np.zeros(n, np.int32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self.m._ck(self.m.lib.kr_multi_db_find_closest(self.m.h, self.h, r.ctypes.data, o.ctypes.data, n, sim.ctypes.data, first.ctypes.data, last.ctypes.data))
+        return sim, first, last
+
+    def any_ge(self, threshold, seqs=None, res=None, off=None):
+        r, o = _flat_args(seqs, res, off)
+        out = np.zeros(len(o) - 1, dtype=np.uint8)
+        self.m._ck(self.m.lib.kr_multi_db_any_ge(self.m.h, self.h, r.ctypes.data, o.ctypes.data, len(o) - 1, int(threshold), out.ctypes.data))
+        return out
+
+    def greedy_build(self, threshold, seqs=None, res=None, off=None, batch=0):
+        r, o = _flat_args(seqs, res, off)
+        added = np.zeros(len(o) - 1, dtype=np.uint8)
+        self.m._ck(self.m.lib.kr_multi_greedy_build(self.m.h, self.h, r.ctypes.data, o.ctypes.data, len(o) - 1, int(threshold), int(batch), added.ctypes.data))
         return added

@@ -1284,6 +1284,120 @@ kr_status kr_db_any_ge(kr_ctx *ctx, const kr_db *db, const kr_seqset *cands, int
     return KR_OK;
 }
 
+}  // extern "C"
+
+// ---- the greedy build, in three steps that the single-GPU and the multi-GPU entry points share (callers hold the
+//      context's lock) --------------------------------------------------------------------------------------------
+// 1. best similarity of candidates [pos0, pos1) of `cands` against the representatives so far -> best[0 .. pos1 - pos0)
+static kr_status build_score_range(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, u32 pos0, u32 pos1, int32_t *best) {
+    const u32 n = pos1 - pos0;
+    if (!n) return KR_OK;
+    if (!db->n) { for (u32 i = 0; i < n; ++i) best[i] = 0; return KR_OK; }
+    kr_status st = KR_OK;
+    int *d_sim = nullptr;
+    CU(dalloc(ctx, &d_sim, n));
+    bool use_index = false;
+    if (cands->d_keys && !(ctx->flags & KR_FORCE_JOIN)) st = db_use_index(ctx, db, cands, &use_index);
+    if (st == KR_OK) {
+        if (use_index) {
+            if ((st = db_refresh(ctx, db)) == KR_OK) st = find_closest_index(ctx, db, const_cast<kr_seqset *>(cands), pos0, pos1, d_sim, nullptr, nullptr);
+        } else {
+            std::vector<u32> idx(n);
+            for (u32 i = 0; i < n; ++i) idx[i] = pos0 + i;
+            kr_seqset *bs = nullptr;
+            if ((st = gather_impl(ctx, cands, idx.data(), n, &bs)) == KR_OK) {
+                st = find_closest_launch(ctx, db, bs, d_sim, nullptr, nullptr);
+                seqset_destroy(bs);      // stream-ordered release
+            }
+        }
+    }
+    if (st == KR_OK) {
+        cudaError_t e = cudaMemcpyAsync(best, d_sim, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
+        ctx->st.d2h_bytes += (u64)n * 4;
+        if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
+    }
+    dfree(ctx, d_sim);
+    return st;
+}
+
+// 2. the in-order sweep of checkGenome over the survivors (candidates no current representative covers): surv holds
+//    their positions in `cands`, ascending; acc receives the indices INTO surv of the accepted ones
+static kr_status build_resolve(kr_ctx *ctx, const kr_seqset *cands, const std::vector<u32> &surv, int32_t threshold, std::vector<u32> *acc) {
+    const u32 S = (u32)surv.size();
+    kr_status st = KR_OK;
+    acc->clear();
+    if (S == 0) return KR_OK;
+    if (S == 1) { acc->push_back(0); return KR_OK; }
+    kr_seqset *ss = nullptr;
+    if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) return st;
+    if (threshold >= 1) {
+        // survivors against one another as the sparse cells with sim >= threshold: a few cells per survivor
+        kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_TRIANGLE, 0, S};
+        uint64_t room = 8 * (uint64_t)S + 1024, ncell = 0;
+        std::vector<u32> cells((size_t)room * 4);
+        st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), room, &ncell, nullptr);
+        if (st == KR_ERR_ARG && ncell > room) {      // more qualifying pairs than guessed: once more with room for all
+            room = ncell; cells.resize((size_t)room * 4);
+            st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), room, &ncell, nullptr);
+        }
+        seqset_destroy(ss);
+        if (st) return st;
+        // earlier[s] = survivors t < s with similarity >= threshold (CSR over the cells)
+        std::vector<u32> start(S + 1, 0), adj((size_t)ncell);
+        for (uint64_t k = 0; k < ncell; ++k) start[cells[4 * k + 1] + 1]++;
+        for (u32 v = 0; v < S; ++v) start[v + 1] += start[v];
+        std::vector<u32> fill(start.begin(), start.end() - 1);
+        for (uint64_t k = 0; k < ncell; ++k) adj[fill[cells[4 * k + 1]]++] = cells[4 * k];
+        std::vector<u8> accepted(S, 0);
+        for (u32 v = 0; v < S; ++v) {
+            bool repd = false;
+            for (u32 k = start[v]; k < start[v + 1] && !repd; ++k) repd = accepted[adj[k]] != 0;
+            if (!repd) { accepted[v] = 1; acc->push_back(v); }
+        }
+        return KR_OK;
+    }
+    // threshold <= 0: every similarity qualifies; the dense survivor matrix keeps the general code path honest
+    kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, S};
+    u16 *d_M = nullptr;
+    cudaError_t e = dalloc(ctx, &d_M, (size_t)S * S + 8);
+    if (e != cudaSuccess) { seqset_destroy(ss); return fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); }
+    st = matrix_launch(ctx, ss, nullptr, true, &d, d_M);
+    std::vector<u16> M((size_t)S * S);
+    if (st == KR_OK) {
+        e = cudaMemcpyAsync(M.data(), d_M, (size_t)S * S * 2, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
+        ctx->st.d2h_bytes += (u64)S * S * 2;
+        if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
+    }
+    dfree(ctx, d_M);
+    seqset_destroy(ss);
+    if (st) return st;
+    for (u32 v = 0; v < S; ++v) {
+        bool rep = false;
+        const u16 *row = M.data() + (size_t)v * S;   // M is symmetric
+        for (u32 t : *acc) if ((int)row[t] >= threshold) { rep = true; break; }
+        if (!rep) acc->push_back(v);
+    }
+    return KR_OK;
+}
+
+// 3. append the accepted candidates (positions in `cands`) to the database
+static kr_status build_accept(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, const std::vector<u32> &acc_idx) {
+    if (acc_idx.empty()) return KR_OK;
+    kr_seqset *as = nullptr;
+    kr_status st = gather_impl(ctx, cands, acc_idx.data(), (u32)acc_idx.size(), &as);
+    if (st) return st;
+    return db_append_owned(ctx, db, as);
+}
+
+static u32 build_default_batch(const kr_ctx *ctx, const kr_seqset *cands) {
+    return (cands->d_keys && !(ctx->flags & KR_FORCE_JOIN)) ? 32768u : 4096u;
+}
+
+extern "C" {
 
 kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_t threshold, uint32_t batch, uint8_t *added) {
     if (!ctx || !db || !cands || !added) return fail(ctx, KR_ERR_ARG, "kr_greedy_build: null argument");
@@ -1294,119 +1408,27 @@ kr_status kr_greedy_build(kr_ctx *ctx, kr_db *db, const kr_seqset *cands, int32_
     //   1. best similarity of every candidate against the representatives so far (index scan straight on the
     //      candidate set -- no gather -- or the tile join when the sets cannot be indexed);
     //   2. the candidates below the threshold ("survivors") against one another, as the sparse cells with
-    //      sim >= threshold: a few cells per survivor instead of an S x S matrix;
-    //   3. the sweep in candidate order over those adjacency lists on the host; accepted candidates are appended
-    //      (the database's tail index is rebuilt by the next batch's scan).
-    const bool by_index = cands->d_keys && !(ctx->flags & KR_FORCE_JOIN);
-    if (batch == 0) batch = by_index ? 32768 : 4096;
+    //      sim >= threshold, and the sweep in candidate order over those adjacency lists on the host;
+    //   3. accepted candidates are appended (the database's tail index is rebuilt by the next batch's scan).
+    if (batch == 0) batch = build_default_batch(ctx, cands);
     const u32 C = cands->n;
     kr_status st = KR_OK;
-    std::vector<u32> idx, surv, acc, cells;
+    std::vector<u32> surv, acc, acc_idx;
     std::vector<int32_t> best;
-    std::vector<u16> M;
     for (u32 pos = 0; pos < C && st == KR_OK; pos += batch) {
         const u32 n = std::min(batch, C - pos);
+        best.resize(n);
+        if ((st = build_score_range(ctx, db, cands, pos, pos + n, best.data()))) break;
         surv.clear();
-        if (db->n) {
-            int *d_sim = nullptr;
-            cudaError_t e = dalloc(ctx, &d_sim, n);
-            if (e != cudaSuccess) { st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
-            bool use_index = false;
-            if (by_index) st = db_use_index(ctx, db, cands, &use_index);
-            if (st != KR_OK) { dfree(ctx, d_sim); break; }
-            if (use_index) {
-                if ((st = db_refresh(ctx, db)) == KR_OK) st = find_closest_index(ctx, db, const_cast<kr_seqset *>(cands), pos, pos + n, d_sim, nullptr, nullptr);
-            } else {
-                idx.resize(n);
-                for (u32 i = 0; i < n; ++i) idx[i] = pos + i;
-                kr_seqset *bs = nullptr;
-                if ((st = gather_impl(ctx, cands, idx.data(), n, &bs)) == KR_OK) {
-                    st = find_closest_launch(ctx, db, bs, d_sim, nullptr, nullptr);
-                    seqset_destroy(bs);      // stream-ordered release
-                }
-            }
-            best.resize(n);
-            if (st == KR_OK) {
-                e = cudaMemcpyAsync(best.data(), d_sim, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-                if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
-                ctx->st.d2h_bytes += (u64)n * 4;
-                if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
-            }
-            dfree(ctx, d_sim);
-            if (st) break;
-            for (u32 i = 0; i < n; ++i) { if (best[i] < threshold) surv.push_back(pos + i); else added[pos + i] = 0; }
-        } else {
-            surv.resize(n);
-            for (u32 i = 0; i < n; ++i) surv[i] = pos + i;
-        }
-        if (surv.empty()) continue;
-        // survivors against one another, then the in-order sweep of checkGenome
-        const u32 S = (u32)surv.size();
-        acc.clear();
-        if (S == 1) {
-            acc.push_back(0);
-        } else if (threshold >= 1) {
-            kr_seqset *ss = nullptr;
-            if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) break;
-            kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_TRIANGLE, 0, S};
-            uint64_t room = 8 * (uint64_t)S + 1024, ncell = 0;
-            cells.resize((size_t)room * 4);
-            st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), room, &ncell, nullptr);
-            if (st == KR_ERR_ARG && ncell > room) {      // more qualifying pairs than guessed: once more with room for all
-                room = ncell; cells.resize((size_t)room * 4);
-                st = sparse_impl(ctx, ss, nullptr, &d, threshold, cells.data(), room, &ncell, nullptr);
-            }
-            seqset_destroy(ss);
-            if (st) break;
-            // earlier[s] = survivors t < s with similarity >= threshold (CSR over the cells)
-            std::vector<u32> start(S + 1, 0), adj((size_t)ncell);
-            for (uint64_t k = 0; k < ncell; ++k) start[cells[4 * k + 1] + 1]++;
-            for (u32 v = 0; v < S; ++v) start[v + 1] += start[v];
-            std::vector<u32> fill(start.begin(), start.end() - 1);
-            for (uint64_t k = 0; k < ncell; ++k) adj[fill[cells[4 * k + 1]]++] = cells[4 * k];
-            std::vector<u8> accepted(S, 0);
-            for (u32 v = 0; v < S; ++v) {
-                bool repd = false;
-                for (u32 k = start[v]; k < start[v + 1] && !repd; ++k) repd = accepted[adj[k]] != 0;
-                if (!repd) { accepted[v] = 1; acc.push_back(v); }
-            }
-        } else {
-            // threshold <= 0: every similarity qualifies; the dense survivor matrix keeps the general code path honest
-            kr_seqset *ss = nullptr;
-            if ((st = gather_impl(ctx, cands, surv.data(), S, &ss))) break;
-            kr_matrix_desc d{KR_ELEM_U16, KR_LAYOUT_FULL, 0, S};
-            u16 *d_M = nullptr;
-            cudaError_t e = dalloc(ctx, &d_M, (size_t)S * S + 8);
-            if (e != cudaSuccess) { seqset_destroy(ss); st = fail(ctx, KR_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)); break; }
-            st = matrix_launch(ctx, ss, nullptr, true, &d, d_M);
-            M.resize((size_t)S * S);
-            if (st == KR_OK) {
-                e = cudaMemcpyAsync(M.data(), d_M, (size_t)S * S * 2, cudaMemcpyDeviceToHost, ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-                if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "copy: %s", cudaGetErrorString(e));
-                ctx->st.d2h_bytes += (u64)S * S * 2;
-                if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
-            }
-            dfree(ctx, d_M);
-            seqset_destroy(ss);
-            if (st) break;
-            for (u32 v = 0; v < S; ++v) {
-                bool rep = false;
-                const u16 *row = M.data() + (size_t)v * S;   // M is symmetric
-                for (u32 t : acc) if ((int)row[t] >= threshold) { rep = true; break; }
-                if (!rep) acc.push_back(v);
-            }
-        }
-        std::vector<u32> acc_idx(acc.size());
-        for (u32 v = 0; v < S; ++v) added[surv[v]] = 0;
+        for (u32 i = 0; i < n; ++i) { added[pos + i] = 0; if (best[i] < threshold || !db->n) surv.push_back(pos + i); }
+        if ((st = build_resolve(ctx, cands, surv, threshold, &acc))) break;
+        acc_idx.resize(acc.size());
         for (size_t k = 0; k < acc.size(); ++k) { acc_idx[k] = surv[acc[k]]; added[acc_idx[k]] = 1; }
-        kr_seqset *as = nullptr;
-        if ((st = gather_impl(ctx, cands, acc_idx.data(), (u32)acc_idx.size(), &as))) break;
-        st = db_append_owned(ctx, db, as);
+        st = build_accept(ctx, db, cands, acc_idx);
     }
     return st;
 }
 
 }  // extern "C"
 
+#include "kr_api_multi.inc"

@@ -349,6 +349,78 @@ def case_api_misc():
     c.close()
 
 
+def case_multi():
+    """several contexts behind one kr_multi handle (KR_EMUL_DEVICES "GPUs", one worker thread each): matrices in every
+    layout, sparse cells with too little room per slice, rectangular, findClosest with ranks, any_ge, the greedy build with
+    the scoring split -- all equal to the oracle, i.e. to the single-GPU calls"""
+    ndev = int(os.environ.get("KR_EMUL_DEVICES", "1"))
+    devs = list(range(ndev)) if ndev > 1 else [0, 0, 0]           # one device listed three times: three contexts on it
+    seqs = family(31, 800, 10, 50, 110) + ["MKV", "", "MKVLAAGIVG", "MKVLAAGIVG", "MKV"]
+    seqs[9] = seqs[700]
+    n = len(seqs)
+    ob = O.batch(seqs, K=8)
+    want = O.sim_matrix(ob, ident_inf=True, threads=4)
+    for path in PATHS:
+        m = kr.MultiContext(devs, K=8, flags=kr.IDENT_IS_INFINITY | path)
+        assert m.ndev == len(devs)
+        assert (m.sim_matrix(seqs, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all(), path
+        tri = m.sim_matrix(seqs, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE)
+        assert (tri == np.concatenate([want[i, i + 1:] for i in range(n)])).all(), path
+        assert (m.sim_matrix(seqs, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == blocktri(want)).all(), path
+        got = m.sim_matrix_sparse(seqs, min_sim=1, layout=kr.LAYOUT_TRIANGLE, cap=1 << 16)
+        assert len(cells(got)) == len(got) and cells(got) == want_cells(want, 1, True), path
+        full = want_cells(want, 20, False)
+        got = m.sim_matrix_sparse(seqs, min_sim=20, layout=kr.LAYOUT_FULL, cap=len(full))     # exact room: slices overflow, the total fits
+        assert cells(got) == full, path
+        try:
+            m.lib.kr_multi_sim_matrix_sparse                                                   # too little room in total: refused with the count
+            c = np.zeros((8, 4), np.uint32); cnt = kr.binding.C.c_uint64(0)
+            r, o = kr.flat(seqs)
+            rc = m.lib.kr_multi_sim_matrix_sparse(m.h, r.ctypes.data, o.ctypes.data, n, None, None, 0, 20, kr.LAYOUT_FULL, c.ctypes.data, 8, kr.binding.C.byref(cnt))
+            assert rc == -1 and cnt.value == len(full)
+        finally:
+            pass
+        # rectangular: 150 query rows against 500 columns
+        qa, qb = seqs[600:750], seqs[:500]
+        wr = O.sim_matrix(O.batch(qa, K=8), O.batch(qb, K=8), ident_inf=True, threads=4)
+        assert (m.sim_matrix(qa, b_seqs=qb, elem=kr.ELEM_I32) == wr).all(), path
+        got = m.sim_matrix_sparse(qa, b_seqs=qb, min_sim=3, layout=kr.LAYOUT_FULL)
+        assert cells(got) == want_cells(wr, 3, False), path
+        # database replicated, queries split
+        reps, qs = seqs[:500], seqs[500:]
+        rank = np.random.default_rng(4).permutation(len(reps)).astype(np.uint32)
+        order = np.argsort(rank).astype(np.int32)
+        bs, bi = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=order, ident_inf=True)
+        bs2, bl2 = O.find_closest(O.batch(reps, K=8), O.batch(qs, K=8), order=order, ident_inf=True, tie_last=True)
+        db = m.db()
+        db.append(reps[:200]); db.append(reps[200:])
+        db.set_ranks(rank)
+        assert db.size == 500
+        sim, first, last = db.find_closest(qs)
+        assert (sim == bs).all() and (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), path
+        assert (last.astype(np.int64) == np.where(bs2 > 0, bl2.astype(np.int64), kr.NO_REP)).all(), path
+        assert (db.any_ge(30, qs) == (bs >= 30)).all()
+        sim1, _, _ = db.find_closest(qs[:2])                         # fewer queries than contexts
+        assert (sim1 == bs[:2]).all()
+        db.free()
+        # greedy build, scoring split over the contexts
+        for thr, batch in ((30, 64), (10, 0)):
+            _, wa, _ = O.greedy_build(ob, thr, ident_inf=True)
+            db = m.db()
+            a0 = db.greedy_build(thr, seqs[:300], batch=batch)
+            a1 = db.greedy_build(thr, seqs[300:], batch=batch)
+            assert (np.concatenate([a0, a1]) == wa).all() and db.size == int(wa.sum()), (path, thr)
+            db.free()
+        st = m.stats()
+        assert st["kernel_launches"] > 0 and st["pairs"] > 0
+        m.close()
+    try:
+        kr.MultiContext([0, 99], K=8)
+        raise AssertionError("device 99 accepted")
+    except kr.KrError as e:
+        assert "device 99" in str(e)
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

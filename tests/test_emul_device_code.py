@@ -79,6 +79,15 @@ def test_device_code_on_the_emulator(emul_lib, case):
     assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]
 
 
+@pytest.mark.parametrize("devices", ["3", "1"])
+def test_multi_gpu_handle_on_the_emulator(emul_lib, devices):
+    """kr_multi: three emulated devices, and one device listed three times; one worker thread per context"""
+    env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2", KR_EMUL_DEVICES=devices)
+    p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), "multi"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=1500)
+    assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK multi"), p.stdout.decode()[-3000:]
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_paths_end_to_end_on_the_emulator(emul_lib, world):
     """gloo ranks, one emulator context each: the block-list exchange (all-gather + import) of the tile-join path, and the

@@ -552,3 +552,55 @@ def test_shard_import_rejects_bad_layout(ctx):
     assert ctx.sim_matrix(ok, elem=kr.ELEM_U16).shape == (600, 600)
     for p in parts:
         p.free()
+
+
+def _gpu_list():
+    """every GPU of the box -- or, on a one-GPU box, that GPU listed twice (two contexts, two worker threads on it)"""
+    import ctypes as C
+    n = C.c_int(0)
+    try:
+        C.CDLL("libcudart.so").cudaGetDeviceCount(C.byref(n))
+    except OSError:
+        import torch
+        n.value = torch.cuda.device_count()
+    return list(range(n.value)) if n.value > 1 else [0, 0]
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_multi_handle_equals_single_gpu_and_oracle(path, rep50, gto_seeds, oracle):
+    """kr_multi (include/kmersreps.h, last section): ONE handle over several contexts with internal sharding gives what the
+    single-GPU calls and the oracle give: rep50.db all-vs-all in every layout, sparse cells, rectangular, findClosest of the
+    GTO seeds (BASELINE configs[0]) with HashMap ranks, and the greedy rebuild of rep50.db (keeps all 1480)."""
+    seqs = [r[2] for r in rep50["reps"]]
+    n = len(seqs)
+    b = oracle.batch(seqs, K=8)
+    want = oracle.sim_matrix(b, ident_inf=True, threads=8)
+    m = kr.MultiContext(_gpu_list(), K=8, flags=kr.IDENT_IS_INFINITY | PATHS[path])
+    assert (m.sim_matrix(seqs, elem=kr.ELEM_I32, layout=kr.LAYOUT_FULL) == want).all()
+    assert (m.sim_matrix(seqs, elem=kr.ELEM_U16, layout=kr.LAYOUT_TRIANGLE) == tri_from_full(want)).all()
+    from kmers.reps_b200 import sharding
+    assert (m.sim_matrix(seqs, elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI) == sharding.blocktri_from_full(want)).all()
+    got = m.sim_matrix_sparse(seqs, min_sim=40, layout=kr.LAYOUT_TRIANGLE)
+    ii, jj = np.nonzero(np.triu(want, 1) >= 40)
+    assert {(int(r), int(c), int(v)) for r, c, v, _ in got} == {(int(i), int(j), int(want[i, j])) for i, j in zip(ii, jj)}
+    qs = [s for (_, _, s) in gto_seeds]
+    wr = oracle.sim_matrix(oracle.batch(qs, K=8), b, ident_inf=True, threads=8)
+    assert (m.sim_matrix(qs, b_seqs=seqs, elem=kr.ELEM_I32) == wr).all()
+    db = m.db()
+    db.append(seqs)
+    bs, bi = oracle.find_closest(b, oracle.batch(qs, K=8), ident_inf=True)
+    sim, first, _ = db.find_closest(qs)
+    assert (sim == bs).all() and (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all()
+    single = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | PATHS[path])
+    sdb = single.db(); sdb.append(seqs)
+    s1, f1, l1 = sdb.find_closest(single.encode(seqs[:300]))
+    s2, f2, l2 = db.find_closest(seqs[:300])
+    assert (s1 == s2).all() and (f1 == f2).all() and (l1 == l2).all()
+    single.close()
+    db.free()
+    db = m.db()
+    added = db.greedy_build(50, seqs, batch=400)
+    assert added.all() and db.size == n          # rep50.db is a threshold-50 database: rebuilding it keeps every representative
+    db.free()
+    assert m.stats()["kernel_launches"] > 0
+    m.close()
