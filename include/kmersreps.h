@@ -97,6 +97,17 @@ kr_status kr_seqset_keys(const kr_seqset *set, uint32_t i, uint64_t *keys, uint3
 kr_status kr_key_decode(const kr_ctx *ctx, uint64_t key, char *out /* K bytes, not NUL-terminated */);
 /* new set holding sequences idx[0..n) of `set` (used to batch sub-lists of ProteinKmers objects) */
 kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *idx, uint32_t n, kr_seqset **out);
+/* SequenceKmers.retainAll(other) / removeAll(other) (TargetProcessor.java:166,184) leave objects whose k-mer set is no
+ * longer "all substrings of the sequence".  The shim merges the two sorted key lists it read with kr_seqset_keys and
+ * makes the result a set again with this call, so everything downstream still runs on the GPU.  keys: strictly
+ * ascending packed k-mers per sequence (key_offsets[nseq + 1]); residues / res_offsets: the objects' unchanged
+ * sequences (what upstream's equal-sequence test compares), or NULL / NULL: then an object equals only itself.
+ * KR_INFINITY is reported for two objects whose sequences AND k-mer sets are equal (the device examines only pairs
+ * whose count equals both sizes); an object whose set really changed is no longer "identical" to a plain object of
+ * the same sequence -- the one corner where this differs from a string comparison, and no reference caller takes a
+ * similarity after retainAll / removeAll. */
+kr_status kr_seqset_from_keys(kr_ctx *ctx, const uint64_t *keys, const uint64_t *key_offsets, const uint8_t *residues,
+                              const uint64_t *res_offsets, uint32_t nseq, kr_seqset **out);
 
 /* ---- multi-GPU: exchanging encoded block lists ------------------------------------------------
  * The tile join reads only a set's block lists.  With several GPUs each one encodes a contiguous slice of the

@@ -20,6 +20,8 @@ public class KmerCollectionGroup {
 
     private final Map<String, List<ProteinKmers>> groups = new HashMap<>();
 
+    public KmerCollectionGroup() { }                               // ClassifyProcessor.java:71
+
     public void addSequence(Sequence seq, String group) {
         groups.computeIfAbsent(group, g -> new ArrayList<>()).add(new ProteinKmers(seq.getSequence()));
     }
@@ -28,6 +30,24 @@ public class KmerCollectionGroup {
 
     public double getDistance(Sequence seq, String group) {
         return getDistances(List.of(seq), List.of(group))[0];
+    }
+
+    /** result of getBest: the closest group and the distance to it */
+    public static final class Result {
+        private final String group; private final double distance;
+        Result(String group, double distance) { this.group = group; this.distance = distance; }
+        public String getGroup() { return group; }
+        public double getDistance() { return distance; }
+    }
+
+    /** the group closest to the sequence [recalled member; groups in map order, first strict minimum wins; null group at distance 1.0 when nothing is closer] */
+    public Result getBest(Sequence seq) {
+        String best = null; double bestDist = 1.0;
+        for (String g : groups.keySet()) {
+            double d = getDistance(seq, g);
+            if (d < bestDist) { bestDist = d; best = g; }
+        }
+        return new Result(best, bestDist);
     }
 
     public double[] getDistances(List<Sequence> seqs, List<String> groupOf) {

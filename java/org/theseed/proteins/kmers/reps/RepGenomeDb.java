@@ -14,6 +14,8 @@ import java.util.List;
 import java.util.SortedSet;
 import java.util.TreeSet;
 
+import org.theseed.genome.Feature;
+import org.theseed.genome.Genome;
 import org.theseed.sequence.FastaInputStream;
 import org.theseed.sequence.KmersRepsNative;
 import org.theseed.sequence.ProteinKmers;
@@ -41,7 +43,11 @@ public class RepGenomeDb implements Iterable<RepGenome> {
     private final int threshold;
     private final int kmerSize;
     private final String protName;
+    private final String[] protNames;
     // device mirror
+    // With -Dkmersreps.devices=0,1,... the mirror is a kr_multi_db (one replica per GPU, calls sharded inside the library);
+    // otherwise a kr_db on the single context.  `db` holds whichever handle is in use.
+    private final MemorySegment multi = KmersRepsNative.multi(ProteinKmers.kmerSize());
     private MemorySegment db = MemorySegment.NULL;
     private final List<RepGenome> onDevice = new ArrayList<>();   // device index -> rep
     private boolean rebuild = false, ranksDirty = true;
@@ -49,17 +55,25 @@ public class RepGenomeDb implements Iterable<RepGenome> {
     public class Representation {
         private final int similarity;
         private final RepGenome representative;
+        private final String genomeId;
         private final double distance;
 
-        public Representation() { this(null, 0, 1.0); }
+        public Representation() { this((RepGenome) null, 0, 1.0); }
         public Representation(RepGenome rep, ProteinKmers query) {   // NeighborProcessor.java:168
             this(rep, rep.similarity(query), rep.distance(query));
         }
-        Representation(RepGenome rep, int sim, double dist) { this.representative = rep; this.similarity = sim; this.distance = dist; }
+        /** a stored result: representative id, score and distance read back from a file (ProteinData.java:242) */
+        public Representation(String repId, int score, double distance) {
+            this.representative = repId == null ? null : genomeMap.get(repId);
+            this.genomeId = repId; this.similarity = score; this.distance = distance;
+        }
+        Representation(RepGenome rep, int sim, double dist) {
+            this.representative = rep; this.genomeId = rep == null ? null : rep.getGenomeId(); this.similarity = sim; this.distance = dist;
+        }
         public int getSimilarity() { return similarity; }
         public double getDistance() { return distance; }
         public RepGenome getRepresentative() { return representative; }
-        public String getGenomeId() { return representative == null ? null : representative.getGenomeId(); }
+        public String getGenomeId() { return genomeId; }
         public boolean isRepresented() { return similarity >= threshold; }
     }
 
@@ -67,6 +81,34 @@ public class RepGenomeDb implements Iterable<RepGenome> {
         this.threshold = threshold;
         this.kmerSize = ProteinKmers.kmerSize();
         this.protName = protNames.length > 0 ? protNames[0] : DEFAULT_PROTEIN;
+        this.protNames = protNames.length > 0 ? protNames.clone() : new String[] { DEFAULT_PROTEIN };
+    }
+
+    /**
+     * The genome's seed protein as a RepGenome, or null when it has none (GtoRepGenomeProcessor.java:213,
+     * NeighborProcessor.java:96, BuildRepDbProcessor.java:134): the LONGEST protein feature whose comment-free function
+     * is one of this database's protein names, with or without a trailing EC number -- the rule of
+     * GtoRepBuildProcessor.computeRepGenome (:176-192) and ScoreCouplingReporter.java:135,164-168.
+     */
+    public RepGenome getSeedProtein(Genome genome) {
+        String bestProtein = "", fid = null;
+        for (Feature feat : genome.getFeatures()) {
+            String prot = feat.getProteinTranslation();
+            if (prot == null || prot.isEmpty() || !isSeedFunction(feat.getFunction())) continue;
+            if (prot.length() > bestProtein.length()) { bestProtein = prot; fid = feat.getId(); }
+        }
+        return fid == null ? null : new RepGenome(fid, genome.getName(), bestProtein);
+    }
+
+    private boolean isSeedFunction(String function) {
+        if (function == null) return false;
+        int cut = function.length();
+        for (int i = 0; i < function.length(); i++) { char c = function.charAt(i); if (c == '#' || c == '!') { cut = i; break; } }
+        String fn = function.substring(0, cut).strip();
+        int ec = fn.lastIndexOf(" (EC ");
+        String bare = (ec > 0 && fn.endsWith(")")) ? fn.substring(0, ec) : fn;
+        for (String name : protNames) if (fn.equals(name) || bare.equals(name)) return true;
+        return false;
     }
 
     public int getThreshold() { return threshold; }
@@ -98,6 +140,7 @@ public class RepGenomeDb implements Iterable<RepGenome> {
 
     public Representation findClosest(ProteinKmers query) { return findClosest(List.of(query)).get(0); }
     public Representation findClosest(Sequence seq) { return findClosest(new ProteinKmers(seq.getSequence())); }
+    public Representation findClosest(RepGenome rep) { return findClosest((ProteinKmers) rep); }   // GtoRepGenomeProcessor.java:271
 
     /** The batched scan: one launch for the whole list (RepGenomeDbProcessor.java:235-252 rewritten). */
     public List<Representation> findClosest(Collection<? extends ProteinKmers> queries) {
@@ -107,6 +150,7 @@ public class RepGenomeDb implements Iterable<RepGenome> {
         List<ProteinKmers> q = new ArrayList<>(queries);
         List<String> prots = new ArrayList<>();
         for (ProteinKmers p : q) prots.add(p.getProtein());
+        if (multi != null) return findClosestMulti(q, prots);
         try (Arena a = Arena.ofConfined(); KmersRepsNative.SeqSet set = KmersRepsNative.encode(kmerSize, prots)) {
             MemorySegment sim = a.allocate(JAVA_INT, q.size()), first = a.allocate(JAVA_INT, q.size());
             MemorySegment ctx = KmersRepsNative.context(kmerSize);
@@ -116,6 +160,28 @@ public class RepGenomeDb implements Iterable<RepGenome> {
                 if (s == 0 || f == KmersRepsNative.NO_REP) { out.add(new Representation()); continue; }
                 RepGenome rep = onDevice.get(f);
                 out.add(new Representation(rep, s, KmersRepsNative.distance(s, set.sizeOf(i), rep.size())));
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+        return out;
+    }
+
+    /** findClosest over every GPU of the kr_multi handle: the library splits the queries; sizes come from the objects */
+    private List<Representation> findClosestMulti(List<ProteinKmers> q, List<String> prots) {
+        List<Representation> out = new ArrayList<>(q.size());
+        ProteinKmers.encodeBatch(q);                                   // sizes for the distances (one launch, first context)
+        try (Arena a = Arena.ofConfined()) {
+            KmersRepsNative.Flat f = KmersRepsNative.flat(a, prots);
+            MemorySegment sim = a.allocate(JAVA_INT, q.size()), first = a.allocate(JAVA_INT, q.size());
+            KmersRepsNative.checkMulti(multi, (int) KmersRepsNative.kr_multi_db_find_closest.invokeExact(multi, db, f.residues, f.offsets, q.size(), sim, first, MemorySegment.NULL));
+            for (int i = 0; i < q.size(); i++) {
+                int s = sim.getAtIndex(JAVA_INT, i), fi = first.getAtIndex(JAVA_INT, i);
+                if (s == 0 || fi == KmersRepsNative.NO_REP) { out.add(new Representation()); continue; }
+                RepGenome rep = onDevice.get(fi);
+                out.add(new Representation(rep, s, KmersRepsNative.distance(s, q.get(i).size(), rep.size())));
             }
         } catch (RuntimeException e) {
             throw e;
@@ -178,10 +244,17 @@ public class RepGenomeDb implements Iterable<RepGenome> {
         sync();
         List<String> prots = new ArrayList<>();
         for (RepGenome c : cands) prots.add(c.getProtein());
-        try (Arena a = Arena.ofConfined(); KmersRepsNative.SeqSet set = KmersRepsNative.encode(kmerSize, prots)) {
+        try (Arena a = Arena.ofConfined()) {
             MemorySegment flags = a.allocate(JAVA_BYTE, cands.size());
-            MemorySegment ctx = KmersRepsNative.context(kmerSize);
-            KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_greedy_build.invokeExact(ctx, db, set.handle(), threshold, 0, flags));
+            if (multi != null) {
+                KmersRepsNative.Flat f = KmersRepsNative.flat(a, prots);
+                KmersRepsNative.checkMulti(multi, (int) KmersRepsNative.kr_multi_greedy_build.invokeExact(multi, db, f.residues, f.offsets, cands.size(), threshold, 0, flags));
+            } else {
+                try (KmersRepsNative.SeqSet set = KmersRepsNative.encode(kmerSize, prots)) {
+                    MemorySegment ctx = KmersRepsNative.context(kmerSize);
+                    KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_greedy_build.invokeExact(ctx, db, set.handle(), threshold, 0, flags));
+                }
+            }
             for (int i = 0; i < added.length; i++)
                 if (flags.get(JAVA_BYTE, i) != 0) {
                     added[i] = true;
@@ -226,12 +299,13 @@ public class RepGenomeDb implements Iterable<RepGenome> {
         MemorySegment ctx = KmersRepsNative.context(kmerSize);
         try (Arena a = Arena.ofConfined()) {
             if (rebuild && !db.equals(MemorySegment.NULL)) {
-                KmersRepsNative.kr_db_free.invokeExact(db);
+                if (multi != null) KmersRepsNative.kr_multi_db_free.invokeExact(db); else KmersRepsNative.kr_db_free.invokeExact(db);
                 db = MemorySegment.NULL; onDevice.clear();
             }
             if (db.equals(MemorySegment.NULL)) {
                 MemorySegment out = a.allocate(ADDRESS);
-                KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_create.invokeExact(ctx, out));
+                if (multi != null) KmersRepsNative.checkMulti(multi, (int) KmersRepsNative.kr_multi_db_create.invokeExact(multi, out));
+                else KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_create.invokeExact(ctx, out));
                 db = out.get(ADDRESS, 0);
             }
             rebuild = false;
@@ -251,7 +325,8 @@ public class RepGenomeDb implements Iterable<RepGenome> {
                     pos += b.length;
                 }
                 off.setAtIndex(JAVA_LONG, fresh.size(), pos);
-                KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_append.invokeExact(ctx, db, res, off, fresh.size()));
+                if (multi != null) KmersRepsNative.checkMulti(multi, (int) KmersRepsNative.kr_multi_db_append.invokeExact(multi, db, res, off, fresh.size()));
+                else KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_append.invokeExact(ctx, db, res, off, fresh.size()));
                 onDevice.addAll(fresh);
                 ranksDirty = true;
             }
@@ -261,7 +336,8 @@ public class RepGenomeDb implements Iterable<RepGenome> {
                 for (RepGenome r : genomeMap.values()) rankOf.put(r, k++);   // the JVM's own HashMap order
                 MemorySegment rank = a.allocate(JAVA_INT, onDevice.size());
                 for (int d = 0; d < onDevice.size(); d++) rank.setAtIndex(JAVA_INT, d, rankOf.get(onDevice.get(d)));
-                KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_set_ranks.invokeExact(ctx, db, rank, onDevice.size()));
+                if (multi != null) KmersRepsNative.checkMulti(multi, (int) KmersRepsNative.kr_multi_db_set_ranks.invokeExact(multi, db, rank, onDevice.size()));
+                else KmersRepsNative.check(ctx, (int) KmersRepsNative.kr_db_set_ranks.invokeExact(ctx, db, rank, onDevice.size()));
                 ranksDirty = false;
             }
         } catch (RuntimeException e) {

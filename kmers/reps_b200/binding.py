@@ -20,7 +20,7 @@ TILE = 256
 # every symbol include/kmersreps.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_build_info", "kr_synchronize", "kr_encode", "kr_encode_device",
-    "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_blocklist_capacity", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather",
+    "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_blocklist_capacity", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather", "kr_seqset_from_keys",
     "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
     "kr_sim_matrix_sparse", "kr_sim_matrix_sparse_device",
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
@@ -107,6 +107,7 @@ def load_library():
     lib.kr_seqset_keys.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
     lib.kr_key_decode.argtypes = [vp, u64, C.c_char_p]
     lib.kr_seqset_gather.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
+    lib.kr_seqset_from_keys.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(vp)]
     lib.kr_sim_pairs.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
     lib.kr_distance.argtypes = [i32, u32, u32]
     lib.kr_distance.restype = C.c_double
@@ -243,6 +244,22 @@ class Context:
         off = np.ascontiguousarray(off, dtype=np.uint64)
         h = C.c_void_p()
         self._ck(self.lib.kr_encode_device(self.h, d_res_ptr, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return SeqSet(self, h)
+
+    def from_keys(self, key_lists, seqs=None) -> "SeqSet":
+        """a set from explicit sorted key lists (the result of retainAll / removeAll); seqs = the objects' sequences"""
+        koff = np.zeros(len(key_lists) + 1, dtype=np.uint64)
+        if key_lists:
+            koff[1:] = np.cumsum([len(k) for k in key_lists], dtype=np.uint64)
+        keys = np.concatenate([np.asarray(k, dtype=np.uint64) for k in key_lists]) if key_lists and int(koff[-1]) else np.zeros(1, np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        res = off = None
+        if seqs is not None:
+            res, off = flat(seqs)
+            if not res.size:
+                res = np.zeros(1, np.uint8)
+        h = C.c_void_p()
+        self._ck(self.lib.kr_seqset_from_keys(self.h, keys.ctypes.data, koff.ctypes.data, _ptr(res), _ptr(off), len(key_lists), C.byref(h)))
         return SeqSet(self, h)
 
     def blocklist_capacity(self, off) -> int:

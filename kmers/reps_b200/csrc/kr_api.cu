@@ -56,6 +56,7 @@ struct kr_ctx {
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool err_pending = false;   // an encode launched by a _device call has not had its error flag read yet
+    u64 keyset_nonce = 1;       // kr_seqset_from_keys without sequences: every such object gets a hash of its own
     // cached tile list of the last matrix launch (the same stripes are usually computed again and again)
     uint2 *d_tasks_cache = nullptr; u32 tasks_cache_n = 0; u32 tasks_key[5] = {0, 0, 0, 0, 0xFFFFFFFFu};
 };
@@ -919,6 +920,73 @@ kr_status kr_seqset_gather(kr_ctx *ctx, const kr_seqset *set, const uint32_t *id
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->dev));
     return gather_impl(ctx, set, idx, n, out);
+}
+
+// SequenceKmers.retainAll / removeAll (TargetProcessor.java:166,184) leave an object whose k-mer set is no longer the set of
+// its sequence's substrings: the shim computes the new key list on the host (a merge of two sorted lists it fetched with
+// kr_seqset_keys) and hands it back here, so that size / similarity / distance / findClosest of such objects still run on
+// the GPU like any other set.  The sequences themselves (optional) keep the equal-sequence rule working as upstream, which
+// compares the unchanged `sequence` strings.
+kr_status kr_seqset_from_keys(kr_ctx *ctx, const uint64_t *keys, const uint64_t *key_offsets, const uint8_t *residues, const uint64_t *res_offsets,
+                              uint32_t nseq, kr_seqset **out) {
+    if (!ctx || !out || (!key_offsets && nseq)) return fail(ctx, KR_ERR_ARG, "kr_seqset_from_keys: null argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->dev));
+    const u64 kc = nseq ? key_offsets[nseq] - key_offsets[0] : 0;
+    if (kc && !keys) return fail(ctx, KR_ERR_ARG, "kr_seqset_from_keys: null keys");
+    const u64 limit = 5 * ctx->K >= 64 ? ~0ull : (1ull << (5 * ctx->K));
+    std::vector<u64> koff(nseq + 1), off(nseq + 1, 0);
+    std::vector<u32> sizes(nseq);
+    for (u32 i = 0; i < nseq; ++i) {
+        if (key_offsets[i + 1] < key_offsets[i]) return fail(ctx, KR_ERR_ARG, "kr_seqset_from_keys: key offsets not monotone at %u", i);
+        const u64 n = key_offsets[i + 1] - key_offsets[i];
+        if (n > 65535u) return fail(ctx, KR_ERR_ARG, "kr_seqset_from_keys: sequence %u has %llu keys; at most 65535 per sequence are supported", i, (unsigned long long)n);
+        const u64 *kp = keys + key_offsets[i];
+        for (u64 t = 0; t < n; ++t)
+            if ((limit != ~0ull && kp[t] >= limit) || (t && kp[t] <= kp[t - 1]))
+                return fail(ctx, KR_ERR_ARG, "kr_seqset_from_keys: keys of sequence %u are not strictly ascending %d-mers (position %llu)", i, ctx->K, (unsigned long long)t);
+        koff[i] = key_offsets[i] - key_offsets[0]; sizes[i] = (u32)n;
+    }
+    koff[nseq] = kc;
+    u64 total = 0;
+    if (res_offsets) {
+        for (u32 i = 0; i < nseq; ++i) {
+            if (res_offsets[i + 1] < res_offsets[i]) return fail(ctx, KR_ERR_ARG, "kr_seqset_from_keys: residue offsets not monotone at %u", i);
+            off[i] = res_offsets[i] - res_offsets[0];
+        }
+        total = nseq ? res_offsets[nseq] - res_offsets[0] : 0;
+        off[nseq] = total;
+        if (total && !residues) return fail(ctx, KR_ERR_ARG, "kr_seqset_from_keys: null residues");
+        for (u64 t = 0; t < total; ++t) {
+            const u8 c = residues[res_offsets[0] + t];
+            if (!((c >= 'A' && c <= 'Z') || c == '*' || c == '-'))
+                return fail(ctx, KR_ERR_ALPHABET, "kr_seqset_from_keys: residue 0x%02x is outside 'A'..'Z', '*', '-'", c);
+        }
+    }
+    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
+    s->ctx = ctx; s->n = nseq; s->key_cap = kc; s->h_sizes = sizes;
+    s->res = std::make_shared<DevMem>();
+    s->res->stream = ctx->stream;
+    CU(pool_alloc(ctx, &s->res->p, total + 16));
+    if (total) { CU(cudaMemcpyAsync(s->res->p, residues + res_offsets[0], total, cudaMemcpyHostToDevice, ctx->stream)); ctx->st.h2d_bytes += total; }
+    CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_koff, nseq + 1));
+    CU(dalloc(ctx, &s->d_keys, kc + 16)); CU(dalloc(ctx, &s->d_meta, nseq));
+    CU(cudaMemcpyAsync(s->d_off, off.data(), (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s->d_koff, koff.data(), (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (kc) CU(cudaMemcpyAsync(s->d_keys, keys + key_offsets[0], (size_t)kc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.h2d_bytes += kc * 8 + 2ull * (nseq + 1) * 8;
+    if (nseq) {
+        StageTimer t(ctx, ST_OTHER);
+        KR_LAUNCH(KR_T(k_meta_from_keys), (nseq + 7) / 8, 256, 0, ctx->stream, s->d_koff, res_offsets ? (const u8 *)s->res->p : (const u8 *)nullptr, s->d_off, nseq,
+                  ctx->keyset_nonce, s->d_meta);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        ctx->keyset_nonce += nseq;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));     // the host vectors above were staged by then
+    *out = s.release();
+    return KR_OK;
 }
 
 uint64_t kr_blocklist_capacity(const kr_ctx *ctx, const uint64_t *offsets, uint32_t nseq) {

@@ -839,6 +839,30 @@ __global__ void __launch_bounds__(256) k_sim_pairs(const u64 *keysA, const u64 *
     }
 }
 
+// records of a set built from explicit key lists (kr_seqset_from_keys): one warp per sequence.  With the sequences at
+// hand the record is K1's (length, the same 64-bit hash, residue pointer), so such an object is "equal" to whatever its
+// sequence equals; without them every object gets a hash of its own and equals only itself.
+__global__ void __launch_bounds__(256) k_meta_from_keys(const u64 *koff, const u8 *res, const u64 *off, u32 nseq, u64 nonce, SeqMeta *meta) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nseq) return;                                    // whole warps leave together
+    SeqMeta m; m.size = (u32)(koff[s + 1] - koff[s]); m.len = 0; m.res = nullptr; m.hash = 0;
+    if (res) {
+        const u8 *r = res + off[s];
+        const u32 L = (u32)(off[s + 1] - off[s]);
+        u64 h = 0;
+        for (u32 i = lane; i < L; i += 32) h += mix64((((u64)i << 8) | r[i]) + 0x9E3779B97F4A7C15ULL);
+        for (int o = 16; o > 0; o >>= 1) {
+            const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)h, o), hi = __shfl_xor_sync(0xffffffffu, (u32)(h >> 32), o);
+            h += ((u64)hi << 32) | lo;
+        }
+        m.len = L; m.hash = h; m.res = r;
+    } else {
+        m.hash = mix64(nonce + s) | 1ull;
+    }
+    if (lane == 0) meta[s] = m;
+}
+
 __global__ void k_fill_u32_iota(u32 *p, u32 n, u32 base) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = base + i;

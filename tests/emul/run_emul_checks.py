@@ -349,6 +349,56 @@ def case_api_misc():
     c.close()
 
 
+def case_set_ops():
+    """kr_seqset_from_keys: the key lists left by SequenceKmers.retainAll / removeAll become a set again; sizes, keys,
+    similarities (pairs, matrix through both paths, findClosest) equal plain Python set arithmetic; the equal-sequence rule
+    follows the unchanged sequences when they are given"""
+    seqs = family(41, 60, 3, 40, 90) + ["MKV", ""]
+    seqs[7] = seqs[3]
+    K = 8
+    sets = [ko.py_kmers(s, K) for s in seqs]
+    for path in PATHS:
+        c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY | path)
+        S = c.encode(seqs)
+        keys = [S.keys(i) for i in range(len(seqs))]
+        other = set(int(k) for k in keys[1])
+        kept = [np.array([k for k in ks if int(k) in other], dtype=np.uint64) for ks in keys]        # retainAll(seqs[1])
+        gone = [np.array([k for k in ks if int(k) not in other], dtype=np.uint64) for ks in keys]     # removeAll(seqs[1])
+        for lists, op in ((kept, set.__and__), (gone, set.__sub__)):
+            want_sets = [op(a, sets[1]) for a in sets]
+            T = c.from_keys(lists, seqs)
+            assert list(T.sizes()) == [len(w) for w in want_sets]
+            for i in (0, 1, 3, 5):
+                assert sorted(T.kmers(i)) == sorted(want_sets[i])
+            # INFINITY needs equal sequences AND equal k-mer sets (the device only looks at pairs whose count equals both sizes):
+            # an object whose set was really changed is no longer "identical" to the plain object of the same sequence
+            def expect(rows, cols):
+                raw = np.array([[len(a & b) for b in cols] for a in rows], dtype=np.int32)
+                inf = np.array([[seqs[i] == seqs[j] and rows[i] == cols[j] for j in range(len(cols))] for i in range(len(rows))])
+                return np.where(inf, kr.INFINITY, raw)
+            assert (c.sim_matrix(T, elem=kr.ELEM_I32) == expect(want_sets, want_sets)).all(), path
+            mixed = expect(want_sets, sets)                                                             # mutated rows against plain columns
+            assert (c.sim_matrix(T, S, elem=kr.ELEM_I32) == mixed).all(), path
+            sim, ident = c.sim_pairs(T, [0, 3, 2], S, [2, 7, 1])
+            assert list(sim) == [int(mixed[0, 2]), int(mixed[3, 7]), int(mixed[2, 1])]
+            db = c.db(); db.append_set(T, np.arange(len(seqs), dtype=np.uint32))
+            s2, f2, _ = db.find_closest(S)
+            col = mixed.T                                                                               # rows = plain queries, columns = mutated reps
+            assert (s2 == col.max(axis=1)).all() and all(col[q, f2[q]] == s2[q] for q in range(len(seqs)) if s2[q] > 0), path
+        U = c.from_keys(kept)                                                                           # without sequences: equal only to itself
+        m = c.sim_matrix(U, elem=kr.ELEM_I32)
+        want = np.array([[len(a & b) for b in [x & sets[1] for x in sets]] for a in [x & sets[1] for x in sets]], dtype=np.int32)
+        np.fill_diagonal(want, kr.INFINITY)
+        assert (m == want).all(), path
+        for bad in ([np.array([5, 5], np.uint64)], [np.array([9, 3], np.uint64)], [np.array([1 << 40], np.uint64)]):
+            try:
+                c.from_keys(bad)
+                raise AssertionError("unsorted / out-of-range keys accepted")
+            except kr.KrError as e:
+                assert e.code == -1
+        c.close()
+
+
 def case_multi():
     """several contexts behind one kr_multi handle (KR_EMUL_DEVICES "GPUs", one worker thread each): matrices in every
     layout, sparse cells with too little room per slice, rectangular, findClosest with ranks, any_ge, the greedy build with

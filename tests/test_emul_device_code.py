@@ -71,7 +71,7 @@ def test_index_overflow_passes_on_the_emulator(emul_lib):
 
 
 @pytest.mark.parametrize("case", ["matrix_layouts", "k10_rectangular_pairs", "find_closest_and_build", "subchunks", "sharded_import", "api_misc",
-                                  "sparse_matrix", "index_crowded", "encode_warp"])
+                                  "sparse_matrix", "index_crowded", "encode_warp", "set_ops"])
 def test_device_code_on_the_emulator(emul_lib, case):
     env = dict(os.environ, KR_LIB_PATH=emul_lib, KR_EMUL_SMS="2")
     p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,

@@ -604,3 +604,32 @@ def test_multi_handle_equals_single_gpu_and_oracle(path, rep50, gto_seeds, oracl
     db.free()
     assert m.stats()["kernel_launches"] > 0
     m.close()
+
+
+def test_sets_from_key_lists(ctx, rep50):
+    """kr_seqset_from_keys (SequenceKmers.retainAll / removeAll, TargetProcessor.java:166,184): the merged key lists become a
+    set again; sizes, decoded k-mers, matrix and findClosest equal Python set arithmetic on substrings"""
+    seqs = [s for (_, _, s) in rep50["reps"]][:400]
+    sets = [ko.py_kmers(s, 8) for s in seqs]
+    S = ctx.encode(seqs)
+    keys = [S.keys(i) for i in range(len(seqs))]
+    pool = set(int(k) for i in (0, 1, 2, 3, 4, 5) for k in keys[i])
+    pool_str = set().union(*[sets[i] for i in range(6)])
+    kept = [np.array([k for k in ks if int(k) in pool], dtype=np.uint64) for ks in keys]
+    gone = [np.array([k for k in ks if int(k) not in pool], dtype=np.uint64) for ks in keys]
+    for lists, want_sets in ((kept, [a & pool_str for a in sets]), (gone, [a - pool_str for a in sets])):
+        T = ctx.from_keys(lists, seqs)
+        assert list(T.sizes()) == [len(w) for w in want_sets]
+        assert sorted(T.kmers(7)) == sorted(want_sets[7])
+        raw = np.array([[len(a & b) for b in sets] for a in want_sets], dtype=np.int32)
+        inf = np.array([[seqs[i] == seqs[j] and want_sets[i] == sets[j] for j in range(len(seqs))] for i in range(len(seqs))])
+        assert (ctx.sim_matrix(T, S, elem=kr.ELEM_I32) == np.where(inf, kr.INFINITY, raw)).all()
+        db = ctx.db()
+        db.append_set(T, np.arange(len(seqs), dtype=np.uint32))
+        sim, first, _ = db.find_closest(S)
+        col = np.where(inf, kr.INFINITY, raw).T
+        assert (sim == col.max(axis=1)).all()
+        assert all(col[q, first[q]] == sim[q] and (col[q, :first[q]] < sim[q]).all() for q in range(len(seqs)) if sim[q] > 0)
+        db.free()
+    with pytest.raises(kr.KrError):
+        ctx.from_keys([np.array([7, 7], np.uint64)])
