@@ -29,32 +29,40 @@ __device__ __forceinline__ u64 shfl_up_u64(u64 v, unsigned d) {
     return ((u64)hi << 32) | lo;
 }
 
-// ascending bitonic sort of 32*R elements, element e = lane*R + t held in reg[t] of `lane`
+// ascending bitonic sort of 32*R elements, element e = lane*R + t held in reg[t] of `lane`.
+// Only the loops over the registers are unrolled (register arrays need static indices); the loops over the network's
+// stages run at run time.  Fully unrolled, the four networks of this kernel were 24,600 SASS instructions (394 KB of
+// straight-line code that every warp streams through once per sequence); rolled up they are a few hundred each and stay
+// in the instruction cache.  The compare-exchanges and their order are the same.
 template <int R>
 __device__ __forceinline__ void warp_bitonic(u64 (&reg)[R], u32 lane) {
     constexpr int P = 32 * R;
-#pragma unroll
+    const u32 e0 = lane * R;
+#pragma unroll 1
     for (int k = 2; k <= P; k <<= 1) {
+        const bool last = k == P;
+        // strides >= R: the partner element sits in lane ^ (j / R), same register
+#pragma unroll 1
+        for (int j = k >> 1; j >= R; j >>= 1) {
+            const int lm = j / R;
+            const bool low = (lane & (u32)lm) == 0;                     // this lane holds the lower index of the pair
+            const bool up = (e0 & (u32)k) == 0 || last;                 // k >= 2R here: bit k of e = lane*R + t is a lane bit
+            const bool take_min = (low == up);
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= R) {
-                const int lm = j / R;                                   // partner lane = lane ^ lm, same register
+            for (int t = 0; t < R; ++t) {
+                const u64 other = shfl_xor_u64(reg[t], lm);
+                const u64 mn = reg[t] < other ? reg[t] : other, mx = reg[t] < other ? other : reg[t];
+                reg[t] = take_min ? mn : mx;
+            }
+        }
+        // strides < R: both elements are registers of this lane
 #pragma unroll
-                for (int t = 0; t < R; ++t) {
-                    const u64 other = shfl_xor_u64(reg[t], lm);
-                    const u32 e = lane * R + t;
-                    const bool up = (e & (u32)k) == 0 || k == P;        // direction of this element's k-block
-                    const bool low = (lane & (u32)lm) == 0;             // this lane holds the lower index of the pair
-                    const bool take_min = (low == up);
-                    const u64 mn = reg[t] < other ? reg[t] : other, mx = reg[t] < other ? other : reg[t];
-                    reg[t] = take_min ? mn : mx;
-                }
-            } else {
+        for (int j = R >> 1; j > 0; j >>= 1) {
+            if (j <= (k >> 1)) {                                        // (uniform run-time test: the stage exists once k >= 2j)
 #pragma unroll
                 for (int t = 0; t < R; ++t) {
                     if ((t & j) == 0) {
-                        const u32 e = lane * R + t;
-                        const bool up = (e & (u32)k) == 0 || k == P;
+                        const bool up = ((e0 + (u32)t) & (u32)k) == 0 || last;
                         const u64 a = reg[t], b = reg[t | j];
                         const bool sw = up ? (b < a) : (a < b);
                         reg[t] = sw ? b : a; reg[t | j] = sw ? a : b;
