@@ -73,6 +73,8 @@ typedef int32_t kr_status;
  * (RepGenomeDbProcessor.java:77-80,121; RepMatrixProcessor.java:51-54). */
 kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out);
 void kr_destroy(kr_ctx *ctx);
+/* message of the context's last error (ctx == NULL: of this thread's last failed kr_create), copied into a buffer of the
+ * calling thread: valid until this thread calls kr_last_error again, whatever other threads do with the context */
 const char *kr_last_error(const kr_ctx *ctx);
 int kr_kmer_size(const kr_ctx *ctx);
 /* build tag of the library ("default": there is one build) */

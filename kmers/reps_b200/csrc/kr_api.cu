@@ -47,7 +47,8 @@ struct kr_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaMemPool_t pool = nullptr;   // this context's own memory pool: the device's default pool (shared with the JVM / torch) is never touched
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    std::mutex mu;
+    std::mutex mu;              // serialises the calls on this context
+    mutable std::mutex err_mu;  // guards `err` alone (fail() also runs before `mu` is taken)
     std::string err;
     u8 *d_lut = nullptr;
     ErrInfo *d_err = nullptr;
@@ -105,7 +106,7 @@ struct kr_db {
 static kr_status fail(kr_ctx *ctx, kr_status code, const char *fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-    if (ctx) ctx->err = buf; else g_create_error = buf;
+    if (ctx) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = buf; } else g_create_error = buf;
     return code;
 }
 // key slots a sequence of L residues can need (one per k-mer position)
@@ -175,7 +176,16 @@ static void make_chunk_lut(u8 *lut) {
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-const char *kr_last_error(const kr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+// The message is copied under its own lock into a buffer of the CALLING thread: argument checks fail before the context's
+// call lock is taken, and another thread may be failing on the same context at the same moment.  The pointer stays valid
+// until this thread asks again.
+const char *kr_last_error(const kr_ctx *ctx) {
+    static thread_local std::string tl_last_error;
+    if (!ctx) return g_create_error.c_str();
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    tl_last_error = ctx->err;
+    return tl_last_error.c_str();
+}
 const char *kr_build_info(void) { return "default"; }
 int kr_kmer_size(const kr_ctx *ctx) { return ctx ? ctx->K : 0; }
 

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
             const u64 body = (bytes - head) & ~15ull;
             for (u64 k = lane * 2; k < head; k += 64) *reinterpret_cast<u16 *>(bp + k) = 0;
             uint4 *vp = reinterpret_cast<uint4 *>(bp + head);
-            for (u64 k = lane; k < body / 16; k += 32) vp[k] = make_uint4(0u, 0u, 0u, 0u);
+            for (u64 k = lane; k < body / 16; k += 32) __stcs(vp + k, make_uint4(0u, 0u, 0u, 0u));   // streaming: never re-read here, L2 is for the index
             for (u64 k = head + body + lane * 2; k < bytes; k += 64) *reinterpret_cast<u16 *>(bp + k) = 0;
             __syncwarp();      // orders the zeros before the cells this warp writes below
         }

@@ -224,6 +224,7 @@ inline void __trap() { throw emu::Trap(); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline void __stcs(T *p, T v) { *p = v; }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> inline T max(T a, T b) { return a > b ? a : b; }
 inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }

@@ -11,6 +11,10 @@ from kmers.reps_b200 import synth
 from oracle import kr_oracle as ko
 
 pytestmark = pytest.mark.gpu
+# "device" tensors: CUDA -- or host memory when KR_LIB_PATH names the CPU emulator build of the library (tools/emul_gpu_suite.sh
+# runs this file against it so that the tests' own expectations are exercised before they meet a GPU)
+EMUL = "libkmersreps_emul" in kr.lib_path()
+DEV = "cpu" if EMUL else "cuda"
 
 
 # every test that takes `ctx` / `ctx_raw` runs three times: the library's own path choice, the tile join pinned, and the
@@ -247,7 +251,7 @@ def test_synthetic_families_vs_oracle(ctx, oracle):
     assert (bt == np.concatenate(parts)).all()
     # encode from a device-resident residue buffer gives the same set
     import torch
-    d = torch.from_numpy(res).cuda()
+    d = torch.from_numpy(res).to(DEV)
     s2 = ctx.encode_device(d.data_ptr(), off)
     assert (s2.sizes() == s.sizes()).all()
     sim, _ = ctx.sim_pairs(s, np.arange(2999), s2, np.arange(1, 3000))
@@ -376,7 +380,7 @@ def test_greedy_build_properties_at_scale():
     assert db.size == R and 5000 < R < n
     reps = cands.gather(rep_idx)
     ne = kr.matrix_elems(R, R, kr.LAYOUT_FULL)
-    out = torch.empty(ne, dtype=torch.int16, device="cuda")
+    out = torch.empty(ne, dtype=torch.int16, device=DEV)
     c.sim_matrix_device(reps, None, out.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL)
     c.synchronize()
     m = out.view(R, R)
@@ -388,7 +392,7 @@ def test_greedy_build_properties_at_scale():
     rng = np.random.default_rng(2)
     ia, ib = rng.integers(0, R, 20000), rng.integers(0, R, 20000)
     sim, _ = c.sim_pairs(reps, ia, reps, ib)
-    got = m[torch.from_numpy(ia).cuda(), torch.from_numpy(ib).cuda()].cpu().numpy().astype(np.int32)
+    got = m[torch.from_numpy(ia).to(DEV), torch.from_numpy(ib).to(DEV)].cpu().numpy().astype(np.int32)
     assert (sim == got).all()                                                      # (d) two kernels agree
     del m, offdiag, out
     rej = np.nonzero(added == 0)[0].astype(np.uint32)
@@ -404,13 +408,13 @@ def test_allvsall_full_size_index_equals_join():
     import torch
     n = 100000
     res, off, _ = synth.generate(0x5EED0003, n, n // 50)
-    d_res = torch.from_numpy(res).cuda()
+    d_res = torch.from_numpy(res).to(DEV)
     ne = kr.matrix_elems(n, n, kr.LAYOUT_BLOCKTRI)
     outs = {}
     for name, flag in (("join", kr.FORCE_JOIN), ("index", kr.FORCE_INDEX), ("auto", 0)):
         c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | flag)
         s = c.encode_device(d_res.data_ptr(), off)
-        out = torch.full((ne + 8,), -1, dtype=torch.int16, device="cuda")
+        out = torch.full((ne + 8,), -1, dtype=torch.int16, device=DEV)
         c.sim_matrix_device(s, None, out.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI)
         c.synchronize()
         st = c.stats()
@@ -422,7 +426,7 @@ def test_allvsall_full_size_index_equals_join():
             pos = 0
             for k in range(4):
                 cnt = kr.matrix_elems(n, n, kr.LAYOUT_BLOCKTRI, int(rb[k]), int(rb[k + 1]))
-                part = torch.full((cnt + 8,), -1, dtype=torch.int16, device="cuda")
+                part = torch.full((cnt + 8,), -1, dtype=torch.int16, device=DEV)
                 c.sim_matrix_device(s, None, part.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=int(rb[k]), row_end=int(rb[k + 1]))
                 c.synchronize()
                 assert torch.equal(part[:cnt], out[pos:pos + cnt]), k
@@ -430,7 +434,7 @@ def test_allvsall_full_size_index_equals_join():
                 del part
             assert pos == ne
             cap = 1 << 23
-            cells = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+            cells = torch.zeros((cap, 4), dtype=torch.int32, device=DEV)
             cnt = c.sim_matrix_sparse_device(s, None, cells.data_ptr(), cap, min_sim=1, layout=kr.LAYOUT_TRIANGLE)
             c.synchronize()
             outs["cells"] = cells[:cnt].cpu().numpy()
@@ -445,14 +449,14 @@ def test_allvsall_full_size_index_equals_join():
     I = i // 256
     idx = 256 * (I * n - 128 * I * (I - 1)) + (i - 256 * I) * (n - 256 * I) + (j - 256 * I)
     dense = outs["join"]
-    assert (dense[torch.from_numpy(idx).cuda()].cpu().numpy().astype(np.int32) == v).all()
+    assert (dense[torch.from_numpy(idx).to(DEV)].cpu().numpy().astype(np.int32) == v).all()
     diag_i = np.arange(n, dtype=np.int64); DI = diag_i // 256
     didx = 256 * (DI * n - 128 * DI * (DI - 1)) + (diag_i - 256 * DI) * (n - 256 * DI) + (diag_i - 256 * DI)
     nz_total = int((dense != 0).sum().item())
     # non-zero cells of the block triangle = the diagonal (INFINITY) + the strict triangle's non-zero cells + the
     # below-diagonal cells inside the 256 x 256 diagonal blocks (mirror images of cells with j > i in the same block)
     same_block = int(((i // 256) == (j // 256)).sum())
-    assert bool((dense[torch.from_numpy(didx).cuda()] == kr.INFINITY).all())
+    assert bool((dense[torch.from_numpy(didx).to(DEV)] == kr.INFINITY).all())
     assert nz_total == n + len(cells) + same_block
 
 
@@ -510,7 +514,7 @@ def test_shard_import_single_process(ctx, oracle):
     res, off, _ = synth.generate(0x5EED0011, 3000 + 37, 60)
     seqs = synth.to_strings(res, off)
     want = oracle.sim_matrix(oracle.batch(seqs, K=8), ident_inf=True, threads=8)
-    d_res = torch.from_numpy(res).cuda()
+    d_res = torch.from_numpy(res).to(DEV)
     plain = ctx.sim_matrix(ctx.encode(res=res, off=off), elem=kr.ELEM_U16, layout=kr.LAYOUT_FULL)
     assert (plain == want).all()
     for nshards in (2, 4, 8):
@@ -529,7 +533,7 @@ def test_shard_import_rejects_bad_layout(ctx):
     """a shard whose arrays break the 16-byte rules of the TMA copies is refused with KR_ERR_ARG; nothing is launched on it"""
     import torch
     res, off, _ = synth.generate(0x5EED0012, 600, 12)
-    d_res = torch.from_numpy(res).cuda()
+    d_res = torch.from_numpy(res).to(DEV)
     parts, shards = _export_shards(ctx, d_res, off, 2)
     bad = [_clone(s) for s in shards]
     bad[1].hi = shards[1].hi + 4                                  # misaligned array start
@@ -541,7 +545,8 @@ def test_shard_import_rejects_bad_layout(ctx):
     nb = shards[1].nblk + 1
     base = sharding._view(shards[1].blk_base, nb * 8, d_res.device).view(torch.int64).clone()
     base += 4
-    torch.cuda.synchronize()
+    if not EMUL:
+        torch.cuda.synchronize()
     bad = [_clone(s) for s in shards]
     bad[1].blk_base = base.data_ptr()
     with pytest.raises(kr.KrError) as e:
@@ -556,14 +561,11 @@ def test_shard_import_rejects_bad_layout(ctx):
 
 def _gpu_list():
     """every GPU of the box -- or, on a one-GPU box, that GPU listed twice (two contexts, two worker threads on it)"""
-    import ctypes as C
-    n = C.c_int(0)
-    try:
-        C.CDLL("libcudart.so").cudaGetDeviceCount(C.byref(n))
-    except OSError:
-        import torch
-        n.value = torch.cuda.device_count()
-    return list(range(n.value)) if n.value > 1 else [0, 0]
+    if EMUL:
+        return [0, 0]
+    import torch
+    n = torch.cuda.device_count()
+    return list(range(n)) if n > 1 else [0, 0]
 
 
 @pytest.mark.parametrize("path", list(PATHS))
