@@ -65,8 +65,11 @@ typedef int32_t kr_status;
 #define KR_FORCE_JOIN 4u
 #define KR_FORCE_INDEX 8u
 
-#define KR_MIN_K 3
-#define KR_MAX_K 11 /* 5 bits per residue + 8 bits of block-local sequence id in one 64-bit key */
+/* K = 1..11.  The reference's validators accept any K >= 1 (SeqTestProcessor.java:118, BuildRepDbProcessor.java:90,
+ * GtoRepBuildProcessor.java:98); 12 and above are refused by kr_create with a message: 5 bits per residue leave no room
+ * beside a 60-bit key for the sequence id of an index entry or the block-local id of a block-list entry in 64 bits. */
+#define KR_MIN_K 1
+#define KR_MAX_K 11
 
 /* ---- context -------------------------------------------------------------------------------
  * Replaces: static state of ProteinKmers -- ProteinKmers.setKmerSize(int) / kmerSize()

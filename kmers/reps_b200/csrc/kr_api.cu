@@ -196,7 +196,8 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     *out = nullptr;
     if (flags & ~(KR_IDENT_IS_INFINITY | KR_TIE_LAST | KR_FORCE_JOIN | KR_FORCE_INDEX)) return fail(nullptr, KR_ERR_ARG, "kr_create: unknown flags 0x%x", flags);
     if (K < KR_MIN_K || K > KR_MAX_K)
-        return fail(nullptr, KR_ERR_ARG, "kr_create: K=%d outside [%d,%d] (5-bit packing + 8-bit sequence id in 64 bits)", K, KR_MIN_K, KR_MAX_K);
+        return fail(nullptr, KR_ERR_ARG, "kr_create: K=%d outside [%d,%d] (5 bits per residue: a 64-bit entry has no room for a sequence id beside a key of 12 or more residues)",
+                    K, KR_MIN_K, KR_MAX_K);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

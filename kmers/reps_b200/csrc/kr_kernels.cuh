@@ -1,7 +1,7 @@
 // kr_kernels.cuh -- sm_100a kernels of the protein k-mer similarity path.
 //
 // Data model (replaces the HashSet<String> of ProteinKmers):
-//   residue  -> 5-bit code; k-mer -> 5K-bit key in a uint64 (K <= 11)
+//   residue  -> 5-bit code; k-mer -> 5K-bit key in a uint64 (K = 1..11)
 //   sequence -> sorted array of its DISTINCT keys            ("key list",   K1)
 //   block    -> 256 consecutive sequences; all their (key,lid) entries, key<<8|lid, sorted and
 //               cut into NCHUNK key-range chunks by a fixed prefix table ("block list", K2);
@@ -165,6 +165,9 @@ __global__ void k_gather_keys(const u64 *src_keys, const u64 *src_koff, const Se
 
 // ---------------------------------------------------------------------------------------------
 // K2: block lists.  count -> offsets -> scatter -> sort each chunk.
+// chunk of a key: the table is indexed by the key's first three residues (15 bits); keys of K < 3 are shorter than
+// that and are left-aligned into the index instead (shift < 0)
+__device__ __forceinline__ u32 chunk_prefix(u64 key, int shift) { return (u32)(shift >= 0 ? key >> shift : key << -shift); }
 __global__ void __launch_bounds__(256) k_bl_count(const u64 *keys, const u64 *koff, const SeqMeta *meta, u32 nseq,
                                                   const u8 *lut, int shift, u32 *chcnt) {
     __shared__ u32 hist[NCHUNK];
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256) k_bl_count(const u64 *keys, const u64 *ko
     u32 s0 = b * TB, s1 = min(nseq, s0 + TB);
     for (u32 s = s0 + warp; s < s1; s += 8) {
         u32 sz = meta[s].size; const u64 *kp = keys + koff[s];
-        for (u32 i = lane; i < sz; i += 32) atomicAdd(&hist[lut[kp[i] >> shift]], 1u);
+        for (u32 i = lane; i < sz; i += 32) atomicAdd(&hist[lut[chunk_prefix(kp[i], shift)]], 1u);
     }
     __syncthreads();
     if (tid < NCHUNK) chcnt[b * NCHUNK + tid] = hist[tid];
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(256) k_bl_scatter(const u64 *keys, const u64 *
         u64 lid = s - s0;
         for (u32 i = lane; i < sz; i += 32) {
             u64 key = kp[i];
-            u32 c = lut[key >> shift];
+            u32 c = lut[chunk_prefix(key, shift)];
             u32 pos = atomicAdd(&cur[c], 1u);
             e[so[c] + pos] = (key << LID_BITS) | lid;
         }

@@ -178,7 +178,7 @@ def test_edge_cases_and_all_k(oracle):
             "MKV*LL-AAGT*", "BJOUZXBJOUZXBJOUZX", "ACDEFGH", ""]
     res, off, _ = synth.generate(5, 300, 5)
     seqs += synth.to_strings(res, off)
-    for K, flags in [(K, f | pth) for K in (3, 5, 8, 9, 11) for f in (0, kr.IDENT_IS_INFINITY) for pth in PATHS.values()]:
+    for K, flags in [(K, f | pth) for K in (1, 2, 3, 5, 8, 9, 11) for f in (0, kr.IDENT_IS_INFINITY) for pth in PATHS.values()]:
         if True:
             c = kr.Context(device=0, K=K, flags=flags)
             s = c.encode(seqs)
@@ -211,7 +211,7 @@ def test_error_paths():
     with pytest.raises(kr.KrError):
         kr.Context(device=0, K=12)
     with pytest.raises(kr.KrError):
-        kr.Context(device=0, K=2)
+        kr.Context(device=0, K=0)
     with pytest.raises(kr.KrError):
         c.sim_matrix(s, layout=kr.LAYOUT_TRIANGLE, row_begin=3)
     other = kr.Context(device=0, K=8)

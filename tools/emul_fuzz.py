@@ -54,7 +54,7 @@ def batch(rng):
 def one(rng):
     seqs = batch(rng)
     n = len(seqs)
-    K = int(rng.choice([3, 5, 8, 8, 8, 9, 10, 11]))
+    K = int(rng.choice([1, 2, 3, 5, 8, 8, 8, 9, 10, 11]))
     ident = bool(rng.random() < 0.7)
     flags = kr.IDENT_IS_INFINITY if ident else 0
     flags |= int(rng.choice([0, kr.FORCE_JOIN, kr.FORCE_INDEX, kr.FORCE_INDEX]))      # the library's choice, or a pinned device path
@@ -109,6 +109,30 @@ def one(rng):
     added = c.db().greedy_build(s, thr, batch=int(rng.choice([0, 7, 64, 300])))
     assert (added == w).all(), desc + " greedy thr=%d" % thr
     c.close()
+    # the same through one kr_multi handle over 1..3 contexts (internal sharding)
+    if rng.random() < 0.3:
+        nd = int(rng.integers(1, 4))
+        m = kr.MultiContext([0] * nd, K=K, flags=flags)
+        got = m.sim_matrix(seqs, elem=elem, layout=layout)
+        if layout == kr.LAYOUT_FULL:
+            exp_all = want
+        elif layout == kr.LAYOUT_TRIANGLE:
+            exp_all = np.concatenate([want[i, i + 1:] for i in range(n)]) if n > 1 else np.zeros(0)
+        else:
+            exp_all = np.concatenate([want[i, 256 * (i // 256):] for i in range(n)])
+        assert (np.asarray(got).ravel() == np.asarray(exp_all).ravel()).all(), desc + " multi x%d layout=%d" % (nd, layout)
+        if n > 1:
+            cells = m.sim_matrix_sparse(seqs, min_sim=2, layout=kr.LAYOUT_TRIANGLE, cap=max(1, int(rng.choice([4, 4096]))))
+            ii, jj = np.nonzero(np.triu(want, 1) >= 2)
+            assert {(int(a), int(b), int(v)) for a, b, v, _ in cells} == {(int(i), int(j), int(want[i, j])) for i, j in zip(ii, jj)}, desc + " multi sparse"
+            nrep = int(rng.integers(1, n))
+            bs, bi = O.find_closest(O.batch(seqs[:nrep], K=K), O.batch(seqs[nrep:], K=K), ident_inf=ident, threads=4)
+            db = m.db(); db.append(seqs[:nrep])
+            sim, first, _ = db.find_closest(seqs[nrep:])
+            assert (sim == bs).all() and (first.astype(np.int64) == np.where(bs > 0, bi.astype(np.int64), kr.NO_REP)).all(), desc + " multi findClosest x%d" % nd
+        added = m.db().greedy_build(thr, seqs, batch=int(rng.choice([0, 7, 64])))
+        assert (added == w).all(), desc + " multi greedy x%d thr=%d" % (nd, thr)
+        m.close()
     return desc
 
 
