@@ -512,12 +512,32 @@ class FastaOutputStream {   // ">label comment", sequence wrapped at 60, LF (for
 
 // ---------------------------------------------------------------------------------------------------
 // The GPU engine behind the classes: one kr_ctx per k-mer size on device $KR_DEVICE (default 0).
+// With KR_DEVICES=0,1,... (a device may be listed more than once) there is one kr_multi per k-mer size instead: the batch
+// calls of the classes below shard over all listed GPUs inside the library, single-object calls use its first context.
 class KmerEngine {
   public:
+    static kr_multi *multi(int key) {
+        const char *list = std::getenv("KR_DEVICES");
+        if (!list || !*list) return nullptr;
+        auto &m = multiMap();
+        auto it = m.find(key);
+        if (it != m.end()) return it->second;
+        std::vector<int> devs;
+        for (const char *p = list; *p;) { devs.push_back(std::atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+        uint32_t flags = KR_IDENT_IS_INFINITY;
+        if (const char *f = std::getenv("KR_FLAGS")) flags = (uint32_t)std::atoi(f);
+        kr_multi *h = nullptr;
+        if (kr_multi_create(devs.data(), (int)devs.size(), key, flags, &h) != KR_OK)
+            throw std::runtime_error(std::string("kmersreps: ") + kr_multi_last_error(nullptr));
+        m[key] = h;
+        return h;
+    }
+    static void checkMulti(kr_multi *m, kr_status st) { if (st != KR_OK) throw std::runtime_error(std::string("kmersreps: ") + kr_multi_last_error(m)); }
     static kr_ctx *ctx(int key) {
         auto &m = map();
         auto it = m.find(key);
         if (it != m.end()) return it->second;
+        if (kr_multi *mh = multi(key)) return m[key] = kr_multi_ctx(mh, 0);
         const char *d = std::getenv("KR_DEVICE");
         uint32_t flags = KR_IDENT_IS_INFINITY;
         if (const char *f = std::getenv("KR_FLAGS")) flags = (uint32_t)std::atoi(f);
@@ -530,6 +550,15 @@ class KmerEngine {
     static void check(kr_ctx *c, kr_status st) { if (st != KR_OK) throw std::runtime_error(std::string("kmersreps: ") + kr_last_error(c)); }
   private:
     static std::map<int, kr_ctx *> &map() { static std::map<int, kr_ctx *> m; return m; }
+    static std::map<int, kr_multi *> &multiMap() { static std::map<int, kr_multi *> m; return m; }
+};
+
+// flat residue buffer + offsets of a list of strings (what every batch entry point takes)
+struct FlatSeqs {
+    std::string res; std::vector<uint64_t> off{0};
+    void add(const std::string &s) { res += s; off.push_back(res.size()); }
+    const uint8_t *data() const { static const uint8_t none = 0; return res.empty() ? &none : (const uint8_t *)res.data(); }
+    uint32_t count() const { return (uint32_t)off.size() - 1; }
 };
 
 struct SetHandle {   // shared ownership of an encoded batch
@@ -583,6 +612,23 @@ class SequenceKmers {
         return out;
     }
 
+    // the sorted packed k-mers (kr_seqset_keys)
+    std::vector<uint64_t> keys() const {
+        ensure();
+        std::vector<uint64_t> k(size_ ? size_ : 1); uint32_t n = 0;
+        KmerEngine::check(set_->ctx, kr_seqset_keys(set_->set, idx_, k.data(), (uint32_t)k.size(), &n));
+        k.resize(n);
+        return k;
+    }
+    // retainAll(other) / removeAll(other) (TargetProcessor.java:166,184): the merge of the two sorted key lists becomes
+    // this object's set (kr_seqset_from_keys; the sequence itself is unchanged, as upstream)
+    void retainAll(const SequenceKmers &other) { edit(other, true); }
+    void removeAll(const SequenceKmers &other) { edit(other, false); }
+    // same sequence and same k-mers (SsuGenome.java:77-104 reaches these through super)
+    bool equals(const SequenceKmers &o) const { return sequence_ == o.sequence_ && ((!edited_ && !o.edited_) || keys() == o.keys()); }
+    size_t hashCode() const { size_t h = std::hash<std::string>()(sequence_); if (edited_) for (uint64_t k : keys()) h = h * 31 + (size_t)k; return h; }
+    bool isEdited() const { return edited_; }
+
     // Encode many objects in one launch (the constructors never touch the device: they are called from parallel
     // streams, GtoRepBuildProcessor.java:127).  Objects already encoded are left alone.
     template <class It> static void encodeBatch(It first, It last) {
@@ -605,10 +651,28 @@ class SequenceKmers {
     template <class T> static const SequenceKmers &deref(const std::unique_ptr<T> &p) { return *p; }
     template <class T> static const SequenceKmers &deref(const std::shared_ptr<T> &p) { return *p; }
     void ensure() const { if (!set_) { const SequenceKmers *self = this; encodeBatch(&self, &self + 1); } }
+    void edit(const SequenceKmers &other, bool keepCommon) {
+        const std::vector<uint64_t> a = keys(), b = other.keys();
+        std::vector<uint64_t> out;
+        size_t j = 0;
+        for (uint64_t x : a) {
+            while (j < b.size() && b[j] < x) ++j;
+            const bool common = j < b.size() && b[j] == x;
+            if (common == keepCommon) out.push_back(x);
+        }
+        kr_ctx *c = KmerEngine::ctx(k_);
+        const uint64_t koff[2] = {0, out.size()}, roff[2] = {0, sequence_.size()};
+        static const uint64_t nokey = 0; static const uint8_t none = 0;
+        kr_seqset *s = nullptr;
+        KmerEngine::check(c, kr_seqset_from_keys(c, out.empty() ? &nokey : out.data(), koff, sequence_.empty() ? &none : (const uint8_t *)sequence_.data(), roff, 1, &s));
+        set_ = std::make_shared<SetHandle>(c, s, k_);
+        idx_ = 0; size_ = (uint32_t)out.size(); edited_ = true;
+    }
     std::string sequence_;
     int k_ = 8;
     mutable std::shared_ptr<SetHandle> set_;
     mutable uint32_t idx_ = 0, size_ = 0;
+    bool edited_ = false;
 };
 
 class ProteinKmers : public SequenceKmers {
@@ -633,6 +697,16 @@ class SimilarityMatrix {
         for (It it = first; it != last; ++it) v.push_back(&ref(*it));
         m.n_ = v.size();
         if (!m.n_) return m;
+        bool edited = false;
+        for (auto p : v) edited = edited || p->isEdited();
+        if (kr_multi *mh = edited ? nullptr : KmerEngine::multi(v[0]->k())) {   // every listed GPU computes a row stripe
+            FlatSeqs f; for (auto p : v) f.add(p->getSequence());
+            m.sizes_.resize(m.n_);
+            for (size_t i = 0; i < m.n_; ++i) m.sizes_[i] = (uint32_t)v[i]->size();
+            m.sim_.resize(m.n_ * m.n_);
+            KmerEngine::checkMulti(mh, kr_multi_sim_matrix(mh, f.data(), f.off.data(), f.count(), nullptr, nullptr, 0, KR_ELEM_I32, KR_LAYOUT_FULL, m.sim_.data()));
+            return m;
+        }
         // gather into one set if the objects come from different batches
         std::shared_ptr<SetHandle> h = v[0]->handle();
         bool same = true;
@@ -696,7 +770,7 @@ class RepGenomeDb {
 
     explicit RepGenomeDb(int threshold, std::string protName = DEFAULT_PROTEIN)   // RepGenomeDbProcessor.java:122
         : threshold_(threshold), kmerSize_(ProteinKmers::kmerSize()), protName_(std::move(protName)) {}
-    ~RepGenomeDb() { if (db_) kr_db_free(db_); }
+    ~RepGenomeDb() { if (db_) kr_db_free(db_); if (mdb_) kr_multi_db_free(mdb_); }
     RepGenomeDb(const RepGenomeDb &) = delete;
     RepGenomeDb &operator=(const RepGenomeDb &) = delete;
 
@@ -740,9 +814,14 @@ class RepGenomeDb {
         for (It it = first; it != last; ++it) v.push_back(ptr(*it));
         if (v.empty()) return out;
         sync();
-        auto h = batchOf(v);
         std::vector<int32_t> sim(v.size()); std::vector<uint32_t> f(v.size()), l(v.size());
-        KmerEngine::check(ctx(), kr_db_find_closest(ctx(), db_, h->set, sim.data(), f.data(), l.data()));
+        if (kr_multi *mh = multi()) {      // the queries are split over the GPUs inside the library
+            FlatSeqs fq; for (auto p : v) fq.add(p->getSequence());
+            KmerEngine::checkMulti(mh, kr_multi_db_find_closest(mh, mdb_, fq.data(), fq.off.data(), fq.count(), sim.data(), f.data(), l.data()));
+        } else {
+            auto h = batchOf(v);
+            KmerEngine::check(ctx(), kr_db_find_closest(ctx(), db_, h->set, sim.data(), f.data(), l.data()));
+        }
         for (size_t i = 0; i < v.size(); ++i) {
             uint32_t pick = tie_last_ ? l[i] : f[i];
             if (sim[i] == 0 || pick == KR_NO_REP) { out.emplace_back(this, nullptr, 0, 1.0); continue; }
@@ -764,6 +843,13 @@ class RepGenomeDb {
         std::vector<int32_t> out(v.size() * reps.size());
         if (v.empty() || reps.empty()) return out;
         SequenceKmers::encodeBatch(reps.begin(), reps.end());   // one launch; the reps keep their sizes for distance()
+        if (kr_multi *mh = multi()) {      // query rows split over the GPUs
+            FlatSeqs fq, fr;
+            for (auto p : v) fq.add(p->getSequence());
+            for (auto r : reps) fr.add(r->getSequence());
+            KmerEngine::checkMulti(mh, kr_multi_sim_matrix(mh, fq.data(), fq.off.data(), fq.count(), fr.data(), fr.off.data(), fr.count(), KR_ELEM_I32, KR_LAYOUT_FULL, out.data()));
+            return out;
+        }
         auto hr = batchOf(std::vector<const SequenceKmers *>(reps.begin(), reps.end()));
         const size_t R = reps.size(), chunk = std::max<size_t>(256, ((size_t)1 << 26) / R / 256 * 256);   // <= 64M cells per launch
         for (size_t q0 = 0; q0 < v.size(); q0 += chunk) {
@@ -799,6 +885,11 @@ class RepGenomeDb {
         if (size() == 0) return false;
         sync();
         uint8_t r = 0;
+        if (kr_multi *mh = multi()) {
+            FlatSeqs fq; fq.add(q.getSequence());
+            KmerEngine::checkMulti(mh, kr_multi_db_any_ge(mh, mdb_, fq.data(), fq.off.data(), 1, sim, &r));
+            return r != 0;
+        }
         const SequenceKmers *p = &q; auto h = batchOf(std::vector<const SequenceKmers *>{p});
         KmerEngine::check(ctx(), kr_db_any_ge(ctx(), db_, h->set, sim, &r));
         return r != 0;
@@ -810,11 +901,16 @@ class RepGenomeDb {
         std::vector<bool> added(cands.size(), false);
         if (cands.empty()) return added;
         sync();
-        SequenceKmers::encodeBatch(cands.begin(), cands.end());
-        std::vector<const SequenceKmers *> v; for (auto &c : cands) v.push_back(&c);
-        auto h = batchOf(v);
         std::vector<uint8_t> a(cands.size());
-        KmerEngine::check(ctx(), kr_greedy_build(ctx(), db_, h->set, threshold_, batch, a.data()));
+        if (kr_multi *mh = multi()) {      // scoring of every batch split over the GPUs, replicas kept identical
+            FlatSeqs fc; for (auto &c : cands) fc.add(c.getSequence());
+            KmerEngine::checkMulti(mh, kr_multi_greedy_build(mh, mdb_, fc.data(), fc.off.data(), fc.count(), threshold_, batch, a.data()));
+        } else {
+            SequenceKmers::encodeBatch(cands.begin(), cands.end());
+            std::vector<const SequenceKmers *> v; for (auto &c : cands) v.push_back(&c);
+            auto h = batchOf(v);
+            KmerEngine::check(ctx(), kr_greedy_build(ctx(), db_, h->set, threshold_, batch, a.data()));
+        }
         for (size_t i = 0; i < cands.size(); ++i)
             if (a[i]) {
                 added[i] = true;
@@ -864,6 +960,22 @@ class RepGenomeDb {
     static const SequenceKmers *ptr(const SequenceKmers &p) { return &p; }
     static const SequenceKmers *ptr(const SequenceKmers *p) { return p; }
     kr_ctx *ctx() const { return KmerEngine::ctx(kmerSize_); }
+    kr_multi *multi() const { return KmerEngine::multi(kmerSize_); }
+    // the device copy: a kr_db on the single context, or a kr_multi_db (one replica per GPU) under KR_DEVICES
+    void devFree() const { if (db_) { kr_db_free(db_); db_ = nullptr; } if (mdb_) { kr_multi_db_free(mdb_); mdb_ = nullptr; } }
+    bool devExists() const { return db_ || mdb_; }
+    void devCreate() const {
+        if (kr_multi *mh = multi()) KmerEngine::checkMulti(mh, kr_multi_db_create(mh, &mdb_));
+        else KmerEngine::check(ctx(), kr_db_create(ctx(), &db_));
+    }
+    void devAppend(const FlatSeqs &f) const {
+        if (kr_multi *mh = multi()) KmerEngine::checkMulti(mh, kr_multi_db_append(mh, mdb_, f.data(), f.off.data(), f.count()));
+        else KmerEngine::check(ctx(), kr_db_append(ctx(), db_, f.data(), f.off.data(), f.count()));
+    }
+    void devSetRanks(const std::vector<uint32_t> &rank) const {
+        if (kr_multi *mh = multi()) KmerEngine::checkMulti(mh, kr_multi_db_set_ranks(mh, mdb_, rank.data(), (uint32_t)rank.size()));
+        else KmerEngine::check(ctx(), kr_db_set_ranks(ctx(), db_, rank.data(), (uint32_t)rank.size()));
+    }
     // one set holding exactly these objects, in order
     static std::shared_ptr<SetHandle> batchOf(const std::vector<const SequenceKmers *> &v) {
         std::shared_ptr<SetHandle> h = v[0]->handle();
@@ -882,18 +994,17 @@ class RepGenomeDb {
     }
     // bring the device copy of the database up to date: append new reps, refresh iteration ranks
     void sync() const {
-        kr_ctx *c = ctx();
-        if (rebuild_ && db_) { kr_db_free(db_); db_ = nullptr; synced_ = 0; dev2host_.clear(); }
-        if (!db_) KmerEngine::check(c, kr_db_create(c, &db_));
+        if (rebuild_ && devExists()) { devFree(); synced_ = 0; dev2host_.clear(); }
+        if (!devExists()) devCreate();
         if (rebuild_) {   // replaced / removed reps: re-append the live ones
-            std::string flat; std::vector<uint64_t> off{0};
-            for (int i : order_.order()) { flat += reps_[i]->getProtein(); off.push_back(flat.size()); dev2host_.push_back(i); }
-            if (off.size() > 1) KmerEngine::check(c, kr_db_append(c, db_, (const uint8_t *)flat.data(), off.data(), (uint32_t)off.size() - 1));
+            FlatSeqs f;
+            for (int i : order_.order()) { f.add(reps_[i]->getProtein()); dev2host_.push_back(i); }
+            if (f.count()) devAppend(f);
             synced_ = reps_.size(); rebuild_ = false; ranks_dirty_ = true;
         } else if (synced_ < reps_.size()) {
-            std::string flat; std::vector<uint64_t> off{0};
-            for (size_t i = synced_; i < reps_.size(); ++i) { flat += reps_[i]->getProtein(); off.push_back(flat.size()); dev2host_.push_back((int)i); }
-            KmerEngine::check(c, kr_db_append(c, db_, (const uint8_t *)flat.data(), off.data(), (uint32_t)off.size() - 1));
+            FlatSeqs f;
+            for (size_t i = synced_; i < reps_.size(); ++i) { f.add(reps_[i]->getProtein()); dev2host_.push_back((int)i); }
+            devAppend(f);
             synced_ = reps_.size(); ranks_dirty_ = true;
         }
         if (ranks_dirty_ && !dev2host_.empty()) {
@@ -901,7 +1012,7 @@ class RepGenomeDb {
             std::vector<uint32_t> rank_of_host(reps_.size(), 0), rank(dev2host_.size());
             for (size_t k = 0; k < ord.size(); ++k) rank_of_host[ord[k]] = (uint32_t)k;
             for (size_t d = 0; d < dev2host_.size(); ++d) rank[d] = rank_of_host[dev2host_[d]];
-            KmerEngine::check(c, kr_db_set_ranks(c, db_, rank.data(), (uint32_t)rank.size()));
+            devSetRanks(rank);
         }
         ranks_dirty_ = false;
     }
@@ -911,6 +1022,7 @@ class RepGenomeDb {
     java::HashMapOrder order_;
     std::vector<std::unique_ptr<RepGenome>> reps_;   // by insertion index
     mutable kr_db *db_ = nullptr;
+    mutable kr_multi_db *mdb_ = nullptr;
     mutable size_t synced_ = 0;                      // reps_[0..synced_) are on the device
     mutable std::vector<int> dev2host_;              // device rep index -> insertion index
     mutable bool rebuild_ = false, ranks_dirty_ = true;

@@ -8,6 +8,7 @@
 //   kmers_reps gtoreps    GtoRepGenomeProcessor.java      closest representative of every genome; --create / --update add the outliers
 //   kmers_reps buildfromgtos GtoRepBuildProcessor.java     greedy representative set from a GTO directory, optional --verify report
 //   kmers_reps neighbors  NeighborProcessor.java          the N closest representatives of each input genome, ties retained
+//   kmers_reps kmerops    TargetProcessor.java:160-195 (the SequenceKmers set members: retainAll / removeAll / iteration)
 //   kmers_reps buildsets  GenomeProcessor.java + BaseGenomeProcessor.java:151-214,348-407,433-442
 //                                                       the hot part of the `genomes` pipeline: hierarchical rep sets at
 //                                                       several thresholds, saved as rep<thr>.ser + rep<thr>.list.tbl
@@ -528,6 +529,29 @@ static int cmd_buildsets(int argc, char **argv) {
     return 0;
 }
 
+// kmerops: the k-mer set members of SequenceKmers that TargetProcessor.java:160-195 uses (retainAll, removeAll, size, the
+// iteration over the k-mers) on the sequences of a FASTA.  Record 0 is the "other" set; for every further record prints
+//   label <TAB> size <TAB> |retainAll(other)| <TAB> |removeAll(other)| <TAB> similarity(edited-retain, other) <TAB> the retained k-mers, comma-joined, sorted
+static int cmd_kmerops(int argc, char **argv) {
+    Args a = parse(argc, argv, 2, {{"-K", "K"}, {"--kmer", "K"}}, {"K"});
+    if (a.opt.count("K")) ProteinKmers::setKmerSize(std::stoi(a.opt["K"]));
+    FastaInputStream in(std::cin);
+    Sequence s;
+    if (!in.next(s)) return 0;
+    ProteinKmers other(s.sequence);
+    while (in.next(s)) {
+        ProteinKmers keep(s.sequence), drop(s.sequence), plain(s.sequence);
+        keep.retainAll(other);
+        drop.removeAll(other);
+        std::vector<std::string> k = keep.kmers();
+        std::sort(k.begin(), k.end());
+        std::cout << s.label << '\t' << plain.size() << '\t' << keep.size() << '\t' << drop.size() << '\t' << keep.similarity(other) << '\t';
+        for (size_t i = 0; i < k.size(); ++i) std::cout << (i ? "," : "") << k[i];
+        std::cout << '\t' << (keep.equals(plain) ? 1 : 0) << (drop.equals(plain) ? 1 : 0) << '\n';
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { usage(); return 2; }
     std::ios::sync_with_stdio(false);
@@ -542,6 +566,7 @@ int main(int argc, char **argv) {
         if (cmd == "buildfromgtos") return cmd_buildfromgtos(argc, argv);
         if (cmd == "neighbors") return cmd_neighbors(argc, argv);
         if (cmd == "buildsets") return cmd_buildsets(argc, argv);
+        if (cmd == "kmerops") return cmd_kmerops(argc, argv);
         usage();
         return 2;
     } catch (const std::exception &e) {   // App.java:129: print the error, exit non-zero

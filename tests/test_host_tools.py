@@ -13,7 +13,7 @@ from oracle import ref_commands as rc
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TOOL = os.path.join(ROOT, "kmers", "reps_b200", "host", "kmers_reps")
+TOOL = os.environ.get("KR_TOOL_PATH") or os.path.join(ROOT, "kmers", "reps_b200", "host", "kmers_reps")   # (tools/emul_gpu_suite.sh points it at a build linked against the emulator)
 
 
 def run(args, stdin=b"", check=True):
@@ -239,3 +239,44 @@ def test_gtoreps_and_buildfromgtos(tmp_path, oracle):
     assert out_db.read_bytes() == want_db
     assert p.stdout.decode() == rc.buildfromgtos_verify(reps, 60, vq)
     assert run(["buildfromgtos", gdir, str(roles), str(tmp_path / "x.db")]).stdout.decode() == "No verification requested.\n"
+
+
+def test_kmerops_set_members(vapb):
+    """SequenceKmers.retainAll / removeAll / size / iteration / equals (TargetProcessor.java:160-195) through the host
+    classes: every number and every retained k-mer equals Python set arithmetic on substrings"""
+    recs = vapb[:40] + [vapb[0], ("short", "", "MKV")]
+    p = run(["kmerops"], stdin=fasta(recs))
+    other = ko.py_kmers(recs[0][2], 8)
+    rows = p.stdout.decode().split("\n")[:-1]
+    assert len(rows) == len(recs) - 1
+    for (label, _, seq), row in zip(recs[1:], rows):
+        f = row.split("\t")
+        mine = ko.py_kmers(seq, 8)
+        kept = mine & other
+        assert f[0] == label and int(f[1]) == len(mine) and int(f[2]) == len(kept) and int(f[3]) == len(mine - other)
+        want_sim = 9999 if (seq == recs[0][2] and kept == other) else len(kept)      # kept is a subset of other
+        assert int(f[4]) == want_sim
+        assert (f[5].split(",") if f[5] else []) == sorted(kept)
+        assert f[6] == ("1" if kept == mine else "0") + ("1" if not (mine & other) else "0")
+
+
+def test_commands_over_a_multi_gpu_handle(tmp_path, rep50, gto_seeds, vapb, monkeypatch):
+    """KR_DEVICES: the same commands with the batch calls sharded inside the library over two contexts (kr_multi) print
+    the same bytes: repdb report, repdb --create (greedy build), distances, group"""
+    import torch
+    ndev = 0 if "emul" in TOOL else torch.cuda.device_count()
+    monkeypatch.setenv("KR_DEVICES", ",".join(str(i) for i in range(ndev)) if ndev > 1 else "0,0")
+    db = tmp_path / "rep50.db"
+    db.write_bytes(rep50["raw"])
+    p = run(["repdb", str(db)], stdin=fasta(gto_seeds))
+    assert p.stdout.decode() == rc.repdb_report(rep50["reps"], 50, gto_seeds)
+    src = tmp_path / "in.fa"
+    src.write_bytes(fasta(rep50["reps"]))
+    out = tmp_path / "out.db"
+    run(["repdb", "--create", str(src), "-m", "50", "--null", "--batch", "400", str(out)])
+    assert out.read_bytes() == rep50["raw"]
+    small = tmp_path / "small.db"
+    small.write_bytes(ko.save_repdb(50, 8, rep50["prot_name"], rep50["reps"][:300]))
+    assert run(["distances", str(small)]).stdout.decode() == rc.distances(rep50["reps"][:300])
+    want, _ = rc.group(vapb)
+    assert run(["group"], stdin=fasta(vapb)).stdout.decode() == want
