@@ -94,22 +94,84 @@ __global__ void __launch_bounds__(1024) k_ix_scan(const u32 *cnt, u32 nbins, u32
     for (u32 i = b0; i < b1; ++i) { const u32 v = cnt[i]; start[i] = run; cursor[i] = run; run += v; }
 }
 
-// K4.4: one CTA per prefix sorts the prefix's entries (shared memory; in place in global memory for the rare prefix
-// that holds more than IX_SORT_CAP entries, e.g. one k-mer shared by thousands of sequences)
-__global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u64 *ent) {
+// K4.4: one CTA per prefix sorts the prefix's entries.  The entries of a prefix share their top B bits and the bits
+// below are a hash, i.e. uniform: a counting sort on the next 11 bits leaves about one entry per bucket, so the sort is
+// three passes over shared memory (histogram with the rank kept in a register, scan, scatter) plus an insertion sort
+// of the few buckets that hold more than one entry -- an order of magnitude fewer instructions than a sorting network
+// over 2,000 entries.  Inputs that are not uniform (one k-mer shared by thousands of sequences puts thousands of equal
+// hashed keys into one bucket) take the network instead; a prefix beyond IX_SORT_CAP entries is sorted in place in
+// global memory.  `low_bits` = number of entry bits below the prefix (key bits below the prefix + id bits).
+constexpr u32 IX_SORT_BUCKET_BITS = 11, IX_SORT_NB = 1u << IX_SORT_BUCKET_BITS;
+constexpr u32 IX_SORT_PER_THREAD = IX_SORT_CAP / IX_SORT_THREADS;      // entries a thread keeps in registers
+constexpr u32 IX_SORT_INSERTION_MAX = 24;                              // a bucket above this sends the prefix to the network
+static_assert(IX_SORT_NB == 8 * IX_SORT_THREADS, "the scan gives every thread 8 consecutive buckets");
+__global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u64 *ent, int low_bits) {
     __shared__ __align__(16) u64 sk[IX_SORT_CAP];
-    const u32 p = blockIdx.x, tid = threadIdx.x;
+    __shared__ u32 cnt[IX_SORT_NB + 1];
+    __shared__ u32 wsum[IX_SORT_THREADS / 32];
+    __shared__ u32 s_big;
+    const u32 p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lo = start[p], n = start[p + 1] - lo;
     if (n < 2) return;
     u64 *g = ent + lo;
-    if (n <= IX_SORT_CAP) {
-        for (u32 i = tid; i < n; i += IX_SORT_THREADS) sk[i] = g[i];
-        __syncthreads();
-        bitonic_sort(sk, n, tid, IX_SORT_THREADS);
-        for (u32 i = tid; i < n; i += IX_SORT_THREADS) g[i] = sk[i];
-    } else {
-        bitonic_sort(g, n, tid, IX_SORT_THREADS);
+    if (n > IX_SORT_CAP) { bitonic_sort(g, n, tid, IX_SORT_THREADS); return; }
+    const int bshift = low_bits > (int)IX_SORT_BUCKET_BITS ? low_bits - (int)IX_SORT_BUCKET_BITS : 0;
+    u64 e[IX_SORT_PER_THREAD];
+    u32 rank[IX_SORT_PER_THREAD];
+    for (u32 i = tid; i <= IX_SORT_NB; i += IX_SORT_THREADS) cnt[i] = 0;
+    if (tid == 0) s_big = 0;
+    __syncthreads();
+    // 1. histogram; the value the atomic returns is the entry's place inside its bucket
+#pragma unroll
+    for (u32 j = 0; j < IX_SORT_PER_THREAD; ++j) {
+        const u32 i = tid + j * IX_SORT_THREADS;
+        if (i < n) {
+            e[j] = g[i];
+            rank[j] = atomicAdd(&cnt[(u32)(e[j] >> bshift) & (IX_SORT_NB - 1)], 1u);
+        }
     }
+    __syncthreads();
+    // 2. exclusive scan of the bucket counts, in place: thread t owns buckets 8t .. 8t+7
+    u32 c[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = cnt[tid * 8 + k]; sum += c[k]; if (c[k] > IX_SORT_INSERTION_MAX) s_big = 1; }
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += up; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 base = incl - sum;
+    for (u32 w = 0; w < warp; ++w) base += wsum[w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { cnt[tid * 8 + k] = base; base += c[k]; }
+    if (tid == IX_SORT_THREADS - 1) cnt[IX_SORT_NB] = base;
+    __syncthreads();
+    // 3. scatter into bucket order
+#pragma unroll
+    for (u32 j = 0; j < IX_SORT_PER_THREAD; ++j) {
+        const u32 i = tid + j * IX_SORT_THREADS;
+        if (i < n) sk[cnt[(u32)(e[j] >> bshift) & (IX_SORT_NB - 1)] + rank[j]] = e[j];
+    }
+    __syncthreads();
+    if (s_big) {
+        bitonic_sort(sk, n, tid, IX_SORT_THREADS);          // (uniform decision: s_big was read after the barrier)
+    } else {
+        // 4. buckets with more than one entry: insertion sort by the thread that owns the bucket
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (c[k] > 1) {
+                u64 *q = sk + cnt[tid * 8 + k];
+                for (u32 x = 1; x < c[k]; ++x) {
+                    const u64 v = q[x];
+                    u32 y = x;
+                    while (y > 0 && q[y - 1] > v) { q[y] = q[y - 1]; --y; }
+                    q[y] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (u32 i = tid; i < n; i += IX_SORT_THREADS) g[i] = sk[i];
 }
 
 // K4.5: the directory.  Entry i opens every D-bit prefix after its predecessor's up to its own; the last entry also

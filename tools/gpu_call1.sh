@@ -13,7 +13,7 @@ tail -3 gpurun_out/c1_memcheck_smoke.log
 
 stage "2. memcheck: N-shard import on one GPU + reference fixtures (small)"
 timeout 1200 $CS --tool memcheck --error-exitcode 86 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
-    -k "shard_import or kat_k10 or vapb_matrix or config1_find_closest" > gpurun_out/c1_memcheck_tests.log 2>&1 || fail memcheck-tests gpurun_out/c1_memcheck_tests.log
+    -k "shard_import or kat_k10 or vapb_matrix or config1_find_closest or sets_from_key_lists or (multi_handle and index)" > gpurun_out/c1_memcheck_tests.log 2>&1 || fail memcheck-tests gpurun_out/c1_memcheck_tests.log
 tail -3 gpurun_out/c1_memcheck_tests.log
 
 stage "3. the whole GPU suite, default library, no tool"
@@ -26,8 +26,12 @@ tail -c 1500 gpurun_out/c1_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/c1_bench_ref.json 2> gpurun_out/c1_bench_ref.err || fail bench-ref gpurun_out/c1_bench_ref.err
 tail -c 600 gpurun_out/c1_bench_ref.json
 
+stage "4b. the tile join pinned, for the comparison of the two device paths"
+timeout 600 python bench.py --path join --steps 5 --no-cpu > gpurun_out/c1_bench_join.json 2> gpurun_out/c1_bench_join.err || fail bench-join gpurun_out/c1_bench_join.err
+tail -c 700 gpurun_out/c1_bench_join.json
+
 stage "5. findClosest / greedy build workload (configs 3, 4), default library"
-timeout 900 python bench.py --workload findclosest --steps 2 > gpurun_out/c1_fc.json 2> gpurun_out/c1_fc.err || fail bench-fc gpurun_out/c1_fc.err
+timeout 1200 python bench.py --workload findclosest --steps 2 > gpurun_out/c1_fc.json 2> gpurun_out/c1_fc.err || fail bench-fc gpurun_out/c1_fc.err
 tail -c 1500 gpurun_out/c1_fc.json
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
 echo "ALL STAGES OK"
