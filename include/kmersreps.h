@@ -251,6 +251,10 @@ typedef struct kr_stats {
     /* posting-list statistics of the index most recently consulted for a path choice: entries (sum of list lengths m),
      * sum of m^2 (postings a self scan walks = sum over ordered pairs of their similarity, diagonal included) */
     uint64_t index_entries, index_walk;
+    /* zero-fill of dense results that ran on a second stream beside an index build (device time of the fill kernels; it
+     * overlaps index_ms, so the stage times no longer add up to the step time) */
+    double fill_ms;
+    uint64_t fill_launches;
 } kr_stats;
 kr_status kr_stats_get(kr_ctx *ctx, kr_stats *out); /* synchronises the context's stream */
 kr_status kr_stats_reset(kr_ctx *ctx);

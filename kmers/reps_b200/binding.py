@@ -59,7 +59,7 @@ class Stats(C.Structure):
                 ("blocklist_ms", C.c_double), ("join_ms", C.c_double), ("other_ms", C.c_double),
                 ("join_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("index_ms", C.c_double), ("scan_ms", C.c_double), ("scan_launches", C.c_uint64), ("index_builds", C.c_uint64),
-                ("index_entries", C.c_uint64), ("index_walk", C.c_uint64)]
+                ("index_entries", C.c_uint64), ("index_walk", C.c_uint64), ("fill_ms", C.c_double), ("fill_launches", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -31,7 +31,7 @@ using namespace kr;
 static thread_local std::string g_create_error;
 
 struct EvPair { cudaEvent_t a, b; int stage; };
-enum { ST_ENCODE = 0, ST_BLOCKLIST = 1, ST_JOIN = 2, ST_OTHER = 3, ST_INDEX = 4, ST_SCAN = 5 };
+enum { ST_ENCODE = 0, ST_BLOCKLIST = 1, ST_JOIN = 2, ST_OTHER = 3, ST_INDEX = 4, ST_SCAN = 5, ST_FILL = 6 };
 
 struct DevMem {   // refcounted device allocation (residue buffers are shared by gathered sets)
     void *p = nullptr;
@@ -44,7 +44,8 @@ struct kr_ctx {
     int dev = 0, K = 8;
     u32 flags = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, fill_stream = nullptr;   // fill_stream: zero-fill of a dense result beside the index build
+    cudaEvent_t ev_fill[2] = {nullptr, nullptr};
     cudaMemPool_t pool = nullptr;   // this context's own memory pool: the device's default pool (shared with the JVM / torch) is never touched
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     std::mutex mu;              // serialises the calls on this context
@@ -131,17 +132,19 @@ static cudaEvent_t get_event(kr_ctx *ctx) {
     if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-struct StageTimer {   // device time of a group of launches, resolved lazily in kr_stats_get
-    kr_ctx *ctx; EvPair ev;
-    StageTimer(kr_ctx *c, int stage) : ctx(c) { ev.a = get_event(c); ev.b = get_event(c); ev.stage = stage; cudaEventRecord(ev.a, c->stream); }
-    ~StageTimer() { cudaEventRecord(ev.b, ctx->stream); ctx->pending.push_back(ev); if (ctx->pending.size() > 4096) drain(ctx); }
+struct StageTimer {   // device time of a group of launches on one stream, resolved lazily in kr_stats_get
+    kr_ctx *ctx; EvPair ev; cudaStream_t stream;
+    StageTimer(kr_ctx *c, int stage, cudaStream_t on = nullptr) : ctx(c), stream(on ? on : c->stream) {
+        ev.a = get_event(c); ev.b = get_event(c); ev.stage = stage; cudaEventRecord(ev.a, stream);
+    }
+    ~StageTimer() { cudaEventRecord(ev.b, stream); ctx->pending.push_back(ev); if (ctx->pending.size() > 4096) drain(ctx); }
     static void drain(kr_ctx *c) {
         for (auto &e : c->pending) {
             cudaEventSynchronize(e.b);
             float ms = 0; cudaEventElapsedTime(&ms, e.a, e.b);
             double *dst = e.stage == ST_ENCODE ? &c->st.encode_ms : e.stage == ST_BLOCKLIST ? &c->st.blocklist_ms
                         : e.stage == ST_JOIN ? &c->st.join_ms : e.stage == ST_INDEX ? &c->st.index_ms
-                        : e.stage == ST_SCAN ? &c->st.scan_ms : &c->st.other_ms;
+                        : e.stage == ST_SCAN ? &c->st.scan_ms : e.stage == ST_FILL ? &c->st.fill_ms : &c->st.other_ms;
             *dst += ms;
             c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b);
         }
@@ -216,6 +219,8 @@ kr_status kr_create(int device, int K, uint32_t flags, kr_ctx **out) {
     CUC(cudaSetDevice(device));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->fill_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&ctx->ev_fill[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CUC(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
@@ -258,6 +263,9 @@ void kr_destroy(kr_ctx *ctx) {
     cudaFree(ctx->d_lut); cudaFree(ctx->d_err);
     if (ctx->d_tasks_cache) cudaFree(ctx->d_tasks_cache);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
+    cudaStreamSynchronize(ctx->fill_stream);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->ev_fill[i]);
+    cudaStreamDestroy(ctx->fill_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -535,14 +543,39 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
         // that share a k-mer; dense ones through the tile join below
         bool use_index = false;
         kr_seqset *Bx = self ? A : B;
-        if ((st = choose_index_path(ctx, A, Bx, self, &use_index))) return st;
-        if (use_index && d->row_end > d->row_begin) {
+        // A dense result of the index path is zeros plus a few cells.  When this call still has to BUILD the index (every
+        // step of a pipeline that re-encodes its batch), the zero-fill -- pure HBM write traffic -- is started on a second
+        // stream first and runs beside the build (atomics, shared-memory sorting).  It is started before the path is known
+        // (the choice needs the built index's statistics); should the join be chosen after all it simply overwrites every
+        // cell, the fill having cost a few percent of a join.  Small collections never take the index and are not filled.
+        bool filled = false;
+        const u64 rows = d->row_end > d->row_begin ? d->row_end - d->row_begin : 0;
+        if (!sparse && rows && !(ctx->flags & KR_FORCE_JOIN) && A->d_keys && Bx->n && set_indexable(ctx, Bx) && !(Bx->ix && Bx->ix->ok) &&
+            ((ctx->flags & KR_FORCE_INDEX) || (double)A->key_cap * 3.0 <= (double)A->n * (double)Bx->n)) {
+            const u64 bytes = (row_start(d->layout, d->row_end, A->n, Bx->n) - row_start(d->layout, d->row_begin, A->n, Bx->n)) * (d->elem == KR_ELEM_U16 ? 2 : 4);
+            CU(cudaEventRecord(ctx->ev_fill[0], ctx->stream));                  // after everything queued so far (earlier users of `out`)
+            CU(cudaStreamWaitEvent(ctx->fill_stream, ctx->ev_fill[0], 0));
+            {
+                StageTimer t(ctx, ST_FILL, ctx->fill_stream);
+                KR_LAUNCH(KR_T(k_zero_fill), std::max(1, ctx->num_sms * 2), 256, 0, ctx->fill_stream, (u8 *)out_dev, bytes);
+                LAUNCHED(ctx); ctx->st.fill_launches++;
+            }
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(ctx->ev_fill[1], ctx->fill_stream));
+            filled = true;
+        }
+        st = choose_index_path(ctx, A, Bx, self, &use_index);
+        // whatever happens next on the main stream (scan, join, the caller's frees) comes after the fill
+        if (filled) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_fill[1], 0));
+        if (st) return st;
+        if (use_index && rows) {
             MatrixTarget tg;
-            const u64 rows = d->row_end - d->row_begin;
             if (sparse) { tg.cells = sparse->cells; tg.cells_cap = sparse->cap; tg.cells_count = sparse->count; tg.min_sim = sparse->min_sim; }
             else {
                 tg.out = out_dev; tg.elem = d->elem; tg.layout = d->layout; tg.origin = row_start(d->layout, d->row_begin, A->n, Bx->n); tg.min_sim = 1;
-                // (the scan writes every cell of its rows: zeros first, then the cells of pairs that share a k-mer)
+                // (the scan leaves every cell of its rows written: zeros -- by the fill above, or else row by row by the warp
+                // that owns the row -- and then the cells of pairs that share a k-mer)
+                tg.prezeroed = filled;
             }
             if ((st = index_matrix(ctx, A, Bx, self, d->layout, d->row_begin, d->row_end, tg))) return st;
             if (d->layout == KR_LAYOUT_FULL) ctx->st.pairs += rows * (u64)Bx->n;

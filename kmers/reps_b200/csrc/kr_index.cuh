@@ -243,7 +243,8 @@ struct IxQueryParams {
     u32 col_mode;                  // 0: every column, 1: columns > q (strict triangle), 2: columns >= 256 * (q / 256)
     u32 min_sim;
     uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;      // CELLS: (row, col, sim, 0), any order
-    void *out; u32 elem, layout; u64 origin; u32 nrows, ncols;                        // DENSE: the zero-filled result
+    void *out; u32 elem, layout; u64 origin; u32 nrows, ncols;                        // DENSE: the result
+    u32 prezeroed;                 // DENSE: the rows were already zero-filled (k_zero_fill overlapped with the index build)
 };
 
 template <int MODE>
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
         unsigned long long bf = 0, bl = 0;   // ARGMAX: (score << 32) | ~rank  and  (score << 32) | rank
         u32 col_min = 0;
         if (MODE != IXQ_ARGMAX) col_min = p.col_mode == 1 ? q + 1 : p.col_mode == 2 ? (q & ~255u) : 0;
-        if (MODE == IXQ_DENSE && p.ncols > col_min) {
+        if (MODE == IXQ_DENSE && !p.prezeroed && p.ncols > col_min) {
             // The warp owns row q of the result: it writes the whole row as zeros (streaming 16-byte stores; the head and
             // tail up to the next 16-byte boundary element-wise) and afterwards the few cells that are not zero.  No
             // separate zero-fill pass over the N^2 result, and the stores overlap the latency-bound walk of other warps.
@@ -410,6 +411,21 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
             }
         }
     }
+}
+
+// Zero-fill of a dense result (16-byte streaming stores, grid-stride).  The host launches it on a second stream when a
+// dense matrix call has to build its index first: the fill is pure HBM write traffic, the index build is atomics and
+// shared-memory sorting, so the two overlap almost perfectly; the scan then only writes the non-zero cells.
+__global__ void __launch_bounds__(256) k_zero_fill(u8 *p, u64 bytes) {
+    u64 head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > bytes) head = bytes;
+    const u64 body = (bytes - head) >> 4;
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (u64)gridDim.x * blockDim.x;
+    uint4 *v = reinterpret_cast<uint4 *>(p + head);
+    for (u64 k = tid; k < body; k += nthr) __stcs(v + k, make_uint4(0u, 0u, 0u, 0u));
+    if (tid < head) p[tid] = 0;
+    const u64 tail0 = head + (body << 4);
+    if (tail0 + tid < bytes && tid < 16) p[tail0 + tid] = 0;
 }
 
 // Sequences without any k-mer (shorter than K) never meet the index, but two EQUAL ones are still "identical": under

@@ -17,6 +17,13 @@ EMUL = "libkmersreps_emul" in kr.lib_path()
 DEV = "cpu" if EMUL else "cuda"
 
 
+def dsync():
+    """torch fills its tensors on ITS stream; the library works on its own non-blocking stream: finish torch's work first"""
+    if not EMUL:
+        import torch
+        torch.cuda.synchronize()
+
+
 # every test that takes `ctx` / `ctx_raw` runs three times: the library's own path choice, the tile join pinned, and the
 # sorted index + warp scan pinned (include/kmersreps.h, KR_FORCE_*): both device paths must equal the oracle
 PATHS = {"auto": 0, "join": kr.FORCE_JOIN, "index": kr.FORCE_INDEX}
@@ -415,6 +422,7 @@ def test_allvsall_full_size_index_equals_join():
         c = kr.Context(device=0, K=8, flags=kr.IDENT_IS_INFINITY | flag)
         s = c.encode_device(d_res.data_ptr(), off)
         out = torch.full((ne + 8,), -1, dtype=torch.int16, device=DEV)
+        dsync()
         c.sim_matrix_device(s, None, out.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI)
         c.synchronize()
         st = c.stats()
@@ -427,6 +435,7 @@ def test_allvsall_full_size_index_equals_join():
             for k in range(4):
                 cnt = kr.matrix_elems(n, n, kr.LAYOUT_BLOCKTRI, int(rb[k]), int(rb[k + 1]))
                 part = torch.full((cnt + 8,), -1, dtype=torch.int16, device=DEV)
+                dsync()
                 c.sim_matrix_device(s, None, part.data_ptr(), elem=kr.ELEM_U16, layout=kr.LAYOUT_BLOCKTRI, row_begin=int(rb[k]), row_end=int(rb[k + 1]))
                 c.synchronize()
                 assert torch.equal(part[:cnt], out[pos:pos + cnt]), k
@@ -435,6 +444,7 @@ def test_allvsall_full_size_index_equals_join():
             assert pos == ne
             cap = 1 << 23
             cells = torch.zeros((cap, 4), dtype=torch.int32, device=DEV)
+            dsync()
             cnt = c.sim_matrix_sparse_device(s, None, cells.data_ptr(), cap, min_sim=1, layout=kr.LAYOUT_TRIANGLE)
             c.synchronize()
             outs["cells"] = cells[:cnt].cpu().numpy()

@@ -60,7 +60,7 @@ def test_buildsets_hierarchy(tmp_path):
     from kmers.reps_b200 import synth
     from oracle import ref_commands as rc
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    tool = os.path.join(root, "kmers", "reps_b200", "host", "kmers_reps")
+    tool = os.environ.get("KR_TOOL_PATH") or os.path.join(root, "kmers", "reps_b200", "host", "kmers_reps")
     res, off, _ = synth.generate(0x5EED0006, 1500, 30)
     seqs = synth.to_strings(res, off)
     recs = [("fig|%d.%d.peg.%d" % (2000 + 3 * i, 1 + i % 7, 10 + i), "Synthetic genome %d" % i, s) for i, s in enumerate(seqs)]
