@@ -690,6 +690,10 @@ class ProteinKmers : public SequenceKmers {
 // DistanceMatrixProcessor.java:71-76 and RepMatrixProcessor.java:88-93).
 class SimilarityMatrix {
   public:
+    // The matrix is fetched as the cells with similarity >= 1 of the strict upper triangle (kr_sim_matrix_sparse: a few
+    // cells per sequence cross PCIe instead of N * N values) plus the diagonal; every pair not listed has similarity 0 by
+    // definition.  The callers' loops still visit every pair in the reference's order (DistanceMatrixProcessor.java:71-83,
+    // SequenceInfo.java:83-89) and read zeros here, so their output and their floating-point sums are unchanged.
     template <class It> static SimilarityMatrix compute(It first, It last) {
         SequenceKmers::encodeBatch(first, last);
         SimilarityMatrix m;
@@ -699,35 +703,77 @@ class SimilarityMatrix {
         if (!m.n_) return m;
         bool edited = false;
         for (auto p : v) edited = edited || p->isEdited();
-        if (kr_multi *mh = edited ? nullptr : KmerEngine::multi(v[0]->k())) {   // every listed GPU computes a row stripe
-            FlatSeqs f; for (auto p : v) f.add(p->getSequence());
-            m.sizes_.resize(m.n_);
-            for (size_t i = 0; i < m.n_; ++i) m.sizes_[i] = (uint32_t)v[i]->size();
-            m.sim_.resize(m.n_ * m.n_);
-            KmerEngine::checkMulti(mh, kr_multi_sim_matrix(mh, f.data(), f.off.data(), f.count(), nullptr, nullptr, 0, KR_ELEM_I32, KR_LAYOUT_FULL, m.sim_.data()));
-            return m;
-        }
-        // gather into one set if the objects come from different batches
-        std::shared_ptr<SetHandle> h = v[0]->handle();
-        bool same = true;
-        for (size_t i = 0; i < v.size(); ++i) same = same && v[i]->handle() == h && v[i]->index() == i;
-        if (!same) { std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getSequence()); h = encodeStrings(v[0]->k(), s); }
+        std::vector<uint32_t> cells;
+        uint64_t count = 0, cap = std::max<uint64_t>(4096, 16 * (uint64_t)m.n_);
         m.sizes_.resize(m.n_);
-        KmerEngine::check(h->ctx, kr_seqset_sizes(h->set, m.sizes_.data()));
-        m.sim_.resize(m.n_ * m.n_);
-        kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_FULL, 0, (uint32_t)m.n_};
-        KmerEngine::check(h->ctx, kr_sim_matrix(h->ctx, h->set, nullptr, &d, m.sim_.data()));
+        m.diag_.resize(m.n_);
+        std::shared_ptr<SetHandle> h;
+        kr_multi *mh = edited ? nullptr : KmerEngine::multi(v[0]->k());
+        FlatSeqs f;
+        if (mh) {      // every listed GPU scans a row stripe
+            for (auto p : v) f.add(p->getSequence());
+            for (size_t i = 0; i < m.n_; ++i) m.sizes_[i] = (uint32_t)v[i]->size();
+        } else {       // one set holding exactly these objects (gathered / re-encoded if they come from different batches)
+            h = v[0]->handle();
+            bool same = true;
+            for (size_t i = 0; i < v.size(); ++i) same = same && v[i]->handle() == h && v[i]->index() == i;
+            if (!same || kr_seqset_count(h->set) != m.n_) {
+                if (edited) throw std::runtime_error("SimilarityMatrix: objects edited by retainAll / removeAll must come from one batch");
+                std::vector<const std::string *> s; for (auto p : v) s.push_back(&p->getSequence()); h = encodeStrings(v[0]->k(), s);
+            }
+            KmerEngine::check(h->ctx, kr_seqset_sizes(h->set, m.sizes_.data()));
+        }
+        for (;;) {     // the library reports how many cells qualify when the room was too small: once more with room for all
+            cells.resize((size_t)cap * 4);
+            kr_status st;
+            if (mh) st = kr_multi_sim_matrix_sparse(mh, f.data(), f.off.data(), f.count(), nullptr, nullptr, 0, 1, KR_LAYOUT_TRIANGLE, cells.data(), cap, &count);
+            else { kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_TRIANGLE, 0, (uint32_t)m.n_}; st = kr_sim_matrix_sparse(h->ctx, h->set, nullptr, &d, 1, cells.data(), cap, &count); }
+            if (st != KR_OK && count > cap) { cap = count; continue; }
+            if (mh) KmerEngine::checkMulti(mh, st); else KmerEngine::check(h->ctx, st);
+            break;
+        }
+        // an object and itself (INFINITY under the equal-sequence rule, else its size): one launch of explicit pairs
+        {
+            std::vector<uint32_t> idx(m.n_);
+            for (size_t i = 0; i < m.n_; ++i) idx[i] = (uint32_t)i;
+            if (mh) { for (size_t i = 0; i < m.n_; ++i) m.diag_[i] = v[i]->similarity(*v[i]); }
+            else KmerEngine::check(h->ctx, kr_sim_pairs(h->ctx, h->set, idx.data(), h->set, idx.data(), m.n_, m.diag_.data(), nullptr));
+        }
+        // CSR over the rows of the strict upper triangle, columns ascending
+        m.start_.assign(m.n_ + 1, 0);
+        for (uint64_t k = 0; k < count; ++k) m.start_[cells[4 * k] + 1]++;
+        for (size_t i = 0; i < m.n_; ++i) m.start_[i + 1] += m.start_[i];
+        m.col_.resize(count); m.val_.resize(count);
+        std::vector<uint64_t> at(m.start_.begin(), m.start_.end() - 1);
+        for (uint64_t k = 0; k < count; ++k) { const uint64_t p = at[cells[4 * k]]++; m.col_[p] = cells[4 * k + 1]; m.val_[p] = (int32_t)cells[4 * k + 2]; }
+        for (size_t i = 0; i < m.n_; ++i) {      // cells arrive in no particular order: sort each row by column
+            const uint64_t a = m.start_[i], b = m.start_[i + 1];
+            if (b - a < 2) continue;
+            std::vector<std::pair<uint32_t, int32_t>> row;
+            for (uint64_t p = a; p < b; ++p) row.emplace_back(m.col_[p], m.val_[p]);
+            std::sort(row.begin(), row.end());
+            for (uint64_t p = a; p < b; ++p) { m.col_[p] = row[p - a].first; m.val_[p] = row[p - a].second; }
+        }
         return m;
     }
-    int similarity(size_t i, size_t j) const { return sim_[i * n_ + j]; }
-    double distance(size_t i, size_t j) const { return kr_distance(sim_[i * n_ + j], sizes_[i], sizes_[j]); }
+    int similarity(size_t i, size_t j) const {
+        if (i == j) return diag_[i];
+        if (i > j) std::swap(i, j);
+        const uint32_t *lo = col_.data() + start_[i], *hi = col_.data() + start_[i + 1];
+        const uint32_t *p = std::lower_bound(lo, hi, (uint32_t)j);
+        return (p != hi && *p == j) ? val_[p - col_.data()] : 0;
+    }
+    double distance(size_t i, size_t j) const { return kr_distance(similarity(i, j), sizes_[i], sizes_[j]); }
     size_t size() const { return n_; }
+    uint64_t cells() const { return col_.size(); }      // pairs that share at least one k-mer
   private:
     static const SequenceKmers &ref(const SequenceKmers &p) { return p; }
     static const SequenceKmers &ref(const SequenceKmers *p) { return *p; }
     template <class T> static const SequenceKmers &ref(const std::unique_ptr<T> &p) { return *p; }
     size_t n_ = 0;
-    std::vector<int32_t> sim_;
+    std::vector<uint64_t> start_;
+    std::vector<uint32_t> col_;
+    std::vector<int32_t> val_, diag_;
     std::vector<uint32_t> sizes_;
 };
 
