@@ -62,6 +62,14 @@ def test_findclosest_line(emul_lib):
     assert d["cpu_baseline"]["unit"] == "queries/s" and d["cpu_baseline_build"]["gpu_same_prefix"]["identical_result"] is True
 
 
+def test_findclosest_two_ranks(emul_lib):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    d = run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+             "bench.py", "--gpus", "2", "--workload", "findclosest", "--ncand", "1200", "--nq", "601", "--nrep", "250", "--q-chunk", "200", "--steps", "1",
+             "--warmup", "1"], emul_lib, KR_EMUL_DEVICES="2")
+    assert d["n_gpus"] == 2 and d["result_allgather_ms"] is not None and d["cpu_baseline"] is None and d["roofline"]["kernel"] == "k_ix_query<ARGMAX>"
+
+
 def test_reference_arm():
     p = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--nseq", "3000", "--ref-sample", "400"], cwd=ROOT,
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
