@@ -393,25 +393,57 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
     CU(cudaSetDevice(ctx->dev));
     const int K = ctx->K;
     u64 total = nseq ? offsets[nseq] - offsets[0] : 0;
+    if (nseq && offsets[nseq] < offsets[0]) return fail(ctx, KR_ERR_ARG, "kr_encode: offsets not monotone");
     if (total && !residues) return fail(ctx, KR_ERR_ARG, "kr_encode: null residues");
+    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
+    s->ctx = ctx; s->n = nseq;
+    s->res = std::make_shared<DevMem>();
+    s->res->stream = ctx->stream;
+    CU(pool_alloc(ctx, &s->res->p, total + 16));
+    // Host batches of a few MB and more are encoded as a pipeline: the residues travel in ENC_PIPE pieces (cut at sequence
+    // boundaries) on the copy stream, and the encoder of piece c starts as soon as piece c has arrived, while the later
+    // pieces are still on the bus -- and while the host is still walking the offsets below.
+    constexpr u32 ENC_PIPE = 4;
+#ifndef KR_ENC_PIPE_MIN
+#define KR_ENC_PIPE_MIN (4u << 20)      // bytes of residues from which the pipeline pays (the tests build a variant that always pipelines)
+#endif
+    const bool piped = !on_device && total >= KR_ENC_PIPE_MIN && nseq >= ENC_PIPE;
+    u32 cut[ENC_PIPE + 1];
+    cudaEvent_t ev_piece[ENC_PIPE];
+    for (u32 c = 0; c <= ENC_PIPE; ++c) cut[c] = (u32)((u64)nseq * c / ENC_PIPE);
+    if (on_device) CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyDeviceToDevice, ctx->stream));
+    else if (!piped) { CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream)); ctx->st.h2d_bytes += total; }
+    else {
+        cudaEvent_t ev_alloc = get_event(ctx);
+        CU(cudaEventRecord(ev_alloc, ctx->stream));                     // the residue buffer exists (stream-ordered allocation)
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ev_alloc, 0));
+        ctx->ev_pool.push_back(ev_alloc);
+        for (u32 c = 0; c < ENC_PIPE; ++c) {
+            const u64 b0 = offsets[cut[c]] - offsets[0], b1 = offsets[cut[c + 1]] - offsets[0];
+            // (pieces of an offset table that is not monotone are not copied; the walk below reports it)
+            if (b1 > b0 && b1 <= total) CU(cudaMemcpyAsync((u8 *)s->res->p + b0, residues + offsets[0] + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ev_piece[c] = get_event(ctx);
+            CU(cudaEventRecord(ev_piece[c], ctx->copy_stream));
+        }
+        ctx->st.h2d_bytes += total;
+    }
     std::vector<u64> off(nseq + 1), koff(nseq + 1);
     u64 kc = 0; u32 maxn = 0;
-    for (u32 i = 0; i < nseq; ++i) {
-        if (offsets[i + 1] < offsets[i]) return fail(ctx, KR_ERR_ARG, "kr_encode: offsets not monotone at %u", i);
+    kr_status bad = KR_OK;
+    for (u32 i = 0; i < nseq && bad == KR_OK; ++i) {
+        if (offsets[i + 1] < offsets[i]) { bad = fail(ctx, KR_ERR_ARG, "kr_encode: offsets not monotone at %u", i); break; }
         u64 L = offsets[i + 1] - offsets[i];
-        if (kmer_slots(ctx, L) > 65535u) return fail(ctx, KR_ERR_ARG, "kr_encode: sequence %u has %llu residues; at most 65535 k-mers per sequence are supported", i, (unsigned long long)L);
+        if (kmer_slots(ctx, L) > 65535u) { bad = fail(ctx, KR_ERR_ARG, "kr_encode: sequence %u has %llu residues; at most 65535 k-mers per sequence are supported", i, (unsigned long long)L); break; }
         off[i] = offsets[i] - offsets[0]; koff[i] = kc;
         u32 n = (u32)kmer_slots(ctx, L);
         kc += n; maxn = std::max(maxn, n);
     }
+    if (bad != KR_OK) {     // copies already queued on the copy stream must have landed before the buffer is released
+        if (piped) { cudaStreamSynchronize(ctx->copy_stream); for (u32 c = 0; c < ENC_PIPE; ++c) ctx->ev_pool.push_back(ev_piece[c]); }
+        return bad;
+    }
     off[nseq] = total; koff[nseq] = kc;
-    std::unique_ptr<kr_seqset, void (*)(kr_seqset *)> s(new kr_seqset(), seqset_destroy);
-    s->ctx = ctx; s->n = nseq; s->key_cap = kc;
-    s->res = std::make_shared<DevMem>();
-    s->res->stream = ctx->stream;
-    CU(pool_alloc(ctx, &s->res->p, total + 16));
-    if (on_device) CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyDeviceToDevice, ctx->stream));
-    else { CU(cudaMemcpyAsync(s->res->p, residues + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream)); ctx->st.h2d_bytes += total; }
+    s->key_cap = kc;
     CU(dalloc(ctx, &s->d_off, nseq + 1)); CU(dalloc(ctx, &s->d_koff, nseq + 1));
     CU(dalloc(ctx, &s->d_keys, kc + 16)); CU(dalloc(ctx, &s->d_meta, nseq));
     CU(cudaMemcpyAsync(s->d_off, off.data(), (nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -419,15 +451,20 @@ static kr_status encode_impl(kr_ctx *ctx, const u8 *residues, bool on_device, co
     ctx->st.h2d_bytes += 2ull * (nseq + 1) * 8;
     if (nseq) {
         StageTimer t(ctx, ST_ENCODE);
-        EncodeParams p;
-        p.res = (const u8 *)s->res->p; p.off = s->d_off; p.koff = s->d_koff; p.keys = s->d_keys; p.meta = s->d_meta;
-        p.err = ctx->d_err; p.nseq = nseq; p.K = K; p.smem_cap = 0;
         // one warp per sequence, keys sorted in registers; the 16-keys-per-lane build serves every batch whose longest
         // sequence has at most 512 k-mers (seed proteins), the 32-keys-per-lane build the others
-        const u32 grid = (nseq + ENC2_WARPS - 1) / ENC2_WARPS;
-        if (maxn <= 512) KR_LAUNCH(KR_T(k_encode_sort_warp<16>), grid, ENC2_WARPS * 32, 0, ctx->stream, p);
-        else KR_LAUNCH(KR_T(k_encode_sort_warp<32>), grid, ENC2_WARPS * 32, 0, ctx->stream, p);
-        LAUNCHED(ctx);
+        for (u32 c = 0; c < (piped ? ENC_PIPE : 1u); ++c) {
+            const u32 s0 = piped ? cut[c] : 0, s1 = piped ? cut[c + 1] : nseq;
+            if (piped) { CU(cudaStreamWaitEvent(ctx->stream, ev_piece[c], 0)); ctx->ev_pool.push_back(ev_piece[c]); }   // piece c has arrived
+            if (s1 == s0) continue;
+            EncodeParams p;
+            p.res = (const u8 *)s->res->p; p.off = s->d_off + s0; p.koff = s->d_koff + s0; p.keys = s->d_keys; p.meta = s->d_meta + s0;
+            p.err = ctx->d_err; p.nseq = s1 - s0; p.K = K; p.seq_base = s0;
+            const u32 grid = (s1 - s0 + ENC2_WARPS - 1) / ENC2_WARPS;
+            if (maxn <= 512) KR_LAUNCH(KR_T(k_encode_sort_warp<16>), grid, ENC2_WARPS * 32, 0, ctx->stream, p);
+            else KR_LAUNCH(KR_T(k_encode_sort_warp<32>), grid, ENC2_WARPS * 32, 0, ctx->stream, p);
+            LAUNCHED(ctx);
+        }
         CU(cudaGetLastError());
     }
     if (on_device) {   // "_device" calls do not synchronise the host: the flag is read at the next call that does

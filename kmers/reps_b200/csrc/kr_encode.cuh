@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(ENC2_WARPS * 32) k_encode_sort_warp(EncodePara
     for (u32 i = lane; i < L; i += 32) {
         const u32 c = r[i];
         const u32 code = residue_code(c);
-        if (code == 0xFFu && atomicCAS(&p.err->flag, 0u, 1u) == 0u) { p.err->seq = s; p.err->pos = i; p.err->byte = c; }
+        if (code == 0xFFu && atomicCAS(&p.err->flag, 0u, 1u) == 0u) { p.err->seq = p.seq_base + s; p.err->pos = i; p.err->byte = c; }
         if (in_regs) codes[i] = (u8)code;
         h += mix64((((u64)i << 8) | c) + 0x9E3779B97F4A7C15ULL);
     }

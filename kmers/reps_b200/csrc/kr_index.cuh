@@ -174,29 +174,24 @@ __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u
     for (u32 i = tid; i < n; i += IX_SORT_THREADS) g[i] = sk[i];
 }
 
-// K4.5: the directory.  Entry i opens every D-bit prefix after its predecessor's up to its own; the last entry also
-// closes the prefixes above it.  An empty index is all zeros (memset by the host).
-__global__ void __launch_bounds__(256) k_ix_dir(const u64 *ent, const u32 *total, int dshift, u32 ndir, u32 *dir) {
+// K4.5: the directory and the posting-list statistics, one thread per entry (one pass over the sorted entries).
+// Directory: entry i opens every D-bit prefix after its predecessor's up to its own; the last entry also closes the
+// prefixes above it.  An empty index is all zeros (memset by the host).
+// Statistics (run starts only): out[0] += sum over the posting lists of m^2 (the postings a self scan walks: every entry
+// walks its own list), out[1] = longest list, out[2] = number of entries, out[3] += number of distinct keys.
+__global__ void __launch_bounds__(256) k_ix_dir(const u64 *ent, const u32 *total, int dshift, u32 ndir, u32 *dir, int idbits, unsigned long long *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 n = *total;      // the number of entries is only known on the device (sum of the distinct-k-mer counts)
-    if (i >= n) return;
-    const u32 d = (u32)(ent[i] >> dshift);
-    const u32 first = i ? (u32)(ent[i - 1] >> dshift) + 1 : 0;
-    for (u32 b = first; b <= d; ++b) dir[b] = i;
-    if (i == n - 1) for (u32 b = d + 1; b <= ndir; ++b) dir[b] = n;
-}
-
-// sum over the posting lists of m^2 (work of a self scan: every entry walks its own list) and the longest list;
-// one thread per entry, run starts only.  out[0] += sum m^2, out[1] = max m, out[2] = number of entries,
-// out[3] += number of distinct keys
-__global__ void __launch_bounds__(256) k_ix_work(const u64 *ent, const u32 *total, int idbits, unsigned long long *out) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 n = *total;
     if (i == 0) out[2] = n;
     unsigned long long w = 0, mx = 0, runs = 0;
     if (i < n) {
-        const u64 hk = ent[i] >> idbits;
-        if (i == 0 || (ent[i - 1] >> idbits) != hk) {
+        const u64 e = ent[i], prev = i ? ent[i - 1] : 0;
+        const u32 d = (u32)(e >> dshift);
+        const u32 first = i ? (u32)(prev >> dshift) + 1 : 0;
+        for (u32 b = first; b <= d; ++b) dir[b] = i;
+        if (i == n - 1) for (u32 b = d + 1; b <= ndir; ++b) dir[b] = n;
+        const u64 hk = e >> idbits;
+        if (i == 0 || (prev >> idbits) != hk) {
             u32 m = 1;
             while (i + m < n && (ent[i + m] >> idbits) == hk) ++m;
             w = (unsigned long long)m * m; mx = m; runs = 1;

@@ -141,7 +141,7 @@ __device__ void bitonic_sort(u64 *d, u32 n, u32 tid, u32 nthr) {
 struct EncodeParams {
     const u8 *res; const u64 *off; const u64 *koff;
     u64 *keys; SeqMeta *meta; ErrInfo *err;
-    u32 nseq; int K; u32 smem_cap;
+    u32 nseq; int K; u32 seq_base;     // sequences [0, nseq) of this launch are sequences seq_base + s of the batch (error reports)
 };
 
 // residue byte -> 5-bit code without a table: 'A'..'Z' -> 0..25, '*' -> 26, '-' -> 27, anything else 0xFF

@@ -228,6 +228,15 @@ def case_encode_warp():
         raise AssertionError("a residue outside the alphabet must fail")
     except kr.KrError as e:
         assert e.code == -4 and "sequence 1 position 5" in str(e)
+    try:      # in a later piece of a pipelined host encode the sequence number is still the batch's
+        c.encode(["MKVLAAGIVG"] * 7 + ["MKVLAbGIVGAAAA", "MKV"])
+        raise AssertionError("a residue outside the alphabet must fail")
+    except kr.KrError as e:
+        assert e.code == -4 and "sequence 7 position 5" in str(e)
+    bad = np.array([0, 10, 5, 20], dtype=np.uint64)                                # offsets that go backwards
+    h = kr.binding.C.c_void_p()
+    assert c.lib.kr_encode(c.h, np.zeros(32, np.uint8).ctypes.data, bad.ctypes.data, 3, kr.binding.C.byref(h)) == -1
+    assert list(c.encode(["MKVLAAGIVG"] * 5).sizes()) == [3] * 5                  # the context is still usable
     c.close()
 
 

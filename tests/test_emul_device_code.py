@@ -70,6 +70,17 @@ def test_index_overflow_passes_on_the_emulator(emul_lib):
         assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]
 
 
+def test_pipelined_host_encode_on_the_emulator(emul_lib):
+    """kr_encode of a host batch in four pieces (copy stream + per-piece encoder launches): a build whose threshold is 256 bytes
+    takes that path for every batch of the ordinary cases -- sizes, keys, the alphabet error's sequence number, matrices"""
+    lib = build_variant("libkmersreps_emul_pipe.so", "-DKR_ENC_PIPE_MIN=256")
+    for case in ("encode_warp", "api_misc", "matrix_layouts"):
+        env = dict(os.environ, KR_LIB_PATH=lib, KR_EMUL_SMS="2")
+        p = subprocess.run([sys.executable, os.path.join(EMUL, "run_emul_checks.py"), case], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           timeout=1500)
+        assert p.returncode == 0 and p.stdout.decode().strip().endswith("OK " + case), p.stdout.decode()[-3000:]
+
+
 @pytest.mark.parametrize("case", ["matrix_layouts", "k10_rectangular_pairs", "find_closest_and_build", "subchunks", "sharded_import", "api_misc",
                                   "sparse_matrix", "index_crowded", "encode_warp", "set_ops"])
 def test_device_code_on_the_emulator(emul_lib, case):
