@@ -1235,6 +1235,8 @@ kr_status kr_sim_matrix_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
     kr_status st = check_desc(ctx, A, B, desc);
     if (st) return st;
     if (!out_dev) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_device: null output");
+    // a misaligned store is a device fault, not an error code: refuse the pointer here
+    if (reinterpret_cast<uintptr_t>(out_dev) & (desc->elem == KR_ELEM_U16 ? 1 : 3)) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_device: output is not aligned to its element size");
     CU(cudaSetDevice(ctx->dev));
     bool self = (B == nullptr || B == A);
     return matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, out_dev);
@@ -1333,6 +1335,7 @@ kr_status kr_sim_matrix_sparse_device(kr_ctx *ctx, const kr_seqset *A, const kr_
                                       void *cells_dev, uint64_t cap, uint64_t *count) {
     if (!ctx) return KR_ERR_ARG;
     if (!cells_dev && cap) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse_device: null output");
+    if (reinterpret_cast<uintptr_t>(cells_dev) & 15) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse_device: cells must be 16-byte aligned (one 16-byte store per cell)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     return sparse_impl(ctx, A, B, desc, min_sim, nullptr, cap, count, cells_dev);
 }
@@ -1395,6 +1398,8 @@ kr_status kr_db_find_closest_device(kr_ctx *ctx, const kr_db *db, const kr_seqse
                                     uint32_t *d_best_first, uint32_t *d_best_last) {
     if (!ctx || !db || !queries || !d_best_sim) return fail(ctx, KR_ERR_ARG, "kr_db_find_closest: null argument");
     if (db->ctx != ctx || queries->ctx != ctx) return fail(ctx, KR_ERR_STATE, "kr_db_find_closest: handle belongs to another context");
+    if ((reinterpret_cast<uintptr_t>(d_best_sim) | reinterpret_cast<uintptr_t>(d_best_first) | reinterpret_cast<uintptr_t>(d_best_last)) & 3)
+        return fail(ctx, KR_ERR_ARG, "kr_db_find_closest_device: outputs must be 4-byte aligned");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->dev));
     return find_closest_launch(ctx, const_cast<kr_db *>(db), const_cast<kr_seqset *>(queries), d_best_sim, d_best_first, d_best_last);

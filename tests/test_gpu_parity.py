@@ -225,6 +225,22 @@ def test_error_paths():
     with pytest.raises(kr.KrError):
         other.sim_matrix(s)
     other.close()
+    # device-pointer entry points refuse pointers their stores could not take (a misaligned store is a device fault, not a status)
+    import torch
+    buf = torch.zeros(4096, dtype=torch.uint8, device=DEV)
+    dsync()
+    base = buf.data_ptr()
+    with pytest.raises(kr.KrError):
+        c.sim_matrix_sparse_device(s, None, base + 8, 16)
+    with pytest.raises(kr.KrError):
+        c.sim_matrix_device(s, None, base + 1, elem=kr.ELEM_U16)
+    with pytest.raises(kr.KrError):
+        c.sim_matrix_device(s, None, base + 2, elem=kr.ELEM_I32)
+    db = c.db(); db.append(["ACDEFGHIKLMN"])
+    with pytest.raises(kr.KrError):
+        db.find_closest_device(s, base + 2)
+    c.sim_matrix_device(s, None, base + 2, elem=kr.ELEM_U16)          # element-aligned is enough for a dense result
+    c.synchronize()
     c.close()
 
 
