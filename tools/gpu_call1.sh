@@ -13,7 +13,7 @@ tail -3 gpurun_out/c1_memcheck_smoke.log
 
 stage "2. memcheck: N-shard import on one GPU + reference fixtures (small)"
 timeout 1200 $CS --tool memcheck --error-exitcode 86 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cacheprovider \
-    -k "shard_import or kat_k10 or vapb_matrix or config1_find_closest or sets_from_key_lists or (multi_handle and index)" > gpurun_out/c1_memcheck_tests.log 2>&1 || fail memcheck-tests gpurun_out/c1_memcheck_tests.log
+    -k "shard_import or kat_k10 or vapb_matrix or config1_find_closest or sets_from_key_lists or error_paths or (multi_handle and index)" > gpurun_out/c1_memcheck_tests.log 2>&1 || fail memcheck-tests gpurun_out/c1_memcheck_tests.log
 tail -3 gpurun_out/c1_memcheck_tests.log
 
 stage "3. the whole GPU suite, default library, no tool"
