@@ -11,7 +11,7 @@ collective).  A step = one pass of the hot path over the batch:
 (the library picks the index scan for this family-structured batch from the index's posting-list statistics;
 --path join pins the tile join, the path of dense collections).
 `value` = pairs (i<j) per second over all ranks, device time (CUDA events on the library's stream), max over
-ranks.  `e2e` = the same through the host-buffer C ABI a caller uses (kr_encode + kr_sim_matrix_sparse): H2D of
+ranks.  `e2e` = the same through the host-buffer C ABI a caller uses (kr_encode + kr_sim_matrix_sparse64): H2D of
 the residues and D2H of this rank's result inside the timed region, the result being the cells with sim >= 1 (all
 other cells are 0 by definition); `e2e_dense` moves the dense stripe instead (kr_sim_matrix).
 
@@ -556,7 +556,7 @@ def main():
         h_res = ctx.host_alloc(max(len(res), 1))
         h_res[: len(res)] = res
         cap = 1 << 23
-        h_cells = ctx.host_alloc(cap * 16, dtype=np.uint32).reshape(cap, 4)
+        h_cells = ctx.host_alloc(cap * 8, dtype=np.uint64)          # packed cells: row << 40 | col << 16 | sim
         ncell = [0]
 
         def timed(fn):
@@ -574,13 +574,22 @@ def main():
 
         def sparse_step():
             s = ctx.encode(res=h_res[: len(res)], off=off)
-            ncell[0] = len(ctx.sim_matrix_sparse(s, None, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1, out=h_cells))
+            ncell[0] = len(ctx.sim_matrix_sparse64(s, None, min_sim=1, layout=kr.LAYOUT_TRIANGLE, row_begin=r0, row_end=r1, out=h_cells))
             s.free()
         dt = timed(sparse_step)
         e2e = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(len(res) + 16 * (N + 1)),
-               "d2h_bytes_per_step": int(8 + 16 * ncell[0]), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
+               "d2h_bytes_per_step": int(8 + 8 * ncell[0]), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
                "cells_per_step": ncell[0],
-               "api": "kr_encode + kr_sim_matrix_sparse (pinned host buffers): the cells with sim >= 1 of this rank's rows; every other cell is 0"}
+               "api": "kr_encode + kr_sim_matrix_sparse64 (pinned host buffers): the cells with sim >= 1 of this rank's rows, 8 bytes each; "
+                      "every other cell is 0"}
+        # the e2e result is checked too: every sampled non-zero cell of the device-resident run above is among the cells, with its value
+        rr, cc, vv = kr.unpack_cells(h_cells[: ncell[0]])
+        got_cells = dict(zip(zip(rr.tolist(), cc.tolist()), vv.tolist()))
+        for (i, j), w in zip(zip(ii.tolist(), jj.tolist()), want):
+            if i < j and w > 0 and got_cells.get((i, j)) != w:
+                raise SystemExit("bench: e2e sparse result differs from the oracle at (%d, %d)" % (i, j))
+            if i < j and w == 0 and (i, j) in got_cells:
+                raise SystemExit("bench: e2e sparse result has a cell the oracle does not (%d, %d)" % (i, j))
         del h_cells
         h_out = ctx.host_alloc(my_elems * esz, dtype=np.uint16 if esz == 2 else np.int32)
 

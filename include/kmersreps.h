@@ -195,6 +195,15 @@ kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
  * return the count */
 kr_status kr_sim_matrix_sparse_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
                                       void *cells_dev, uint64_t cap, uint64_t *count);
+/* The same with PACKED cells, 8 bytes each: cell = row << 40 | col << 16 | sim (KR_CELL_ROW / _COL / _SIM).  Half the bytes
+ * over PCIe for callers that fetch millions of cells; both sets must hold at most 2^24 sequences (KR_ERR_ARG otherwise). */
+#define KR_CELL_ROW(c) ((uint32_t)((c) >> 40))
+#define KR_CELL_COL(c) ((uint32_t)(((c) >> 16) & 0xFFFFFFu))
+#define KR_CELL_SIM(c) ((int32_t)((c) & 0xFFFFu))
+kr_status kr_sim_matrix_sparse64(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                                 uint64_t *cells_host, uint64_t cap, uint64_t *count);
+kr_status kr_sim_matrix_sparse64_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc,
+                                        int32_t min_sim, void *cells_dev, uint64_t cap, uint64_t *count);
 
 /* ---- RepGenomeDb ---------------------------------------------------------------------------
  * Replaces the representative store of RepGenomeDb: new RepGenomeDb(threshold, protName)

@@ -60,6 +60,7 @@ public final class KmersRepsNative {
     public static final MethodHandle kr_greedy_build = h("kr_greedy_build", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 
     public static final MethodHandle kr_seqset_from_keys = h("kr_seqset_from_keys", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+    public static final MethodHandle kr_sim_matrix_sparse64 = h("kr_sim_matrix_sparse64", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
     public static final MethodHandle kr_sim_matrix_sparse = h("kr_sim_matrix_sparse", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
     // several GPUs behind one handle (include/kmersreps.h, last section): -Dkmersreps.devices=0,1,2,3
     public static final MethodHandle kr_multi_create = h("kr_multi_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
@@ -303,14 +304,23 @@ public final class KmersRepsNative {
                 MemorySegment desc = ar.allocate(JAVA_INT, 4);
                 desc.setAtIndex(JAVA_INT, 0, ELEM_I32); desc.setAtIndex(JAVA_INT, 1, b == null ? LAYOUT_TRIANGLE : LAYOUT_FULL);
                 desc.setAtIndex(JAVA_INT, 2, 0); desc.setAtIndex(JAVA_INT, 3, a.count);
-                MemorySegment cells = ar.allocate(JAVA_INT, 4 * cap), cnt = ar.allocate(JAVA_LONG);
-                int rc = (int) kr_sim_matrix_sparse.invokeExact(a.ctx, a.handle, b == null ? MemorySegment.NULL : b.handle, desc, minSim, cells, cap, cnt);
+                // packed cells (8 bytes: row << 40 | col << 16 | sim) when both sets have at most 2^24 sequences, else 16-byte cells
+                boolean packed = a.count <= (1 << 24) && (b == null || b.count <= (1 << 24));
+                MemorySegment cells = ar.allocate(JAVA_LONG, (packed ? 1 : 2) * cap), cnt = ar.allocate(JAVA_LONG);
+                MemorySegment bh = b == null ? MemorySegment.NULL : b.handle;
+                int rc = packed ? (int) kr_sim_matrix_sparse64.invokeExact(a.ctx, a.handle, bh, desc, minSim, cells, cap, cnt)
+                                : (int) kr_sim_matrix_sparse.invokeExact(a.ctx, a.handle, bh, desc, minSim, cells, cap, cnt);
                 long n = cnt.get(JAVA_LONG, 0);
                 if (rc != 0 && n > cap) { cap = n; continue; }      // the library told how many cells qualify: once more with room
                 check(a.ctx, rc);
                 int[] out = new int[(int) (3 * n)];
-                for (long k = 0; k < n; k++)
-                    for (int f = 0; f < 3; f++) out[(int) (3 * k + f)] = cells.getAtIndex(JAVA_INT, 4 * k + f);
+                for (long k = 0; k < n; k++) {
+                    if (packed) {
+                        long c = cells.getAtIndex(JAVA_LONG, k);
+                        out[(int) (3 * k)] = (int) (c >>> 40); out[(int) (3 * k + 1)] = (int) ((c >>> 16) & 0xFFFFFF); out[(int) (3 * k + 2)] = (int) (c & 0xFFFF);
+                    } else
+                        for (int f = 0; f < 3; f++) out[(int) (3 * k + f)] = cells.getAtIndex(JAVA_INT, 4 * k + f);
+                }
                 return out;
             } catch (RuntimeException e) {
                 throw e;

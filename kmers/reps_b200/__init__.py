@@ -9,5 +9,5 @@ library or without a CUDA device raises.
 from .binding import (  # noqa: F401
     INFINITY, NO_REP, IDENT_IS_INFINITY, TIE_LAST, FORCE_JOIN, FORCE_INDEX, ELEM_I32, ELEM_U16, LAYOUT_FULL, LAYOUT_TRIANGLE,
     LAYOUT_BLOCKTRI, TILE, Context, SeqSet, RepDb, KrError, BlockLists, lib_path, load_library, distance,
-    matrix_elems, matrix_stripes, flat, MultiContext, MultiDb,
+    matrix_elems, matrix_stripes, flat, MultiContext, MultiDb, unpack_cells,
 )

@@ -22,7 +22,7 @@ SYMBOLS = [
     "kr_create", "kr_destroy", "kr_last_error", "kr_kmer_size", "kr_build_info", "kr_synchronize", "kr_encode", "kr_encode_device",
     "kr_seqset_free", "kr_seqset_count", "kr_seqset_export_blocklists", "kr_seqset_import_blocklists", "kr_blocklist_capacity", "kr_seqset_sizes", "kr_seqset_keys", "kr_key_decode", "kr_seqset_gather", "kr_seqset_from_keys",
     "kr_sim_pairs", "kr_distance", "kr_matrix_elems", "kr_matrix_stripes", "kr_sim_matrix", "kr_sim_matrix_device",
-    "kr_sim_matrix_sparse", "kr_sim_matrix_sparse_device",
+    "kr_sim_matrix_sparse", "kr_sim_matrix_sparse_device", "kr_sim_matrix_sparse64", "kr_sim_matrix_sparse64_device",
     "kr_db_create", "kr_db_free", "kr_db_size", "kr_db_append", "kr_db_append_set", "kr_db_set_ranks",
     "kr_db_find_closest", "kr_db_find_closest_device", "kr_db_any_ge", "kr_greedy_build", "kr_stats_get",
     "kr_stats_reset", "kr_timer_begin", "kr_timer_end", "kr_host_alloc", "kr_host_free",
@@ -137,6 +137,8 @@ def load_library():
     lib.kr_host_free.restype = None
     lib.kr_sim_matrix_sparse.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
     lib.kr_sim_matrix_sparse_device.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
+    lib.kr_sim_matrix_sparse64.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
+    lib.kr_sim_matrix_sparse64_device.argtypes = [vp, vp, vp, C.POINTER(MatrixDesc), i32, vp, u64, C.POINTER(u64)]
     lib.kr_multi_create.argtypes = [vp, C.c_int, C.c_int, u32, C.POINTER(vp)]
     lib.kr_multi_destroy.argtypes = [vp]
     lib.kr_multi_destroy.restype = None
@@ -319,6 +321,27 @@ class Context:
                 self._ck(rc)
             cap = int(n.value)                     # the library reported how many cells qualify: retry with room
 
+    def sim_matrix_sparse64(self, A: "SeqSet", B: "SeqSet" = None, min_sim=1, layout=LAYOUT_TRIANGLE, row_begin=0, row_end=None, cap=1 << 22, out=None):
+        """the same cells packed into one uint64 each (row << 40 | col << 16 | sim), as a uint64 array; unpack_cells() splits them"""
+        row_end = A.count if row_end is None else row_end
+        d = MatrixDesc(ELEM_I32, layout, row_begin, row_end)
+        while True:
+            cells = out if out is not None else np.zeros(cap, dtype=np.uint64)
+            n = C.c_uint64(0)
+            rc = self.lib.kr_sim_matrix_sparse64(self.h, A.h, None if B is None else B.h, C.byref(d), int(min_sim), cells.ctypes.data, len(cells), C.byref(n))
+            if rc == 0:
+                return cells[: n.value]
+            if n.value <= len(cells) or out is not None:
+                self._ck(rc)
+            cap = int(n.value)
+
+    def sim_matrix_sparse64_device(self, A: "SeqSet", B, d_cells_ptr: int, cap: int, min_sim=1, layout=LAYOUT_TRIANGLE, row_begin=0, row_end=None) -> int:
+        row_end = A.count if row_end is None else row_end
+        d = MatrixDesc(ELEM_I32, layout, row_begin, row_end)
+        n = C.c_uint64(0)
+        self._ck(self.lib.kr_sim_matrix_sparse64_device(self.h, A.h, None if B is None else B.h, C.byref(d), int(min_sim), d_cells_ptr, int(cap), C.byref(n)))
+        return int(n.value)
+
     def sim_matrix_sparse_device(self, A: "SeqSet", B, d_cells_ptr: int, cap: int, min_sim=1, layout=LAYOUT_TRIANGLE, row_begin=0, row_end=None) -> int:
         """same, cells left in device memory (16 bytes each); returns how many qualify"""
         row_end = A.count if row_end is None else row_end
@@ -459,6 +482,12 @@ class RepDb:
         added = np.zeros(cands.count, dtype=np.uint8)
         self.ctx._ck(self.ctx.lib.kr_greedy_build(self.ctx.h, self.h, cands.h, threshold, batch, added.ctypes.data))
         return added
+
+
+def unpack_cells(cells64):
+    """packed cells (kr_sim_matrix_sparse64) -> (row, col, sim) uint32 arrays"""
+    c = np.asarray(cells64, dtype=np.uint64)
+    return (c >> np.uint64(40)).astype(np.uint32), ((c >> np.uint64(16)) & np.uint64(0xFFFFFF)).astype(np.uint32), (c & np.uint64(0xFFFF)).astype(np.uint32)
 
 
 def _flat_args(seqs, res, off):

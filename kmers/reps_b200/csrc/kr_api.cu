@@ -569,7 +569,7 @@ static u64 row_start(u32 layout, u64 r, u64 nrows, u64 ncols) {
     return 256ull * (I * nrows - 128ull * I * (I - 1)) + (r - c0) * (nrows - c0);
 }
 
-struct SparseSink { uint4 *cells; unsigned long long cap; unsigned long long *count; u32 min_sim; };
+struct SparseSink { uint4 *cells; unsigned long long cap; unsigned long long *count; u32 min_sim; bool packed; };
 
 
 static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool self, const kr_matrix_desc *d, void *out_dev,
@@ -607,7 +607,7 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
         if (st) return st;
         if (use_index && rows) {
             MatrixTarget tg;
-            if (sparse) { tg.cells = sparse->cells; tg.cells_cap = sparse->cap; tg.cells_count = sparse->count; tg.min_sim = sparse->min_sim; }
+            if (sparse) { tg.cells = sparse->cells; tg.cells_cap = sparse->cap; tg.cells_count = sparse->count; tg.min_sim = sparse->min_sim; tg.packed = sparse->packed; }
             else {
                 tg.out = out_dev; tg.elem = d->elem; tg.layout = d->layout; tg.origin = row_start(d->layout, d->row_begin, A->n, Bx->n); tg.min_sim = 1;
                 // (the scan leaves every cell of its rows written: zeros -- by the fill above, or else row by row by the warp
@@ -654,7 +654,7 @@ static kr_status matrix_launch(kr_ctx *ctx, kr_seqset *A, kr_seqset *B, bool sel
         StageTimer t(ctx, ST_JOIN);
         u32 grid = std::min<u32>(p.ntasks, (u32)ctx->num_sms);
         if (sparse) {   // the join's epilogue keeps only the cells that reach min_sim
-            p.cells = sparse->cells; p.cells_cap = sparse->cap; p.cells_count = sparse->count; p.min_sim = sparse->min_sim;
+            p.cells = sparse->cells; p.cells_cap = sparse->cap; p.cells_count = sparse->count; p.min_sim = sparse->min_sim; p.cells_packed = sparse->packed ? 1u : 0u;
             if (lo_bits(ctx->K) <= 16) KR_LAUNCH(KR_T(k_join<MODE_SPARSE, false>), grid, JOIN_THREADS, join_smem_bytes(false), ctx->stream, p);
             else KR_LAUNCH(KR_T(k_join<MODE_SPARSE, true>), grid, JOIN_THREADS, join_smem_bytes(true), ctx->stream, p);
         }
@@ -1293,34 +1293,37 @@ kr_status kr_sim_matrix(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, con
 
 // the caller holds the context's lock
 static kr_status sparse_impl(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
-                             uint32_t *cells_host, uint64_t cap, uint64_t *count, void *cells_dev) {
+                             void *cells_host, uint64_t cap, uint64_t *count, void *cells_dev, bool packed = false) {
     kr_status st = check_desc(ctx, A, B, desc);
     if (st) return st;
+    const size_t csz = packed ? 8 : 16;
+    if (packed && (A->n > (1u << 24) || (B ? B->n : A->n) > (1u << 24)))
+        return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse64: packed cells hold row and column numbers below 2^24");
     if (!count || (!cells_host && !cells_dev && cap) || min_sim < 1 || desc->layout == KR_LAYOUT_BLOCKTRI)
         return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: bad argument (min_sim >= 1; layout FULL or TRIANGLE)");
     CU(cudaSetDevice(ctx->dev));
     *count = 0;
     const bool self = (B == nullptr || B == A);
     uint4 *d_cells = reinterpret_cast<uint4 *>(cells_dev); unsigned long long *d_count = nullptr;
-    if (!cells_dev) CU(dalloc(ctx, &d_cells, cap));
+    if (!cells_dev) { u8 *raw = nullptr; CU(dalloc(ctx, &raw, cap * csz + 16)); d_cells = reinterpret_cast<uint4 *>(raw); }
     CU(dalloc(ctx, &d_count, 1));
     CU(cudaMemsetAsync(d_count, 0, 8, ctx->stream));
-    SparseSink sink{d_cells, cap, d_count, (u32)min_sim};
+    SparseSink sink{d_cells, cap, d_count, (u32)min_sim, packed};
     st = matrix_launch(ctx, const_cast<kr_seqset *>(A), const_cast<kr_seqset *>(B), self, desc, d_cells, &sink);
     if (st == KR_OK) {
         unsigned long long n = 0;
         cudaError_t e = cudaMemcpyAsync(&n, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         const unsigned long long take = std::min<unsigned long long>(n, cap);
-        if (e == cudaSuccess && take && cells_host) e = cudaMemcpyAsync(cells_host, d_cells, take * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && take && cells_host) e = cudaMemcpyAsync(cells_host, d_cells, take * csz, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) st = fail(ctx, KR_ERR_CUDA, "sparse matrix copy to host failed: %s", cudaGetErrorString(e));
-        ctx->st.d2h_bytes += 8 + (cells_host ? take * 16 : 0);
+        ctx->st.d2h_bytes += 8 + (cells_host ? take * csz : 0);
         *count = n;
         if (st == KR_OK && ctx->err_pending) st = check_alphabet(ctx);
         if (st == KR_OK && n > cap) st = fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse: %llu cells qualify, room for %llu", n, (unsigned long long)cap);
     }
-    if (!cells_dev) dfree(ctx, d_cells);
+    if (!cells_dev) dfree(ctx, reinterpret_cast<u8 *>(d_cells));
     dfree(ctx, d_count);
     return st;
 }
@@ -1330,6 +1333,20 @@ kr_status kr_sim_matrix_sparse(kr_ctx *ctx, const kr_seqset *A, const kr_seqset 
     if (!ctx) return KR_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     return sparse_impl(ctx, A, B, desc, min_sim, cells_host, cap, count, nullptr);
+}
+kr_status kr_sim_matrix_sparse64(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                                 uint64_t *cells_host, uint64_t cap, uint64_t *count) {
+    if (!ctx) return KR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return sparse_impl(ctx, A, B, desc, min_sim, cells_host, cap, count, nullptr, true);
+}
+kr_status kr_sim_matrix_sparse64_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
+                                        void *cells_dev, uint64_t cap, uint64_t *count) {
+    if (!ctx) return KR_ERR_ARG;
+    if (!cells_dev && cap) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse64_device: null output");
+    if (reinterpret_cast<uintptr_t>(cells_dev) & 7) return fail(ctx, KR_ERR_ARG, "kr_sim_matrix_sparse64_device: cells must be 8-byte aligned");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return sparse_impl(ctx, A, B, desc, min_sim, nullptr, cap, count, cells_dev, true);
 }
 kr_status kr_sim_matrix_sparse_device(kr_ctx *ctx, const kr_seqset *A, const kr_seqset *B, const kr_matrix_desc *desc, int32_t min_sim,
                                       void *cells_dev, uint64_t cap, uint64_t *count) {

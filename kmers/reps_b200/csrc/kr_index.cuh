@@ -238,6 +238,7 @@ struct IxQueryParams {
     u32 col_mode;                  // 0: every column, 1: columns > q (strict triangle), 2: columns >= 256 * (q / 256)
     u32 min_sim;
     uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;      // CELLS: (row, col, sim, 0), any order
+    u32 cells_packed;              // CELLS: 8-byte cells (put_cell)
     void *out; u32 elem, layout; u64 origin; u32 nrows, ncols;                        // DENSE: the result
     u32 prezeroed;                 // DENSE: the rows were already zero-filled (k_zero_fill overlapped with the index build)
 };
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
                                 if (lane == 0) base = atomicAdd(p.cells_count, (unsigned long long)__popc(bal));
                                 base = ((unsigned long long)__shfl_sync(0xffffffffu, (u32)(base >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (u32)base, 0);
                                 const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
-                                if (emit && pos < p.cells_cap) p.cells[pos] = make_uint4(q, id, sc, 0u);
+                                if (emit && pos < p.cells_cap) put_cell(p.cells, p.cells_packed, pos, q, id, sc);
                             }
                         } else {
                             if (t < T && sc >= p.min_sim && id >= col_min && id < p.ncols) {
@@ -431,7 +432,7 @@ struct EmptyPairsParams {
     const SeqMeta *metaA, *metaB;
     u32 row_begin, row_end, col_mode, min_sim;
     void *out; u32 elem, layout; u64 origin; u32 nrows, ncols;
-    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count;
+    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count; u32 cells_packed;
 };
 __global__ void __launch_bounds__(256) k_ix_empty_pairs(EmptyPairsParams p) {
     const u64 na = *p.nrows_e, nb = *p.ncols_e, total = na * nb;
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(256) k_ix_empty_pairs(EmptyPairsParams p) {
             if (p.elem == 1) reinterpret_cast<u16 *>(p.out)[idx] = (u16)KR_INF; else reinterpret_cast<int *>(p.out)[idx] = KR_INF;
         } else {
             const unsigned long long pos = atomicAdd(p.cells_count, 1ull);
-            if (pos < p.cells_cap) p.cells[pos] = make_uint4(i, j, (u32)KR_INF, 0u);
+            if (pos < p.cells_cap) put_cell(p.cells, p.cells_packed, pos, i, j, (u32)KR_INF);
         }
     }
 }

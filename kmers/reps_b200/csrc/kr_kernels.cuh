@@ -411,8 +411,15 @@ struct JoinParams {
     // ARGMAX
     u32 nsplit; const u32 *rankB; int4 *partial;
     // SPARSE: cells (row, col, sim, 0) with sim >= min_sim, appended in no particular order
-    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count; u32 min_sim;
+    uint4 *cells; unsigned long long cells_cap; unsigned long long *cells_count; u32 min_sim; u32 cells_packed;
 };
+
+// one sparse result cell: 16 bytes (row, col, sim, 0) or, packed, one uint64 = row << 40 | col << 16 | sim (rows and columns
+// below 2^24, which the host checks; INFINITY = 9999 and every count <= 65535 fit the low 16 bits)
+__device__ __forceinline__ void put_cell(uint4 *cells, u32 packed, unsigned long long pos, u32 row, u32 col, u32 sim) {
+    if (packed) reinterpret_cast<u64 *>(cells)[pos] = ((u64)row << 40) | ((u64)col << 16) | (u64)sim;
+    else cells[pos] = make_uint4(row, col, sim, 0u);
+}
 
 __device__ __forceinline__ u64 cell_index(u32 layout, u64 i, u64 j, u64 nrows, u64 ncols) {
     if (layout == 0) return i * ncols + j;
@@ -755,7 +762,7 @@ __global__ void __launch_bounds__(JOIN_THREADS, 1) k_join(JoinParams p) {
                     unsigned long long pos = base + incl - c;
 #pragma unroll
                     for (int t = 0; t < 8; ++t)
-                        if ((m >> t) & 1u) { if (pos < p.cells_cap) p.cells[pos] = make_uint4(i, jb + t, (u32)cv[t], 0u); ++pos; }
+                        if ((m >> t) & 1u) { if (pos < p.cells_cap) put_cell(p.cells, p.cells_packed, pos, i, jb + t, (u32)cv[t]); ++pos; }
                 }
             }
             else {

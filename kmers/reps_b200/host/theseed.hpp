@@ -703,7 +703,8 @@ class SimilarityMatrix {
         if (!m.n_) return m;
         bool edited = false;
         for (auto p : v) edited = edited || p->isEdited();
-        std::vector<uint32_t> cells;
+        std::vector<uint32_t> cells;       // kr_multi path: 16-byte cells
+        std::vector<uint64_t> cells64;     // single context: packed 8-byte cells (half the bytes over PCIe)
         uint64_t count = 0, cap = std::max<uint64_t>(4096, 16 * (uint64_t)m.n_);
         m.sizes_.resize(m.n_);
         m.diag_.resize(m.n_);
@@ -724,12 +725,20 @@ class SimilarityMatrix {
             KmerEngine::check(h->ctx, kr_seqset_sizes(h->set, m.sizes_.data()));
         }
         for (;;) {     // the library reports how many cells qualify when the room was too small: once more with room for all
-            cells.resize((size_t)cap * 4);
             kr_status st;
-            if (mh) st = kr_multi_sim_matrix_sparse(mh, f.data(), f.off.data(), f.count(), nullptr, nullptr, 0, 1, KR_LAYOUT_TRIANGLE, cells.data(), cap, &count);
-            else { kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_TRIANGLE, 0, (uint32_t)m.n_}; st = kr_sim_matrix_sparse(h->ctx, h->set, nullptr, &d, 1, cells.data(), cap, &count); }
+            const bool packed = !mh && m.n_ <= (1u << 24);
+            if (mh) { cells.resize((size_t)cap * 4); st = kr_multi_sim_matrix_sparse(mh, f.data(), f.off.data(), f.count(), nullptr, nullptr, 0, 1, KR_LAYOUT_TRIANGLE, cells.data(), cap, &count); }
+            else {
+                kr_matrix_desc d{KR_ELEM_I32, KR_LAYOUT_TRIANGLE, 0, (uint32_t)m.n_};
+                if (packed) { cells64.resize((size_t)cap); st = kr_sim_matrix_sparse64(h->ctx, h->set, nullptr, &d, 1, cells64.data(), cap, &count); }
+                else { cells.resize((size_t)cap * 4); st = kr_sim_matrix_sparse(h->ctx, h->set, nullptr, &d, 1, cells.data(), cap, &count); }
+            }
             if (st != KR_OK && count > cap) { cap = count; continue; }
             if (mh) KmerEngine::checkMulti(mh, st); else KmerEngine::check(h->ctx, st);
+            if (packed) {      // unpack into the (row, col, sim, 0) form the CSR build below reads
+                cells.resize((size_t)count * 4);
+                for (uint64_t k = 0; k < count; ++k) { const uint64_t c = cells64[k]; cells[4 * k] = KR_CELL_ROW(c); cells[4 * k + 1] = KR_CELL_COL(c); cells[4 * k + 2] = (uint32_t)KR_CELL_SIM(c); }
+            }
             break;
         }
         // an object and itself (INFINITY under the equal-sequence rule, else its size): one launch of explicit pairs

@@ -191,6 +191,14 @@ def case_sparse_matrix():
         q = c.encode(seqs[:290])
         got = c.sim_matrix_sparse(q, s, min_sim=10, layout=kr.LAYOUT_FULL, row_begin=256, row_end=290)
         assert cells(got) == want_cells(want[256:290], 10, False, row0=256), path
+        # packed 8-byte cells: the same sets of cells
+        unp = lambda a: {(int(r), int(cc), int(v)) for r, cc, v in zip(*kr.unpack_cells(a))}
+        for min_sim in (1, 20, 9999):
+            got = c.sim_matrix_sparse64(s, min_sim=min_sim, layout=kr.LAYOUT_TRIANGLE)
+            assert len(unp(got)) == len(got) and unp(got) == want_cells(want, min_sim, True), (path, min_sim)
+        assert unp(c.sim_matrix_sparse64(s, min_sim=1, layout=kr.LAYOUT_TRIANGLE, cap=16)) == want_cells(want, 1, True), path
+        got = c.sim_matrix_sparse64(q, s, min_sim=10, layout=kr.LAYOUT_FULL, row_begin=256, row_end=290)
+        assert unp(got) == want_cells(want[256:290], 10, False, row0=256), path
         c.close()
 
 
