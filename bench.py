@@ -591,16 +591,27 @@ def main():
             if i < j and w == 0 and (i, j) in got_cells:
                 raise SystemExit("bench: e2e sparse result has a cell the oracle does not (%d, %d)" % (i, j))
         del h_cells
-        h_out = ctx.host_alloc(my_elems * esz, dtype=np.uint16 if esz == 2 else np.int32)
-
-        def dense_step():
-            s = ctx.encode(res=h_res[: len(res)], off=off)
-            ctx.sim_matrix(s, None, elem=elem, layout=layout, row_begin=r0, row_end=r1, out=h_out)
-            s.free()
-        dt = timed(dense_step)
-        e2e_dense = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(len(res) + 16 * (N + 1)),
-                     "d2h_bytes_per_step": int(my_elems * esz), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
-                     "api": "kr_encode + kr_sim_matrix (pinned host buffers): the dense stripe over PCIe"}
+        # the dense variant needs a pinned host buffer as large as the stripe (10 GB at N = 1): informational, and a box that
+        # cannot pin that much must not cost the run its line (every rank takes the same decision: the size is the same test)
+        try:
+            h_out = ctx.host_alloc(my_elems * esz, dtype=np.uint16 if esz == 2 else np.int32)
+        except kr.KrError as e:
+            h_out = None
+            e2e_dense = {"skipped": "pinned host allocation of %d bytes failed: %s" % (my_elems * esz, e)}
+        ok_all = torch.tensor([1 if h_out is not None else 0], dtype=torch.int32, device=dev.name)
+        if world > 1:
+            dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        if int(ok_all.item()) == 1:
+            def dense_step():
+                s = ctx.encode(res=h_res[: len(res)], off=off)
+                ctx.sim_matrix(s, None, elem=elem, layout=layout, row_begin=r0, row_end=r1, out=h_out)
+                s.free()
+            dt = timed(dense_step)
+            e2e_dense = {"value": total_pairs / (dt / args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(len(res) + 16 * (N + 1)),
+                         "d2h_bytes_per_step": int(my_elems * esz), "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps,
+                         "api": "kr_encode + kr_sim_matrix (pinned host buffers): the dense stripe over PCIe"}
+        elif e2e_dense is None:
+            e2e_dense = {"skipped": "another rank could not pin its host buffer"}
 
     gather = None
     if args.gather_cells and world > 1:
