@@ -2,6 +2,7 @@
 refuses to run without a GPU (no CPU fallback), and its pure-host helpers agree with the oracle."""
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -71,3 +72,12 @@ def test_synth_is_deterministic():
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
     import hashlib
     assert hashlib.sha256(a[0].tobytes()).hexdigest()[:16] == hashlib.sha256(b[0].tobytes()).hexdigest()[:16]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/kmersreps.h is the drop-in boundary: it must compile as C99 (no C++ in the signatures), warnings as errors"""
+    src = tmp_path / "t.c"
+    src.write_text('#include "kmersreps.h"\nint main(void) { kr_multi *m = 0; kr_ctx *c = 0; (void)m; (void)c; return KR_CELL_SIM(5ull) == 5 ? 0 : 1; }\n')
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert p.returncode == 0, p.stdout.decode()
