@@ -230,7 +230,9 @@ kr_status kr_db_find_closest(kr_ctx *ctx, const kr_db *db, const kr_seqset *quer
 kr_status kr_db_find_closest_device(kr_ctx *ctx, const kr_db *db, const kr_seqset *queries, int32_t *d_best_sim,
                                     uint32_t *d_best_first, uint32_t *d_best_last);
 /* RepGenomeDb.checkSimilarity(ProteinKmers, int sim) for a batch (BaseGenomeProcessor.java:203):
- * represented[c] = 1 iff some representative has similarity >= threshold */
+ * represented[c] = 1 iff some representative has similarity >= threshold.  (The reference's loop stops at the first
+ * such representative; the index scan scores all representatives that share a k-mer with the candidate in one pass
+ * over the candidate's ~300 keys, so there is nothing left to cut short.) */
 kr_status kr_db_any_ge(kr_ctx *ctx, const kr_db *db, const kr_seqset *cands, int32_t threshold, uint8_t *represented);
 /* The greedy build loop: for each candidate in order, RepGenomeDb.checkGenome(candidate)
  * (RepGenomeDbProcessor.java:160-163; GtoRepBuildProcessor.java:130-137;
