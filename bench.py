@@ -635,6 +635,11 @@ def main():
             v, pairs, dt, n = cpu_baseline(res, off, args.cpu_sample, cores)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "all i<j pairs of the first %d sequences of the workload (%d pairs, %.1f s)" % (n, pairs, dt)}
+            # the reference's own loops are single-threaded (DistanceMatrixProcessor.java:71-76): the same port on ONE thread,
+            # on a smaller sample (2,000 x 2,000)
+            v1, pairs1, dt1, n1 = cpu_baseline(res, off, min(2000, args.cpu_sample), 1)
+            cpu["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1,
+                                    "sample": "all i<j pairs of the first %d sequences (%d pairs, %.1f s)" % (n1, pairs1, dt1)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
