@@ -37,7 +37,11 @@
 #define __noinline__
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__ static
+// static __shared__ variables are statics placed in one ELF section of their own, so that the launcher can poison them all
+// before every CTA: on hardware shared memory starts undefined in every CTA, and a kernel that relies on zeros (or on what
+// the previous CTA left there) must fail here too
+#define __shared__ static __attribute__((section("kr_emu_smem")))
+extern "C" { extern char __start_kr_emu_smem[] __attribute__((weak)), __stop_kr_emu_smem[] __attribute__((weak)); }
 #define __restrict__
 
 struct uint2 { uint32_t x, y; };
@@ -182,6 +186,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
         cur_block() = &blk;
         blockIdx.x = b;
         memset(base, 0xCD, smem_bytes);                // shared memory starts undefined in every CTA: make reliance on zeros show
+        if (__start_kr_emu_smem && __stop_kr_emu_smem > __start_kr_emu_smem) memset(__start_kr_emu_smem, 0xCD, (size_t)(__stop_kr_emu_smem - __start_kr_emu_smem));
         for (unsigned t = 0; t < block.x; ++t) {
             Fiber &f = sc.fibers[t];
             f.done = false; f.tid = dim3(t);
