@@ -41,6 +41,7 @@ def test_the_check_notices_a_missing_member():
 
 def test_ffm_handles_match_the_header():
     assert cj.check_ffm_against_header() == []
+    assert cj.check_brackets() == []
 
 
 def test_committed_use_list_is_current():

@@ -223,6 +223,30 @@ def check_ffm_against_header():
     return bad
 
 
+def check_brackets():
+    """every shim source has balanced (), [] and {} outside comments and literals (the one syntax check a script can do)"""
+    bad = []
+    pairs = {")": "(", "]": "[", "}": "{"}
+    for dp, _, fs in os.walk(JAVA):
+        for f in fs:
+            if not f.endswith(".java"):
+                continue
+            src = strip_comments(open(os.path.join(dp, f), encoding="utf-8").read())
+            stack = []
+            for i, ch in enumerate(src):
+                if ch in "([{":
+                    stack.append((ch, i))
+                elif ch in ")]}":
+                    if not stack or stack[-1][0] != pairs[ch]:
+                        bad.append("%s: unmatched '%s' at line %d" % (f, ch, src.count("\n", 0, i) + 1))
+                        break
+                    stack.pop()
+            else:
+                if stack:
+                    bad.append("%s: unclosed '%s' from line %d" % (f, stack[-1][0], src.count("\n", 0, stack[-1][1]) + 1))
+    return bad
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     ref = args[0] if args else "/root/reference"
@@ -233,7 +257,7 @@ def main():
     else:
         uses = json.load(open(GOLDEN))
     missing = check(uses)
-    bad = check_ffm_against_header()
+    bad = check_ffm_against_header() + check_brackets()
     by = {}
     for u in uses:
         by.setdefault((u["cls"], u["member"]), 0)
