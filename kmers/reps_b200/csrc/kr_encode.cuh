@@ -1,9 +1,10 @@
 // kr_encode.cuh -- K1: ProteinKmers(String) for a whole batch, one WARP per sequence.
 //
-// A seed protein has a few hundred k-mers, so a warp keeps them in registers -- R consecutive elements per lane,
-// R = 2..32 chosen from the sequence length -- and sorts them with a bitonic network that uses register
-// compare-exchanges for strides below R and warp shuffles for the rest: no block barrier, no shared-memory traffic in
-// the sort, four sequences per CTA in flight.  Residues are read once (coalesced), mapped to 5-bit codes in shared
+// A seed protein has a few hundred k-mers.  The warp sorts them by counting (warp_encode_countsort: buckets of the key's
+// first two residues in the warp's own shared memory, a few hundred instructions per lane).  Sequences of 513..1024
+// k-mers, and low-complexity ones that crowd a bucket, keep their keys in registers -- 16 or 32 consecutive elements per
+// lane -- and sort them with a bitonic network that uses register compare-exchanges for strides below R and warp
+// shuffles for the rest.  No block barrier either way, four sequences per CTA in flight.  Residues are read once (coalesced), mapped to 5-bit codes in shared
 // memory, and every lane builds its keys with a rolling 5K-bit window.  Sequences with more than 1024 k-mers (rare)
 // are sorted in place in global memory by their warp.
 // Output per sequence: sorted DISTINCT keys, their number, the length, a 64-bit hash of the residues (pre-filter of the
@@ -111,6 +112,107 @@ __device__ __forceinline__ u32 warp_encode_sort(const u8 *codes, u32 n, int K, u
     return total;
 }
 
+// The same result by a COUNTING sort, for sequences of up to ENC_CS_CAP k-mers (every seed protein): the keys are bucketed by
+// their top nine bits (512 buckets: a protein's few hundred k-mers leave at most a handful per bucket), the value the
+// shared-memory atomic returns is the key's place inside its bucket, a warp scan turns the counts into offsets, the keys are
+// scattered into bucket order and the buckets with more than one key are finished by insertion sort -- a few hundred
+// instructions per lane where the sorting network takes a few thousand (it sorts 512 slots however short the sequence is).
+// A low-complexity sequence that crowds one bucket (poly-A: its keys are mostly repeats) is handed to the network instead.
+constexpr u32 ENC_NB = 512;               // buckets: the top 9 bits of the key (first residue + four bits of the second)
+constexpr int ENC_NB_BITS = 9;
+constexpr u32 ENC_PER_LANE = ENC_NB / 32; // buckets a lane owns in the scan and the insertion sort
+constexpr u32 ENC_CS_CAP = 512;           // keys a warp sorts this way (16 per lane)
+constexpr u32 ENC_CS_R = ENC_CS_CAP / 32;
+constexpr u32 ENC_INS_MAX = 24;           // a bucket above this sends the sequence to the sorting network
+// The count array is skewed by one word per ENC_PER_LANE buckets: lane l owns buckets ENC_PER_LANE l .. ENC_PER_LANE (l + 1) - 1
+// for the scan and the insertion sort; bucket ENC_PER_LANE l + k then sits in word (ENC_PER_LANE + 1) l + k, and an odd
+// stride spreads the 32 lanes over all 32 shared-memory banks in every step of those loops (unskewed they would share two).
+__device__ __forceinline__ u32 enc_slot(u32 b) { return b + b / ENC_PER_LANE; }
+struct EncScratch { u32 cnt[ENC_NB + 32 + 4]; u64 buf[ENC_CS_CAP]; };      // per warp, shared memory
+
+// returns the number of distinct keys, or 0xFFFFFFFF when a bucket is crowded (nothing has been written to dst then)
+__device__ __forceinline__ u32 warp_encode_countsort(const u8 *codes, u32 n, int K, u64 *dst, u32 lane, EncScratch *sc) {
+    const u64 mask = (K * 5 >= 64) ? ~0ull : ((1ull << (5 * K)) - 1);
+    const int bshift = 5 * K - ENC_NB_BITS;   // (negative for K = 1: the key is shorter than the bucket index)
+    for (u32 i = lane; i < ENC_NB + 32 + 4; i += 32) sc->cnt[i] = 0;
+    __syncwarp();
+    u64 key[ENC_CS_R];
+    u32 rank4[ENC_CS_R / 4] = {};        // a key's place inside its bucket, one byte each (used only when every bucket holds <= ENC_INS_MAX keys)
+    {
+        const u32 e0 = lane * ENC_CS_R;
+        u64 k = 0;
+        if (e0 < n) for (int t = 0; t < K - 1; ++t) k = (k << 5) | (u64)(codes[e0 + t] & 31);
+#pragma unroll
+        for (u32 t = 0; t < ENC_CS_R; ++t) {
+            const u32 e = e0 + t;
+            if (e < n) {
+                k = ((k << 5) | (u64)(codes[e + K - 1] & 31)) & mask;
+                key[t] = k;
+                const u32 b = (u32)(bshift >= 0 ? k >> bshift : k << -bshift);
+                rank4[t >> 2] |= (atomicAdd(&sc->cnt[enc_slot(b)], 1u) & 0xFFu) << ((t & 3) * 8);
+            }
+        }
+    }
+    __syncwarp();
+    // exclusive scan of the counts: lane l owns buckets ENC_PER_LANE l .. ENC_PER_LANE (l + 1) - 1
+    u32 sum = 0, big = 0;
+#pragma unroll 4
+    for (u32 k = 0; k < ENC_PER_LANE; ++k) { const u32 c = sc->cnt[enc_slot(lane * ENC_PER_LANE + k)]; sum += c; big |= (c > ENC_INS_MAX); }
+    if (__any_sync(0xffffffffu, big != 0)) return 0xFFFFFFFFu;
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += up; }
+    u32 run = incl - sum;
+#pragma unroll 4
+    for (u32 k = 0; k < ENC_PER_LANE; ++k) { const u32 sl = enc_slot(lane * ENC_PER_LANE + k); const u32 c = sc->cnt[sl]; sc->cnt[sl] = run; run += c; }
+    if (lane == 31) sc->cnt[enc_slot(ENC_NB)] = run;            // = n
+    __syncwarp();
+    // scatter into bucket order
+#pragma unroll
+    for (u32 t = 0; t < ENC_CS_R; ++t) {
+        const u32 e = lane * ENC_CS_R + t;
+        if (e < n) {
+            const u32 b = (u32)(bshift >= 0 ? key[t] >> bshift : key[t] << -bshift);
+            sc->buf[sc->cnt[enc_slot(b)] + ((rank4[t >> 2] >> ((t & 3) * 8)) & 0xFFu)] = key[t];
+        }
+    }
+    __syncwarp();
+    // buckets with more than one key: insertion sort by the lane that owns the bucket
+    {
+        u32 a = sc->cnt[enc_slot(lane * ENC_PER_LANE)];
+#pragma unroll 1
+        for (u32 k = 0; k < ENC_PER_LANE; ++k) {
+            const u32 nxt = sc->cnt[enc_slot(lane * ENC_PER_LANE + k + 1)], c = nxt - a;
+            if (c > 1) {
+                u64 *q = sc->buf + a;
+                for (u32 x = 1; x < c; ++x) {
+                    const u64 v = q[x];
+                    u32 y = x;
+                    while (y > 0 && q[y - 1] > v) { q[y] = q[y - 1]; --y; }
+                    q[y] = v;
+                }
+            }
+            a = nxt;
+        }
+    }
+    __syncwarp();
+    // distinct keys, 32 consecutive elements per round (lane l looks at element 32 r + l: consecutive shared-memory words,
+    // consecutive global addresses): an element counts when it differs from its predecessor
+    u32 total = 0;
+#pragma unroll 1
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 e = base + lane;
+        const bool valid = e < n;
+        const u64 v = valid ? sc->buf[e] : 0;
+        const bool flag = valid && (e == 0 || v != sc->buf[e - 1]);
+        const u32 bal = __ballot_sync(0xffffffffu, flag);
+        if (flag) dst[total + __popc(bal & ((1u << lane) - 1))] = v;
+        total += __popc(bal);
+    }
+    __syncwarp();                                                // the scratch is reused by the warp's next sequence
+    return total;
+}
+
 // in-place bitonic sort in (global) memory by one warp: the slow path of sequences longer than the register budget
 __device__ __forceinline__ void bitonic_sort_warp_mem(u64 *d, u32 n, u32 lane) {
     if (n < 2) return;
@@ -134,8 +236,9 @@ __device__ __forceinline__ void bitonic_sort_warp_mem(u64 *d, u32 n, u32 lane) {
 }
 
 template <int MAXR>
-__global__ void __launch_bounds__(ENC2_WARPS * 32) k_encode_sort_warp(EncodeParams p) {
+__global__ void __launch_bounds__(ENC2_WARPS * 32, MAXR < 32 ? 6 : 1) k_encode_sort_warp(EncodeParams p) {
     __shared__ u8 s_codes[ENC2_WARPS][ENC2_CODES];
+    __shared__ __align__(16) EncScratch s_scratch[ENC2_WARPS];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 s = blockIdx.x * ENC2_WARPS + warp;
     if (s >= p.nseq) return;                                   // whole warps leave together
@@ -158,11 +261,12 @@ __global__ void __launch_bounds__(ENC2_WARPS * 32) k_encode_sort_warp(EncodePara
     __syncwarp();
     u32 size;
     if (in_regs) {
-        if (n <= 64) size = warp_encode_sort<2>(codes, n, K, dst, lane);
-        else if (n <= 128) size = warp_encode_sort<4>(codes, n, K, dst, lane);
-        else if (n <= 256) size = warp_encode_sort<8>(codes, n, K, dst, lane);
-        else if (n <= 512 || MAXR < 32) size = warp_encode_sort<16>(codes, n, K, dst, lane);
-        else size = warp_encode_sort<(MAXR < 32 ? 16 : 32)>(codes, n, K, dst, lane);
+        size = 0xFFFFFFFFu;
+        if (n <= ENC_CS_CAP) size = warp_encode_countsort(codes, n, K, dst, lane, &s_scratch[warp]);
+        if (size == 0xFFFFFFFFu) {                              // longer than 512 k-mers, or a crowded bucket: the sorting network
+            if (n <= 512 || MAXR < 32) size = warp_encode_sort<16>(codes, n, K, dst, lane);
+            else size = warp_encode_sort<(MAXR < 32 ? 16 : 32)>(codes, n, K, dst, lane);
+        }
     } else {
         for (u32 i = lane; i < n; i += 32) {
             u64 key = 0;

@@ -105,9 +105,12 @@ constexpr u32 IX_SORT_BUCKET_BITS = 11, IX_SORT_NB = 1u << IX_SORT_BUCKET_BITS;
 constexpr u32 IX_SORT_PER_THREAD = IX_SORT_CAP / IX_SORT_THREADS;      // entries a thread keeps in registers
 constexpr u32 IX_SORT_INSERTION_MAX = 24;                              // a bucket above this sends the prefix to the network
 static_assert(IX_SORT_NB == 8 * IX_SORT_THREADS, "the scan gives every thread 8 consecutive buckets");
+// bucket b lives in word b + (b >> 5): thread t owns buckets 8 t .. 8 t + 7, and the skew spreads the 32 threads of a warp over
+// all 32 shared-memory banks in every step of its loops (unskewed, they would share four)
+__device__ __forceinline__ u32 ix_sort_slot(u32 b) { return b + (b >> 5); }
 __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u64 *ent, int low_bits) {
     __shared__ __align__(16) u64 sk[IX_SORT_CAP];
-    __shared__ u32 cnt[IX_SORT_NB + 1];
+    __shared__ u32 cnt[IX_SORT_NB + IX_SORT_NB / 32 + 2];
     __shared__ u32 wsum[IX_SORT_THREADS / 32];
     __shared__ u32 s_big;
     const u32 p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u
     const int bshift = low_bits > (int)IX_SORT_BUCKET_BITS ? low_bits - (int)IX_SORT_BUCKET_BITS : 0;
     u64 e[IX_SORT_PER_THREAD];
     u32 rank[IX_SORT_PER_THREAD];
-    for (u32 i = tid; i <= IX_SORT_NB; i += IX_SORT_THREADS) cnt[i] = 0;
+    for (u32 i = tid; i < IX_SORT_NB + IX_SORT_NB / 32 + 2; i += IX_SORT_THREADS) cnt[i] = 0;
     if (tid == 0) s_big = 0;
     __syncthreads();
     // 1. histogram; the value the atomic returns is the entry's place inside its bucket
@@ -127,14 +130,14 @@ __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u
         const u32 i = tid + j * IX_SORT_THREADS;
         if (i < n) {
             e[j] = g[i];
-            rank[j] = atomicAdd(&cnt[(u32)(e[j] >> bshift) & (IX_SORT_NB - 1)], 1u);
+            rank[j] = atomicAdd(&cnt[ix_sort_slot((u32)(e[j] >> bshift) & (IX_SORT_NB - 1))], 1u);
         }
     }
     __syncthreads();
     // 2. exclusive scan of the bucket counts, in place: thread t owns buckets 8t .. 8t+7
     u32 c[8], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { c[k] = cnt[tid * 8 + k]; sum += c[k]; if (c[k] > IX_SORT_INSERTION_MAX) s_big = 1; }
+    for (int k = 0; k < 8; ++k) { c[k] = cnt[ix_sort_slot(tid * 8 + k)]; sum += c[k]; if (c[k] > IX_SORT_INSERTION_MAX) s_big = 1; }
     u32 incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += up; }
@@ -143,14 +146,13 @@ __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u
     u32 base = incl - sum;
     for (u32 w = 0; w < warp; ++w) base += wsum[w];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { cnt[tid * 8 + k] = base; base += c[k]; }
-    if (tid == IX_SORT_THREADS - 1) cnt[IX_SORT_NB] = base;
+    for (int k = 0; k < 8; ++k) { cnt[ix_sort_slot(tid * 8 + k)] = base; base += c[k]; }
     __syncthreads();
     // 3. scatter into bucket order
 #pragma unroll
     for (u32 j = 0; j < IX_SORT_PER_THREAD; ++j) {
         const u32 i = tid + j * IX_SORT_THREADS;
-        if (i < n) sk[cnt[(u32)(e[j] >> bshift) & (IX_SORT_NB - 1)] + rank[j]] = e[j];
+        if (i < n) sk[cnt[ix_sort_slot((u32)(e[j] >> bshift) & (IX_SORT_NB - 1))] + rank[j]] = e[j];
     }
     __syncthreads();
     if (s_big) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (c[k] > 1) {
-                u64 *q = sk + cnt[tid * 8 + k];
+                u64 *q = sk + cnt[ix_sort_slot(tid * 8 + k)];
                 for (u32 x = 1; x < c[k]; ++x) {
                     const u64 v = q[x];
                     u32 y = x;

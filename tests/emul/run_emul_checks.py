@@ -203,7 +203,7 @@ def case_sparse_matrix():
 
 
 def case_encode_warp():
-    """K1, one warp per sequence (register bitonic network): every register budget, the in-memory path for very long
+    """K1, one warp per sequence (counting sort; sorting network for crowded buckets and 513..1024 k-mers): the in-memory path for very long
     sequences, repeats, all K; keys come back sorted and distinct"""
     rng = np.random.default_rng(9)
     alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX*-", dtype=np.uint8)
@@ -211,7 +211,7 @@ def case_encode_warp():
     seqs = [alpha[rng.integers(0, len(alpha), n)].tobytes().decode() for n in lens]
     seqs += ["A" * 50, "AC" * 200, "ACDEFGHIK" * 130, seqs[10], seqs[24]]            # repeats (few distinct k-mers), duplicates
     seqs += family(17, 40, 3, 200, 420)
-    for K in (8, 3, 11):
+    for K in (8, 3, 11, 1, 2):
         ob = O.batch(seqs, K=K)
         want = O.sim_matrix(ob, ident_inf=True, threads=4)
         c = kr.Context(device=0, K=K, flags=kr.IDENT_IS_INFINITY)
