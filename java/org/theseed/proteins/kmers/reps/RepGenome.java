@@ -29,7 +29,29 @@ public class RepGenome extends ProteinKmers implements Comparable<RepGenome> {
     public String getFid() { return fid; }
     public String getName() { return name; }
     public String getGenomeId() { return genomeId; }
-    @Override public int compareTo(RepGenome o) { return genomeId.compareTo(o.genomeId); }
+    /**
+     * Order of genome ids.  Upstream's compareTo cannot be read here (un-vendored module), so the order is a policy:
+     * String.compareTo of the ids (default) or, with -Dkmersreps.idOrder=natural, taxon number then version number.
+     * Same rule as RepGenome::compareIds in kmers/reps_b200/host/theseed.hpp.  Only the orientation / order of the
+     * rows of `distances` depends on it (DistanceMatrixProcessor.java:74), never a value.
+     */
+    private static final boolean NATURAL_ORDER = "natural".equals(System.getProperty("kmersreps.idOrder"));
+
+    public static int compareIds(String a, String b) {
+        if (NATURAL_ORDER) {
+            String[] fa = a.split("\\.", -1), fb = b.split("\\.", -1);
+            for (int i = 0; i < Math.min(fa.length, fb.length); i++) {
+                boolean na = !fa[i].isEmpty() && fa[i].chars().allMatch(c -> c >= '0' && c <= '9');
+                boolean nb = !fb[i].isEmpty() && fb[i].chars().allMatch(c -> c >= '0' && c <= '9');
+                int c = (na && nb) ? new java.math.BigInteger(fa[i]).compareTo(new java.math.BigInteger(fb[i])) : fa[i].compareTo(fb[i]);
+                if (c != 0) return c < 0 ? -1 : 1;
+            }
+            if (fa.length != fb.length) return fa.length < fb.length ? -1 : 1;
+        }
+        return Integer.signum(a.compareTo(b));
+    }
+
+    @Override public int compareTo(RepGenome o) { return compareIds(genomeId, o.genomeId); }
     @Override public boolean equals(Object o) { return o instanceof RepGenome && ((RepGenome) o).genomeId.equals(genomeId); }
     @Override public int hashCode() { return genomeId.hashCode(); }
     @Override public String toString() { return genomeId + " (" + name + ")"; }

@@ -9,6 +9,7 @@
 //   selftest dtos               < doubles                    -> Double.toString
 //   selftest resave IN OUT                                   -> RepGenomeDb::load(IN)->save(OUT)
 //   selftest fasta              < FASTA                      -> "label\tcomment\tsequence" lines
+//   selftest idcmp              < "a\tb" lines                -> RepGenome.compareTo sign, lexical and natural id order
 //   selftest seed FILE.gto ...                               -> GTO ingest + seed-protein lookup, one line per genome
 #include "genome.hpp"
 
@@ -58,6 +59,16 @@ int main(int argc, char **argv) {
                 const std::string fid = findSeed(g);
                 std::cout << g.getId() << '\t' << g.getDomain() << '\t' << fid << '\t' << g.getName() << '\t'
                           << (fid.empty() ? std::string() : g.getFeature(fid)->getProteinTranslation()) << '\n';
+            }
+        } else if (cmd == "idcmp") {     // "a\tb" per line -> RepGenome.compareTo sign under the lexical and the natural id order
+            std::string line;
+            while (std::getline(std::cin, line)) {
+                const size_t t = line.find('\t');
+                const std::string a = line.substr(0, t), b = line.substr(t + 1);
+                RepGenome::setIdOrder(RepGenome::IdOrder::LEXICAL);
+                const int l = RepGenome::compareIds(a, b);
+                RepGenome::setIdOrder(RepGenome::IdOrder::NATURAL);
+                std::cout << l << '\t' << RepGenome::compareIds(a, b) << '\n';
             }
         } else if (cmd == "genomeof") {
             std::string line;

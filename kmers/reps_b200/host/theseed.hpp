@@ -796,8 +796,45 @@ class RepGenome : public ProteinKmers {   // a representative: (fid, name, prote
     const std::string &getFid() const { return fid_; }
     const std::string &getName() const { return name_; }
     const std::string &getGenomeId() const { return genomeId_; }
-    // used only to visit each unordered pair once (DistanceMatrixProcessor.java:74); order of genome-id strings
-    int compareTo(const RepGenome &o) const { return genomeId_.compare(o.genomeId_); }
+    // Used only to visit each unordered pair once (DistanceMatrixProcessor.java:74) and to break ties in sorted reports.
+    // The class is in un-vendored org.theseed:shared, so which order its compareTo imposes on genome ids cannot be read
+    // here (open semantic questions): a run-time policy, not a guess baked in.  LEXICAL = String.compareTo
+    // of the ids (default); NATURAL = taxon number, then version number ("83333.1" < "511145.12").  KR_ID_ORDER=natural
+    // in the environment (or setIdOrder) selects the other; values never change, only row order / pair orientation.
+    enum class IdOrder { LEXICAL, NATURAL };
+    static IdOrder &idOrder() {
+        static IdOrder o = [] { const char *e = std::getenv("KR_ID_ORDER"); return (e && std::string(e) == "natural") ? IdOrder::NATURAL : IdOrder::LEXICAL; }();
+        return o;
+    }
+    static void setIdOrder(IdOrder o) { idOrder() = o; }
+    static int compareIds(const std::string &a, const std::string &b) {
+        if (idOrder() == IdOrder::NATURAL) {
+            // dot-separated fields, numeric where both are digit strings (no leading-zero ids exist; longer = larger)
+            size_t i = 0, j = 0;
+            while (i < a.size() && j < b.size()) {
+                size_t ie = a.find('.', i), je = b.find('.', j);
+                if (ie == std::string::npos) ie = a.size();
+                if (je == std::string::npos) je = b.size();
+                const std::string fa = a.substr(i, ie - i), fb = b.substr(j, je - j);
+                const bool na = !fa.empty() && fa.find_first_not_of("0123456789") == std::string::npos;
+                const bool nb = !fb.empty() && fb.find_first_not_of("0123456789") == std::string::npos;
+                int c;
+                if (na && nb) {
+                    const size_t za = std::min(fa.find_first_not_of('0'), fa.size() - 1), zb = std::min(fb.find_first_not_of('0'), fb.size() - 1);
+                    const size_t la = fa.size() - za, lb = fb.size() - zb;
+                    c = la != lb ? (la < lb ? -1 : 1) : fa.compare(za, la, fb, zb, lb);
+                } else c = fa.compare(fb);
+                if (c) return c < 0 ? -1 : 1;
+                i = ie + 1; j = je + 1;
+            }
+            const bool ra = i < a.size(), rb = j < b.size();
+            if (ra != rb) return ra ? 1 : -1;
+            // numerically equal but differently written ids stay distinct: fall through to the string order
+        }
+        const int c = a.compare(b);
+        return c < 0 ? -1 : c > 0 ? 1 : 0;
+    }
+    int compareTo(const RepGenome &o) const { return compareIds(genomeId_, o.genomeId_); }
     std::string toString() const { return genomeId_ + " (" + name_ + ")"; }
   private:
     std::string fid_, name_, genomeId_;

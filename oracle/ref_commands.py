@@ -50,7 +50,27 @@ def repdb_report(db_reps, threshold, queries, K=8, ident_inf=True):
     return "\n".join(out) + "\n"
 
 
-def distances(db_reps, K=8, ident_inf=True):
+def _natural_key(gid):
+    """genome id as (taxon number, version number, ...): the other order RepGenome.compareTo may impose"""
+    return [(0, int(f), f) if f.isdigit() else (1, 0, f) for f in gid.split(".")]
+
+
+def compare_ids(a, b, id_order="lexical"):
+    """sign of RepGenome.compareTo under the two candidate orders of genome-id strings"""
+    if id_order == "natural":
+        ka, kb = _natural_key(a), _natural_key(b)
+        for x, y in zip(ka, kb):
+            if x[0] == 0 and y[0] == 0:
+                if x[1] != y[1]:
+                    return -1 if x[1] < y[1] else 1
+            elif x[2] != y[2]:
+                return -1 if x[2] < y[2] else 1
+        if len(ka) != len(kb):
+            return -1 if len(ka) < len(kb) else 1
+    return -1 if a < b else 1 if a > b else 0
+
+
+def distances(db_reps, K=8, ident_inf=True, id_order="lexical"):
     o = ko.get()
     b = o.batch([r[2] for r in db_reps], K=K)
     m = o.sim_matrix(b, ident_inf=ident_inf, threads=4)
@@ -59,7 +79,7 @@ def distances(db_reps, K=8, ident_inf=True):
     out = ["genome_1\tgenome_2\tdistance\tsim"]
     for i in range(len(ids)):
         for j in range(len(ids)):
-            if ids[i] < ids[j]:
+            if compare_ids(ids[i], ids[j], id_order) < 0:
                 d = o.distance(m[i, j], sz[i], sz[j])
                 out.append("%s\t%s\t%s\t%d" % (ids[i], ids[j], ko.java_fixed(d, 8, 6), m[i, j]))
     return "\n".join(out) + "\n"

@@ -233,3 +233,20 @@ def test_gto_reader_and_seed_lookup(gto_seeds):
         full = [os.path.join(ref, "202462.4.gto")] + sorted(os.path.join(ref, "P3Master", f) for f in os.listdir(os.path.join(ref, "P3Master")) if f.endswith(".gto"))
         rows = [ln.split("\t") for ln in run(["seed"] + full).stdout.decode().split("\n")[:-1]]
         assert [(r[2], r[3], r[4]) for r in rows] == [tuple(x) for x in gto_seeds]
+
+
+def test_repgenome_id_order_policy(rep50):
+    """RepGenome.compareTo lives in an un-vendored module: lexical vs natural order of genome ids is a run-time policy
+    (KR_ID_ORDER / RepGenome::setIdOrder), checked against the oracle's independent restatement of both orders."""
+    from oracle import ref_commands as rc
+    ids = [ko.genome_id_of(f) for (f, _, _) in rep50["reps"][:120]] + ["83333.1", "511145.12", "9.10", "10.9", "10.10", "1.2.3", "1.2", "x.1", "1", "01.1", "1.1"]
+    rng = np.random.default_rng(7)
+    pairs = [(ids[a], ids[b]) for a, b in rng.integers(0, len(ids), (600, 2))] + [(i, i) for i in ids[-11:]]
+    got = [tuple(int(v) for v in l.split("\t")) for l in run(["idcmp"], "".join("%s\t%s\n" % p for p in pairs)).stdout.decode().split("\n")[:-1]]
+    want = [(rc.compare_ids(a, b, "lexical"), rc.compare_ids(a, b, "natural")) for a, b in pairs]
+    assert got == want
+    assert any(l != n for l, n in got), "the two orders never differed on the sample"
+    # both are strict total orders on distinct ids: antisymmetric, and 0 only for equal strings
+    for (a, b), (l, n) in zip(pairs, got):
+        assert (l == 0) == (a == b) and (n == 0) == (a == b)
+        assert (rc.compare_ids(b, a, "natural"), rc.compare_ids(b, a, "lexical")) == (-n, -l)

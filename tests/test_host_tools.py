@@ -16,8 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOOL = os.environ.get("KR_TOOL_PATH") or os.path.join(ROOT, "kmers", "reps_b200", "host", "kmers_reps")   # (tools/emul_gpu_suite.sh points it at a build linked against the emulator)
 
 
-def run(args, stdin=b"", check=True):
-    p = subprocess.run([TOOL] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+def run(args, stdin=b"", check=True, env=None):
+    p = subprocess.run([TOOL] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600,
+                       env=dict(os.environ, **env) if env else None)
     if check:
         assert p.returncode == 0, p.stderr.decode()
     return p
@@ -88,6 +89,11 @@ def test_distances(tmp_path, rep50):
     db.write_bytes(ko.save_repdb(50, 8, rep50["prot_name"], reps))
     p = run(["distances", str(db)])
     assert p.stdout.decode() == rc.distances(reps)
+    # RepGenome.compareTo's order of genome ids is a policy (un-vendored class): the natural order visits the same pairs,
+    # oriented and ordered differently
+    pn = run(["distances", str(db)], env={"KR_ID_ORDER": "natural"})
+    assert pn.stdout.decode() == rc.distances(reps, id_order="natural")
+    assert pn.stdout != p.stdout and len(pn.stdout.splitlines()) == len(p.stdout.splitlines())
 
 
 def test_group_vapb(vapb):
