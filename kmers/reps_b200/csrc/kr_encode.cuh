@@ -235,10 +235,13 @@ __device__ __forceinline__ void bitonic_sort_warp_mem(u64 *d, u32 n, u32 lane) {
     }
 }
 
+// K1's shared memory: the staged residue codes and the counting sort's scratch of the CTA's warps.  Declared at namespace
+// scope (one definition for both instantiations of the kernel template; only kernels that name them get them).
+__shared__ u8 s_codes[ENC2_WARPS][ENC2_CODES];
+__shared__ __align__(16) EncScratch s_scratch[ENC2_WARPS];
+
 template <int MAXR>
 __global__ void __launch_bounds__(ENC2_WARPS * 32, MAXR < 32 ? 6 : 1) k_encode_sort_warp(EncodeParams p) {
-    __shared__ u8 s_codes[ENC2_WARPS][ENC2_CODES];
-    __shared__ __align__(16) EncScratch s_scratch[ENC2_WARPS];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 s = blockIdx.x * ENC2_WARPS + warp;
     if (s >= p.nseq) return;                                   // whole warps leave together

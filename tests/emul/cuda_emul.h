@@ -11,7 +11,18 @@
 //   mbarrier (init / arrive / expect_tx / try_wait.parity) and 1-D bulk copies completing a transaction count
 //   (with the alignment rules of cp.async.bulk CHECKED: 16-byte aligned source, destination and size),
 //   cudaMalloc/Memcpy/Memset/streams/events as plain host operations.
-// What it cannot show: performance, memory-ordering races, register pressure.
+// What it cannot show: performance, register pressure, hardware memory ordering beyond the happens-before model below.
+//
+// RACE DETECTION (-DKR_EMUL_TSAN, built with g++ -fsanitize=thread --param tsan-distinguish-volatile=1; tools/emul_race.sh):
+// every CUDA thread of a CTA is a ThreadSanitizer fiber, switched WITHOUT synchronisation, and the only happens-before
+// edges are the ones the hardware gives: __syncthreads / named barriers / __syncwarp (all-to-all among the arrivers),
+// mbarrier arrive -> successful try_wait of that phase, CTA start and end.  Shuffles and votes order nothing; atomics are
+// relaxed; volatile accesses count as relaxed atomics.  Two threads of a CTA touching the same bytes of shared OR global
+// memory, one of them writing, with no such edge in between, is reported as a data race -- what compute-sanitizer's
+// racecheck reports for shared memory on hardware, extended to global memory.  CTAs of a launch are ordered one after
+// another in this mode.  KR_EMUL_RACE=grid drops that order instead: the CTAs of a launch are concurrent, as on the
+// device, and a global-memory word that two CTAs touch (one writing, no atomics) is reported; shared memory, which the
+// emulated CTAs re-use, is left out of that mode.
 #pragma once
 #include <algorithm>
 #include <atomic>
@@ -30,6 +41,52 @@
 #include <vector>
 #include <ucontext.h>
 
+#ifdef KR_EMUL_TSAN
+extern "C" {
+void *__tsan_get_current_fiber(void);
+void *__tsan_create_fiber(unsigned flags);
+void __tsan_switch_to_fiber(void *fiber, unsigned flags);
+void __tsan_acquire(void *addr);
+void __tsan_release(void *addr);
+void AnnotateIgnoreReadsBegin(const char *f, int l);
+void AnnotateIgnoreReadsEnd(const char *f, int l);
+void AnnotateIgnoreWritesBegin(const char *f, int l);
+void AnnotateIgnoreWritesEnd(const char *f, int l);
+void AnnotateBenignRaceSized(const char *f, int l, const volatile void *mem, size_t size, const char *desc);
+// volatile accesses (GCC --param tsan-distinguish-volatile=1 calls these instead of the plain hooks; libtsan itself does
+// not define them): a relaxed atomic load, or a relaxed read-modify-write that leaves the value alone
+#define KR_TSAN_VOL(N, T)                                                                                                      \
+    __attribute__((weak)) void __tsan_volatile_read##N(void *a) { (void)__atomic_load_n((T *)a, __ATOMIC_RELAXED); }            \
+    __attribute__((weak)) void __tsan_volatile_write##N(void *a) { (void)__atomic_fetch_add((T *)a, (T)0, __ATOMIC_RELAXED); }
+KR_TSAN_VOL(1, uint8_t) KR_TSAN_VOL(2, uint16_t) KR_TSAN_VOL(4, uint32_t) KR_TSAN_VOL(8, uint64_t)
+#undef KR_TSAN_VOL
+}
+namespace emu {
+// the emulator's own bookkeeping (barrier counters, scheduler state, exchange buffers) is shared by all fibers by design:
+// accesses inside a Quiet scope are not recorded
+struct Quiet {
+    Quiet() { AnnotateIgnoreReadsBegin(__FILE__, __LINE__); AnnotateIgnoreWritesBegin(__FILE__, __LINE__); }
+    ~Quiet() { AnnotateIgnoreWritesEnd(__FILE__, __LINE__); AnnotateIgnoreReadsEnd(__FILE__, __LINE__); }
+};
+inline void hb_release(void *a) { __tsan_release(a); }
+inline void hb_acquire(void *a) { __tsan_acquire(a); }
+inline void *tsan_fiber(unsigned t) {      // one ThreadSanitizer fiber per CUDA thread index, kept for the life of the process
+    static std::vector<void *> pool;
+    if (pool.size() <= t) pool.resize(t + 1, nullptr);
+    if (!pool[t]) pool[t] = __tsan_create_fiber(0);
+    return pool[t];
+}
+inline void *&tsan_main() { static void *m = nullptr; return m; }
+inline void tsan_to(void *f) { __tsan_switch_to_fiber(f, 1u /* no synchronisation */); }
+}
+#else
+namespace emu {
+struct Quiet { Quiet() {} ~Quiet() {} };
+inline void hb_release(void *) {}
+inline void hb_acquire(void *) {}
+}
+#endif
+
 #define __global__
 #define __device__
 #define __host__
@@ -39,7 +96,8 @@
 #define __align__(n) __attribute__((aligned(n)))
 // static __shared__ variables are statics placed in one ELF section of their own, so that the launcher can poison them all
 // before every CTA: on hardware shared memory starts undefined in every CTA, and a kernel that relies on zeros (or on what
-// the previous CTA left there) must fail here too
+// the previous CTA left there) must fail here too.  (GCC ignores the section for statics of a TEMPLATE function -- they are
+// COMDAT -- so kernels that are templates declare their __shared__ arrays at namespace scope, as kr_encode.cuh does.)
 #define __shared__ static __attribute__((section("kr_emu_smem")))
 extern "C" { extern char __start_kr_emu_smem[] __attribute__((weak)), __stop_kr_emu_smem[] __attribute__((weak)); }
 #define __restrict__
@@ -100,10 +158,14 @@ struct Sched {
     unsigned long long idle_yields = 0;   // yields since the last sign of progress
 };
 inline Sched *&sched() { static Sched *s = nullptr; return s; }
-inline void progress() { sched()->idle_yields = 0; }
+inline void progress() { Quiet q; sched()->idle_yields = 0; }
 inline void yield() {
+    Quiet q;
     Sched *s = sched();
     if (++s->idle_yields > 50000000ull) { fprintf(stderr, "cuda_emul: deadlock (every thread of the CTA is waiting)\n"); abort(); }
+#ifdef KR_EMUL_TSAN
+    tsan_to(tsan_main());
+#endif
     ctx_switch(&s->fibers[s->cur].ctx, &s->main);
 }
 
@@ -111,17 +173,30 @@ inline void yield() {
 class Barrier {
   public:
     explicit Barrier(unsigned n) : parties_(n), waiting_(0), gen_(0) {}
-    void arrive_and_wait() {
-        const unsigned g = gen_;
-        if (++waiting_ >= parties_) { waiting_ = 0; ++gen_; progress(); return; }
-        while (gen_ == g) yield();
+    // orders = true: everything the arrivers did before happens-before everything they do after (__syncthreads, named
+    // barriers, __syncwarp); false: a lock-step exchange that orders no memory (shuffles, votes).  One token per
+    // generation parity, so that a thread already arriving at the NEXT barrier adds nothing to what a slow thread still
+    // leaving this one acquires.
+    void arrive_and_wait(bool orders = true) {
+        unsigned g;
+        { Quiet q; g = gen_; }
+        if (orders) hb_release(&tok_[g & 1]);
+        {
+            Quiet q;
+            if (++waiting_ >= parties_) { waiting_ = 0; ++gen_; progress(); }
+            else while (gen_ == g) yield();
+        }
+        if (orders) hb_acquire(&tok_[g & 1]);
     }
-    void drop() {
+    void drop() {      // a thread that leaves the kernel: what it did is visible to the others from their next barrier on
+        hb_release(&tok_[0]); hb_release(&tok_[1]);
+        Quiet q;
         --parties_;
         if (parties_ && waiting_ >= parties_) { waiting_ = 0; ++gen_; progress(); }
     }
   private:
     unsigned parties_, waiting_, gen_;
+    char tok_[2] = {0, 0};
 };
 
 struct Warp { Barrier bar; uint64_t buf[32]; unsigned n; explicit Warp(unsigned k) : bar(k), n(k) {} };
@@ -146,31 +221,58 @@ struct Trap {};
 inline std::function<void()> *&cur_body() { static std::function<void()> *f = nullptr; return f; }
 inline bool &trapped() { static bool t = false; return t; }
 
+inline char *cta_tokens() { static char t[2]; return t; }   // [0]: launcher -> threads at CTA start, [1]: threads -> launcher at CTA end
 inline void fiber_main() {
-    Sched *s = sched();
-    Fiber &f = s->fibers[s->cur];
-    try { (*cur_body())(); } catch (Trap &) { trapped() = true; }
-    f.done = true;
+    hb_acquire(&cta_tokens()[0]);
+    Sched *s; Fiber *f; std::function<void()> *body;
+    { Quiet q; s = sched(); f = &s->fibers[s->cur]; body = cur_body(); }
+    try { (*body)(); } catch (Trap &) { trapped() = true; }
+    { Quiet q; f->done = true; }
     progress();
-    cur_block()->sync.drop();                      // a thread that has left the kernel no longer takes part
-    cur_block()->warps[f.tid.x >> 5]->bar.drop();
-    ctx_switch(&f.ctx, &s->main);
+    Barrier *b0, *b1;
+    { Quiet q; Block *blk = cur_block(); b0 = &blk->sync; b1 = &blk->warps[f->tid.x >> 5]->bar; }
+    b0->drop();                                    // a thread that has left the kernel no longer takes part
+    b1->drop();
+    hb_release(&cta_tokens()[1]);                  // (last: nothing this thread touches comes after it)
+    Quiet q;
+#ifdef KR_EMUL_TSAN
+    tsan_to(tsan_main());
+#endif
+    ctx_switch(&f->ctx, &s->main);
     abort();                                       // a finished fiber is never resumed
 }
 
 }  // namespace emu
 
 inline dim3 blockIdx, blockDim, gridDim;
-#define threadIdx (emu::sched()->fibers[emu::sched()->cur].tid)
+namespace emu { inline dim3 tid() { Quiet q; Sched *s = sched(); return s->fibers[s->cur].tid; } }
+#define threadIdx (emu::tid())
 
 namespace emu {
 
-inline Warp &my_warp() { return *cur_block()->warps[threadIdx.x >> 5]; }
+inline Warp &my_warp() { const unsigned w = threadIdx.x >> 5; Quiet q; return *cur_block()->warps[w]; }
 
 template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
     std::lock_guard<std::mutex> lk(launch_lock());
+    Quiet quiet;                                       // the launcher's bookkeeping is not the kernel's memory traffic
     gridDim = grid; blockDim = block;
+#ifdef KR_EMUL_TSAN
+    // one buffer for the life of the process (so that grid mode can exclude it once), and the race mode of this process
+    static std::vector<uint8_t> smem(232448 + 2048);
+    static const bool grid_mode = [] {
+        const char *m = getenv("KR_EMUL_RACE");
+        if (!m || strcmp(m, "grid")) return false;
+        uint8_t *b0 = smem.data();
+        AnnotateBenignRaceSized(__FILE__, __LINE__, b0, smem.size(), "emulated shared memory (re-used by the CTAs of a launch)");
+        if (__start_kr_emu_smem && __stop_kr_emu_smem > __start_kr_emu_smem)
+            AnnotateBenignRaceSized(__FILE__, __LINE__, __start_kr_emu_smem, (size_t)(__stop_kr_emu_smem - __start_kr_emu_smem), "emulated static shared memory");
+        return true;
+    }();
+    if (smem_bytes > 232448) { fprintf(stderr, "cuda_emul: %zu bytes of dynamic shared memory\n", smem_bytes); abort(); }
+#else
+    const bool grid_mode = false;
     std::vector<uint8_t> smem(smem_bytes + 2048);
+#endif
     uint8_t *base = smem.data() + (1024 - (reinterpret_cast<uintptr_t>(smem.data()) & 1023));
     dyn_smem() = base; dyn_smem_size() = smem_bytes;
     std::function<void()> fn = body;
@@ -181,8 +283,12 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
     for (unsigned t = 0; t < block.x; ++t) sc.fibers[t].stack = fiber_stack(t, stack_bytes);
     sched() = &sc;
     trapped() = false;
+#ifdef KR_EMUL_TSAN
+    tsan_main() = __tsan_get_current_fiber();
+#endif
     for (unsigned b = 0; b < grid.x; ++b) {
-        Block blk(block.x);
+        std::unique_ptr<Block> blkp(new Block(block.x));   // (heap: ThreadSanitizer forgets a barrier's history when its memory is freed)
+        Block &blk = *blkp;
         cur_block() = &blk;
         blockIdx.x = b;
         memset(base, 0xCD, smem_bytes);                // shared memory starts undefined in every CTA: make reliance on zeros show
@@ -190,6 +296,9 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
         for (unsigned t = 0; t < block.x; ++t) {
             Fiber &f = sc.fibers[t];
             f.done = false; f.tid = dim3(t);
+            // grid mode: the threads of four consecutive CTAs are four different ThreadSanitizer fibers (with stacks of their
+            // own), so that thread t of one CTA and thread t of the next are not "the same thread" to the detector
+            if (grid_mode) f.stack = fiber_stack((b & 3) * block.x + t, stack_bytes);
             ctx_make(&f.ctx, f.stack, stack_bytes, fiber_main);
         }
         sc.idle_yields = 0;
@@ -204,26 +313,32 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
             uint64_t x = 0x9E3779B97F4A7C15ull * (b + 1) + block.x;
             for (unsigned t = block.x; t > 1; --t) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; std::swap(order[t - 1], order[x % t]); }
         }
+        hb_release(&cta_tokens()[0]);                  // everything the host and the earlier CTAs did is visible to this CTA's threads
         for (unsigned live = block.x; live;) {
             live = 0;
             for (unsigned ti = 0; ti < block.x; ++ti) {
                 const unsigned t = order[ti];
                 if (sc.fibers[t].done) continue;
                 sc.cur = t;
+#ifdef KR_EMUL_TSAN
+                tsan_to(tsan_fiber(grid_mode ? (b & 3) * block.x + t : t));
+#endif
                 ctx_switch(&sc.main, &sc.fibers[t].ctx);
                 if (!sc.fibers[t].done) ++live;
             }
         }
+        if (!grid_mode) hb_acquire(&cta_tokens()[1]);  // ... and what they did, to the host and the later CTAs
         cur_block() = nullptr;
         if (trapped()) { fprintf(stderr, "cuda_emul: kernel trapped in block %u\n", b); abort(); }
     }
+    if (grid_mode) hb_acquire(&cta_tokens()[1]);       // grid mode: only the end of the launch orders its CTAs before what follows
     sched() = nullptr;
 }
 
 }  // namespace emu
 
 // ---- device-side intrinsics ------------------------------------------------------------------------------------
-inline void __syncthreads() { emu::cur_block()->sync.arrive_and_wait(); }
+inline void __syncthreads() { emu::Block *b; { emu::Quiet q; b = emu::cur_block(); } b->sync.arrive_and_wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::my_warp().bar.arrive_and_wait(); }
 inline void __trap() { throw emu::Trap(); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -241,11 +356,12 @@ template <class T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T
 template <class T> inline T exchange(T v, unsigned src_lane, bool keep_own_if_out_of_range) {
     Warp &w = my_warp();
     const unsigned lane = threadIdx.x & 31;
-    w.buf[lane] = to_bits(v);
-    w.bar.arrive_and_wait();
-    T r = (src_lane < w.n) ? from_bits<T>(w.buf[src_lane]) : v;
+    { Quiet q; w.buf[lane] = to_bits(v); }
+    w.bar.arrive_and_wait(false);                  // a shuffle is not a memory barrier
+    T r;
+    { Quiet q; r = (src_lane < w.n) ? from_bits<T>(w.buf[src_lane]) : v; }
     (void)keep_own_if_out_of_range;
-    w.bar.arrive_and_wait();
+    w.bar.arrive_and_wait(false);
     return r;
 }
 }  // namespace emu
@@ -258,11 +374,11 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
 inline unsigned __ballot_sync(unsigned, bool pred) {
     emu::Warp &w = emu::my_warp();
     const unsigned lane = threadIdx.x & 31;
-    w.buf[lane] = pred ? 1 : 0;
-    w.bar.arrive_and_wait();
+    { emu::Quiet q; w.buf[lane] = pred ? 1 : 0; }
+    w.bar.arrive_and_wait(false);                  // a vote is not a memory barrier
     unsigned r = 0;
-    for (unsigned l = 0; l < w.n; ++l) if (w.buf[l]) r |= 1u << l;
-    w.bar.arrive_and_wait();
+    { emu::Quiet q; for (unsigned l = 0; l < w.n; ++l) if (w.buf[l]) r |= 1u << l; }
+    w.bar.arrive_and_wait(false);
     return r;
 }
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
@@ -274,41 +390,60 @@ inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) !=
 namespace emu {
 inline void preempt() {
     static const long mode = [] { const char *s = getenv("KR_EMUL_PREEMPT"); return s ? atol(s) : 0L; }();
-    if (!mode || !sched()) return;
-    static uint64_t x = 0x2545F4914F6CDD1Dull * (uint64_t)mode + 1;
-    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
-    if ((x & 3) == 0) { progress(); yield(); }
+    bool go;
+    {
+        Quiet q;
+        if (!mode || !sched()) return;
+        static uint64_t x = 0x2545F4914F6CDD1Dull * (uint64_t)mode + 1;
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        go = (x & 3) == 0;
+    }
+    if (go) { progress(); yield(); }
 }
 }  // namespace emu
-// atomics (global or shared memory alike)
-template <class T> inline T atomicAdd(T *p, T v) { emu::preempt(); return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-inline unsigned atomicAdd(unsigned *p, int v) { emu::preempt(); return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_SEQ_CST); }
-inline unsigned long long atomicAdd(unsigned long long *p, unsigned long v) { emu::preempt(); return __atomic_fetch_add(p, (unsigned long long)v, __ATOMIC_SEQ_CST); }
-template <class T> inline T atomicMax(T *p, T v) { emu::preempt(); T o = *p; if (v > o) *p = v; return o; }   // (one fiber runs at a time)
-template <class T> inline T atomicExch(T *p, T v) { emu::preempt(); return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
-template <class T> inline T atomicCAS(T *p, T cmp, T v) { emu::preempt(); __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+// atomics (global or shared memory alike).  RELAXED, as on the device: an atomic orders nothing but itself.
+template <class T> inline T atomicAdd(T *p, T v) { emu::preempt(); return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned *p, int v) { emu::preempt(); return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long v) { emu::preempt(); return __atomic_fetch_add(p, (unsigned long long)v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicMax(T *p, T v) {
+    emu::preempt();
+    T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
+template <class T> inline T atomicExch(T *p, T v) { emu::preempt(); return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicCAS(T *p, T cmp, T v) { emu::preempt(); __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return cmp; }
 
 // ---- mbarrier + bulk copy (the PTX wrappers of kr_kernels.cuh call these under KR_EMUL) -------------------------------
 namespace emu {
 struct MBar { uint32_t phase : 1, pending : 15, expected : 15; int32_t tx; };
 static_assert(sizeof(MBar) == 8, "an mbarrier is 64 bits");
+// happens-before: an arrival (or a completed transaction) of the phase with parity P releases token P of the barrier, a
+// successful try_wait.parity(P) acquires it (the tokens are the first two bytes of the barrier word itself, as addresses)
+inline void mbar_hb_release(void *bar) { unsigned ph; { Quiet q; ph = ((MBar *)bar)->phase; } hb_release((char *)bar + ph); }
 inline void mbar_check(MBar *b) { if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->expected; progress(); } }
-inline void mbar_init(void *bar, uint32_t count) { MBar *b = (MBar *)bar; b->phase = 0; b->pending = b->expected = count; b->tx = 0; }
+inline void mbar_init(void *bar, uint32_t count) { Quiet q; MBar *b = (MBar *)bar; b->phase = 0; b->pending = b->expected = count; b->tx = 0; }
 inline void mbar_arrive(void *bar, uint32_t n) {
+    mbar_hb_release(bar);
+    Quiet q;
     MBar *b = (MBar *)bar;
     if (b->pending < n) { fprintf(stderr, "cuda_emul: mbarrier over-arrival\n"); abort(); }
     b->pending -= n; mbar_check(b);
 }
 inline void mbar_expect_tx(void *bar, uint32_t bytes) {   // arrive.expect_tx: one arrival + a transaction count
+    mbar_hb_release(bar);
+    Quiet q;
     MBar *b = (MBar *)bar;
     b->tx += (int32_t)bytes;
     if (b->pending < 1) { fprintf(stderr, "cuda_emul: mbarrier over-arrival\n"); abort(); }
     b->pending -= 1; mbar_check(b);
 }
-inline void mbar_complete_tx(void *bar, uint32_t bytes) { MBar *b = (MBar *)bar; b->tx -= (int32_t)bytes; mbar_check(b); }
+inline void mbar_complete_tx(void *bar, uint32_t bytes) { mbar_hb_release(bar); Quiet q; MBar *b = (MBar *)bar; b->tx -= (int32_t)bytes; mbar_check(b); }
 inline bool mbar_try_wait(void *bar, uint32_t parity) {
-    const bool done = ((MBar *)bar)->phase != (parity & 1);
+    bool done;
+    { Quiet q; done = ((MBar *)bar)->phase != (parity & 1); }
     if (!done) yield();
+    else hb_acquire((char *)bar + (parity & 1));
     return done;
 }
 inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar) {
@@ -321,20 +456,23 @@ inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar) {
     mbar_complete_tx(bar, bytes);
 }
 inline void named_barrier(int id, unsigned count) {
-    Block *blk = cur_block();
     Barrier *b;
-    { auto &slot = blk->named[id]; if (!slot) slot.reset(new Barrier(count)); b = slot.get(); }
+    { Quiet q; Block *blk = cur_block(); auto &slot = blk->named[id]; if (!slot) slot.reset(new Barrier(count)); b = slot.get(); }
     b->arrive_and_wait();
 }
 // barrier.cta.red.or.pred: the same barrier with an OR reduction of a predicate; every thread gets the same answer
 inline bool named_barrier_or(int id, unsigned count, bool pred) {
-    Block *blk = cur_block();
-    Block::Vote &v = blk->votes[id];
-    const unsigned g = v.gen & 1;
-    if (pred) v.acc[g] = 1;
-    if (++v.arrived == count) { v.arrived = 0; ++v.gen; v.acc[v.gen & 1] = 0; }   // the last arriver opens the next generation
+    Block::Vote *v; unsigned g;
+    {
+        Quiet q;
+        v = &cur_block()->votes[id];
+        g = v->gen & 1;
+        if (pred) v->acc[g] = 1;
+        if (++v->arrived == count) { v->arrived = 0; ++v->gen; v->acc[v->gen & 1] = 0; }   // the last arriver opens the next generation
+    }
     named_barrier(id, count);
-    return v.acc[g] != 0;
+    Quiet q;
+    return v->acc[g] != 0;
 }
 // shared-memory "addresses" are offsets into the dynamic buffer (+ a bias so that 0 is never valid)
 inline uint32_t smem_addr(const void *p) {

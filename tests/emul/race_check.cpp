@@ -1,0 +1,226 @@
+// race_check.cpp -- TEST INFRASTRUCTURE, CPU only: the product's device + host code (kr_api.cu and everything it includes)
+// compiled with g++ -fsanitize=thread -DKR_EMUL -DKR_EMUL_TSAN and run on the emulator with every CUDA thread a
+// ThreadSanitizer fiber (tests/emul/cuda_emul.h, "RACE DETECTION").  Each case drives the C ABI through one device path on a
+// small synthetic batch; ThreadSanitizer reports every pair of conflicting accesses of two threads of a CTA that no
+// barrier / __syncwarp / mbarrier orders -- the stand-in for `compute-sanitizer --tool racecheck` where there is no GPU.
+// Results are also cross-checked between the device paths (tile join == index scan), so a run that is silent has also
+// computed the right thing.
+//
+//   tools/emul_race.sh [case ...]        (builds tests/emul/_build/race_check and runs it; non-zero exit on any report)
+#include "../../kmers/reps_b200/csrc/kr_api.cu"
+
+#include <cinttypes>
+#include <set>
+#include <tuple>
+
+namespace {
+
+struct Rng { uint64_t s; uint32_t next() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 11); } uint32_t below(uint32_t n) { return next() % n; } };
+const char AA[] = "ACDEFGHIKLMNPQRSTVWY";
+
+struct Batch { std::vector<uint8_t> res; std::vector<uint64_t> off{0}; uint32_t n() const { return (uint32_t)off.size() - 1; }
+               void add(const std::string &s) { res.insert(res.end(), s.begin(), s.end()); off.push_back(res.size()); } };
+
+// `n` sequences in `nfam` families (a root, point mutations, a random cut), plus the special cases the kernels branch on
+Batch families(uint64_t seed, uint32_t n, uint32_t nfam, uint32_t len, bool specials) {
+    Rng r{seed * 0x9E3779B97F4A7C15ull + 1};
+    std::vector<std::string> roots(nfam);
+    for (auto &s : roots) { s.resize(len + r.below(len / 2 + 1)); for (auto &c : s) c = AA[r.below(20)]; }
+    Batch b;
+    for (uint32_t i = 0; i < n; ++i) {
+        std::string s = roots[r.below(nfam)];
+        const uint32_t mut = (uint32_t)s.size() * r.below(4) / 20;
+        for (uint32_t k = 0; k < mut; ++k) s[r.below((uint32_t)s.size())] = AA[r.below(20)];
+        s.resize(s.size() / 2 + r.below((uint32_t)s.size() / 2 + 1));
+        b.add(s);
+    }
+    if (specials) {
+        b.add(""); b.add("MKV"); b.add("MKV"); b.add(std::string(400, 'A'));                 // k-mer-less, equal k-mer-less, one crowded bucket
+        std::string lng(700, 'A'); for (auto &c : lng) c = AA[r.below(20)]; b.add(lng);        // 513..1024 k-mers: the register network
+        std::string xl(1500, 'A'); for (auto &c : xl) c = AA[r.below(20)]; b.add(xl);          // > 1024 k-mers: sorted in global memory
+        b.add(roots[0]); b.add(roots[0]);                                                      // equal sequences
+    }
+    return b;
+}
+
+#define OK(call) do { kr_status st_ = (call); if (st_ != KR_OK) { fprintf(stderr, "race_check: %s failed (%d): %s\n", #call, st_, kr_last_error(ctx)); exit(3); } } while (0)
+
+std::vector<int32_t> full_matrix(kr_ctx *ctx, kr_seqset *a, kr_seqset *b, uint32_t rows, uint32_t cols) {
+    std::vector<int32_t> m((size_t)rows * cols);
+    kr_matrix_desc d{}; d.elem = KR_ELEM_I32; d.layout = KR_LAYOUT_FULL; d.row_begin = 0; d.row_end = rows;
+    OK(kr_sim_matrix(ctx, a, b, &d, m.data()));
+    return m;
+}
+
+// one context per device path: encode, dense matrices in every layout, sparse cells, pairs -- and the paths must agree
+void case_matrix(int K, uint32_t n, bool specials) {
+    Batch b = families(100 + K, n, 5, 90, specials);
+    std::vector<int32_t> ref;
+    for (uint32_t path : {KR_FORCE_JOIN, KR_FORCE_INDEX}) {
+        kr_ctx *ctx = nullptr;
+        OK(kr_create(0, K, KR_IDENT_IS_INFINITY | path, &ctx));
+        kr_seqset *s = nullptr;
+        OK(kr_encode(ctx, b.res.data(), b.off.data(), b.n(), &s));
+        std::vector<int32_t> m = full_matrix(ctx, s, nullptr, b.n(), b.n());
+        if (ref.empty()) ref = m; else if (ref != m) { fprintf(stderr, "race_check: the two device paths disagree (K=%d)\n", K); exit(4); }
+        for (uint32_t layout : {KR_LAYOUT_TRIANGLE, KR_LAYOUT_BLOCKTRI}) {
+            kr_matrix_desc d{}; d.elem = KR_ELEM_U16; d.layout = layout; d.row_begin = 0; d.row_end = b.n();
+            std::vector<uint16_t> t(kr_matrix_elems(b.n(), b.n(), layout, 0, b.n()) + 8);
+            OK(kr_sim_matrix(ctx, s, nullptr, &d, t.data()));
+            size_t at = 0;
+            for (uint32_t i = 0; i < b.n(); ++i)
+                for (uint32_t j = layout == KR_LAYOUT_TRIANGLE ? i + 1 : (i & ~255u); j < b.n(); ++j, ++at)
+                    if (t[at] != (uint16_t)ref[(size_t)i * b.n() + j]) { fprintf(stderr, "race_check: layout %u cell (%u,%u)\n", layout, i, j); exit(4); }
+        }
+        {   // sparse cells, packed
+            kr_matrix_desc d{}; d.elem = KR_ELEM_I32; d.layout = KR_LAYOUT_TRIANGLE; d.row_begin = 0; d.row_end = b.n();
+            std::vector<uint64_t> cells((size_t)b.n() * b.n());
+            uint64_t cnt = 0;
+            OK(kr_sim_matrix_sparse64(ctx, s, nullptr, &d, 1, cells.data(), cells.size(), &cnt));
+            uint64_t want = 0;
+            for (uint32_t i = 0; i < b.n(); ++i) for (uint32_t j = i + 1; j < b.n(); ++j) want += ref[(size_t)i * b.n() + j] > 0;
+            if (cnt != want) { fprintf(stderr, "race_check: %" PRIu64 " sparse cells, %" PRIu64 " non-zero pairs\n", cnt, want); exit(4); }
+            for (uint64_t k = 0; k < cnt; ++k)
+                if (KR_CELL_SIM(cells[k]) != ref[(size_t)KR_CELL_ROW(cells[k]) * b.n() + KR_CELL_COL(cells[k])]) { fprintf(stderr, "race_check: sparse cell value\n"); exit(4); }
+        }
+        {   // pairs
+            std::vector<uint32_t> ia, ib;
+            for (uint32_t i = 0; i < b.n(); i += 3) { ia.push_back(i); ib.push_back((i * 7 + 1) % b.n()); }
+            std::vector<int32_t> sim(ia.size()); std::vector<uint8_t> ident(ia.size());
+            OK(kr_sim_pairs(ctx, s, ia.data(), s, ib.data(), ia.size(), sim.data(), ident.data()));
+            for (size_t k = 0; k < ia.size(); ++k)
+                if (sim[k] != ref[(size_t)ia[k] * b.n() + ib[k]]) { fprintf(stderr, "race_check: kr_sim_pairs (%u,%u)\n", ia[k], ib[k]); exit(4); }
+        }
+        kr_seqset_free(s);
+        kr_destroy(ctx);
+    }
+}
+
+// findClosest with ranks + greedy build on both paths; the results must agree
+void case_db(int K) {
+    Batch reps = families(7, 300, 12, 100, true), q = families(8, 120, 12, 100, true);
+    std::vector<int32_t> sim0; std::vector<uint32_t> first0, last0; std::vector<uint8_t> added0;
+    for (uint32_t path : {KR_FORCE_JOIN, KR_FORCE_INDEX}) {
+        kr_ctx *ctx = nullptr;
+        OK(kr_create(0, K, KR_IDENT_IS_INFINITY | path, &ctx));
+        kr_db *db = nullptr;
+        OK(kr_db_create(ctx, &db));
+        OK(kr_db_append(ctx, db, reps.res.data(), reps.off.data(), 200));
+        OK(kr_db_append(ctx, db, reps.res.data(), reps.off.data() + 200, reps.n() - 200));      // second segment / tail level
+        std::vector<uint32_t> rank(reps.n());
+        for (uint32_t i = 0; i < reps.n(); ++i) rank[i] = (i * 131u) % reps.n();      // 131 is coprime to every n used here? checked below
+        { std::set<uint32_t> u(rank.begin(), rank.end()); if (u.size() != rank.size()) for (uint32_t i = 0; i < reps.n(); ++i) rank[i] = reps.n() - 1 - i; }
+        OK(kr_db_set_ranks(ctx, db, rank.data(), reps.n()));
+        kr_seqset *qs = nullptr;
+        OK(kr_encode(ctx, q.res.data(), q.off.data(), q.n(), &qs));
+        std::vector<int32_t> sim(q.n()); std::vector<uint32_t> first(q.n()), last(q.n());
+        OK(kr_db_find_closest(ctx, db, qs, sim.data(), first.data(), last.data()));
+        std::vector<uint8_t> rep(q.n());
+        OK(kr_db_any_ge(ctx, db, qs, 20, rep.data()));
+        for (uint32_t i = 0; i < q.n(); ++i) if ((sim[i] >= 20) != (rep[i] != 0)) { fprintf(stderr, "race_check: kr_db_any_ge vs findClosest at %u\n", i); exit(4); }
+        // greedy build of the queries into a fresh database, small batches (score / resolve / accept, tail level, compaction)
+        kr_db *db2 = nullptr;
+        OK(kr_db_create(ctx, &db2));
+        std::vector<uint8_t> added(q.n());
+        OK(kr_greedy_build(ctx, db2, qs, 15, 16, added.data()));
+        if (sim0.empty()) { sim0 = sim; first0 = first; last0 = last; added0 = added; }
+        else if (sim0 != sim || first0 != first || last0 != last || added0 != added) { fprintf(stderr, "race_check: the two device paths disagree (db, K=%d)\n", K); exit(4); }
+        kr_db_free(db2);
+        kr_seqset_free(qs);
+        kr_db_free(db);
+        kr_destroy(ctx);
+    }
+}
+
+// export block lists, import them as 3 shards, join the imported set (the path that faulted in round 1)
+void case_shards() {
+    Batch b = families(21, 700, 9, 80, true);
+    kr_ctx *ctx = nullptr;
+    OK(kr_create(0, 8, KR_IDENT_IS_INFINITY | KR_FORCE_JOIN, &ctx));
+    kr_seqset *whole = nullptr;
+    OK(kr_encode(ctx, b.res.data(), b.off.data(), b.n(), &whole));
+    std::vector<int32_t> ref = full_matrix(ctx, whole, nullptr, b.n(), b.n());
+    const uint32_t cut[4] = {0, 256, 512, b.n()};
+    kr_seqset *part[3]; kr_blocklists bl[3];
+    for (int k = 0; k < 3; ++k) {
+        OK(kr_encode(ctx, b.res.data(), b.off.data() + cut[k], cut[k + 1] - cut[k], &part[k]));   // (offsets are absolute)
+        OK(kr_seqset_export_blocklists(ctx, part[k], &bl[k]));
+    }
+    uint8_t *d_res = nullptr;
+    cudaMalloc((void **)&d_res, b.res.size() + 16);
+    cudaMemcpy(d_res, b.res.data(), b.res.size(), cudaMemcpyHostToDevice);
+    kr_seqset *imp = nullptr;
+    OK(kr_seqset_import_blocklists(ctx, bl, 3, d_res, b.off.data(), b.n(), &imp));
+    if (full_matrix(ctx, imp, nullptr, b.n(), b.n()) != ref) { fprintf(stderr, "race_check: imported shards differ\n"); exit(4); }
+    kr_seqset_free(imp);
+    for (int k = 0; k < 3; ++k) kr_seqset_free(part[k]);
+    kr_seqset_free(whole);
+    cudaFree(d_res);
+    kr_destroy(ctx);
+}
+
+// Positive controls (kernels of this file, not of the product): the detector must report each of these, or a silent run
+// of the product cases means nothing.  `tools/emul_race.sh` runs them separately and requires a report from every one.
+__global__ void k_ctl_missing_syncthreads(u32 *out) {
+    __shared__ u32 buf[64];
+    buf[threadIdx.x] = threadIdx.x;
+    out[threadIdx.x] = buf[threadIdx.x ^ 32];          // another warp's word, no __syncthreads in between
+}
+__global__ void k_ctl_missing_syncwarp(u32 *out) {
+    __shared__ u32 buf[32];
+    buf[threadIdx.x] = threadIdx.x;
+    const u32 v = __shfl_xor_sync(0xffffffffu, threadIdx.x, 1);   // a shuffle orders no memory
+    out[threadIdx.x] = buf[threadIdx.x ^ 1] + v;
+}
+__global__ void k_ctl_global_conflict(u32 *out) { out[threadIdx.x >> 1] = threadIdx.x; }   // two threads, one word, different values
+__global__ void k_ctl_clean(u32 *out) {                // the same exchanges, ordered: must stay silent
+    __shared__ u32 buf[64];
+    buf[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    u32 v = buf[threadIdx.x ^ 32];
+    __syncthreads();
+    buf[threadIdx.x] = v;
+    __syncwarp();
+    v += buf[threadIdx.x ^ 1];
+    atomicAdd(&out[0], v);
+    volatile u32 *flag = out + 1;
+    if (threadIdx.x == 0) *flag = 1; else (void)*flag;  // volatile accesses are relaxed atomics
+}
+__global__ void k_ctl_grid_conflict(u32 *out) { if (threadIdx.x == 0) out[0] = blockIdx.x; }   // two CTAs, one word: a race only between CTAs
+void case_control(int which) {
+    u32 *d = nullptr;
+    cudaMalloc((void **)&d, 64 * 4);
+    cudaMemset(d, 0, 64 * 4);
+    if (which == 0) KR_LAUNCH(k_ctl_missing_syncthreads, 1, 64, 0, nullptr, d);
+    if (which == 1) KR_LAUNCH(k_ctl_missing_syncwarp, 1, 32, 0, nullptr, d);
+    if (which == 2) KR_LAUNCH(k_ctl_global_conflict, 1, 64, 0, nullptr, d);
+    if (which == 3) KR_LAUNCH(k_ctl_clean, 2, 64, 0, nullptr, d);
+    if (which == 4) KR_LAUNCH(k_ctl_grid_conflict, 2, 32, 0, nullptr, d);
+    cudaFree(d);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    std::set<std::string> want;
+    for (int i = 1; i < argc; ++i) want.insert(argv[i]);
+    auto run = [&](const char *name, auto fn) {
+        if (!want.empty() && !want.count(name)) return;
+        fprintf(stderr, "race_check: %s\n", name);
+        fn();
+    };
+    if (want.count("smoke")) { fprintf(stderr, "race_check: smoke\n"); case_matrix(8, 60, true); }   // the CPU suite's quick pass
+    run("matrix_k8", [] { case_matrix(8, 300, true); });
+    run("matrix_k10", [] { case_matrix(10, 120, true); });      // 32-bit low words in the tile join
+    run("matrix_k3", [] { case_matrix(3, 270, false); });       // few distinct keys: long posting lists, crowded buckets, multi-pass queries
+    run("db_k8", [] { case_db(8); });
+    run("shards", [] { case_shards(); });
+    // controls run only when named (each of the first three MUST be reported)
+    if (want.count("ctl_syncthreads")) case_control(0);
+    if (want.count("ctl_syncwarp")) case_control(1);
+    if (want.count("ctl_global")) case_control(2);
+    if (want.count("ctl_clean")) case_control(3);
+    if (want.count("ctl_grid")) case_control(4);       // reported under KR_EMUL_RACE=grid only
+    fprintf(stderr, "race_check: done\n");
+    return 0;
+}

@@ -1,0 +1,67 @@
+"""TEST INFRASTRUCTURE, CPU only: data-race detection over the emulated device code (tests/emul/race_check.cpp; the long
+form is tools/emul_race.sh).  The product sources are compiled with ThreadSanitizer; every CUDA thread of a CTA is a TSan
+fiber ordered only by what the hardware orders (barriers, __syncwarp, mbarriers), so a missing barrier in a kernel is a
+report -- the stand-in for `compute-sanitizer --tool racecheck` in a container without a GPU.  Here: the detector's own
+controls (three seeded races must be reported, the ordered twin must not) and a quick pass over both device paths of the
+matrix in both race modes; the full set of cases takes ~15 minutes and lives in the script."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "emul", "_build")
+BIN = os.path.join(BUILD, "race_check_suite")
+TSAN = "halt_on_error=0 exitcode=66 history_size=4 report_signal_unsafe=0"
+
+
+@pytest.fixture(scope="module")
+def race_bin():
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    os.makedirs(BUILD, exist_ok=True)
+    srcs = [os.path.join(ROOT, "tests", "emul", f) for f in ("race_check.cpp", "cuda_emul.h")]
+    csrc = os.path.join(ROOT, "kmers", "reps_b200", "csrc")
+    srcs += [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if not os.path.exists(BIN) or any(os.path.getmtime(s) > os.path.getmtime(BIN) for s in srcs):
+        p = subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "--param", "tsan-distinguish-volatile=1", "-pthread",
+                            "-DKR_EMUL", "-DKR_EMUL_TSAN", "-I" + os.path.join(ROOT, "tests", "emul"), "-Wno-unknown-pragmas", "-o", BIN,
+                            os.path.join(ROOT, "tests", "emul", "race_check.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        assert p.returncode == 0, p.stdout.decode()[-3000:]
+    # ThreadSanitizer needs an address-space layout it knows; where it cannot start at all the test has nothing to say
+    probe = subprocess.run([BIN, "none"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=dict(os.environ, TSAN_OPTIONS=TSAN))
+    if probe.returncode != 0 and b"unexpected memory mapping" in probe.stdout:
+        pytest.skip("ThreadSanitizer cannot run in this container: " + probe.stdout.decode()[-200:])
+    return BIN
+
+
+def run(binary, case, grid=False):
+    env = dict(os.environ, TSAN_OPTIONS=TSAN, KR_EMUL_SMS="2")
+    if grid:
+        env["KR_EMUL_RACE"] = "grid"
+    p = subprocess.run([binary, case], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=900)
+    return p.returncode, p.stdout.decode()
+
+
+def test_detector_controls(race_bin):
+    for ctl in ("ctl_syncthreads", "ctl_syncwarp", "ctl_global"):
+        rc, out = run(race_bin, ctl)
+        assert rc == 66 and "WARNING: ThreadSanitizer: data race" in out, "seeded race %s was not reported\n%s" % (ctl, out[-1500:])
+    rc, out = run(race_bin, "ctl_clean")
+    assert rc == 0, "the ordered control was reported:\n" + out[-3000:]
+    rc, out = run(race_bin, "ctl_grid", grid=True)
+    assert rc == 66, "a conflict between two CTAs was not reported in grid mode\n" + out[-1500:]
+    rc, out = run(race_bin, "ctl_grid")
+    assert rc == 0, out[-3000:]
+    rc, out = run(race_bin, "ctl_clean", grid=True)
+    assert rc == 0, out[-3000:]
+
+
+@pytest.mark.parametrize("grid", [False, True])
+def test_device_code_has_no_data_race_quick(race_bin, grid):
+    """encode (counting sort, register network, global-memory sort), block lists + TMA-fed tile join, index build + the
+    three scans, pairs: both device paths on one small batch, results cross-checked, no report"""
+    rc, out = run(race_bin, "smoke", grid=grid)
+    assert rc == 0, out[-4000:]
+    assert "race_check: done" in out
