@@ -22,7 +22,8 @@ using namespace kr;
 // code; for nvcc it expands to exactly the <<< >>> launch it replaces.
 #define KR_T(...) __VA_ARGS__
 #ifdef KR_EMUL
-#define KR_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+#define KR_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu::launch(dim3(grid), dim3(block), (size_t)(smem), stream, [kr_args_ = std::make_tuple(__VA_ARGS__)] { std::apply(kernel, kr_args_); })   // (arguments by value, as a launch takes them)
 #else
 #define KR_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(IX_SORT_THREADS) k_ix_sort(const u32 *start, u
     // 2. exclusive scan of the bucket counts, in place: thread t owns buckets 8t .. 8t+7
     u32 c[8], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { c[k] = cnt[ix_sort_slot(tid * 8 + k)]; sum += c[k]; if (c[k] > IX_SORT_INSERTION_MAX) s_big = 1; }
+    for (int k = 0; k < 8; ++k) { c[k] = cnt[ix_sort_slot(tid * 8 + k)]; sum += c[k]; if (c[k] > IX_SORT_INSERTION_MAX) atomicExch(&s_big, 1u); }   // (several threads may: an atomic, not a plain store)
     u32 incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += up; }
@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(IXQ_WARPS * 32) k_ix_query(IxQueryParams p) {
                     }
                     __syncwarp();
                     // two slots share a score word: clear whole words (a word next to a touched slot holds no other live score)
-                    for (u32 t = lane; t < T; t += 32) ts[tl[t] >> 1] = 0;
+                    // (two lanes may clear the same word: volatile stores, i.e. plain st.volatile.shared, not a data race on one word)
+                    for (u32 t = lane; t < T; t += 32) *reinterpret_cast<volatile u32 *>(&ts[tl[t] >> 1]) = 0;
                     __syncwarp();
                     if (lane == 0) { tc[0] = 0; tc[1] = 0; }
                     __syncwarp();

@@ -21,8 +21,15 @@
 // memory, one of them writing, with no such edge in between, is reported as a data race -- what compute-sanitizer's
 // racecheck reports for shared memory on hardware, extended to global memory.  CTAs of a launch are ordered one after
 // another in this mode.  KR_EMUL_RACE=grid drops that order instead: the CTAs of a launch are concurrent, as on the
-// device, and a global-memory word that two CTAs touch (one writing, no atomics) is reported; shared memory, which the
-// emulated CTAs re-use, is left out of that mode.
+// device, and a global-memory word that two CTAs touch (one writing, no atomics) is reported.  (Shared memory, which the
+// emulated CTAs re-use, gets a fresh history per CTA in both modes.)
+// STREAM ORDER is part of the same model: the emulator still executes every operation at once, in host program order,
+// but each stream carries a clock of its own.  A kernel, an async copy / memset, a stream-ordered allocation or free is
+// attributed to its stream (ordered after the host at the moment of the call and after the stream's earlier work); the
+// host is ordered after a stream only by cudaStreamSynchronize / cudaEventSynchronize / a blocking copy to pageable
+// memory / cudaFree, and one stream after another only by cudaEventRecord + cudaStreamWaitEvent.  A host read of a
+// result before the synchronisation, two streams touching one buffer without an event, a free ordered before the last
+// use: each is a report, although the emulated run itself computed the right thing.
 #pragma once
 #include <algorithm>
 #include <atomic>
@@ -38,13 +45,17 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <tuple>
 #include <vector>
 #include <ucontext.h>
 
+// (runtime calls that act as a stream run on the caller's stack: their own locals are not the detector's business)
+#define KR_NOTSAN __attribute__((no_sanitize("thread")))
 #ifdef KR_EMUL_TSAN
 extern "C" {
 void *__tsan_get_current_fiber(void);
 void *__tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void *fiber);
 void __tsan_switch_to_fiber(void *fiber, unsigned flags);
 void __tsan_acquire(void *addr);
 void __tsan_release(void *addr);
@@ -52,7 +63,6 @@ void AnnotateIgnoreReadsBegin(const char *f, int l);
 void AnnotateIgnoreReadsEnd(const char *f, int l);
 void AnnotateIgnoreWritesBegin(const char *f, int l);
 void AnnotateIgnoreWritesEnd(const char *f, int l);
-void AnnotateBenignRaceSized(const char *f, int l, const volatile void *mem, size_t size, const char *desc);
 // volatile accesses (GCC --param tsan-distinguish-volatile=1 calls these instead of the plain hooks; libtsan itself does
 // not define them): a relaxed atomic load, or a relaxed read-modify-write that leaves the value alone
 #define KR_TSAN_VOL(N, T)                                                                                                      \
@@ -87,6 +97,61 @@ inline void hb_acquire(void *) {}
 }
 #endif
 
+// streams and events (race detection: a stream carries a clock -- `tok` = everything it has completed, `tok_out` = what the
+// kernel in flight has done so far -- and an "actor", the ThreadSanitizer identity its copies / memsets / frees run under)
+typedef struct CUstream_st {
+    int id; char *tok; char *tok_out; void *actor;
+    // race detection: the CUDA threads of kernels on this stream are ThreadSanitizer fibers (and stacks) of this stream alone,
+    // so that thread t of a kernel on one stream and thread t of a kernel on another are two threads to the detector
+    std::vector<void *> fibers; std::vector<uint8_t *> stacks;
+} *cudaStream_t;
+typedef struct CUevent_st { std::chrono::steady_clock::time_point t; char *tok; } *cudaEvent_t;
+namespace emu {
+inline char *launch_tok() { static char t; return &t; }          // host -> stream work: released by the calling host thread
+inline CUstream_st *stream_of(cudaStream_t s) {                   // the null stream is a stream like the others here
+    static CUstream_st *null_stream = nullptr;
+    if (s) return s;
+    Quiet q;
+    if (!null_stream) {
+        null_stream = new CUstream_st{0, new char(0), new char(0), nullptr, {}, {}};
+#ifdef KR_EMUL_TSAN
+        null_stream->actor = __tsan_create_fiber(0);
+#endif
+    }
+    return null_stream;
+}
+inline std::mutex &registry_lock() { static std::mutex m; return m; }
+inline std::vector<CUstream_st *> &all_streams() { static std::vector<CUstream_st *> v; return v; }
+inline std::map<const void *, size_t> &pinned_ranges() { static std::map<const void *, size_t> m; return m; }
+inline bool is_pinned(const void *p) {
+    std::lock_guard<std::mutex> lk(registry_lock());
+    auto &m = pinned_ranges();
+    auto it = m.upper_bound(p);
+    if (it == m.begin()) return false;
+    --it;
+    return (const char *)p < (const char *)it->first + it->second;
+}
+#ifdef KR_EMUL_TSAN
+// The calling host thread executes one operation of a stream: ordered after the host's own past and the stream's, and
+// nothing of it flows back to the host (that takes a synchronisation).  Only ThreadSanitizer's idea of "who" changes; the
+// code keeps running on the caller's stack, so the scope holds nothing but calls into intercepted libc functions.
+struct OnStream {
+    void *prev; CUstream_st *s;
+    KR_NOTSAN explicit OnStream(cudaStream_t st) : s(stream_of(st)) {
+        hb_release(launch_tok());
+        prev = __tsan_get_current_fiber();
+        __tsan_switch_to_fiber(s->actor, 1u);
+        hb_acquire(launch_tok()); hb_acquire(s->tok);
+    }
+    KR_NOTSAN ~OnStream() { hb_release(s->tok); __tsan_switch_to_fiber(prev, 1u); }
+};
+inline void host_waits_for(char *tok) { if (tok) hb_acquire(tok); }
+#else
+struct OnStream { explicit OnStream(cudaStream_t) {} };
+inline void host_waits_for(char *) {}
+#endif
+}
+
 #define __global__
 #define __device__
 #define __host__
@@ -110,6 +175,24 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a) : x(a) {} };
 
+#ifdef KR_EMUL_TSAN
+#include <sys/mman.h>
+// first object of the static shared-memory section, page-aligned; race_check.cpp defines the last one (kr_emu_smem_tail)
+__attribute__((section("kr_emu_smem"), aligned(4096), used)) static char kr_emu_smem_head[8192];
+extern "C" char kr_emu_smem_tail[];
+namespace emu {
+inline void static_smem_renew() {      // (the compiler may lay the section out in either order of definition)
+    char *lo = __start_kr_emu_smem, *hi = __stop_kr_emu_smem;
+    char *h = kr_emu_smem_head, *t = kr_emu_smem_tail;
+    char *first = h < t ? h : t, *last = h < t ? t : h;
+    if (lo != first || (reinterpret_cast<uintptr_t>(lo) & 4095) || last + 8192 != hi) {
+        fprintf(stderr, "cuda_emul: the static shared-memory section is not bracketed by its head and tail objects\n"); abort();
+    }
+    if (mmap(lo, (size_t)(hi - lo), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED, -1, 0) != lo) { perror("cuda_emul: mmap"); abort(); }
+}
+}
+#endif
+
 namespace emu {
 
 // One CUDA thread = one fiber (ucontext); the fibers of a CTA are run round-robin by the launching OS thread, so
@@ -126,7 +209,7 @@ __asm__(".text\n.weak kr_emu_switch\n.type kr_emu_switch,@function\nkr_emu_switc
         "popq %r15\npopq %r14\npopq %r13\npopq %r12\npopq %rbx\npopq %rbp\nret\n"
         ".size kr_emu_switch, .-kr_emu_switch\n");
 struct Ctx { void *sp = nullptr; };
-inline void ctx_switch(Ctx *from, Ctx *to) { kr_emu_switch(&from->sp, to->sp); }
+KR_NOTSAN inline void ctx_switch(Ctx *from, Ctx *to) { kr_emu_switch(&from->sp, to->sp); }
 inline void ctx_make(Ctx *c, uint8_t *stack, size_t bytes, void (*entry)()) {
     uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~uintptr_t(15);
     void **sp = reinterpret_cast<void **>(top);
@@ -137,7 +220,7 @@ inline void ctx_make(Ctx *c, uint8_t *stack, size_t bytes, void (*entry)()) {
 }
 #else
 struct Ctx { ucontext_t uc; };
-inline void ctx_switch(Ctx *from, Ctx *to) { swapcontext(&from->uc, &to->uc); }
+KR_NOTSAN inline void ctx_switch(Ctx *from, Ctx *to) { swapcontext(&from->uc, &to->uc); }
 inline void ctx_make(Ctx *c, uint8_t *stack, size_t bytes, void (*entry)()) {
     getcontext(&c->uc); c->uc.uc_stack.ss_sp = stack; c->uc.uc_stack.ss_size = bytes; c->uc.uc_link = nullptr;
     makecontext(&c->uc, entry, 0);
@@ -221,9 +304,11 @@ struct Trap {};
 inline std::function<void()> *&cur_body() { static std::function<void()> *f = nullptr; return f; }
 inline bool &trapped() { static bool t = false; return t; }
 
-inline char *cta_tokens() { static char t[2]; return t; }   // [0]: launcher -> threads at CTA start, [1]: threads -> launcher at CTA end
+inline CUstream_st *&cur_stream();
 inline void fiber_main() {
-    hb_acquire(&cta_tokens()[0]);
+    CUstream_st *st;
+    { Quiet q; st = cur_stream(); }
+    hb_acquire(launch_tok()); hb_acquire(st->tok);     // after the host at launch time and after the stream's earlier work
     Sched *s; Fiber *f; std::function<void()> *body;
     { Quiet q; s = sched(); f = &s->fibers[s->cur]; body = cur_body(); }
     try { (*body)(); } catch (Trap &) { trapped() = true; }
@@ -233,12 +318,13 @@ inline void fiber_main() {
     { Quiet q; Block *blk = cur_block(); b0 = &blk->sync; b1 = &blk->warps[f->tid.x >> 5]->bar; }
     b0->drop();                                    // a thread that has left the kernel no longer takes part
     b1->drop();
-    hb_release(&cta_tokens()[1]);                  // (last: nothing this thread touches comes after it)
-    Quiet q;
+    hb_release(st->tok_out);                       // (last: nothing this thread touches comes after it)
+    Ctx *mine, *back;
+    { Quiet q; mine = &f->ctx; back = &s->main; }  // (no ignore scope stays open: the fiber is destroyed with its stream)
 #ifdef KR_EMUL_TSAN
     tsan_to(tsan_main());
 #endif
-    ctx_switch(&f->ctx, &s->main);
+    ctx_switch(mine, back);
     abort();                                       // a finished fiber is never resumed
 }
 
@@ -252,30 +338,28 @@ namespace emu {
 
 inline Warp &my_warp() { const unsigned w = threadIdx.x >> 5; Quiet q; return *cur_block()->warps[w]; }
 
-template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
+inline CUstream_st *&cur_stream() { static CUstream_st *s = nullptr; return s; }
+template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, cudaStream_t stream, F body) {
     std::lock_guard<std::mutex> lk(launch_lock());
+    hb_release(launch_tok());                          // the kernel comes after everything this host thread has done
     Quiet quiet;                                       // the launcher's bookkeeping is not the kernel's memory traffic
+    cur_stream() = stream_of(stream);
     gridDim = grid; blockDim = block;
 #ifdef KR_EMUL_TSAN
-    // one buffer for the life of the process (so that grid mode can exclude it once), and the race mode of this process
-    static std::vector<uint8_t> smem(232448 + 2048);
-    static const bool grid_mode = [] {
-        const char *m = getenv("KR_EMUL_RACE");
-        if (!m || strcmp(m, "grid")) return false;
-        uint8_t *b0 = smem.data();
-        AnnotateBenignRaceSized(__FILE__, __LINE__, b0, smem.size(), "emulated shared memory (re-used by the CTAs of a launch)");
-        if (__start_kr_emu_smem && __stop_kr_emu_smem > __start_kr_emu_smem)
-            AnnotateBenignRaceSized(__FILE__, __LINE__, __start_kr_emu_smem, (size_t)(__stop_kr_emu_smem - __start_kr_emu_smem), "emulated static shared memory");
-        return true;
-    }();
-    if (smem_bytes > 232448) { fprintf(stderr, "cuda_emul: %zu bytes of dynamic shared memory\n", smem_bytes); abort(); }
+    static const bool grid_mode = [] { const char *m = getenv("KR_EMUL_RACE"); return m && !strcmp(m, "grid"); }();
 #else
     const bool grid_mode = false;
-    std::vector<uint8_t> smem(smem_bytes + 2048);
 #endif
+    std::vector<uint8_t> smem(smem_bytes + 2048);
     uint8_t *base = smem.data() + (1024 - (reinterpret_cast<uintptr_t>(smem.data()) & 1023));
     dyn_smem() = base; dyn_smem_size() = smem_bytes;
+#ifdef KR_EMUL_TSAN
+    // (never freed: the kernel is asynchronous to the host in the detector's eyes, so the host may not touch -- or
+    // re-use the memory of -- what the kernel's threads read; the arguments were captured by value into this object)
+    std::function<void()> &fn = *new std::function<void()>(body);
+#else
     std::function<void()> fn = body;
+#endif
     cur_body() = &fn;
     Sched sc;
     sc.fibers.resize(block.x);
@@ -291,14 +375,33 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
         Block &blk = *blkp;
         cur_block() = &blk;
         blockIdx.x = b;
+#ifdef KR_EMUL_TSAN
+        // Every CTA has shared memory of its own on the device; here all CTAs of all launches (of all streams) re-use the same
+        // bytes.  So that the detector does not take that re-use for a conflict, both kinds of shared memory get a fresh
+        // history per CTA: allocating inside the launcher's ignore scope resets ThreadSanitizer's shadow for the range
+        // (malloc for the dynamic part, an anonymous mapping laid over the page-aligned section of the static part).
+        smem = std::vector<uint8_t>(smem_bytes + 2048);
+        base = smem.data() + (1024 - (reinterpret_cast<uintptr_t>(smem.data()) & 1023));
+        dyn_smem() = base;
+        static_smem_renew();
+#endif
         memset(base, 0xCD, smem_bytes);                // shared memory starts undefined in every CTA: make reliance on zeros show
         if (__start_kr_emu_smem && __stop_kr_emu_smem > __start_kr_emu_smem) memset(__start_kr_emu_smem, 0xCD, (size_t)(__stop_kr_emu_smem - __start_kr_emu_smem));
         for (unsigned t = 0; t < block.x; ++t) {
             Fiber &f = sc.fibers[t];
             f.done = false; f.tid = dim3(t);
-            // grid mode: the threads of four consecutive CTAs are four different ThreadSanitizer fibers (with stacks of their
+            // grid mode: the threads of two consecutive CTAs are different ThreadSanitizer fibers (with stacks of their
             // own), so that thread t of one CTA and thread t of the next are not "the same thread" to the detector
-            if (grid_mode) f.stack = fiber_stack((b & 3) * block.x + t, stack_bytes);
+#ifdef KR_EMUL_TSAN
+            {
+                CUstream_st *st = cur_stream();
+                const unsigned idx = grid_mode ? (b & 1) * block.x + t : t;
+                if (st->stacks.size() <= idx) { st->stacks.resize(idx + 1, nullptr); st->fibers.resize(idx + 1, nullptr); }
+                if (!st->stacks[idx]) st->stacks[idx] = static_cast<uint8_t *>(malloc(stack_bytes));
+                if (!st->fibers[idx]) st->fibers[idx] = __tsan_create_fiber(0);
+                f.stack = st->stacks[idx];
+            }
+#endif
             ctx_make(&f.ctx, f.stack, stack_bytes, fiber_main);
         }
         sc.idle_yields = 0;
@@ -313,25 +416,42 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F body)
             uint64_t x = 0x9E3779B97F4A7C15ull * (b + 1) + block.x;
             for (unsigned t = block.x; t > 1; --t) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; std::swap(order[t - 1], order[x % t]); }
         }
-        hb_release(&cta_tokens()[0]);                  // everything the host and the earlier CTAs did is visible to this CTA's threads
         for (unsigned live = block.x; live;) {
             live = 0;
             for (unsigned ti = 0; ti < block.x; ++ti) {
                 const unsigned t = order[ti];
                 if (sc.fibers[t].done) continue;
                 sc.cur = t;
+                Ctx *to = &sc.fibers[t].ctx;           // (nothing of the launcher's is touched under the thread's identity)
 #ifdef KR_EMUL_TSAN
-                tsan_to(tsan_fiber(grid_mode ? (b & 3) * block.x + t : t));
+                tsan_to(cur_stream()->fibers[grid_mode ? (b & 1) * block.x + t : t]);
 #endif
-                ctx_switch(&sc.main, &sc.fibers[t].ctx);
+                ctx_switch(&sc.main, to);
                 if (!sc.fibers[t].done) ++live;
             }
         }
-        if (!grid_mode) hb_acquire(&cta_tokens()[1]);  // ... and what they did, to the host and the later CTAs
+#ifdef KR_EMUL_TSAN
+        // CTA mode: what this CTA did is the stream's past for the next CTA (nothing flows to the host: a launch is asynchronous)
+        if (!grid_mode) { void *me = __tsan_get_current_fiber(); CUstream_st *st = cur_stream(); __tsan_switch_to_fiber(st->actor, 1u);
+                          hb_acquire(st->tok_out); hb_release(st->tok); __tsan_switch_to_fiber(me, 1u); }
+#endif
         cur_block() = nullptr;
         if (trapped()) { fprintf(stderr, "cuda_emul: kernel trapped in block %u\n", b); abort(); }
     }
-    if (grid_mode) hb_acquire(&cta_tokens()[1]);       // grid mode: only the end of the launch orders its CTAs before what follows
+#ifdef KR_EMUL_TSAN
+    // grid mode: only the end of the launch orders its CTAs before what follows on the stream
+    if (grid_mode) { void *me = __tsan_get_current_fiber(); CUstream_st *st = cur_stream(); __tsan_switch_to_fiber(st->actor, 1u);
+                     hb_acquire(st->tok_out); hb_release(st->tok); __tsan_switch_to_fiber(me, 1u); }
+#endif
+#ifdef KR_EMUL_TSAN
+    // ThreadSanitizer multiplexes 256 thread slots and loses history when more threads than that are alive: the identities of
+    // a wide launch (the 800-thread tile join, grid mode) are given back as soon as it has ended (the stacks stay; the next
+    // launch on this stream is ordered after this one through the stream's clock)
+    if (cur_stream()->fibers.size() > 192) {
+        for (void *f : cur_stream()->fibers) if (f) __tsan_destroy_fiber(f);
+        std::fill(cur_stream()->fibers.begin(), cur_stream()->fibers.end(), nullptr);
+    }
+#endif
     sched() = nullptr;
 }
 
@@ -489,8 +609,6 @@ inline void *smem_ptr(uint32_t a) {
 // ---- the runtime API subset kr_api.cu uses (single device, synchronous streams) -------------------------------------
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorEmul = 1 };
-typedef struct CUstream_st { int id; } *cudaStream_t;
-typedef struct CUevent_st { std::chrono::steady_clock::time_point t; } *cudaEvent_t;
 typedef struct CUmempool_st { int id; } *cudaMemPool_t;
 enum { cudaMemAllocationTypePinned = 1, cudaMemLocationTypeDevice = 1 };
 struct cudaMemLocation { int type = 0, id = 0; };
@@ -504,30 +622,92 @@ inline cudaError_t cudaGetDeviceCount(int *n) { const char *s = getenv("KR_EMUL_
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp(); if (const char *s = getenv("KR_EMUL_SMS")) p->multiProcessorCount = atoi(s); return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new CUstream_st{0}; return cudaSuccess; }
-inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new CUevent_st(); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+    CUstream_st *st = new CUstream_st{1, new char(0), new char(0), nullptr, {}, {}};
+#ifdef KR_EMUL_TSAN
+    st->actor = __tsan_create_fiber(0);
+#endif
+    { std::lock_guard<std::mutex> lk(emu::registry_lock()); emu::all_streams().push_back(st); }
+    *s = st;
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) {      // (the record is kept: an event may still name the stream's clock)
+    std::lock_guard<std::mutex> lk(emu::registry_lock());
+    auto &v = emu::all_streams();
+    v.erase(std::remove(v.begin(), v.end(), s), v.end());
+#ifdef KR_EMUL_TSAN
+    for (void *f : s->fibers) if (f) __tsan_destroy_fiber(f);
+    for (uint8_t *st : s->stacks) free(st);
+    s->fibers.clear(); s->stacks.clear();
+#endif
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { emu::host_waits_for(emu::stream_of(s)->tok); return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronizeEmul() {              // what a blocking cudaFree / cudaMalloc implies
+    std::vector<CUstream_st *> v;
+    { std::lock_guard<std::mutex> lk(emu::registry_lock()); v = emu::all_streams(); }
+    for (CUstream_st *st : v) emu::host_waits_for(st->tok);
+    emu::host_waits_for(emu::stream_of(nullptr)->tok);
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new CUevent_st(); (*e)->tok = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
-inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
+KR_NOTSAN inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {      // the event takes the stream's clock as of now (a fresh token per record)
+    char *tok = new char(0);
+    { emu::OnStream on(s); emu::hb_release(tok); }
+    emu::Quiet q;
+    e->t = std::chrono::steady_clock::now(); e->tok = tok;
+    return cudaSuccess;
+}
+KR_NOTSAN inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    char *tok;
+    { emu::Quiet q; tok = e->tok; }
+    if (tok) { emu::OnStream on(s); emu::hb_acquire(tok); }
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { char *tok; { emu::Quiet q; tok = e->tok; } emu::host_waits_for(tok); return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { emu::Quiet q; *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
 inline cudaError_t cudaMemPoolCreate(cudaMemPool_t *p, const cudaMemPoolProps *) { *p = new CUmempool_st{1}; return cudaSuccess; }
 inline cudaError_t cudaMemPoolDestroy(cudaMemPool_t p) { delete p; return cudaSuccess; }
 inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 // allocations are 256-byte aligned like cudaMalloc's and poisoned so that reads of uninitialised device memory show
-inline cudaError_t cudaMalloc(void **p, size_t n) { if (posix_memalign(p, 256, n ? n : 1)) return cudaErrorEmul; memset(*p, 0xCD, n); return cudaSuccess; }
+KR_NOTSAN inline cudaError_t cudaMalloc(void **p, size_t n) { if (posix_memalign(p, 256, n ? n : 1)) return cudaErrorEmul; memset(*p, 0xCD, n); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
-inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
-inline cudaError_t cudaMallocFromPoolAsync(void **p, size_t n, cudaMemPool_t, cudaStream_t) { return cudaMalloc(p, n); }
-inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
-inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorEmul; }
-inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
-inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
-inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { return cudaMemset(d, v, n); }
+// stream-ordered allocation and release: the memory exists from this point of the stream on, and is gone after that one
+KR_NOTSAN inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t s) {
+    void *q = nullptr; cudaError_t r;
+    { emu::OnStream on(s); r = cudaMalloc(&q, n); }
+    *p = q;
+    return r;
+}
+inline cudaError_t cudaMallocFromPoolAsync(void **p, size_t n, cudaMemPool_t, cudaStream_t s) { return cudaMallocAsync(p, n, s); }
+inline cudaError_t cudaFree(void *p) { cudaDeviceSynchronizeEmul(); free(p); return cudaSuccess; }      // cudaFree synchronises the device
+KR_NOTSAN inline cudaError_t cudaFreeAsync(void *p, cudaStream_t s) { emu::OnStream on(s); free(p); return cudaSuccess; }
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) {
+    *p = malloc(n ? n : 1);
+    if (!*p) return cudaErrorEmul;
+    std::lock_guard<std::mutex> lk(emu::registry_lock());
+    emu::pinned_ranges()[*p] = n ? n : 1;
+    return cudaSuccess;
+}
+inline cudaError_t cudaFreeHost(void *p) { { std::lock_guard<std::mutex> lk(emu::registry_lock()); emu::pinned_ranges().erase(p); } free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { cudaDeviceSynchronizeEmul(); if (n) memmove(d, s, n); return cudaSuccess; }
+// An asynchronous copy belongs to its stream.  Pageable host memory makes it partly synchronous, as on the device: a
+// pageable SOURCE is staged before the call returns (the host may re-use it at once), a pageable DESTINATION is complete
+// when the call returns.  Pinned memory (cudaHostAlloc) gets neither favour.
+KR_NOTSAN inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    if (k == cudaMemcpyHostToDevice && !emu::is_pinned(s)) {
+        void *stage = malloc(n);
+        memcpy(stage, s, n);                               // read by the host, now
+        { emu::OnStream on(st); memcpy(d, stage, n); free(stage); }
+        return cudaSuccess;
+    }
+    { emu::OnStream on(st); memmove(d, s, n); }
+    if (k == cudaMemcpyDeviceToHost && !emu::is_pinned(d)) emu::host_waits_for(emu::stream_of(st)->tok);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { cudaDeviceSynchronizeEmul(); if (n) memset(d, v, n); return cudaSuccess; }
+KR_NOTSAN inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t s) { if (n) { emu::OnStream on(s); memset(d, v, n); } return cudaSuccess; }

@@ -11,6 +11,7 @@
 
 #include <cinttypes>
 #include <set>
+#include <thread>
 #include <tuple>
 
 namespace {
@@ -159,6 +160,133 @@ void case_shards() {
     kr_destroy(ctx);
 }
 
+// What bench.py does: device-resident inputs and outputs through the _device entry points (no host synchronisation inside
+// the step: encode -> matrix -> free the previous set, stream-ordered), then the e2e step with PINNED host buffers, whose
+// copies are truly asynchronous -- the library has to synchronise before it returns, or the host reads below are races.
+void case_bench_like() {
+    Batch b = families(41, 520, 8, 90, true), q = families(42, 64, 8, 90, false);
+    for (uint32_t path : {KR_FORCE_INDEX, KR_FORCE_JOIN}) {
+        kr_ctx *ctx = nullptr;
+        OK(kr_create(0, 8, KR_IDENT_IS_INFINITY | path, &ctx));
+        uint8_t *d_res = nullptr;
+        cudaMalloc((void **)&d_res, b.res.size() + 16);
+        cudaMemcpy(d_res, b.res.data(), b.res.size(), cudaMemcpyHostToDevice);
+        const uint64_t elems = kr_matrix_elems(b.n(), b.n(), KR_LAYOUT_BLOCKTRI, 0, b.n());
+        uint16_t *d_out = nullptr;
+        cudaMalloc((void **)&d_out, elems * 2 + 16);
+        kr_matrix_desc d{}; d.elem = KR_ELEM_U16; d.layout = KR_LAYOUT_BLOCKTRI; d.row_begin = 0; d.row_end = b.n();
+        kr_seqset *prev = nullptr;
+        OK(kr_timer_begin(ctx));
+        for (int step = 0; step < 3; ++step) {
+            kr_seqset *cur = nullptr;
+            OK(kr_encode_device(ctx, d_res, b.off.data(), b.n(), &cur));
+            OK(kr_sim_matrix_device(ctx, cur, nullptr, &d, d_out));
+            if (prev) kr_seqset_free(prev);
+            prev = cur;
+        }
+        double ms = 0;
+        OK(kr_timer_end(ctx, &ms));                    // synchronises
+        std::vector<uint16_t> dense(elems);
+        cudaMemcpy(dense.data(), d_out, elems * 2, cudaMemcpyDeviceToHost);
+        // findClosest through the device entry points, chunked as the bench does
+        kr_db *db = nullptr;
+        OK(kr_db_create(ctx, &db));
+        OK(kr_db_append_set(ctx, db, prev, nullptr, 0));
+        std::vector<uint32_t> idx(300); for (uint32_t i = 0; i < 300; ++i) idx[i] = i;
+        OK(kr_db_append_set(ctx, db, prev, idx.data(), 300));
+        uint8_t *d_q = nullptr; int32_t *d_sim = nullptr; uint32_t *d_first = nullptr, *d_last = nullptr;
+        cudaMalloc((void **)&d_q, q.res.size() + 16); cudaMemcpy(d_q, q.res.data(), q.res.size(), cudaMemcpyHostToDevice);
+        cudaMalloc((void **)&d_sim, q.n() * 4); cudaMalloc((void **)&d_first, q.n() * 4); cudaMalloc((void **)&d_last, q.n() * 4);
+        for (int step = 0; step < 2; ++step)
+            for (uint32_t a0 = 0; a0 < q.n(); a0 += 32) {
+                kr_seqset *qs = nullptr;
+                OK(kr_encode_device(ctx, d_q, q.off.data() + a0, std::min(32u, q.n() - a0), &qs));
+                OK(kr_db_find_closest_device(ctx, db, qs, d_sim + a0, d_first + a0, d_last + a0));
+                kr_seqset_free(qs);
+            }
+        OK(kr_synchronize(ctx));
+        std::vector<int32_t> sim(q.n());
+        cudaMemcpy(sim.data(), d_sim, q.n() * 4, cudaMemcpyDeviceToHost);
+        // e2e: pinned buffers
+        uint8_t *h_res = nullptr; uint64_t *h_cells = nullptr;
+        OK(kr_host_alloc(ctx, b.res.size() + 1, (void **)&h_res));
+        OK(kr_host_alloc(ctx, 8 * 200000, (void **)&h_cells));
+        memcpy(h_res, b.res.data(), b.res.size());
+        uint64_t total = 0;
+        for (int step = 0; step < 2; ++step) {
+            kr_seqset *s = nullptr;
+            OK(kr_encode(ctx, h_res, b.off.data(), b.n(), &s));
+            uint64_t cnt = 0;
+            kr_matrix_desc t{}; t.elem = KR_ELEM_I32; t.layout = KR_LAYOUT_TRIANGLE; t.row_begin = 0; t.row_end = b.n();
+            OK(kr_sim_matrix_sparse64(ctx, s, nullptr, &t, 1, h_cells, 200000, &cnt));
+            for (uint64_t k = 0; k < cnt && k < 200000; ++k) total += KR_CELL_SIM(h_cells[k]);      // the host reads the pinned result at once
+            h_res[0] = h_res[0];                                                                     // ... and may write its input again
+            kr_seqset_free(s);
+        }
+        // the dense result and the sparse cells describe the same matrix
+        uint64_t dsum = 0; size_t at = 0;
+        for (uint32_t i = 0; i < b.n(); ++i) for (uint32_t j = (i & ~255u); j < b.n(); ++j, ++at) if (j > i) dsum += dense[at];
+        if (dsum * 2 != total) { fprintf(stderr, "race_check: dense stripe and sparse cells disagree (%" PRIu64 " vs %" PRIu64 ")\n", dsum * 2, total); exit(4); }
+        kr_host_free(ctx, h_res); kr_host_free(ctx, h_cells);
+        kr_db_free(db);
+        kr_seqset_free(prev);
+        cudaFree(d_q); cudaFree(d_sim); cudaFree(d_first); cudaFree(d_last); cudaFree(d_res); cudaFree(d_out);
+        kr_destroy(ctx);
+    }
+}
+
+// kr_multi: three emulated devices behind one handle.  The worker threads are real OS threads, so here ThreadSanitizer
+// also checks the HOST side of the library -- the hand-over of jobs to the workers, their writes into slices of the
+// caller's buffers, the shared error string -- and concurrent callers of one handle (NeighborProcessor --para).
+void case_multi() {
+    setenv("KR_EMUL_DEVICES", "3", 1);
+    Batch b = families(31, 600, 8, 90, true), q = families(32, 90, 8, 90, true);
+    kr_ctx *ctx = nullptr;       // (for the OK macro's message only)
+    kr_multi *m = nullptr;
+    const int devs[3] = {0, 1, 2};
+    if (kr_multi_create(devs, 3, 8, KR_IDENT_IS_INFINITY, &m) != KR_OK) { fprintf(stderr, "race_check: kr_multi_create: %s\n", kr_multi_last_error(nullptr)); exit(3); }
+    // reference: one plain context
+    OK(kr_create(0, 8, KR_IDENT_IS_INFINITY, &ctx));
+    kr_seqset *s = nullptr;
+    OK(kr_encode(ctx, b.res.data(), b.off.data(), b.n(), &s));
+    std::vector<int32_t> ref = full_matrix(ctx, s, nullptr, b.n(), b.n());
+    std::vector<int32_t> got((size_t)b.n() * b.n());
+    if (kr_multi_sim_matrix(m, b.res.data(), b.off.data(), b.n(), nullptr, nullptr, 0, KR_ELEM_I32, KR_LAYOUT_FULL, got.data()) != KR_OK || got != ref) {
+        fprintf(stderr, "race_check: kr_multi_sim_matrix: %s\n", kr_multi_last_error(m)); exit(4);
+    }
+    kr_multi_db *mdb = nullptr;
+    if (kr_multi_db_create(m, &mdb) != KR_OK || kr_multi_db_append(m, mdb, b.res.data(), b.off.data(), b.n()) != KR_OK) { fprintf(stderr, "race_check: kr_multi_db: %s\n", kr_multi_last_error(m)); exit(3); }
+    kr_db *db = nullptr;
+    OK(kr_db_create(ctx, &db));
+    OK(kr_db_append(ctx, db, b.res.data(), b.off.data(), b.n()));
+    kr_seqset *qs = nullptr;
+    OK(kr_encode(ctx, q.res.data(), q.off.data(), q.n(), &qs));
+    std::vector<int32_t> sim(q.n()); std::vector<uint32_t> first(q.n()), last(q.n());
+    OK(kr_db_find_closest(ctx, db, qs, sim.data(), first.data(), last.data()));
+    // two caller threads on the one handle at the same time
+    auto caller = [&](int who) {
+        std::vector<int32_t> msim(q.n()); std::vector<uint32_t> mfirst(q.n()), mlast(q.n());
+        for (int rep = 0; rep < 2; ++rep) {
+            if (kr_multi_db_find_closest(m, mdb, q.res.data(), q.off.data(), q.n(), msim.data(), mfirst.data(), mlast.data()) != KR_OK ||
+                msim != sim || mfirst != first || mlast != last) { fprintf(stderr, "race_check: kr_multi_db_find_closest (caller %d): %s\n", who, kr_multi_last_error(m)); exit(4); }
+        }
+    };
+    std::thread t1(caller, 1), t2(caller, 2);
+    t1.join(); t2.join();
+    // greedy build over the handle == over one context
+    std::vector<uint8_t> a1(q.n()), a2(q.n());
+    kr_db *db2 = nullptr; kr_multi_db *mdb2 = nullptr;
+    OK(kr_db_create(ctx, &db2));
+    OK(kr_greedy_build(ctx, db2, qs, 15, 16, a1.data()));
+    if (kr_multi_db_create(m, &mdb2) != KR_OK || kr_multi_greedy_build(m, mdb2, q.res.data(), q.off.data(), q.n(), 15, 16, a2.data()) != KR_OK || a1 != a2) {
+        fprintf(stderr, "race_check: kr_multi_greedy_build: %s\n", kr_multi_last_error(m)); exit(4);
+    }
+    kr_multi_db_free(mdb2); kr_multi_db_free(mdb);
+    kr_db_free(db2); kr_db_free(db); kr_seqset_free(qs); kr_seqset_free(s);
+    kr_destroy(ctx);
+    kr_multi_destroy(m);
+}
+
 // Positive controls (kernels of this file, not of the product): the detector must report each of these, or a silent run
 // of the product cases means nothing.  `tools/emul_race.sh` runs them separately and requires a report from every one.
 __global__ void k_ctl_missing_syncthreads(u32 *out) {
@@ -196,10 +324,52 @@ void case_control(int which) {
     if (which == 2) KR_LAUNCH(k_ctl_global_conflict, 1, 64, 0, nullptr, d);
     if (which == 3) KR_LAUNCH(k_ctl_clean, 2, 64, 0, nullptr, d);
     if (which == 4) KR_LAUNCH(k_ctl_grid_conflict, 2, 32, 0, nullptr, d);
-    cudaFree(d);
+    cudaFree(d);       // (synchronises the device)
+}
+
+// Stream-order controls: the emulator executes everything at once, so each of these computes the "right" values -- and each
+// is a bug on a device that the detector must report: a host read before the synchronisation, two streams on one buffer
+// without an event, a stream-ordered free that is not ordered after the last use.  The last one is their ordered twin.
+__global__ void k_ctl_fill(u32 *out, u32 v) { out[threadIdx.x] = v + threadIdx.x; }
+u32 case_stream_control(int which) {
+    cudaStream_t a, b;
+    cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking);
+    cudaEvent_t ev; cudaEventCreate(&ev);
+    u32 *d = nullptr, *h = nullptr;
+    cudaMallocAsync((void **)&d, 64 * 4, a);
+    cudaHostAlloc((void **)&h, 64 * 4, cudaHostAllocDefault);
+    u32 sum = 0;
+    KR_LAUNCH(k_ctl_fill, 1, 64, 0, a, d, 7u);
+    if (which == 0) {            // pinned destination: the copy is asynchronous, the host reads too early
+        cudaMemcpyAsync(h, d, 64 * 4, cudaMemcpyDeviceToHost, a);
+        for (int i = 0; i < 64; ++i) sum += h[i];
+        cudaStreamSynchronize(a);
+    } else if (which == 1) {     // a second stream writes the buffer with no event between the two
+        KR_LAUNCH(k_ctl_fill, 1, 64, 0, b, d, 9u);
+        cudaStreamSynchronize(a); cudaStreamSynchronize(b);
+    } else if (which == 2) {     // freed in stream b's order while stream a's kernel may still be running
+        cudaFreeAsync(d, b); d = nullptr;
+        cudaStreamSynchronize(a); cudaStreamSynchronize(b);
+    } else {                     // the ordered twin of all three
+        cudaEventRecord(ev, a);
+        cudaStreamWaitEvent(b, ev, 0);
+        KR_LAUNCH(k_ctl_fill, 1, 64, 0, b, d, 9u);
+        cudaMemcpyAsync(h, d, 64 * 4, cudaMemcpyDeviceToHost, b);
+        cudaStreamSynchronize(b);
+        for (int i = 0; i < 64; ++i) sum += h[i];
+        cudaFreeAsync(d, b); d = nullptr;
+        cudaStreamSynchronize(b);
+    }
+    if (d) { cudaFreeAsync(d, a); cudaStreamSynchronize(a); }
+    cudaFreeHost(h);
+    cudaEventDestroy(ev); cudaStreamDestroy(a); cudaStreamDestroy(b);
+    return sum;
 }
 
 }  // namespace
+
+// last object of the static shared-memory section (see static_smem_renew in cuda_emul.h)
+extern "C" { __attribute__((section("kr_emu_smem"), aligned(4096), used)) char kr_emu_smem_tail[8192]; }
 
 int main(int argc, char **argv) {
     std::set<std::string> want;
@@ -215,11 +385,17 @@ int main(int argc, char **argv) {
     run("matrix_k3", [] { case_matrix(3, 270, false); });       // few distinct keys: long posting lists, crowded buckets, multi-pass queries
     run("db_k8", [] { case_db(8); });
     run("shards", [] { case_shards(); });
+    run("multi", [] { case_multi(); });
+    run("bench_like", [] { case_bench_like(); });
     // controls run only when named (each of the first three MUST be reported)
     if (want.count("ctl_syncthreads")) case_control(0);
     if (want.count("ctl_syncwarp")) case_control(1);
     if (want.count("ctl_global")) case_control(2);
     if (want.count("ctl_clean")) case_control(3);
+    if (want.count("ctl_host_early")) case_stream_control(0);
+    if (want.count("ctl_two_streams")) case_stream_control(1);
+    if (want.count("ctl_free_order")) case_stream_control(2);
+    if (want.count("ctl_streams_clean")) case_stream_control(3);
     if (want.count("ctl_grid")) case_control(4);       // reported under KR_EMUL_RACE=grid only
     fprintf(stderr, "race_check: done\n");
     return 0;

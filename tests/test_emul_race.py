@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE, CPU only: data-race detection over the emulated device code (tests/emul/race_check.cpp; the long
 form is tools/emul_race.sh).  The product sources are compiled with ThreadSanitizer; every CUDA thread of a CTA is a TSan
-fiber ordered only by what the hardware orders (barriers, __syncwarp, mbarriers), so a missing barrier in a kernel is a
-report -- the stand-in for `compute-sanitizer --tool racecheck` in a container without a GPU.  Here: the detector's own
+fiber ordered only by what the hardware orders (barriers, __syncwarp, mbarriers), and every stream has a clock of its own
+(host and streams are ordered only by synchronisations and events), so a missing barrier in a kernel, a host read before
+the synchronisation, or two streams on one buffer without an event is a report -- the stand-in for `compute-sanitizer --tool racecheck` in a container without a GPU.  Here: the detector's own
 controls (three seeded races must be reported, the ordered twin must not) and a quick pass over both device paths of the
 matrix in both race modes; the full set of cases takes ~15 minutes and lives in the script."""
 import os
@@ -26,7 +27,7 @@ def race_bin():
     srcs += [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if not os.path.exists(BIN) or any(os.path.getmtime(s) > os.path.getmtime(BIN) for s in srcs):
         p = subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "--param", "tsan-distinguish-volatile=1", "-pthread",
-                            "-DKR_EMUL", "-DKR_EMUL_TSAN", "-I" + os.path.join(ROOT, "tests", "emul"), "-Wno-unknown-pragmas", "-o", BIN,
+                            "-DKR_EMUL", "-DKR_EMUL_TSAN", "-DKR_ENC_PIPE_MIN=256", "-I" + os.path.join(ROOT, "tests", "emul"), "-Wno-unknown-pragmas", "-o", BIN,
                             os.path.join(ROOT, "tests", "emul", "race_check.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
         assert p.returncode == 0, p.stdout.decode()[-3000:]
     # ThreadSanitizer needs an address-space layout it knows; where it cannot start at all the test has nothing to say
@@ -45,11 +46,16 @@ def run(binary, case, grid=False):
 
 
 def test_detector_controls(race_bin):
-    for ctl in ("ctl_syncthreads", "ctl_syncwarp", "ctl_global"):
+    # missing __syncthreads / missing __syncwarp (a shuffle orders nothing) / two threads on one global word /
+    # host read of a pinned buffer before the synchronisation / two streams on one buffer without an event /
+    # a stream-ordered free not ordered after the last use
+    for ctl in ("ctl_syncthreads", "ctl_syncwarp", "ctl_global", "ctl_host_early", "ctl_two_streams", "ctl_free_order"):
         rc, out = run(race_bin, ctl)
         assert rc == 66 and "WARNING: ThreadSanitizer: data race" in out, "seeded race %s was not reported\n%s" % (ctl, out[-1500:])
     rc, out = run(race_bin, "ctl_clean")
     assert rc == 0, "the ordered control was reported:\n" + out[-3000:]
+    rc, out = run(race_bin, "ctl_streams_clean")
+    assert rc == 0, "the ordered stream control was reported:\n" + out[-3000:]
     rc, out = run(race_bin, "ctl_grid", grid=True)
     assert rc == 66, "a conflict between two CTAs was not reported in grid mode\n" + out[-1500:]
     rc, out = run(race_bin, "ctl_grid")

@@ -7,20 +7,21 @@
 cd "$(dirname "$0")/.."
 B=$PWD/tests/emul/_build
 mkdir -p $B
-g++ -x c++ -std=c++17 -O1 -g -fsanitize=thread --param tsan-distinguish-volatile=1 -pthread -DKR_EMUL -DKR_EMUL_TSAN -Itests/emul \
+g++ -x c++ -std=c++17 -O1 -g -fsanitize=thread --param tsan-distinguish-volatile=1 -pthread -DKR_EMUL -DKR_EMUL_TSAN -DKR_ENC_PIPE_MIN=256 -Itests/emul \
     -Wno-unknown-pragmas -o $B/race_check tests/emul/race_check.cpp || exit 1
 export KR_EMUL_SMS=${KR_EMUL_SMS:-2}
 export TSAN_OPTIONS="halt_on_error=0 exitcode=66 history_size=4 report_signal_unsafe=0 ${TSAN_EXTRA}"
 if [ $# -gt 0 ]; then $B/race_check "$@"; exit $?; fi
 # positive controls first: a detector that cannot see a missing barrier proves nothing by staying silent
-for c in ctl_syncthreads ctl_syncwarp ctl_global; do
+for c in ctl_syncthreads ctl_syncwarp ctl_global ctl_host_early ctl_two_streams ctl_free_order; do
     $B/race_check $c > $B/race_$c.log 2>&1
     [ $? -eq 66 ] || { echo "emul_race: control $c was NOT reported"; exit 2; }
 done
 $B/race_check ctl_clean > $B/race_ctl_clean.log 2>&1 || { echo "emul_race: the clean control was reported"; cat $B/race_ctl_clean.log | head -40; exit 2; }
-echo "emul_race: controls OK (3 reported, 1 silent)"
+$B/race_check ctl_streams_clean > $B/race_ctl_streams_clean.log 2>&1 || { echo "emul_race: the ordered stream control was reported"; head -40 $B/race_ctl_streams_clean.log; exit 2; }
+echo "emul_race: controls OK (6 seeded races reported, 2 ordered twins silent)"
 rc=0
-for c in matrix_k8 matrix_k10 matrix_k3 db_k8 shards; do
+for c in matrix_k8 matrix_k10 matrix_k3 db_k8 shards multi bench_like; do
     $B/race_check $c > $B/race_$c.log 2>&1
     r=$?
     n=$(grep -c "WARNING: ThreadSanitizer" $B/race_$c.log)
