@@ -87,6 +87,17 @@ inline void *tsan_fiber(unsigned t) {      // one ThreadSanitizer fiber per CUDA
     return pool[t];
 }
 inline void *&tsan_main() { static void *m = nullptr; return m; }
+// Who a CUDA thread is to the detector.  ThreadSanitizer multiplexes 256 thread slots and loses history when more threads
+// than that are alive, so there are two granularities: a thread of its own (default: what finds a missing __syncwarp; the
+// identities are given back at the end of every launch, so only one CTA's worth is ever alive), or -- KR_EMUL_RACE_ID=warp
+// -- one identity per WARP, kept for the life of the stream: a few dozen identities in all, which is what makes conflicts
+// BETWEEN launches, streams and CTAs (and between the warps of the 800-thread tile join) reliably visible.  The warp
+// build needs --param tsan-instrument-func-entry-exit=0 (32 fibers share one shadow call stack otherwise).
+inline bool warp_identity() { static const bool w = [] { const char *m = getenv("KR_EMUL_RACE_ID"); return m && !strcmp(m, "warp"); }(); return w; }
+inline unsigned tsan_identity(bool grid_mode, unsigned b, unsigned nthreads, unsigned t) {
+    const unsigned per = warp_identity() ? (nthreads + 31) / 32 : nthreads, me = warp_identity() ? t >> 5 : t;
+    return grid_mode ? (b & 1) * per + me : me;
+}
 inline void tsan_to(void *f) { __tsan_switch_to_fiber(f, 1u /* no synchronisation */); }
 }
 #else
@@ -395,11 +406,12 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, cudaStr
 #ifdef KR_EMUL_TSAN
             {
                 CUstream_st *st = cur_stream();
-                const unsigned idx = grid_mode ? (b & 1) * block.x + t : t;
-                if (st->stacks.size() <= idx) { st->stacks.resize(idx + 1, nullptr); st->fibers.resize(idx + 1, nullptr); }
-                if (!st->stacks[idx]) st->stacks[idx] = static_cast<uint8_t *>(malloc(stack_bytes));
+                const unsigned sidx = grid_mode ? (b & 1) * block.x + t : t, idx = tsan_identity(grid_mode, b, block.x, t);
+                if (st->stacks.size() <= sidx) st->stacks.resize(sidx + 1, nullptr);
+                if (st->fibers.size() <= idx) st->fibers.resize(idx + 1, nullptr);
+                if (!st->stacks[sidx]) st->stacks[sidx] = static_cast<uint8_t *>(malloc(stack_bytes));
                 if (!st->fibers[idx]) st->fibers[idx] = __tsan_create_fiber(0);
-                f.stack = st->stacks[idx];
+                f.stack = st->stacks[sidx];
             }
 #endif
             ctx_make(&f.ctx, f.stack, stack_bytes, fiber_main);
@@ -424,7 +436,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, cudaStr
                 sc.cur = t;
                 Ctx *to = &sc.fibers[t].ctx;           // (nothing of the launcher's is touched under the thread's identity)
 #ifdef KR_EMUL_TSAN
-                tsan_to(cur_stream()->fibers[grid_mode ? (b & 1) * block.x + t : t]);
+                tsan_to(cur_stream()->fibers[tsan_identity(grid_mode, b, block.x, t)]);
 #endif
                 ctx_switch(&sc.main, to);
                 if (!sc.fibers[t].done) ++live;
@@ -444,10 +456,9 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, cudaStr
                      hb_acquire(st->tok_out); hb_release(st->tok); __tsan_switch_to_fiber(me, 1u); }
 #endif
 #ifdef KR_EMUL_TSAN
-    // ThreadSanitizer multiplexes 256 thread slots and loses history when more threads than that are alive: the identities of
-    // a wide launch (the 800-thread tile join, grid mode) are given back as soon as it has ended (the stacks stay; the next
+    // per-thread identities are given back as soon as the launch has ended (see tsan_identity; the stacks stay: the next
     // launch on this stream is ordered after this one through the stream's clock)
-    if (cur_stream()->fibers.size() > 192) {
+    if (!warp_identity()) {
         for (void *f : cur_stream()->fibers) if (f) __tsan_destroy_fiber(f);
         std::fill(cur_stream()->fibers.begin(), cur_stream()->fibers.end(), nullptr);
     }

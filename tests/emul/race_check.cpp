@@ -347,6 +347,15 @@ u32 case_stream_control(int which) {
     } else if (which == 1) {     // a second stream writes the buffer with no event between the two
         KR_LAUNCH(k_ctl_fill, 1, 64, 0, b, d, 9u);
         cudaStreamSynchronize(a); cudaStreamSynchronize(b);
+    } else if (which == 4) {     // the same with wide launches (NT threads x NG CTAs per stream: far more CUDA threads than the detector has slots)
+        const char *e = getenv("NT"), *g = getenv("NG");
+        const unsigned nt = e ? atoi(e) : 512, ng = g ? atoi(g) : 4;
+        u32 *big = nullptr;
+        cudaMallocAsync((void **)&big, 4096 * 4, a);
+        KR_LAUNCH(k_ctl_fill, ng, nt, 0, a, big, 7u);
+        KR_LAUNCH(k_ctl_fill, ng, nt, 0, b, big, 9u);
+        cudaStreamSynchronize(a); cudaStreamSynchronize(b);
+        cudaFreeAsync(big, a);
     } else if (which == 2) {     // freed in stream b's order while stream a's kernel may still be running
         cudaFreeAsync(d, b); d = nullptr;
         cudaStreamSynchronize(a); cudaStreamSynchronize(b);
@@ -395,6 +404,7 @@ int main(int argc, char **argv) {
     if (want.count("ctl_host_early")) case_stream_control(0);
     if (want.count("ctl_two_streams")) case_stream_control(1);
     if (want.count("ctl_free_order")) case_stream_control(2);
+    if (want.count("ctl_two_streams_wide")) case_stream_control(4);
     if (want.count("ctl_streams_clean")) case_stream_control(3);
     if (want.count("ctl_grid")) case_control(4);       // reported under KR_EMUL_RACE=grid only
     fprintf(stderr, "race_check: done\n");
