@@ -160,6 +160,76 @@ void case_shards() {
     kr_destroy(ctx);
 }
 
+// The rest of the ABI, each entry point with a synchronisation discipline of its own: rectangular matrices, row stripes,
+// 16-byte sparse cells, gathered sets, key export / import, and an alphabet error in the middle (the context stays usable).
+void case_misc() {
+    Batch a = families(51, 300, 6, 90, true), b = families(52, 140, 6, 90, true);
+    std::vector<int32_t> ref_rect, ref_self;
+    for (uint32_t path : {KR_FORCE_JOIN, KR_FORCE_INDEX, 0u}) {
+        kr_ctx *ctx = nullptr;
+        OK(kr_create(0, 8, KR_IDENT_IS_INFINITY | path, &ctx));
+        kr_seqset *sa = nullptr, *sb = nullptr;
+        OK(kr_encode(ctx, a.res.data(), a.off.data(), a.n(), &sa));
+        OK(kr_encode(ctx, b.res.data(), b.off.data(), b.n(), &sb));
+        std::vector<int32_t> rect = full_matrix(ctx, sa, sb, a.n(), b.n());
+        if (ref_rect.empty()) ref_rect = rect; else if (rect != ref_rect) { fprintf(stderr, "race_check: rectangular matrix differs between paths\n"); exit(4); }
+        std::vector<int32_t> self = full_matrix(ctx, sa, nullptr, a.n(), a.n());
+        if (ref_self.empty()) ref_self = self; else if (self != ref_self) { fprintf(stderr, "race_check: self matrix differs between paths\n"); exit(4); }
+        {   // second stripe of the block-triangle (the index exists by now: the scan writes the zeros itself)
+            kr_matrix_desc d{}; d.elem = KR_ELEM_U16; d.layout = KR_LAYOUT_BLOCKTRI; d.row_begin = 256; d.row_end = a.n();
+            std::vector<uint16_t> t(kr_matrix_elems(a.n(), a.n(), KR_LAYOUT_BLOCKTRI, 256, a.n()) + 8);
+            OK(kr_sim_matrix(ctx, sa, nullptr, &d, t.data()));
+            size_t at = 0;
+            for (uint32_t i = 256; i < a.n(); ++i) for (uint32_t j = 256; j < a.n(); ++j, ++at)
+                if (t[at] != (uint16_t)ref_self[(size_t)i * a.n() + j]) { fprintf(stderr, "race_check: stripe cell (%u,%u)\n", i, j); exit(4); }
+        }
+        {   // 16-byte sparse cells of the rectangular matrix
+            kr_matrix_desc d{}; d.elem = KR_ELEM_I32; d.layout = KR_LAYOUT_FULL; d.row_begin = 0; d.row_end = a.n();
+            std::vector<uint32_t> cells((size_t)4 * a.n() * b.n());
+            uint64_t cnt = 0, want = 0;
+            OK(kr_sim_matrix_sparse(ctx, sa, sb, &d, 2, cells.data(), (uint64_t)a.n() * b.n(), &cnt));
+            for (int32_t v : ref_rect) want += v >= 2;
+            if (cnt != want) { fprintf(stderr, "race_check: %" PRIu64 " sparse cells, want %" PRIu64 "\n", cnt, want); exit(4); }
+            for (uint64_t k = 0; k < cnt; ++k)
+                if ((int32_t)cells[4 * k + 2] != ref_rect[(size_t)cells[4 * k] * b.n() + cells[4 * k + 1]]) { fprintf(stderr, "race_check: sparse cell\n"); exit(4); }
+        }
+        {   // a gathered set, its keys exported and imported again
+            std::vector<uint32_t> idx;
+            for (uint32_t i = 0; i < a.n(); i += 7) idx.push_back(a.n() - 1 - i);
+            kr_seqset *g = nullptr;
+            OK(kr_seqset_gather(ctx, sa, idx.data(), (uint32_t)idx.size(), &g));
+            std::vector<int32_t> gm = full_matrix(ctx, g, sb, (uint32_t)idx.size(), b.n());
+            for (size_t r = 0; r < idx.size(); ++r) for (uint32_t c = 0; c < b.n(); ++c)
+                if (gm[r * b.n() + c] != ref_rect[(size_t)idx[r] * b.n() + c]) { fprintf(stderr, "race_check: gathered row %zu\n", r); exit(4); }
+            std::vector<uint64_t> keys, koff{0}, roff{0}; std::vector<uint8_t> res;
+            for (uint32_t i = 0; i < 24 && i < idx.size(); ++i) {
+                uint32_t n = 0;
+                OK(kr_seqset_keys(g, i, nullptr, 0, &n) == KR_OK || n ? KR_OK : KR_OK);
+                std::vector<uint64_t> k(n + 1);
+                if (n) OK(kr_seqset_keys(g, i, k.data(), n, &n));
+                keys.insert(keys.end(), k.begin(), k.begin() + n); koff.push_back(keys.size());
+                res.insert(res.end(), a.res.begin() + a.off[idx[i]], a.res.begin() + a.off[idx[i] + 1]); roff.push_back(res.size());
+            }
+            kr_seqset *fk = nullptr;
+            OK(kr_seqset_from_keys(ctx, keys.data(), koff.data(), res.data(), roff.data(), (uint32_t)koff.size() - 1, &fk));
+            std::vector<int32_t> fm = full_matrix(ctx, fk, sb, (uint32_t)koff.size() - 1, b.n());
+            for (size_t r = 0; r + 1 < koff.size(); ++r) for (uint32_t c = 0; c < b.n(); ++c)
+                if (fm[r * b.n() + c] != ref_rect[(size_t)idx[r] * b.n() + c]) { fprintf(stderr, "race_check: key-list set row %zu col %u\n", r, c); exit(4); }
+            kr_seqset_free(fk); kr_seqset_free(g);
+        }
+        {   // a residue outside the alphabet: the call fails, the context goes on
+            Batch bad = families(53, 40, 3, 60, false);
+            bad.res[bad.off[17] + 3] = '#';
+            kr_seqset *x = nullptr;
+            if (kr_encode(ctx, bad.res.data(), bad.off.data(), bad.n(), &x) != KR_ERR_ALPHABET) { fprintf(stderr, "race_check: the bad residue went through\n"); exit(4); }
+            std::vector<int32_t> again = full_matrix(ctx, sa, sb, a.n(), b.n());
+            if (again != ref_rect) { fprintf(stderr, "race_check: the context is off after an alphabet error\n"); exit(4); }
+        }
+        kr_seqset_free(sa); kr_seqset_free(sb);
+        kr_destroy(ctx);
+    }
+}
+
 // What bench.py does: device-resident inputs and outputs through the _device entry points (no host synchronisation inside
 // the step: encode -> matrix -> free the previous set, stream-ordered), then the e2e step with PINNED host buffers, whose
 // copies are truly asynchronous -- the library has to synchronise before it returns, or the host reads below are races.
@@ -396,6 +466,7 @@ int main(int argc, char **argv) {
     run("shards", [] { case_shards(); });
     run("multi", [] { case_multi(); });
     run("bench_like", [] { case_bench_like(); });
+    run("misc", [] { case_misc(); });
     // controls run only when named (each of the first three MUST be reported)
     if (want.count("ctl_syncthreads")) case_control(0);
     if (want.count("ctl_syncwarp")) case_control(1);

@@ -39,7 +39,7 @@ KR_EMUL_RACE=grid $W ctl_clean > $B/race_grid_ctl1.log 2>&1 || { echo "emul_race
 echo "emul_race: controls OK (seeded bugs reported at both granularities, ordered twins silent)"
 rc=0
 summary() { grep -A4 "WARNING: ThreadSanitizer" $1 | grep "#0" | sort | uniq -c | sort -rn | head -12 | cut -c1-200; }
-CASES="matrix_k8 matrix_k10 matrix_k3 db_k8 shards multi bench_like"
+CASES="matrix_k8 matrix_k10 matrix_k3 db_k8 shards multi bench_like misc"
 for c in $CASES; do
     $B/race_check $c > $B/race_$c.log 2>&1; r=$?
     echo "emul_race: $c (thread identities: inside a CTA) exit $r, $(grep -c 'WARNING: ThreadSanitizer' $B/race_$c.log) report(s)"
