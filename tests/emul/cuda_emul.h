@@ -80,12 +80,6 @@ struct Quiet {
 };
 inline void hb_release(void *a) { __tsan_release(a); }
 inline void hb_acquire(void *a) { __tsan_acquire(a); }
-inline void *tsan_fiber(unsigned t) {      // one ThreadSanitizer fiber per CUDA thread index, kept for the life of the process
-    static std::vector<void *> pool;
-    if (pool.size() <= t) pool.resize(t + 1, nullptr);
-    if (!pool[t]) pool[t] = __tsan_create_fiber(0);
-    return pool[t];
-}
 inline void *&tsan_main() { static void *m = nullptr; return m; }
 // Who a CUDA thread is to the detector.  ThreadSanitizer multiplexes 256 thread slots and loses history when more threads
 // than that are alive, so there are two granularities: a thread of its own (default: what finds a missing __syncwarp; the
